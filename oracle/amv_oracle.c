@@ -1,0 +1,708 @@
+/*
+ * amv_oracle.c -- CPU restatement of the AMV intra-frame codec path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (amv-codec-tools_b200/,
+ * libamvcuda) includes, links or calls this file.  It exists so that tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg have a bit-exact,
+ * single-threaded, scalar statement of what the reference computes.
+ *
+ * PARITY PINNED: tests/test_oracle_vs_ref.py checks every function below
+ * against the unmodified reference compiled in place (oracle/build_ref.sh ->
+ * oracle/_ref/libamvref.so) and against the in-tree fixture
+ * C-AMVDecoder/bin/AMV1.amv; tests/golden/ holds vectors produced by that
+ * reference build so the pin also holds where /root/reference is absent.
+ *
+ * Every function cites the reference lines it restates
+ * (paths relative to AMVmuxer/ffmpeg/libavcodec/).  The code is written from
+ * the arithmetic, not transcribed: loops, table layouts and bit I/O are ours.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define AMVO_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ tables */
+
+/* Decoder quantiser: the two fixed tables the reference wraps every AMV packet
+ * with (sp5xdec.c:40,60-61 -> sp5x.h "index 5, Q60", rows 10 and 11), listed
+ * in the order they appear in a DQT segment, i.e. zigzag order. */
+static const uint8_t kDecQuantZZ[2][64] = {
+  { 13,  9, 10, 11, 10,  8, 13, 11, 10, 11, 14, 14, 13, 15, 19, 32,
+    21, 19, 18, 18, 19, 39, 28, 30, 23, 32, 46, 41, 49, 48, 46, 41,
+    45, 44, 51, 58, 74, 62, 51, 54, 70, 55, 44, 45, 64, 87, 65, 70,
+    76, 78, 82, 83, 82, 50, 62, 90, 97, 90, 80, 96, 74, 81, 82, 79 },
+  { 14, 14, 14, 19, 17, 19, 38, 21, 21, 38, 79, 53, 45, 53, 79, 79,
+    79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79,
+    79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79,
+    79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79 },
+};
+
+/* Encoder quantiser base: MPEG-1 default intra matrix, raster order
+ * (mpeg12data.c:30-39; used by mpegvideo_enc.c:2866-2873). */
+static const uint8_t kEncBase[64] = {
+   8, 16, 19, 22, 26, 27, 29, 34,  16, 16, 22, 24, 27, 29, 34, 37,
+  19, 22, 26, 27, 29, 34, 34, 38,  22, 22, 26, 27, 29, 34, 37, 40,
+  22, 26, 27, 29, 32, 35, 40, 48,  26, 27, 29, 32, 35, 40, 48, 58,
+  26, 27, 29, 34, 38, 46, 56, 69,  27, 29, 35, 38, 46, 56, 69, 83,
+};
+
+/* JPEG Annex K.3 Huffman specifications: count of codes per length 1..16,
+ * then the symbols in code order (mjpeg.c:65-126; the same bytes sit in the
+ * DHT template sp5x.h:76-132 the decoder parses). */
+static const uint8_t kCnt[4][16] = {
+  /* DC luma   */ { 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0 },
+  /* DC chroma */ { 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0 },
+  /* AC luma   */ { 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d },
+  /* AC chroma */ { 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77 },
+};
+static const uint8_t kSymDC[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
+static const uint8_t kSymACL[162] = {
+  0x01,0x02,0x03,0x00,0x04,0x11,0x05,0x12,0x21,0x31,0x41,0x06,0x13,0x51,0x61,0x07,
+  0x22,0x71,0x14,0x32,0x81,0x91,0xa1,0x08,0x23,0x42,0xb1,0xc1,0x15,0x52,0xd1,0xf0,
+  0x24,0x33,0x62,0x72,0x82,0x09,0x0a,0x16,0x17,0x18,0x19,0x1a,0x25,0x26,0x27,0x28,
+  0x29,0x2a,0x34,0x35,0x36,0x37,0x38,0x39,0x3a,0x43,0x44,0x45,0x46,0x47,0x48,0x49,
+  0x4a,0x53,0x54,0x55,0x56,0x57,0x58,0x59,0x5a,0x63,0x64,0x65,0x66,0x67,0x68,0x69,
+  0x6a,0x73,0x74,0x75,0x76,0x77,0x78,0x79,0x7a,0x83,0x84,0x85,0x86,0x87,0x88,0x89,
+  0x8a,0x92,0x93,0x94,0x95,0x96,0x97,0x98,0x99,0x9a,0xa2,0xa3,0xa4,0xa5,0xa6,0xa7,
+  0xa8,0xa9,0xaa,0xb2,0xb3,0xb4,0xb5,0xb6,0xb7,0xb8,0xb9,0xba,0xc2,0xc3,0xc4,0xc5,
+  0xc6,0xc7,0xc8,0xc9,0xca,0xd2,0xd3,0xd4,0xd5,0xd6,0xd7,0xd8,0xd9,0xda,0xe1,0xe2,
+  0xe3,0xe4,0xe5,0xe6,0xe7,0xe8,0xe9,0xea,0xf1,0xf2,0xf3,0xf4,0xf5,0xf6,0xf7,0xf8,
+  0xf9,0xfa };
+static const uint8_t kSymACC[162] = {
+  0x00,0x01,0x02,0x03,0x11,0x04,0x05,0x21,0x31,0x06,0x12,0x41,0x51,0x07,0x61,0x71,
+  0x13,0x22,0x32,0x81,0x08,0x14,0x42,0x91,0xa1,0xb1,0xc1,0x09,0x23,0x33,0x52,0xf0,
+  0x15,0x62,0x72,0xd1,0x0a,0x16,0x24,0x34,0xe1,0x25,0xf1,0x17,0x18,0x19,0x1a,0x26,
+  0x27,0x28,0x29,0x2a,0x35,0x36,0x37,0x38,0x39,0x3a,0x43,0x44,0x45,0x46,0x47,0x48,
+  0x49,0x4a,0x53,0x54,0x55,0x56,0x57,0x58,0x59,0x5a,0x63,0x64,0x65,0x66,0x67,0x68,
+  0x69,0x6a,0x73,0x74,0x75,0x76,0x77,0x78,0x79,0x7a,0x82,0x83,0x84,0x85,0x86,0x87,
+  0x88,0x89,0x8a,0x92,0x93,0x94,0x95,0x96,0x97,0x98,0x99,0x9a,0xa2,0xa3,0xa4,0xa5,
+  0xa6,0xa7,0xa8,0xa9,0xaa,0xb2,0xb3,0xb4,0xb5,0xb6,0xb7,0xb8,0xb9,0xba,0xc2,0xc3,
+  0xc4,0xc5,0xc6,0xc7,0xc8,0xc9,0xca,0xd2,0xd3,0xd4,0xd5,0xd6,0xd7,0xd8,0xd9,0xda,
+  0xe2,0xe3,0xe4,0xe5,0xe6,0xe7,0xe8,0xe9,0xea,0xf2,0xf3,0xf4,0xf5,0xf6,0xf7,0xf8,
+  0xf9,0xfa };
+
+/* IMA ADPCM tables (adpcm.c:56-75). */
+static const int16_t kImaStep[89] = {
+      7,     8,     9,    10,    11,    12,    13,    14,    16,    17,
+     19,    21,    23,    25,    28,    31,    34,    37,    41,    45,
+     50,    55,    60,    66,    73,    80,    88,    97,   107,   118,
+    130,   143,   157,   173,   190,   209,   230,   253,   279,   307,
+    337,   371,   408,   449,   494,   544,   598,   658,   724,   796,
+    876,   963,  1060,  1166,  1282,  1411,  1552,  1707,  1878,  2066,
+   2272,  2499,  2749,  3024,  3327,  3660,  4026,  4428,  4871,  5358,
+   5894,  6484,  7132,  7845,  8630,  9493, 10442, 11487, 12635, 13899,
+  15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767 };
+static const int8_t kImaIdxAdj[8] = { -1, -1, -1, -1, 2, 4, 6, 8 };
+
+/* derived tables, filled once */
+static uint8_t  g_zz[64];            /* zigzag scan position -> raster index (dsputil.c:50-59) */
+static uint8_t  g_hlen[4][256];      /* code length per symbol (mjpeg.c:129-147) */
+static uint16_t g_hcode[4][256];     /* right-aligned code per symbol */
+static int g_ready;
+
+static void build_tables(void)
+{
+    if (g_ready) return;
+    /* zigzag: walk the anti-diagonals of the 8x8 grid, alternating direction */
+    int n = 0;
+    for (int d = 0; d < 15; d++) {
+        for (int t = 0; t <= d; t++) {
+            int r = (d & 1) ? t : d - t, c = d - r;
+            if (r < 8 && c < 8) g_zz[n++] = (uint8_t)(r * 8 + c);
+        }
+    }
+    /* canonical Huffman codes: consecutive integers within a length, doubled
+     * when the length grows (mjpeg.c:129-147) */
+    for (int t = 0; t < 4; t++) {
+        const uint8_t *sym = t < 2 ? kSymDC : (t == 2 ? kSymACL : kSymACC);
+        unsigned next = 0; int k = 0;
+        memset(g_hlen[t], 0, 256);
+        for (int len = 1; len <= 16; len++) {
+            for (int j = 0; j < kCnt[t][len - 1]; j++, k++) {
+                g_hlen[t][sym[k]] = (uint8_t)len;
+                g_hcode[t][sym[k]] = (uint16_t)next++;
+            }
+            next <<= 1;
+        }
+    }
+    g_ready = 1;
+}
+
+AMVO_API void amvo_get_zigzag(uint8_t out[64]) { build_tables(); memcpy(out, g_zz, 64); }
+AMVO_API void amvo_get_huff(int table, uint8_t len[256], uint16_t code[256])
+{
+    build_tables(); memcpy(len, g_hlen[table], 256); memcpy(code, g_hcode[table], 512);
+}
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* ------------------------------------------------- inverse transform (dec) */
+
+/* simple_idct_put (simple_idct.c:390-398): rows in place on int16 with the
+ * DC-only shortcut (:93-127), then columns with clamp-and-store (:183-253).
+ * W4 is 16383 (:50); sums are 32-bit two's complement.  We keep the sums in
+ * uint32_t so wrap-around is defined, and convert at the shifts. */
+enum { W1 = 22725, W2 = 21407, W3 = 19266, W4 = 16383, W5 = 12873, W6 = 8867, W7 = 4520 };
+
+static inline int32_t asr32(uint32_t v, int s) { return (int32_t)v >> s; }
+
+static void idct_row(int16_t *r)
+{
+    if (!(r[1] | r[2] | r[3] | r[4] | r[5] | r[6] | r[7])) {
+        /* (row[0] << 3) & 0xffff replicated (:98-103) */
+        int16_t dc = (int16_t)(uint16_t)((uint32_t)(int32_t)r[0] << 3);
+        for (int i = 0; i < 8; i++) r[i] = dc;
+        return;
+    }
+    uint32_t e0 = (uint32_t)(W4 * r[0]) + (1u << 10);
+    uint32_t e[4] = { e0 + (uint32_t)(W2 * r[2]), e0 + (uint32_t)(W6 * r[2]),
+                      e0 - (uint32_t)(W6 * r[2]), e0 - (uint32_t)(W2 * r[2]) };
+    uint32_t o[4] = { (uint32_t)(W1 * r[1]) + (uint32_t)(W3 * r[3]),
+                      (uint32_t)(W3 * r[1]) - (uint32_t)(W7 * r[3]),
+                      (uint32_t)(W5 * r[1]) - (uint32_t)(W1 * r[3]),
+                      (uint32_t)(W7 * r[1]) - (uint32_t)(W5 * r[3]) };
+    /* rows 4..7 contribute nothing when zero, so the :147 test is only a speed-up */
+    e[0] += (uint32_t)(W4 * r[4]) + (uint32_t)(W6 * r[6]);
+    e[1] -= (uint32_t)(W4 * r[4]) + (uint32_t)(W2 * r[6]);
+    e[2] += (uint32_t)(W2 * r[6]) - (uint32_t)(W4 * r[4]);
+    e[3] += (uint32_t)(W4 * r[4]) - (uint32_t)(W6 * r[6]);
+    o[0] += (uint32_t)(W5 * r[5]) + (uint32_t)(W7 * r[7]);
+    o[1] -= (uint32_t)(W1 * r[5]) + (uint32_t)(W5 * r[7]);
+    o[2] += (uint32_t)(W7 * r[5]) + (uint32_t)(W3 * r[7]);
+    o[3] += (uint32_t)(W3 * r[5]) - (uint32_t)(W1 * r[7]);
+    for (int i = 0; i < 4; i++) {
+        r[i]     = (int16_t)asr32(e[i] + o[i], 11);
+        r[7 - i] = (int16_t)asr32(e[i] - o[i], 11);
+    }
+}
+
+static void idct_col_put(uint8_t *dst, int ls, const int16_t *c, uint8_t *undef)
+{
+    /* a0 = W4 * (col[0] + 32)  (:190; (1<<19)/W4 == 32) */
+    uint32_t e0 = (uint32_t)(W4 * (c[0] + 32));
+    uint32_t e[4] = { e0 + (uint32_t)(W2 * c[16]), e0 + (uint32_t)(W6 * c[16]),
+                      e0 - (uint32_t)(W6 * c[16]), e0 - (uint32_t)(W2 * c[16]) };
+    uint32_t o[4] = { (uint32_t)(W1 * c[8]) + (uint32_t)(W3 * c[24]),
+                      (uint32_t)(W3 * c[8]) - (uint32_t)(W7 * c[24]),
+                      (uint32_t)(W5 * c[8]) - (uint32_t)(W1 * c[24]),
+                      (uint32_t)(W7 * c[8]) - (uint32_t)(W5 * c[24]) };
+    e[0] += (uint32_t)(W4 * c[32]) + (uint32_t)(W6 * c[48]);
+    e[1] -= (uint32_t)(W4 * c[32]) + (uint32_t)(W2 * c[48]);
+    e[2] += (uint32_t)(W2 * c[48]) - (uint32_t)(W4 * c[32]);
+    e[3] += (uint32_t)(W4 * c[32]) - (uint32_t)(W6 * c[48]);
+    o[0] += (uint32_t)(W5 * c[40]) + (uint32_t)(W7 * c[56]);
+    o[1] -= (uint32_t)(W1 * c[40]) + (uint32_t)(W5 * c[56]);
+    o[2] += (uint32_t)(W7 * c[40]) + (uint32_t)(W3 * c[56]);
+    o[3] += (uint32_t)(W3 * c[40]) - (uint32_t)(W1 * c[56]);
+    for (int i = 0; i < 4; i++) {
+        /* ff_cropTbl (dsputil.c:3812-3820) is a clamp to 0..255 over its domain;
+         * outside it the reference is undefined, we clamp */
+        int hi = asr32(e[i] + o[i], 20), lo = asr32(e[i] - o[i], 20);
+        dst[i * ls]       = (uint8_t)clampi(hi, 0, 255);
+        dst[(7 - i) * ls] = (uint8_t)clampi(lo, 0, 255);
+        if (undef) {   /* index outside ff_cropTbl's -1024..1279: the reference reads foreign memory */
+            undef[i * ls]       = hi < -1024 || hi > 1279;
+            undef[(7 - i) * ls] = lo < -1024 || lo > 1279;
+        }
+    }
+}
+
+/* out[64]: the 8x8 pixels, row-major */
+AMVO_API void amvo_idct_put_ex(const int16_t in[64], uint8_t out[64], uint8_t *undef /* 64 or NULL */)
+{
+    int16_t b[64];
+    memcpy(b, in, sizeof(b));
+    for (int r = 0; r < 8; r++) idct_row(b + 8 * r);
+    for (int c = 0; c < 8; c++) idct_col_put(out + c, 8, b + c, undef ? undef + c : NULL);
+}
+AMVO_API void amvo_idct_put(const int16_t in[64], uint8_t out[64]) { amvo_idct_put_ex(in, out, NULL); }
+
+/* -------------------------------------------------- forward transform (enc) */
+
+/* ff_jpeg_fdct_islow (jfdctint.c:184-341): LL&M 1-D DCT, CONST_BITS 13,
+ * PASS1_BITS 4 (:127-128); rows first (outputs kept <<4, stored as int16),
+ * then columns (descaled by 4 resp. 13+4). */
+/* the reference's temporaries are int_fast32_t, i.e. 64-bit on the x86-64 build
+ * it is pinned against; for 8-bit pixel input nothing exceeds 32 bits anyway
+ * (8 + CONST_BITS + PASS1_BITS = 25 <= 26, jfdctint.c:120-124) */
+typedef int64_t fdct_t;
+static inline fdct_t descale(fdct_t v, int n) { return (v + ((fdct_t)1 << (n - 1))) >> n; }
+
+static void fdct_1d(const fdct_t s[8], fdct_t out[8], int sh_even, int sh_odd, int row_pass)
+{
+    enum { C0_298 = 2446, C0_390 = 3196, C0_541 = 4433, C0_765 = 6270, C0_899 = 7373,
+           C1_175 = 9633, C1_501 = 12299, C1_847 = 15137, C1_961 = 16069,
+           C2_053 = 16819, C2_562 = 20995, C3_072 = 25172 };
+    fdct_t p0 = s[0] + s[7], m0 = s[0] - s[7];
+    fdct_t p1 = s[1] + s[6], m1 = s[1] - s[6];
+    fdct_t p2 = s[2] + s[5], m2 = s[2] - s[5];
+    fdct_t p3 = s[3] + s[4], m3 = s[3] - s[4];
+    /* even half */
+    fdct_t q0 = p0 + p3, q3 = p0 - p3, q1 = p1 + p2, q2 = p1 - p2;
+    if (row_pass) { out[0] = (q0 + q1) * (1 << sh_even); out[4] = (q0 - q1) * (1 << sh_even); }
+    else          { out[0] = descale(q0 + q1, sh_even); out[4] = descale(q0 - q1, sh_even); }
+    fdct_t r = (q2 + q3) * C0_541;
+    out[2] = descale(r + q3 * C0_765, sh_odd);
+    out[6] = descale(r - q2 * C1_847, sh_odd);
+    /* odd half: m3,m2,m1,m0 are the paper's i0..i3 */
+    fdct_t a = m3 + m0, b = m2 + m1, c = m3 + m1, d = m2 + m0;
+    fdct_t z = (c + d) * C1_175;
+    fdct_t t3 = m3 * C0_298, t2 = m2 * C2_053, t1 = m1 * C3_072, t0 = m0 * C1_501;
+    a *= -C0_899; b *= -C2_562;
+    c = c * -C1_961 + z;
+    d = d * -C0_390 + z;
+    out[7] = descale(t3 + a + c, sh_odd);
+    out[5] = descale(t2 + b + d, sh_odd);
+    out[3] = descale(t1 + b + c, sh_odd);
+    out[1] = descale(t0 + a + d, sh_odd);
+}
+
+AMVO_API void amvo_fdct_islow(int16_t blk[64])
+{
+    fdct_t in[8], out[8];
+    for (int r = 0; r < 8; r++) {
+        for (int i = 0; i < 8; i++) in[i] = blk[8 * r + i];
+        fdct_1d(in, out, 4, 13 - 4, 1);
+        for (int i = 0; i < 8; i++) blk[8 * r + i] = (int16_t)out[i];
+    }
+    for (int c = 0; c < 8; c++) {
+        for (int i = 0; i < 8; i++) in[i] = blk[8 * i + c];
+        fdct_1d(in, out, 4, 13 + 4, 0);
+        for (int i = 0; i < 8; i++) blk[8 * i + c] = (int16_t)out[i];
+    }
+}
+
+/* ---------------------------------------------------------------- quantiser */
+
+/* qscale from AVFrame.quality / lambda (mpegvideo_enc.c:143-148, qmin 2 qmax 31
+ * utils.c:497-498) */
+AMVO_API int amvo_qscale_from_lambda(int lambda, int qmin, int qmax)
+{
+    return clampi((lambda * 139 + 128 * 64) >> 14, qmin, qmax);
+}
+
+/* Per-frame matrix: M[0]=8, M[i]=clip_u8(base[i]*qscale>>3); multiplier
+ * (1<<22)/(8*M[i]) (mpegvideo_enc.c:2866-2877, ff_convert_matrix :69-91). */
+AMVO_API void amvo_enc_qmat(int qscale, int32_t qmat[64])
+{
+    for (int i = 0; i < 64; i++) {
+        int m = i ? clampi((kEncBase[i] * qscale) >> 3, 0, 255) : kEncBase[0];
+        qmat[i] = (int32_t)((1u << 22) / (unsigned)(8 * (m ? m : 1)));
+        if (!m) qmat[i] = 0; /* unreachable for qscale >= 2 */
+    }
+}
+
+/* dct_quantize_c intra path (mpegvideo_enc.c:3647-3725) after the FDCT:
+ * DC (b+32)/64 ; AC sign * (|b*qmat| >> 22) (bias 0 :492-496) ; returns the last
+ * zigzag position holding a non-zero AC (0 if none); AC clipped to +-1023
+ * (clip_coeffs :1403-1432 with mjpegenc.c:55-56). */
+AMVO_API int amvo_quantize(int16_t blk[64], const int32_t qmat[64])
+{
+    build_tables();
+    int last = 0;
+    blk[0] = (int16_t)((blk[0] + 32) / 64);
+    for (int k = 1; k < 64; k++) {
+        int j = g_zz[k];
+        int32_t lv = (int32_t)((uint32_t)(int32_t)blk[j] * (uint32_t)qmat[j]);
+        int q = 0;
+        if (lv >= (1 << 22))        q =  (lv >> 22);
+        else if (lv <= -(1 << 22))  q = -(int)((uint32_t)(-(int64_t)lv) >> 22);
+        q = clampi(q, -1023, 1023);
+        blk[j] = (int16_t)q;
+        if (q) last = k;
+    }
+    return last;
+}
+
+/* ---------------------------------------------------------- MSB-first writer */
+
+typedef struct { uint8_t *p; size_t cap, nbytes; uint32_t acc; int nacc; int overflow; } bitw;
+
+static void bw_put(bitw *w, int n, uint32_t v)       /* n <= 24 (bitstream.h:213-250 semantics) */
+{
+    w->acc = (w->acc << n) | (v & ((1u << n) - 1));
+    w->nacc += n;
+    while (w->nacc >= 8) {
+        uint8_t b = (uint8_t)(w->acc >> (w->nacc - 8));
+        if (w->nbytes < w->cap) w->p[w->nbytes] = b; else w->overflow = 1;
+        w->nbytes++;
+        w->nacc -= 8;
+    }
+}
+
+static int bit_width(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
+
+/* magnitude category + low bits (ff_mjpeg_encode_dc mjpegenc.c:357-377 and the
+ * AC branch :413-426): negative values send (v-1) masked to the category. */
+static void put_coef(bitw *w, int tbl, int run, int v)
+{
+    int mag = v < 0 ? -v : v;
+    int nb = bit_width((unsigned)mag);
+    int sym = (run << 4) | nb;
+    bw_put(w, g_hlen[tbl][sym], g_hcode[tbl][sym]);
+    if (nb) bw_put(w, nb, (uint32_t)(v < 0 ? v - 1 : v));
+}
+
+/* ------------------------------------------------------------------ encoder */
+
+/* Row the reference starts reading a plane from before walking upwards
+ * (mjpegenc.c:467-470): vs*(8*mb_h - ((h/2)&7)) - 1, vs = 2 luma / 1 chroma. */
+static int flip_start_row(int h, int vs)
+{
+    int mb_h = (h + 15) / 16;
+    return vs * (8 * mb_h - ((h / 2) & 7)) - 1;
+}
+
+/* Encode one frame into out[0..cap). Returns packet size, or
+ *  -1 unsupported geometry (reference would read outside the picture),
+ *  -2 packet does not fit.
+ * amv_encode_picture (mjpegenc.c:454-472) -> MPV_encode_picture
+ * (mpegvideo_enc.c:1205-1352) -> encode_thread (:2004-2631) ->
+ * encode_mb_internal (:1457-1750) -> ff_mjpeg_encode_mb (mjpegenc.c:437-450)
+ * -> trailer (mjpegenc.c:345-355). */
+AMVO_API int amvo_encode_frame(const uint8_t *py, const uint8_t *pu, const uint8_t *pv,
+                               int ls_y, int ls_c, int w, int h, int qscale,
+                               uint8_t *out, uint32_t cap)
+{
+    build_tables();
+    if (w < 2 || h < 2 || qscale < 1 || qscale > 31) return -1;
+    const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
+    const int cw = w >> 1, chh = h >> 1;                      /* chroma extent the reference copies (:866-867) */
+    const int y0 = flip_start_row(h, 2), c0 = flip_start_row(h, 1);
+    if (y0 != h - 1 || c0 > ((h + 1) >> 1) - 1 || c0 - (chh - 1) < 0) return -1;
+
+    int32_t qmat[64];
+    amvo_enc_qmat(qscale, qmat);
+
+    /* entropy-coded segment is produced un-stuffed first, stuffing afterwards
+     * (escape_FF mjpegenc.c:282-336 runs once over the finished frame) */
+    size_t rawcap = (size_t)mbw * mbh * 6 * 256 + 64;
+    uint8_t *raw = (uint8_t *)malloc(rawcap);
+    bitw bw = { raw, rawcap, 0, 0, 0, 0 };
+    int pred[3] = { 128, 128, 128 };                           /* mpegvideo_enc.c:2033-2036 */
+
+    for (int my = 0; my < mbh; my++)
+    for (int mx = 0; mx < mbw; mx++)
+    for (int b = 0; b < 6; b++) {
+        int16_t blk[64];
+        const int comp = b < 4 ? 0 : b - 3;
+        const uint8_t *pl = comp == 0 ? py : (comp == 1 ? pu : pv);
+        const int ls = comp ? ls_c : ls_y;
+        const int vw = comp ? cw : w, vh = comp ? chh : h, r0 = comp ? c0 : y0;
+        const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
+        const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+        /* get_pixels (dsputil.c:399-416) on the flipped, edge-replicated picture
+         * (load_input_picture :857-879 + ff_emulated_edge_mc mpegvideo.c:1416-1470) */
+        for (int yy = 0; yy < 8; yy++)
+            for (int xx = 0; xx < 8; xx++) {
+                int X = bx + xx, Y = by + yy;
+                if (X > vw - 1) X = vw - 1;
+                if (Y > vh - 1) Y = vh - 1;
+                blk[yy * 8 + xx] = pl[(ptrdiff_t)(r0 - Y) * ls + X];
+            }
+        amvo_fdct_islow(blk);
+        int last = amvo_quantize(blk, qmat);
+        /* encode_block (mjpegenc.c:379-435) */
+        int diff = blk[0] - pred[comp];
+        pred[comp] = blk[0];
+        put_coef(&bw, comp ? 1 : 0, 0, diff);
+        const int ac = comp ? 3 : 2;
+        int run = 0;
+        for (int k = 1; k <= last; k++) {
+            int v = blk[g_zz[k]];
+            if (!v) { run++; continue; }
+            for (; run >= 16; run -= 16) bw_put(&bw, g_hlen[ac][0xf0], g_hcode[ac][0xf0]);
+            put_coef(&bw, ac, run, v);
+            run = 0;
+        }
+        if (last < 63) bw_put(&bw, g_hlen[ac][0], g_hcode[ac][0]);
+    }
+    /* pad to a byte with ones (ff_mjpeg_encode_stuffing mjpegenc.c:338-343) */
+    if (bw.nacc) bw_put(&bw, 8 - bw.nacc, 0xff);
+
+    /* SOI, stuffed segment, EOI */
+    size_t o = 0; int fits = 1;
+#define EMIT(b) do { if (o < cap) out[o] = (uint8_t)(b); else fits = 0; o++; } while (0)
+    EMIT(0xff); EMIT(0xd8);
+    for (size_t i = 0; i < bw.nbytes; i++) { EMIT(raw[i]); if (raw[i] == 0xff) EMIT(0x00); }
+    EMIT(0xff); EMIT(0xd9);
+#undef EMIT
+    free(raw);
+    return fits ? (int)o : -2;
+}
+
+/* ------------------------------------------------------------------ decoder */
+
+typedef struct { const uint8_t *p; size_t n, pos; uint64_t acc; int nacc; int overrun; } bitr;
+
+static inline void br_fill(bitr *r)
+{
+    while (r->nacc <= 56) {
+        uint64_t b = 0;
+        if (r->pos < r->n) b = r->p[r->pos]; else if (r->pos >= r->n + 8) r->overrun = 1;
+        r->pos++;
+        r->acc |= b << (56 - r->nacc);
+        r->nacc += 8;
+    }
+}
+static inline uint32_t br_peek(bitr *r, int n) { br_fill(r); return n ? (uint32_t)(r->acc >> (64 - n)) : 0; }
+static inline void br_skip(bitr *r, int n) { r->acc <<= n; r->nacc -= n; }
+static inline size_t br_bits_used(const bitr *r) { return r->pos * 8 - (size_t)r->nacc; }
+
+/* canonical decode: find the shortest length whose code range contains the
+ * next bits (what the 9-bit two-level VLC of bitstream.h:813-839 resolves to) */
+static int huff_get(bitr *r, int t)
+{
+    uint32_t v = br_peek(r, 16);
+    unsigned first = 0; int k = 0;
+    const uint8_t *sym = t < 2 ? kSymDC : (t == 2 ? kSymACL : kSymACC);
+    for (int len = 1; len <= 16; len++) {
+        unsigned c = v >> (16 - len);
+        int cnt = kCnt[t][len - 1];
+        if (c >= first && c < first + cnt) { br_skip(r, len); return sym[k + (c - first)]; }
+        k += cnt;
+        first = (first + cnt) << 1;
+    }
+    return -1;
+}
+
+/* get_xbits (bitstream.h:629-639): n-bit two's-complement-ish JPEG extend */
+static int get_extend(bitr *r, int n)
+{
+    if (!n) return 0;
+    int v = (int)br_peek(r, n);
+    br_skip(r, n);
+    return (v >> (n - 1)) ? v : v - ((1 << n) - 1);
+}
+
+/* status bits returned by amvo_decode_frame */
+enum { AMVO_E_SHORT = 1, AMVO_E_BADCODE = 2, AMVO_E_COEFIDX = 4, AMVO_E_MARKER = 8, AMVO_E_OVERRUN = 16 };
+
+/* Remove byte stuffing exactly like the SOS branch of ff_mjpeg_decode_frame
+ * (mjpegdec.c:1137-1160) does on `payload ++ FF D9` (sp5xdec.c:75-88):
+ * FF followed by 00 -> FF; FF D0..D7 kept; runs of FF collapse; FF + any other
+ * non-zero byte ends the scan data. Returns unstuffed length. */
+AMVO_API size_t amvo_unstuff(const uint8_t *pkt, uint32_t size, uint8_t *dst, int *flags)
+{
+    size_t n = 0, i = 2, end = size >= 4 ? size - 2 : 2;   /* payload = pkt[2 .. size-2) */
+    int stop = 0;
+    if (size < 4) { if (flags) *flags |= AMVO_E_SHORT; }
+    while (i < end && !stop) {
+        uint8_t x = pkt[i++];
+        dst[n++] = x;
+        if (x != 0xff) continue;
+        uint8_t z = 0xff;
+        while (i < end && z == 0xff) z = pkt[i++];
+        if (z == 0xff) { z = 0xd9; }                       /* ran into the appended EOI */
+        if (z >= 0xd0 && z <= 0xd7) dst[n++] = z;
+        else if (z) { stop = 1; if (z != 0xd9 && flags) *flags |= AMVO_E_MARKER; }
+    }
+    if (!stop) dst[n++] = 0xff;                            /* the FF of the appended EOI is copied too */
+    else if (i < end && flags) *flags |= AMVO_E_MARKER;     /* scan cut short by a marker inside the payload */
+    return n;
+}
+
+/* Decode one packet into three planes (strides in bytes).  Returns 0 or a mask
+ * of AMVO_E_*; on error the picture content is unspecified.
+ * sp5x_decode_frame (sp5xdec.c:33-93) -> ff_mjpeg_decode_frame
+ * (mjpegdec.c:1106-1340) -> mjpeg_decode_scan (:660-736) -> decode_block
+ * (:376-430) -> simple_idct_put. */
+AMVO_API int amvo_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int h,
+                                  uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
+                                  int16_t *coef_dump /* optional: 64*6*mbw*mbh dequantised coefs */,
+                                  uint8_t *uy, uint8_t *uu, uint8_t *uv /* optional: 1 where the reference is undefined */)
+{
+    build_tables();
+    int flags = 0;
+    const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
+    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    int16_t q[2][64];                                       /* raster order (mjpegdec.c:131-134) */
+    for (int t = 0; t < 2; t++) for (int k = 0; k < 64; k++) q[t][g_zz[k]] = kDecQuantZZ[t][k];
+
+    uint8_t *scan = (uint8_t *)malloc((size_t)size + 16);
+    size_t nscan = amvo_unstuff(pkt, size, scan, &flags);
+    bitr br = { scan, nscan, 0, 0, 0, 0 };
+    int pred[3] = { 1024, 1024, 1024 };                     /* mjpegdec.c:805-806 */
+    const int y0 = flip_start_row(h, 2), c0 = flip_start_row(h, 1);
+    int nblk = 0;
+
+    for (int my = 0; my < mbh && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); my++)
+    for (int mx = 0; mx < mbw && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); mx++)
+    for (int b = 0; b < 6; b++, nblk++) {
+        const int comp = b < 4 ? 0 : b - 3, tq = comp ? 1 : 0;
+        int16_t blk[64] = { 0 };
+        int s = huff_get(&br, tq);
+        if (s < 0) { flags |= AMVO_E_BADCODE; break; }
+        pred[comp] += get_extend(&br, s) * q[tq][0];
+        blk[0] = (int16_t)pred[comp];
+        for (int k = 0;;) {
+            int rs = huff_get(&br, 2 + tq);
+            if (rs < 0) { flags |= AMVO_E_BADCODE; break; }
+            if (rs == 0x00) break;                           /* EOB */
+            if (rs == 0xf0) { k += 16; continue; }           /* ZRL: no range check (:400-401) */
+            k += (rs >> 4) + 1;
+            int lv = get_extend(&br, rs & 15);
+            if (k > 63) { flags |= AMVO_E_COEFIDX; break; }
+            blk[g_zz[k]] = (int16_t)(lv * q[tq][g_zz[k]]);
+            if (k == 63) break;
+        }
+        if (flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)) break;
+        if (coef_dump) memcpy(coef_dump + (size_t)nblk * 64, blk, sizeof(blk));
+
+        uint8_t px[64], ud[64];
+        amvo_idct_put_ex(blk, px, ud);
+        /* bottom-up placement (mjpegdec.c:672-677,710-716), clipped to the picture */
+        uint8_t *pl = comp == 0 ? py : (comp == 1 ? pu : pv);
+        uint8_t *um = comp == 0 ? uy : (comp == 1 ? uu : uv);
+        const int ls = comp ? ls_c : ls_y, vw = comp ? cw : w, vh = comp ? chh : h;
+        const int r0 = comp ? c0 : y0;
+        const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
+        const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+        for (int yy = 0; yy < 8; yy++) {
+            int row = r0 - (by + yy);
+            if (row < 0 || row >= vh) continue;
+            for (int xx = 0; xx < 8; xx++)
+                if (bx + xx < vw) {
+                    pl[(ptrdiff_t)row * ls + bx + xx] = px[yy * 8 + xx];
+                    if (um) um[(ptrdiff_t)row * ls + bx + xx] = ud[yy * 8 + xx];
+                }
+        }
+    }
+    if (br_bits_used(&br) > nscan * 8) flags |= AMVO_E_OVERRUN;
+    free(scan);
+    return flags;
+}
+
+AMVO_API int amvo_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,
+                               uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
+                               int16_t *coef_dump)
+{
+    return amvo_decode_frame_ex(pkt, size, w, h, py, pu, pv, ls_y, ls_c, coef_dump, NULL, NULL, NULL);
+}
+
+/* -------------------------------------------------------------------- ADPCM */
+
+/* adpcm_decode_frame, CODEC_ID_ADPCM_IMA_AMV (adpcm.c:1268-1292) with
+ * adpcm_ima_expand_nibble(...,3) (:716-742).  Returns samples written
+ * (2*(size-8)), or -1 if the chunk is shorter than its header / the header's
+ * step index is outside 0..88 (the reference indexes out of bounds there). */
+AMVO_API int amvo_adpcm_decode_chunk(const uint8_t *c, uint32_t size, int16_t *pcm)
+{
+    if (size < 8) return -1;
+    int pred = (int16_t)(c[0] | (c[1] << 8));
+    int idx = (int16_t)(c[2] | (c[3] << 8));
+    if (idx < 0 || idx > 88) return -1;
+    int n = 0;
+    for (uint32_t i = 8; i < size; i++)
+        for (int half = 0; half < 2; half++) {
+            int nib = half ? (c[i] & 15) : (c[i] >> 4);       /* high nibble first (:1281-1282) */
+            int step = kImaStep[idx];
+            idx = clampi(idx + kImaIdxAdj[nib & 7], 0, 88);
+            int diff = ((2 * (nib & 7) + 1) * step) >> 3;
+            pred = clampi(nib & 8 ? pred - diff : pred + diff, -32768, 32767);
+            pcm[n++] = (int16_t)pred;
+        }
+    return n;
+}
+
+/* adpcm_encode_frame, CODEC_ID_ADPCM_IMA_AMV (adpcm.c:461-496, non-trellis) for
+ * one chunk of `nsamples` (even) samples with the step index carried in.
+ * adpcm_ima_compress_sample (:219-227).  Returns bytes written (8+nsamples/2). */
+AMVO_API int amvo_adpcm_encode_chunk(const int16_t *pcm, uint32_t nsamples, int step_index_in,
+                                     uint8_t *out, int *step_index_out)
+{
+    if ((nsamples & 1) || step_index_in < 0 || step_index_in > 88) return -1;
+    int prev = nsamples ? pcm[0] : 0, idx = step_index_in;
+    if (!nsamples) prev = 0;
+    out[0] = (uint8_t)prev; out[1] = (uint8_t)(prev >> 8);
+    out[2] = (uint8_t)idx;  out[3] = (uint8_t)(idx >> 8);
+    out[4] = (uint8_t)nsamples; out[5] = (uint8_t)(nsamples >> 8);
+    out[6] = (uint8_t)(nsamples >> 16); out[7] = (uint8_t)(nsamples >> 24);
+    for (uint32_t i = 0; i < nsamples; i++) {
+        int step = kImaStep[idx];
+        int delta = pcm[i] - prev;
+        int mag = delta < 0 ? -delta : delta;
+        int q = mag * 4 / step;
+        if (q > 7) q = 7;
+        int nib = q + (delta < 0 ? 8 : 0);
+        int mv = (step * (2 * q + 1)) / 8;                    /* yamaha_difflookup (:124-127), C division */
+        prev = clampi(delta < 0 ? prev - mv : prev + mv, -32768, 32767);
+        idx = clampi(idx + kImaIdxAdj[q], 0, 88);
+        if (i & 1) out[8 + (i >> 1)] |= (uint8_t)nib;
+        else       out[8 + (i >> 1)]  = (uint8_t)(nib << 4);
+    }
+    if (step_index_out) *step_index_out = idx;
+    return 8 + (int)(nsamples >> 1);
+}
+
+/* How many samples (2n) the reference encoder puts in the next chunk
+ * (adpcm.c:468-477): host-side bookkeeping of the AVCodec shim. */
+AMVO_API uint32_t amvo_adpcm_next_chunk_samples(int frame_size, int sample_rate,
+                                                uint64_t samples_written, int *extra_carry)
+{
+    int n = frame_size >> 1;
+    *extra_carry += frame_size & 1;
+    n += *extra_carry >> 1;
+    *extra_carry &= 1;
+    int i = (int)((samples_written + 2 * (uint64_t)n) % (uint64_t)sample_rate);
+    if (i && i + frame_size > sample_rate) n += (sample_rate - i) >> 1;
+    return (uint32_t)n * 2;
+}
+
+/* ------------------------------------------------------------ batch drivers */
+
+AMVO_API int amvo_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                                int n, int w, int h, int qscale,
+                                uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
+{
+    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    uint64_t pos = 0;
+    for (int i = 0; i < n; i++) {
+        uint64_t room = cap - pos;
+        int sz = amvo_encode_frame(y + (size_t)i * w * h, u + (size_t)i * cw * chh, v + (size_t)i * cw * chh,
+                                   w, cw, w, h, qscale, out + pos, room > 0xffffffffu ? 0xffffffffu : (uint32_t)room);
+        if (sz < 0) return sz;
+        off[i] = pos; size[i] = (uint32_t)sz; pos += (uint32_t)sz;
+    }
+    return n;
+}
+
+AMVO_API int amvo_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                                int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int *status,
+                                uint8_t *uy, uint8_t *uu, uint8_t *uv)
+{
+    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    for (int i = 0; i < n; i++) {
+        size_t yo = (size_t)i * w * h, co = (size_t)i * cw * chh;
+        int st = amvo_decode_frame_ex(pkts + off[i], size[i], w, h, y + yo, u + co, v + co, w, cw, NULL,
+                                      uy ? uy + yo : NULL, uu ? uu + co : NULL, uv ? uv + co : NULL);
+        if (status) status[i] = st;
+    }
+    return n;
+}
+
+AMVO_API int amvo_adpcm_decode_chunks(const uint8_t *chunks, const uint64_t *off, const uint32_t *size,
+                                      int n, int16_t *pcm, const uint64_t *pcm_off, int *status)
+{
+    for (int i = 0; i < n; i++) {
+        int r = amvo_adpcm_decode_chunk(chunks + off[i], size[i], pcm + pcm_off[i]);
+        if (status) status[i] = r < 0 ? r : 0;
+    }
+    return n;
+}
+
+AMVO_API int amvo_adpcm_encode_chunks(const int16_t *pcm, const uint64_t *pcm_off, const uint32_t *nsamples,
+                                      const int16_t *step_in, int16_t *step_out, int n,
+                                      uint8_t *out, const uint64_t *out_off)
+{
+    for (int i = 0; i < n; i++) {
+        int so = 0;
+        int r = amvo_adpcm_encode_chunk(pcm + pcm_off[i], nsamples[i], step_in ? step_in[i] : 0,
+                                        out + out_off[i], &so);
+        if (r < 0) return r;
+        if (step_out) step_out[i] = (int16_t)so;
+    }
+    return n;
+}

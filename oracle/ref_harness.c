@@ -1,0 +1,192 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- never linked into, or called by, the product.
+ *
+ * Thin batch driver around the UNMODIFIED reference codecs (AMVmuxer FFmpeg
+ * fork) compiled in place by oracle/build_ref.sh into oracle/_ref/libamvref.so.
+ * It goes through the reference's own public plug-in API
+ * (avcodec_open / avcodec_encode_video / avcodec_decode_video /
+ * avcodec_encode_audio / avcodec_decode_audio2: libavcodec/utils.c:835-976)
+ * with the reference's own AVCodec instances
+ * (amv_decoder sp5xdec.c:203, amv_encoder mjpegenc.c:485,
+ *  adpcm_ima_amv_{en,de}coder adpcm.c:1535) -- one frame / chunk per call,
+ * exactly like ffmpeg.c:1083/814/1062/522 does.
+ *
+ * Used by tests/ (to pin oracle/amv_oracle.c and to generate tests/golden/)
+ * and by bench.py's cpu_baseline / --impl reference arm.
+ */
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+#include "avcodec.h"
+
+extern AVCodec amv_decoder, amv_encoder;
+extern AVCodec adpcm_ima_amv_decoder, adpcm_ima_amv_encoder;
+
+static int g_inited;
+static void ref_init(void)
+{
+    if (!g_inited) {
+        avcodec_init();
+        av_log_set_level(AV_LOG_QUIET);
+        g_inited = 1;
+    }
+}
+
+const char *amvref_version(void) { return "amv-codec-tools AMVmuxer libavcodec " AV_STRINGIFY(LIBAVCODEC_VERSION) " generic-C"; }
+
+/* ---- video encode: n frames, planes tightly packed (Y w*h, Cb/Cr cw*ch) ----
+ * quality = AVFrame.quality (lambda; 0 => reference default qscale 2).
+ * Packets are written back to back into out[0..cap); off[i]/size[i] locate them.
+ * Returns number of frames encoded, or a negative error. */
+int amvref_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                         int n, int w, int h, int quality,
+                         uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
+{
+    ref_init();
+    AVCodecContext *c = avcodec_alloc_context();
+    AVFrame *pic = avcodec_alloc_frame();
+    int cw = (w + 1) >> 1, ch = (h + 1) >> 1, i, ret = 0;
+    int bufsz = w * h * 6 + 262144;
+    uint8_t *buf = av_malloc(bufsz);
+    uint64_t pos = 0;
+    c->width = w; c->height = h;
+    c->time_base.num = 1; c->time_base.den = 16;
+    c->pix_fmt = PIX_FMT_YUVJ420P;
+    if (avcodec_open(c, &amv_encoder) < 0) { ret = -2; goto done; }
+    for (i = 0; i < n; i++) {
+        /* amv_encode_picture mutates data[]/linesize[] (mjpegenc.c:467-470): refill every frame */
+        pic->data[0] = (uint8_t *)y + (size_t)i * w * h;
+        pic->data[1] = (uint8_t *)u + (size_t)i * cw * ch;
+        pic->data[2] = (uint8_t *)v + (size_t)i * cw * ch;
+        pic->linesize[0] = w; pic->linesize[1] = cw; pic->linesize[2] = cw;
+        pic->quality = quality;
+        pic->pts = i;
+        int sz = avcodec_encode_video(c, buf, bufsz, pic);
+        if (sz < 0) { ret = -3; goto close; }
+        if (pos + sz > cap) { ret = -4; goto close; }
+        memcpy(out + pos, buf, sz);
+        off[i] = pos; size[i] = sz; pos += sz;
+    }
+    ret = n;
+close:
+    avcodec_close(c);
+done:
+    av_free(buf); av_free(pic); av_free(c);
+    return ret;
+}
+
+/* ---- video decode: n packets -> tightly packed planes ----
+ * got[i] receives got_picture; ret_bytes[i] the decoder's return value (may be NULL). */
+int amvref_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                         int n, int w, int h,
+                         uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes)
+{
+    ref_init();
+    AVCodecContext *c = avcodec_alloc_context();
+    AVFrame *pic = avcodec_alloc_frame();
+    int cw = (w + 1) >> 1, ch = (h + 1) >> 1, i, r, ret = 0;
+    uint32_t maxsz = 0;
+    for (i = 0; i < n; i++) if (size[i] > maxsz) maxsz = size[i];
+    uint8_t *buf = av_mallocz(maxsz + FF_INPUT_BUFFER_PADDING_SIZE + 16);
+    c->width = w; c->height = h;          /* container supplies dims: avidec.c:429-434 */
+    c->coded_width = w; c->coded_height = h;
+    if (avcodec_open(c, &amv_decoder) < 0) { ret = -2; goto done; }
+    for (i = 0; i < n; i++) {
+        int g = 0;
+        memcpy(buf, pkts + off[i], size[i]);
+        memset(buf + size[i], 0, FF_INPUT_BUFFER_PADDING_SIZE);
+        r = avcodec_decode_video(c, pic, &g, buf, size[i]);
+        if (got) got[i] = g;
+        if (ret_bytes) ret_bytes[i] = r;
+        if (r < 0 || !g) continue;
+        for (r = 0; r < h; r++)
+            memcpy(y + (size_t)i * w * h + (size_t)r * w, pic->data[0] + r * pic->linesize[0], w);
+        for (r = 0; r < ch; r++) {
+            memcpy(u + (size_t)i * cw * ch + (size_t)r * cw, pic->data[1] + r * pic->linesize[1], cw);
+            memcpy(v + (size_t)i * cw * ch + (size_t)r * cw, pic->data[2] + r * pic->linesize[2], cw);
+        }
+    }
+    ret = n;
+    avcodec_close(c);
+done:
+    av_free(buf); av_free(pic); av_free(c);
+    return ret;
+}
+
+/* ---- ADPCM decode: n chunks -> pcm; nsamp[i] = samples produced ---- */
+int amvref_adpcm_decode(const uint8_t *chunks, const uint64_t *off, const uint32_t *size,
+                        int n, int16_t *pcm, const uint64_t *pcm_off, uint32_t *nsamp)
+{
+    ref_init();
+    AVCodecContext *c = avcodec_alloc_context();
+    int i, ret = 0;
+    int16_t *tmp = av_malloc(AVCODEC_MAX_AUDIO_FRAME_SIZE * 2);
+    uint8_t *buf = av_mallocz(65536 + 16);
+    c->channels = 1; c->sample_rate = 22050;
+    if (avcodec_open(c, &adpcm_ima_amv_decoder) < 0) { ret = -2; goto done; }
+    for (i = 0; i < n; i++) {
+        int bytes = AVCODEC_MAX_AUDIO_FRAME_SIZE * 2;
+        if (size[i] > 65536) { ret = -5; break; }
+        memcpy(buf, chunks + off[i], size[i]);
+        int r = avcodec_decode_audio2(c, tmp, &bytes, buf, size[i]);
+        if (r < 0) { nsamp[i] = 0; continue; }
+        /* adpcm_decode_frame sets *data_size = (uint8_t*)samples - (uint8_t*)data */
+        nsamp[i] = bytes / 2;
+        memcpy(pcm + pcm_off[i], tmp, bytes);
+    }
+    if (!ret) ret = n;
+    avcodec_close(c);
+done:
+    av_free(tmp); av_free(buf); av_free(c);
+    return ret;
+}
+
+/* ---- ADPCM encode of ONE continuous stream, chunk by chunk (state chained,
+ * adpcm.c:461-496).  frame_size = samples per call as the AMV muxer sets it
+ * (amvenc.c:276-281).  Every call consumes 2n samples where 2n is what the
+ * encoder wrote into the chunk header (bytes 4..7); the harness advances by
+ * that (ffmpeg.c itself advances by frame_size -- SURVEY §9.10).
+ * Returns number of chunks written. consumed[i] = samples consumed by chunk i. */
+int amvref_adpcm_encode_stream(const int16_t *pcm, uint64_t total_samples, int frame_size,
+                               uint8_t *out, uint64_t *off, uint32_t *size,
+                               uint32_t *consumed, int max_chunks, uint64_t cap)
+{
+    ref_init();
+    AVCodecContext *c = avcodec_alloc_context();
+    int k = 0;
+    uint64_t pos = 0, opos = 0;
+    uint8_t *buf = av_malloc(FF_MIN_BUFFER_SIZE + 4 * frame_size + 65536);
+    c->channels = 1; c->sample_rate = 22050; c->frame_size = frame_size;
+    if (avcodec_open(c, &adpcm_ima_amv_encoder) < 0) { k = -2; goto done; }
+    c->frame_size = frame_size;
+    while (k < max_chunks && pos + 2 * (uint64_t)frame_size + 2 <= total_samples) {
+        int sz = avcodec_encode_audio(c, buf, FF_MIN_BUFFER_SIZE + 4 * frame_size + 65536, pcm + pos);
+        if (sz < 8) { k = -3; break; }
+        if (opos + sz > cap) { k = -4; break; }
+        uint32_t two_n = buf[4] | (buf[5] << 8) | (buf[6] << 16) | ((uint32_t)buf[7] << 24);
+        memcpy(out + opos, buf, sz);
+        off[k] = opos; size[k] = sz; consumed[k] = two_n;
+        opos += sz; pos += two_n; k++;
+    }
+    avcodec_close(c);
+done:
+    av_free(buf); av_free(c);
+    return k;
+}
+
+/* ---- single-stage entry points, for pinning the oracle stage by stage ---- */
+void ff_jpeg_fdct_islow(int16_t *data);
+void simple_idct_put(uint8_t *dest, int line_size, int16_t *block);
+void amvref_fdct_islow(int16_t *blocks, int nblocks)
+{
+    int i; for (i = 0; i < nblocks; i++) ff_jpeg_fdct_islow(blocks + 64 * i);
+}
+void amvref_simple_idct_put(const int16_t *blocks, int nblocks, uint8_t *dest /* 64 B per block */)
+{
+    int i; int16_t tmp[64];
+    ref_init();                       /* fills ff_cropTbl (dsputil.c:3812-3820) */
+    for (i = 0; i < nblocks; i++) {
+        memcpy(tmp, blocks + 64 * i, sizeof(tmp));
+        simple_idct_put(dest + 64 * i, 8, tmp);
+    }
+}

@@ -1,0 +1,318 @@
+"""ctypes front-ends for the CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+* ``Oracle``  -> oracle/_build/libamvoracle.so  (our C restatement, oracle/amv_oracle.c)
+* ``Ref``     -> oracle/_ref/libamvref.so       (the unmodified reference codecs, built in
+                 place by oracle/build_ref.sh; may be absent on a box without the prebuilt file)
+
+Plus the shared synthetic input generators and an AMV
+container walker used to pull packets out of the in-tree fixture.
+"""
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libamvoracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libamvref.so")
+FIXTURE_AMV = "/root/reference/C-AMVDecoder/bin/AMV1.amv"
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def build_oracle():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
+        os.path.join(ORACLE_DIR, "amv_oracle.c")
+    ):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "_build/libamvoracle.so"])
+    return ORACLE_SO
+
+
+def chroma_dims(w, h):
+    return (w + 1) // 2, (h + 1) // 2
+
+
+def offsets_of(sizes):
+    sizes = np.asarray(sizes, dtype=np.uint64)
+    off = np.zeros(len(sizes), dtype=np.uint64)
+    if len(sizes) > 1:
+        off[1:] = np.cumsum(sizes)[:-1]
+    return off
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.amvo_unstuff.restype = C.c_size_t
+
+    # -- stages
+    def zigzag(self):
+        z = np.zeros(64, np.uint8)
+        self.lib.amvo_get_zigzag(_p(z))
+        return z
+
+    def huff(self, t):
+        ln = np.zeros(256, np.uint8)
+        cd = np.zeros(256, np.uint16)
+        self.lib.amvo_get_huff(t, _p(ln), _p(cd))
+        return ln, cd
+
+    def fdct(self, blocks):
+        b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64).copy()
+        for i in range(b.shape[0]):
+            self.lib.amvo_fdct_islow(_p(b[i]))
+        return b
+
+    def idct_put(self, blocks):
+        b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64)
+        out = np.zeros((b.shape[0], 64), np.uint8)
+        for i in range(b.shape[0]):
+            self.lib.amvo_idct_put(_p(b[i]), _p(out[i]))
+        return out
+
+    def enc_qmat(self, qscale):
+        q = np.zeros(64, np.int32)
+        self.lib.amvo_enc_qmat(int(qscale), _p(q))
+        return q
+
+    def qscale_from_lambda(self, lam, qmin=2, qmax=31):
+        return self.lib.amvo_qscale_from_lambda(int(lam), qmin, qmax)
+
+    # -- video
+    def encode_frames(self, y, u, v, w, h, qscale=2, cap=None):
+        n = y.shape[0]
+        cap = cap or n * (w * h * 3 + 4096)
+        out = np.zeros(cap, np.uint8)
+        off = np.zeros(n, np.uint64)
+        size = np.zeros(n, np.uint32)
+        r = self.lib.amvo_encode_frames(_p(y), _p(u), _p(v), n, w, h, int(qscale), _p(out), _p(off), _p(size),
+                                        C.c_uint64(cap))
+        if r != n:
+            raise RuntimeError("oracle encode failed: %d" % r)
+        return out[: int(size.sum())].copy(), off, size
+
+    def decode_frames(self, pkts, off, size, w, h, undef=False):
+        """-> y, u, v, status[, (uy, uu, uv)]: the undef planes are 1 where the pre-clamp value
+        falls outside ff_cropTbl's domain, i.e. where the reference itself is undefined."""
+        n = len(size)
+        cw, ch = chroma_dims(w, h)
+        y = np.zeros((n, h, w), np.uint8)
+        u = np.zeros((n, ch, cw), np.uint8)
+        v = np.zeros((n, ch, cw), np.uint8)
+        m = [np.zeros_like(a) for a in (y, u, v)] if undef else [None] * 3
+        st = np.zeros(n, np.int32)
+        pk = np.ascontiguousarray(pkts, np.uint8)
+        self.lib.amvo_decode_frames(_p(pk), _p(np.ascontiguousarray(off, np.uint64)),
+                                    _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v), _p(st),
+                                    _p(m[0]), _p(m[1]), _p(m[2]))
+        return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
+
+    def decode_frame_coefs(self, pkt, w, h):
+        """Dequantised coefficients of every block in bitstream order (raster inside a block)."""
+        mbw, mbh = (w + 15) // 16, (h + 15) // 16
+        cw, ch = chroma_dims(w, h)
+        coef = np.zeros((mbw * mbh * 6, 64), np.int16)
+        y = np.zeros((h, w), np.uint8)
+        u = np.zeros((ch, cw), np.uint8)
+        v = np.zeros((ch, cw), np.uint8)
+        pk = np.ascontiguousarray(pkt, np.uint8)
+        st = self.lib.amvo_decode_frame(_p(pk), len(pk), w, h, _p(y), _p(u), _p(v), w, cw, _p(coef))
+        return coef, st
+
+    def unstuff(self, pkt):
+        pk = np.ascontiguousarray(pkt, np.uint8)
+        dst = np.zeros(len(pk) + 16, np.uint8)
+        fl = C.c_int(0)
+        n = self.lib.amvo_unstuff(_p(pk), len(pk), _p(dst), C.byref(fl))
+        return dst[:n].copy(), fl.value
+
+    # -- audio
+    def adpcm_decode(self, chunks, off, size):
+        n = len(size)
+        ns = np.maximum(np.asarray(size, np.int64) - 8, 0) * 2
+        poff = offsets_of(ns)
+        pcm = np.zeros(int(ns.sum()), np.int16)
+        st = np.zeros(n, np.int32)
+        self.lib.amvo_adpcm_decode_chunks(_p(np.ascontiguousarray(chunks, np.uint8)),
+                                          _p(np.ascontiguousarray(off, np.uint64)),
+                                          _p(np.ascontiguousarray(size, np.uint32)), n, _p(pcm), _p(poff), _p(st))
+        return pcm, poff, st
+
+    def adpcm_encode(self, pcm, pcm_off, nsamples, step_in):
+        n = len(nsamples)
+        nsamples = np.ascontiguousarray(nsamples, np.uint32)
+        osz = 8 + nsamples.astype(np.uint64) // 2
+        ooff = offsets_of(osz)
+        out = np.zeros(int(osz.sum()), np.uint8)
+        step_out = np.zeros(n, np.int16)
+        r = self.lib.amvo_adpcm_encode_chunks(_p(np.ascontiguousarray(pcm, np.int16)),
+                                              _p(np.ascontiguousarray(pcm_off, np.uint64)), _p(nsamples),
+                                              _p(np.ascontiguousarray(step_in, np.int16)), _p(step_out), n,
+                                              _p(out), _p(ooff))
+        if r != n:
+            raise RuntimeError("oracle adpcm encode failed: %d" % r)
+        return out, ooff, osz.astype(np.uint32), step_out
+
+
+class Ref:
+    """The unmodified reference codecs (libavcodec 51.47.1 of the AMVmuxer fork)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_SO)
+        self.lib.amvref_version.restype = C.c_char_p
+
+    def version(self):
+        return self.lib.amvref_version().decode()
+
+    def encode_frames(self, y, u, v, w, h, quality=0, cap=None):
+        n = y.shape[0]
+        cap = cap or n * (w * h * 3 + 4096)
+        out = np.zeros(cap, np.uint8)
+        off = np.zeros(n, np.uint64)
+        size = np.zeros(n, np.uint32)
+        r = self.lib.amvref_encode_frames(_p(y), _p(u), _p(v), n, w, h, int(quality), _p(out), _p(off), _p(size),
+                                          C.c_uint64(cap))
+        if r != n:
+            raise RuntimeError("reference encode failed: %d" % r)
+        return out[: int(size.sum())].copy(), off, size
+
+    def decode_frames(self, pkts, off, size, w, h):
+        n = len(size)
+        cw, ch = chroma_dims(w, h)
+        y = np.zeros((n, h, w), np.uint8)
+        u = np.zeros((n, ch, cw), np.uint8)
+        v = np.zeros((n, ch, cw), np.uint8)
+        got = np.zeros(n, np.int32)
+        rb = np.zeros(n, np.int32)
+        r = self.lib.amvref_decode_frames(_p(np.ascontiguousarray(pkts, np.uint8)),
+                                          _p(np.ascontiguousarray(off, np.uint64)),
+                                          _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v),
+                                          _p(got), _p(rb))
+        if r != n:
+            raise RuntimeError("reference decode failed: %d" % r)
+        return y, u, v, got, rb
+
+    def adpcm_decode(self, chunks, off, size):
+        n = len(size)
+        ns = np.maximum(np.asarray(size, np.int64) - 8, 0) * 2
+        poff = offsets_of(ns)
+        pcm = np.zeros(int(ns.sum()), np.int16)
+        nsamp = np.zeros(n, np.uint32)
+        r = self.lib.amvref_adpcm_decode(_p(np.ascontiguousarray(chunks, np.uint8)),
+                                         _p(np.ascontiguousarray(off, np.uint64)),
+                                         _p(np.ascontiguousarray(size, np.uint32)), n, _p(pcm), _p(poff), _p(nsamp))
+        if r != n:
+            raise RuntimeError("reference adpcm decode failed: %d" % r)
+        return pcm, poff, nsamp
+
+    def adpcm_encode_stream(self, pcm, frame_size, max_chunks=1 << 20):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        cap = len(pcm) + 16 * (len(pcm) // max(frame_size, 1) + 4) + 65536
+        out = np.zeros(cap, np.uint8)
+        mc = min(max_chunks, len(pcm) // max(frame_size, 1) + 2)
+        off = np.zeros(mc, np.uint64)
+        size = np.zeros(mc, np.uint32)
+        cons = np.zeros(mc, np.uint32)
+        k = self.lib.amvref_adpcm_encode_stream(_p(pcm), C.c_uint64(len(pcm)), int(frame_size), _p(out), _p(off),
+                                                _p(size), _p(cons), mc, C.c_uint64(cap))
+        if k < 0:
+            raise RuntimeError("reference adpcm encode failed: %d" % k)
+        return out[: int(size[:k].sum())].copy(), off[:k], size[:k], cons[:k]
+
+    def fdct(self, blocks):
+        b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64).copy()
+        self.lib.amvref_fdct_islow(_p(b), b.shape[0])
+        return b
+
+    def idct_put(self, blocks):
+        b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64)
+        out = np.zeros((b.shape[0], 64), np.uint8)
+        self.lib.amvref_simple_idct_put(_p(b), b.shape[0], _p(out))
+        return out
+
+
+# ----------------------------------------------------------------- generators
+
+def synth_frames(n, w, h, seed=1, t0=0, kind="sinus"):
+    """YUVJ420P test content. kind: sinus | noise | flat | edges"""
+    cw, ch = chroma_dims(w, h)
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return (rng.integers(0, 256, (n, h, w), dtype=np.uint8),
+                rng.integers(0, 256, (n, ch, cw), dtype=np.uint8),
+                rng.integers(0, 256, (n, ch, cw), dtype=np.uint8))
+    if kind == "flat":
+        lv = rng.integers(0, 256, (n, 3))
+        y = np.broadcast_to(lv[:, 0, None, None], (n, h, w)).astype(np.uint8).copy()
+        u = np.broadcast_to(lv[:, 1, None, None], (n, ch, cw)).astype(np.uint8).copy()
+        v = np.broadcast_to(lv[:, 2, None, None], (n, ch, cw)).astype(np.uint8).copy()
+        if n > 1:  # one frame with a few isolated impulses: single-coefficient rows/columns
+            y[1, ::13, ::7] = 255
+        return y, u, v
+    if kind == "edges":
+        y = np.zeros((n, h, w), np.uint8)
+        u = np.full((n, ch, cw), 128, np.uint8)
+        v = np.full((n, ch, cw), 128, np.uint8)
+        for i in range(n):
+            p = 1 + (i % 7)
+            yy, xx = np.mgrid[0:h, 0:w]
+            y[i] = (((xx // p) + (yy // p)) & 1) * 255
+            u[i, :, ::2] = 0 if i & 1 else 255
+            v[i, ::2, :] = 255 if i & 1 else 0
+        return y, u, v
+    t = (np.arange(n) + t0)[:, None, None].astype(np.float64)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    Y = 128 + 60 * np.sin((xx[None] + 3 * t) / 17.0) + 50 * np.cos((yy[None] - 2 * t) / 11.0)
+    Y = Y + rng.normal(0.0, 6.0, size=Y.shape)
+    cy, cx = np.mgrid[0:ch, 0:cw].astype(np.float64)
+    U = 128 + 40 * np.sin((cx[None] + t) / 23.0) + 0 * cy[None]
+    V = 128 + 40 * np.cos((cy[None] + t) / 19.0) + 0 * cx[None]
+    f = lambda a: np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    return f(Y), f(U), f(V)
+
+
+def synth_pcm(nsamples, seed=1, kind="tones"):
+    t = np.arange(nsamples, dtype=np.float64)
+    if kind == "noise":
+        return np.random.default_rng(seed).integers(-32768, 32768, nsamples).astype(np.int16)
+    if kind == "square":
+        return np.where((np.arange(nsamples) // 37) & 1, 32767, -32768).astype(np.int16)
+    if kind == "silence":
+        return np.zeros(nsamples, np.int16)
+    s = 8000 * np.sin(2 * np.pi * 440 * t / 22050) + 2000 * np.sin(2 * np.pi * 1234 * t / 22050)
+    return np.rint(s).astype(np.int16)
+
+
+# ------------------------------------------------------------ AMV container
+
+def walk_amv(data):
+    """Chunk walker in the spirit of AMVmuxer/compare_amv.c:44-94: returns
+    (width, height, fps, [video packets], [audio chunks])."""
+    i = data.find(b"amvh")
+    hdr = struct.unpack_from("<14I", data, i + 8)
+    w, h, fps = hdr[8], hdr[9], hdr[10]
+    p = data.find(b"movi") + 4
+    vids, auds = [], []
+    while p + 8 <= len(data):
+        tag = data[p:p + 4]
+        if tag not in (b"00dc", b"01wb"):
+            break
+        sz = struct.unpack_from("<I", data, p + 4)[0]
+        (vids if tag == b"00dc" else auds).append(data[p + 8:p + 8 + sz])
+        p += 8 + sz
+    return w, h, fps, vids, auds
+
+
+def pack(chunks):
+    size = np.array([len(c) for c in chunks], np.uint32)
+    return np.frombuffer(b"".join(chunks), np.uint8).copy(), offsets_of(size), size

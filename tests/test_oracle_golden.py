@@ -1,0 +1,90 @@
+"""The oracle against the committed golden vectors (tests/golden/amv_golden.npz,
+made by tests/golden/make_golden.py from the unmodified reference).  Needs neither
+/root/reference nor oracle/_ref: this is the pin that travels."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle, offsets_of
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "amv_golden.npz"))
+VIDEO_CASES = bytes(G["video_cases"]).decode().split("\n")
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def test_tables(oracle):
+    zz = oracle.zigzag()
+    assert sorted(zz.tolist()) == list(range(64))
+    assert zz[:10].tolist() == [0, 1, 8, 16, 9, 2, 3, 10, 17, 24] and zz[63] == 63
+    for t, nsym in ((0, 12), (1, 12), (2, 162), (3, 162)):
+        ln, cd = oracle.huff(t)
+        assert (ln > 0).sum() == nsym
+        # prefix-free and Kraft-complete except for the reserved all-ones code
+        kraft = sum(2.0 ** -int(l) for l in ln if l)
+        assert kraft < 1.0 and kraft + 2.0 ** -int(ln.max()) == 1.0
+    ln, cd = oracle.huff(2)
+    assert (ln[0x00], cd[0x00]) == (4, 0b1010) and (ln[0xF0], cd[0xF0]) == (11, 0b11111111001)
+    ln, cd = oracle.huff(3)
+    assert (ln[0x00], cd[0x00]) == (2, 0b00) and (ln[0xF0], cd[0xF0]) == (10, 0b1111111010)
+    q = oracle.enc_qmat(2)      # qmat[0..2] = 65536 131072 131072
+    assert q[:3].tolist() == [65536, 131072, 131072]
+
+
+@pytest.mark.parametrize("case", VIDEO_CASES)
+def test_encode_matches_golden(oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    qscale = oracle.qscale_from_lambda(int(q[1:]))
+    pk, off, sz = oracle.encode_frames(G[case + "/y"], G[case + "/u"], G[case + "/v"], w, h, qscale)
+    assert np.array_equal(sz, G[case + "/sz"]) and np.array_equal(pk, G[case + "/pk"])
+
+
+@pytest.mark.parametrize("case", VIDEO_CASES)
+def test_decode_matches_golden(oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    y, u, v, st, masks = oracle.decode_frames(G[case + "/pk"], G[case + "/off"], G[case + "/sz"], w, h, undef=True)
+    assert (st == 0).all()
+    for got, want, m in zip((y, u, v), (G[case + "/dy"], G[case + "/du"], G[case + "/dv"]), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])
+        if kind != "noise":
+            assert not m.any()
+
+
+def test_decode_reference_fixture_head(oracle):
+    w, h, fps, n = G["AMV1/dims"].tolist()
+    y, u, v, st = oracle.decode_frames(G["AMV1/pk"], G["AMV1/off"], G["AMV1/sz"], w, h)
+    assert (st == 0).all()
+    assert np.array_equal(y, G["AMV1/dy"]) and np.array_equal(u, G["AMV1/du"]) and np.array_equal(v, G["AMV1/dv"])
+    pcm, _, ast = oracle.adpcm_decode(G["AMV1/ak"], G["AMV1/aoff"], G["AMV1/asz"])
+    assert (ast == 0).all() and np.array_equal(pcm, G["AMV1/pcm"])
+
+
+@pytest.mark.parametrize("kind", ["tones", "noise", "square"])
+def test_adpcm_matches_golden(oracle, kind):
+    k = "adpcm_%s/" % kind
+    out, off, sz, cons = G[k + "out"], G[k + "off"], G[k + "sz"], G[k + "cons"]
+    step_in = np.array([int(out[int(o) + 2]) | (int(out[int(o) + 3]) << 8) for o in off], np.int16)
+    eo, eoff, esz, step_out = oracle.adpcm_encode(G[k + "src"], offsets_of(cons), cons, step_in)
+    assert np.array_equal(eo, out) and np.array_equal(esz, sz)
+    dp, _, st = oracle.adpcm_decode(out, off, sz)
+    assert (st == 0).all() and np.array_equal(dp, G[k + "dec"])
+
+
+def test_error_statuses(oracle):
+    # truncated packet -> overrun / bad code flagged, never a crash
+    case = VIDEO_CASES[0]
+    w, h = 160, 120
+    pk = G[case + "/pk"][: int(G[case + "/sz"][0])]
+    cut = np.concatenate([pk[:200], np.array([0xFF, 0xD9], np.uint8)])
+    _, _, _, st = oracle.decode_frames(cut, np.array([0], np.uint64), np.array([len(cut)], np.uint32), w, h)
+    assert st[0] != 0
+    # ADPCM: short chunk and out-of-range step index are rejected
+    bad = np.array([0, 0, 89, 0, 0, 0, 0, 0, 0x11], np.uint8)
+    _, _, st = oracle.adpcm_decode(bad, np.array([0], np.uint64), np.array([9], np.uint32))
+    assert st[0] < 0

@@ -1,0 +1,171 @@
+"""Pin oracle/amv_oracle.c against the UNMODIFIED reference compiled in place
+(oracle/_ref/libamvref.so, built by oracle/build_ref.sh) -- SURVEY.md 8c.
+
+Runs wherever the prebuilt reference library exists (this container, and the
+GPU box, since oracle/_ref/ travels with the snapshot).  Nothing here reads
+/root/reference except the AMV1.amv fixture test, which skips without it.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import FIXTURE_AMV, Oracle, Ref, pack, synth_frames, synth_pcm, walk_amv
+
+pytestmark = pytest.mark.skipif(not Ref.available(), reason="oracle/_ref/libamvref.so not built")
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return Ref()
+
+
+def test_fdct_matches_reference(oracle, ref):
+    rng = np.random.default_rng(7)
+    blocks = np.concatenate([
+        rng.integers(0, 256, (4000, 64)),                 # pixel domain (what the encoder feeds)
+        np.full((1, 64), 255), np.zeros((1, 64), int),
+        (np.indices((8, 8)).sum(0) & 1).reshape(1, 64) * 255,
+        rng.integers(-2048, 2048, (1000, 64)),            # beyond the pixel domain
+    ]).astype(np.int16)
+    assert np.array_equal(oracle.fdct(blocks), ref.fdct(blocks))
+
+
+def test_idct_matches_reference(oracle, ref):
+    rng = np.random.default_rng(8)
+    sparse = np.zeros((3000, 64), np.int16)
+    for i in range(sparse.shape[0]):                      # few coefficients: DC-only row shortcuts
+        k = rng.integers(0, 6)
+        sparse[i, rng.integers(0, 64, k)] = rng.integers(-1200, 1200, k)
+        sparse[i, 0] = rng.integers(-2000, 4000)
+    dense = rng.integers(-300, 300, (3000, 64)).astype(np.int16)
+    dc = np.zeros((512, 64), np.int16)
+    dc[:, 0] = np.arange(-256, 256) * 16
+    blocks = np.concatenate([sparse, dense, dc])
+    assert np.array_equal(oracle.idct_put(blocks), ref.idct_put(blocks))
+
+
+@pytest.mark.parametrize("w,h", [(160, 120), (320, 240), (208, 176), (128, 96), (48, 40), (16, 16), (72, 24)])
+@pytest.mark.parametrize("kind", ["sinus", "noise", "flat", "edges"])
+def test_encode_bytes_identical(oracle, ref, w, h, kind):
+    n = 3 if w * h > 40000 else 6
+    y, u, v = synth_frames(n, w, h, seed=3, kind=kind)
+    rp, roff, rsz = ref.encode_frames(y, u, v, w, h, quality=0)       # quality 0 -> qscale 2
+    op, ooff, osz = oracle.encode_frames(y, u, v, w, h, qscale=2)
+    assert np.array_equal(rsz, osz)
+    assert np.array_equal(rp, op)
+
+
+@pytest.mark.parametrize("qscale", [2, 3, 5, 10, 17, 31])
+def test_encode_qscale_sweep(oracle, ref, qscale):
+    w, h = 64, 48
+    y, u, v = synth_frames(4, w, h, seed=5, kind="sinus")
+    y2, u2, v2 = synth_frames(2, w, h, seed=6, kind="noise")
+    y, u, v = np.concatenate([y, y2]), np.concatenate([u, u2]), np.concatenate([v, v2])
+    lam = qscale * 118                                              # ffmpeg.c -qscale N -> quality = N*FF_QP2LAMBDA
+    assert oracle.qscale_from_lambda(lam) == qscale
+    rp, _, rsz = ref.encode_frames(y, u, v, w, h, quality=lam)
+    op, _, osz = oracle.encode_frames(y, u, v, w, h, qscale=qscale)
+    assert np.array_equal(rsz, osz) and np.array_equal(rp, op)
+
+
+@pytest.mark.parametrize("w,h", [(160, 120), (320, 240), (208, 176), (128, 96), (48, 40), (16, 16), (72, 24)])
+@pytest.mark.parametrize("kind", ["sinus", "noise", "flat", "edges"])
+def test_decode_planes_identical(oracle, ref, w, h, kind):
+    n = 3 if w * h > 40000 else 6
+    y, u, v = synth_frames(n, w, h, seed=4, kind=kind)
+    pk, off, sz = ref.encode_frames(y, u, v, w, h, quality=0)
+    ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h)
+    oy, ou, ov, st, (my, mu, mv) = oracle.decode_frames(pk, off, sz, w, h, undef=True)
+    assert (got != 0).all() and (st == 0).all()
+    # Pixels whose pre-clamp value leaves ff_cropTbl's -1024..1279 domain read foreign memory in the
+    # reference: excluded, and they only occur for the max-entropy content.
+    if kind != "noise":
+        assert not (my.any() or mu.any() or mv.any())
+    assert my.mean() < 0.01 and mu.mean() < 0.15 and mv.mean() < 0.15
+    for r_, o_, m_ in ((ry, oy, my), (ru, ou, mu), (rv, ov, mv)):
+        assert np.array_equal(r_[m_ == 0], o_[m_ == 0])
+
+
+def test_decode_high_qscale_streams(oracle, ref):
+    """Streams made at other qscales still decode with the decoder's fixed tables."""
+    w, h = 96, 80
+    y, u, v = synth_frames(4, w, h, seed=9, kind="noise")
+    for q in (2, 7, 31):
+        pk, off, sz = ref.encode_frames(y, u, v, w, h, quality=q * 118)
+        ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h)
+        oy, ou, ov, st, masks = oracle.decode_frames(pk, off, sz, w, h, undef=True)
+        assert (st == 0).all()
+        for r_, o_, m_ in zip((ry, ru, rv), (oy, ou, ov), masks):
+            assert np.array_equal(r_[m_ == 0], o_[m_ == 0])
+
+
+@pytest.mark.skipif(not os.path.exists(FIXTURE_AMV), reason="reference fixture not on this box")
+def test_fixture_amv1_known_answers(oracle, ref):
+    """The only AMV bitstream in the reference tree (real device clip, 128x96, 252 frames,
+    16 kHz mono).  md5s are those recorded in SURVEY.md 8c for the reference C path."""
+    w, h, fps, vids, auds = walk_amv(open(FIXTURE_AMV, "rb").read())
+    assert (w, h, fps, len(vids), len(auds)) == (128, 96, 12, 252, 252)
+    pk, off, sz = pack(vids)
+    oy, ou, ov, st = oracle.decode_frames(pk, off, sz, w, h)
+    ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h)
+    assert (st == 0).all()
+    assert np.array_equal(ry, oy) and np.array_equal(ru, ou) and np.array_equal(rv, ov)
+    m = hashlib.md5()
+    for i in range(len(vids)):
+        m.update(oy[i].tobytes()); m.update(ou[i].tobytes()); m.update(ov[i].tobytes())
+    assert m.hexdigest() == "9a4b7972e9a7bbcb12cee586d038c887"
+    ak, aoff, asz = pack(auds)
+    opcm, _, ast = oracle.adpcm_decode(ak, aoff, asz)
+    rpcm, _, _ = ref.adpcm_decode(ak, aoff, asz)
+    assert (ast == 0).all() and np.array_equal(opcm, rpcm)
+    assert hashlib.md5(opcm.tobytes()).hexdigest() == "10ee1d7766cb30742c65ea70558cff22"
+
+
+@pytest.mark.parametrize("kind", ["tones", "noise", "square", "silence"])
+@pytest.mark.parametrize("frame_size", [1378, 1379, 1837, 64])
+def test_adpcm_encode_stream_identical(oracle, ref, kind, frame_size):
+    pcm = synth_pcm(22050 * 3 + 777, seed=11, kind=kind)
+    rout, roff, rsz, cons = ref.adpcm_encode_stream(pcm, frame_size)
+    assert len(rsz) > 10
+    assert np.array_equal(rsz, 8 + cons // 2)
+    # chain state is in every chunk header (bytes 2..3); feed it to the per-chunk oracle
+    step_in = np.array([int(rout[int(o) + 2]) | (int(rout[int(o) + 3]) << 8) for o in roff], np.int16)
+    pcm_off = np.concatenate([[0], np.cumsum(cons.astype(np.uint64))[:-1]]).astype(np.uint64)
+    oout, ooff, osz, step_out = oracle.adpcm_encode(pcm, pcm_off, cons, step_in)
+    assert np.array_equal(osz, rsz) and np.array_equal(oout, rout)
+    assert np.array_equal(step_out[:-1], step_in[1:])               # the chain the reference carried
+    # and the chunk-size bookkeeping of adpcm.c:468-477
+    import ctypes as C
+    carry = C.c_int(0)
+    written = 0
+    for k in range(len(cons)):
+        two_n = oracle.lib.amvo_adpcm_next_chunk_samples(frame_size, 22050, C.c_uint64(written), C.byref(carry))
+        assert two_n == cons[k]
+        written += int(cons[k])
+
+
+@pytest.mark.parametrize("kind", ["tones", "noise", "square", "silence"])
+def test_adpcm_decode_identical(oracle, ref, kind):
+    pcm = synth_pcm(1378 * 40, seed=12, kind=kind)
+    out, off, sz, _ = ref.adpcm_encode_stream(pcm, 1378)
+    rp, _, ns = ref.adpcm_decode(out, off, sz)
+    op, _, st = oracle.adpcm_decode(out, off, sz)
+    assert (st == 0).all() and np.array_equal(rp, op)
+    # arbitrary nibbles and every legal header step index
+    rng = np.random.default_rng(13)
+    chunks = []
+    for idx in range(89):
+        body = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        pred = int(rng.integers(-32768, 32768))
+        chunks.append(int(pred & 0xFFFF).to_bytes(2, "little") + idx.to_bytes(2, "little") + (128).to_bytes(4, "little") + body)
+    ck, coff, csz = pack(chunks)
+    rp, _, _ = ref.adpcm_decode(ck, coff, csz)
+    op, _, st = oracle.adpcm_decode(ck, coff, csz)
+    assert (st == 0).all() and np.array_equal(rp, op)
