@@ -1,0 +1,258 @@
+"""amv-codec-tools_b200 -- B200-native AMV codec path (libamvcuda) and its Python host binding.
+
+The product is the C-ABI shared library ``lib/libamvcuda.so`` (include/amvcuda.h) built from the
+hand-written sm_100a kernels under ``csrc/``.  This module is a thin ctypes front-end over that
+ABI -- the same calls the reference-side AVCodec / amvlib shims make -- used by
+tests/, bench.py and __graft_entry__.py.  PyTorch appears only as plumbing (device buffers, streams).
+
+There is NO CPU path: if the library is missing or no sm_100 device is present, construction of
+:class:`AmvCuda` raises.
+
+Import name: the directory name is not a Python identifier; ``import amv_codec_tools_b200`` (the
+alias module at the repository root) loads this package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libamvcuda.so")
+HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "amvcuda.h")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+LAYOUT_PACKED, LAYOUT_SLOTS = 0, 1
+
+ST_SHORT, ST_BADCODE, ST_COEFIDX, ST_MARKER, ST_OVERRUN, ST_RANGE, ST_NOSPACE = (1 << i for i in range(7))
+
+EXPORTS = [
+    "amv_create", "amv_destroy", "amv_set_stream", "amv_sync", "amv_strerror", "amv_last_error", "amv_version",
+    "amv_launch_count", "amv_host_alloc", "amv_host_free", "amv_set_option", "amv_get_stat",
+    "amv_qscale_from_quality", "amv_decode_frames", "amv_encode_frames", "amv_adpcm_dec_chunks",
+    "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams",
+]
+
+
+class AmvError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libamvcuda.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", PKG_DIR, "-j4"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise AmvError("building libamvcuda failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+class _Params(C.Structure):
+    _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("flags", C.c_uint32)]
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise AmvError("libamvcuda.so not built (%s): run amv_codec_tools_b200.build() -- there is no fallback" % path)
+    lib = C.CDLL(path)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    lib.amv_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
+    lib.amv_destroy.argtypes = [vp]
+    lib.amv_destroy.restype = None
+    lib.amv_set_stream.argtypes = [vp, vp]
+    lib.amv_sync.argtypes = [vp]
+    lib.amv_strerror.argtypes = [i32]
+    lib.amv_strerror.restype = C.c_char_p
+    lib.amv_last_error.argtypes = [vp]
+    lib.amv_last_error.restype = C.c_char_p
+    lib.amv_launch_count.argtypes = [vp]
+    lib.amv_launch_count.restype = u64
+    lib.amv_host_alloc.argtypes = [C.c_size_t]
+    lib.amv_host_alloc.restype = vp
+    lib.amv_host_free.argtypes = [vp]
+    lib.amv_host_free.restype = None
+    lib.amv_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.amv_get_stat.argtypes = [vp, C.c_char_p]
+    lib.amv_get_stat.restype = C.c_int64
+    lib.amv_qscale_from_quality.argtypes = [i32, i32, i32]
+    lib.amv_decode_frames.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, vp, i32]
+    lib.amv_encode_frames.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, vp, vp, u64, u32, i32, vp, vp,
+                                      vp, i32]
+    lib.amv_adpcm_dec_chunks.argtypes = [vp, vp, u64, vp, vp, i32, vp, u64, vp, vp, i32]
+    lib.amv_adpcm_enc_chunks.argtypes = [vp, vp, u64, vp, vp, vp, vp, i32, vp, u64, vp, vp, i32]
+    lib.amv_adpcm_enc_streams.argtypes = [vp, vp, u64, vp, vp, vp, i32, i32, vp, vp, vp, u64, vp, vp, i32]
+    return lib
+
+
+def _ptr(a):
+    """Raw address of a numpy array (host) or a torch tensor (device or pinned host); None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise AmvError("array must be C-contiguous")
+        return a.ctypes.data
+    return a.data_ptr()          # torch tensor
+
+
+def chroma_dims(w, h):
+    return (w + 1) // 2, (h + 1) // 2
+
+
+def offsets_of(sizes):
+    sizes = np.asarray(sizes, dtype=np.uint64)
+    off = np.zeros(len(sizes), dtype=np.uint64)
+    if len(sizes) > 1:
+        off[1:] = np.cumsum(sizes)[:-1]
+    return off
+
+
+class AmvCuda:
+    """One libamvcuda context (one CUDA stream).  Mirrors include/amvcuda.h one to one."""
+
+    def __init__(self, device=-1, stream=None, lib_path=LIB_PATH):
+        self.lib = load_library(lib_path)
+        prm = _Params(device, stream, 0)
+        ctx = C.c_void_p()
+        r = self.lib.amv_create(C.byref(prm), C.byref(ctx))
+        if r != 0:
+            raise AmvError("amv_create failed: %s" % self.lib.amv_strerror(r).decode())
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.amv_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def _ck(self, r):
+        if r != 0:
+            raise AmvError("%s (%s)" % (self.lib.amv_strerror(r).decode(), self.lib.amv_last_error(self.ctx).decode()))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.lib.amv_set_stream(self.ctx, stream_ptr))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def sync(self):
+        self._ck(self.lib.amv_sync(self.ctx))
+
+    def set_option(self, key, value):
+        self._ck(self.lib.amv_set_option(self.ctx, key.encode(), int(value)))
+
+    def get_stat(self, key):
+        return int(self.lib.amv_get_stat(self.ctx, key.encode()))
+
+    def launch_count(self):
+        return int(self.lib.amv_launch_count(self.ctx))
+
+    def qscale_from_quality(self, quality, qmin=2, qmax=31):
+        return self.lib.amv_qscale_from_quality(int(quality), qmin, qmax)
+
+    # ---------------------------------------------------------------- raw ABI calls (any memory kind)
+    def decode_frames_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem):
+        self._ck(self.lib.amv_decode_frames(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
+                                            _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, _ptr(status), mem))
+
+    def encode_frames_raw(self, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, qscale, out, out_cap, pkt_cap, layout, out_off,
+                          out_size, status, mem):
+        self._ck(self.lib.amv_encode_frames(self.ctx, _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, n, w, h,
+                                            _ptr(qscale), _ptr(out), out_cap, pkt_cap, layout, _ptr(out_off),
+                                            _ptr(out_size), _ptr(status), mem))
+
+    def adpcm_dec_chunks_raw(self, chunks, chunks_bytes, off, size, n, pcm, pcm_samples, pcm_off, status, mem):
+        self._ck(self.lib.amv_adpcm_dec_chunks(self.ctx, _ptr(chunks), chunks_bytes, _ptr(off), _ptr(size), n, _ptr(pcm),
+                                               pcm_samples, _ptr(pcm_off), _ptr(status), mem))
+
+    def adpcm_enc_chunks_raw(self, pcm, pcm_samples, pcm_off, nsamples, step_in, step_out, n, out, out_bytes, out_off,
+                             status, mem):
+        self._ck(self.lib.amv_adpcm_enc_chunks(self.ctx, _ptr(pcm), pcm_samples, _ptr(pcm_off), _ptr(nsamples),
+                                               _ptr(step_in), _ptr(step_out), n, _ptr(out), out_bytes, _ptr(out_off),
+                                               _ptr(status), mem))
+
+    def adpcm_enc_streams_raw(self, pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, nchunks, step_in, step_out,
+                              out, out_bytes, out_off, status, mem):
+        self._ck(self.lib.amv_adpcm_enc_streams(self.ctx, _ptr(pcm), pcm_samples, _ptr(pcm_off), _ptr(nsamples),
+                                                _ptr(first_chunk), nstreams, nchunks, _ptr(step_in), _ptr(step_out),
+                                                _ptr(out), out_bytes, _ptr(out_off), _ptr(status), mem))
+
+    # ---------------------------------------------------------------- host (numpy) convenience wrappers
+    def decode_frames(self, pkts, pkt_off, pkt_size, w, h):
+        """numpy in / numpy out through AMV_MEM_HOST. -> (y[n,h,w], u[n,ch,cw], v[n,ch,cw], status[n])"""
+        pkts = np.ascontiguousarray(pkts, np.uint8)
+        pkt_off = np.ascontiguousarray(pkt_off, np.uint64)
+        pkt_size = np.ascontiguousarray(pkt_size, np.uint32)
+        n = len(pkt_size)
+        cw, ch = chroma_dims(w, h)
+        y = np.zeros((n, h, w), np.uint8)
+        u = np.zeros((n, ch, cw), np.uint8)
+        v = np.zeros((n, ch, cw), np.uint8)
+        st = np.zeros(n, np.int32)
+        self.decode_frames_raw(pkts, pkts.nbytes, pkt_off, pkt_size, n, w, h, y, u, v, w, cw, w * h, cw * ch, st, MEM_HOST)
+        return y, u, v, st
+
+    def encode_frames(self, y, u, v, qscale=None, pkt_cap=None, layout=LAYOUT_PACKED):
+        """numpy planes [n,h,w] / [n,ch,cw] -> (packets, off[n], size[n], status[n])"""
+        y = np.ascontiguousarray(y, np.uint8)
+        u = np.ascontiguousarray(u, np.uint8)
+        v = np.ascontiguousarray(v, np.uint8)
+        n, h, w = y.shape
+        cw, ch = chroma_dims(w, h)
+        assert u.shape == (n, ch, cw) and v.shape == (n, ch, cw)
+        pkt_cap = int(pkt_cap or (w * h * 3 + 4096))
+        q = None if qscale is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qscale, np.int32), (n,)))
+        out = np.zeros(n * pkt_cap, np.uint8)
+        off = np.zeros(n, np.uint64)
+        size = np.zeros(n, np.uint32)
+        st = np.zeros(n, np.int32)
+        self.encode_frames_raw(y, u, v, w, cw, w * h, cw * ch, n, w, h, q, out, out.nbytes, pkt_cap, layout, off, size, st,
+                               MEM_HOST)
+        if layout == LAYOUT_PACKED:
+            out = out[: int(size.astype(np.uint64).sum())].copy()
+        return out, off, size, st
+
+    def adpcm_decode(self, chunks, off, size):
+        chunks = np.ascontiguousarray(chunks, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        size = np.ascontiguousarray(size, np.uint32)
+        n = len(size)
+        ns = np.maximum(size.astype(np.int64) - 8, 0) * 2
+        poff = offsets_of(ns)
+        pcm = np.zeros(max(int(ns.sum()), 1), np.int16)
+        st = np.zeros(n, np.int32)
+        self.adpcm_dec_chunks_raw(chunks, chunks.nbytes, off, size, n, pcm, int(ns.sum()), poff, st, MEM_HOST)
+        return pcm[: int(ns.sum())], poff, st
+
+    def adpcm_encode(self, pcm, pcm_off, nsamples, step_in=None):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        pcm_off = np.ascontiguousarray(pcm_off, np.uint64)
+        nsamples = np.ascontiguousarray(nsamples, np.uint32)
+        n = len(nsamples)
+        osz = 8 + nsamples.astype(np.uint64) // 2
+        ooff = offsets_of(osz)
+        out = np.zeros(int(osz.sum()), np.uint8)
+        si = None if step_in is None else np.ascontiguousarray(step_in, np.int16)
+        so = np.zeros(n, np.int16)
+        st = np.zeros(n, np.int32)
+        self.adpcm_enc_chunks_raw(pcm, len(pcm), pcm_off, nsamples, si, so, n, out, out.nbytes, ooff, st, MEM_HOST)
+        return out, ooff, osz.astype(np.uint32), so, st
+
+    def adpcm_encode_streams(self, pcm, pcm_off, nsamples, first_chunk, step_in=None):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        pcm_off = np.ascontiguousarray(pcm_off, np.uint64)
+        nsamples = np.ascontiguousarray(nsamples, np.uint32)
+        first_chunk = np.ascontiguousarray(first_chunk, np.uint32)
+        nchunks, nstreams = len(nsamples), len(first_chunk) - 1
+        osz = 8 + nsamples.astype(np.uint64) // 2
+        ooff = offsets_of(osz)
+        out = np.zeros(int(osz.sum()), np.uint8)
+        si = None if step_in is None else np.ascontiguousarray(step_in, np.int16)
+        so = np.zeros(nstreams, np.int16)
+        st = np.zeros(nchunks, np.int32)
+        self.adpcm_enc_streams_raw(pcm, len(pcm), pcm_off, nsamples, first_chunk, nstreams, nchunks, si, so, out, out.nbytes,
+                                   ooff, st, MEM_HOST)
+        return out, ooff, osz.astype(np.uint32), so, st

@@ -1,0 +1,278 @@
+// amv_adpcm.cu -- IMA-ADPCM-AMV chunk decode / encode (sm_100a).
+//
+// The sample recurrence (predictor, step index) is strictly serial inside a chunk, and chunks
+// are independent (decode: state is in the 8-byte header, adpcm.c:1270-1271; encode: given the
+// step index carried in, adpcm.c:466).  So: one thread per chunk (or per chained stream), 32
+// chunks per warp, and the warp moves data for its 32 chunks cooperatively through shared
+// memory so that global traffic is coalesced although each thread walks its own chunk:
+//
+//   decode tile : 32 nibble bytes in  -> 64 samples (128 B) out per chunk
+//   encode tile : 64 samples (128 B) in -> 32 nibble bytes out per chunk
+//
+// Input rows are fetched by the whole warp one chunk at a time (32 consecutive bytes / 64
+// consecutive samples per instruction), transposed through a padded shared-memory tile
+// (pitch odd in words => conflict-free column access), and results go back the same way.
+#include "amv_common.cuh"
+#include "amv_tables.cuh"
+#include "amv_kernels.h"
+
+namespace amv {
+
+constexpr int kAdpcmWarps = 8;
+constexpr int kAdpcmThreads = kAdpcmWarps * 32;
+constexpr int kTileBytes = 32;                 // nibble bytes per chunk per tile
+constexpr int kTileSamples = 2 * kTileBytes;   // 64
+constexpr int kNibPitch = kTileBytes / 4 + 1;  // 9 words
+constexpr int kPcmPitch = kTileSamples / 2 + 1;  // 33 words
+
+__device__ uint16_t g_ima_step[96];
+
+struct AdpcmSmem {
+    uint16_t step[96];
+    uint32_t nib[kAdpcmWarps][32 * kNibPitch];
+    uint32_t pcm[kAdpcmWarps][32 * kPcmPitch];
+};
+
+__device__ __forceinline__ int ima_index_adjust(int q /* 0..7 */) { return (q & 4) ? ((q & 3) + 1) * 2 : -1; }
+
+// adpcm_ima_expand_nibble(c, nibble, 3)  (adpcm.c:716-742)
+__device__ __forceinline__ int ima_expand(int nib, int &pred, int &idx, const uint16_t *step_tab) {
+    const int step = step_tab[idx];
+    const int q = nib & 7;
+    idx = min(max(idx + ima_index_adjust(q), 0), 88);
+    const int diff = ((2 * q + 1) * step) >> 3;
+    pred = (nib & 8) ? pred - diff : pred + diff;
+    pred = min(max(pred, -32768), 32767);
+    return pred;
+}
+
+// adpcm_ima_compress_sample (adpcm.c:219-227): q = min(7, |delta|*4/step) found by three
+// compare/subtract steps against 4*step, 2*step, step (exact integer quotient, no division).
+__device__ __forceinline__ int ima_compress(int sample, int &prev, int &idx, const uint16_t *step_tab) {
+    const int step = step_tab[idx];
+    const int delta = sample - prev;
+    int t = (delta < 0 ? -delta : delta) * 4;
+    int q = 0;
+    if (t >= 4 * step) { q = 4; t -= 4 * step; }
+    if (t >= 2 * step) { q |= 2; t -= 2 * step; }
+    if (t >= step) q |= 1;
+    const int mv = (step * (2 * q + 1)) >> 3;        // (step * difflookup) / 8, magnitude part
+    prev = delta < 0 ? prev - mv : prev + mv;
+    prev = min(max(prev, -32768), 32767);
+    idx = min(max(idx + ima_index_adjust(q), 0), 88);
+    return q | (delta < 0 ? 8 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAdpcmThreads)
+k_adpcm_decode(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, const uint64_t *__restrict__ off,
+               const uint32_t *__restrict__ size, int n, int16_t *__restrict__ pcm, uint64_t pcm_samples,
+               const uint64_t *__restrict__ pcm_off, int32_t *__restrict__ status) {
+    __shared__ AdpcmSmem S;
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) S.step[i] = g_ima_step[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *nib = S.nib[wid], *out = S.pcm[wid];
+    const int nwarps = (n + 31) >> 5;
+
+    for (int wg = blockIdx.x * kAdpcmWarps + wid; wg < nwarps; wg += gridDim.x * kAdpcmWarps) {
+        const int c = wg * 32 + lane;
+        uint64_t src = 0, dsts = 0;
+        uint32_t nbytes = 0;      // nibble bytes of this lane's chunk
+        int pred = 0, idx = 0, st = 0;
+        if (c < n) {
+            const uint64_t o = off[c];
+            const uint32_t sz = size[c];
+            dsts = pcm_off[c];
+            if (sz < 8) st = AMV_ST_SHORT;
+            else if (o + sz > chunks_bytes || dsts + 2ull * (sz - 8) > pcm_samples) st = AMV_ST_RANGE;
+            else {
+                const uint8_t *h = chunks + o;
+                pred = (int)(int16_t)(h[0] | (h[1] << 8));
+                idx = (int)(int16_t)(h[2] | (h[3] << 8));
+                if (idx < 0 || idx > 88) st = AMV_ST_RANGE;   // the reference indexes step_table out of bounds here
+                else { src = o + 8; nbytes = sz - 8; }
+            }
+            status[c] = st;
+        }
+        uint32_t maxb = nbytes;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, d));
+
+        for (uint32_t t0 = 0; t0 < maxb; t0 += kTileBytes) {
+            // warp-cooperative load: chunk j's 32 tile bytes with one byte per lane
+            for (int j = 0; j < 32; j++) {
+                const uint64_t sj = __shfl_sync(0xffffffffu, src, j);
+                const uint32_t nj = __shfl_sync(0xffffffffu, nbytes, j);
+                if (t0 >= nj) continue;
+                uint8_t b = 0;
+                if (t0 + lane < nj) b = chunks[sj + t0 + lane];
+                reinterpret_cast<uint8_t *>(nib + j * kNibPitch)[lane] = b;
+            }
+            __syncwarp();
+            if (t0 < nbytes) {
+                const uint32_t *row = nib + lane * kNibPitch;
+                uint32_t *orow = out + lane * kPcmPitch;
+#pragma unroll
+                for (int w = 0; w < kTileBytes / 4; w++) {
+                    const uint32_t v = row[w];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int byte = (v >> (8 * b)) & 0xff;
+                        const int s0 = ima_expand(byte >> 4, pred, idx, S.step);      // high nibble first (:1281-1282)
+                        const int s1 = ima_expand(byte & 15, pred, idx, S.step);
+                        orow[w * 4 + b] = (uint32_t)(s0 & 0xffff) | ((uint32_t)s1 << 16);
+                    }
+                }
+            }
+            __syncwarp();
+            // warp-cooperative store: chunk j's 64 samples, 32-bit per lane when aligned
+            for (int j = 0; j < 32; j++) {
+                const uint64_t dj = __shfl_sync(0xffffffffu, dsts, j);
+                const uint32_t nj = __shfl_sync(0xffffffffu, nbytes, j);
+                if (t0 >= nj) continue;
+                const uint32_t v = out[j * kPcmPitch + lane];
+                const uint64_t s0 = dj + 2ull * t0 + 2 * lane;           // sample index of this lane's pair
+                if (t0 + lane < nj) {
+                    if ((reinterpret_cast<uintptr_t>(pcm + s0) & 3) == 0) *reinterpret_cast<uint32_t *>(pcm + s0) = v;
+                    else { pcm[s0] = (int16_t)(v & 0xffff); pcm[s0 + 1] = (int16_t)(v >> 16); }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One lane per stream; a stream is a run of chunks whose step index is chained.  With
+// first_chunk == NULL every chunk is its own stream.
+__global__ void __launch_bounds__(kAdpcmThreads)
+k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint64_t *__restrict__ pcm_off,
+               const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams,
+               const int16_t *__restrict__ step_in, int16_t *__restrict__ step_out, uint8_t *__restrict__ outb,
+               uint64_t out_bytes, const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
+    __shared__ AdpcmSmem S;
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) S.step[i] = g_ima_step[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *nib = S.nib[wid], *in = S.pcm[wid];
+    const int nwarps = (nstreams + 31) >> 5;
+
+    for (int wg = blockIdx.x * kAdpcmWarps + wid; wg < nwarps; wg += gridDim.x * kAdpcmWarps) {
+        const int s = wg * 32 + lane;
+        uint32_t c0 = 0, c1 = 0;
+        int idx = 0;
+        bool dead = false;          // a bad chunk stops its stream
+        if (s < nstreams) {
+            c0 = first_chunk ? first_chunk[s] : (uint32_t)s;
+            c1 = first_chunk ? first_chunk[s + 1] : (uint32_t)s + 1;
+            idx = step_in ? step_in[s] : 0;
+            if (idx < 0 || idx > 88) { dead = true; for (uint32_t c = c0; c < c1; c++) status[c] = AMV_ST_RANGE; }
+        }
+        uint32_t maxc = c1 - c0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+
+        for (uint32_t k = 0; k < maxc; k++) {
+            const uint32_t c = c0 + k;
+            const bool have = !dead && c < c1;
+            if (dead && c < c1 && s < nstreams) status[c] = AMV_ST_RANGE;     // rest of a broken stream
+            uint64_t src = 0, dst = 0;
+            uint32_t ns = 0;
+            int prev = 0;
+            if (have) {
+                ns = nsamples[c]; src = pcm_off[c]; dst = out_off[c];
+                int st = 0;
+                if (ns & 1) st = AMV_ST_RANGE;
+                else if (src + ns > pcm_samples || dst + 8 + ns / 2 > out_bytes) st = AMV_ST_RANGE;
+                status[c] = st;
+                if (st) { dead = true; ns = 0; }
+                else {
+                    // header: first sample, step index carried in, sample count (adpcm.c:464-479)
+                    prev = ns ? pcm[src] : 0;
+                    uint8_t *h = outb + dst;
+                    h[0] = (uint8_t)prev; h[1] = (uint8_t)(prev >> 8);
+                    h[2] = (uint8_t)idx;  h[3] = (uint8_t)(idx >> 8);
+                    h[4] = (uint8_t)ns; h[5] = (uint8_t)(ns >> 8); h[6] = (uint8_t)(ns >> 16); h[7] = (uint8_t)(ns >> 24);
+                }
+            }
+            uint32_t maxs = ns;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) maxs = max(maxs, __shfl_xor_sync(0xffffffffu, maxs, d));
+
+            for (uint32_t t0 = 0; t0 < maxs; t0 += kTileSamples) {
+                for (int j = 0; j < 32; j++) {
+                    const uint64_t sj = __shfl_sync(0xffffffffu, src, j);
+                    const uint32_t nj = __shfl_sync(0xffffffffu, ns, j);
+                    if (t0 >= nj) continue;
+                    // 64 samples of chunk j: lanes take samples lane and lane+32
+                    int16_t a = 0, b = 0;
+                    if (t0 + lane < nj) a = pcm[sj + t0 + lane];
+                    if (t0 + 32 + lane < nj) b = pcm[sj + t0 + 32 + lane];
+                    int16_t *row = reinterpret_cast<int16_t *>(in + j * kPcmPitch);
+                    row[lane] = a; row[32 + lane] = b;
+                }
+                __syncwarp();
+                if (t0 < ns) {
+                    const uint32_t *row = in + lane * kPcmPitch;
+                    uint32_t *orow = nib + lane * kNibPitch;
+#pragma unroll
+                    for (int w = 0; w < kTileBytes / 4; w++) {
+                        uint32_t packed = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const uint32_t v = row[w * 4 + b];
+                            // sample pairs past the end of the chunk are not encoded (keeps the carried state exact)
+                            if (t0 + 2 * (w * 4 + b) < ns) {
+                                const int n0 = ima_compress((int)(int16_t)(v & 0xffff), prev, idx, S.step);
+                                const int n1 = ima_compress((int)(int16_t)(v >> 16), prev, idx, S.step);
+                                packed |= (uint32_t)((n0 << 4) | n1) << (8 * b);
+                            }
+                        }
+                        orow[w] = packed;
+                    }
+                }
+                __syncwarp();
+                for (int j = 0; j < 32; j++) {
+                    const uint64_t dj = __shfl_sync(0xffffffffu, dst, j);
+                    const uint32_t nj = __shfl_sync(0xffffffffu, ns, j);
+                    if (t0 >= nj) continue;
+                    const uint32_t bytes_left = (nj - t0 + 1) / 2;
+                    if ((uint32_t)lane < bytes_left)
+                        outb[dj + 8 + t0 / 2 + lane] = reinterpret_cast<const uint8_t *>(nib + j * kNibPitch)[lane];
+                }
+                __syncwarp();
+            }
+        }
+        if (s < nstreams && step_out) step_out[s] = (int16_t)idx;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+cudaError_t upload_adpcm_tables(cudaStream_t s) {
+    static uint16_t h[96];
+    for (int i = 0; i < 96; i++) h[i] = kImaStep[i < 89 ? i : 88];
+    return cudaMemcpyToSymbolAsync(g_ima_step, h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+}
+
+static int adpcm_grid(int units) {
+    const int warps = (units + 31) / 32;
+    const int ctas = (warps + kAdpcmWarps - 1) / kAdpcmWarps;
+    const int cap = kNumSMs * 5;
+    return ctas < 1 ? 1 : (ctas < cap ? ctas : cap);
+}
+
+void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *off, const uint32_t *size, int n,
+                         int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s) {
+    k_adpcm_decode<<<adpcm_grid(n), kAdpcmThreads, 0, s>>>(chunks, chunks_bytes, off, size, n, pcm, pcm_samples, pcm_off,
+                                                           status);
+}
+
+void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
+                         const uint32_t *first_chunk, int nstreams, const int16_t *step_in, int16_t *step_out,
+                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, cudaStream_t s) {
+    k_adpcm_encode<<<adpcm_grid(nstreams), kAdpcmThreads, 0, s>>>(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams,
+                                                                  step_in, step_out, out, out_bytes, out_off, status);
+}
+
+}  // namespace amv

@@ -1,0 +1,485 @@
+// amv_api.cu -- the C ABI of libamvcuda (include/amvcuda.h): context, workspaces, host<->device
+// staging, and the kernel sequences behind each entry point.  No arithmetic of the codec lives
+// here and there is no CPU path: without a usable sm_100 device amv_create fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <string>
+
+#include "../../include/amvcuda.h"
+#include "amv_common.cuh"
+#include "amv_kernels.h"
+
+using namespace amv;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+enum WsId {
+    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS,
+    // device mirrors of host arguments (AMV_MEM_HOST calls)
+    WS_H_A, WS_H_B, WS_H_C, WS_H_D, WS_H_E, WS_H_F, WS_H_G, WS_H_H, WS_H_I,
+    WS_COUNT
+};
+
+}  // namespace
+
+struct amv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    int opt_log2p = -1;                 // decode lanes per frame, -1 = choose from the batch size
+    uint64_t opt_slot_ws_bytes = 4ull << 30;
+    uint32_t last_rounds = 0;
+    std::string err;
+    DevBuf ws[WS_COUNT];
+};
+
+namespace {
+
+int fail(amv_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, AMV_ERR_CUDA, #call, e_);         \
+    } while (0)
+
+int ensure(amv_ctx *ctx, WsId id, size_t bytes, void **out) {
+    DevBuf &b = ctx->ws[id];
+    if (bytes > b.cap) {
+        if (b.p) {
+            CK(cudaStreamSynchronize(ctx->stream));     // nothing in flight may still use the old block
+            CK(cudaFree(b.p));
+            b.p = nullptr; b.cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, AMV_ERR_NOMEM, "cudaMalloc workspace", e); }
+        b.cap = want;
+    }
+    *out = b.p;
+    return AMV_OK;
+}
+
+#define ENSURE(id, bytes, ptr)                                                    \
+    do {                                                                          \
+        void *p_ = nullptr;                                                       \
+        int r_ = ensure(ctx, id, (bytes), &p_);                                   \
+        if (r_ != AMV_OK) return r_;                                              \
+        ptr = reinterpret_cast<decltype(ptr)>(p_);                                \
+    } while (0)
+
+int check_launch(amv_ctx *ctx, const char *what, int count = 1) {
+    ctx->launches += count;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(ctx, AMV_ERR_CUDA, what, e);
+    return AMV_OK;
+}
+
+int pick_log2p(const amv_ctx *ctx, int n) {
+    if (ctx->opt_log2p >= 0) return ctx->opt_log2p > 5 ? 5 : ctx->opt_log2p;
+    // enough lanes to give every SM ~16 warps; beyond that one lane per frame has no
+    // synchronisation overhead at all
+    const int64_t want = (int64_t)kNumSMs * 16 * 32 / 2;
+    int l = 0;
+    while (l < 5 && ((int64_t)n << l) < want) l++;
+    return l;
+}
+
+// ---------------------------------------------------------------------------------- device paths
+int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                  const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
+                  uint64_t fs_y, uint64_t fs_c, int32_t *status) {
+    const Geom g = make_geom(w, h);
+    const int log2p = pick_log2p(ctx, n);
+    uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
+    uint32_t *rounds;
+    const uint64_t scratch_bytes = pkts_bytes + 48ull * n + 64;
+    ENSURE(WS_SLOT_OFF, sizeof(uint64_t) * n, slot_off);
+    ENSURE(WS_SCAN_LEN, sizeof(uint32_t) * n, scan_len);
+    ENSURE(WS_SCRATCH, scratch_bytes, scratch);
+    ENSURE(WS_ROUNDS, sizeof(uint32_t), rounds);
+    if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
+    if (log2p) ENSURE(WS_STARTS, sizeof(LaneStart) * ((size_t)n << log2p), starts);
+
+    launch_scan_sizes(pkt_size, n, 15u, 32u, slot_off, nullptr, ctx->stream);
+    launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, ctx->stream);
+    int lc = 2;
+    if (log2p) {
+        CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
+        launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, ctx->stream);
+        lc++;
+    }
+    launch_decode(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c, fs_y, fs_c, st, ctx->stream);
+    lc++;
+    return check_launch(ctx, "decode kernels", lc);
+}
+
+bool encode_geometry_ok(int w, int h) {
+    if (w < 2 || h < 2) return false;
+    const Geom g = make_geom(w, h);
+    // the reference starts reading each plane at rows y0 / c0 and walks up h resp. h>>1 rows
+    // (mjpegenc.c:467-470, mpegvideo_enc.c:857-879); outside this set it reads out of the picture
+    return g.y0 == h - 1 && g.c0 <= g.ch - 1 && g.c0 - ((h >> 1) - 1) >= 0;
+}
+
+int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
+                  uint64_t fs_c, int n, int w, int h, const int32_t *qscale, uint8_t *out, uint64_t out_cap,
+                  uint32_t pkt_cap, int layout, uint64_t *out_off, uint32_t *out_size, int32_t *status) {
+    const Geom g = make_geom(w, h);
+    int32_t *st = status;
+    if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
+    if (layout == AMV_LAYOUT_SLOTS) {
+        if ((uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
+        launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out, pkt_cap, pkt_cap, out_size, st, ctx->stream);
+        launch_slot_offsets(out_off, n, pkt_cap, ctx->stream);
+        return check_launch(ctx, "encode kernels", 2);
+    }
+    // packed: encode into 16-byte aligned workspace slots, scan the sizes, compact
+    const uint64_t stride = ((uint64_t)pkt_cap + 15) & ~15ull;
+    int sub = (int)(ctx->opt_slot_ws_bytes / stride);
+    if (sub < 1) sub = 1;
+    if (sub > n) sub = n;
+    uint8_t *slots; uint64_t *carry;
+    ENSURE(WS_SLOTS, stride * sub + 64, slots);
+    ENSURE(WS_CARRY, sizeof(uint64_t), carry);
+    CK(cudaMemsetAsync(carry, 0, sizeof(uint64_t), ctx->stream));
+    int lc = 0;
+    for (int f0 = 0; f0 < n; f0 += sub) {
+        const int m = n - f0 < sub ? n - f0 : sub;
+        launch_encode(y + fs_y * f0, u + fs_c * f0, v + fs_c * f0, ls_y, ls_c, fs_y, fs_c, m, g, qscale ? qscale + f0 : nullptr,
+                      slots, stride, pkt_cap, out_size + f0, st + f0, ctx->stream);
+        launch_scan_sizes(out_size + f0, m, 0u, 0u, out_off + f0, carry, ctx->stream);
+        launch_compact(slots, stride, out_size + f0, out_off + f0, m, out, out_cap, st + f0, ctx->stream);
+        lc += 3;
+    }
+    return check_launch(ctx, "encode kernels", lc);
+}
+
+// ------------------------------------------------------------------------------------ host staging
+// Copies a host array into a device mirror (workspace id) and returns the device pointer.
+int to_device(amv_ctx *ctx, WsId id, const void *host, size_t bytes, void **dev) {
+    int r = ensure(ctx, id, bytes ? bytes : 1, dev);
+    if (r != AMV_OK) return r;
+    if (bytes) CK(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return AMV_OK;
+}
+
+#define TO_DEVICE(id, host, bytes, ptr)                                           \
+    do {                                                                          \
+        void *p_ = nullptr;                                                       \
+        int r_ = to_device(ctx, id, (host), (bytes), &p_);                        \
+        if (r_ != AMV_OK) return r_;                                              \
+        ptr = reinterpret_cast<decltype(ptr)>(p_);                                \
+    } while (0)
+
+// planes: host (ls, fs) layout <-> tight device layout (ls = width, fs = width*height)
+int copy_planes(amv_ctx *ctx, uint8_t *dev, uint8_t *host, int width, int height, int ls, uint64_t fs, int n, bool to_host) {
+    const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+    const uint64_t tight = (uint64_t)width * height;
+    if (ls == width && fs == tight) {
+        if (to_host) CK(cudaMemcpyAsync(host, dev, tight * n, kind, ctx->stream));
+        else         CK(cudaMemcpyAsync(dev, host, tight * n, kind, ctx->stream));
+        return AMV_OK;
+    }
+    for (int i = 0; i < n; i++) {
+        if (to_host) CK(cudaMemcpy2DAsync(host + fs * i, ls, dev + tight * i, width, width, height, kind, ctx->stream));
+        else         CK(cudaMemcpy2DAsync(dev + tight * i, width, host + fs * i, ls, width, height, kind, ctx->stream));
+    }
+    return AMV_OK;
+}
+
+bool bad_mem(int mem) { return mem != AMV_MEM_HOST && mem != AMV_MEM_DEVICE; }
+
+}  // namespace
+
+// ================================================================================== public ABI
+extern "C" {
+
+AMV_API int amv_version(void) { return AMVCUDA_VERSION; }
+
+AMV_API const char *amv_strerror(int err) {
+    switch (err) {
+    case AMV_OK: return "ok";
+    case AMV_ERR_ARG: return "invalid argument";
+    case AMV_ERR_NODEVICE: return "no usable CUDA device (libamvcuda has no CPU path)";
+    case AMV_ERR_CUDA: return "CUDA runtime error";
+    case AMV_ERR_NOMEM: return "out of device memory";
+    case AMV_ERR_UNSUPPORTED: return "unsupported option";
+    default: return "unknown error";
+    }
+}
+
+AMV_API const char *amv_last_error(const amv_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+AMV_API uint64_t amv_launch_count(const amv_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+AMV_API int amv_qscale_from_quality(int quality, int qmin, int qmax) {
+    int q = (quality * 139 + 128 * 64) >> 14;          // update_qscale, mpegvideo_enc.c:143-148
+    return q < qmin ? qmin : (q > qmax ? qmax : q);
+}
+
+AMV_API void *amv_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+AMV_API void amv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+AMV_API int amv_create(const amv_params *params, amv_ctx **out_ctx) {
+    if (!out_ctx) return AMV_ERR_ARG;
+    *out_ctx = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return AMV_ERR_NODEVICE; }
+    int dev = params ? params->device : -1;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return AMV_ERR_NODEVICE; }
+    if (dev >= ndev) return AMV_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return AMV_ERR_NODEVICE;
+    if (prop.major != 10) return AMV_ERR_NODEVICE;     // kernels are built for sm_100a only
+    if (cudaSetDevice(dev) != cudaSuccess) return AMV_ERR_NODEVICE;
+    amv_ctx *ctx = new (std::nothrow) amv_ctx();
+    if (!ctx) return AMV_ERR_NOMEM;
+    ctx->device = dev;
+    if (params && params->stream) ctx->stream = (cudaStream_t)params->stream;
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AMV_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaError_t e = upload_dec_tables(ctx->stream);
+    if (e == cudaSuccess) e = upload_enc_tables(ctx->stream);
+    if (e == cudaSuccess) e = upload_adpcm_tables(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { amv_destroy(ctx); return AMV_ERR_CUDA; }
+    *out_ctx = ctx;
+    return AMV_OK;
+}
+
+AMV_API void amv_destroy(amv_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < WS_COUNT; i++) if (ctx->ws[i].p) cudaFree(ctx->ws[i].p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+AMV_API int amv_set_stream(amv_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return AMV_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return AMV_OK;
+}
+
+AMV_API int amv_sync(amv_ctx *ctx) {
+    if (!ctx) return AMV_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return AMV_ERR_ARG;
+    if (!strcmp(key, "decode_log2_lanes")) { ctx->opt_log2p = (int)value; return AMV_OK; }
+    if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
+    return AMV_ERR_UNSUPPORTED;
+}
+
+AMV_API int64_t amv_get_stat(amv_ctx *ctx, const char *key) {
+    if (!ctx || !key) return -1;
+    if (!strcmp(key, "decode_sync_rounds")) {
+        uint32_t r = 0;
+        if (!ctx->ws[WS_ROUNDS].p) return 0;
+        if (cudaMemcpyAsync(&r, ctx->ws[WS_ROUNDS].p, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+        cudaStreamSynchronize(ctx->stream);
+        return r;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------- decode
+AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                              const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
+                              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
+    if (n == 0) return AMV_OK;
+    if (!pkts || !pkt_off || !pkt_size || !y || !u || !v) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    if (ls_y < w || ls_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw)
+        return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE)
+        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status);
+
+    uint8_t *d_pk; uint64_t *d_off; uint32_t *d_sz; uint8_t *d_y, *d_u, *d_v; int32_t *d_st;
+    TO_DEVICE(WS_H_A, pkts, pkts_bytes, d_pk);
+    TO_DEVICE(WS_H_B, pkt_off, sizeof(uint64_t) * n, d_off);
+    TO_DEVICE(WS_H_C, pkt_size, sizeof(uint32_t) * n, d_sz);
+    ENSURE(WS_H_D, (size_t)w * h * n, d_y);
+    ENSURE(WS_H_E, (size_t)cw * ch * n, d_u);
+    ENSURE(WS_H_F, (size_t)cw * ch * n, d_v);
+    ENSURE(WS_H_G, sizeof(int32_t) * n, d_st);
+    int r = decode_device(ctx, d_pk, pkts_bytes, d_off, d_sz, n, w, h, d_y, d_u, d_v, w, cw, (uint64_t)w * h,
+                          (uint64_t)cw * ch, d_st);
+    if (r != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_y, y, w, h, ls_y, fs_y, n, true)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_u, u, cw, ch, ls_c, fs_c, n, true)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_v, v, cw, ch, ls_c, fs_c, n, true)) != AMV_OK) return r;
+    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+// ---------------------------------------------------------------------------------------- encode
+AMV_API int amv_encode_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
+                              uint64_t fs_y, uint64_t fs_c, int n, int w, int h, const int32_t *qscale, uint8_t *out,
+                              uint64_t out_cap, uint32_t pkt_cap, int layout, uint64_t *out_off, uint32_t *out_size,
+                              int32_t *status, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
+    if (layout != AMV_LAYOUT_PACKED && layout != AMV_LAYOUT_SLOTS) return fail(ctx, AMV_ERR_ARG, "bad layout");
+    if (!encode_geometry_ok(w, h))
+        return fail(ctx, AMV_ERR_UNSUPPORTED, "height outside the reference encoder's defined domain ((h/2)%8 must be 0 or 4)");
+    if (n == 0) return AMV_OK;
+    if (!y || !u || !v || !out || !out_off || !out_size) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    if (pkt_cap < 4) return fail(ctx, AMV_ERR_ARG, "pkt_cap too small");
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    if (ls_y < w || ls_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw)
+        return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE)
+        return encode_device(ctx, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, qscale, out, out_cap, pkt_cap, layout, out_off,
+                             out_size, status);
+
+    if (qscale) for (int i = 0; i < n; i++) if (qscale[i] < 2 || qscale[i] > 31) return fail(ctx, AMV_ERR_UNSUPPORTED, "qscale outside 2..31");
+    uint8_t *d_y, *d_u, *d_v, *d_out; int32_t *d_q = nullptr; uint64_t *d_off; uint32_t *d_sz; int32_t *d_st;
+    ENSURE(WS_H_A, (size_t)w * h * n, d_y);
+    ENSURE(WS_H_B, (size_t)cw * ch * n, d_u);
+    ENSURE(WS_H_C, (size_t)cw * ch * n, d_v);
+    int r;
+    if ((r = copy_planes(ctx, d_y, const_cast<uint8_t *>(y), w, h, ls_y, fs_y, n, false)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_u, const_cast<uint8_t *>(u), cw, ch, ls_c, fs_c, n, false)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_v, const_cast<uint8_t *>(v), cw, ch, ls_c, fs_c, n, false)) != AMV_OK) return r;
+    if (qscale) TO_DEVICE(WS_H_D, qscale, sizeof(int32_t) * n, d_q);
+    const uint64_t dcap = layout == AMV_LAYOUT_SLOTS ? (uint64_t)pkt_cap * n : out_cap;
+    ENSURE(WS_H_E, dcap, d_out);
+    ENSURE(WS_H_F, sizeof(uint64_t) * n, d_off);
+    ENSURE(WS_H_G, sizeof(uint32_t) * n, d_sz);
+    ENSURE(WS_H_H, sizeof(int32_t) * n, d_st);
+    r = encode_device(ctx, d_y, d_u, d_v, w, cw, (uint64_t)w * h, (uint64_t)cw * ch, n, w, h, d_q, d_out, dcap, pkt_cap, layout,
+                      d_off, d_sz, d_st);
+    if (r != AMV_OK) return r;
+    CK(cudaMemcpyAsync(out_off, d_off, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_size, d_sz, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // only the bytes that were produced travel back
+    uint64_t used = 0;
+    if (layout == AMV_LAYOUT_SLOTS) used = (uint64_t)pkt_cap * n;
+    else for (int i = 0; i < n; i++) if (out_off[i] + out_size[i] > used) used = out_off[i] + out_size[i];
+    if (used > out_cap) used = out_cap;
+    if (used) CK(cudaMemcpyAsync(out, d_out, used, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+// ----------------------------------------------------------------------------------------- adpcm
+AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx, const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *chunk_off,
+                                 const uint32_t *chunk_size, int n, int16_t *pcm, uint64_t pcm_samples,
+                                 const uint64_t *pcm_off, int32_t *status, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (n < 0 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / mem");
+    if (n == 0) return AMV_OK;
+    if (!chunks || !chunk_off || !chunk_size || !pcm || !pcm_off) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE) {
+        int32_t *st = status;
+        if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
+        launch_adpcm_decode(chunks, chunks_bytes, chunk_off, chunk_size, n, pcm, pcm_samples, pcm_off, st, ctx->stream);
+        return check_launch(ctx, "adpcm decode kernel");
+    }
+    uint8_t *d_c; uint64_t *d_off, *d_poff; uint32_t *d_sz; int16_t *d_pcm; int32_t *d_st;
+    TO_DEVICE(WS_H_A, chunks, chunks_bytes, d_c);
+    TO_DEVICE(WS_H_B, chunk_off, sizeof(uint64_t) * n, d_off);
+    TO_DEVICE(WS_H_C, chunk_size, sizeof(uint32_t) * n, d_sz);
+    TO_DEVICE(WS_H_D, pcm_off, sizeof(uint64_t) * n, d_poff);
+    ENSURE(WS_H_E, sizeof(int16_t) * pcm_samples, d_pcm);
+    ENSURE(WS_H_F, sizeof(int32_t) * n, d_st);
+    launch_adpcm_decode(d_c, chunks_bytes, d_off, d_sz, n, d_pcm, pcm_samples, d_poff, d_st, ctx->stream);
+    int r = check_launch(ctx, "adpcm decode kernel");
+    if (r != AMV_OK) return r;
+    CK(cudaMemcpyAsync(pcm, d_pcm, sizeof(int16_t) * pcm_samples, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off,
+                               const uint32_t *nsamples, const uint32_t *first_chunk, int nstreams, int nchunks,
+                               const int16_t *step_in, int16_t *step_out, uint8_t *out, uint64_t out_bytes,
+                               const uint64_t *out_off, int32_t *status, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (nstreams < 0 || nchunks < 0 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / mem");
+    if (nstreams == 0 || nchunks == 0) return AMV_OK;
+    if (!pcm || !pcm_off || !nsamples || !out || !out_off) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE) {
+        int32_t *st = status;
+        if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * nchunks, st);
+        launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, step_in, step_out, out, out_bytes,
+                            out_off, st, ctx->stream);
+        return check_launch(ctx, "adpcm encode kernel");
+    }
+    int16_t *d_pcm; uint64_t *d_poff, *d_ooff; uint32_t *d_ns, *d_fc = nullptr; int16_t *d_si = nullptr, *d_so; uint8_t *d_out;
+    int32_t *d_st;
+    TO_DEVICE(WS_H_A, pcm, sizeof(int16_t) * pcm_samples, d_pcm);
+    TO_DEVICE(WS_H_B, pcm_off, sizeof(uint64_t) * nchunks, d_poff);
+    TO_DEVICE(WS_H_C, nsamples, sizeof(uint32_t) * nchunks, d_ns);
+    TO_DEVICE(WS_H_D, out_off, sizeof(uint64_t) * nchunks, d_ooff);
+    if (first_chunk) TO_DEVICE(WS_H_E, first_chunk, sizeof(uint32_t) * (nstreams + 1), d_fc);
+    if (step_in) TO_DEVICE(WS_H_F, step_in, sizeof(int16_t) * nstreams, d_si);
+    ENSURE(WS_H_G, sizeof(int16_t) * nstreams, d_so);
+    ENSURE(WS_H_H, out_bytes ? out_bytes : 1, d_out);
+    ENSURE(WS_H_I, sizeof(int32_t) * nchunks, d_st);
+    CK(cudaMemsetAsync(d_st, 0, sizeof(int32_t) * nchunks, ctx->stream));
+    launch_adpcm_encode(d_pcm, pcm_samples, d_poff, d_ns, d_fc, nstreams, d_si, d_so, d_out, out_bytes, d_ooff, d_st, ctx->stream);
+    int r = check_launch(ctx, "adpcm encode kernel");
+    if (r != AMV_OK) return r;
+    CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (step_out) CK(cudaMemcpyAsync(step_out, d_so, sizeof(int16_t) * nstreams, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * nchunks, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+AMV_API int amv_adpcm_enc_chunks(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off,
+                                 const uint32_t *nsamples, const int16_t *step_in, int16_t *step_out, int n, uint8_t *out,
+                                 uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int mem) {
+    return adpcm_encode_common(ctx, pcm, pcm_samples, pcm_off, nsamples, nullptr, n, n, step_in, step_out, out, out_bytes,
+                               out_off, status, mem);
+}
+
+AMV_API int amv_adpcm_enc_streams(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off,
+                                  const uint32_t *nsamples, const uint32_t *first_chunk, int nstreams, int nchunks,
+                                  const int16_t *step_in, int16_t *step_out, uint8_t *out, uint64_t out_bytes,
+                                  const uint64_t *out_off, int32_t *status, int mem) {
+    if (!first_chunk) return fail(ctx, AMV_ERR_ARG, "first_chunk is NULL");
+    return adpcm_encode_common(ctx, pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, nchunks, step_in, step_out, out,
+                               out_bytes, out_off, status, mem);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// amv_common.cuh -- shared definitions for the libamvcuda kernels (sm_100a).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define AMV_HD __host__ __device__ __forceinline__
+#define AMV_D  __device__ __forceinline__
+#else
+#define AMV_HD inline
+#define AMV_D  inline
+#endif
+
+// per-unit status bits: keep in sync with include/amvcuda.h
+#define AMV_ST_SHORT    (1 << 0)
+#define AMV_ST_BADCODE  (1 << 1)
+#define AMV_ST_COEFIDX  (1 << 2)
+#define AMV_ST_MARKER   (1 << 3)
+#define AMV_ST_OVERRUN  (1 << 4)
+#define AMV_ST_RANGE    (1 << 5)
+#define AMV_ST_NOSPACE  (1 << 6)
+
+namespace amv {
+
+constexpr int kNumSMs = 148;              // B200
+
+// Picture geometry shared by encoder and decoder kernels.
+struct Geom {
+    int w, h;          // luma size
+    int cw, ch;        // chroma plane size, ceil(w/2) x ceil(h/2)
+    int mbw, mbh;      // macroblock grid, ceil(w/16) x ceil(h/16)
+    int nblk;          // 6 * mbw * mbh
+    int y0, c0;        // first (bottom-most stored) row of luma / chroma in flipped order
+};
+
+// Row the codec starts from before walking upwards: vs*(8*mb_h - ((h/2)&7)) - 1
+// (mjpegdec.c:672-677 and mjpegenc.c:467-470 use the same expression).
+AMV_HD int flip_start_row(int h, int vs) {
+    const int mbh = (h + 15) >> 4;
+    return vs * (8 * mbh - ((h >> 1) & 7)) - 1;
+}
+
+AMV_HD Geom make_geom(int w, int h) {
+    Geom g;
+    g.w = w; g.h = h;
+    g.cw = (w + 1) >> 1; g.ch = (h + 1) >> 1;
+    g.mbw = (w + 15) >> 4; g.mbh = (h + 15) >> 4;
+    g.nblk = 6 * g.mbw * g.mbh;
+    g.y0 = flip_start_row(h, 2);
+    g.c0 = flip_start_row(h, 1);
+    return g;
+}
+
+AMV_HD uint32_t bswap32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+#endif
+}
+
+AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+}  // namespace amv

@@ -1,0 +1,142 @@
+// amv_dct.cuh -- the two integer 8x8 transforms of the AMV path as straight-line
+// register code (one thread = one block).  Both are ring arithmetic mod 2^32
+// (adds, multiplies) up to the right shifts, so any regrouping of the sums is
+// bit-identical to the reference's evaluation order.
+#pragma once
+#include "amv_common.cuh"
+
+namespace amv {
+
+AMV_HD int sext16(int v) { return (int)(int16_t)v; }
+
+AMV_HD int clamp_u8(int v) {
+#if defined(__CUDA_ARCH__)
+    return __vimin_s32_relu(v, 255);          // max(min(v,255),0): one VIMNMX on sm_90+
+#else
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+#endif
+}
+
+// ---------------------------------------------------------------- simple_idct
+// simple_idct_put (simple_idct.c:390-398): idctRowCondDC (:78-181) on each row,
+// results truncated to int16, then idctSparseColPut (:183-253) with clamp.
+// W4 = 16383 (:50), row shift 11, column shift 20, column bias W4*32.
+struct IdctC { enum { W1 = 22725, W2 = 21407, W3 = 19266, W4 = 16383, W5 = 12873, W6 = 8867, W7 = 4520 }; };
+
+// 1-D butterfly shared by both passes: e0 is the pre-biased DC term.
+AMV_HD void idct_1d(int e0, int x1, int x2, int x3, int x4, int x5, int x6, int x7, int (&s)[4], int (&d)[4]) {
+    const int t4 = IdctC::W4 * x4;
+    const int ea = e0 + t4, eb = e0 - t4;
+    const int g0 = IdctC::W2 * x2 + IdctC::W6 * x6;
+    const int g1 = IdctC::W6 * x2 - IdctC::W2 * x6;
+    const int a0 = ea + g0, a1 = eb + g1, a2 = eb - g1, a3 = ea - g0;
+    const int b0 = IdctC::W1 * x1 + IdctC::W3 * x3 + IdctC::W5 * x5 + IdctC::W7 * x7;
+    const int b1 = IdctC::W3 * x1 - IdctC::W7 * x3 - IdctC::W1 * x5 - IdctC::W5 * x7;
+    const int b2 = IdctC::W5 * x1 - IdctC::W1 * x3 + IdctC::W7 * x5 + IdctC::W3 * x7;
+    const int b3 = IdctC::W7 * x1 - IdctC::W5 * x3 + IdctC::W3 * x5 - IdctC::W1 * x7;
+    s[0] = a0 + b0; s[1] = a1 + b1; s[2] = a2 + b2; s[3] = a3 + b3;
+    d[0] = a0 - b0; d[1] = a1 - b1; d[2] = a2 - b2; d[3] = a3 - b3;
+}
+
+// in : c[32], word 4*r+i = coefficient (r,2i) in the low half, (r,2i+1) in the high half
+// out: o[16], words 2*r and 2*r+1 = the 8 pixels of row r, column 0 in the lowest byte
+AMV_HD void idct_put_block(const uint32_t (&c)[32], uint32_t (&o)[16]) {
+    int m[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t w0 = c[4 * r], w1 = c[4 * r + 1], w2 = c[4 * r + 2], w3 = c[4 * r + 3];
+        const int x0 = sext16((int)w0), x1 = (int)w0 >> 16;
+        const int x2 = sext16((int)w1), x3 = (int)w1 >> 16;
+        const int x4 = sext16((int)w2), x5 = (int)w2 >> 16;
+        const int x6 = sext16((int)w3), x7 = (int)w3 >> 16;
+        // DC-only rows take (row[0] << 3) & 0xffff for every output (:98-103); feeding
+        // that value, pre-shifted, as the DC term makes the general path produce it.
+        const bool dc_only = ((w0 >> 16) | w1 | w2 | w3) == 0;
+        const int e0 = dc_only ? (int)((uint32_t)sext16((int)((uint32_t)x0 << 3)) << 11)
+                               : IdctC::W4 * x0 + (1 << 10);
+        int s[4], d[4];
+        idct_1d(e0, x1, x2, x3, x4, x5, x6, x7, s, d);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            m[8 * r + i]     = sext16(s[i] >> 11);
+            m[8 * r + 7 - i] = sext16(d[i] >> 11);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i] = 0;
+#pragma unroll
+    for (int col = 0; col < 8; col++) {
+        int s[4], d[4];
+        idct_1d(IdctC::W4 * (m[col] + 32), m[8 + col], m[16 + col], m[24 + col], m[32 + col], m[40 + col],
+                m[48 + col], m[56 + col], s, d);
+        const int sh = 8 * (col & 3), wsel = col >> 2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            o[2 * i + wsel]       += (uint32_t)clamp_u8(s[i] >> 20) << sh;
+            o[2 * (7 - i) + wsel] += (uint32_t)clamp_u8(d[i] >> 20) << sh;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ fdct_islow
+// ff_jpeg_fdct_islow (jfdctint.c:184-341): CONST_BITS 13, PASS1_BITS 4.  The
+// reference evaluates in 64-bit temporaries and stores int16 between the passes;
+// for 8-bit pixel input every stored value fits int16 and every pre-shift sum fits
+// int32 (checked exhaustively over the extremal patterns in tests/), so 32-bit
+// wrap-around arithmetic reproduces it exactly.
+struct FdctC {
+    enum { C0_298 = 2446, C0_390 = 3196, C0_541 = 4433, C0_765 = 6270, C0_899 = 7373, C1_175 = 9633,
+           C1_501 = 12299, C1_847 = 15137, C1_961 = 16069, C2_053 = 16819, C2_562 = 20995, C3_072 = 25172 };
+};
+
+// One 8-point pass.  ROW: outputs 0/4 are shifted up by 4, the others descaled by 9;
+// column pass: 0/4 descaled by 4, the others by 17.
+template <bool ROW>
+AMV_HD void fdct_1d(int &v0, int &v1, int &v2, int &v3, int &v4, int &v5, int &v6, int &v7) {
+    constexpr int SH = ROW ? 9 : 17;
+    constexpr int RND = 1 << (SH - 1);
+    const int p0 = v0 + v7, m0 = v0 - v7, p1 = v1 + v6, m1 = v1 - v6;
+    const int p2 = v2 + v5, m2 = v2 - v5, p3 = v3 + v4, m3 = v3 - v4;
+    const int q0 = p0 + p3, q3 = p0 - p3, q1 = p1 + p2, q2 = p1 - p2;
+    if (ROW) { v0 = (q0 + q1) << 4; v4 = (q0 - q1) << 4; }
+    else     { v0 = (q0 + q1 + 8) >> 4; v4 = (q0 - q1 + 8) >> 4; }
+    const int r = (q2 + q3) * FdctC::C0_541 + RND;
+    v2 = (r + q3 * FdctC::C0_765) >> SH;
+    v6 = (r - q2 * FdctC::C1_847) >> SH;
+    const int sc = m3 + m1, sd = m2 + m0;
+    const int z = (sc + sd) * FdctC::C1_175 + RND;
+    const int a = (m3 + m0) * -FdctC::C0_899, b = (m2 + m1) * -FdctC::C2_562;
+    const int c = sc * -FdctC::C1_961 + z, d = sd * -FdctC::C0_390 + z;
+    v7 = (m3 * FdctC::C0_298 + a + c) >> SH;
+    v5 = (m2 * FdctC::C2_053 + b + d) >> SH;
+    v3 = (m1 * FdctC::C3_072 + b + c) >> SH;
+    v1 = (m0 * FdctC::C1_501 + a + d) >> SH;
+}
+
+// in place on 64 ints (raster order), pixels in -> coefficients out
+AMV_HD void fdct_block(int (&b)[64]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        fdct_1d<true>(b[8 * r], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3], b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        fdct_1d<false>(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+}
+
+// ------------------------------------------------------------------ quantiser
+// dct_quantize_c intra, bias 0 (mpegvideo_enc.c:3647-3725, :492-496):
+//   DC: (b + 32) / 64 (C division);  AC: sign(b) * ((|b| * qmat) >> 22), clipped to +-1023
+// with qmat = (1<<22) / (8*M).  qm10 = qmat << 10 turns the shift into a high-half multiply.
+AMV_HD int quant_dc(int b) { return (b + 32) / 64; }
+AMV_HD int quant_ac(int b, uint32_t qm10) {
+    const uint32_t a = (uint32_t)(b < 0 ? -b : b);
+#if defined(__CUDA_ARCH__)
+    int q = (int)__umulhi(a, qm10);
+#else
+    int q = (int)(((uint64_t)a * qm10) >> 32);
+#endif
+    q = q > 1023 ? 1023 : q;
+    return b < 0 ? -q : q;
+}
+
+}  // namespace amv

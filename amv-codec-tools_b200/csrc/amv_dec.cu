@@ -1,0 +1,457 @@
+// amv_dec.cu -- AMV video decode kernels (sm_100a).
+//
+//   k_unstuff   : one CTA per packet; strips FF00 byte stuffing (mjpegdec.c:1137-1160 applied to
+//                 sp5xdec.c:75-88's `payload ++ FF D9`) into a 16-byte aligned scratch slot.
+//                 128-bit coalesced loads, ballot/popc + CTA scan for the compaction, shared-memory
+//                 staging so the scratch is written in 128-bit units.
+//   k_vlc_sync  : self-synchronising subsequence decode.  P lanes of a warp share a frame, each
+//                 walks its own subsequence from a guessed state; lanes hand their exit state to
+//                 the right neighbour with __shfl_up and the warp iterates until a __ballot shows
+//                 no lane's entry state changed.  A segmented shuffle scan then gives every lane
+//                 its first block index and DC predictors.
+//   k_decode    : every lane re-walks its (now exactly delimited) subsequence, writes dequantised
+//                 coefficients to a conflict-free shared-memory slot, runs simple_idct in registers
+//                 and stores the 8x8 pixels bottom-up (mjpegdec.c:672-677,710-716).
+#include "amv_common.cuh"
+#include "amv_tables.cuh"
+#include "amv_dct.cuh"
+#include "amv_vlc.cuh"
+#include "amv_kernels.h"
+
+namespace amv {
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of (aligned) sizes -> offsets, single CTA (n is at most a few million; the scan
+// is a vanishing fraction of the work it feeds)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t *__restrict__ size, int n, uint32_t align_mask,
+                                                     uint32_t pad, uint64_t *__restrict__ off,
+                                                     uint64_t *__restrict__ carry_io /* running total in/out, may be NULL */) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t running;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = carry_io ? *carry_io : 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        uint64_t v = 0;
+        if (i < n) v = (uint64_t)((size[i] + align_mask) & ~align_mask) + pad;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t w = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += t;
+            }
+            warp_tot[lane] = w;          // inclusive over warps
+        }
+        __syncthreads();
+        const uint64_t before = running + (wid ? warp_tot[wid - 1] : 0) + (inc - v);
+        if (i < n) off[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && carry_io) *carry_io = running;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_unstuff
+// ------------------------------------------------------------------------------------------------
+constexpr int kUnstuffThreads = 256;
+constexpr int kUnstuffTile = kUnstuffThreads * 16;
+
+__global__ void __launch_bounds__(kUnstuffThreads)
+k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t *__restrict__ pkt_off,
+          const uint32_t *__restrict__ pkt_size, int n, uint8_t *__restrict__ scratch,
+          const uint64_t *__restrict__ slot_off, uint64_t scratch_bytes, uint32_t *__restrict__ scan_len,
+          int32_t *__restrict__ status) {
+    __shared__ __align__(16) uint8_t stage[kUnstuffTile + 32];
+    __shared__ uint32_t warp_cnt[kUnstuffThreads / 32];
+    __shared__ uint32_t s_first_term;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        const uint64_t off = pkt_off[f];
+        const uint32_t size = pkt_size[f];
+        const uint64_t slot = slot_off[f];
+        int32_t st = 0;
+        if (off + size > pkts_bytes || slot + ((size + 15u) & ~15u) + 32u > scratch_bytes) {
+            if (tid == 0) { scan_len[f] = 0; status[f] = AMV_ST_RANGE; }
+            continue;
+        }
+        if (size < 4) st |= AMV_ST_SHORT;
+        // virtual stream: payload bytes pkt[2 .. size-2) followed by FF D9
+        const uint32_t npay = size >= 4 ? size - 4 : 0;
+        const uint32_t V = npay + 2;
+        const uint8_t *pay = pkts + off + 2;
+        const uint32_t mis = (uint32_t)((uintptr_t)pay & 15);       // bytes before the payload in its first 16 B unit
+        const uint8_t *abase = pay - mis;
+        uint8_t *dst = scratch + slot;
+        uint32_t carry = 0;       // bytes waiting in stage[0..carry)
+        uint32_t written = 0;     // bytes already flushed to dst
+        bool done = false;
+
+        for (uint32_t t0 = 0; !done; t0 += kUnstuffTile) {
+            // this thread's 16 bytes: virtual indices i0 .. i0+15, i = (t0 + tid*16 + b) - mis
+            const int64_t i0 = (int64_t)t0 + tid * 16 - mis;
+            uint32_t wv[4] = { 0, 0, 0, 0 };
+            if (i0 + 16 > 0 && i0 < (int64_t)npay) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(abase + t0 + tid * 16);
+                wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+            }
+            // previous byte (virtual index i0-1)
+            uint32_t prev = 0;
+            if (i0 - 1 >= 0 && i0 - 1 < (int64_t)npay) prev = pay[i0 - 1];
+            else if (i0 - 1 == (int64_t)npay) prev = 0xff;
+            uint32_t keep = 0, term = 0;
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const int64_t i = i0 + b;
+                uint32_t x = (wv[b >> 2] >> (8 * (b & 3))) & 0xff;
+                if (i == (int64_t)npay) x = 0xff;              // appended EOI
+                else if (i == (int64_t)npay + 1) x = 0xd9;
+                const bool valid = i >= 0 && i < (int64_t)V;
+                const bool after_ff = prev == 0xff && i > 0;   // the byte before the payload is the SOS header's 00
+                const bool drop = after_ff && (x == 0x00 || x == 0xff);
+                const bool is_term = after_ff && !(x == 0x00 || x == 0xff || (x >= 0xd0 && x <= 0xd7));
+                if (valid && !drop) keep |= 1u << b;
+                if (valid && is_term) term |= 1u << b;
+                // patch the byte in place so the emit loop below sees the virtual FF
+                if (i == (int64_t)npay) wv[b >> 2] |= 0xffu << (8 * (b & 3));
+                prev = x;
+            }
+            // first terminator in this tile (virtual index relative to the tile)
+            if (tid == 0) s_first_term = 0xffffffffu;
+            __syncthreads();
+            if (term) atomicMin(&s_first_term, (uint32_t)(tid * 16 + (__ffs(term) - 1)));
+            __syncthreads();
+            const uint32_t ft = s_first_term;
+            if (ft != 0xffffffffu) {
+                // keep only bytes strictly before the terminator
+                const int rel = (int)ft - tid * 16;
+                if (rel <= 0) keep = 0; else if (rel < 16) keep &= (1u << rel) - 1u;
+                done = true;
+                // the terminator must be the appended D9, anything earlier is a marker inside the scan
+                if ((int64_t)t0 + ft - mis != (int64_t)V - 1) st |= AMV_ST_MARKER;
+            } else if ((int64_t)t0 + kUnstuffTile - mis >= (int64_t)V) {
+                done = true;   // unreachable (D9 always terminates), kept for safety
+            }
+            // CTA exclusive scan of kept counts
+            const uint32_t cnt = __popc(keep);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) warp_cnt[wid] = inc;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kUnstuffThreads / 32; w++) {
+                const uint32_t c = warp_cnt[w];
+                if (w < wid) wbase += c;
+                total += c;
+            }
+            uint32_t pos = carry + wbase + inc - cnt;
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                if (keep & (1u << b)) stage[pos++] = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
+            }
+            __syncthreads();
+            uint32_t have = carry + total;
+            if (done) {   // zero pad so the readers see zeros past the data, and flush everything
+                for (uint32_t i = have + tid; i < ((have + 15u) & ~15u) + 16u; i += kUnstuffThreads) stage[i] = 0;
+                __syncthreads();
+            }
+            const uint32_t flush = done ? (((have + 15u) & ~15u) + 16u) : (have & ~15u);
+            for (uint32_t i = tid * 16; i < flush; i += kUnstuffThreads * 16)
+                *reinterpret_cast<uint4 *>(dst + written + i) = *reinterpret_cast<const uint4 *>(stage + i);
+            __syncthreads();
+            if (!done) {
+                const uint32_t rem = have - flush;
+                uint8_t keepb = 0;
+                if (tid < rem) keepb = stage[flush + tid];
+                __syncthreads();
+                if (tid < rem) stage[tid] = keepb;
+                carry = rem;
+                written += flush;
+                __syncthreads();
+            } else {
+                written += have;     // logical length
+            }
+        }
+        if (tid == 0) { scan_len[f] = written; status[f] = st; }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory tables for the VLC kernels
+// ------------------------------------------------------------------------------------------------
+struct DecTablesDev {
+    VlcTables vlc;
+    DequantTables dq;
+};
+__device__ DecTablesDev g_dec_tables;
+
+struct DecSmem {
+    uint16_t lut[kVlcMaxEntries];
+    uint32_t zq[2][64];
+    int      base[4];
+};
+
+__device__ __forceinline__ void load_dec_tables(DecSmem &s) {
+    for (int i = threadIdx.x; i < kVlcMaxEntries / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s.lut)[i] = reinterpret_cast<const uint32_t *>(g_dec_tables.vlc.e)[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&s.zq[0][0])[i] = (&g_dec_tables.dq.zq[0][0])[i];
+    if (threadIdx.x < 4) s.base[threadIdx.x] = g_dec_tables.vlc.base[threadIdx.x];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_vlc_sync
+// ------------------------------------------------------------------------------------------------
+struct NoPut { __device__ __forceinline__ void operator()(int, int) const {} };
+
+__device__ __forceinline__ void walk_subsequence(const uint32_t *words, uint32_t nwords, uint32_t start_bit,
+                                                 uint32_t start_phase, uint32_t end_bit, const DecSmem &T,
+                                                 LaneExit &ex) {
+    BitReader br;
+    br.init(words, nwords, start_bit);
+    uint32_t phase = start_phase, nb = 0;
+    int dc0 = 0, dc1 = 0, dc2 = 0;
+    while (br.bitpos() < end_bit) {
+        int diff;
+        decode_block<false>(br, T.lut, T.base, phase >= 4 ? 1 : 0, diff, NoPut());
+        if (phase < 4) dc0 += diff; else if (phase == 4) dc1 += diff; else dc2 += diff;
+        phase = phase == 5 ? 0 : phase + 1;
+        nb++;
+    }
+    ex.bitpos = br.bitpos(); ex.phase = phase; ex.nblocks = nb;
+    ex.dc[0] = dc0; ex.dc[1] = dc1; ex.dc[2] = dc2;
+}
+
+constexpr int kVlcThreads = 128;
+
+__global__ void __launch_bounds__(kVlcThreads)
+k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
+           const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
+           uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */) {
+    __shared__ DecSmem T;
+    load_dec_tables(T);
+    const int P = 1 << log2p;
+    const int lane = threadIdx.x & 31;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (int)(gt >> log2p);
+    const int p = (int)(gt & (P - 1));
+    const bool active = f < n;
+
+    const uint32_t *words = nullptr;
+    uint32_t nwords = 0, end_bit = 0, total_bits = 0, L = 0;
+    if (active) {
+        const uint32_t U = scan_len[f];
+        words = reinterpret_cast<const uint32_t *>(scratch + slot_off[f]);
+        nwords = (U + 3) >> 2;
+        total_bits = U * 8u;
+        L = (((total_bits + P - 1) >> log2p) + 31u) & ~31u;
+        const uint64_t e = (uint64_t)(p + 1) * L;
+        end_bit = e < total_bits ? (uint32_t)e : total_bits;
+    }
+    uint32_t start_bit = active ? (uint32_t)min((uint64_t)p * L, (uint64_t)total_bits) : 0u, start_phase = 0;
+    LaneExit ex = { 0, 0, 0, { 0, 0, 0 } };
+    if (active) walk_subsequence(words, nwords, start_bit, start_phase, end_bit, T, ex);
+
+    uint32_t rounds = 1;
+    for (int r = 0; r < P; r++) {
+        // entry state = left neighbour's exit state (lane 0 of a frame starts the scan)
+        uint32_t nbit = __shfl_up_sync(0xffffffffu, ex.bitpos, 1);
+        uint32_t nph = __shfl_up_sync(0xffffffffu, ex.phase, 1);
+        if (p == 0) { nbit = 0; nph = 0; }
+        const bool changed = active && (nbit != start_bit || nph != start_phase);
+        if (!__ballot_sync(0xffffffffu, changed)) break;
+        rounds++;
+        if (changed) {
+            start_bit = nbit; start_phase = nph;
+            walk_subsequence(words, nwords, start_bit, start_phase, end_bit, T, ex);
+        }
+    }
+    // segmented (width P) exclusive scans: first block index and DC difference sums
+    uint32_t nb_inc = ex.nblocks;
+    int d0 = ex.dc[0], d1 = ex.dc[1], d2 = ex.dc[2];
+    for (int d = 1; d < P; d <<= 1) {
+        const uint32_t tn = __shfl_up_sync(0xffffffffu, nb_inc, d);
+        const int t0 = __shfl_up_sync(0xffffffffu, d0, d), t1 = __shfl_up_sync(0xffffffffu, d1, d),
+                  t2 = __shfl_up_sync(0xffffffffu, d2, d);
+        if (p >= d) { nb_inc += tn; d0 += t0; d1 += t1; d2 += t2; }
+    }
+    if (active) {
+        LaneStart s;
+        s.bitpos = start_bit;
+        s.first_block = nb_inc - ex.nblocks;
+        s.nblocks = ex.nblocks;
+        const int q0l = (int)(T.zq[0][0] >> 8), q0c = (int)(T.zq[1][0] >> 8);
+        s.pred[0] = 1024 + q0l * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
+        s.pred[1] = 1024 + q0c * (d1 - ex.dc[1]);
+        s.pred[2] = 1024 + q0c * (d2 - ex.dc[2]);
+        starts[gt] = s;
+    }
+    if (rounds_out && lane == 0) atomicMax(rounds_out, rounds);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_decode
+// ------------------------------------------------------------------------------------------------
+struct SlotPut {
+    uint32_t *slot;          // this lane's column of the warp's coefficient tile: word w at slot[w*32]
+    const uint32_t *zq;      // zq[tq]
+    __device__ __forceinline__ void operator()(int k, int v) const {
+        const uint32_t e = zq[k];
+        const int j = e & 63;
+        const int val = v * (int)(e >> 8);                 // level * quant_matrix[j], stored as int16 (mjpegdec.c:420,428)
+        reinterpret_cast<int16_t *>(slot + (j >> 1) * 32)[j & 1] = (int16_t)val;
+    }
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kVlcThreads)
+k_decode(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
+         const uint32_t *__restrict__ scan_len, int n, int log2p, const LaneStart *__restrict__ starts,
+         Geom g, uint8_t *__restrict__ py, uint8_t *__restrict__ pu, uint8_t *__restrict__ pv,
+         int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *__restrict__ status) {
+    __shared__ DecSmem T;
+    __shared__ uint32_t tile[kVlcThreads / 32][32 * 32];
+    load_dec_tables(T);
+    const int P = 1 << log2p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (int)(gt >> log2p);
+    const int p = (int)(gt & (P - 1));
+    if (f >= n) return;
+
+    const uint32_t U = scan_len[f];
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(scratch + slot_off[f]);
+    uint32_t first = 0, count = g.nblk, bit = 0;
+    int pred0 = 1024, pred1 = 1024, pred2 = 1024;       // last_dc per component (mjpegdec.c:805-806)
+    uint32_t st = 0;
+    if (log2p) {
+        const LaneStart s = starts[gt];
+        first = s.first_block; bit = s.bitpos; count = s.nblocks;
+        pred0 = s.pred[0]; pred1 = s.pred[1]; pred2 = s.pred[2];
+        if (first >= (uint32_t)g.nblk) count = 0;
+        else if (first + count > (uint32_t)g.nblk) count = g.nblk - first;
+        if (p == P - 1 && first + s.nblocks < (uint32_t)g.nblk) {
+            // the scan ran out before the picture was complete: keep decoding (zeros) like a
+            // sequential reader would, and say so
+            count = g.nblk - first;
+            st |= AMV_ST_OVERRUN;
+        }
+    }
+    uint32_t *slot = &tile[wid][lane];
+#pragma unroll
+    for (int i = 0; i < 32; i++) slot[i * 32] = 0;
+
+    BitReader br;
+    br.init(words, (U + 3) >> 2, bit);
+    uint32_t mb = first / 6u;
+    int b = (int)(first - mb * 6u);
+    int mx = (int)(mb % (uint32_t)g.mbw), my = (int)(mb / (uint32_t)g.mbw);
+    uint8_t *fy = py + (uint64_t)f * fs_y, *fu = pu + (uint64_t)f * fs_c, *fv = pv + (uint64_t)f * fs_c;
+    const int q0l = (int)(T.zq[0][0] >> 8), q0c = (int)(T.zq[1][0] >> 8);
+
+    for (uint32_t i = 0; i < count; i++) {
+        const int tq = b >= 4 ? 1 : 0;
+        const int comp = b < 4 ? 0 : b - 3;
+        int diff;
+        SlotPut put = { slot, T.zq[tq] };
+        st |= decode_block<true>(br, T.lut, T.base, tq, diff, put);
+        int pr;
+        if (comp == 0) pr = (pred0 += diff * q0l);
+        else if (comp == 1) pr = (pred1 += diff * q0c);
+        else pr = (pred2 += diff * q0c);
+        reinterpret_cast<int16_t *>(slot)[0] = (int16_t)pr;
+
+        uint32_t c[32], o[16];
+#pragma unroll
+        for (int k = 0; k < 32; k++) { c[k] = slot[k * 32]; slot[k * 32] = 0; }
+        idct_put_block(c, o);
+
+        uint8_t *pl = comp == 0 ? fy : (comp == 1 ? fu : fv);
+        const int ls = comp ? ls_c : ls_y;
+        const int vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
+        const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
+        const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+#pragma unroll
+        for (int yy = 0; yy < 8; yy++) {
+            const int row = r0 - (by + yy);
+            if (row < 0 || row >= vh) continue;
+            uint8_t *d = pl + (int64_t)row * ls + bx;
+            if (FAST) {
+                *reinterpret_cast<uint2 *>(d) = make_uint2(o[2 * yy], o[2 * yy + 1]);
+            } else {
+#pragma unroll
+                for (int xx = 0; xx < 8; xx++)
+                    if (bx + xx < vw) d[xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
+            }
+        }
+        if (++b == 6) { b = 0; if (++mx == g.mbw) { mx = 0; my++; } }
+    }
+    if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;     // lanes that own no block just pass through
+    if (st) atomicOr(&status[f], (int32_t)st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t upload_dec_tables(cudaStream_t s) {
+    static DecTablesDev h;      // built once; identical for every context
+    static bool built = false;
+    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); built = true; }
+    return cudaMemcpyToSymbolAsync(g_dec_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+}
+
+void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_t pad, uint64_t *off,
+                       uint64_t *carry_io, cudaStream_t s) {
+    k_scan_sizes<<<1, 1024, 0, s>>>(size, n, align_mask, pad, off, carry_io);
+}
+
+void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                    uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
+                    int32_t *status, cudaStream_t s) {
+    const int grid = n < kNumSMs * 8 ? n : kNumSMs * 8;
+    k_unstuff<<<grid, kUnstuffThreads, 0, s>>>(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes,
+                                               scan_len, status);
+}
+
+void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
+                     LaneStart *starts, uint32_t *rounds_out, cudaStream_t s) {
+    const int64_t lanes = (int64_t)n << log2p;
+    const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
+    k_vlc_sync<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out);
+}
+
+void launch_decode(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
+                   const LaneStart *starts, const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
+                   uint64_t fs_y, uint64_t fs_c, int32_t *status, cudaStream_t s) {
+    const int64_t lanes = (int64_t)n << log2p;
+    const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
+    const bool fast = (g.w % 16 == 0) &&
+                      ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
+    if (fast)
+        k_decode<true><<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c,
+                                                    fs_y, fs_c, status);
+    else
+        k_decode<false><<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c,
+                                                     fs_y, fs_c, status);
+}
+
+}  // namespace amv

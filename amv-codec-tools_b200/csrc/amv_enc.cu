@@ -1,0 +1,388 @@
+// amv_enc.cu -- AMV video encode kernel (sm_100a).
+//
+// One CTA encodes one frame at a time (persistent, grid-stride over the batch) so that the two
+// serial quantities of a frame -- the running bit position of the entropy-coded segment and the
+// count of stuffed FF bytes -- never leave the CTA: no inter-CTA look-back, no scratch traffic,
+// the packet is written once.  A frame is cut into segments of 16 macroblocks = 96 blocks =
+// 96 threads (3 warps: two luma warps, one chroma warp, so a warp never mixes Huffman tables):
+//
+//   A  thread-per-block: 128-bit/64-bit coalesced row loads of the bottom-up picture
+//      (amv_encode_picture mjpegenc.c:454-472 + edge replication mpegvideo.c:1416-1470),
+//      fdct_islow and the truncating quantiser in registers (jfdctint.c:261, mpegvideo_enc.c:3647)
+//   B  pass 1: Huffman code LENGTHS per block (encode_block mjpegenc.c:379-435)
+//   C  prefix scan of the 96 lengths in bitstream order (warp shuffles)
+//   D  pass 2: warp-cooperative bit packer -- every thread ORs its codes into the segment's
+//      shared-memory bit buffer at its scanned bit offset
+//   E  FF00 stuffing (escape_FF mjpegenc.c:282-336) as a second scan over FF counts, bytes
+//      stored straight to the packet slot; SOI/EOI framing and 1-bit padding
+//      (ff_mjpeg_encode_stuffing :338-343, trailer :345-355) at frame start / end.
+#include "amv_common.cuh"
+#include "amv_tables.cuh"
+#include "amv_dct.cuh"
+#include "amv_kernels.h"
+
+namespace amv {
+
+constexpr int kEncThreads = 96;
+constexpr int kSegMB = 16;
+// worst case: 96 blocks x (20-bit DC + 63 x 26-bit AC) = 159168 bits, + carry word + slack
+constexpr int kSegWords = (96 * (20 + 63 * 26) + 31) / 32 + 8;
+
+struct EncTablesDev {
+    EncHuffTables huff;
+    uint8_t zigzag[64];
+    uint8_t intra_base[64];
+};
+__device__ EncTablesDev g_enc_tables;
+
+struct EncSmem {
+    uint32_t huff[kEncHuffEntries];
+    uint32_t qm10[64];
+    uint32_t coef[32 * kEncThreads];   // word (k>>1)*96 + t : zigzag coefficients k, k+1 of thread t's block
+    uint32_t seg[kSegWords];
+    uint32_t lens[kEncThreads];        // bit length per block in bitstream order -> exclusive offsets
+    int      dcq[kEncThreads];         // quantised DC per block in bitstream order
+    int      carry_dc[3];              // last DC of each component from the previous segment
+    uint32_t warp_tot[4];
+    uint32_t seg_bits;                 // total bits of the segment
+    uint32_t overflow;
+};
+
+// MSB-first bit sink into the segment buffer.  First and last word of a block are shared with
+// the neighbouring blocks (atomicOr); the words in between belong to this thread alone.
+struct BitSink {
+    uint32_t *seg;
+    uint32_t widx;
+    uint64_t acc;
+    int fill;
+    bool first;
+    __device__ __forceinline__ void init(uint32_t *s, uint32_t bitpos) {
+        seg = s; widx = bitpos >> 5; fill = (int)(bitpos & 31); acc = 0; first = true;
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {     // len <= 27
+        acc |= (uint64_t)code << (64 - fill - len);
+        fill += len;
+        if (fill >= 32) {
+            const uint32_t w = (uint32_t)(acc >> 32);
+            if (first) { atomicOr(&seg[widx], w); first = false; } else seg[widx] = w;
+            widx++; acc <<= 32; fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (fill > 0) atomicOr(&seg[widx], (uint32_t)(acc >> 32));
+    }
+};
+
+__device__ __forceinline__ int bit_width(uint32_t v) { return 32 - __clz(v); }
+
+template <bool FAST>
+__global__ void __launch_bounds__(kEncThreads)
+k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
+         int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
+         uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
+         int32_t *__restrict__ status) {
+    __shared__ EncSmem S;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    for (int i = t; i < kEncHuffEntries; i += kEncThreads) S.huff[i] = g_enc_tables.huff.e[i];
+
+    // block role of this thread inside a segment
+    int mi, b;
+    if (wid < 2) { mi = lane >> 1; b = wid * 2 + (lane & 1); }
+    else         { mi = lane & 15; b = 4 + (lane >> 4); }
+    const int comp = b < 4 ? 0 : b - 3;
+    const int sigma = mi * 6 + b;                       // position in bitstream order
+    const int dc_tab = comp ? kEncDcChroma : kEncDcLuma, ac_tab = comp ? kEncAcChroma : kEncAcLuma;
+    const int total_mb = g.mbw * g.mbh;
+    // valid source extent: the reference copies w x h luma and (w>>1) x (h>>1) chroma (mpegvideo_enc.c:866-867)
+    const int vw = comp ? (g.w >> 1) : g.w, vh = comp ? (g.h >> 1) : g.h, r0 = comp ? g.c0 : g.y0;
+    const int ls = comp ? ls_c : ls_y;
+
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        const int qs = qscale ? qscale[f] : 2;
+        __syncthreads();
+        if (t < 64) {
+            // intra_matrix / q_intra_matrix for this frame (mpegvideo_enc.c:2866-2877, ff_convert_matrix :69-91)
+            int m = 8;
+            if (t) m = min(max(((int)g_enc_tables.intra_base[t] * qs) >> 3, 1), 255);
+            S.qm10[t] = ((1u << 22) / (uint32_t)(8 * m)) << 10;
+        }
+        if (t < 3) S.carry_dc[t] = 128;                 // last_dc init (mpegvideo_enc.c:2033-2036)
+        if (t == 0) { S.seg[0] = 0; S.overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0; }   // qscale domain: SURVEY 9.13
+        const uint8_t *pl = (comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c);
+        uint8_t *pkt = slots + (uint64_t)f * slot_stride;
+        uint32_t G = 2;                                 // bytes written so far (SOI)
+        uint32_t r = 0;                                 // carried bits sitting in seg[0]
+        if (t == 0 && pkt_cap >= 2) { pkt[0] = 0xff; pkt[1] = 0xd8; }
+        __syncthreads();
+
+        for (int m0 = 0; m0 < total_mb; m0 += kSegMB) {
+            const int nmb = min(kSegMB, total_mb - m0);
+            const bool active = mi < nmb;
+            const bool last_seg = m0 + kSegMB >= total_mb;
+            uint64_t mask = 0;          // non-zero AC positions (zigzag) of this block
+            int dc = 0;
+
+            // ---------------- A: load, FDCT, quantise
+            if (active) {
+                const int mb = m0 + mi;
+                const int mx = mb % g.mbw, my = mb / g.mbw;
+                const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
+                const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+                int v[64];
+#pragma unroll
+                for (int yy = 0; yy < 8; yy++) {
+                    const int Y = min(by + yy, vh - 1);                 // bottom edge replication
+                    const uint8_t *row = pl + (int64_t)(r0 - Y) * ls;
+                    if (FAST) {
+                        const uint2 q = *reinterpret_cast<const uint2 *>(row + bx);
+#pragma unroll
+                        for (int xx = 0; xx < 4; xx++) {
+                            v[yy * 8 + xx]     = (q.x >> (8 * xx)) & 0xff;
+                            v[yy * 8 + 4 + xx] = (q.y >> (8 * xx)) & 0xff;
+                        }
+                    } else {
+#pragma unroll
+                        for (int xx = 0; xx < 8; xx++) v[yy * 8 + xx] = row[min(bx + xx, vw - 1)];   // right edge replication
+                    }
+                }
+                fdct_block(v);
+                dc = quant_dc(v[0]);
+#pragma unroll
+                for (int k = 1; k < 64; k++) {
+                    const int j = zigzag_at(k);
+                    const int q = quant_ac(v[j], S.qm10[j]);
+                    v[j] = q;
+                    if (q) mask |= 1ull << k;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t lo = (uint32_t)v[zigzag_at(2 * i)] & 0xffffu;
+                    const uint32_t hi = (uint32_t)v[zigzag_at(2 * i + 1)] << 16;
+                    S.coef[i * kEncThreads + t] = lo | hi;
+                }
+                S.dcq[sigma] = dc;
+            }
+            __syncthreads();
+
+            // ---------------- B: pass 1, code lengths
+            int pred = 0;
+            uint32_t len = 0;
+            if (active) {
+                if (comp == 0) pred = (b > 0) ? S.dcq[sigma - 1] : (mi > 0 ? S.dcq[sigma - 3] : S.carry_dc[0]);
+                else           pred = mi > 0 ? S.dcq[sigma - 6] : S.carry_dc[comp];
+                const int diff = dc - pred;
+                const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
+                len = (S.huff[dc_tab + nb] & 31) + nb;
+                const uint32_t zrl_len = S.huff[ac_tab + 0xf0] & 31, eob_len = S.huff[ac_tab] & 31;
+                uint64_t m = mask;
+                int prevk = 0;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int run = k - prevk - 1;
+                    prevk = k;
+                    const int cv = (int)reinterpret_cast<const int16_t *>(&S.coef[(k >> 1) * kEncThreads + t])[k & 1];
+                    const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
+                    len += (run >> 4) * zrl_len + (S.huff[ac_tab + (((run & 15) << 4) | cb)] & 31) + cb;
+                }
+                if (prevk != 63) len += eob_len;            // EOB only if last_index < 63 (mjpegenc.c:432-434)
+            }
+            S.lens[sigma] = len;
+            __syncthreads();
+
+            // ---------------- C: exclusive scan of the 96 lengths (warp 0, 3 per lane)
+            if (wid == 0) {
+                const uint32_t a0 = S.lens[3 * lane], a1 = S.lens[3 * lane + 1], a2 = S.lens[3 * lane + 2];
+                uint32_t inc = a0 + a1 + a2;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += u;
+                }
+                const uint32_t ex = inc - (a0 + a1 + a2);
+                S.lens[3 * lane] = ex; S.lens[3 * lane + 1] = ex + a0; S.lens[3 * lane + 2] = ex + a0 + a1;
+                if (lane == 31) S.seg_bits = inc;
+            }
+            // DC predictors for the next segment (everyone has read the old ones before the last barrier)
+            if (active && mi == nmb - 1 && (b == 3 || b >= 4)) S.carry_dc[comp] = dc;
+            __syncthreads();
+            const uint32_t T = S.seg_bits;
+            uint32_t R = r + T;                              // bits in the buffer after this segment
+            // clear the words this segment will OR into (word 0 keeps the carried bits)
+            const uint32_t used_words = (R + 7 + 31) >> 5;
+            for (uint32_t i = 1 + t; i <= used_words; i += kEncThreads) S.seg[i] = 0;
+            __syncthreads();
+
+            // ---------------- D: pass 2, bit packing
+            if (active) {
+                BitSink bs;
+                bs.init(S.seg, r + S.lens[sigma]);
+                const int diff = dc - pred;
+                const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
+                {
+                    const uint32_t e = S.huff[dc_tab + nb];
+                    const uint32_t mant = (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u);
+                    bs.put(((e >> 5) << nb) | mant, (int)(e & 31) + nb);
+                }
+                const uint32_t ezrl = S.huff[ac_tab + 0xf0], eeob = S.huff[ac_tab];
+                uint64_t m = mask;
+                int prevk = 0;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    int run = k - prevk - 1;
+                    prevk = k;
+                    const int cv = (int)reinterpret_cast<const int16_t *>(&S.coef[(k >> 1) * kEncThreads + t])[k & 1];
+                    const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
+                    for (; run >= 16; run -= 16) bs.put(ezrl >> 5, (int)(ezrl & 31));
+                    const uint32_t e = S.huff[ac_tab + ((run << 4) | cb)];
+                    const uint32_t mant = (uint32_t)(cv + (cv >> 31)) & ((1u << cb) - 1u);
+                    bs.put(((e >> 5) << cb) | mant, (int)(e & 31) + cb);
+                }
+                if (prevk != 63) bs.put(eeob >> 5, (int)(eeob & 31));
+                bs.finish();
+            }
+            __syncthreads();
+            if (last_seg) {
+                // pad to a byte with ones (ff_mjpeg_encode_stuffing, mjpegenc.c:338-343)
+                const uint32_t pad = (0u - R) & 7u;
+                if (t == 0 && pad) S.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
+                R += pad;
+                __syncthreads();
+            }
+
+            // ---------------- E: stuffing + output of the complete bytes
+            const uint32_t B = last_seg ? (R >> 3) : ((R >> 5) << 2);     // bytes leaving the buffer now
+            const uint32_t nw = (B + 3) >> 2;
+            const uint32_t per = (nw + kEncThreads - 1) / kEncThreads;
+            const uint32_t w0 = min((uint32_t)t * per, nw), w1 = min(w0 + per, nw);
+            uint32_t ffc = 0;
+            for (uint32_t w = w0; w < w1; w++) {
+                const uint32_t v = S.seg[w];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (w * 4 + k < B && ((v >> (24 - 8 * k)) & 0xff) == 0xff) ffc++;
+            }
+            uint32_t inc = ffc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            if (lane == 31) S.warp_tot[wid] = inc;
+            __syncthreads();
+            const uint32_t wt0 = S.warp_tot[0], wt1 = S.warp_tot[1], wt2 = S.warp_tot[2];
+            const uint32_t ff_total = wt0 + wt1 + wt2;
+            const uint32_t ff_before = (wid > 0 ? wt0 : 0) + (wid > 1 ? wt1 : 0) + inc - ffc;
+            const bool fits = (uint64_t)G + B + ff_total + 2 <= pkt_cap && !S.overflow;
+            if (fits) {
+                uint8_t *o = pkt + G + w0 * 4 + ff_before;
+                for (uint32_t w = w0; w < w1; w++) {
+                    const uint32_t v = S.seg[w];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (w * 4 + k < B) {
+                            const uint8_t by = (uint8_t)(v >> (24 - 8 * k));
+                            *o++ = by;
+                            if (by == 0xff) *o++ = 0;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (t == 0) {
+                if (!fits && !S.overflow) S.overflow = AMV_ST_NOSPACE;
+                S.seg[0] = last_seg ? 0 : S.seg[R >> 5];        // carry the partial word
+            }
+            G += B + ff_total;
+            r = last_seg ? 0 : (R & 31);
+            __syncthreads();
+        }
+        if (t == 0) {
+            const uint32_t ovf = S.overflow;
+            if (!ovf) { pkt[G] = 0xff; pkt[G + 1] = 0xd9; }      // EOI (mjpegenc.c:354)
+            out_size[f] = ovf ? 0 : G + 2;
+            status[f] = (int32_t)ovf;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed layout: copy each packet from its slot to its scanned offset
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_compact(const uint8_t *__restrict__ slots, uint64_t slot_stride, const uint32_t *__restrict__ size,
+          const uint64_t *__restrict__ off, int n, uint8_t *__restrict__ out, uint64_t out_cap,
+          int32_t *__restrict__ status) {
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        const uint32_t sz = size[f];
+        const uint64_t o = off[f];
+        if (o + sz > out_cap) { if (threadIdx.x == 0) atomicOr(&status[f], AMV_ST_NOSPACE); continue; }
+        const uint8_t *src = slots + (uint64_t)f * slot_stride;
+        uint8_t *dst = out + o;
+        // head bytes up to 16-byte alignment of dst, then 128-bit stores fed by two aligned
+        // source loads realigned with byte permutes, then the tail
+        const uint32_t head = min(sz, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
+        if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+        const uint32_t body = (sz - head) & ~15u;
+        const uint32_t sh = head & 3;            // src is slot-aligned (>= 16 B): misalignment of src+head to 4 B
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(src + (head & ~3u));
+        for (uint32_t i = threadIdx.x * 16; i < body; i += blockDim.x * 16) {
+            const uint32_t *p = sw + (i >> 2);
+            const uint32_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = sh ? p[4] : 0;
+            uint4 q;
+            q.x = __funnelshift_r(a0, a1, 8 * sh); q.y = __funnelshift_r(a1, a2, 8 * sh);
+            q.z = __funnelshift_r(a2, a3, 8 * sh); q.w = __funnelshift_r(a3, a4, 8 * sh);
+            *reinterpret_cast<uint4 *>(dst + head + i) = q;
+        }
+        for (uint32_t i = head + body + threadIdx.x; i < sz; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+__global__ void k_slot_offsets(uint64_t *off, int n, uint64_t stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] = (uint64_t)i * stride;
+}
+
+// ------------------------------------------------------------------------------------------------
+cudaError_t upload_enc_tables(cudaStream_t s) {
+    static EncTablesDev h;
+    static bool built = false;
+    if (!built) {
+        build_enc_huff_tables(h.huff);
+        memcpy(h.zigzag, kZigzag, 64);
+        memcpy(h.intra_base, kEncIntraBase, 64);
+        built = true;
+    }
+    return cudaMemcpyToSymbolAsync(g_enc_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+}
+
+int encode_grid(int n) {
+    const int cap = kNumSMs * 6;      // 6 resident CTAs of 96 threads per SM (shared memory bound)
+    return n < cap ? (n < 1 ? 1 : n) : cap;
+}
+
+void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                   int n, const Geom &g, const int32_t *qscale, uint8_t *slots, uint64_t slot_stride, uint32_t pkt_cap,
+                   uint32_t *out_size, int32_t *status, cudaStream_t s) {
+    const bool fast = (g.w % 16 == 0) &&
+                      ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
+    if (fast)
+        k_encode<true><<<encode_grid(n), kEncThreads, 0, s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                              slot_stride, pkt_cap, out_size, status);
+    else
+        k_encode<false><<<encode_grid(n), kEncThreads, 0, s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                               slot_stride, pkt_cap, out_size, status);
+}
+
+void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
+                    uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s) {
+    const int grid = n < kNumSMs * 8 ? (n < 1 ? 1 : n) : kNumSMs * 8;
+    k_compact<<<grid, 256, 0, s>>>(slots, slot_stride, size, off, n, out, out_cap, status);
+}
+
+void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, cudaStream_t s) {
+    k_slot_offsets<<<(n + 255) / 256, 256, 0, s>>>(off, n, stride);
+}
+
+}  // namespace amv

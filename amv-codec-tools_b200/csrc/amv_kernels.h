@@ -1,0 +1,48 @@
+// amv_kernels.h -- internal launcher interface between the kernels (*.cu) and the C ABI (amv_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "amv_common.cuh"
+
+namespace amv {
+
+// entry state of one decode lane, produced by k_vlc_sync and consumed by k_decode
+struct LaneStart {
+    uint32_t bitpos;        // where the lane's first block starts in the un-stuffed scan
+    uint32_t first_block;   // index of that block in bitstream order
+    uint32_t nblocks;       // blocks the lane owns
+    int      pred[3];       // DC predictors (Y, Cb, Cr) before that block
+};
+
+// ---- decode
+cudaError_t upload_dec_tables(cudaStream_t s);
+void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_t pad, uint64_t *off,
+                       uint64_t *carry_io, cudaStream_t s);
+void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                    uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
+                    int32_t *status, cudaStream_t s);
+void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
+                     LaneStart *starts, uint32_t *rounds_out, cudaStream_t s);
+void launch_decode(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
+                   const LaneStart *starts, const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
+                   uint64_t fs_y, uint64_t fs_c, int32_t *status, cudaStream_t s);
+
+// ---- encode
+cudaError_t upload_enc_tables(cudaStream_t s);
+int  encode_grid(int n);
+void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                   int n, const Geom &g, const int32_t *qscale, uint8_t *slots, uint64_t slot_stride, uint32_t pkt_cap,
+                   uint32_t *out_size, int32_t *status, cudaStream_t s);
+void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
+                    uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s);
+void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, cudaStream_t s);
+
+// ---- adpcm
+cudaError_t upload_adpcm_tables(cudaStream_t s);
+void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *off, const uint32_t *size, int n,
+                         int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s);
+void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
+                         const uint32_t *first_chunk, int nstreams, const int16_t *step_in, int16_t *step_out,
+                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, cudaStream_t s);
+
+}  // namespace amv

@@ -1,0 +1,187 @@
+// amv_tables.cuh -- the fixed tables of the AMV codec path and the host-side
+// builders that turn them into the lookup structures the kernels stage in
+// shared memory.  Values are the format's (JPEG Annex K.3 Huffman specs, the
+// AMV decoder's two quantiser tables, MPEG-1 intra matrix, IMA step sizes);
+// reference locations are cited per table.  Layouts are ours.
+#pragma once
+#include "amv_common.cuh"
+#include <string.h>
+
+namespace amv {
+
+// zigzag scan position -> raster index (dsputil.c:50-59)
+static const uint8_t kZigzag[64] = {
+     0,  1,  8, 16,  9,  2,  3, 10, 17, 24, 32, 25, 18, 11,  4,  5,
+    12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+    58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+
+// same table, usable with compile-time indices inside fully unrolled device loops
+AMV_HD constexpr int zigzag_at(int k) {
+    constexpr uint8_t t[64] = {
+         0,  1,  8, 16,  9,  2,  3, 10, 17, 24, 32, 25, 18, 11,  4,  5,
+        12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
+        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+        58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+    return t[k];
+}
+
+// Decoder quantisers in zigzag order: sp5x_quant_table[10] / [11] (sp5x.h:187-195),
+// selected by sp5xdec.c:40,60-61.
+static const uint8_t kDecQuant[2][64] = {
+  { 13,  9, 10, 11, 10,  8, 13, 11, 10, 11, 14, 14, 13, 15, 19, 32,
+    21, 19, 18, 18, 19, 39, 28, 30, 23, 32, 46, 41, 49, 48, 46, 41,
+    45, 44, 51, 58, 74, 62, 51, 54, 70, 55, 44, 45, 64, 87, 65, 70,
+    76, 78, 82, 83, 82, 50, 62, 90, 97, 90, 80, 96, 74, 81, 82, 79 },
+  { 14, 14, 14, 19, 17, 19, 38, 21, 21, 38, 79, 53, 45, 53, 79, 79,
+    79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79,
+    79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79,
+    79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79 } };
+
+// Encoder matrix base, raster order: ff_mpeg1_default_intra_matrix (mpeg12data.c:30-39)
+static const uint8_t kEncIntraBase[64] = {
+     8, 16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37,
+    19, 22, 26, 27, 29, 34, 34, 38, 22, 22, 26, 27, 29, 34, 37, 40,
+    22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32, 35, 40, 48, 58,
+    26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83 };
+
+// Huffman specs (mjpeg.c:65-126): table order DC-luma, DC-chroma, AC-luma, AC-chroma
+static const uint8_t kHuffCount[4][16] = {
+    { 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0 },
+    { 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0 },
+    { 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 125 },
+    { 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 119 } };
+static const uint8_t kHuffSymDC[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
+static const uint8_t kHuffSymACLuma[162] = {
+    0x01,0x02,0x03,0x00,0x04,0x11,0x05,0x12,0x21,0x31,0x41,0x06,0x13,0x51,0x61,0x07,0x22,0x71,
+    0x14,0x32,0x81,0x91,0xa1,0x08,0x23,0x42,0xb1,0xc1,0x15,0x52,0xd1,0xf0,0x24,0x33,0x62,0x72,
+    0x82,0x09,0x0a,0x16,0x17,0x18,0x19,0x1a,0x25,0x26,0x27,0x28,0x29,0x2a,0x34,0x35,0x36,0x37,
+    0x38,0x39,0x3a,0x43,0x44,0x45,0x46,0x47,0x48,0x49,0x4a,0x53,0x54,0x55,0x56,0x57,0x58,0x59,
+    0x5a,0x63,0x64,0x65,0x66,0x67,0x68,0x69,0x6a,0x73,0x74,0x75,0x76,0x77,0x78,0x79,0x7a,0x83,
+    0x84,0x85,0x86,0x87,0x88,0x89,0x8a,0x92,0x93,0x94,0x95,0x96,0x97,0x98,0x99,0x9a,0xa2,0xa3,
+    0xa4,0xa5,0xa6,0xa7,0xa8,0xa9,0xaa,0xb2,0xb3,0xb4,0xb5,0xb6,0xb7,0xb8,0xb9,0xba,0xc2,0xc3,
+    0xc4,0xc5,0xc6,0xc7,0xc8,0xc9,0xca,0xd2,0xd3,0xd4,0xd5,0xd6,0xd7,0xd8,0xd9,0xda,0xe1,0xe2,
+    0xe3,0xe4,0xe5,0xe6,0xe7,0xe8,0xe9,0xea,0xf1,0xf2,0xf3,0xf4,0xf5,0xf6,0xf7,0xf8,0xf9,0xfa };
+static const uint8_t kHuffSymACChroma[162] = {
+    0x00,0x01,0x02,0x03,0x11,0x04,0x05,0x21,0x31,0x06,0x12,0x41,0x51,0x07,0x61,0x71,0x13,0x22,
+    0x32,0x81,0x08,0x14,0x42,0x91,0xa1,0xb1,0xc1,0x09,0x23,0x33,0x52,0xf0,0x15,0x62,0x72,0xd1,
+    0x0a,0x16,0x24,0x34,0xe1,0x25,0xf1,0x17,0x18,0x19,0x1a,0x26,0x27,0x28,0x29,0x2a,0x35,0x36,
+    0x37,0x38,0x39,0x3a,0x43,0x44,0x45,0x46,0x47,0x48,0x49,0x4a,0x53,0x54,0x55,0x56,0x57,0x58,
+    0x59,0x5a,0x63,0x64,0x65,0x66,0x67,0x68,0x69,0x6a,0x73,0x74,0x75,0x76,0x77,0x78,0x79,0x7a,
+    0x82,0x83,0x84,0x85,0x86,0x87,0x88,0x89,0x8a,0x92,0x93,0x94,0x95,0x96,0x97,0x98,0x99,0x9a,
+    0xa2,0xa3,0xa4,0xa5,0xa6,0xa7,0xa8,0xa9,0xaa,0xb2,0xb3,0xb4,0xb5,0xb6,0xb7,0xb8,0xb9,0xba,
+    0xc2,0xc3,0xc4,0xc5,0xc6,0xc7,0xc8,0xc9,0xca,0xd2,0xd3,0xd4,0xd5,0xd6,0xd7,0xd8,0xd9,0xda,
+    0xe2,0xe3,0xe4,0xe5,0xe6,0xe7,0xe8,0xe9,0xea,0xf2,0xf3,0xf4,0xf5,0xf6,0xf7,0xf8,0xf9,0xfa };
+
+// IMA ADPCM step sizes (adpcm.c:64-75)
+static const uint16_t kImaStep[89] = {
+        7,     8,     9,    10,    11,    12,    13,    14,    16,    17,    19,    21,
+       23,    25,    28,    31,    34,    37,    41,    45,    50,    55,    60,    66,
+       73,    80,    88,    97,   107,   118,   130,   143,   157,   173,   190,   209,
+      230,   253,   279,   307,   337,   371,   408,   449,   494,   544,   598,   658,
+      724,   796,   876,   963,  1060,  1166,  1282,  1411,  1552,  1707,  1878,  2066,
+     2272,  2499,  2749,  3024,  3327,  3660,  4026,  4428,  4871,  5358,  5894,  6484,
+     7132,  7845,  8630,  9493, 10442, 11487, 12635, 13899, 15289, 16818, 18500, 20350,
+    22385, 24623, 27086, 29794, 32767 };
+
+// ----------------------------------------------------------------------------
+// Decoder lookup structure.
+//
+// One uint16 array holds, for each of the four Huffman tables, a 512-entry first
+// level indexed by the next 9 bits, followed by 128-entry second-level tables for
+// the few 9-bit prefixes that continue into longer codes (canonical JPEG codes put
+// every code longer than 9 bits behind a handful of all-ones prefixes).
+//
+// entry: [4:0] code length  [8:5] size (magnitude bits that follow)  [12:9] run
+//        bit 13 = this is a pointer, [12:0] = index of the second-level table
+//        bit 14 = no such code (length field 1 so a garbage lane still advances)
+// EOB is (run 0, size 0); ZRL is (run 15, size 0).
+constexpr int kVlcFirstBits = 9;
+constexpr int kVlcSecondBits = 7;
+constexpr uint16_t kVlcPtr = 1u << 13;
+constexpr uint16_t kVlcBad = 1u << 14;
+constexpr int kVlcMaxEntries = 4 * 512 + 24 * 128;
+
+struct VlcTables {
+    uint16_t e[kVlcMaxEntries];
+    int      base[4];        // first-level base of DC-luma, DC-chroma, AC-luma, AC-chroma
+    int      count;          // entries used
+};
+
+// zigzag position -> (raster index | quantiser << 8), per component class (luma, chroma)
+struct DequantTables { uint32_t zq[2][64]; };
+
+// Encoder: symbol -> (code << 5 | length).  Index: DC-luma 0..15, DC-chroma 16..31,
+// AC-luma 32..287, AC-chroma 288..543.
+constexpr int kEncDcLuma = 0, kEncDcChroma = 16, kEncAcLuma = 32, kEncAcChroma = 288, kEncHuffEntries = 544;
+struct EncHuffTables { uint32_t e[kEncHuffEntries]; };
+
+inline const uint8_t *huff_symbols(int t) {
+    return t < 2 ? kHuffSymDC : (t == 2 ? kHuffSymACLuma : kHuffSymACChroma);
+}
+
+// canonical code assignment (ff_mjpeg_build_huffman_codes, mjpeg.c:129-147)
+inline void huff_codes(int t, uint8_t len[256], uint16_t code[256]) {
+    const uint8_t *sym = huff_symbols(t);
+    memset(len, 0, 256);
+    memset(code, 0, 512);
+    unsigned next = 0;
+    int k = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int j = 0; j < kHuffCount[t][l - 1]; j++, k++) {
+            len[sym[k]] = (uint8_t)l;
+            code[sym[k]] = (uint16_t)next++;
+        }
+        next <<= 1;
+    }
+}
+
+inline void build_vlc_tables(VlcTables &T) {
+    for (int i = 0; i < kVlcMaxEntries; i++) T.e[i] = kVlcBad | 1;
+    int used = 0;
+    for (int t = 0; t < 4; t++) {
+        uint8_t len[256]; uint16_t code[256];
+        huff_codes(t, len, code);
+        T.base[t] = used;
+        used += 1 << kVlcFirstBits;
+        for (int s = 0; s < 256; s++) {
+            if (!len[s]) continue;
+            const int run = t < 2 ? 0 : (s >> 4), size = t < 2 ? s : (s & 15);
+            const uint16_t ent = (uint16_t)(len[s] | (size << 5) | (run << 9));
+            if (len[s] <= kVlcFirstBits) {
+                const int lo = code[s] << (kVlcFirstBits - len[s]);
+                for (int i = 0; i < (1 << (kVlcFirstBits - len[s])); i++) T.e[T.base[t] + lo + i] = ent;
+            } else {
+                const int pre = code[s] >> (len[s] - kVlcFirstBits);
+                uint16_t &slot = T.e[T.base[t] + pre];
+                if (!(slot & kVlcPtr)) {
+                    slot = (uint16_t)(kVlcPtr | used);
+                    used += 1 << kVlcSecondBits;
+                }
+                const int sub = slot & 0x1fff;
+                const int rest = len[s] - kVlcFirstBits;               // 1..7 bits left
+                const int lo = (code[s] & ((1 << rest) - 1)) << (kVlcSecondBits - rest);
+                for (int i = 0; i < (1 << (kVlcSecondBits - rest)); i++) T.e[sub + lo + i] = ent;
+            }
+        }
+    }
+    T.count = used;
+}
+
+inline void build_dequant_tables(DequantTables &D) {
+    for (int c = 0; c < 2; c++)
+        for (int k = 0; k < 64; k++) D.zq[c][k] = (uint32_t)kZigzag[k] | ((uint32_t)kDecQuant[c][k] << 8);
+}
+
+inline void build_enc_huff_tables(EncHuffTables &E) {
+    memset(E.e, 0, sizeof(E.e));
+    const int base[4] = { kEncDcLuma, kEncDcChroma, kEncAcLuma, kEncAcChroma };
+    for (int t = 0; t < 4; t++) {
+        uint8_t len[256]; uint16_t code[256];
+        huff_codes(t, len, code);
+        for (int s = 0; s < (t < 2 ? 16 : 256); s++)
+            E.e[base[t] + s] = ((uint32_t)code[s] << 5) | len[s];
+    }
+}
+
+}  // namespace amv

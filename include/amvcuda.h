@@ -1,0 +1,191 @@
+/*
+ * amvcuda.h -- C ABI of libamvcuda: the AMV intra-frame codec path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Each entry point replaces the per-frame /
+ * per-chunk body of one reference codec callback (paths relative to
+ * /root/reference/AMVmuxer/ffmpeg/libavcodec/ unless noted); the reference-side
+ * AVCodec and amvlib bindings that call them are in INTEGRATION.md and glue/.
+ *
+ *   amv_decode_frames     <- AVCodec amv_decoder.decode   = sp5x_decode_frame  sp5xdec.c:33-188,203-212
+ *                            (-> ff_mjpeg_decode_frame mjpegdec.c:1106, mjpeg_decode_scan :660,
+ *                                decode_block :376, simple_idct_put simple_idct.c:390)
+ *   amv_encode_frames     <- AVCodec amv_encoder.encode   = amv_encode_picture mjpegenc.c:454-472,485-494
+ *                            (-> MPV_encode_picture mpegvideo_enc.c:1205, encode_mb_internal :1457,
+ *                                dct_quantize_c :3647, ff_jpeg_fdct_islow jfdctint.c:261,
+ *                                encode_block mjpegenc.c:379, escape_FF :282, trailer :345)
+ *   amv_adpcm_dec_chunks  <- AVCodec adpcm_ima_amv_decoder.decode = adpcm_decode_frame adpcm.c:894,1268-1292
+ *   amv_adpcm_enc_chunks  <- AVCodec adpcm_ima_amv_encoder.encode = adpcm_encode_frame adpcm.c:445,461-496
+ *   (amvlib mirror: AmvVideoDecode / AmvAudioDecode, C-AMVDecoder/amvlib/AMVDec.c:259-340 -- see INTEGRATION.md)
+ *
+ * Contract
+ *  - Plain C, plain pointers and sizes.  No CPU fallback: every call either runs the
+ *    CUDA kernels or returns a negative AMV_ERR_*; without a usable device amv_create fails.
+ *  - `mem` says where ALL buffer arguments of that call live: AMV_MEM_HOST (the library
+ *    stages through pinned memory and copies both ways inside the call, which returns
+ *    after the results are in the caller's buffers) or AMV_MEM_DEVICE (pointers are device
+ *    pointers on the context's device; the call only enqueues work on the context's
+ *    stream and returns -- synchronise with amv_sync or the stream you passed).
+ *  - A call processes a BATCH of n independent units (frames / chunks).  The reference
+ *    callbacks are the n == 1 case.
+ *  - Results are bit-exact with the reference C paths for every input inside the
+ *    reference's defined domain; outside it (corrupt streams, values that make the
+ *    reference index out of its tables) the per-unit status says so and the output for
+ *    that unit is unspecified but memory-safe.
+ *  - One context per host thread / CUDA stream; contexts are independent.
+ */
+#ifndef AMVCUDA_H
+#define AMVCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AMV_API __attribute__((visibility("default")))
+#else
+#define AMV_API
+#endif
+
+#define AMVCUDA_VERSION 0x000100
+
+typedef struct amv_ctx amv_ctx;
+
+enum amv_mem { AMV_MEM_HOST = 0, AMV_MEM_DEVICE = 1 };
+
+/* return codes (negative = failure of the whole call) */
+enum {
+    AMV_OK            =  0,
+    AMV_ERR_ARG       = -1,   /* bad argument (NULL, n < 0, zero dims, unsupported geometry) */
+    AMV_ERR_NODEVICE  = -2,   /* no CUDA device / wrong architecture: there is no CPU path */
+    AMV_ERR_CUDA      = -3,   /* a CUDA runtime call failed; see amv_last_error */
+    AMV_ERR_NOMEM     = -4,
+    AMV_ERR_UNSUPPORTED = -5  /* option outside the contract */
+};
+
+/* per-unit status words written to `status[i]` (0 = ok, otherwise an OR of these) */
+enum {
+    AMV_ST_SHORT     = 1 << 0,  /* packet/chunk shorter than its framing */
+    AMV_ST_BADCODE   = 1 << 1,  /* bit pattern that is no Huffman code (mjpegdec.c:362-366) */
+    AMV_ST_COEFIDX   = 1 << 2,  /* run past coefficient 63 ("error count", mjpegdec.c:423-424) */
+    AMV_ST_MARKER    = 1 << 3,  /* FF xx marker inside the scan data cut it short (mjpegdec.c:1153-1157) */
+    AMV_ST_OVERRUN   = 1 << 4,  /* decoder needed more bits than the packet holds */
+    AMV_ST_RANGE     = 1 << 5,  /* offset/size outside the supplied buffer, or ADPCM step index > 88 */
+    AMV_ST_NOSPACE   = 1 << 6   /* encoder: packet does not fit the per-frame capacity */
+};
+
+typedef struct amv_params {
+    int      device;          /* CUDA ordinal; -1 = current device */
+    void    *stream;          /* cudaStream_t to run on; NULL = the context creates its own */
+    uint32_t flags;           /* reserved, 0 */
+} amv_params;
+
+/* How the encoder lays packets out in `out`. */
+enum amv_layout {
+    AMV_LAYOUT_PACKED = 0,    /* back to back in frame order; out_off[i] is written by the call */
+    AMV_LAYOUT_SLOTS  = 1     /* frame i at out + i*pkt_cap; out_off[i] = i*pkt_cap is written too */
+};
+
+AMV_API int         amv_create(const amv_params *params, amv_ctx **out_ctx);
+AMV_API void        amv_destroy(amv_ctx *ctx);
+AMV_API int         amv_set_stream(amv_ctx *ctx, void *cuda_stream);
+AMV_API int         amv_sync(amv_ctx *ctx);
+AMV_API const char *amv_strerror(int err);
+AMV_API const char *amv_last_error(const amv_ctx *ctx);
+AMV_API int         amv_version(void);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+AMV_API uint64_t    amv_launch_count(const amv_ctx *ctx);
+/* pinned host memory for AMV_MEM_HOST callers that want zero staging copies */
+AMV_API void       *amv_host_alloc(size_t bytes);
+AMV_API void        amv_host_free(void *p);
+
+/* Tuning knobs (never change results):
+ *   "decode_log2_lanes"            0..5: decode lanes (subsequences) per frame = 1 << value; -1 = from batch size
+ *   "encode_slot_workspace_bytes"  cap of the packed-layout staging workspace (frames are sub-batched to fit) */
+AMV_API int         amv_set_option(amv_ctx *ctx, const char *key, int64_t value);
+/* "decode_sync_rounds": rounds the last multi-lane decode needed to self-synchronise (max over warps) */
+AMV_API int64_t     amv_get_stat(amv_ctx *ctx, const char *key);
+
+/* qscale the reference derives from AVFrame.quality (lambda): update_qscale,
+ * mpegvideo_enc.c:143-148 with qmin/qmax = 2/31 (utils.c:497-498). Pure host arithmetic. */
+AMV_API int amv_qscale_from_quality(int quality, int qmin, int qmax);
+
+/*
+ * Decode n AMV video packets (each `FF D8 | stuffed scan | FF D9`, no tables inside) of
+ * w x h pixels into YUVJ420P planes.
+ *   pkts/pkts_bytes          one buffer holding all packets
+ *   pkt_off[i], pkt_size[i]  location of packet i inside pkts
+ *   y,u,v                    plane bases of frame 0; frame i's planes start at
+ *                            y + i*fs_y, u + i*fs_c, v + i*fs_c (bytes); rows are ls_y / ls_c apart.
+ *                            Y is w x h, Cb/Cr are ceil(w/2) x ceil(h/2); rows are stored top-down
+ *                            (the codec's bottom-up order is undone, mjpegdec.c:672-677).
+ *   status[i]                per-frame status word (may be NULL)
+ */
+AMV_API int amv_decode_frames(amv_ctx *ctx,
+                              const uint8_t *pkts, uint64_t pkts_bytes,
+                              const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                              int w, int h,
+                              uint8_t *y, uint8_t *u, uint8_t *v,
+                              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                              int32_t *status, int mem);
+
+/*
+ * Encode n YUVJ420P frames into AMV packets, byte-identical to amv_encoder.
+ *   y,u,v, ls_*, fs_*        as above (source planes)
+ *   qscale                   per-frame quantiser scale 2..31 (NULL = 2, the reference default;
+ *                            use amv_qscale_from_quality for AVFrame.quality)
+ *   out/out_cap              packet buffer; pkt_cap = capacity reserved per frame
+ *   out_off[i], out_size[i]  where packet i was written and its size (0 if status[i] != 0)
+ * Requires (h/2)%8 in {0,4} (otherwise the reference reads outside the picture).
+ */
+AMV_API int amv_encode_frames(amv_ctx *ctx,
+                              const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                              int n, int w, int h, const int32_t *qscale,
+                              uint8_t *out, uint64_t out_cap, uint32_t pkt_cap, int layout,
+                              uint64_t *out_off, uint32_t *out_size,
+                              int32_t *status, int mem);
+
+/*
+ * Decode n IMA-ADPCM-AMV chunks (le16 predictor, le16 step index, le32 count, nibbles)
+ * into mono int16 PCM.  Chunk i yields 2*(chunk_size[i]-8) samples at pcm + pcm_off[i]
+ * (offsets in samples).
+ */
+AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx,
+                                 const uint8_t *chunks, uint64_t chunks_bytes,
+                                 const uint64_t *chunk_off, const uint32_t *chunk_size, int n,
+                                 int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off,
+                                 int32_t *status, int mem);
+
+/*
+ * Encode n chunks.  Chunk i takes nsamples[i] (even) samples from pcm + pcm_off[i] and the
+ * encoder state step_in[i] (0..88; NULL = 0); writes 8 + nsamples[i]/2 bytes at
+ * out + out_off[i] and the state after the chunk to step_out[i] (may be NULL).  A single
+ * stream is encoded by chaining step_out[i] -> step_in[i+1] on the host (adpcm.c:466);
+ * independent streams/chunks run in parallel.
+ */
+AMV_API int amv_adpcm_enc_chunks(amv_ctx *ctx,
+                                 const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off,
+                                 const uint32_t *nsamples, const int16_t *step_in, int16_t *step_out, int n,
+                                 uint8_t *out, uint64_t out_bytes, const uint64_t *out_off,
+                                 int32_t *status, int mem);
+
+/*
+ * Encode `nstreams` continuous streams chunk by chunk with the state carried inside each
+ * stream exactly like repeated adpcm_encode_frame calls (adpcm.c:461-496): stream s is
+ * chunks [first_chunk[s], first_chunk[s+1]) of the arrays above (first_chunk has
+ * nstreams+1 entries); step_in gives the state before each stream's first chunk.
+ */
+AMV_API int amv_adpcm_enc_streams(amv_ctx *ctx,
+                                  const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off,
+                                  const uint32_t *nsamples, const uint32_t *first_chunk, int nstreams, int nchunks,
+                                  const int16_t *step_in, int16_t *step_out,
+                                  uint8_t *out, uint64_t out_bytes, const uint64_t *out_off,
+                                  int32_t *status, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMVCUDA_H */

@@ -1,0 +1,178 @@
+// TEST-ONLY: runs the __host__ __device__ per-lane logic of the kernels (Huffman LUTs, BitReader,
+// decode_block, idct_put_block, fdct_block, quant_*) on the CPU, one emulated lane at a time, so
+// the intricate parts can be checked against the oracle in a container without a GPU.  This is
+// not a product path: nothing outside tests/ builds or loads it, and libamvcuda never links it.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../amv-codec-tools_b200/csrc/amv_common.cuh"
+#include "../../amv-codec-tools_b200/csrc/amv_tables.cuh"
+#include "../../amv-codec-tools_b200/csrc/amv_dct.cuh"
+#include "../../amv-codec-tools_b200/csrc/amv_vlc.cuh"
+#include "../../amv-codec-tools_b200/csrc/amv_kernels.h"
+
+using namespace amv;
+
+static VlcTables g_vlc;
+static DequantTables g_dq;
+static EncHuffTables g_eh;
+static bool g_init;
+static void init() {
+    if (g_init) return;
+    build_vlc_tables(g_vlc); build_dequant_tables(g_dq); build_enc_huff_tables(g_eh);
+    g_init = true;
+}
+
+// same rule as k_unstuff, sequential
+static std::vector<uint8_t> unstuff(const uint8_t *pkt, uint32_t size, int *st) {
+    std::vector<uint8_t> v;
+    const uint32_t npay = size >= 4 ? size - 4 : 0;
+    std::vector<uint8_t> in(pkt + (size >= 4 ? 2 : 0), pkt + (size >= 4 ? 2 : 0) + npay);
+    in.push_back(0xff); in.push_back(0xd9);
+    uint32_t prev = 0;
+    for (size_t i = 0; i < in.size(); i++) {
+        const uint32_t x = in[i];
+        const bool after_ff = prev == 0xff && i > 0;
+        const bool drop = after_ff && (x == 0 || x == 0xff);
+        const bool term = after_ff && !(x == 0 || x == 0xff || (x >= 0xd0 && x <= 0xd7));
+        if (term) { if (i != in.size() - 1) *st |= AMV_ST_MARKER; break; }
+        if (!drop) v.push_back((uint8_t)x);
+        prev = x;
+    }
+    return v;
+}
+
+struct Put {
+    int16_t *blk; const uint32_t *zq;
+    void operator()(int k, int v) const { const uint32_t e = zq[k]; blk[e & 63] = (int16_t)(v * (int)(e >> 8)); }
+};
+struct NoPut { void operator()(int, int) const {} };
+
+static void walk(const uint32_t *words, uint32_t nwords, uint32_t sbit, uint32_t sph, uint32_t end_bit, LaneExit &ex) {
+    BitReader br; br.init(words, nwords, sbit);
+    uint32_t phase = sph, nb = 0; int dc[3] = { 0, 0, 0 };
+    while (br.bitpos() < end_bit) {
+        int diff;
+        decode_block<false>(br, g_vlc.e, g_vlc.base, phase >= 4, diff, NoPut());
+        dc[phase < 4 ? 0 : phase - 3] += diff;
+        phase = phase == 5 ? 0 : phase + 1; nb++;
+    }
+    ex.bitpos = br.bitpos(); ex.phase = phase; ex.nblocks = nb; ex.dc[0] = dc[0]; ex.dc[1] = dc[1]; ex.dc[2] = dc[2];
+}
+
+extern "C" {
+
+int emul_vlc_entries(void) { init(); return g_vlc.count; }
+
+// decode one frame with P = 1 << log2p emulated lanes; returns status, *rounds = sync rounds used
+int emul_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h, uint8_t *py, uint8_t *pu, uint8_t *pv,
+                      int log2p, int *rounds) {
+    init();
+    int st = 0;
+    std::vector<uint8_t> scan = unstuff(pkt, size, &st);
+    const uint32_t U = (uint32_t)scan.size();
+    scan.resize(((U + 15) & ~15u) + 32, 0);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(scan.data());
+    const uint32_t nwords = (U + 3) >> 2, total_bits = U * 8;
+    const Geom g = make_geom(w, h);
+    const int P = 1 << log2p;
+    std::vector<LaneStart> starts(P);
+    if (rounds) *rounds = 0;
+    if (log2p == 0) { starts[0] = { 0, 0, (uint32_t)g.nblk, { 1024, 1024, 1024 } }; }
+    else {
+        const uint32_t L = (((total_bits + P - 1) >> log2p) + 31u) & ~31u;
+        std::vector<uint32_t> sb(P), sp(P, 0), eb(P);
+        std::vector<LaneExit> ex(P);
+        for (int p = 0; p < P; p++) {
+            uint64_t s = (uint64_t)p * L, e = (uint64_t)(p + 1) * L;
+            sb[p] = (uint32_t)(s < total_bits ? s : total_bits); eb[p] = (uint32_t)(e < total_bits ? e : total_bits);
+            walk(words, nwords, sb[p], 0, eb[p], ex[p]);
+        }
+        int r = 1;
+        for (int it = 0; it < P; it++) {
+            bool any = false;
+            std::vector<LaneExit> old = ex;
+            for (int p = 0; p < P; p++) {
+                uint32_t nb = p ? old[p - 1].bitpos : 0, np = p ? old[p - 1].phase : 0;
+                if (nb != sb[p] || np != sp[p]) { any = true; sb[p] = nb; sp[p] = np; walk(words, nwords, nb, np, eb[p], ex[p]); }
+            }
+            if (!any) break;
+            r++;
+        }
+        if (rounds) *rounds = r;
+        uint32_t first = 0; int d[3] = { 0, 0, 0 };
+        const int q0l = g_dq.zq[0][0] >> 8, q0c = g_dq.zq[1][0] >> 8;
+        for (int p = 0; p < P; p++) {
+            starts[p].bitpos = sb[p]; starts[p].first_block = first; starts[p].nblocks = ex[p].nblocks;
+            starts[p].pred[0] = 1024 + q0l * d[0]; starts[p].pred[1] = 1024 + q0c * d[1]; starts[p].pred[2] = 1024 + q0c * d[2];
+            first += ex[p].nblocks; d[0] += ex[p].dc[0]; d[1] += ex[p].dc[1]; d[2] += ex[p].dc[2];
+        }
+    }
+    for (int p = 0; p < P; p++) {
+        uint32_t first = starts[p].first_block, count = starts[p].nblocks;
+        if (log2p) {
+            if (first >= (uint32_t)g.nblk) count = 0; else if (first + count > (uint32_t)g.nblk) count = g.nblk - first;
+            if (p == P - 1 && first + starts[p].nblocks < (uint32_t)g.nblk) { count = g.nblk - first; st |= AMV_ST_OVERRUN; }
+        }
+        BitReader br; br.init(words, nwords, starts[p].bitpos);
+        int pred[3] = { starts[p].pred[0], starts[p].pred[1], starts[p].pred[2] };
+        uint32_t mb = first / 6; int b = first - mb * 6, mx = mb % g.mbw, my = mb / g.mbw;
+        for (uint32_t i = 0; i < count; i++) {
+            const int tq = b >= 4, comp = b < 4 ? 0 : b - 3;
+            int16_t blk[64] = { 0 }; int diff;
+            Put put = { blk, g_dq.zq[tq] };
+            st |= decode_block<true>(br, g_vlc.e, g_vlc.base, tq, diff, put);
+            pred[comp] += diff * (int)(g_dq.zq[tq][0] >> 8);
+            blk[0] = (int16_t)pred[comp];
+            uint32_t c[32], o[16];
+            for (int k = 0; k < 32; k++) c[k] = (uint16_t)blk[2 * k] | ((uint32_t)(uint16_t)blk[2 * k + 1] << 16);
+            idct_put_block(c, o);
+            uint8_t *pl = comp == 0 ? py : (comp == 1 ? pu : pv);
+            const int ls = comp ? g.cw : g.w, vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
+            const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8, by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+            for (int yy = 0; yy < 8; yy++) {
+                const int row = r0 - (by + yy);
+                if (row < 0 || row >= vh) continue;
+                for (int xx = 0; xx < 8; xx++)
+                    if (bx + xx < vw) pl[row * ls + bx + xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
+            }
+            if (++b == 6) { b = 0; if (++mx == g.mbw) { mx = 0; my++; } }
+        }
+        if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;
+    }
+    return st;
+}
+
+void emul_idct(const int16_t *blocks, int n, uint8_t *out) {
+    for (int i = 0; i < n; i++) {
+        uint32_t c[32], o[16];
+        for (int k = 0; k < 32; k++) c[k] = (uint16_t)blocks[64 * i + 2 * k] | ((uint32_t)(uint16_t)blocks[64 * i + 2 * k + 1] << 16);
+        idct_put_block(c, o);
+        memcpy(out + 64 * i, o, 64);
+    }
+}
+
+// pixels (0..255 as int16) -> fdct -> quantised coefficients in raster order, like the kernel's stage A
+void emul_fdct_quant(const int16_t *blocks, int n, int qscale, int16_t *out, int16_t *fdct_out) {
+    uint32_t qm10[64];
+    for (int t = 0; t < 64; t++) {
+        int m = 8;
+        if (t) { m = (kEncIntraBase[t] * qscale) >> 3; m = m < 1 ? 1 : (m > 255 ? 255 : m); }
+        qm10[t] = ((1u << 22) / (uint32_t)(8 * m)) << 10;
+    }
+    for (int i = 0; i < n; i++) {
+        int v[64];
+        for (int k = 0; k < 64; k++) v[k] = blocks[64 * i + k];
+        fdct_block(v);
+        if (fdct_out) for (int k = 0; k < 64; k++) fdct_out[64 * i + k] = (int16_t)v[k];
+        out[64 * i] = (int16_t)quant_dc(v[0]);
+        for (int k = 1; k < 64; k++) out[64 * i + k] = (int16_t)quant_ac(v[k], qm10[k]);
+    }
+}
+
+// worst-case magnitudes inside fdct_block for a block: reports whether every intermediate the
+// 32-bit kernel shifts fits (|x| < 2^31) by redoing the pass in 64 bit
+int emul_enc_huff(int idx) { init(); return (int)g_eh.e[idx]; }
+
+}

@@ -1,0 +1,322 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs, against the committed golden vectors, and through size-independent
+properties at larger sizes.  Bit-exact everywhere (integer / byte work)."""
+import os
+
+import numpy as np
+import pytest
+
+import amv_codec_tools_b200 as amv
+from oracle_lib import Oracle, chroma_dims, offsets_of, pack, synth_frames, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "amv_golden.npz"))
+VIDEO_CASES = bytes(G["video_cases"]).decode().split("\n")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = amv.AmvCuda(device=0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+# ------------------------------------------------------------------ ADPCM
+@pytest.mark.parametrize("kind", ["tones", "noise", "square", "silence"])
+@pytest.mark.parametrize("nchunks,ns", [(1, 1378), (33, 1378), (257, 1378), (64, 2), (40, 64), (17, 4000)])
+def test_adpcm_roundtrip_vs_oracle(ctx, oracle, kind, nchunks, ns):
+    pcm = synth_pcm(nchunks * ns, seed=41, kind=kind)
+    nsamp = np.full(nchunks, ns, np.uint32)
+    poff = offsets_of(nsamp)
+    step_in = (np.arange(nchunks) * 7 % 89).astype(np.int16)
+    out, ooff, osz, so, st = ctx.adpcm_encode(pcm, poff, nsamp, step_in)
+    wout, _, wsz, wso = oracle.adpcm_encode(pcm, poff, nsamp, step_in)
+    assert (st == 0).all()
+    assert np.array_equal(osz, wsz) and np.array_equal(out, wout) and np.array_equal(so, wso)
+    dec, _, dst = ctx.adpcm_decode(out, ooff, osz)
+    wdec, _, wst = oracle.adpcm_decode(out, ooff, osz)
+    assert (dst == 0).all() and np.array_equal(dec, wdec)
+
+
+def test_adpcm_ragged_and_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(42)
+    nsamp = (rng.integers(0, 900, 200) * 2).astype(np.uint32)      # includes empty chunks
+    nsamp[:3] = [0, 2, 4]
+    pcm = synth_pcm(int(nsamp.sum()) + 2, seed=43, kind="noise")
+    poff = offsets_of(nsamp)
+    out, ooff, osz, so, st = ctx.adpcm_encode(pcm, poff, nsamp)
+    wout, _, wsz, wso = oracle.adpcm_encode(pcm, poff, nsamp, np.zeros(200, np.int16))
+    assert (st == 0).all() and np.array_equal(out, wout) and np.array_equal(so, wso)
+    dec, _, dst = ctx.adpcm_decode(out, ooff, osz)
+    wdec, _, _ = oracle.adpcm_decode(out, ooff, osz)
+    assert (dst == 0).all() and np.array_equal(dec, wdec)
+    # arbitrary nibbles, every legal header step index, odd chunk sizes / unaligned offsets
+    chunks = []
+    for idx in range(89):
+        body = rng.integers(0, 256, int(rng.integers(1, 200)), dtype=np.uint8).tobytes()
+        pred = int(rng.integers(-32768, 32768)) & 0xFFFF
+        chunks.append(pred.to_bytes(2, "little") + idx.to_bytes(2, "little") + (2 * len(body)).to_bytes(4, "little") + body)
+    ck, coff, csz = pack(chunks)
+    dec, _, dst = ctx.adpcm_decode(ck, coff, csz)
+    wdec, _, _ = oracle.adpcm_decode(ck, coff, csz)
+    assert (dst == 0).all() and np.array_equal(dec, wdec)
+    # rejected inputs: short chunk, step index 89
+    bad = [b"\x00\x00\x00", (0).to_bytes(2, "little") + (89).to_bytes(2, "little") + bytes(8)]
+    ck, coff, csz = pack(bad)
+    _, _, dst = ctx.adpcm_decode(ck, coff, csz)
+    assert dst[0] == amv.ST_SHORT and dst[1] == amv.ST_RANGE
+
+
+def test_adpcm_stream_chaining(ctx, oracle):
+    """amv_adpcm_enc_streams carries the step index inside a stream like repeated adpcm_encode_frame calls."""
+    k = "adpcm_tones/"
+    for kind in ("tones", "noise", "square"):
+        k = "adpcm_%s/" % kind
+        cons = G[k + "cons"]
+        poff = offsets_of(cons)
+        # three copies of the golden stream as three independent streams
+        nchunk = len(cons)
+        src = np.concatenate([G[k + "src"]] * 3)
+        pcm_off = np.concatenate([poff + i * len(G[k + "src"]) for i in range(3)]).astype(np.uint64)
+        nsamp = np.concatenate([cons] * 3).astype(np.uint32)
+        first = np.array([0, nchunk, 2 * nchunk, 3 * nchunk], np.uint32)
+        out, ooff, osz, so, st = ctx.adpcm_encode_streams(src, pcm_off, nsamp, first)
+        assert (st == 0).all()
+        one = G[k + "out"]
+        assert np.array_equal(out, np.concatenate([one] * 3))
+
+
+@pytest.mark.parametrize("kind", ["tones", "noise", "square"])
+def test_adpcm_golden(ctx, kind):
+    k = "adpcm_%s/" % kind
+    out, off, sz = G[k + "out"], G[k + "off"], G[k + "sz"]
+    dec, _, st = ctx.adpcm_decode(out, off, sz)
+    assert (st == 0).all() and np.array_equal(dec, G[k + "dec"])
+
+
+# ------------------------------------------------------------------ video encode
+@pytest.mark.parametrize("w,h", [(160, 120), (320, 240), (208, 176), (128, 96), (48, 40), (16, 16), (72, 24), (1280, 720)])
+@pytest.mark.parametrize("kind", ["sinus", "noise", "flat", "edges"])
+def test_encode_byte_identical(ctx, oracle, w, h, kind):
+    n = 2 if w * h > 200000 else (5 if w * h > 40000 else 9)
+    y, u, v = synth_frames(n, w, h, seed=51, kind=kind)
+    pk, off, sz, st = ctx.encode_frames(y, u, v)
+    wpk, woff, wsz = oracle.encode_frames(y, u, v, w, h, 2)
+    assert (st == 0).all()
+    assert np.array_equal(sz, wsz) and np.array_equal(off, woff)
+    assert np.array_equal(pk, wpk)
+
+
+@pytest.mark.parametrize("case", VIDEO_CASES)
+def test_encode_golden(ctx, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    qs = ctx.qscale_from_quality(int(q[1:]))
+    pk, off, sz, st = ctx.encode_frames(G[case + "/y"], G[case + "/u"], G[case + "/v"], qscale=qs)
+    assert (st == 0).all() and np.array_equal(sz, G[case + "/sz"]) and np.array_equal(pk, G[case + "/pk"])
+
+
+def test_encode_qscale_per_frame_and_layouts(ctx, oracle):
+    w, h = 64, 48
+    y, u, v = synth_frames(30, w, h, seed=52, kind="sinus")
+    qs = (2 + np.arange(30) % 30).astype(np.int32)
+    pk, off, sz, st = ctx.encode_frames(y, u, v, qscale=qs)
+    assert (st == 0).all()
+    for i in range(30):
+        wpk, _, wsz = oracle.encode_frames(y[i:i + 1], u[i:i + 1], v[i:i + 1], w, h, int(qs[i]))
+        assert np.array_equal(pk[int(off[i]): int(off[i]) + int(sz[i])], wpk)
+    # slot layout: same packets at i*pkt_cap
+    cap = 8192
+    spk, soff, ssz, sst = ctx.encode_frames(y, u, v, qscale=qs, pkt_cap=cap, layout=amv.LAYOUT_SLOTS)
+    assert np.array_equal(ssz, sz) and np.array_equal(soff, np.arange(30, dtype=np.uint64) * cap)
+    for i in range(30):
+        assert np.array_equal(spk[i * cap: i * cap + int(sz[i])], pk[int(off[i]): int(off[i]) + int(sz[i])])
+    # capacity too small -> per-frame NOSPACE, size 0, neighbours unaffected
+    tiny = int(sz.min()) + 1
+    tpk, toff, tsz, tst = ctx.encode_frames(y, u, v, qscale=qs, pkt_cap=tiny, layout=amv.LAYOUT_SLOTS)
+    for i in range(30):
+        if sz[i] <= tiny:
+            assert tst[i] == 0 and tsz[i] == sz[i]
+        else:
+            assert tst[i] == amv.ST_NOSPACE and tsz[i] == 0
+
+
+def test_encode_rejects_unsupported(ctx):
+    y, u, v = synth_frames(1, 32, 20, seed=1)            # (h/2)%8 == 2: the reference reads outside the picture
+    with pytest.raises(amv.AmvError):
+        ctx.encode_frames(y, u, v)
+    y, u, v = synth_frames(1, 32, 32, seed=1)
+    with pytest.raises(amv.AmvError):
+        ctx.encode_frames(y, u, v, qscale=1)
+    assert ctx.encode_frames(y[:0], u[:0], v[:0])[1].shape == (0,)      # empty batch
+
+
+def test_encode_strided_device_buffers(ctx, oracle):
+    """Device-resident input with padded rows / frame strides and an odd width (generic, non-8-byte path)."""
+    import torch
+    for (w, h, pad) in [(320, 240, 32), (72, 24, 3), (34, 16, 5)]:
+        n = 4
+        cw, ch = chroma_dims(w, h)
+        y, u, v = synth_frames(n, w, h, seed=53, kind="noise")
+        ls_y, ls_c = w + pad, cw + pad
+        fs_y, fs_c = ls_y * h + 7 * pad, ls_c * ch + 3 * pad
+        Y = np.zeros((n, fs_y), np.uint8); U = np.zeros((n, fs_c), np.uint8); V = np.zeros((n, fs_c), np.uint8)
+        for i in range(n):
+            Y[i, : ls_y * h].reshape(h, ls_y)[:, :w] = y[i]
+            U[i, : ls_c * ch].reshape(ch, ls_c)[:, :cw] = u[i]
+            V[i, : ls_c * ch].reshape(ch, ls_c)[:, :cw] = v[i]
+        dY, dU, dV = (torch.from_numpy(a).cuda() for a in (Y, U, V))
+        cap = w * h * 3 + 4096
+        out = torch.zeros(n * cap, dtype=torch.uint8, device="cuda")
+        off = torch.zeros(n, dtype=torch.int64, device="cuda")
+        size = torch.zeros(n, dtype=torch.int32, device="cuda")
+        st = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.encode_frames_raw(dY, dU, dV, ls_y, ls_c, fs_y, fs_c, n, w, h, None, out, out.numel(), cap, amv.LAYOUT_PACKED,
+                              off, size, st, amv.MEM_DEVICE)
+        ctx.sync()
+        wpk, woff, wsz = oracle.encode_frames(y, u, v, w, h, 2)
+        assert (st.cpu().numpy() == 0).all()
+        assert np.array_equal(size.cpu().numpy().astype(np.uint32), wsz)
+        assert np.array_equal(out.cpu().numpy()[: len(wpk)], wpk)
+
+
+# ------------------------------------------------------------------ video decode
+@pytest.mark.parametrize("log2p", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (320, 240, "sinus"), (208, 176, "noise"), (128, 96, "edges"),
+                                      (48, 40, "flat"), (16, 16, "sinus"), (72, 24, "noise")])
+def test_decode_identical_all_lane_counts(ctx, oracle, w, h, kind, log2p):
+    n = 5 if w * h > 40000 else 11
+    y, u, v = synth_frames(n, w, h, seed=61, kind=kind)
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 2)
+    ctx.set_option("decode_log2_lanes", log2p)
+    try:
+        dy, du, dv, st = ctx.decode_frames(pk, off, sz, w, h)
+    finally:
+        ctx.set_option("decode_log2_lanes", -1)
+    wy, wu, wv, wst = oracle.decode_frames(pk, off, sz, w, h)
+    assert (st == 0).all() and (wst == 0).all()
+    assert np.array_equal(dy, wy) and np.array_equal(du, wu) and np.array_equal(dv, wv)
+    if log2p:
+        assert 1 <= ctx.get_stat("decode_sync_rounds") <= (1 << log2p) + 1
+
+
+@pytest.mark.parametrize("case", VIDEO_CASES)
+def test_decode_golden(ctx, oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    dy, du, dv, st = ctx.decode_frames(G[case + "/pk"], G[case + "/off"], G[case + "/sz"], w, h)
+    assert (st == 0).all()
+    # pixels where the reference itself indexes outside its clamp table are excluded
+    _, _, _, _, masks = oracle.decode_frames(G[case + "/pk"], G[case + "/off"], G[case + "/sz"], w, h, undef=True)
+    for got, want, m in zip((dy, du, dv), (G[case + "/dy"], G[case + "/du"], G[case + "/dv"]), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])
+
+
+def test_decode_reference_fixture_head(ctx):
+    """First packets of the reference's own AMV1.amv (real device stream) + its audio."""
+    w, h, fps, n = G["AMV1/dims"].tolist()
+    for log2p in (0, 5):
+        ctx.set_option("decode_log2_lanes", log2p)
+        dy, du, dv, st = ctx.decode_frames(G["AMV1/pk"], G["AMV1/off"], G["AMV1/sz"], w, h)
+        ctx.set_option("decode_log2_lanes", -1)
+        assert (st == 0).all()
+        assert np.array_equal(dy, G["AMV1/dy"]) and np.array_equal(du, G["AMV1/du"]) and np.array_equal(dv, G["AMV1/dv"])
+    pcm, _, ast = ctx.adpcm_decode(G["AMV1/ak"], G["AMV1/aoff"], G["AMV1/asz"])
+    assert (ast == 0).all() and np.array_equal(pcm, G["AMV1/pcm"])
+
+
+def test_decode_container_style_offsets_and_strides(ctx, oracle):
+    """Packets at arbitrary (unaligned, gapped, unordered) offsets; padded device output planes."""
+    import torch
+    w, h, n = 208, 176, 6
+    cw, ch = chroma_dims(w, h)
+    y, u, v = synth_frames(n, w, h, seed=62, kind="sinus")
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 2)
+    rng = np.random.default_rng(63)
+    order = rng.permutation(n)
+    blob = bytearray(rng.integers(0, 256, 13, dtype=np.uint8).tobytes())
+    noff = np.zeros(n, np.uint64)
+    for i in order:                                      # 00dc-style 8-byte headers between packets, no padding
+        blob += b"00dc" + int(sz[i]).to_bytes(4, "little")
+        noff[i] = len(blob)
+        blob += pk[int(off[i]): int(off[i]) + int(sz[i])].tobytes()
+    blob = np.frombuffer(bytes(blob), np.uint8)
+    wy, wu, wv, _ = oracle.decode_frames(pk, off, sz, w, h)
+    dy, du, dv, st = ctx.decode_frames(blob, noff, sz, w, h)
+    assert (st == 0).all() and np.array_equal(dy, wy) and np.array_equal(du, wu) and np.array_equal(dv, wv)
+    # padded device planes (generic store path: strides not multiples of 8)
+    ls_y, ls_c = w + 3, cw + 5
+    fs_y, fs_c = ls_y * h + 11, ls_c * ch + 1
+    Y = torch.full((n * fs_y,), 7, dtype=torch.uint8, device="cuda")
+    U = torch.full((n * fs_c,), 7, dtype=torch.uint8, device="cuda")
+    V = torch.full((n * fs_c,), 7, dtype=torch.uint8, device="cuda")
+    st = torch.zeros(n, dtype=torch.int32, device="cuda")
+    dblob, doff, dsz = torch.from_numpy(blob.copy()).cuda(), torch.from_numpy(noff.astype(np.int64)).cuda(), \
+        torch.from_numpy(sz.astype(np.int32)).cuda()
+    ctx.decode_frames_raw(dblob, dblob.numel(), doff, dsz, n, w, h, Y, U, V, ls_y, ls_c, fs_y, fs_c, st, amv.MEM_DEVICE)
+    ctx.sync()
+    Yh = Y.cpu().numpy().reshape(n, fs_y)
+    for i in range(n):
+        assert np.array_equal(Yh[i, : ls_y * h].reshape(h, ls_y)[:, :w], wy[i])
+        assert (Yh[i, : ls_y * h].reshape(h, ls_y)[:, w:] == 7).all()      # padding untouched
+    Uh = U.cpu().numpy().reshape(n, fs_c)
+    for i in range(n):
+        assert np.array_equal(Uh[i, : ls_c * ch].reshape(ch, ls_c)[:, :cw], wu[i])
+
+
+def test_decode_corrupt_streams_flagged_not_fatal(ctx, oracle):
+    w, h = 160, 120
+    y, u, v = synth_frames(4, w, h, seed=64, kind="sinus")
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 2)
+    good = [pk[int(off[i]): int(off[i]) + int(sz[i])].tobytes() for i in range(4)]
+    bad = [good[0], good[1][:300] + b"\xff\xd9", b"\xff\xd8\xff\xd9", b"\xff", good[2][:100] + b"\xff\xc4" + good[2][100:],
+           good[3]]
+    bk, boff, bsz = pack(bad)
+    for log2p in (0, 3):
+        ctx.set_option("decode_log2_lanes", log2p)
+        dy, du, dv, st = ctx.decode_frames(bk, boff, bsz, w, h)
+        ctx.set_option("decode_log2_lanes", -1)
+        wy, wu, wv, _ = oracle.decode_frames(pk, off, sz, w, h)
+        assert st[0] == 0 and st[5] == 0
+        assert np.array_equal(dy[0], wy[0]) and np.array_equal(dy[5], wy[3])
+        assert st[1] != 0 and st[2] != 0 and st[3] & amv.ST_SHORT and st[4] & amv.ST_MARKER
+    # out-of-range offsets are rejected per frame
+    st = ctx.decode_frames(pk, off + np.uint64(10 ** 9), sz, w, h)[3]
+    assert (st == amv.ST_RANGE).all()
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_roundtrip_properties_large_batch(ctx, oracle):
+    """4096 frames of 320x240: (1) the packets of a frame do not depend on its position in the batch
+    or the batch size; (2) decode(encode(x)) is identical whichever lane count decodes it and equals
+    the oracle on an audited subset; (3) a checksum of checksums over the whole batch is stable."""
+    import zlib
+    w, h, n = 320, 240, 4096
+    base_y, base_u, base_v = synth_frames(64, w, h, seed=71, kind="sinus")
+    idx = np.random.default_rng(72).integers(0, 64, n)
+    y, u, v = base_y[idx], base_u[idx], base_v[idx]
+    pk, off, sz, st = ctx.encode_frames(y, u, v, pkt_cap=65536)
+    assert (st == 0).all()
+    bpk, boff, bsz, _ = ctx.encode_frames(base_y, base_u, base_v)
+    wpk, woff, wsz = oracle.encode_frames(base_y[:8], base_u[:8], base_v[:8], w, h, 2)
+    assert np.array_equal(bpk[: len(wpk)], wpk)
+    crc_base = [zlib.crc32(bpk[int(boff[j]): int(boff[j]) + int(bsz[j])].tobytes()) for j in range(64)]
+    for i in range(n):
+        assert zlib.crc32(pk[int(off[i]): int(off[i]) + int(sz[i])].tobytes()) == crc_base[idx[i]]
+    outs = []
+    for log2p in (0, 2):
+        ctx.set_option("decode_log2_lanes", log2p)
+        dy, du, dv, dst = ctx.decode_frames(pk, off, sz, w, h)
+        ctx.set_option("decode_log2_lanes", -1)
+        assert (dst == 0).all()
+        outs.append(zlib.crc32(dy.tobytes()) ^ zlib.crc32(du.tobytes()) ^ zlib.crc32(dv.tobytes()))
+    assert outs[0] == outs[1]
+    wy, wu, wv, _ = oracle.decode_frames(bpk, boff, bsz, w, h)
+    for i in range(0, n, 37):
+        assert np.array_equal(dy[i], wy[idx[i]]) and np.array_equal(du[i], wu[idx[i]]) and np.array_equal(dv[i], wv[idx[i]])
