@@ -7,6 +7,7 @@
 #include <string.h>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/amvcuda.h"
 #include "amv_common.cuh"
@@ -30,7 +31,15 @@ enum WsId {
 
 }  // namespace
 
+// optional per-kernel device timing (option "profile_events"): CUDA events recorded on the
+// context's stream right around the launch of each hot kernel
+enum KernelKind { KK_ENCODE, KK_DECODE, KK_UNSTUFF, KK_SYNC, KK_ADPCM_DEC, KK_ADPCM_ENC, KK_COMPACT, KK_COUNT };
+static const char *const kKernelKindName[KK_COUNT] = { "encode", "decode", "unstuff", "sync", "adpcm_dec", "adpcm_enc", "compact" };
+struct EvPair { cudaEvent_t a, b; int kind; };
+
 struct amv_ctx {
+    bool opt_profile = false;
+    std::vector<EvPair> evs;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -90,6 +99,21 @@ int check_launch(amv_ctx *ctx, const char *what, int count = 1) {
     return AMV_OK;
 }
 
+struct ScopedTimer {
+    amv_ctx *c; EvPair e; bool on;
+    ScopedTimer(amv_ctx *ctx, int kind) : c(ctx), on(ctx->opt_profile) {
+        if (!on) return;
+        e.kind = kind;
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(e.a, c->stream);
+    }
+    ~ScopedTimer() {
+        if (!on) return;
+        cudaEventRecord(e.b, c->stream);
+        c->evs.push_back(e);
+    }
+};
+
 int pick_log2p(const amv_ctx *ctx, int n) {
     if (ctx->opt_log2p >= 0) return ctx->opt_log2p > 5 ? 5 : ctx->opt_log2p;
     // enough lanes to give every SM ~16 warps; beyond that one lane per frame has no
@@ -117,14 +141,17 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     if (log2p) ENSURE(WS_STARTS, sizeof(LaneStart) * ((size_t)n << log2p), starts);
 
     launch_scan_sizes(pkt_size, n, 15u, 32u, slot_off, nullptr, ctx->stream);
-    launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, ctx->stream);
+    { ScopedTimer tm(ctx, KK_UNSTUFF);
+      launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, ctx->stream); }
     int lc = 2;
     if (log2p) {
         CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
-        launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, ctx->stream);
+        { ScopedTimer tm(ctx, KK_SYNC);
+          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, ctx->stream); }
         lc++;
     }
-    launch_decode(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c, fs_y, fs_c, st, ctx->stream);
+    { ScopedTimer tm(ctx, KK_DECODE);
+      launch_decode(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c, fs_y, fs_c, st, ctx->stream); }
     lc++;
     return check_launch(ctx, "decode kernels", lc);
 }
@@ -145,7 +172,8 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
     if (layout == AMV_LAYOUT_SLOTS) {
         if ((uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
-        launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out, pkt_cap, pkt_cap, out_size, st, ctx->stream);
+        { ScopedTimer tm(ctx, KK_ENCODE);
+          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out, pkt_cap, pkt_cap, out_size, st, ctx->stream); }
         launch_slot_offsets(out_off, n, pkt_cap, ctx->stream);
         return check_launch(ctx, "encode kernels", 2);
     }
@@ -161,10 +189,12 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
     int lc = 0;
     for (int f0 = 0; f0 < n; f0 += sub) {
         const int m = n - f0 < sub ? n - f0 : sub;
-        launch_encode(y + fs_y * f0, u + fs_c * f0, v + fs_c * f0, ls_y, ls_c, fs_y, fs_c, m, g, qscale ? qscale + f0 : nullptr,
-                      slots, stride, pkt_cap, out_size + f0, st + f0, ctx->stream);
+        { ScopedTimer tm(ctx, KK_ENCODE);
+          launch_encode(y + fs_y * f0, u + fs_c * f0, v + fs_c * f0, ls_y, ls_c, fs_y, fs_c, m, g, qscale ? qscale + f0 : nullptr,
+                        slots, stride, pkt_cap, out_size + f0, st + f0, ctx->stream); }
         launch_scan_sizes(out_size + f0, m, 0u, 0u, out_off + f0, carry, ctx->stream);
-        launch_compact(slots, stride, out_size + f0, out_off + f0, m, out, out_cap, st + f0, ctx->stream);
+        { ScopedTimer tm(ctx, KK_COMPACT);
+          launch_compact(slots, stride, out_size + f0, out_off + f0, m, out, out_cap, st + f0, ctx->stream); }
         lc += 3;
     }
     return check_launch(ctx, "encode kernels", lc);
@@ -273,6 +303,7 @@ AMV_API void amv_destroy(amv_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < WS_COUNT; i++) if (ctx->ws[i].p) cudaFree(ctx->ws[i].p);
+    for (size_t i = 0; i < ctx->evs.size(); i++) { cudaEventDestroy(ctx->evs[i].a); cudaEventDestroy(ctx->evs[i].b); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -295,11 +326,38 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return AMV_ERR_ARG;
     if (!strcmp(key, "decode_log2_lanes")) { ctx->opt_log2p = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
+    if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     return AMV_ERR_UNSUPPORTED;
 }
 
 AMV_API int64_t amv_get_stat(amv_ctx *ctx, const char *key) {
     if (!ctx || !key) return -1;
+    // "<kernel>_kernel_ns" / "<kernel>_kernel_launches": device time and launch count of one hot kernel
+    // accumulated since the last query of that key pair (needs option profile_events = 1)
+    for (int k = 0; k < KK_COUNT; k++) {
+        char kn[64], kl[64];
+        snprintf(kn, sizeof kn, "%s_kernel_ns", kKernelKindName[k]);
+        snprintf(kl, sizeof kl, "%s_kernel_launches", kKernelKindName[k]);
+        const bool want_ns = !strcmp(key, kn), want_l = !strcmp(key, kl);
+        if (!want_ns && !want_l) continue;
+        cudaStreamSynchronize(ctx->stream);
+        double ns = 0; int64_t cnt = 0;
+        for (size_t i = 0; i < ctx->evs.size(); i++) {
+            if (ctx->evs[i].kind != k) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->evs[i].a, ctx->evs[i].b) == cudaSuccess) ns += (double)ms * 1e6;
+            cnt++;
+        }
+        if (want_l) return cnt;
+        // the ns query consumes the samples
+        std::vector<EvPair> keep;
+        for (size_t i = 0; i < ctx->evs.size(); i++) {
+            if (ctx->evs[i].kind == k) { cudaEventDestroy(ctx->evs[i].a); cudaEventDestroy(ctx->evs[i].b); }
+            else keep.push_back(ctx->evs[i]);
+        }
+        ctx->evs.swap(keep);
+        return (int64_t)ns;
+    }
     if (!strcmp(key, "decode_sync_rounds")) {
         uint32_t r = 0;
         if (!ctx->ws[WS_ROUNDS].p) return 0;
@@ -409,7 +467,8 @@ AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx, const uint8_t *chunks, uint64_t c
     if (mem == AMV_MEM_DEVICE) {
         int32_t *st = status;
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
-        launch_adpcm_decode(chunks, chunks_bytes, chunk_off, chunk_size, n, pcm, pcm_samples, pcm_off, st, ctx->stream);
+        { ScopedTimer tm(ctx, KK_ADPCM_DEC);
+          launch_adpcm_decode(chunks, chunks_bytes, chunk_off, chunk_size, n, pcm, pcm_samples, pcm_off, st, ctx->stream); }
         return check_launch(ctx, "adpcm decode kernel");
     }
     uint8_t *d_c; uint64_t *d_off, *d_poff; uint32_t *d_sz; int16_t *d_pcm; int32_t *d_st;
@@ -440,8 +499,9 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
     if (mem == AMV_MEM_DEVICE) {
         int32_t *st = status;
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * nchunks, st);
-        launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, step_in, step_out, out, out_bytes,
-                            out_off, st, ctx->stream);
+        { ScopedTimer tm(ctx, KK_ADPCM_ENC);
+          launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, step_in, step_out, out, out_bytes,
+                              out_off, st, ctx->stream); }
         return check_launch(ctx, "adpcm encode kernel");
     }
     int16_t *d_pcm; uint64_t *d_poff, *d_ooff; uint32_t *d_ns, *d_fc = nullptr; int16_t *d_si = nullptr, *d_so; uint8_t *d_out;

@@ -339,6 +339,7 @@ k_decode(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_
     if (f >= n) return;
 
     const uint32_t U = scan_len[f];
+    if (U == 0) return;        // rejected by k_unstuff (status already says why); a real scan is never empty
     const uint32_t *words = reinterpret_cast<const uint32_t *>(scratch + slot_off[f]);
     uint32_t first = 0, count = g.nblk, bit = 0;
     int pred0 = 1024, pred1 = 1024, pred2 = 1024;       // last_dc per component (mjpegdec.c:805-806)

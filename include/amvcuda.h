@@ -103,9 +103,12 @@ AMV_API void        amv_host_free(void *p);
 
 /* Tuning knobs (never change results):
  *   "decode_log2_lanes"            0..5: decode lanes (subsequences) per frame = 1 << value; -1 = from batch size
- *   "encode_slot_workspace_bytes"  cap of the packed-layout staging workspace (frames are sub-batched to fit) */
+ *   "encode_slot_workspace_bytes"  cap of the packed-layout staging workspace (frames are sub-batched to fit)
+ *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream */
 AMV_API int         amv_set_option(amv_ctx *ctx, const char *key, int64_t value);
-/* "decode_sync_rounds": rounds the last multi-lane decode needed to self-synchronise (max over warps) */
+/* "decode_sync_rounds": rounds the last multi-lane decode needed to self-synchronise (max over warps)
+ * "<k>_kernel_launches", then "<k>_kernel_ns" (k = encode|decode|unstuff|sync|compact|adpcm_dec|adpcm_enc):
+ * launches and summed device time of that kernel since the last "_ns" query (needs profile_events) */
 AMV_API int64_t     amv_get_stat(amv_ctx *ctx, const char *key);
 
 /* qscale the reference derives from AVFrame.quality (lambda): update_qscale,
