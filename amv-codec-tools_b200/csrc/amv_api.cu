@@ -23,7 +23,7 @@ struct DevBuf {
 };
 
 enum WsId {
-    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS,
+    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS, WS_TOKENS, WS_BLKOFF,
     // device mirrors of host arguments (AMV_MEM_HOST calls)
     WS_H_A, WS_H_B, WS_H_C, WS_H_D, WS_H_E, WS_H_F, WS_H_G, WS_H_H, WS_H_I,
     WS_COUNT
@@ -33,8 +33,8 @@ enum WsId {
 
 // optional per-kernel device timing (option "profile_events"): CUDA events recorded on the
 // context's stream right around the launch of each hot kernel
-enum KernelKind { KK_ENCODE, KK_DECODE, KK_UNSTUFF, KK_SYNC, KK_ADPCM_DEC, KK_ADPCM_ENC, KK_COMPACT, KK_COUNT };
-static const char *const kKernelKindName[KK_COUNT] = { "encode", "decode", "unstuff", "sync", "adpcm_dec", "adpcm_enc", "compact" };
+enum KernelKind { KK_ENCODE, KK_IDCT, KK_UNSTUFF, KK_SYNC, KK_ADPCM_DEC, KK_ADPCM_ENC, KK_COMPACT, KK_TOKENS, KK_COUNT };
+static const char *const kKernelKindName[KK_COUNT] = { "encode", "idct", "unstuff", "sync", "adpcm_dec", "adpcm_enc", "compact", "tokens" };
 struct EvPair { cudaEvent_t a, b; int kind; };
 
 struct amv_ctx {
@@ -131,12 +131,14 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     const Geom g = make_geom(w, h);
     const int log2p = pick_log2p(ctx, n);
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
-    uint32_t *rounds;
+    uint32_t *rounds; uint16_t *tokens; uint32_t *blk_off;
     const uint64_t scratch_bytes = pkts_bytes + 48ull * n + 64;
     ENSURE(WS_SLOT_OFF, sizeof(uint64_t) * n, slot_off);
     ENSURE(WS_SCAN_LEN, sizeof(uint32_t) * n, scan_len);
     ENSURE(WS_SCRATCH, scratch_bytes, scratch);
     ENSURE(WS_ROUNDS, sizeof(uint32_t), rounds);
+    ENSURE(WS_TOKENS, scratch_bytes * 8 + 1024, tokens);          // at most one 16-bit token per 2 scan bits
+    ENSURE(WS_BLKOFF, sizeof(uint32_t) * (size_t)n * g.nblk, blk_off);
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
     if (log2p) ENSURE(WS_STARTS, sizeof(LaneStart) * ((size_t)n << log2p), starts);
 
@@ -150,9 +152,11 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
           launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, ctx->stream); }
         lc++;
     }
-    { ScopedTimer tm(ctx, KK_DECODE);
-      launch_decode(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c, fs_y, fs_c, st, ctx->stream); }
-    lc++;
+    { ScopedTimer tm(ctx, KK_TOKENS);
+      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, ctx->stream); }
+    { ScopedTimer tm(ctx, KK_IDCT);
+      launch_idct(tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
+    lc += 2;
     return check_launch(ctx, "decode kernels", lc);
 }
 

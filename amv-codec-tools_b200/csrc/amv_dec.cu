@@ -9,9 +9,11 @@
 //                 the right neighbour with __shfl_up and the warp iterates until a __ballot shows
 //                 no lane's entry state changed.  A segmented shuffle scan then gives every lane
 //                 its first block index and DC predictors.
-//   k_decode    : every lane re-walks its (now exactly delimited) subsequence, writes dequantised
-//                 coefficients to a conflict-free shared-memory slot, runs simple_idct in registers
-//                 and stores the 8x8 pixels bottom-up (mjpegdec.c:672-677,710-716).
+//   k_vlc_tokens: every lane re-walks its (now exactly delimited) subsequence and turns the
+//                 variable-length codes into fixed-width 16-bit tokens + per-block offsets.
+//   k_idct      : one thread per 8x8 block in plane raster order (coalesced 256-byte row stores):
+//                 tokens -> dequantised coefficients in a conflict-free shared-memory column ->
+//                 simple_idct in registers -> bottom-up store (mjpegdec.c:672-677,710-716).
 #include "amv_common.cuh"
 #include "amv_tables.cuh"
 #include "amv_dct.cuh"
@@ -204,36 +206,39 @@ struct DecTablesDev {
 };
 __device__ DecTablesDev g_dec_tables;
 
-struct DecSmem {
-    uint16_t lut[kVlcMaxEntries];
-    uint32_t zq[2][64];
+struct VlcSmem {
+    uint32_t lut[kVlcMaxEntries];
     int      base[4];
+    int      q0[2];          // DC quantiser of luma / chroma
 };
 
-__device__ __forceinline__ void load_dec_tables(DecSmem &s) {
-    for (int i = threadIdx.x; i < kVlcMaxEntries / 2; i += blockDim.x)
-        reinterpret_cast<uint32_t *>(s.lut)[i] = reinterpret_cast<const uint32_t *>(g_dec_tables.vlc.e)[i];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&s.zq[0][0])[i] = (&g_dec_tables.dq.zq[0][0])[i];
+__device__ __forceinline__ void load_vlc_tables(VlcSmem &s) {
+    for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) s.lut[i] = g_dec_tables.vlc.e[i];
     if (threadIdx.x < 4) s.base[threadIdx.x] = g_dec_tables.vlc.base[threadIdx.x];
+    if (threadIdx.x < 2) s.q0[threadIdx.x] = (int)(g_dec_tables.dq.zq[threadIdx.x][0] >> 8);
     __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_vlc_sync
 // ------------------------------------------------------------------------------------------------
-struct NoPut { __device__ __forceinline__ void operator()(int, int) const {} };
+struct CountSink {
+    int dcv;
+    __device__ __forceinline__ void dc(int d) { dcv = d; }
+    __device__ __forceinline__ void ac(uint32_t) {}
+};
 
 __device__ __forceinline__ void walk_subsequence(const uint32_t *words, uint32_t nwords, uint32_t start_bit,
-                                                 uint32_t start_phase, uint32_t end_bit, const DecSmem &T,
+                                                 uint32_t start_phase, uint32_t end_bit, const VlcSmem &T,
                                                  LaneExit &ex) {
     BitReader br;
     br.init(words, nwords, start_bit);
     uint32_t phase = start_phase, nb = 0;
     int dc0 = 0, dc1 = 0, dc2 = 0;
+    CountSink sink;
     while (br.bitpos() < end_bit) {
-        int diff;
-        decode_block<false>(br, T.lut, T.base, phase >= 4 ? 1 : 0, diff, NoPut());
-        if (phase < 4) dc0 += diff; else if (phase == 4) dc1 += diff; else dc2 += diff;
+        walk_block(br, T.lut, T.base, phase >= 4 ? 1 : 0, sink);
+        if (phase < 4) dc0 += sink.dcv; else if (phase == 4) dc1 += sink.dcv; else dc2 += sink.dcv;
         phase = phase == 5 ? 0 : phase + 1;
         nb++;
     }
@@ -247,8 +252,8 @@ __global__ void __launch_bounds__(kVlcThreads)
 k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
            const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
            uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */) {
-    __shared__ DecSmem T;
-    load_dec_tables(T);
+    __shared__ VlcSmem T;
+    load_vlc_tables(T);
     const int P = 1 << log2p;
     const int lane = threadIdx.x & 31;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,115 +304,162 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
         s.bitpos = start_bit;
         s.first_block = nb_inc - ex.nblocks;
         s.nblocks = ex.nblocks;
-        const int q0l = (int)(T.zq[0][0] >> 8), q0c = (int)(T.zq[1][0] >> 8);
-        s.pred[0] = 1024 + q0l * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
-        s.pred[1] = 1024 + q0c * (d1 - ex.dc[1]);
-        s.pred[2] = 1024 + q0c * (d2 - ex.dc[2]);
+        s.pred[0] = 1024 + T.q0[0] * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
+        s.pred[1] = 1024 + T.q0[1] * (d1 - ex.dc[1]);
+        s.pred[2] = 1024 + T.q0[1] * (d2 - ex.dc[2]);
         starts[gt] = s;
     }
     if (rounds_out && lane == 0) atomicMax(rounds_out, rounds);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_decode
+// k_vlc_tokens: Huffman -> fixed-width tokens.  Every lane re-walks its (now exactly delimited)
+// subsequence and writes, per block, the absolute dequantised DC followed by the AC tokens into the
+// frame's token region, plus the block's token offset.  A block of b bits yields at most b/2
+// tokens (every symbol is at least 2 bits), so the region is 8 bytes per scan byte and a lane that
+// starts at bit s writes from token s/2 (+2 per lane of slack for even alignment) without ever
+// meeting its neighbour.
 // ------------------------------------------------------------------------------------------------
-struct SlotPut {
-    uint32_t *slot;          // this lane's column of the warp's coefficient tile: word w at slot[w*32]
-    const uint32_t *zq;      // zq[tq]
-    __device__ __forceinline__ void operator()(int k, int v) const {
-        const uint32_t e = zq[k];
-        const int j = e & 63;
-        const int val = v * (int)(e >> 8);                 // level * quant_matrix[j], stored as int16 (mjpegdec.c:420,428)
-        reinterpret_cast<int16_t *>(slot + (j >> 1) * 32)[j & 1] = (int16_t)val;
+struct TokenSink {
+    uint16_t *tok;          // frame token region
+    uint32_t cnt, limit;    // next token index, first index that may not be written
+    int dcv;
+    __device__ __forceinline__ void dc(int d) { dcv = d; }
+    __device__ __forceinline__ void ac(uint32_t t) {
+        if (cnt < limit) tok[cnt] = (uint16_t)t;
+        cnt++;
     }
 };
 
-template <bool FAST>
 __global__ void __launch_bounds__(kVlcThreads)
-k_decode(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
-         const uint32_t *__restrict__ scan_len, int n, int log2p, const LaneStart *__restrict__ starts,
-         Geom g, uint8_t *__restrict__ py, uint8_t *__restrict__ pu, uint8_t *__restrict__ pv,
-         int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *__restrict__ status) {
-    __shared__ DecSmem T;
-    __shared__ uint32_t tile[kVlcThreads / 32][32 * 32];
-    load_dec_tables(T);
+k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
+             const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
+             const LaneStart *__restrict__ starts, int nblk, uint16_t *__restrict__ tokens,
+             uint32_t *__restrict__ blk_off, int32_t *__restrict__ status) {
+    __shared__ VlcSmem T;
+    load_vlc_tables(T);
     const int P = 1 << log2p;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (int)(gt >> log2p);
     const int p = (int)(gt & (P - 1));
     if (f >= n) return;
-
     const uint32_t U = scan_len[f];
     if (U == 0) return;        // rejected by k_unstuff (status already says why); a real scan is never empty
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(scratch + slot_off[f]);
-    uint32_t first = 0, count = g.nblk, bit = 0;
+    const uint64_t so = slot_off[f];
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(scratch + so);
+    uint32_t first = 0, count = (uint32_t)nblk, bit = 0;
     int pred0 = 1024, pred1 = 1024, pred2 = 1024;       // last_dc per component (mjpegdec.c:805-806)
     uint32_t st = 0;
     if (log2p) {
         const LaneStart s = starts[gt];
         first = s.first_block; bit = s.bitpos; count = s.nblocks;
         pred0 = s.pred[0]; pred1 = s.pred[1]; pred2 = s.pred[2];
-        if (first >= (uint32_t)g.nblk) count = 0;
-        else if (first + count > (uint32_t)g.nblk) count = g.nblk - first;
-        if (p == P - 1 && first + s.nblocks < (uint32_t)g.nblk) {
+        if (first >= (uint32_t)nblk) count = 0;
+        else if (first + count > (uint32_t)nblk) count = nblk - first;
+        if (p == P - 1 && first + s.nblocks < (uint32_t)nblk) {
             // the scan ran out before the picture was complete: keep decoding (zeros) like a
             // sequential reader would, and say so
-            count = g.nblk - first;
+            count = nblk - first;
             st |= AMV_ST_OVERRUN;
         }
     }
-    uint32_t *slot = &tile[wid][lane];
-#pragma unroll
-    for (int i = 0; i < 32; i++) slot[i * 32] = 0;
+    TokenSink sink;
+    sink.tok = tokens + so * 4;                               // 8 bytes of tokens per scratch byte
+    sink.limit = (((pkt_size[f] + 15u) & ~15u) + 32u) * 4u - 8u;
+    sink.cnt = ((bit >> 1) + 2u * (uint32_t)p + 1u) & ~1u;
+    uint32_t *boff = blk_off + (uint64_t)f * nblk + first;
 
     BitReader br;
     br.init(words, (U + 3) >> 2, bit);
-    uint32_t mb = first / 6u;
-    int b = (int)(first - mb * 6u);
-    int mx = (int)(mb % (uint32_t)g.mbw), my = (int)(mb / (uint32_t)g.mbw);
-    uint8_t *fy = py + (uint64_t)f * fs_y, *fu = pu + (uint64_t)f * fs_c, *fv = pv + (uint64_t)f * fs_c;
-    const int q0l = (int)(T.zq[0][0] >> 8), q0c = (int)(T.zq[1][0] >> 8);
-
+    int b = (int)(first % 6u);
     for (uint32_t i = 0; i < count; i++) {
         const int tq = b >= 4 ? 1 : 0;
-        const int comp = b < 4 ? 0 : b - 3;
-        int diff;
-        SlotPut put = { slot, T.zq[tq] };
-        st |= decode_block<true>(br, T.lut, T.base, tq, diff, put);
+        const uint32_t at = sink.cnt < sink.limit ? sink.cnt : sink.limit;
+        boff[i] = at;
+        sink.cnt++;                                           // DC token slot, filled below
+        st |= walk_block(br, T.lut, T.base, tq, sink);
         int pr;
-        if (comp == 0) pr = (pred0 += diff * q0l);
-        else if (comp == 1) pr = (pred1 += diff * q0c);
-        else pr = (pred2 += diff * q0c);
-        reinterpret_cast<int16_t *>(slot)[0] = (int16_t)pr;
-
-        uint32_t c[32], o[16];
-#pragma unroll
-        for (int k = 0; k < 32; k++) { c[k] = slot[k * 32]; slot[k * 32] = 0; }
-        idct_put_block(c, o);
-
-        uint8_t *pl = comp == 0 ? fy : (comp == 1 ? fu : fv);
-        const int ls = comp ? ls_c : ls_y;
-        const int vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
-        const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
-        const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
-#pragma unroll
-        for (int yy = 0; yy < 8; yy++) {
-            const int row = r0 - (by + yy);
-            if (row < 0 || row >= vh) continue;
-            uint8_t *d = pl + (int64_t)row * ls + bx;
-            if (FAST) {
-                *reinterpret_cast<uint2 *>(d) = make_uint2(o[2 * yy], o[2 * yy + 1]);
-            } else {
-#pragma unroll
-                for (int xx = 0; xx < 8; xx++)
-                    if (bx + xx < vw) d[xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
-            }
-        }
-        if (++b == 6) { b = 0; if (++mx == g.mbw) { mx = 0; my++; } }
+        if (b < 4) pr = (pred0 += sink.dcv * T.q0[0]);
+        else if (b == 4) pr = (pred1 += sink.dcv * T.q0[1]);
+        else pr = (pred2 += sink.dcv * T.q0[1]);
+        if (at < sink.limit) sink.tok[at] = (uint16_t)pr;     // block[0] = (int16) val (mjpegdec.c:387-389)
+        if (++b == 6) b = 0;
     }
-    if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;     // lanes that own no block just pass through
+    if (count && sink.cnt > sink.limit) st |= AMV_ST_OVERRUN;      // a lane without blocks may sit past the region
+    if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;      // lanes that own no block just pass through
     if (st) atomicOr(&status[f], (int32_t)st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_idct: one thread per 8x8 block, blocks enumerated in PLANE raster order so that the 32 lanes
+// of a warp own 32 horizontally adjacent blocks: every pixel-row store of the warp is one
+// contiguous 256-byte run.  Tokens -> dequantised coefficients in a conflict-free shared-memory
+// column -> simple_idct in registers -> bottom-up store (mjpegdec.c:672-677,710-716).
+// ------------------------------------------------------------------------------------------------
+constexpr int kIdctThreads = 128;
+
+template <bool FAST>
+__global__ void __launch_bounds__(kIdctThreads)
+k_idct(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off, const uint64_t *__restrict__ slot_off,
+       const uint32_t *__restrict__ scan_len, int n, Geom g, uint8_t *__restrict__ py, uint8_t *__restrict__ pu,
+       uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c) {
+    __shared__ uint32_t zq[2][64];
+    __shared__ uint32_t tile[kIdctThreads / 32][32 * 32];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&zq[0][0])[i] = (&g_dec_tables.dq.zq[0][0])[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (int)(gt / g.nblk);
+    if (f >= n) return;
+    if (scan_len[f] == 0) return;
+    const int i = (int)(gt - (int64_t)f * g.nblk);
+    const int nluma = 4 * g.mbw * g.mbh, nchroma = g.mbw * g.mbh;
+    int comp, bx, by, blk;
+    if (i < nluma) {
+        comp = 0;
+        by = i / (2 * g.mbw); bx = i - by * 2 * g.mbw;
+        blk = ((by >> 1) * g.mbw + (bx >> 1)) * 6 + (by & 1) * 2 + (bx & 1);
+    } else {
+        const int j = i - nluma;
+        comp = j < nchroma ? 1 : 2;
+        const int jj = comp == 1 ? j : j - nchroma;
+        by = jj / g.mbw; bx = jj - by * g.mbw;
+        blk = jj * 6 + 3 + comp;
+    }
+    const int tq = comp ? 1 : 0;
+    const uint16_t *tp = tokens + slot_off[f] * 4 + blk_off[(uint64_t)f * g.nblk + blk];
+    uint32_t *slot = &tile[wid][lane];
+#pragma unroll
+    for (int k = 0; k < 32; k++) slot[k * 32] = 0;
+    reinterpret_cast<int16_t *>(slot)[0] = (int16_t)__ldg(tp);
+    uint32_t nxt = __ldg(tp + 1);
+    int ti = 2;
+    expand_tokens(
+        [&]() { const uint32_t t = nxt; nxt = __ldg(tp + ti); ti++; return t; }, zq[tq],
+        [&](int j, int val) { reinterpret_cast<int16_t *>(slot + (j >> 1) * 32)[j & 1] = (int16_t)val; });
+
+    uint32_t c[32], o[16];
+#pragma unroll
+    for (int k = 0; k < 32; k++) c[k] = slot[k * 32];
+    idct_put_block(c, o);
+
+    uint8_t *pl = comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c;
+    const int ls = comp ? ls_c : ls_y;
+    const int vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
+    const int x0 = bx * 8, y0 = by * 8;
+#pragma unroll
+    for (int yy = 0; yy < 8; yy++) {
+        const int row = r0 - (y0 + yy);
+        if (row < 0 || row >= vh) continue;
+        uint8_t *d = pl + (int64_t)row * ls + x0;
+        if (FAST) {
+            *reinterpret_cast<uint2 *>(d) = make_uint2(o[2 * yy], o[2 * yy + 1]);
+        } else {
+#pragma unroll
+            for (int xx = 0; xx < 8; xx++)
+                if (x0 + xx < vw) d[xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -440,19 +492,28 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
     k_vlc_sync<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out);
 }
 
-void launch_decode(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
-                   const LaneStart *starts, const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
-                   uint64_t fs_y, uint64_t fs_c, int32_t *status, cudaStream_t s) {
+void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
+                       int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
+                       int32_t *status, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
+    k_vlc_tokens<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk, tokens, blk_off,
+                                              status);
+}
+
+void launch_idct(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
+                 const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                 cudaStream_t s) {
+    const int64_t threads = (int64_t)n * g.nblk;
+    const int64_t grid = (threads + kIdctThreads - 1) / kIdctThreads;
     const bool fast = (g.w % 16 == 0) &&
                       ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
     if (fast)
-        k_decode<true><<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c,
-                                                    fs_y, fs_c, status);
+        k_idct<true><<<(unsigned)grid, kIdctThreads, 0, s>>>(tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
+                                                             fs_y, fs_c);
     else
-        k_decode<false><<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, g, y, u, v, ls_y, ls_c,
-                                                     fs_y, fs_c, status);
+        k_idct<false><<<(unsigned)grid, kIdctThreads, 0, s>>>(tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
+                                                              fs_y, fs_c);
 }
 
 }  // namespace amv

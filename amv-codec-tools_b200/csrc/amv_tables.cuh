@@ -87,23 +87,32 @@ static const uint16_t kImaStep[89] = {
 // ----------------------------------------------------------------------------
 // Decoder lookup structure.
 //
-// One uint16 array holds, for each of the four Huffman tables, a 512-entry first
-// level indexed by the next 9 bits, followed by 128-entry second-level tables for
-// the few 9-bit prefixes that continue into longer codes (canonical JPEG codes put
-// every code longer than 9 bits behind a handful of all-ones prefixes).
+// One uint32 array holds, for each of the four Huffman tables, a 1024-entry first
+// level indexed by the next 10 bits, followed by 64-entry second-level tables for
+// the few 10-bit prefixes that continue into longer codes (canonical JPEG codes put
+// every code longer than 10 bits behind a handful of all-ones prefixes).
 //
-// entry: [4:0] code length  [8:5] size (magnitude bits that follow)  [12:9] run
-//        bit 13 = this is a pointer, [12:0] = index of the second-level table
+// entry: [4:0]  code length            [8:5] size (magnitude bits that follow)
+//        [12:9] run                    bit 13 = pointer: [12:0] = index of the second-level table
 //        bit 14 = no such code (length field 1 so a garbage lane still advances)
+//        bit 15 = resolved: code AND magnitude bits fit in the 10 index bits, so
+//        [31:16] already holds the finished value -- for AC tables the token
+//        (run << 12 | level & 0xfff), for DC tables the signed difference.
 // EOB is (run 0, size 0); ZRL is (run 15, size 0).
-constexpr int kVlcFirstBits = 9;
-constexpr int kVlcSecondBits = 7;
-constexpr uint16_t kVlcPtr = 1u << 13;
-constexpr uint16_t kVlcBad = 1u << 14;
-constexpr int kVlcMaxEntries = 4 * 512 + 24 * 128;
+constexpr int kVlcFirstBits = 10;
+constexpr int kVlcSecondBits = 6;
+constexpr uint32_t kVlcPtr = 1u << 13;
+constexpr uint32_t kVlcBad = 1u << 14;
+constexpr uint32_t kVlcResolved = 1u << 15;
+constexpr int kVlcMaxEntries = 4 * 1024 + 20 * 64;
+
+// tokens handed from the Huffman kernel to the IDCT kernel (16 bit each):
+//   block = DC token (absolute, dequantised, int16) then AC tokens run<<12 | level&0xfff,
+//   terminated by EOB (0x0000) unless the block's last coefficient is number 63.
+constexpr uint32_t kTokEOB = 0x0000u, kTokZRL = 0xF000u;
 
 struct VlcTables {
-    uint16_t e[kVlcMaxEntries];
+    uint32_t e[kVlcMaxEntries];
     int      base[4];        // first-level base of DC-luma, DC-chroma, AC-luma, AC-chroma
     int      count;          // entries used
 };
@@ -136,6 +145,8 @@ inline void huff_codes(int t, uint8_t len[256], uint16_t code[256]) {
     }
 }
 
+inline int jpeg_extend(int v, int size) { return size && v < (1 << (size - 1)) ? v - ((1 << size) - 1) : v; }
+
 inline void build_vlc_tables(VlcTables &T) {
     for (int i = 0; i < kVlcMaxEntries; i++) T.e[i] = kVlcBad | 1;
     int used = 0;
@@ -147,19 +158,29 @@ inline void build_vlc_tables(VlcTables &T) {
         for (int s = 0; s < 256; s++) {
             if (!len[s]) continue;
             const int run = t < 2 ? 0 : (s >> 4), size = t < 2 ? s : (s & 15);
-            const uint16_t ent = (uint16_t)(len[s] | (size << 5) | (run << 9));
+            const uint32_t ent = (uint32_t)(len[s] | (size << 5) | (run << 9));
             if (len[s] <= kVlcFirstBits) {
-                const int lo = code[s] << (kVlcFirstBits - len[s]);
-                for (int i = 0; i < (1 << (kVlcFirstBits - len[s])); i++) T.e[T.base[t] + lo + i] = ent;
+                const int spare = kVlcFirstBits - len[s];
+                const int lo = code[s] << spare;
+                for (int i = 0; i < (1 << spare); i++) {
+                    uint32_t e = ent;
+                    if (size <= spare) {
+                        // the magnitude bits are the top `size` bits of i: finish the value here
+                        const int v = jpeg_extend(size ? i >> (spare - size) : 0, size);
+                        const uint32_t val = t < 2 ? (uint32_t)(v & 0xffff) : (uint32_t)((run << 12) | (v & 0xfff));
+                        e |= kVlcResolved | (val << 16);
+                    }
+                    T.e[T.base[t] + lo + i] = e;
+                }
             } else {
                 const int pre = code[s] >> (len[s] - kVlcFirstBits);
-                uint16_t &slot = T.e[T.base[t] + pre];
+                uint32_t &slot = T.e[T.base[t] + pre];
                 if (!(slot & kVlcPtr)) {
-                    slot = (uint16_t)(kVlcPtr | used);
+                    slot = kVlcPtr | (uint32_t)used;
                     used += 1 << kVlcSecondBits;
                 }
                 const int sub = slot & 0x1fff;
-                const int rest = len[s] - kVlcFirstBits;               // 1..7 bits left
+                const int rest = len[s] - kVlcFirstBits;               // 1..6 bits left
                 const int lo = (code[s] & ((1 << rest) - 1)) << (kVlcSecondBits - rest);
                 for (int i = 0; i < (1 << (kVlcSecondBits - rest)); i++) T.e[sub + lo + i] = ent;
             }

@@ -30,6 +30,10 @@ CW, CH = W // 2, H // 2
 FRAME_BYTES = W * H * 3 // 2
 METRIC = "AMV 320x240 frames/sec enc+dec"
 PKT_CAP = 65536                     # per-frame packet capacity handed to the encoder
+KERNELS = ("encode", "compact", "unstuff", "sync", "tokens", "idct")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+# (profiles/), scaled per frame; filled in after each profiling pass
+TRAFFIC = {}
 
 
 def load_peaks():
@@ -252,7 +256,7 @@ def main():
     ctx.sync()
     assert int(st_e.abs().sum().item()) == 0 and int(st_d.abs().sum().item()) == 0, "codec reported errors"
     pkt_bytes = int(size.to(torch.int64).sum().item())
-    for k in ("encode", "decode", "unstuff", "sync", "compact"):      # drop warm-up samples
+    for k in KERNELS:      # drop warm-up samples
         ctx.get_stat(k + "_kernel_ns")
 
     sampler = ClockSampler(dev.index)
@@ -270,7 +274,7 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
     kern = {}
-    for k in ("encode", "decode", "unstuff", "sync", "compact"):
+    for k in KERNELS:
         cnt = ctx.get_stat(k + "_kernel_launches")
         ns = ctx.get_stat(k + "_kernel_ns")
         kern[k] = {"launches": cnt, "ms": ns / 1e6}
@@ -344,19 +348,21 @@ def main():
         return 0
 
     peak, peak_src = load_peaks()
-    enc_ms = kern["encode"]["ms"] / max(1, kern["encode"]["launches"])
-    dec_ms = kern["decode"]["ms"] / max(1, kern["decode"]["launches"])
-    frames_per_enc_launch = n * args.steps / max(1, kern["encode"]["launches"])
-    frames_per_dec_launch = n * args.steps / max(1, kern["decode"]["launches"])
     bytes_per_frame = FRAME_BYTES + pkt_bytes / n          # raw planes + packet, per direction
-    enc_gbs = bytes_per_frame * frames_per_enc_launch / (enc_ms / 1e3) / 1e9
-    dec_gbs = bytes_per_frame * frames_per_dec_launch / (dec_ms / 1e3) / 1e9
-    dom = "encode" if kern["encode"]["ms"] >= kern["decode"]["ms"] else "decode"
-    roof = {"bound": "hbm", "kernel": "k_encode" if dom == "encode" else "k_decode",
-            "achieved": enc_gbs if dom == "encode" else dec_gbs, "peak": peak, "unit": "GB/s",
-            "frac": (enc_gbs if dom == "encode" else dec_gbs) / peak, "peak_source": peak_src,
-            "traffic": None, "ms_per_launch": enc_ms if dom == "encode" else dec_ms,
-            "bytes_per_frame": bytes_per_frame}
+
+    def roof_of(k):
+        """algorithmic bytes of the frames one launch of kernel k processes / its mean launch duration"""
+        ms = kern[k]["ms"] / max(1, kern[k]["launches"])
+        frames = n * args.steps / max(1, kern[k]["launches"])
+        gbs = bytes_per_frame * frames / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": "k_" + ("vlc_" + k if k in ("sync", "tokens") else k), "achieved": gbs,
+                "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src, "traffic": TRAFFIC.get(k),
+                "ms_per_launch": ms, "bytes_per_frame": bytes_per_frame}
+
+    dom = max(("encode", "tokens", "idct"), key=lambda k: kern[k]["ms"])
+    roof = roof_of(dom)
+    enc_dir_ms = (kern["encode"]["ms"] + kern["compact"]["ms"]) / args.steps
+    dec_dir_ms = (kern["idct"]["ms"] + kern["tokens"]["ms"] + kern["unstuff"]["ms"] + kern["sync"]["ms"]) / args.steps
     step_ms = ms_total / args.steps
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -367,15 +373,17 @@ def main():
                    "frames_per_gpu": n, "width": W, "height": H, "qscale": 2, "avg_packet_bytes": pkt_bytes / n,
                    "l2": "inputs per step (%.1f GB) far exceed the 126 MB L2; no flush needed" % (n * FRAME_BYTES / 1e9),
                    "sharding": "contiguous frame range per GPU, no collective on the data path"},
-        "encode_fps_per_gpu": n * args.steps / ((kern["encode"]["ms"] + kern["compact"]["ms"]) / 1e3),
-        "decode_fps_per_gpu": n * args.steps / ((kern["decode"]["ms"] + kern["unstuff"]["ms"] + kern["sync"]["ms"]) / 1e3),
+        "encode_fps_per_gpu": n / (enc_dir_ms / 1e3),
+        "decode_fps_per_gpu": n / (dec_dir_ms / 1e3),
+        "direction_roofline": {
+            "encode": {"achieved": bytes_per_frame * n / (enc_dir_ms / 1e3) / 1e9, "unit": "GB/s",
+                       "frac": bytes_per_frame * n / (enc_dir_ms / 1e3) / 1e9 / peak},
+            "decode": {"achieved": bytes_per_frame * n / (dec_dir_ms / 1e3) / 1e9, "unit": "GB/s",
+                       "frac": bytes_per_frame * n / (dec_dir_ms / 1e3) / 1e9 / peak}},
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in kern.items()},
         "kernel_share_of_step": {k: (v["ms"] / args.steps) / step_ms for k, v in kern.items()},
         "roofline": roof,
-        "roofline_other": {"kernel": "k_decode" if dom == "encode" else "k_encode",
-                           "achieved": dec_gbs if dom == "encode" else enc_gbs, "peak": peak, "unit": "GB/s",
-                           "frac": (dec_gbs if dom == "encode" else enc_gbs) / peak,
-                           "ms_per_launch": dec_ms if dom == "encode" else enc_ms},
+        "roofline_by_kernel": {k: roof_of(k) for k in ("encode", "tokens", "idct") if k != dom},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "frames_per_step_per_gpu": ne, "api": "amv_encode_frames + amv_decode_frames, AMV_MEM_HOST, pinned buffers"},
         "gpu_launches": int(launches),

@@ -43,19 +43,20 @@ static std::vector<uint8_t> unstuff(const uint8_t *pkt, uint32_t size, int *st) 
     return v;
 }
 
-struct Put {
-    int16_t *blk; const uint32_t *zq;
-    void operator()(int k, int v) const { const uint32_t e = zq[k]; blk[e & 63] = (int16_t)(v * (int)(e >> 8)); }
+struct CountSink { int dcv; void dc(int d) { dcv = d; } void ac(uint32_t) {} };
+struct VecSink {
+    std::vector<uint16_t> *tok; int dcv;
+    void dc(int d) { dcv = d; }
+    void ac(uint32_t t) { tok->push_back((uint16_t)t); }
 };
-struct NoPut { void operator()(int, int) const {} };
 
 static void walk(const uint32_t *words, uint32_t nwords, uint32_t sbit, uint32_t sph, uint32_t end_bit, LaneExit &ex) {
     BitReader br; br.init(words, nwords, sbit);
     uint32_t phase = sph, nb = 0; int dc[3] = { 0, 0, 0 };
+    CountSink sink;
     while (br.bitpos() < end_bit) {
-        int diff;
-        decode_block<false>(br, g_vlc.e, g_vlc.base, phase >= 4, diff, NoPut());
-        dc[phase < 4 ? 0 : phase - 3] += diff;
+        walk_block(br, g_vlc.e, g_vlc.base, phase >= 4, sink);
+        dc[phase < 4 ? 0 : phase - 3] += sink.dcv;
         phase = phase == 5 ? 0 : phase + 1; nb++;
     }
     ex.bitpos = br.bitpos(); ex.phase = phase; ex.nblocks = nb; ex.dc[0] = dc[0]; ex.dc[1] = dc[1]; ex.dc[2] = dc[2];
@@ -109,6 +110,10 @@ int emul_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h, uint8_t *
             first += ex[p].nblocks; d[0] += ex[p].dc[0]; d[1] += ex[p].dc[1]; d[2] += ex[p].dc[2];
         }
     }
+    // pass 1 (k_vlc_tokens): tokens + per-block offsets; pass 2 (k_idct): tokens -> pixels
+    std::vector<uint16_t> tok;
+    std::vector<uint32_t> boff(g.nblk, 0);
+    std::vector<uint8_t> have(g.nblk, 0);
     for (int p = 0; p < P; p++) {
         uint32_t first = starts[p].first_block, count = starts[p].nblocks;
         if (log2p) {
@@ -117,29 +122,42 @@ int emul_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h, uint8_t *
         }
         BitReader br; br.init(words, nwords, starts[p].bitpos);
         int pred[3] = { starts[p].pred[0], starts[p].pred[1], starts[p].pred[2] };
-        uint32_t mb = first / 6; int b = first - mb * 6, mx = mb % g.mbw, my = mb / g.mbw;
+        int b = first % 6;
+        VecSink sink; sink.tok = &tok;
         for (uint32_t i = 0; i < count; i++) {
             const int tq = b >= 4, comp = b < 4 ? 0 : b - 3;
-            int16_t blk[64] = { 0 }; int diff;
-            Put put = { blk, g_dq.zq[tq] };
-            st |= decode_block<true>(br, g_vlc.e, g_vlc.base, tq, diff, put);
-            pred[comp] += diff * (int)(g_dq.zq[tq][0] >> 8);
-            blk[0] = (int16_t)pred[comp];
-            uint32_t c[32], o[16];
-            for (int k = 0; k < 32; k++) c[k] = (uint16_t)blk[2 * k] | ((uint32_t)(uint16_t)blk[2 * k + 1] << 16);
-            idct_put_block(c, o);
-            uint8_t *pl = comp == 0 ? py : (comp == 1 ? pu : pv);
-            const int ls = comp ? g.cw : g.w, vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
-            const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8, by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
-            for (int yy = 0; yy < 8; yy++) {
-                const int row = r0 - (by + yy);
-                if (row < 0 || row >= vh) continue;
-                for (int xx = 0; xx < 8; xx++)
-                    if (bx + xx < vw) pl[row * ls + bx + xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
-            }
-            if (++b == 6) { b = 0; if (++mx == g.mbw) { mx = 0; my++; } }
+            boff[first + i] = (uint32_t)tok.size(); have[first + i] = 1;
+            tok.push_back(0);
+            const size_t at = tok.size() - 1;
+            st |= walk_block(br, g_vlc.e, g_vlc.base, tq, sink);
+            pred[comp] += sink.dcv * (int)(g_dq.zq[tq][0] >> 8);
+            tok[at] = (uint16_t)pred[comp];
+            if (++b == 6) b = 0;
         }
         if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;
+    }
+    tok.resize(tok.size() + 8, 0);
+    for (int blk = 0; blk < g.nblk; blk++) {
+        if (!have[blk]) continue;
+        const int mb = blk / 6, b = blk % 6, mx = mb % g.mbw, my = mb / g.mbw;
+        const int tq = b >= 4, comp = b < 4 ? 0 : b - 3;
+        int16_t coef[64] = { 0 };
+        const uint16_t *tp = tok.data() + boff[blk];
+        coef[0] = (int16_t)tp[0];
+        int ti = 1;
+        expand_tokens([&]() { return (uint32_t)tp[ti++]; }, g_dq.zq[tq], [&](int j, int val) { coef[j] = (int16_t)val; });
+        uint32_t c[32], o[16];
+        for (int k = 0; k < 32; k++) c[k] = (uint16_t)coef[2 * k] | ((uint32_t)(uint16_t)coef[2 * k + 1] << 16);
+        idct_put_block(c, o);
+        uint8_t *pl = comp == 0 ? py : (comp == 1 ? pu : pv);
+        const int ls = comp ? g.cw : g.w, vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
+        const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8, by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+        for (int yy = 0; yy < 8; yy++) {
+            const int row = r0 - (by + yy);
+            if (row < 0 || row >= vh) continue;
+            for (int xx = 0; xx < 8; xx++)
+                if (bx + xx < vw) pl[row * ls + bx + xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
+        }
     }
     return st;
 }

@@ -41,7 +41,7 @@ def oracle():
 
 def test_vlc_table_size(emul):
     n = emul.emul_vlc_entries()
-    assert 4 * 512 < n <= 4 * 512 + 24 * 128
+    assert 4 * 1024 < n <= 4 * 1024 + 20 * 64
 
 
 def test_enc_huff_entries(emul, oracle):
