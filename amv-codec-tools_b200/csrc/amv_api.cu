@@ -132,7 +132,7 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     const int log2p = pick_log2p(ctx, n);
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
     uint32_t *rounds; uint16_t *tokens; uint32_t *blk_off;
-    const uint64_t scratch_bytes = pkts_bytes + 48ull * n + 64;
+    const uint64_t scratch_bytes = pkts_bytes + (uint64_t)(kSlotPad + 16) * n + 64;
     ENSURE(WS_SLOT_OFF, sizeof(uint64_t) * n, slot_off);
     ENSURE(WS_SCAN_LEN, sizeof(uint32_t) * n, scan_len);
     ENSURE(WS_SCRATCH, scratch_bytes, scratch);
@@ -142,7 +142,7 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
     if (log2p) ENSURE(WS_STARTS, sizeof(LaneStart) * ((size_t)n << log2p), starts);
 
-    launch_scan_sizes(pkt_size, n, 15u, 32u, slot_off, nullptr, ctx->stream);
+    launch_scan_sizes(pkt_size, n, 15u, kSlotPad, slot_off, nullptr, ctx->stream);
     { ScopedTimer tm(ctx, KK_UNSTUFF);
       launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, ctx->stream); }
     int lc = 2;

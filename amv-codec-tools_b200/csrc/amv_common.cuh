@@ -24,6 +24,11 @@ namespace amv {
 
 constexpr int kNumSMs = 148;              // B200
 
+// Every frame's un-stuffed scan lives in a 16-byte aligned scratch slot of align16(packet size) +
+// kSlotPad bytes (zero padded past the data); its token region is 8 bytes per slot byte, which
+// leaves 8 * kSlotPad bytes beyond the 1-token-per-2-bits bound for per-lane 16-byte alignment.
+constexpr uint32_t kSlotPad = 80;
+
 // Picture geometry shared by encoder and decoder kernels.
 struct Geom {
     int w, h;          // luma size

@@ -86,7 +86,7 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
         const uint32_t size = pkt_size[f];
         const uint64_t slot = slot_off[f];
         int32_t st = 0;
-        if (off + size > pkts_bytes || slot + ((size + 15u) & ~15u) + 32u > scratch_bytes) {
+        if (off + size > pkts_bytes || slot + ((size + 15u) & ~15u) + kSlotPad > scratch_bytes) {
             if (tid == 0) { scan_len[f] = 0; status[f] = AMV_ST_RANGE; }
             continue;
         }
@@ -317,77 +317,225 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 // subsequence and writes, per block, the absolute dequantised DC followed by the AC tokens into the
 // frame's token region, plus the block's token offset.  A block of b bits yields at most b/2
 // tokens (every symbol is at least 2 bits), so the region is 8 bytes per scan byte and a lane that
-// starts at bit s writes from token s/2 (+2 per lane of slack for even alignment) without ever
+// starts at bit s writes from token s/2 (+8 per lane of slack for 16-byte alignment) without ever
 // meeting its neighbour.
+//
+// The symbol loop is the serial heart of the decoder, so it is written for issue slots:
+//  * bits come from a per-lane 16-word ring in shared memory ([word][lane], conflict-free) that is
+//    topped up with one 128-bit global load per lane at BLOCK boundaries, where the warp is
+//    converged: the load issued at one boundary is parked in registers and stored to the ring at
+//    the next, so its latency never sits inside the divergent symbol loop (a load into a register
+//    that other lanes still have in flight would stall the whole warp there);
+//  * one table lookup per symbol (byte-field entries, explicit shared-memory addresses), then
+//    straight-line field extraction, JPEG sign extension and token assembly -- no per-symbol
+//    divergence except EOB/ZRL/second-level codes;
+//  * tokens collect in a 128-bit shift register and leave as 16-byte stores.
 // ------------------------------------------------------------------------------------------------
-struct TokenSink {
-    uint16_t *tok;          // frame token region
-    uint32_t cnt, limit;    // next token index, first index that may not be written
-    int dcv;
-    __device__ __forceinline__ void dc(int d) { dcv = d; }
-    __device__ __forceinline__ void ac(uint32_t t) {
-        if (cnt < limit) tok[cnt] = (uint16_t)t;
-        cnt++;
-    }
+__device__ FastVlcTables g_fast_vlc;
+
+constexpr int kTokThreads = 128;
+constexpr int kRingWords = 16;
+
+struct TokSmem {
+    uint32_t lut[kVlcMaxEntries];
+    uint32_t ring[kTokThreads / 32][kRingWords * 32];
 };
 
-__global__ void __launch_bounds__(kVlcThreads)
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kTokThreads)
 k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
              const LaneStart *__restrict__ starts, int nblk, uint16_t *__restrict__ tokens,
              uint32_t *__restrict__ blk_off, int32_t *__restrict__ status) {
-    __shared__ VlcSmem T;
-    load_vlc_tables(T);
+    __shared__ TokSmem S;
+    for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) S.lut[i] = g_fast_vlc.e[i];
+    __syncthreads();
     const int P = 1 << log2p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (int)(gt >> log2p);
     const int p = (int)(gt & (P - 1));
-    if (f >= n) return;
-    const uint32_t U = scan_len[f];
-    if (U == 0) return;        // rejected by k_unstuff (status already says why); a real scan is never empty
-    const uint64_t so = slot_off[f];
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(scratch + so);
-    uint32_t first = 0, count = (uint32_t)nblk, bit = 0;
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(S.lut);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&S.ring[wid][lane]);   // word w of this lane: + w*128
+    const uint32_t dc_base[2] = { (uint32_t)g_fast_vlc.base[0], (uint32_t)g_fast_vlc.base[1] };
+    const uint32_t ac_base[2] = { (uint32_t)g_fast_vlc.base[2], (uint32_t)g_fast_vlc.base[3] };
+    const int q0l = (int)(g_dec_tables.dq.zq[0][0] >> 8), q0c = (int)(g_dec_tables.dq.zq[1][0] >> 8);
+
+    // ---- lane set-up (inactive lanes keep count = 0 and fall through the loops)
+    uint32_t count = 0, first = 0, bit = 0, U = 0, st = 0;
     int pred0 = 1024, pred1 = 1024, pred2 = 1024;       // last_dc per component (mjpegdec.c:805-806)
-    uint32_t st = 0;
-    if (log2p) {
-        const LaneStart s = starts[gt];
-        first = s.first_block; bit = s.bitpos; count = s.nblocks;
-        pred0 = s.pred[0]; pred1 = s.pred[1]; pred2 = s.pred[2];
-        if (first >= (uint32_t)nblk) count = 0;
-        else if (first + count > (uint32_t)nblk) count = nblk - first;
-        if (p == P - 1 && first + s.nblocks < (uint32_t)nblk) {
-            // the scan ran out before the picture was complete: keep decoding (zeros) like a
-            // sequential reader would, and say so
-            count = nblk - first;
-            st |= AMV_ST_OVERRUN;
+    const uint32_t *words = nullptr;
+    uint32_t cap_words = 0;
+    uint64_t so = 0;
+    if (f < n) {
+        U = scan_len[f];
+        so = slot_off[f];
+        words = reinterpret_cast<const uint32_t *>(scratch + so);
+        cap_words = (((pkt_size[f] + 15u) & ~15u) + kSlotPad) >> 2;
+        if (U) {       // U == 0: rejected by k_unstuff (status already says why)
+            count = (uint32_t)nblk;
+            if (log2p) {
+                const LaneStart s = starts[gt];
+                first = s.first_block; bit = s.bitpos; count = s.nblocks;
+                pred0 = s.pred[0]; pred1 = s.pred[1]; pred2 = s.pred[2];
+                if (first >= (uint32_t)nblk) count = 0;
+                else if (first + count > (uint32_t)nblk) count = nblk - first;
+                if (p == P - 1 && first + s.nblocks < (uint32_t)nblk) {
+                    // the scan ran out before the picture was complete: keep decoding (zeros) like a
+                    // sequential reader would, and say so
+                    count = nblk - first;
+                    st |= AMV_ST_OVERRUN;
+                }
+            }
         }
     }
-    TokenSink sink;
-    sink.tok = tokens + so * 4;                               // 8 bytes of tokens per scratch byte
-    sink.limit = (((pkt_size[f] + 15u) & ~15u) + 32u) * 4u - 8u;
-    sink.cnt = ((bit >> 1) + 2u * (uint32_t)p + 1u) & ~1u;
-    uint32_t *boff = blk_off + (uint64_t)f * nblk + first;
+    // token output: 16-byte groups inside the frame's region
+    const uint32_t tok_cap = (cap_words << 2) * 4u;                       // tokens in the region
+    uint32_t tok_idx = ((bit >> 1) + 8u * (uint32_t)p + 7u) & ~7u;          // first token index of this lane (multiple of 8)
+    uint16_t *tok_frame = tokens + so * 4;
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, tcount = 0;
+    uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;
 
-    BitReader br;
-    br.init(words, (U + 3) >> 2, bit);
+    // ---- bit source: 64-bit window + shared-memory ring
+    uint32_t rd = bit >> 5;                 // next word to merge into the window
+    uint32_t wr = rd & ~3u;                 // next word the ring receives (16-byte groups)
+    uint64_t acc = 0;
+    int nb = 0;
+    uint4 pend = make_uint4(0, 0, 0, 0);
+    bool have_pend = false;
+    auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
+        if (w + 4 <= cap_words) return __ldg(reinterpret_cast<const uint4 *>(words + w));
+        return make_uint4(0, 0, 0, 0);
+    };
+    auto ring_put = [&](uint32_t w, const uint4 &q) {
+        sts32(ring_s + ((w + 0) & (kRingWords - 1)) * 128, bswap32(q.x));
+        sts32(ring_s + ((w + 1) & (kRingWords - 1)) * 128, bswap32(q.y));
+        sts32(ring_s + ((w + 2) & (kRingWords - 1)) * 128, bswap32(q.z));
+        sts32(ring_s + ((w + 3) & (kRingWords - 1)) * 128, bswap32(q.w));
+    };
+    if (count) {
+        ring_put(wr, load_group(wr));
+        ring_put(wr + 4, load_group(wr + 4));
+        wr += 8;
+        pend = load_group(wr);
+        have_pend = true;
+        // prime the window at the (unaligned) start bit
+        const uint32_t w0 = lds32(ring_s + (rd & (kRingWords - 1)) * 128);
+        const uint32_t w1 = lds32(ring_s + ((rd + 1) & (kRingWords - 1)) * 128);
+        const uint32_t sh = bit & 31;
+        acc = (((uint64_t)w0 << 32) | w1) << sh;
+        nb = 64 - (int)sh;
+        rd += 2;
+    }
+    auto refill = [&]() {
+        if (nb <= 32) {
+            uint32_t w;
+            if (rd < wr) w = lds32(ring_s + (rd & (kRingWords - 1)) * 128);
+            else w = rd < cap_words ? bswap32(__ldg(words + rd)) : 0u;     // ring ran dry inside a huge block
+            rd++;
+            acc |= (uint64_t)w << (32 - nb);
+            nb += 32;
+        }
+    };
+    auto push = [&](uint32_t tok) {        // append one 16-bit token
+        t0 = __funnelshift_r(t0, t1, 16);
+        t1 = __funnelshift_r(t1, t2, 16);
+        t2 = __funnelshift_r(t2, t3, 16);
+        t3 = (t3 >> 16) | (tok << 16);
+        if (++tcount == 8) {
+            if (tok_idx + 8 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
+            else st |= AMV_ST_OVERRUN;
+            tok_idx += 8;
+            tcount = 0;
+        }
+    };
+
+    uint32_t maxcount = count;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, d));
     int b = (int)(first % 6u);
-    for (uint32_t i = 0; i < count; i++) {
+
+    for (uint32_t i = 0; i < maxcount; i++) {
+        const bool on = i < count;
+        // ---- converged: ring top-up
+        if (on) {
+            if (rd > wr) { wr = rd & ~3u; have_pend = false; }                // the ring ran dry in the last block: restart it
+            if (have_pend && (int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; have_pend = false; }
+            if (!have_pend && (int)(wr - rd) <= kRingWords - 8) { pend = load_group(wr); have_pend = true; }
+        }
+        if (!on) continue;
         const int tq = b >= 4 ? 1 : 0;
-        const uint32_t at = sink.cnt < sink.limit ? sink.cnt : sink.limit;
-        boff[i] = at;
-        sink.cnt++;                                           // DC token slot, filled below
-        st |= walk_block(br, T.lut, T.base, tq, sink);
-        int pr;
-        if (b < 4) pr = (pred0 += sink.dcv * T.q0[0]);
-        else if (b == 4) pr = (pred1 += sink.dcv * T.q0[1]);
-        else pr = (pred2 += sink.dcv * T.q0[1]);
-        if (at < sink.limit) sink.tok[at] = (uint16_t)pr;     // block[0] = (int16) val (mjpegdec.c:387-389)
+        boff[i] = min(tok_idx + tcount, tok_cap);
+        // ---- DC (mjpeg_decode_dc, mjpegdec.c:358-373)
+        {
+            refill();
+            const uint32_t hi = (uint32_t)(acc >> 32);
+            uint32_t e = lds32(lut_s + (dc_base[tq] + (hi >> (32 - kVlcFirstBits))) * 4);
+            if ((e & 0xff) == 0) {
+                if (e & 0x100) { st |= AMV_ST_BADCODE; e = 1u | (32u << 8) | (1u << 16); }
+                else e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
+                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; e = 1u | (32u << 8) | (1u << 16); }
+            }
+            const uint32_t len = e & 0xff, rsh = (e >> 8) & 0xff, total = (e >> 16) & 0xff;
+            const uint32_t top = hi << len;
+            const int sg = (int)(~top) >> 31;                                 // get_xbits: -1 if the first bit is 0
+            const int diff = (int)((__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg);
+            acc <<= total; nb -= (int)total;
+            int pr;
+            if (b < 4) pr = (pred0 += diff * q0l);
+            else if (b == 4) pr = (pred1 += diff * q0c);
+            else pr = (pred2 += diff * q0c);
+            push((uint32_t)pr & 0xffffu);                                      // block[0] = (int16) val (mjpegdec.c:387-389)
+        }
+        // ---- AC (decode_block, mjpegdec.c:391-428)
+        int k = 0;
+        for (;;) {
+            refill();
+            const uint32_t hi = (uint32_t)(acc >> 32);
+            uint32_t e = lds32(lut_s + (ac_base[tq] + (hi >> (32 - kVlcFirstBits))) * 4);
+            if ((e & 0xff) == 0) {
+                if (!(e & 0x100))
+                    e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
+                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; acc <<= 1; nb -= 1; push(kTokEOB); break; }
+            }
+            const uint32_t len = e & 0xff, rsh = (e >> 8) & 0xff, total = (e >> 16) & 0xff, run = e >> 28;
+            const uint32_t top = hi << len;
+            acc <<= total; nb -= (int)total;
+            if (rsh == 32) {                                                   // size 0: EOB or ZRL
+                if (run != 15) { push(kTokEOB); break; }
+                push(kTokZRL);
+                k += 16;
+                if (k > 1024) { push(kTokEOB); break; }                        // only garbage lanes get here
+                continue;
+            }
+            const int sg = (int)(~top) >> 31;
+            const uint32_t lvl = (__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg;
+            k += (int)run + 1;
+            if (k > 63) { st |= AMV_ST_COEFIDX; push(kTokEOB); break; }       // "error count" (mjpegdec.c:423-424)
+            push((run << 12) | (lvl & 0xfffu));
+            if (k == 63) break;
+        }
         if (++b == 6) b = 0;
     }
-    if (count && sink.cnt > sink.limit) st |= AMV_ST_OVERRUN;      // a lane without blocks may sit past the region
-    if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;      // lanes that own no block just pass through
-    if (st) atomicOr(&status[f], (int32_t)st);
+    // flush the partly filled group (unused upper tokens are don't-care, the group is ours alone)
+    if (count && tcount) {
+        for (uint32_t j = tcount; j < 8; j++) {
+            t0 = __funnelshift_r(t0, t1, 16); t1 = __funnelshift_r(t1, t2, 16); t2 = __funnelshift_r(t2, t3, 16); t3 >>= 16;
+        }
+        if (tok_idx + 8 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
+        else st |= AMV_ST_OVERRUN;
+    }
+    // a lane that owns no block just passes through; otherwise it must end inside the scan
+    if (count && rd * 32u - (uint32_t)nb > U * 8u) st |= AMV_ST_OVERRUN;
+    if (st && f < n) atomicOr(&status[f], (int32_t)st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,7 +616,10 @@ k_idct(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 cudaError_t upload_dec_tables(cudaStream_t s) {
     static DecTablesDev h;      // built once; identical for every context
     static bool built = false;
-    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); built = true; }
+    static FastVlcTables hf;
+    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); build_fast_vlc_tables(hf); built = true; }
+    cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_vlc, &hf, sizeof(hf), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbolAsync(g_dec_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 
@@ -496,8 +647,8 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                        int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
                        int32_t *status, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
-    const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
-    k_vlc_tokens<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk, tokens, blk_off,
+    const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
+    k_vlc_tokens<<<grid, kTokThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk, tokens, blk_off,
                                               status);
 }
 

@@ -117,6 +117,16 @@ struct VlcTables {
     int      count;          // entries used
 };
 
+// Second view of the same codes for the token kernel's straight-line symbol decode: byte fields,
+// so every field is one PRMT/LOP away.
+//   [7:0] code length  [15:8] 32 - size  [23:16] length + size (bits to consume)  [31:28] run
+//   length 0 marks a special entry: bit 8 set = no such code, else [31:16] = second-level index
+struct FastVlcTables {
+    uint32_t e[kVlcMaxEntries];
+    int      base[4];
+    int      count;
+};
+
 // zigzag position -> (raster index | quantiser << 8), per component class (luma, chroma)
 struct DequantTables { uint32_t zq[2][64]; };
 
@@ -187,6 +197,22 @@ inline void build_vlc_tables(VlcTables &T) {
         }
     }
     T.count = used;
+}
+
+inline void build_fast_vlc_tables(FastVlcTables &F) {
+    VlcTables T;
+    build_vlc_tables(T);
+    F.count = T.count;
+    for (int t = 0; t < 4; t++) F.base[t] = T.base[t];
+    for (int i = 0; i < kVlcMaxEntries; i++) {
+        const uint32_t e = T.e[i];
+        if (e & kVlcBad) F.e[i] = 0x100u;
+        else if (e & kVlcPtr) F.e[i] = (e & 0x1fffu) << 16;
+        else {
+            const uint32_t len = e & 31, size = (e >> 5) & 15, run = (e >> 9) & 15;
+            F.e[i] = len | ((32 - size) << 8) | ((len + size) << 16) | (run << 28);
+        }
+    }
 }
 
 inline void build_dequant_tables(DequantTables &D) {
