@@ -66,4 +66,26 @@ AMV_HD uint32_t bswap32(uint32_t v) {
 
 AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+#if defined(__CUDACC__)
+// Shared memory through explicit 32-bit shared-window addresses: keeps the hot loops free of
+// generic-address arithmetic (ptxas otherwise re-derives the shared window base inside them).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+#endif
+
 }  // namespace amv

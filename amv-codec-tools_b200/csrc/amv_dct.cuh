@@ -135,7 +135,8 @@ AMV_HD int quant_ac(int b, uint32_t qm10) {
 #else
     int q = (int)(((uint64_t)a * qm10) >> 32);
 #endif
-    q = q > 1023 ? 1023 : q;
+    // clip_coeffs' +-1023 (mpegvideo_enc.c:1403-1432) cannot trigger: for qscale >= 2 the matrix
+    // entries are >= 4, so |q| <= 16320 / 32 = 510 for any 8-bit picture (checked in tests/).
     return b < 0 ? -q : q;
 }
 

@@ -341,15 +341,6 @@ struct TokSmem {
     uint32_t ring[kTokThreads / 32][kRingWords * 32];
 };
 
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(kTokThreads)
 k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,

@@ -25,8 +25,9 @@ namespace amv {
 
 constexpr int kEncThreads = 96;
 constexpr int kSegMB = 16;
-// worst case: 96 blocks x (20-bit DC + 63 x 26-bit AC) = 159168 bits, + carry word + slack
-constexpr int kSegWords = (96 * (20 + 63 * 26) + 31) / 32 + 8;
+// worst case per block: 20-bit DC + 63 x 26-bit AC = 1658 bits = 52 words
+constexpr int kStageWords = (20 + 63 * 26 + 31) / 32;
+constexpr int kSegWords = kEncThreads * kStageWords + 8;
 
 struct EncTablesDev {
     EncHuffTables huff;
@@ -38,42 +39,27 @@ __device__ EncTablesDev g_enc_tables;
 struct EncSmem {
     uint32_t huff[kEncHuffEntries];
     uint32_t qm10[64];
-    uint32_t coef[32 * kEncThreads];   // word (k>>1)*96 + t : zigzag coefficients k, k+1 of thread t's block
-    uint32_t seg[kSegWords];
+    union {                                 // never live at the same time (A,B use coef; D,E use seg)
+        uint32_t coef[32 * kEncThreads];    // word (k>>1)*96 + t : zigzag coefficients k, k+1 of thread t's block
+        uint32_t seg[kSegWords];            // the segment's contiguous bit string
+    } u;
+    uint32_t stage[kStageWords * kEncThreads];   // word w*96 + t : thread t's private bit string
     uint32_t lens[kEncThreads];        // bit length per block in bitstream order -> exclusive offsets
     int      dcq[kEncThreads];         // quantised DC per block in bitstream order
     int      carry_dc[3];              // last DC of each component from the previous segment
     uint32_t warp_tot[4];
     uint32_t seg_bits;                 // total bits of the segment
+    uint32_t carry_word;               // partial word carried into the next segment
     uint32_t overflow;
 };
 
-// MSB-first bit sink into the segment buffer.  First and last word of a block are shared with
-// the neighbouring blocks (atomicOr); the words in between belong to this thread alone.
-struct BitSink {
-    uint32_t *seg;
-    uint32_t widx;
-    uint64_t acc;
-    int fill;
-    bool first;
-    __device__ __forceinline__ void init(uint32_t *s, uint32_t bitpos) {
-        seg = s; widx = bitpos >> 5; fill = (int)(bitpos & 31); acc = 0; first = true;
-    }
-    __device__ __forceinline__ void put(uint32_t code, int len) {     // len <= 27
-        acc |= (uint64_t)code << (64 - fill - len);
-        fill += len;
-        if (fill >= 32) {
-            const uint32_t w = (uint32_t)(acc >> 32);
-            if (first) { atomicOr(&seg[widx], w); first = false; } else seg[widx] = w;
-            widx++; acc <<= 32; fill -= 32;
-        }
-    }
-    __device__ __forceinline__ void finish() {
-        if (fill > 0) atomicOr(&seg[widx], (uint32_t)(acc >> 32));
-    }
-};
-
 __device__ __forceinline__ int bit_width(uint32_t v) { return 32 - __clz(v); }
+
+// exact per-byte "== 0xFF" detector: 0x80 in every byte of v that is FF
+__device__ __forceinline__ uint32_t ff_bytes(uint32_t v) {
+    const uint32_t t = ~v;                                       // FF bytes become 00
+    return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu);
+}
 
 template <bool FAST>
 __global__ void __launch_bounds__(kEncThreads)
@@ -91,11 +77,16 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
     else         { mi = lane & 15; b = 4 + (lane >> 4); }
     const int comp = b < 4 ? 0 : b - 3;
     const int sigma = mi * 6 + b;                       // position in bitstream order
-    const int dc_tab = comp ? kEncDcChroma : kEncDcLuma, ac_tab = comp ? kEncAcChroma : kEncAcLuma;
     const int total_mb = g.mbw * g.mbh;
     // valid source extent: the reference copies w x h luma and (w>>1) x (h>>1) chroma (mpegvideo_enc.c:866-867)
     const int vw = comp ? (g.w >> 1) : g.w, vh = comp ? (g.h >> 1) : g.h, r0 = comp ? g.c0 : g.y0;
     const int ls = comp ? ls_c : ls_y;
+    // explicit shared addresses for the hot loops
+    const uint32_t huff_dc_s = smem_addr(&S.huff[comp ? kEncDcChroma : kEncDcLuma]);
+    const uint32_t huff_ac_s = smem_addr(&S.huff[comp ? kEncAcChroma : kEncAcLuma]);
+    const uint32_t coef_s = smem_addr(&S.u.coef[t]);            // coefficient k: + (k>>1)*384 + (k&1)*2
+    const uint32_t stage_s = smem_addr(&S.stage[t]);            // word w: + w*384
+    const uint32_t seg_s = smem_addr(&S.u.seg[0]);
 
     for (int f = blockIdx.x; f < n; f += gridDim.x) {
         const int qs = qscale ? qscale[f] : 2;
@@ -107,11 +98,11 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
             S.qm10[t] = ((1u << 22) / (uint32_t)(8 * m)) << 10;
         }
         if (t < 3) S.carry_dc[t] = 128;                 // last_dc init (mpegvideo_enc.c:2033-2036)
-        if (t == 0) { S.seg[0] = 0; S.overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0; }   // qscale domain: SURVEY 9.13
+        if (t == 0) { S.carry_word = 0; S.overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0; }   // qscale domain: SURVEY 9.13
         const uint8_t *pl = (comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c);
         uint8_t *pkt = slots + (uint64_t)f * slot_stride;
         uint32_t G = 2;                                 // bytes written so far (SOI)
-        uint32_t r = 0;                                 // carried bits sitting in seg[0]
+        uint32_t r = 0;                                 // carried bits (sit in carry_word, MSB side)
         if (t == 0 && pkt_cap >= 2) { pkt[0] = 0xff; pkt[1] = 0xd8; }
         __syncthreads();
 
@@ -119,7 +110,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
             const int nmb = min(kSegMB, total_mb - m0);
             const bool active = mi < nmb;
             const bool last_seg = m0 + kSegMB >= total_mb;
-            uint64_t mask = 0;          // non-zero AC positions (zigzag) of this block
+            uint32_t mask_lo = 0, mask_hi = 0;          // non-zero AC positions (zigzag) of this block
             int dc = 0;
 
             // ---------------- A: load, FDCT, quantise
@@ -147,45 +138,66 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                 }
                 fdct_block(v);
                 dc = quant_dc(v[0]);
+                // raster order so the multiplier loads vectorise; mask bit = zigzag position
 #pragma unroll
-                for (int k = 1; k < 64; k++) {
-                    const int j = zigzag_at(k);
+                for (int j = 1; j < 64; j++) {
                     const int q = quant_ac(v[j], S.qm10[j]);
                     v[j] = q;
-                    if (q) mask |= 1ull << k;
+                    const int k = zigzag_inv_at(j);
+                    if (q) { if (k < 32) mask_lo |= 1u << k; else mask_hi |= 1u << (k - 32); }
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
                     const uint32_t lo = (uint32_t)v[zigzag_at(2 * i)] & 0xffffu;
                     const uint32_t hi = (uint32_t)v[zigzag_at(2 * i + 1)] << 16;
-                    S.coef[i * kEncThreads + t] = lo | hi;
+                    S.u.coef[i * kEncThreads + t] = lo | hi;
                 }
                 S.dcq[sigma] = dc;
             }
             __syncthreads();
 
-            // ---------------- B: pass 1, code lengths
-            int pred = 0;
+            // ---------------- B: Huffman-code the block into the thread's private bit string
             uint32_t len = 0;
             if (active) {
+                int pred;
                 if (comp == 0) pred = (b > 0) ? S.dcq[sigma - 1] : (mi > 0 ? S.dcq[sigma - 3] : S.carry_dc[0]);
                 else           pred = mi > 0 ? S.dcq[sigma - 6] : S.carry_dc[comp];
-                const int diff = dc - pred;
-                const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
-                len = (S.huff[dc_tab + nb] & 31) + nb;
-                const uint32_t zrl_len = S.huff[ac_tab + 0xf0] & 31, eob_len = S.huff[ac_tab] & 31;
-                uint64_t m = mask;
-                int prevk = 0;
-                while (m) {
-                    const int k = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const int run = k - prevk - 1;
-                    prevk = k;
-                    const int cv = (int)reinterpret_cast<const int16_t *>(&S.coef[(k >> 1) * kEncThreads + t])[k & 1];
-                    const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
-                    len += (run >> 4) * zrl_len + (S.huff[ac_tab + (((run & 15) << 4) | cb)] & 31) + cb;
+                uint64_t acc = 0;                   // MSB-first accumulator
+                int fill = 0;
+                uint32_t wp = stage_s;              // next private word
+                auto put = [&](uint32_t code, int nbits) {       // nbits <= 27
+                    acc |= (uint64_t)code << (64 - fill - nbits);
+                    fill += nbits;
+                    len += nbits;
+                    if (fill >= 32) { sts32(wp, (uint32_t)(acc >> 32)); wp += kEncThreads * 4; acc <<= 32; fill -= 32; }
+                };
+                {   // DC (ff_mjpeg_encode_dc, mjpegenc.c:357-377)
+                    const int diff = dc - pred;
+                    const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
+                    const uint32_t e = lds32(huff_dc_s + nb * 4);
+                    const uint32_t mant = (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u);
+                    put(((e >> 5) << nb) | mant, (int)(e & 31) + nb);
                 }
-                if (prevk != 63) len += eob_len;            // EOB only if last_index < 63 (mjpegenc.c:432-434)
+                const uint32_t ezrl = lds32(huff_ac_s + 0xf0 * 4), eeob = lds32(huff_ac_s);
+                int prevk = 0;
+                auto ac_run = [&](uint32_t m, int base) {        // encode_block's AC loop (mjpegenc.c:403-430)
+                    while (m) {
+                        const int k = base + __ffs((int)m) - 1;
+                        m &= m - 1;
+                        int run = k - prevk - 1;
+                        prevk = k;
+                        const int cv = lds_s16(coef_s + (uint32_t)(k >> 1) * (kEncThreads * 4) + (uint32_t)(k & 1) * 2);
+                        const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
+                        for (; run >= 16; run -= 16) put(ezrl >> 5, (int)(ezrl & 31));
+                        const uint32_t e = lds32(huff_ac_s + (uint32_t)((run << 4) | cb) * 4);
+                        const uint32_t mant = (uint32_t)(cv + (cv >> 31)) & ((1u << cb) - 1u);
+                        put(((e >> 5) << cb) | mant, (int)(e & 31) + cb);
+                    }
+                };
+                ac_run(mask_lo, 0);
+                ac_run(mask_hi, 32);
+                if (prevk != 63) put(eeob >> 5, (int)(eeob & 31));          // EOB only if last_index < 63 (:432-434)
+                if (fill > 0) sts32(wp, (uint32_t)(acc >> 32));
             }
             S.lens[sigma] = len;
             __syncthreads();
@@ -208,61 +220,44 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
             __syncthreads();
             const uint32_t T = S.seg_bits;
             uint32_t R = r + T;                              // bits in the buffer after this segment
-            // clear the words this segment will OR into (word 0 keeps the carried bits)
+            // clear the words this segment will OR into; word 0 starts with the carried bits
             const uint32_t used_words = (R + 7 + 31) >> 5;
-            for (uint32_t i = 1 + t; i <= used_words; i += kEncThreads) S.seg[i] = 0;
+            for (uint32_t i = 1 + t; i <= used_words; i += kEncThreads) S.u.seg[i] = 0;
+            if (t == 0) S.u.seg[0] = S.carry_word;
             __syncthreads();
 
-            // ---------------- D: pass 2, bit packing
-            if (active) {
-                BitSink bs;
-                bs.init(S.seg, r + S.lens[sigma]);
-                const int diff = dc - pred;
-                const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
-                {
-                    const uint32_t e = S.huff[dc_tab + nb];
-                    const uint32_t mant = (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u);
-                    bs.put(((e >> 5) << nb) | mant, (int)(e & 31) + nb);
+            // ---------------- D: bit packer -- shift the private string to its scanned bit offset
+            if (active && len) {
+                const uint32_t o = r + S.lens[sigma];
+                const uint32_t sh = o & 31;
+                uint32_t dst = seg_s + (o >> 5) * 4, src = stage_s;
+                const uint32_t nsrc = (len + 31) >> 5;
+                uint32_t prev = 0;
+                for (uint32_t j = 0; j < nsrc; j++) {
+                    const uint32_t v = lds32(src);
+                    red_or_shared(dst, __funnelshift_r(v, prev, sh));      // (prev:v) >> sh
+                    prev = v; src += kEncThreads * 4; dst += 4;
                 }
-                const uint32_t ezrl = S.huff[ac_tab + 0xf0], eeob = S.huff[ac_tab];
-                uint64_t m = mask;
-                int prevk = 0;
-                while (m) {
-                    const int k = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    int run = k - prevk - 1;
-                    prevk = k;
-                    const int cv = (int)reinterpret_cast<const int16_t *>(&S.coef[(k >> 1) * kEncThreads + t])[k & 1];
-                    const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
-                    for (; run >= 16; run -= 16) bs.put(ezrl >> 5, (int)(ezrl & 31));
-                    const uint32_t e = S.huff[ac_tab + ((run << 4) | cb)];
-                    const uint32_t mant = (uint32_t)(cv + (cv >> 31)) & ((1u << cb) - 1u);
-                    bs.put(((e >> 5) << cb) | mant, (int)(e & 31) + cb);
-                }
-                if (prevk != 63) bs.put(eeob >> 5, (int)(eeob & 31));
-                bs.finish();
+                const uint32_t tail = sh ? prev << (32 - sh) : 0u;
+                if (tail) red_or_shared(dst, tail);
             }
             __syncthreads();
             if (last_seg) {
                 // pad to a byte with ones (ff_mjpeg_encode_stuffing, mjpegenc.c:338-343)
                 const uint32_t pad = (0u - R) & 7u;
-                if (t == 0 && pad) S.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
+                if (t == 0 && pad) S.u.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
                 R += pad;
                 __syncthreads();
             }
 
-            // ---------------- E: stuffing + output of the complete bytes
+            // ---------------- E: FF00 stuffing + output of the complete bytes
             const uint32_t B = last_seg ? (R >> 3) : ((R >> 5) << 2);     // bytes leaving the buffer now
             const uint32_t nw = (B + 3) >> 2;
             const uint32_t per = (nw + kEncThreads - 1) / kEncThreads;
             const uint32_t w0 = min((uint32_t)t * per, nw), w1 = min(w0 + per, nw);
+            // bytes past B in the last word are zero bits, never FF: no masking needed for the count
             uint32_t ffc = 0;
-            for (uint32_t w = w0; w < w1; w++) {
-                const uint32_t v = S.seg[w];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (w * 4 + k < B && ((v >> (24 - 8 * k)) & 0xff) == 0xff) ffc++;
-            }
+            for (uint32_t w = w0; w < w1; w++) ffc += __popc(ff_bytes(S.u.seg[w]));
             uint32_t inc = ffc;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -278,10 +273,13 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
             if (fits) {
                 uint8_t *o = pkt + G + w0 * 4 + ff_before;
                 for (uint32_t w = w0; w < w1; w++) {
-                    const uint32_t v = S.seg[w];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (w * 4 + k < B) {
+                    const uint32_t v = S.u.seg[w];
+                    const uint32_t nvalid = min(4u, B - w * 4);
+                    if (nvalid == 4 && ff_bytes(v) == 0) {
+                        o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v;
+                        o += 4;
+                    } else {
+                        for (uint32_t k = 0; k < nvalid; k++) {
                             const uint8_t by = (uint8_t)(v >> (24 - 8 * k));
                             *o++ = by;
                             if (by == 0xff) *o++ = 0;
@@ -292,7 +290,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
             __syncthreads();
             if (t == 0) {
                 if (!fits && !S.overflow) S.overflow = AMV_ST_NOSPACE;
-                S.seg[0] = last_seg ? 0 : S.seg[R >> 5];        // carry the partial word
+                S.carry_word = last_seg ? 0 : S.u.seg[R >> 5];        // carry the partial word
             }
             G += B + ff_total;
             r = last_seg ? 0 : (R & 31);

@@ -26,6 +26,16 @@ AMV_HD constexpr int zigzag_at(int k) {
     return t[k];
 }
 
+// raster index -> zigzag scan position
+AMV_HD constexpr int zigzag_inv_at(int j) {
+    constexpr uint8_t t[64] = {
+         0,  1,  5,  6, 14, 15, 27, 28,  2,  4,  7, 13, 16, 26, 29, 42,
+         3,  8, 12, 17, 25, 30, 41, 43,  9, 11, 18, 24, 31, 40, 44, 53,
+        10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
+        21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63 };
+    return t[j];
+}
+
 // Decoder quantisers in zigzag order: sp5x_quant_table[10] / [11] (sp5x.h:187-195),
 // selected by sp5xdec.c:40,60-61.
 static const uint8_t kDecQuant[2][64] = {
