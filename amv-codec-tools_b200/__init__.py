@@ -17,6 +17,8 @@ import subprocess
 
 import numpy as np
 
+from . import sharding  # noqa: F401  (host-side multi-GPU partitioning)
+
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libamvcuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "amvcuda.h")

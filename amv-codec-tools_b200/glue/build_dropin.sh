@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# Builds glue/_build/dropin_check: the AVCodec shims (glue/ffmpeg/amvcuda_codecs.c) compiled against
+# the reference's own headers, linked with the reference's unmodified libavcodec objects (produced
+# by oracle/build_ref.sh) and with libamvcuda.so.  Needs the reference tree; the binary travels.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+REF="${AMV_REFERENCE_ROOT:-/root/reference}/AMVmuxer/ffmpeg"
+OBJ="$ROOT/oracle/_ref/obj"
+[ -d "$REF/libavcodec" ] || { echo "build_dropin: reference tree absent, keeping prebuilt binary" >&2; exit 0; }
+[ -d "$OBJ" ] || "$ROOT/oracle/build_ref.sh" > /dev/null
+mkdir -p "$HERE/_build"
+CFLAGS="-O2 -std=gnu99 -fgnu89-inline -fcommon -w -DHAVE_AV_CONFIG_H -D_GNU_SOURCE \
+ -I$ROOT/oracle/_ref/cfg -I$REF -I$REF/libavcodec -I$REF/libavutil -I$ROOT/include"
+gcc $CFLAGS -c "$HERE/ffmpeg/amvcuda_codecs.c" -o "$HERE/_build/amvcuda_codecs.o"
+# the checker is an API *user* of libavcodec (no HAVE_AV_CONFIG_H: that poisons printf/malloc)
+gcc ${CFLAGS/-DHAVE_AV_CONFIG_H/} -c "$HERE/ffmpeg/dropin_check.c" -o "$HERE/_build/dropin_check.o"
+OBJS=$(ls "$OBJ"/avc_*.o "$OBJ"/avu_*.o)
+gcc -o "$HERE/_build/dropin_check" "$HERE/_build/dropin_check.o" "$HERE/_build/amvcuda_codecs.o" $OBJS \
+    -L"$HERE/../lib" -lamvcuda -Wl,-rpath,'$ORIGIN/../../lib' -lm
+echo "built $HERE/_build/dropin_check"

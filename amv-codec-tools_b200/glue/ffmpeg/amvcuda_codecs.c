@@ -1,0 +1,233 @@
+/*
+ * amvcuda_codecs.c -- reference-side binding: AVCodec instances that drop libamvcuda into the
+ * AMVmuxer FFmpeg fork (libavcodec 51.47.1) in place of its CPU codecs.
+ *
+ * This file is compiled INSIDE the reference tree's include path (it needs avcodec.h); it is
+ * the stub a maintainer adds next to sp5xdec.c / mjpegenc.c / adpcm.c.  It holds no codec
+ * arithmetic: every callback translates AVCodecContext / AVFrame / packet fields and calls the
+ * C ABI of include/amvcuda.h with n = 1.
+ *
+ *   amvcuda_amv_decoder            replaces amv_decoder            (sp5xdec.c:203-212)
+ *   amvcuda_amv_encoder            replaces amv_encoder            (mjpegenc.c:485-494)
+ *   amvcuda_adpcm_ima_amv_decoder  replaces adpcm_ima_amv_decoder  (adpcm.c:1535)
+ *   amvcuda_adpcm_ima_amv_encoder  replaces adpcm_ima_amv_encoder  (adpcm.c:1535)
+ *
+ * avcodec_find_decoder/encoder return the FIRST registered match (utils.c:1023-1056), so
+ * amvcuda_register_codecs() must run before avcodec_register_all() -- or the four
+ * REGISTER_ENCDEC lines of allcodecs.c:64,255 are pointed at these symbols.
+ */
+#include <string.h>
+#include "avcodec.h"
+#include "amvcuda.h"
+
+/* ------------------------------------------------------------------------------ video decode */
+typedef struct AmvCudaVideoDec {
+    amv_ctx *h;
+    AVFrame picture;
+} AmvCudaVideoDec;
+
+static int amvcuda_dec_init(AVCodecContext *avctx)
+{
+    AmvCudaVideoDec *c = avctx->priv_data;
+    avctx->pix_fmt = PIX_FMT_YUVJ420P;                     /* mjpegdec.c:311-312 for 0x221111 */
+    return amv_create(NULL, &c->h) == AMV_OK ? 0 : -1;     /* no device => the codec cannot open: no CPU path */
+}
+
+static int amvcuda_dec_close(AVCodecContext *avctx)
+{
+    AmvCudaVideoDec *c = avctx->priv_data;
+    if (c->picture.data[0]) avctx->release_buffer(avctx, &c->picture);
+    amv_destroy(c->h);
+    c->h = NULL;
+    return 0;
+}
+
+/* same contract as sp5x_decode_frame (sp5xdec.c:33-93) + the EOI branch of
+ * ff_mjpeg_decode_frame (mjpegdec.c:1271-1297): decoder-owned picture from get_buffer, released
+ * on the next call (:327-328); key frame, I type, quality = FF_QP2LAMBDA * max qscale. */
+static int amvcuda_dec_frame(AVCodecContext *avctx, void *data, int *data_size, uint8_t *buf, int buf_size)
+{
+    AmvCudaVideoDec *c = avctx->priv_data;
+    AVFrame *out = data;
+    const int w = avctx->width, h = avctx->height;
+    uint64_t off = 0;
+    uint32_t size = (uint32_t)buf_size;
+    int32_t status = 0;
+
+    if (!w || !h) return -1;                               /* sp5xdec.c:45-46 */
+    avctx->pix_fmt = PIX_FMT_YUVJ420P;
+    if (c->picture.data[0]) avctx->release_buffer(avctx, &c->picture);
+    c->picture.reference = 0;
+    if (avctx->get_buffer(avctx, &c->picture) < 0) return -1;
+    c->picture.pict_type = FF_I_TYPE;
+    c->picture.key_frame = 1;
+    if (amv_decode_frames(c->h, buf, (uint64_t)buf_size, &off, &size, 1, w, h,
+                          c->picture.data[0], c->picture.data[1], c->picture.data[2],
+                          c->picture.linesize[0], c->picture.linesize[1],
+                          (uint64_t)c->picture.linesize[0] * h, (uint64_t)c->picture.linesize[1] * ((h + 1) / 2),
+                          &status, AMV_MEM_HOST) != AMV_OK)
+        return -1;
+    /* scan errors are swallowed by the reference too (mjpegdec.c:1300): the picture is returned */
+    *out = c->picture;
+    /* qscale[i] = max(q[1], q[8]) >> 1 of the two fixed tables (mjpegdec.c:137-139): 10>>1 and 19>>1 */
+    out->quality = 9 * FF_QP2LAMBDA;
+    *data_size = sizeof(AVFrame);
+    return buf_size;
+}
+
+AVCodec amvcuda_amv_decoder = {
+    "amv", CODEC_TYPE_VIDEO, CODEC_ID_AMV, sizeof(AmvCudaVideoDec),
+    amvcuda_dec_init, NULL, amvcuda_dec_close, amvcuda_dec_frame,
+};
+
+/* ------------------------------------------------------------------------------ video encode */
+typedef struct AmvCudaVideoEnc {
+    amv_ctx *h;
+    AVFrame coded;
+} AmvCudaVideoEnc;
+
+static int amvcuda_enc_init(AVCodecContext *avctx)
+{
+    AmvCudaVideoEnc *c = avctx->priv_data;
+    /* what MPV_encode_init accepts for CODEC_ID_AMV (mpegvideo_enc.c:249-257) minus 4:2:2, which the
+     * reference's own decoder cannot read; options outside the contract are refused */
+    if (avctx->pix_fmt != PIX_FMT_YUVJ420P && avctx->pix_fmt != PIX_FMT_YUV420P) return -1;
+    if (avctx->thread_count > 1 || avctx->trellis || avctx->intra_dc_precision || (avctx->flags & CODEC_FLAG_GRAY)) return -1;
+    if (!avctx->time_base.num || !avctx->time_base.den) return -1;    /* mpegvideo_enc.c:461-464 */
+    avctx->coded_frame = &c->coded;
+    avctx->delay = 0;
+    return amv_create(NULL, &c->h) == AMV_OK ? 0 : -1;
+}
+
+static int amvcuda_enc_close(AVCodecContext *avctx)
+{
+    AmvCudaVideoEnc *c = avctx->priv_data;
+    amv_destroy(c->h);
+    c->h = NULL;
+    return 0;
+}
+
+/* amv_encode_picture (mjpegenc.c:454-472): one frame in, one packet out, delay 0.
+ * The reference flips pic->data/linesize in place; callers never rely on that, we leave pic alone. */
+static int amvcuda_enc_frame(AVCodecContext *avctx, uint8_t *buf, int buf_size, void *data)
+{
+    AmvCudaVideoEnc *c = avctx->priv_data;
+    AVFrame *pic = data;
+    const int w = avctx->width, h = avctx->height;
+    int32_t qscale, status = 0;
+    uint64_t off = 0;
+    uint32_t size = 0;
+
+    if (avctx->flags & CODEC_FLAG_EMU_EDGE) return -1;                       /* mjpegenc.c:463-464 */
+    qscale = amv_qscale_from_quality(pic->quality, avctx->qmin, avctx->qmax);  /* update_qscale */
+    if (amv_encode_frames(c->h, pic->data[0], pic->data[1], pic->data[2], pic->linesize[0], pic->linesize[1],
+                          (uint64_t)pic->linesize[0] * h, (uint64_t)pic->linesize[1] * ((h + 1) / 2),
+                          1, w, h, &qscale, buf, (uint64_t)buf_size, (uint32_t)buf_size, AMV_LAYOUT_SLOTS,
+                          &off, &size, &status, AMV_MEM_HOST) != AMV_OK)
+        return -1;
+    if (status) return -1;                                  /* "encoded frame too large" (mpegvideo_enc.c:2077-2080) */
+    c->coded.key_frame = 1;
+    c->coded.pict_type = FF_I_TYPE;
+    c->coded.quality = pic->quality;
+    c->coded.pts = pic->pts;
+    return (int)size;
+}
+
+static const enum PixelFormat amvcuda_pix_fmts[] = { PIX_FMT_YUVJ420P, -1 };
+
+AVCodec amvcuda_amv_encoder = {
+    "amv", CODEC_TYPE_VIDEO, CODEC_ID_AMV, sizeof(AmvCudaVideoEnc),
+    amvcuda_enc_init, amvcuda_enc_frame, amvcuda_enc_close, NULL,
+    .pix_fmts = amvcuda_pix_fmts,
+};
+
+/* ------------------------------------------------------------------------------------- audio */
+typedef struct AmvCudaAudio {
+    amv_ctx *h;
+    AVFrame coded;
+    int16_t step_index;          /* carried across calls like ADPCMChannelStatus.step_index (adpcm.c:466) */
+    int extra_amv_samples;       /* adpcm.c:148-149 */
+    int samples_written;
+} AmvCudaAudio;
+
+static int amvcuda_adpcm_init(AVCodecContext *avctx)
+{
+    AmvCudaAudio *c = avctx->priv_data;
+    if (avctx->codec->encode) {                                           /* adpcm.c:190-199 */
+        if (avctx->channels != 1 || avctx->sample_rate != 22050 || avctx->trellis > 0) return -1;
+        avctx->coded_frame = &c->coded;
+        c->coded.key_frame = 1;
+    } else if (avctx->channels > 2) return -1;
+    return amv_create(NULL, &c->h) == AMV_OK ? 0 : -1;
+}
+
+static int amvcuda_adpcm_close(AVCodecContext *avctx)
+{
+    AmvCudaAudio *c = avctx->priv_data;
+    amv_destroy(c->h);
+    c->h = NULL;
+    return 0;
+}
+
+/* adpcm_decode_frame, AMV case (adpcm.c:894-935,1268-1292) */
+static int amvcuda_adpcm_dec_frame(AVCodecContext *avctx, void *data, int *data_size, uint8_t *buf, int buf_size)
+{
+    AmvCudaAudio *c = avctx->priv_data;
+    uint64_t off = 0, pcm_off = 0;
+    uint32_t size = (uint32_t)buf_size;
+    int32_t status = 0;
+    if (!buf_size) return 0;
+    if (*data_size / 4 < buf_size + 8) return -1;                          /* adpcm.c:924 */
+    *data_size = 0;
+    if (buf_size < 8) return buf_size;
+    if (amv_adpcm_dec_chunks(c->h, buf, (uint64_t)buf_size, &off, &size, 1, (int16_t *)data,
+                             2ull * (buf_size - 8), &pcm_off, &status, AMV_MEM_HOST) != AMV_OK || status)
+        return -1;
+    *data_size = 4 * (buf_size - 8);
+    return buf_size;
+}
+
+/* adpcm_encode_frame, AMV case (adpcm.c:461-496): the chunk takes 2n samples where n follows the
+ * reference's frame_size / odd-sample / second-boundary bookkeeping; the step index is chained. */
+static int amvcuda_adpcm_enc_frame(AVCodecContext *avctx, unsigned char *frame, int buf_size, void *data)
+{
+    AmvCudaAudio *c = avctx->priv_data;
+    uint64_t pcm_off = 0, out_off = 0;
+    uint32_t nsamples;
+    int16_t step_out = 0;
+    int32_t status = 0;
+    int n, i;
+    avctx->coded_frame->pts = c->samples_written;
+    n = avctx->frame_size >> 1;
+    c->extra_amv_samples += avctx->frame_size & 1;
+    n += c->extra_amv_samples >> 1;
+    c->extra_amv_samples &= 1;
+    i = (c->samples_written + 2 * n) % avctx->sample_rate;
+    if (i && i + avctx->frame_size > avctx->sample_rate) n += (avctx->sample_rate - i) >> 1;
+    nsamples = 2u * (uint32_t)n;
+    if (buf_size < 8 + n) return -1;
+    if (amv_adpcm_enc_chunks(c->h, (const int16_t *)data, nsamples, &pcm_off, &nsamples, &c->step_index, &step_out, 1,
+                             frame, (uint64_t)(8 + n), &out_off, &status, AMV_MEM_HOST) != AMV_OK || status)
+        return -1;
+    c->step_index = step_out;
+    c->samples_written += (int)nsamples;
+    return 8 + n;
+}
+
+AVCodec amvcuda_adpcm_ima_amv_decoder = {
+    "adpcm_ima_amv", CODEC_TYPE_AUDIO, CODEC_ID_ADPCM_IMA_AMV, sizeof(AmvCudaAudio),
+    amvcuda_adpcm_init, NULL, amvcuda_adpcm_close, amvcuda_adpcm_dec_frame,
+};
+AVCodec amvcuda_adpcm_ima_amv_encoder = {
+    "adpcm_ima_amv", CODEC_TYPE_AUDIO, CODEC_ID_ADPCM_IMA_AMV, sizeof(AmvCudaAudio),
+    amvcuda_adpcm_init, amvcuda_adpcm_enc_frame, amvcuda_adpcm_close, NULL,
+};
+
+/* Call before avcodec_register_all(): first match wins in avcodec_find_{en,de}coder. */
+void amvcuda_register_codecs(void)
+{
+    register_avcodec(&amvcuda_amv_encoder);
+    register_avcodec(&amvcuda_amv_decoder);
+    register_avcodec(&amvcuda_adpcm_ima_amv_encoder);
+    register_avcodec(&amvcuda_adpcm_ima_amv_decoder);
+}

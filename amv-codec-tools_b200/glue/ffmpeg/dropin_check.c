@@ -1,0 +1,160 @@
+/*
+ * dropin_check.c -- exercises the AVCodec drop-in exactly the way ffmpeg.c drives a codec
+ * (avcodec_find_* -> avcodec_open -> avcodec_{en,de}code_* per frame/chunk, ffmpeg.c:1062,1083,522,814)
+ * once with the libamvcuda shims registered first and once with the reference's own codecs, and
+ * compares packets, planes, chunks and PCM byte for byte.  Built against the reference's headers
+ * and objects by glue/build_dropin.sh (only where the reference tree is mounted); the binary
+ * travels to the GPU box.  Exit code 0 = identical.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "avcodec.h"
+
+extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder;
+extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_decoder, amvcuda_adpcm_ima_amv_encoder;
+void amvcuda_register_codecs(void);
+
+static unsigned rng_state = 12345;
+static unsigned rnd(void) { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+
+static void make_frame(uint8_t *y, uint8_t *u, uint8_t *v, int w, int h, int t)
+{
+    int cw = (w + 1) / 2, ch = (h + 1) / 2, x, r;
+    for (r = 0; r < h; r++) for (x = 0; x < w; x++) {
+        double s = 128 + 60 * sin((x + 3 * t) / 17.0) + 50 * cos((r - 2 * t) / 11.0) + (int)(rnd() % 25) - 12;
+        y[r * w + x] = s < 0 ? 0 : (s > 255 ? 255 : (uint8_t)s);
+    }
+    for (r = 0; r < ch; r++) for (x = 0; x < cw; x++) {
+        u[r * cw + x] = (uint8_t)(128 + 40 * sin((x + t) / 23.0));
+        v[r * cw + x] = (uint8_t)(128 + 40 * cos((r + t) / 19.0));
+    }
+}
+
+typedef struct { uint8_t *pk; int size; } Packet;
+
+static int encode_all(AVCodec *codec, int w, int h, int n, int quality, uint8_t **ys, uint8_t **us, uint8_t **vs, Packet *out)
+{
+    AVCodecContext *c = avcodec_alloc_context();
+    AVFrame *pic = avcodec_alloc_frame();
+    int i, bufsz = w * h * 6 + 262144, cw = (w + 1) / 2;
+    uint8_t *buf = av_malloc(bufsz);
+    c->width = w; c->height = h; c->time_base.num = 1; c->time_base.den = 16; c->pix_fmt = PIX_FMT_YUVJ420P;
+    if (avcodec_open(c, codec) < 0) return -1;
+    for (i = 0; i < n; i++) {
+        pic->data[0] = ys[i]; pic->data[1] = us[i]; pic->data[2] = vs[i];
+        pic->linesize[0] = w; pic->linesize[1] = cw; pic->linesize[2] = cw;
+        pic->quality = quality; pic->pts = i;
+        int sz = avcodec_encode_video(c, buf, bufsz, pic);
+        if (sz < 0) return -2;
+        out[i].pk = malloc(sz + FF_INPUT_BUFFER_PADDING_SIZE); memset(out[i].pk, 0, sz + FF_INPUT_BUFFER_PADDING_SIZE);
+        memcpy(out[i].pk, buf, sz); out[i].size = sz;
+        if (!c->coded_frame->key_frame) return -3;
+    }
+    avcodec_close(c); av_free(c); av_free(pic); av_free(buf);
+    return 0;
+}
+
+static int decode_all(AVCodec *codec, int w, int h, int n, Packet *pk, uint8_t *planes /* n * w*h*3/2 tight */)
+{
+    AVCodecContext *c = avcodec_alloc_context();
+    AVFrame *pic = avcodec_alloc_frame();
+    int i, r, cw = (w + 1) / 2, ch = (h + 1) / 2;
+    c->width = w; c->height = h; c->coded_width = w; c->coded_height = h;
+    if (avcodec_open(c, codec) < 0) return -1;
+    for (i = 0; i < n; i++) {
+        int got = 0;
+        int ret = avcodec_decode_video(c, pic, &got, pk[i].pk, pk[i].size);
+        if (ret < 0 || !got) return -2;
+        if (!pic->key_frame || pic->pict_type != FF_I_TYPE || c->pix_fmt != PIX_FMT_YUVJ420P) return -3;
+        uint8_t *d = planes + (size_t)i * (w * h + 2 * cw * ch);
+        for (r = 0; r < h; r++) memcpy(d + r * w, pic->data[0] + r * pic->linesize[0], w);
+        for (r = 0; r < ch; r++) {
+            memcpy(d + w * h + r * cw, pic->data[1] + r * pic->linesize[1], cw);
+            memcpy(d + w * h + cw * ch + r * cw, pic->data[2] + r * pic->linesize[2], cw);
+        }
+    }
+    avcodec_close(c); av_free(c); av_free(pic);
+    return 0;
+}
+
+static int audio_roundtrip(AVCodec *enc, AVCodec *dec, const int16_t *pcm, int total, int frame_size,
+                           uint8_t *chunks, int *chunk_bytes, int16_t *out_pcm, int *out_samples)
+{
+    AVCodecContext *e = avcodec_alloc_context(), *d = avcodec_alloc_context();
+    int pos = 0, cb = 0, os = 0;
+    uint8_t buf[FF_MIN_BUFFER_SIZE + 65536];
+    int16_t *tmp = av_malloc(AVCODEC_MAX_AUDIO_FRAME_SIZE * 2);
+    e->channels = 1; e->sample_rate = 22050; e->frame_size = frame_size;
+    d->channels = 1; d->sample_rate = 22050;
+    if (avcodec_open(e, enc) < 0 || avcodec_open(d, dec) < 0) return -1;
+    e->frame_size = frame_size;
+    while (pos + 2 * frame_size + 2 <= total) {
+        int sz = avcodec_encode_audio(e, buf, sizeof(buf), pcm + pos);
+        if (sz < 8) return -2;
+        int two_n = buf[4] | (buf[5] << 8) | (buf[6] << 16) | (buf[7] << 24);
+        memcpy(chunks + cb, buf, sz); cb += sz; pos += two_n;
+        int bytes = AVCODEC_MAX_AUDIO_FRAME_SIZE * 2;
+        if (avcodec_decode_audio2(d, tmp, &bytes, buf, sz) < 0) return -3;
+        memcpy(out_pcm + os, tmp, bytes); os += bytes / 2;
+    }
+    *chunk_bytes = cb; *out_samples = os;
+    avcodec_close(e); avcodec_close(d); av_free(e); av_free(d); av_free(tmp);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    const int w = argc > 1 ? atoi(argv[1]) : 160, h = argc > 2 ? atoi(argv[2]) : 120, n = argc > 3 ? atoi(argv[3]) : 24;
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2, fb = w * h + 2 * cw * ch;
+    int i, fail = 0;
+    avcodec_init();
+    av_log_set_level(AV_LOG_QUIET);
+    amvcuda_register_codecs();                       /* first match wins ...                              */
+    register_avcodec(&amv_encoder); register_avcodec(&amv_decoder);   /* ... then what avcodec_register_all adds */
+    register_avcodec(&adpcm_ima_amv_encoder); register_avcodec(&adpcm_ima_amv_decoder);
+    if (avcodec_find_decoder(CODEC_ID_AMV) != &amvcuda_amv_decoder || avcodec_find_encoder(CODEC_ID_AMV) != &amvcuda_amv_encoder ||
+        avcodec_find_decoder(CODEC_ID_ADPCM_IMA_AMV) != &amvcuda_adpcm_ima_amv_decoder ||
+        avcodec_find_encoder(CODEC_ID_ADPCM_IMA_AMV) != &amvcuda_adpcm_ima_amv_encoder) {
+        printf("FAIL: lookup does not return the drop-in codecs\n");
+        return 2;
+    }
+    uint8_t **ys = malloc(n * sizeof(*ys)), **us = malloc(n * sizeof(*us)), **vs = malloc(n * sizeof(*vs));
+    for (i = 0; i < n; i++) {
+        ys[i] = malloc(w * h); us[i] = malloc(cw * ch); vs[i] = malloc(cw * ch);
+        make_frame(ys[i], us[i], vs[i], w, h, i);
+    }
+    int q;
+    for (q = 0; q <= 2; q++) {
+        const int quality = q == 0 ? 0 : (q == 1 ? 5 * FF_QP2LAMBDA : 31 * FF_QP2LAMBDA);
+        Packet *pa = calloc(n, sizeof(Packet)), *pb = calloc(n, sizeof(Packet));
+        int ra = encode_all(avcodec_find_encoder(CODEC_ID_AMV), w, h, n, quality, ys, us, vs, pa);
+        int rb = encode_all(&amv_encoder, w, h, n, quality, ys, us, vs, pb);
+        if (ra || rb) { printf("FAIL: encode returned %d / %d\n", ra, rb); return 3; }
+        for (i = 0; i < n; i++)
+            if (pa[i].size != pb[i].size || memcmp(pa[i].pk, pb[i].pk, pa[i].size)) { printf("FAIL: packet %d differs (quality %d)\n", i, quality); fail = 1; }
+        uint8_t *da = malloc((size_t)n * fb), *db = malloc((size_t)n * fb);
+        ra = decode_all(avcodec_find_decoder(CODEC_ID_AMV), w, h, n, pb, da);
+        rb = decode_all(&amv_decoder, w, h, n, pb, db);
+        if (ra || rb) { printf("FAIL: decode returned %d / %d\n", ra, rb); return 4; }
+        if (memcmp(da, db, (size_t)n * fb)) { printf("FAIL: decoded planes differ (quality %d)\n", quality); fail = 1; }
+        printf("video %dx%d x%d quality %d: packets and planes %s\n", w, h, n, quality, fail ? "DIFFER" : "identical");
+        free(da); free(db);
+    }
+    {
+        const int total = 22050 * 2 + 999, fs = 1378;
+        int16_t *pcm = malloc(total * 2), *oa = malloc(total * 4), *ob = malloc(total * 4);
+        uint8_t *ca = malloc(total), *cb = malloc(total);
+        int cba = 0, cbb = 0, sa = 0, sb = 0;
+        for (i = 0; i < total; i++) pcm[i] = (int16_t)(8000 * sin(i * 0.1254) + 2000 * sin(i * 0.3516) + (int)(rnd() % 200));
+        int ra = audio_roundtrip(avcodec_find_encoder(CODEC_ID_ADPCM_IMA_AMV), avcodec_find_decoder(CODEC_ID_ADPCM_IMA_AMV),
+                                 pcm, total, fs, ca, &cba, oa, &sa);
+        int rb = audio_roundtrip(&adpcm_ima_amv_encoder, &adpcm_ima_amv_decoder, pcm, total, fs, cb, &cbb, ob, &sb);
+        if (ra || rb) { printf("FAIL: audio returned %d / %d\n", ra, rb); return 5; }
+        if (cba != cbb || memcmp(ca, cb, cba) || sa != sb || memcmp(oa, ob, sa * 2)) { printf("FAIL: audio differs\n"); fail = 1; }
+        printf("audio %d samples: %d chunk bytes, %d decoded samples %s\n", total, cba, sa, fail ? "DIFFER" : "identical");
+    }
+    printf(fail ? "DROP-IN CHECK FAILED\n" : "DROP-IN CHECK OK\n");
+    return fail;
+}

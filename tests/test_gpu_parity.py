@@ -320,3 +320,19 @@ def test_roundtrip_properties_large_batch(ctx, oracle):
     wy, wu, wv, _ = oracle.decode_frames(bpk, boff, bsz, w, h)
     for i in range(0, n, 37):
         assert np.array_equal(dy[i], wy[idx[i]]) and np.array_equal(du[i], wu[idx[i]]) and np.array_equal(dv[i], wv[idx[i]])
+
+
+# ------------------------------------------------------------------ the drop-in boundary itself
+DROPIN = os.path.join(amv.PKG_DIR, "glue", "_build", "dropin_check")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="glue/_build/dropin_check not built (needs the reference tree)")
+@pytest.mark.parametrize("w,h,n", [(160, 120, 24), (320, 240, 6), (208, 176, 5)])
+def test_avcodec_dropin_matches_reference_codecs(w, h, n):
+    """The reference's own libavcodec, driven like ffmpeg.c drives it, once with the libamvcuda AVCodec
+    shims registered first (avcodec_find_* returns them) and once with its CPU codecs: identical
+    packets, planes, ADPCM chunks and PCM (glue/ffmpeg/dropin_check.c)."""
+    import subprocess
+    out = subprocess.run([DROPIN, str(w), str(h), str(n)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "DROP-IN CHECK OK" in out.stdout
