@@ -49,6 +49,12 @@ struct amv_ctx {
     uint32_t last_rounds = 0;
     std::string err;
     DevBuf ws[WS_COUNT];
+    // host-memory calls: copy-in / copy-out streams next to the compute stream, and a pinned
+    // bounce buffer for the per-frame metadata (the caller's arrays may be pageable)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    void *pinned_meta = nullptr;
+    size_t pinned_meta_cap = 0;
+    int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
 };
 
 namespace {
@@ -125,14 +131,15 @@ int pick_log2p(const amv_ctx *ctx, int n) {
 }
 
 // ---------------------------------------------------------------------------------- device paths
+// payload_bytes: upper bound of the bytes of the n packets (pkts_bytes if unknown); sizes the scratch
 int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                   const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
-                  uint64_t fs_y, uint64_t fs_c, int32_t *status) {
+                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes) {
     const Geom g = make_geom(w, h);
     const int log2p = pick_log2p(ctx, n);
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
     uint32_t *rounds; uint16_t *tokens; uint32_t *blk_off;
-    const uint64_t scratch_bytes = pkts_bytes + (uint64_t)(kSlotPad + 16) * n + 64;
+    const uint64_t scratch_bytes = payload_bytes + (uint64_t)(kSlotPad + 16) * n + 64;
     ENSURE(WS_SLOT_OFF, sizeof(uint64_t) * n, slot_off);
     ENSURE(WS_SCAN_LEN, sizeof(uint32_t) * n, scan_len);
     ENSURE(WS_SCRATCH, scratch_bytes, scratch);
@@ -170,15 +177,16 @@ bool encode_geometry_ok(int w, int h) {
 
 int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
                   uint64_t fs_c, int n, int w, int h, const int32_t *qscale, uint8_t *out, uint64_t out_cap,
-                  uint32_t pkt_cap, int layout, uint64_t *out_off, uint32_t *out_size, int32_t *status) {
+                  uint32_t pkt_cap, int layout, uint64_t *out_off, uint32_t *out_size, int32_t *status,
+                  bool reset_carry = true, uint64_t slot_base = 0) {
     const Geom g = make_geom(w, h);
     int32_t *st = status;
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
     if (layout == AMV_LAYOUT_SLOTS) {
-        if ((uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
+        if (slot_base + (uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
         { ScopedTimer tm(ctx, KK_ENCODE);
-          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out, pkt_cap, pkt_cap, out_size, st, ctx->stream); }
-        launch_slot_offsets(out_off, n, pkt_cap, ctx->stream);
+          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out + slot_base, pkt_cap, pkt_cap, out_size, st, ctx->stream); }
+        launch_slot_offsets(out_off, n, pkt_cap, slot_base, ctx->stream);
         return check_launch(ctx, "encode kernels", 2);
     }
     // packed: encode into 16-byte aligned workspace slots, scan the sizes, compact
@@ -189,7 +197,7 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
     uint8_t *slots; uint64_t *carry;
     ENSURE(WS_SLOTS, stride * sub + 64, slots);
     ENSURE(WS_CARRY, sizeof(uint64_t), carry);
-    CK(cudaMemsetAsync(carry, 0, sizeof(uint64_t), ctx->stream));
+    if (reset_carry) CK(cudaMemsetAsync(carry, 0, sizeof(uint64_t), ctx->stream));
     int lc = 0;
     for (int f0 = 0; f0 < n; f0 += sub) {
         const int m = n - f0 < sub ? n - f0 : sub;
@@ -234,6 +242,248 @@ int copy_planes(amv_ctx *ctx, uint8_t *dev, uint8_t *host, int width, int height
         if (to_host) CK(cudaMemcpy2DAsync(host + fs * i, ls, dev + tight * i, width, width, height, kind, ctx->stream));
         else         CK(cudaMemcpy2DAsync(dev + tight * i, width, host + fs * i, ls, width, height, kind, ctx->stream));
     }
+    return AMV_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ host pipeline
+// AMV_MEM_HOST calls run as a three-stage pipeline over chunks of frames: copy-in of chunk i+1
+// (stream s_in), kernels of chunk i (the context's stream), copy-out of chunk i-1 (stream s_out),
+// so PCIe traffic in both directions overlaps the compute.  Chunk buffers are rings of 3.
+constexpr int kRing = 3;
+
+int ensure_pipeline(amv_ctx *ctx, size_t meta_bytes) {
+    if (!ctx->s_in) CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    if (meta_bytes > ctx->pinned_meta_cap) {
+        CK(cudaStreamSynchronize(ctx->s_out));
+        if (ctx->pinned_meta) cudaFreeHost(ctx->pinned_meta);
+        ctx->pinned_meta = nullptr; ctx->pinned_meta_cap = 0;
+        CK(cudaMallocHost(&ctx->pinned_meta, meta_bytes + 4096));
+        ctx->pinned_meta_cap = meta_bytes + 4096;
+    }
+    return AMV_OK;
+}
+
+int host_chunk_frames(const amv_ctx *ctx, int n, size_t frame_bytes) {
+    if (ctx->opt_host_chunk > 0) return ctx->opt_host_chunk < n ? ctx->opt_host_chunk : n;
+    // ~8 stages per call, between 96 MB and 512 MB of frames per stage: a stage costs ~10 launches
+    // and one host wake-up, which must stay small against its PCIe time (~2 ms per 100 MB)
+    int c = (n + 7) / 8;
+    const int lo = (int)((96u << 20) / frame_bytes) + 1, hi = (int)((512u << 20) / frame_bytes) + 1;
+    if (c < lo) c = lo;
+    if (c > hi) c = hi;
+    return c < n ? c : n;
+}
+
+// Large transfers are issued in pieces: a copy engine serves its queue in submission order, so a
+// short copy of another stream (metadata, the other direction's packets) would otherwise wait
+// behind a 100+ MB transfer and stall that stream's whole pipeline.
+constexpr size_t kCopyPiece = 16u << 20;
+cudaError_t copy_pieces(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+    for (size_t o = 0; o < bytes; o += kCopyPiece) {
+        const size_t m = bytes - o < kCopyPiece ? bytes - o : kCopyPiece;
+        cudaError_t e = cudaMemcpyAsync((uint8_t *)dst + o, (const uint8_t *)src + o, m, kind, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// planes of frames [f0, f0+m): host (ls, fs) layout <-> tight device layout, on stream s
+int copy_planes_on(amv_ctx *ctx, cudaStream_t s, uint8_t *dev, uint8_t *host, int width, int height, int ls, uint64_t fs,
+                   int m, bool to_host) {
+    const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+    const uint64_t tight = (uint64_t)width * height;
+    if (ls == width && fs == tight) {
+        if (to_host) CK(copy_pieces(host, dev, tight * m, kind, s));
+        else         CK(copy_pieces(dev, host, tight * m, kind, s));
+        return AMV_OK;
+    }
+    for (int i = 0; i < m; i++) {
+        if (to_host) CK(cudaMemcpy2DAsync(host + fs * i, ls, dev + tight * i, width, width, height, kind, s));
+        else         CK(cudaMemcpy2DAsync(dev + tight * i, width, host + fs * i, ls, width, height, kind, s));
+    }
+    return AMV_OK;
+}
+
+struct EventRing {
+    cudaEvent_t e[kRing] = { nullptr, nullptr, nullptr };
+    bool used[kRing] = { false, false, false };
+    ~EventRing() { for (int i = 0; i < kRing; i++) if (e[i]) cudaEventDestroy(e[i]); }
+    cudaError_t init() {
+        for (int i = 0; i < kRing; i++) {
+            cudaError_t r = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming);
+            if (r != cudaSuccess) return r;
+        }
+        return cudaSuccess;
+    }
+};
+
+// Device-accessible alias of a pinned (page-locked) host buffer, or NULL if the buffer is pageable.
+// Under UVA every cudaMallocHost / cudaHostRegister allocation is mapped into the device's address
+// space, so kernels can read and write it directly over PCIe.
+void *device_view(const void *host_ptr) {
+    if (!host_ptr) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
+    return nullptr;
+}
+
+// How the host path moves data:
+//  * bulk planes travel by DMA (cudaMemcpyAsync, in <= 16 MB pieces) on their own copy streams, in a
+//    3-deep ring of chunks that overlaps copy-in, kernels and copy-out;
+//  * everything small and latency-critical -- per-frame metadata, the decoder's input packets, the
+//    encoder's packed output -- never enters a copy-engine queue: the kernels read / write the
+//    caller's pinned buffers (or the context's own pinned bounce buffer) in place.  A copy engine
+//    serves its queue strictly in submission order, so a 16-byte status copy queued behind another
+//    call's gigabyte of planes would otherwise stall a whole pipeline (measured: two concurrent
+//    calls, one H2D-bound and one D2H-bound, ran at the SUM of their times).
+
+int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
+                int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                int32_t *status) {
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
+    // pinned bounce: status (4) + offsets (8) + sizes (4) per frame
+    int r = ensure_pipeline(ctx, 16 * (size_t)n);
+    if (r != AMV_OK) return r;
+    uint64_t *p_off = reinterpret_cast<uint64_t *>(ctx->pinned_meta);
+    uint32_t *p_sz = reinterpret_cast<uint32_t *>(p_off + n);
+    int32_t *p_st = reinterpret_cast<int32_t *>(p_sz + n);
+    // offsets / sizes: read in place if the caller's arrays are pinned, else from our pinned copy
+    const uint64_t *v_off = static_cast<const uint64_t *>(device_view(pkt_off));
+    const uint32_t *v_sz = static_cast<const uint32_t *>(device_view(pkt_size));
+    if (!v_off) { memcpy(p_off, pkt_off, sizeof(uint64_t) * n); v_off = static_cast<const uint64_t *>(device_view(p_off)); }
+    if (!v_sz) { memcpy(p_sz, pkt_size, sizeof(uint32_t) * n); v_sz = static_cast<const uint32_t *>(device_view(p_sz)); }
+    int32_t *v_st = static_cast<int32_t *>(device_view(p_st));
+    if (!v_off || !v_sz || !v_st) return fail(ctx, AMV_ERR_CUDA, "pinned bounce buffer is not device-mapped");
+    const uint8_t *v_pk = static_cast<const uint8_t *>(device_view(pkts));    // zero-copy packets if pinned
+    uint8_t *d_pk = nullptr, *d_y, *d_u, *d_v; int32_t *d_st;
+    if (!v_pk) ENSURE(WS_H_A, pkts_bytes ? pkts_bytes : 1, d_pk);
+    ENSURE(WS_H_D, ty * C * kRing, d_y);
+    ENSURE(WS_H_E, tc * C * kRing, d_u);
+    ENSURE(WS_H_F, tc * C * kRing, d_v);
+    ENSURE(WS_H_G, sizeof(int32_t) * n, d_st);
+    EventRing e_in, e_cmp, e_out;
+    if (e_in.init() != cudaSuccess || e_cmp.init() != cudaSuccess || e_out.init() != cudaSuccess)
+        return fail(ctx, AMV_ERR_CUDA, "cudaEventCreate");
+    int rc = AMV_OK;
+    const int nchunks = (n + C - 1) / C;
+    for (int i = 0; i < nchunks && rc == AMV_OK; i++) {
+        const int f0 = i * C, m = n - f0 < C ? n - f0 : C, slot = i % kRing;
+        uint64_t lo = UINT64_MAX, hi = 0, payload = 0;
+        for (int f = f0; f < f0 + m; f++) {
+            const uint64_t a = pkt_off[f], b = a + pkt_size[f];
+            payload += ((uint64_t)pkt_size[f] + 15) & ~15ull;
+            if (b > pkts_bytes || b < a) continue;        // reported per frame by the kernels
+            if (a < lo) lo = a;
+            if (b > hi) hi = b;
+        }
+        if (!v_pk) {       // pageable packets: staged copy of this chunk's byte range
+            if (hi > lo) CK(copy_pieces(d_pk + lo, pkts + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_in));
+            CK(cudaEventRecord(e_in.e[slot], ctx->s_in));
+            CK(cudaStreamWaitEvent(ctx->stream, e_in.e[slot], 0));
+        }
+        if (e_out.used[slot]) CK(cudaStreamWaitEvent(ctx->stream, e_out.e[slot], 0));      // ring slot drained?
+        rc = decode_device(ctx, v_pk ? v_pk : d_pk, pkts_bytes, v_off + f0, v_sz + f0, m, w, h, d_y + ty * C * slot,
+                           d_u + tc * C * slot, d_v + tc * C * slot, w, cw, ty, tc, d_st + f0, payload);
+        if (rc != AMV_OK) break;
+        CK(cudaEventRecord(e_cmp.e[slot], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, e_cmp.e[slot], 0));
+        if ((rc = copy_planes_on(ctx, ctx->s_out, d_y + ty * C * slot, y + fs_y * f0, w, h, ls_y, fs_y, m, true)) != AMV_OK) break;
+        if ((rc = copy_planes_on(ctx, ctx->s_out, d_u + tc * C * slot, u + fs_c * f0, cw, ch, ls_c, fs_c, m, true)) != AMV_OK) break;
+        if ((rc = copy_planes_on(ctx, ctx->s_out, d_v + tc * C * slot, v + fs_c * f0, cw, ch, ls_c, fs_c, m, true)) != AMV_OK) break;
+        CK(cudaEventRecord(e_out.e[slot], ctx->s_out));
+        e_out.used[slot] = true;
+    }
+    if (rc == AMV_OK) { launch_export_meta(nullptr, nullptr, d_st, nullptr, nullptr, v_st, n, ctx->stream); ctx->launches++; }
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->s_out);
+    if (rc != AMV_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, AMV_ERR_CUDA, "decode pipeline", e);
+    if (status) memcpy(status, p_st, sizeof(int32_t) * n);
+    return AMV_OK;
+}
+
+int encode_host(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
+                uint64_t fs_c, int n, int w, int h, const int32_t *qscale, uint8_t *out, uint64_t out_cap, uint32_t pkt_cap,
+                int layout, uint64_t *out_off, uint32_t *out_size, int32_t *status) {
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
+    // pinned metadata: offsets (8), sizes (4), status (4), qscale (4) per frame
+    int r = ensure_pipeline(ctx, 20 * (size_t)n);
+    if (r != AMV_OK) return r;
+    uint64_t *p_off = reinterpret_cast<uint64_t *>(ctx->pinned_meta);
+    uint32_t *p_sz = reinterpret_cast<uint32_t *>(p_off + n);
+    int32_t *p_st = reinterpret_cast<int32_t *>(p_sz + n);
+    int32_t *p_q = p_st + n;
+    uint64_t *v_off = static_cast<uint64_t *>(device_view(p_off));
+    uint32_t *v_sz = static_cast<uint32_t *>(device_view(p_sz));
+    int32_t *v_st = static_cast<int32_t *>(device_view(p_st));
+    const int32_t *v_q = nullptr;
+    if (qscale) {
+        v_q = static_cast<const int32_t *>(device_view(qscale));
+        if (!v_q) { memcpy(p_q, qscale, sizeof(int32_t) * n); v_q = static_cast<const int32_t *>(device_view(p_q)); }
+    }
+    if (!v_off || !v_sz || !v_st || (qscale && !v_q)) return fail(ctx, AMV_ERR_CUDA, "pinned bounce buffer is not device-mapped");
+    // packed output into a pinned caller buffer is written in place by k_compact (128-bit stores over
+    // PCIe); slot layout (byte stores) and pageable buffers are staged in device memory and copied
+    uint8_t *v_out = layout == AMV_LAYOUT_PACKED ? static_cast<uint8_t *>(device_view(out)) : nullptr;
+    uint8_t *d_y, *d_u, *d_v, *d_out = nullptr; uint64_t *d_off; uint32_t *d_sz; int32_t *d_st;
+    ENSURE(WS_H_A, ty * C * kRing, d_y);
+    ENSURE(WS_H_B, tc * C * kRing, d_u);
+    ENSURE(WS_H_C, tc * C * kRing, d_v);
+    const uint64_t dcap = layout == AMV_LAYOUT_SLOTS ? (uint64_t)pkt_cap * n : out_cap;
+    if (layout == AMV_LAYOUT_SLOTS && dcap > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
+    if (!v_out) ENSURE(WS_H_E, dcap ? dcap : 1, d_out);
+    ENSURE(WS_H_F, sizeof(uint64_t) * n, d_off);
+    ENSURE(WS_H_G, sizeof(uint32_t) * n, d_sz);
+    ENSURE(WS_H_H, sizeof(int32_t) * n, d_st);
+    const int nchunks = (n + C - 1) / C;
+    EventRing e_in;
+    if (e_in.init() != cudaSuccess) return fail(ctx, AMV_ERR_CUDA, "cudaEventCreate");
+    std::vector<cudaEvent_t> e_cmp(nchunks, nullptr);
+    for (int i = 0; i < nchunks; i++)
+        if (cudaEventCreateWithFlags(&e_cmp[i], cudaEventDisableTiming) != cudaSuccess) return fail(ctx, AMV_ERR_CUDA, "cudaEventCreate");
+    int rc = AMV_OK;
+    for (int i = 0; i < nchunks && rc == AMV_OK; i++) {
+        const int f0 = i * C, m = n - f0 < C ? n - f0 : C, slot = i % kRing;
+        // at most kRing - 1 chunks in flight: bounds what this call keeps queued on the H2D engine and
+        // makes ring slot `slot` (last used by chunk i - kRing) free
+        if (i >= kRing - 1) CK(cudaEventSynchronize(e_cmp[i - (kRing - 1)]));
+        if ((rc = copy_planes_on(ctx, ctx->s_in, d_y + ty * C * slot, const_cast<uint8_t *>(y) + fs_y * f0, w, h, ls_y, fs_y, m, false)) != AMV_OK) break;
+        if ((rc = copy_planes_on(ctx, ctx->s_in, d_u + tc * C * slot, const_cast<uint8_t *>(u) + fs_c * f0, cw, ch, ls_c, fs_c, m, false)) != AMV_OK) break;
+        if ((rc = copy_planes_on(ctx, ctx->s_in, d_v + tc * C * slot, const_cast<uint8_t *>(v) + fs_c * f0, cw, ch, ls_c, fs_c, m, false)) != AMV_OK) break;
+        CK(cudaEventRecord(e_in.e[slot], ctx->s_in));
+        CK(cudaStreamWaitEvent(ctx->stream, e_in.e[slot], 0));
+        rc = encode_device(ctx, d_y + ty * C * slot, d_u + tc * C * slot, d_v + tc * C * slot, w, cw, ty, tc, m, w, h,
+                           v_q ? v_q + f0 : nullptr, v_out ? v_out : d_out, dcap, pkt_cap, layout, d_off + f0, d_sz + f0,
+                           d_st + f0, /*reset_carry=*/i == 0, /*slot_base=*/(uint64_t)pkt_cap * f0);
+        if (rc != AMV_OK) break;
+        launch_export_meta(d_off + f0, d_sz + f0, d_st + f0, v_off + f0, v_sz + f0, v_st + f0, m, ctx->stream);
+        ctx->launches++;
+        CK(cudaEventRecord(e_cmp[i], ctx->stream));
+    }
+    cudaStreamSynchronize(ctx->s_in);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < nchunks; i++) cudaEventDestroy(e_cmp[i]);
+    if (rc != AMV_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, AMV_ERR_CUDA, "encode pipeline", e);
+    if (!v_out) {      // staged output: the metadata is home, send the bytes that were produced
+        uint64_t used = 0;
+        if (layout == AMV_LAYOUT_SLOTS) used = (uint64_t)pkt_cap * n;
+        else for (int f = 0; f < n; f++) if (p_off[f] + p_sz[f] > used) used = p_off[f] + p_sz[f];
+        if (used > out_cap) used = out_cap;
+        if (used) CK(copy_pieces(out, d_out, used, cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaStreamSynchronize(ctx->s_out));
+    }
+    memcpy(out_off, p_off, sizeof(uint64_t) * n);
+    memcpy(out_size, p_sz, sizeof(uint32_t) * n);
+    if (status) memcpy(status, p_st, sizeof(int32_t) * n);
     return AMV_OK;
 }
 
@@ -308,6 +558,9 @@ AMV_API void amv_destroy(amv_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < WS_COUNT; i++) if (ctx->ws[i].p) cudaFree(ctx->ws[i].p);
     for (size_t i = 0; i < ctx->evs.size(); i++) { cudaEventDestroy(ctx->evs[i].a); cudaEventDestroy(ctx->evs[i].b); }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->pinned_meta) cudaFreeHost(ctx->pinned_meta);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -331,6 +584,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "decode_log2_lanes")) { ctx->opt_log2p = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
+    if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
     return AMV_ERR_UNSUPPORTED;
 }
 
@@ -385,25 +639,9 @@ AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_b
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
     CK(cudaSetDevice(ctx->device));
     if (mem == AMV_MEM_DEVICE)
-        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status);
+        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes);
 
-    uint8_t *d_pk; uint64_t *d_off; uint32_t *d_sz; uint8_t *d_y, *d_u, *d_v; int32_t *d_st;
-    TO_DEVICE(WS_H_A, pkts, pkts_bytes, d_pk);
-    TO_DEVICE(WS_H_B, pkt_off, sizeof(uint64_t) * n, d_off);
-    TO_DEVICE(WS_H_C, pkt_size, sizeof(uint32_t) * n, d_sz);
-    ENSURE(WS_H_D, (size_t)w * h * n, d_y);
-    ENSURE(WS_H_E, (size_t)cw * ch * n, d_u);
-    ENSURE(WS_H_F, (size_t)cw * ch * n, d_v);
-    ENSURE(WS_H_G, sizeof(int32_t) * n, d_st);
-    int r = decode_device(ctx, d_pk, pkts_bytes, d_off, d_sz, n, w, h, d_y, d_u, d_v, w, cw, (uint64_t)w * h,
-                          (uint64_t)cw * ch, d_st);
-    if (r != AMV_OK) return r;
-    if ((r = copy_planes(ctx, d_y, y, w, h, ls_y, fs_y, n, true)) != AMV_OK) return r;
-    if ((r = copy_planes(ctx, d_u, u, cw, ch, ls_c, fs_c, n, true)) != AMV_OK) return r;
-    if ((r = copy_planes(ctx, d_v, v, cw, ch, ls_c, fs_c, n, true)) != AMV_OK) return r;
-    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return AMV_OK;
+    return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status);
 }
 
 // ---------------------------------------------------------------------------------------- encode
@@ -428,35 +666,7 @@ AMV_API int amv_encode_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, 
                              out_size, status);
 
     if (qscale) for (int i = 0; i < n; i++) if (qscale[i] < 2 || qscale[i] > 31) return fail(ctx, AMV_ERR_UNSUPPORTED, "qscale outside 2..31");
-    uint8_t *d_y, *d_u, *d_v, *d_out; int32_t *d_q = nullptr; uint64_t *d_off; uint32_t *d_sz; int32_t *d_st;
-    ENSURE(WS_H_A, (size_t)w * h * n, d_y);
-    ENSURE(WS_H_B, (size_t)cw * ch * n, d_u);
-    ENSURE(WS_H_C, (size_t)cw * ch * n, d_v);
-    int r;
-    if ((r = copy_planes(ctx, d_y, const_cast<uint8_t *>(y), w, h, ls_y, fs_y, n, false)) != AMV_OK) return r;
-    if ((r = copy_planes(ctx, d_u, const_cast<uint8_t *>(u), cw, ch, ls_c, fs_c, n, false)) != AMV_OK) return r;
-    if ((r = copy_planes(ctx, d_v, const_cast<uint8_t *>(v), cw, ch, ls_c, fs_c, n, false)) != AMV_OK) return r;
-    if (qscale) TO_DEVICE(WS_H_D, qscale, sizeof(int32_t) * n, d_q);
-    const uint64_t dcap = layout == AMV_LAYOUT_SLOTS ? (uint64_t)pkt_cap * n : out_cap;
-    ENSURE(WS_H_E, dcap, d_out);
-    ENSURE(WS_H_F, sizeof(uint64_t) * n, d_off);
-    ENSURE(WS_H_G, sizeof(uint32_t) * n, d_sz);
-    ENSURE(WS_H_H, sizeof(int32_t) * n, d_st);
-    r = encode_device(ctx, d_y, d_u, d_v, w, cw, (uint64_t)w * h, (uint64_t)cw * ch, n, w, h, d_q, d_out, dcap, pkt_cap, layout,
-                      d_off, d_sz, d_st);
-    if (r != AMV_OK) return r;
-    CK(cudaMemcpyAsync(out_off, d_off, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(out_size, d_sz, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    // only the bytes that were produced travel back
-    uint64_t used = 0;
-    if (layout == AMV_LAYOUT_SLOTS) used = (uint64_t)pkt_cap * n;
-    else for (int i = 0; i < n; i++) if (out_off[i] + out_size[i] > used) used = out_off[i] + out_size[i];
-    if (used > out_cap) used = out_cap;
-    if (used) CK(cudaMemcpyAsync(out, d_out, used, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return AMV_OK;
+    return encode_host(ctx, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, qscale, out, out_cap, pkt_cap, layout, out_off, out_size, status);
 }
 
 // ----------------------------------------------------------------------------------------- adpcm

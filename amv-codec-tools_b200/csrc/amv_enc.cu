@@ -337,9 +337,19 @@ k_compact(const uint8_t *__restrict__ slots, uint64_t slot_stride, const uint32_
     }
 }
 
-__global__ void k_slot_offsets(uint64_t *off, int n, uint64_t stride) {
+// copies per-frame metadata to (mapped, pinned) host memory without touching a copy engine
+__global__ void k_export_meta(const uint64_t *__restrict__ off, const uint32_t *__restrict__ sz, const int32_t *__restrict__ st,
+                              uint64_t *__restrict__ hoff, uint32_t *__restrict__ hsz, int32_t *__restrict__ hst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) off[i] = (uint64_t)i * stride;
+    if (i >= n) return;
+    if (off) hoff[i] = off[i];
+    if (sz) hsz[i] = sz[i];
+    if (st) hst[i] = st[i];
+}
+
+__global__ void k_slot_offsets(uint64_t *off, int n, uint64_t stride, uint64_t base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] = base + (uint64_t)i * stride;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,8 +389,13 @@ void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *
     k_compact<<<grid, 256, 0, s>>>(slots, slot_stride, size, off, n, out, out_cap, status);
 }
 
-void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, cudaStream_t s) {
-    k_slot_offsets<<<(n + 255) / 256, 256, 0, s>>>(off, n, stride);
+void launch_export_meta(const uint64_t *off, const uint32_t *sz, const int32_t *st, uint64_t *hoff, uint32_t *hsz, int32_t *hst,
+                        int n, cudaStream_t s) {
+    k_export_meta<<<(n + 255) / 256, 256, 0, s>>>(off, sz, st, hoff, hsz, hst, n);
+}
+
+void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, uint64_t base, cudaStream_t s) {
+    k_slot_offsets<<<(n + 255) / 256, 256, 0, s>>>(off, n, stride, base);
 }
 
 }  // namespace amv

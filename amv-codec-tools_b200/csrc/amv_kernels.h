@@ -38,7 +38,9 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
                    uint32_t *out_size, int32_t *status, cudaStream_t s);
 void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
                     uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s);
-void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, cudaStream_t s);
+void launch_export_meta(const uint64_t *off, const uint32_t *sz, const int32_t *st, uint64_t *hoff, uint32_t *hsz, int32_t *hst,
+                        int n, cudaStream_t s);
+void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, uint64_t base, cudaStream_t s);
 
 // ---- adpcm
 cudaError_t upload_adpcm_tables(cudaStream_t s);

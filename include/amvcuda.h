@@ -104,7 +104,8 @@ AMV_API void        amv_host_free(void *p);
 /* Tuning knobs (never change results):
  *   "decode_log2_lanes"            0..5: decode lanes (subsequences) per frame = 1 << value; -1 = from batch size
  *   "encode_slot_workspace_bytes"  cap of the packed-layout staging workspace (frames are sub-batched to fit)
- *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream */
+ *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream
+ *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose) */
 AMV_API int         amv_set_option(amv_ctx *ctx, const char *key, int64_t value);
 /* "decode_sync_rounds": rounds the last multi-lane decode needed to self-synchronise (max over warps)
  * "<k>_kernel_launches", then "<k>_kernel_ns" (k = encode|decode|unstuff|sync|compact|adpcm_dec|adpcm_enc):

@@ -336,3 +336,42 @@ def test_avcodec_dropin_matches_reference_codecs(w, h, n):
     out = subprocess.run([DROPIN, str(w), str(h), str(n)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DROP-IN CHECK OK" in out.stdout
+
+
+def test_host_path_pinned_zero_copy_and_chunked(ctx, oracle):
+    """AMV_MEM_HOST with page-locked buffers: metadata, input packets and the packed output are read /
+    written in place by the kernels (no staging copies), planes go through the chunked DMA ring.
+    Small chunks force several ring turns; results must equal the pageable (staged) path and the oracle."""
+    import torch
+    w, h, n = 160, 120, 37
+    cw, ch = chroma_dims(w, h)
+    y, u, v = synth_frames(n, w, h, seed=91, kind="sinus")
+    wpk, woff, wsz = oracle.encode_frames(y, u, v, w, h, 2)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hy, hu, hv = pin(y), pin(u), pin(v)
+    cap = n * 65536
+    out = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    off = torch.zeros(n, dtype=torch.int64).pin_memory()
+    size = torch.zeros(n, dtype=torch.int32).pin_memory()
+    st = torch.zeros(n, dtype=torch.int32).pin_memory()
+    ctx.set_option("host_chunk_frames", 5)
+    try:
+        ctx.encode_frames_raw(hy, hu, hv, w, cw, w * h, cw * ch, n, w, h, None, out, cap, 65536, amv.LAYOUT_PACKED, off, size, st,
+                              amv.MEM_HOST)
+        assert (st.numpy() == 0).all()
+        assert np.array_equal(size.numpy().astype(np.uint32), wsz) and np.array_equal(off.numpy().astype(np.uint64), woff)
+        assert np.array_equal(out.numpy()[: len(wpk)], wpk)
+        dy = torch.zeros((n, h, w), dtype=torch.uint8).pin_memory()
+        du = torch.zeros((n, ch, cw), dtype=torch.uint8).pin_memory()
+        dv = torch.zeros((n, ch, cw), dtype=torch.uint8).pin_memory()
+        ctx.decode_frames_raw(out, cap, off, size, n, w, h, dy, du, dv, w, cw, w * h, cw * ch, st, amv.MEM_HOST)
+        wy, wu, wv, _ = oracle.decode_frames(wpk, woff, wsz, w, h)
+        assert (st.numpy() == 0).all()
+        assert np.array_equal(dy.numpy(), wy) and np.array_equal(du.numpy(), wu) and np.array_equal(dv.numpy(), wv)
+        # pageable inputs, same chunking: staged path
+        pk2, off2, sz2, st2 = ctx.encode_frames(y, u, v)
+        assert np.array_equal(pk2, wpk) and (st2 == 0).all()
+        qy, qu, qv, qst = ctx.decode_frames(wpk, woff, wsz, w, h)
+        assert np.array_equal(qy, wy) and np.array_equal(qu, wu) and np.array_equal(qv, wv)
+    finally:
+        ctx.set_option("host_chunk_frames", 0)
