@@ -1,10 +1,10 @@
 // amv_enc.cu -- AMV video encode kernel (sm_100a).
 //
-// One CTA encodes one frame at a time (persistent, grid-stride over the batch) so that the two
+// One WARP encodes one frame at a time (persistent, warp-stride over the batch) so that the two
 // serial quantities of a frame -- the running bit position of the entropy-coded segment and the
-// count of stuffed FF bytes -- never leave the CTA: no inter-CTA look-back, no scratch traffic,
-// the packet is written once.  A frame is cut into segments of 16 macroblocks = 96 blocks =
-// 96 threads (3 warps: two luma warps, one chroma warp, so a warp never mixes Huffman tables):
+// count of stuffed FF bytes -- never leave the warp: no look-back, no scratch traffic, no CTA
+// barriers, the packet is written once.  A frame is cut into segments of 5 macroblocks = 30 blocks
+// = 30 lanes (20 luma, 5 Cb, 5 Cr):
 //
 //   A  thread-per-block: 128-bit/64-bit coalesced row loads of the bottom-up picture
 //      (amv_encode_picture mjpegenc.c:454-472 + edge replication mpegvideo.c:1416-1470),
@@ -23,11 +23,13 @@
 
 namespace amv {
 
-constexpr int kEncThreads = 96;
-constexpr int kSegMB = 16;
+constexpr int kEncWarps = 4;                    // warps per CTA, each encoding its own frames
+constexpr int kEncThreads = kEncWarps * 32;
+constexpr int kSegMB = 5;                       // macroblocks per segment: 30 blocks on 30 lanes
+constexpr int kSegBlocks = kSegMB * 6;
 // worst case per block: 20-bit DC + 63 x 26-bit AC = 1658 bits = 52 words
 constexpr int kStageWords = (20 + 63 * 26 + 31) / 32;
-constexpr int kSegWords = kEncThreads * kStageWords + 8;
+constexpr int kSegWords = kSegBlocks * kStageWords + 8;
 
 struct EncTablesDev {
     EncHuffTables huff;
@@ -36,21 +38,21 @@ struct EncTablesDev {
 };
 __device__ EncTablesDev g_enc_tables;
 
-struct EncSmem {
-    uint32_t huff[kEncHuffEntries];
-    uint32_t qm10[64];
+// per-warp working set (dynamic shared memory, one instance per warp)
+struct EncWarpSmem {
     union {                                 // never live at the same time (A,B use coef; D,E use seg)
-        uint32_t coef[32 * kEncThreads];    // word (k>>1)*96 + t : zigzag coefficients k, k+1 of thread t's block
+        uint32_t coef[32 * 32];             // word (k>>1)*32 + lane : zigzag coefficients k, k+1 of the lane's block
         uint32_t seg[kSegWords];            // the segment's contiguous bit string
     } u;
-    uint32_t stage[kStageWords * kEncThreads];   // word w*96 + t : thread t's private bit string
-    uint32_t lens[kEncThreads];        // bit length per block in bitstream order -> exclusive offsets
-    int      dcq[kEncThreads];         // quantised DC per block in bitstream order
-    int      carry_dc[3];              // last DC of each component from the previous segment
-    uint32_t warp_tot[4];
-    uint32_t seg_bits;                 // total bits of the segment
-    uint32_t carry_word;               // partial word carried into the next segment
-    uint32_t overflow;
+    uint32_t stage[kStageWords * 32];       // word w*32 + lane : the lane's private bit string
+    uint32_t qm10[64];
+    uint32_t lens[32];                      // bit length per block in bitstream order -> exclusive offsets
+    int      dcq[32];                       // quantised DC per block in bitstream order
+    int      carry_dc[4];                   // last DC of each component from the previous segment
+};
+struct EncSmem {
+    uint32_t huff[kEncHuffEntries];
+    EncWarpSmem w[kEncWarps];
 };
 
 __device__ __forceinline__ int bit_width(uint32_t v) { return 32 - __clz(v); }
@@ -61,22 +63,39 @@ __device__ __forceinline__ uint32_t ff_bytes(uint32_t v) {
     return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu);
 }
 
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += u;
+    }
+    return v;
+}
+
+// One WARP encodes one frame at a time (persistent, warp-stride over the batch), so the frame's two
+// serial quantities -- running bit position and count of stuffed FF bytes -- never leave the warp
+// and every synchronisation is a __syncwarp: warps of an SM run fully independently of each other.
 template <bool FAST>
 __global__ void __launch_bounds__(kEncThreads)
 k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
          int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
          uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
          int32_t *__restrict__ status) {
-    __shared__ EncSmem S;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    for (int i = t; i < kEncHuffEntries; i += kEncThreads) S.huff[i] = g_enc_tables.huff.e[i];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kEncHuffEntries; i += kEncThreads) S.huff[i] = g_enc_tables.huff.e[i];
+    __syncthreads();
+    EncWarpSmem &W = S.w[wid];
 
-    // block role of this thread inside a segment
+    // block role of this lane inside a segment: lanes 0..19 luma (4 per MB), 20..24 Cb, 25..29 Cr
     int mi, b;
-    if (wid < 2) { mi = lane >> 1; b = wid * 2 + (lane & 1); }
-    else         { mi = lane & 15; b = 4 + (lane >> 4); }
+    if (lane < 20) { mi = lane >> 2; b = lane & 3; }
+    else if (lane < 25) { mi = lane - 20; b = 4; }
+    else { mi = lane - 25; b = 5; }
+    const bool has_role = lane < kSegBlocks;
     const int comp = b < 4 ? 0 : b - 3;
-    const int sigma = mi * 6 + b;                       // position in bitstream order
+    const int sigma = has_role ? mi * 6 + b : 31;        // position in bitstream order (0..29)
     const int total_mb = g.mbw * g.mbh;
     // valid source extent: the reference copies w x h luma and (w>>1) x (h>>1) chroma (mpegvideo_enc.c:866-867)
     const int vw = comp ? (g.w >> 1) : g.w, vh = comp ? (g.h >> 1) : g.h, r0 = comp ? g.c0 : g.y0;
@@ -84,31 +103,33 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
     // explicit shared addresses for the hot loops
     const uint32_t huff_dc_s = smem_addr(&S.huff[comp ? kEncDcChroma : kEncDcLuma]);
     const uint32_t huff_ac_s = smem_addr(&S.huff[comp ? kEncAcChroma : kEncAcLuma]);
-    const uint32_t coef_s = smem_addr(&S.u.coef[t]);            // coefficient k: + (k>>1)*384 + (k&1)*2
-    const uint32_t stage_s = smem_addr(&S.stage[t]);            // word w: + w*384
-    const uint32_t seg_s = smem_addr(&S.u.seg[0]);
+    const uint32_t coef_s = smem_addr(&W.u.coef[lane]);          // coefficient k: + (k>>1)*128 + (k&1)*2
+    const uint32_t stage_s = smem_addr(&W.stage[lane]);          // word w: + w*128
+    const uint32_t seg_s = smem_addr(&W.u.seg[0]);
+    const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
 
-    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+    for (int f = gw; f < n; f += nw_total) {
         const int qs = qscale ? qscale[f] : 2;
-        __syncthreads();
-        if (t < 64) {
+        __syncwarp();
+        for (int t = lane; t < 64; t += 32) {
             // intra_matrix / q_intra_matrix for this frame (mpegvideo_enc.c:2866-2877, ff_convert_matrix :69-91)
             int m = 8;
             if (t) m = min(max(((int)g_enc_tables.intra_base[t] * qs) >> 3, 1), 255);
-            S.qm10[t] = ((1u << 22) / (uint32_t)(8 * m)) << 10;
+            W.qm10[t] = ((1u << 22) / (uint32_t)(8 * m)) << 10;
         }
-        if (t < 3) S.carry_dc[t] = 128;                 // last_dc init (mpegvideo_enc.c:2033-2036)
-        if (t == 0) { S.carry_word = 0; S.overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0; }   // qscale domain: SURVEY 9.13
+        if (lane < 3) W.carry_dc[lane] = 128;            // last_dc init (mpegvideo_enc.c:2033-2036)
+        uint32_t overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0;      // qscale domain: SURVEY 9.13
+        uint32_t carry_word = 0;                        // partial word carried into the next segment
         const uint8_t *pl = (comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c);
         uint8_t *pkt = slots + (uint64_t)f * slot_stride;
         uint32_t G = 2;                                 // bytes written so far (SOI)
         uint32_t r = 0;                                 // carried bits (sit in carry_word, MSB side)
-        if (t == 0 && pkt_cap >= 2) { pkt[0] = 0xff; pkt[1] = 0xd8; }
-        __syncthreads();
+        if (lane == 0 && pkt_cap >= 2) { pkt[0] = 0xff; pkt[1] = 0xd8; }
+        __syncwarp();
 
         for (int m0 = 0; m0 < total_mb; m0 += kSegMB) {
             const int nmb = min(kSegMB, total_mb - m0);
-            const bool active = mi < nmb;
+            const bool active = has_role && mi < nmb;
             const bool last_seg = m0 + kSegMB >= total_mb;
             uint32_t mask_lo = 0, mask_hi = 0;          // non-zero AC positions (zigzag) of this block
             int dc = 0;
@@ -141,7 +162,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                 // raster order so the multiplier loads vectorise; mask bit = zigzag position
 #pragma unroll
                 for (int j = 1; j < 64; j++) {
-                    const int q = quant_ac(v[j], S.qm10[j]);
+                    const int q = quant_ac(v[j], W.qm10[j]);
                     v[j] = q;
                     const int k = zigzag_inv_at(j);
                     if (q) { if (k < 32) mask_lo |= 1u << k; else mask_hi |= 1u << (k - 32); }
@@ -150,18 +171,18 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                 for (int i = 0; i < 32; i++) {
                     const uint32_t lo = (uint32_t)v[zigzag_at(2 * i)] & 0xffffu;
                     const uint32_t hi = (uint32_t)v[zigzag_at(2 * i + 1)] << 16;
-                    S.u.coef[i * kEncThreads + t] = lo | hi;
+                    W.u.coef[i * 32 + lane] = lo | hi;
                 }
-                S.dcq[sigma] = dc;
+                W.dcq[sigma] = dc;
             }
-            __syncthreads();
+            __syncwarp();
 
-            // ---------------- B: Huffman-code the block into the thread's private bit string
+            // ---------------- B: Huffman-code the block into the lane's private bit string
             uint32_t len = 0;
             if (active) {
                 int pred;
-                if (comp == 0) pred = (b > 0) ? S.dcq[sigma - 1] : (mi > 0 ? S.dcq[sigma - 3] : S.carry_dc[0]);
-                else           pred = mi > 0 ? S.dcq[sigma - 6] : S.carry_dc[comp];
+                if (comp == 0) pred = (b > 0) ? W.dcq[sigma - 1] : (mi > 0 ? W.dcq[sigma - 3] : W.carry_dc[0]);
+                else           pred = mi > 0 ? W.dcq[sigma - 6] : W.carry_dc[comp];
                 uint64_t acc = 0;                   // MSB-first accumulator
                 int fill = 0;
                 uint32_t wp = stage_s;              // next private word
@@ -169,7 +190,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                     acc |= (uint64_t)code << (64 - fill - nbits);
                     fill += nbits;
                     len += nbits;
-                    if (fill >= 32) { sts32(wp, (uint32_t)(acc >> 32)); wp += kEncThreads * 4; acc <<= 32; fill -= 32; }
+                    if (fill >= 32) { sts32(wp, (uint32_t)(acc >> 32)); wp += 128; acc <<= 32; fill -= 32; }
                 };
                 {   // DC (ff_mjpeg_encode_dc, mjpegenc.c:357-377)
                     const int diff = dc - pred;
@@ -186,7 +207,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                         m &= m - 1;
                         int run = k - prevk - 1;
                         prevk = k;
-                        const int cv = lds_s16(coef_s + (uint32_t)(k >> 1) * (kEncThreads * 4) + (uint32_t)(k & 1) * 2);
+                        const int cv = lds_s16(coef_s + (uint32_t)(k >> 1) * 128 + (uint32_t)(k & 1) * 2);
                         const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
                         for (; run >= 16; run -= 16) put(ezrl >> 5, (int)(ezrl & 31));
                         const uint32_t e = lds32(huff_ac_s + (uint32_t)((run << 4) | cb) * 4);
@@ -199,36 +220,27 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                 if (prevk != 63) put(eeob >> 5, (int)(eeob & 31));          // EOB only if last_index < 63 (:432-434)
                 if (fill > 0) sts32(wp, (uint32_t)(acc >> 32));
             }
-            S.lens[sigma] = len;
-            __syncthreads();
+            W.lens[sigma] = len;               // lanes 30/31 and inactive blocks write 0 (slot 31 is a dummy)
+            __syncwarp();
 
-            // ---------------- C: exclusive scan of the 96 lengths (warp 0, 3 per lane)
-            if (wid == 0) {
-                const uint32_t a0 = S.lens[3 * lane], a1 = S.lens[3 * lane + 1], a2 = S.lens[3 * lane + 2];
-                uint32_t inc = a0 + a1 + a2;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += u;
-                }
-                const uint32_t ex = inc - (a0 + a1 + a2);
-                S.lens[3 * lane] = ex; S.lens[3 * lane + 1] = ex + a0; S.lens[3 * lane + 2] = ex + a0 + a1;
-                if (lane == 31) S.seg_bits = inc;
-            }
-            // DC predictors for the next segment (everyone has read the old ones before the last barrier)
-            if (active && mi == nmb - 1 && (b == 3 || b >= 4)) S.carry_dc[comp] = dc;
-            __syncthreads();
-            const uint32_t T = S.seg_bits;
+            // ---------------- C: exclusive scan of the block lengths in bitstream order (lane = sigma)
+            const uint32_t mylen_sigma = lane < kSegBlocks ? W.lens[lane] : 0;
+            const uint32_t inc_sigma = warp_incl_scan(mylen_sigma, lane);
+            const uint32_t T = __shfl_sync(0xffffffffu, inc_sigma, 31);
+            __syncwarp();
+            W.lens[lane] = inc_sigma - mylen_sigma;
+            // DC predictors for the next segment (everyone read the old ones before the last __syncwarp)
+            if (active && mi == nmb - 1 && (b == 3 || b >= 4)) W.carry_dc[comp] = dc;
             uint32_t R = r + T;                              // bits in the buffer after this segment
             // clear the words this segment will OR into; word 0 starts with the carried bits
             const uint32_t used_words = (R + 7 + 31) >> 5;
-            for (uint32_t i = 1 + t; i <= used_words; i += kEncThreads) S.u.seg[i] = 0;
-            if (t == 0) S.u.seg[0] = S.carry_word;
-            __syncthreads();
+            for (uint32_t i = 1 + lane; i <= used_words; i += 32) W.u.seg[i] = 0;
+            if (lane == 0) W.u.seg[0] = carry_word;
+            __syncwarp();
 
             // ---------------- D: bit packer -- shift the private string to its scanned bit offset
             if (active && len) {
-                const uint32_t o = r + S.lens[sigma];
+                const uint32_t o = r + W.lens[sigma];
                 const uint32_t sh = o & 31;
                 uint32_t dst = seg_s + (o >> 5) * 4, src = stage_s;
                 const uint32_t nsrc = (len + 31) >> 5;
@@ -236,44 +248,36 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                 for (uint32_t j = 0; j < nsrc; j++) {
                     const uint32_t v = lds32(src);
                     red_or_shared(dst, __funnelshift_r(v, prev, sh));      // (prev:v) >> sh
-                    prev = v; src += kEncThreads * 4; dst += 4;
+                    prev = v; src += 128; dst += 4;
                 }
                 const uint32_t tail = sh ? prev << (32 - sh) : 0u;
                 if (tail) red_or_shared(dst, tail);
             }
-            __syncthreads();
+            __syncwarp();
             if (last_seg) {
                 // pad to a byte with ones (ff_mjpeg_encode_stuffing, mjpegenc.c:338-343)
                 const uint32_t pad = (0u - R) & 7u;
-                if (t == 0 && pad) S.u.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
+                if (lane == 0 && pad) W.u.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
                 R += pad;
-                __syncthreads();
+                __syncwarp();
             }
 
             // ---------------- E: FF00 stuffing + output of the complete bytes
             const uint32_t B = last_seg ? (R >> 3) : ((R >> 5) << 2);     // bytes leaving the buffer now
             const uint32_t nw = (B + 3) >> 2;
-            const uint32_t per = (nw + kEncThreads - 1) / kEncThreads;
-            const uint32_t w0 = min((uint32_t)t * per, nw), w1 = min(w0 + per, nw);
+            const uint32_t per = (nw + 31) >> 5;
+            const uint32_t w0 = min((uint32_t)lane * per, nw), w1 = min(w0 + per, nw);
             // bytes past B in the last word are zero bits, never FF: no masking needed for the count
             uint32_t ffc = 0;
-            for (uint32_t w = w0; w < w1; w++) ffc += __popc(ff_bytes(S.u.seg[w]));
-            uint32_t inc = ffc;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += u;
-            }
-            if (lane == 31) S.warp_tot[wid] = inc;
-            __syncthreads();
-            const uint32_t wt0 = S.warp_tot[0], wt1 = S.warp_tot[1], wt2 = S.warp_tot[2];
-            const uint32_t ff_total = wt0 + wt1 + wt2;
-            const uint32_t ff_before = (wid > 0 ? wt0 : 0) + (wid > 1 ? wt1 : 0) + inc - ffc;
-            const bool fits = (uint64_t)G + B + ff_total + 2 <= pkt_cap && !S.overflow;
+            for (uint32_t w = w0; w < w1; w++) ffc += __popc(ff_bytes(W.u.seg[w]));
+            const uint32_t inc = warp_incl_scan(ffc, lane);
+            const uint32_t ff_total = __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t ff_before = inc - ffc;
+            const bool fits = (uint64_t)G + B + ff_total + 2 <= pkt_cap && !overflow;
             if (fits) {
                 uint8_t *o = pkt + G + w0 * 4 + ff_before;
                 for (uint32_t w = w0; w < w1; w++) {
-                    const uint32_t v = S.u.seg[w];
+                    const uint32_t v = W.u.seg[w];
                     const uint32_t nvalid = min(4u, B - w * 4);
                     if (nvalid == 4 && ff_bytes(v) == 0) {
                         o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v;
@@ -286,21 +290,16 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                         }
                     }
                 }
-            }
-            __syncthreads();
-            if (t == 0) {
-                if (!fits && !S.overflow) S.overflow = AMV_ST_NOSPACE;
-                S.carry_word = last_seg ? 0 : S.u.seg[R >> 5];        // carry the partial word
-            }
+            } else if (!overflow) overflow = AMV_ST_NOSPACE;
+            carry_word = last_seg ? 0 : W.u.seg[R >> 5];                  // carry the partial word (same for all lanes)
             G += B + ff_total;
             r = last_seg ? 0 : (R & 31);
-            __syncthreads();
+            __syncwarp();
         }
-        if (t == 0) {
-            const uint32_t ovf = S.overflow;
-            if (!ovf) { pkt[G] = 0xff; pkt[G + 1] = 0xd9; }      // EOI (mjpegenc.c:354)
-            out_size[f] = ovf ? 0 : G + 2;
-            status[f] = (int32_t)ovf;
+        if (lane == 0) {
+            if (!overflow) { pkt[G] = 0xff; pkt[G + 1] = 0xd9; }      // EOI (mjpegenc.c:354)
+            out_size[f] = overflow ? 0 : G + 2;
+            status[f] = (int32_t)overflow;
         }
     }
 }
@@ -366,8 +365,10 @@ cudaError_t upload_enc_tables(cudaStream_t s) {
 }
 
 int encode_grid(int n) {
-    const int cap = kNumSMs * 6;      // 6 resident CTAs of 96 threads per SM (shared memory bound)
-    return n < cap ? (n < 1 ? 1 : n) : cap;
+    const int per_sm = 4;                              // CTAs per SM (shared memory bound): 16 independent warps
+    const int cap = kNumSMs * per_sm;
+    const int need = (n + kEncWarps - 1) / kEncWarps;  // one frame per warp at a time
+    return need < 1 ? 1 : (need < cap ? need : cap);
 }
 
 void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
@@ -375,12 +376,18 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
                    uint32_t *out_size, int32_t *status, cudaStream_t s) {
     const bool fast = (g.w % 16 == 0) &&
                       ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+        cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+        attr_set = true;
+    }
     if (fast)
-        k_encode<true><<<encode_grid(n), kEncThreads, 0, s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                              slot_stride, pkt_cap, out_size, status);
+        k_encode<true><<<encode_grid(n), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                                            slot_stride, pkt_cap, out_size, status);
     else
-        k_encode<false><<<encode_grid(n), kEncThreads, 0, s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                               slot_stride, pkt_cap, out_size, status);
+        k_encode<false><<<encode_grid(n), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                                             slot_stride, pkt_cap, out_size, status);
 }
 
 void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
