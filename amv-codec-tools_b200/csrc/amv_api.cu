@@ -138,13 +138,13 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     const Geom g = make_geom(w, h);
     const int log2p = pick_log2p(ctx, n);
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
-    uint32_t *rounds; uint16_t *tokens; uint32_t *blk_off;
+    uint32_t *rounds; uint32_t *tokens; uint32_t *blk_off;
     const uint64_t scratch_bytes = payload_bytes + (uint64_t)(kSlotPad + 16) * n + 64;
     ENSURE(WS_SLOT_OFF, sizeof(uint64_t) * n, slot_off);
     ENSURE(WS_SCAN_LEN, sizeof(uint32_t) * n, scan_len);
     ENSURE(WS_SCRATCH, scratch_bytes, scratch);
     ENSURE(WS_ROUNDS, sizeof(uint32_t), rounds);
-    ENSURE(WS_TOKENS, scratch_bytes * 8 + 1024, tokens);          // at most one 16-bit token per 2 scan bits
+    ENSURE(WS_TOKENS, scratch_bytes * 16 + 1024, tokens);         // at most one 32-bit token per 2 scan bits
     ENSURE(WS_BLKOFF, sizeof(uint32_t) * (size_t)n * g.nblk, blk_off);
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
     if (log2p) ENSURE(WS_STARTS, sizeof(LaneStart) * ((size_t)n << log2p), starts);

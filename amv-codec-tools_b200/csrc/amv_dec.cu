@@ -225,7 +225,7 @@ __device__ __forceinline__ void load_vlc_tables(VlcSmem &s) {
 struct CountSink {
     int dcv;
     __device__ __forceinline__ void dc(int d) { dcv = d; }
-    __device__ __forceinline__ void ac(uint32_t) {}
+    __device__ __forceinline__ void ac(int, int) {}
 };
 
 __device__ __forceinline__ void walk_subsequence(const uint32_t *words, uint32_t nwords, uint32_t start_bit,
@@ -314,11 +314,12 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 
 // ------------------------------------------------------------------------------------------------
 // k_vlc_tokens: Huffman -> fixed-width tokens.  Every lane re-walks its (now exactly delimited)
-// subsequence and writes, per block, the absolute dequantised DC followed by the AC tokens into the
-// frame's token region, plus the block's token offset.  A block of b bits yields at most b/2
-// tokens (every symbol is at least 2 bits), so the region is 8 bytes per scan byte and a lane that
-// starts at bit s writes from token s/2 (+8 per lane of slack for 16-byte alignment) without ever
-// meeting its neighbour.
+// subsequence and writes, per block, a DC token (absolute dequantised DC) followed by one 32-bit
+// token per non-zero AC coefficient -- already de-zigzagged and dequantised, so the consumer only
+// scatters them -- plus the block's (count, offset) entry.  A block of b bits yields at most b/2
+// tokens (a coefficient costs at least 3 bits, DC + EOB at least 4), so the region is 16 bytes per
+// scan byte and a lane that starts at bit s writes from token s/2 (+4 per lane of slack for 16-byte
+// alignment) without ever meeting its neighbour.
 //
 // The symbol loop is the serial heart of the decoder, so it is written for issue slots:
 //  * bits come from a per-lane 16-word ring in shared memory ([word][lane], conflict-free) that is
@@ -329,7 +330,7 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 //  * one table lookup per symbol (byte-field entries, explicit shared-memory addresses), then
 //    straight-line field extraction, JPEG sign extension and token assembly -- no per-symbol
 //    divergence except EOB/ZRL/second-level codes;
-//  * tokens collect in a 128-bit shift register and leave as 16-byte stores.
+//  * tokens collect four at a time in registers and leave as 16-byte stores.
 // ------------------------------------------------------------------------------------------------
 __device__ FastVlcTables g_fast_vlc;
 
@@ -338,16 +339,18 @@ constexpr int kRingWords = 16;
 
 struct TokSmem {
     uint32_t lut[kVlcMaxEntries];
+    uint32_t tz[2][64];          // zigzag position -> (consumer column byte offset << 16) | quantiser
     uint32_t ring[kTokThreads / 32][kRingWords * 32];
 };
 
 __global__ void __launch_bounds__(kTokThreads)
 k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
-             const LaneStart *__restrict__ starts, int nblk, uint16_t *__restrict__ tokens,
+             const LaneStart *__restrict__ starts, int nblk, uint32_t *__restrict__ tokens,
              uint32_t *__restrict__ blk_off, int32_t *__restrict__ status) {
     __shared__ TokSmem S;
     for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) S.lut[i] = g_fast_vlc.e[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&S.tz[0][0])[i] = (&g_dec_tables.dq.tz[0][0])[i];
     __syncthreads();
     const int P = 1 << log2p;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -356,6 +359,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     const int p = (int)(gt & (P - 1));
     const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(S.lut);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&S.ring[wid][lane]);   // word w of this lane: + w*128
+    const uint32_t tz_s = (uint32_t)__cvta_generic_to_shared(&S.tz[0][0]);
     const uint32_t dc_base[2] = { (uint32_t)g_fast_vlc.base[0], (uint32_t)g_fast_vlc.base[1] };
     const uint32_t ac_base[2] = { (uint32_t)g_fast_vlc.base[2], (uint32_t)g_fast_vlc.base[3] };
     const int q0l = (int)(g_dec_tables.dq.zq[0][0] >> 8), q0c = (int)(g_dec_tables.dq.zq[1][0] >> 8);
@@ -388,10 +392,10 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             }
         }
     }
-    // token output: 16-byte groups inside the frame's region
-    const uint32_t tok_cap = (cap_words << 2) * 4u;                       // tokens in the region
-    uint32_t tok_idx = ((bit >> 1) + 8u * (uint32_t)p + 7u) & ~7u;          // first token index of this lane (multiple of 8)
-    uint16_t *tok_frame = tokens + so * 4;
+    // token output: groups of four 32-bit tokens (16 bytes) inside the frame's region
+    const uint32_t tok_cap = cap_words * 16u;                               // tokens in the region (16 B per scan byte)
+    uint32_t tok_idx = ((bit >> 1) + 4u * (uint32_t)p + 3u) & ~3u;          // first token index of this lane (multiple of 4)
+    uint32_t *tok_frame = tokens + so * 4;
     uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, tcount = 0;
     uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;
 
@@ -436,15 +440,12 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             nb += 32;
         }
     };
-    auto push = [&](uint32_t tok) {        // append one 16-bit token
-        t0 = __funnelshift_r(t0, t1, 16);
-        t1 = __funnelshift_r(t1, t2, 16);
-        t2 = __funnelshift_r(t2, t3, 16);
-        t3 = (t3 >> 16) | (tok << 16);
-        if (++tcount == 8) {
-            if (tok_idx + 8 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
+    auto push = [&](uint32_t tok) {        // append one 32-bit token
+        t0 = t1; t1 = t2; t2 = t3; t3 = tok;
+        if (++tcount == 4) {
+            if (tok_idx + 4 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
             else st |= AMV_ST_OVERRUN;
-            tok_idx += 8;
+            tok_idx += 4;
             tcount = 0;
         }
     };
@@ -464,7 +465,8 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         }
         if (!on) continue;
         const int tq = b >= 4 ? 1 : 0;
-        boff[i] = min(tok_idx + tcount, tok_cap);
+        const uint32_t blk_start = min(tok_idx + tcount, tok_cap);
+        const uint32_t tzq_s = tz_s + (uint32_t)tq * 256u;
         // ---- DC (mjpeg_decode_dc, mjpegdec.c:358-373)
         {
             refill();
@@ -488,6 +490,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         }
         // ---- AC (decode_block, mjpegdec.c:391-428)
         int k = 0;
+        uint32_t nac = 0;
         for (;;) {
             refill();
             const uint32_t hi = (uint32_t)(acc >> 32);
@@ -495,33 +498,33 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             if ((e & 0xff) == 0) {
                 if (!(e & 0x100))
                     e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
-                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; acc <<= 1; nb -= 1; push(kTokEOB); break; }
+                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; acc <<= 1; nb -= 1; break; }
             }
             const uint32_t len = e & 0xff, rsh = (e >> 8) & 0xff, total = (e >> 16) & 0xff, run = e >> 28;
             const uint32_t top = hi << len;
             acc <<= total; nb -= (int)total;
             if (rsh == 32) {                                                   // size 0: EOB or ZRL
-                if (run != 15) { push(kTokEOB); break; }
-                push(kTokZRL);
+                if (run != 15) break;
                 k += 16;
-                if (k > 1024) { push(kTokEOB); break; }                        // only garbage lanes get here
+                if (k > 1024) break;                                           // only garbage lanes get here
                 continue;
             }
             const int sg = (int)(~top) >> 31;
-            const uint32_t lvl = (__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg;
+            const int lvl = (int)((__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg);
             k += (int)run + 1;
-            if (k > 63) { st |= AMV_ST_COEFIDX; push(kTokEOB); break; }       // "error count" (mjpegdec.c:423-424)
-            push((run << 12) | (lvl & 0xfffu));
+            if (k > 63) { st |= AMV_ST_COEFIDX; break; }                      // "error count" (mjpegdec.c:423-424)
+            const uint32_t z = lds32(tzq_s + (uint32_t)k * 4);
+            push((z & 0xffff0000u) | ((uint32_t)(lvl * (int)(z & 0xffffu)) & 0xffffu));   // level * quant_matrix[j] as int16 (:420,428)
+            nac++;
             if (k == 63) break;
         }
+        boff[i] = (nac << kTokCountShift) | blk_start;
         if (++b == 6) b = 0;
     }
     // flush the partly filled group (unused upper tokens are don't-care, the group is ours alone)
     if (count && tcount) {
-        for (uint32_t j = tcount; j < 8; j++) {
-            t0 = __funnelshift_r(t0, t1, 16); t1 = __funnelshift_r(t1, t2, 16); t2 = __funnelshift_r(t2, t3, 16); t3 >>= 16;
-        }
-        if (tok_idx + 8 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
+        for (uint32_t j = tcount; j < 4; j++) { t0 = t1; t1 = t2; t2 = t3; t3 = 0; }
+        if (tok_idx + 4 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
         else st |= AMV_ST_OVERRUN;
     }
     // a lane that owns no block just passes through; otherwise it must end inside the scan
@@ -539,13 +542,10 @@ constexpr int kIdctThreads = 128;
 
 template <bool FAST>
 __global__ void __launch_bounds__(kIdctThreads)
-k_idct(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off, const uint64_t *__restrict__ slot_off,
+k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off, const uint64_t *__restrict__ slot_off,
        const uint32_t *__restrict__ scan_len, int n, Geom g, uint8_t *__restrict__ py, uint8_t *__restrict__ pu,
        uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c) {
-    __shared__ uint32_t zq[2][64];
     __shared__ uint32_t tile[kIdctThreads / 32][32 * 32];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&zq[0][0])[i] = (&g_dec_tables.dq.zq[0][0])[i];
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (int)(gt / g.nblk);
@@ -565,17 +565,20 @@ k_idct(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
         by = jj / g.mbw; bx = jj - by * g.mbw;
         blk = jj * 6 + 3 + comp;
     }
-    const int tq = comp ? 1 : 0;
-    const uint16_t *tp = tokens + slot_off[f] * 4 + blk_off[(uint64_t)f * g.nblk + blk];
+    const uint32_t bo = blk_off[(uint64_t)f * g.nblk + blk];
+    const uint32_t *tp = tokens + slot_off[f] * 4 + (bo & ((1u << kTokCountShift) - 1u));
+    const uint32_t nac = bo >> kTokCountShift;
     uint32_t *slot = &tile[wid][lane];
+    const uint32_t slot_s = smem_addr(slot);
 #pragma unroll
     for (int k = 0; k < 32; k++) slot[k * 32] = 0;
-    reinterpret_cast<int16_t *>(slot)[0] = (int16_t)__ldg(tp);
-    uint32_t nxt = __ldg(tp + 1);
-    int ti = 2;
-    expand_tokens(
-        [&]() { const uint32_t t = nxt; nxt = __ldg(tp + ti); ti++; return t; }, zq[tq],
-        [&](int j, int val) { reinterpret_cast<int16_t *>(slot + (j >> 1) * 32)[j & 1] = (int16_t)val; });
+    // the tokens are already (column offset, value): scatter them, one ahead in flight
+    uint32_t t = __ldg(tp);
+    for (uint32_t a = 0; a <= nac; a++) {
+        const uint32_t nx = __ldg(tp + a + 1);
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(slot_s + (t >> 16)), "h"((unsigned short)t) : "memory");
+        t = nx;
+    }
 
     uint32_t c[32], o[16];
 #pragma unroll
@@ -635,7 +638,7 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
 }
 
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
-                       int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
+                       int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
                        int32_t *status, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
@@ -643,7 +646,7 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                                               status);
 }
 
-void launch_idct(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
+void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
                  const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                  cudaStream_t s) {
     const int64_t threads = (int64_t)n * g.nblk;

@@ -116,10 +116,12 @@ constexpr uint32_t kVlcBad = 1u << 14;
 constexpr uint32_t kVlcResolved = 1u << 15;
 constexpr int kVlcMaxEntries = 4 * 1024 + 20 * 64;
 
-// tokens handed from the Huffman kernel to the IDCT kernel (16 bit each):
-//   block = DC token (absolute, dequantised, int16) then AC tokens run<<12 | level&0xfff,
-//   terminated by EOB (0x0000) unless the block's last coefficient is number 63.
-constexpr uint32_t kTokEOB = 0x0000u, kTokZRL = 0xF000u;
+// Tokens handed from the Huffman kernel to the IDCT kernel (32 bit each).  A block is its DC token
+// (low half = absolute dequantised DC as int16) followed by one token per non-zero AC coefficient:
+//   [31:16] byte offset of the coefficient inside the consumer's shared-memory column
+//           ((j >> 1) * 128 + (j & 1) * 2 for raster index j), [15:0] level * quantiser as int16.
+// The block-offset table entry is (AC token count << 24) | index of the DC token in the frame's region.
+constexpr uint32_t kTokCountShift = 24;
 
 struct VlcTables {
     uint32_t e[kVlcMaxEntries];
@@ -137,8 +139,9 @@ struct FastVlcTables {
     int      count;
 };
 
-// zigzag position -> (raster index | quantiser << 8), per component class (luma, chroma)
-struct DequantTables { uint32_t zq[2][64]; };
+// zigzag position -> (raster index | quantiser << 8), per component class (luma, chroma);
+// tz: the same for the token producer: (column byte offset << 16) | quantiser
+struct DequantTables { uint32_t zq[2][64]; uint32_t tz[2][64]; };
 
 // Encoder: symbol -> (code << 5 | length).  Index: DC-luma 0..15, DC-chroma 16..31,
 // AC-luma 32..287, AC-chroma 288..543.
@@ -227,7 +230,11 @@ inline void build_fast_vlc_tables(FastVlcTables &F) {
 
 inline void build_dequant_tables(DequantTables &D) {
     for (int c = 0; c < 2; c++)
-        for (int k = 0; k < 64; k++) D.zq[c][k] = (uint32_t)kZigzag[k] | ((uint32_t)kDecQuant[c][k] << 8);
+        for (int k = 0; k < 64; k++) {
+            const uint32_t j = kZigzag[k];
+            D.zq[c][k] = j | ((uint32_t)kDecQuant[c][k] << 8);
+            D.tz[c][k] = (((j >> 1) * 128u + (j & 1u) * 2u) << 16) | (uint32_t)kDecQuant[c][k];
+        }
 }
 
 inline void build_enc_huff_tables(EncHuffTables &E) {

@@ -69,8 +69,8 @@ AMV_HD uint32_t vlc_lookup(const uint32_t *lut, int base, uint32_t p) {
 }
 
 // Walk one 8x8 block.  Sink interface:
-//   void dc(int diff)        -- DC difference (caller owns the predictor chain)
-//   void ac(uint32_t token)  -- every AC token incl. ZRL, and EOB when the block ends with one
+//   void dc(int diff)          -- DC difference (caller owns the predictor chain)
+//   void ac(int k, int level)  -- every non-zero AC coefficient: zigzag position 1..63 and its level
 // Returns status bits (0 = clean).  Mirrors decode_block (mjpegdec.c:376-430): ZRL advances
 // without a range check, a coefficient index > 63 is the "error count" condition.
 template <class Sink>
@@ -91,17 +91,16 @@ AMV_HD uint32_t walk_block(BitReader &br, const uint32_t *lut, const int *tbl_ba
         len = e & 31; size = (e >> 5) & 15;
         const uint32_t run = (e >> 9) & 15;
         br.skip(len + size);
-        if (e & kVlcBad) { st |= AMV_ST_BADCODE; sink.ac(kTokEOB); break; }
+        if (e & kVlcBad) { st |= AMV_ST_BADCODE; break; }
         if (size == 0) {
-            if (run != 15) { sink.ac(kTokEOB); break; }
-            sink.ac(kTokZRL);
-            k += 16;
-            if (k > 1024) { sink.ac(kTokEOB); break; }   // only garbage lanes get here; keeps them bounded
+            if (run != 15) break;            // EOB
+            k += 16;                         // ZRL
+            if (k > 1024) break;             // only garbage lanes get here; keeps them bounded
             continue;
         }
         k += (int)run + 1;
-        if (k > 63) { st |= AMV_ST_COEFIDX; sink.ac(kTokEOB); break; }
-        sink.ac((e & kVlcResolved) ? (e >> 16) : ((run << 12) | ((uint32_t)extend_bits(p << len, size) & 0xfffu)));
+        if (k > 63) { st |= AMV_ST_COEFIDX; break; }
+        sink.ac(k, (e & kVlcResolved) ? (int)((int32_t)(e << 4) >> 20) : extend_bits(p << len, size));
         if (k == 63) break;
     }
     return st;
@@ -116,28 +115,5 @@ struct LaneExit {
     uint32_t nblocks;    // blocks decoded by this lane
     int      dc[3];      // sum of DC differences per component over those blocks
 };
-
-// Expand one block's tokens into dequantised coefficients (the consumer side of the token
-// format).  put(j, value) receives raster index and level * quant (mjpegdec.c:420,428).
-template <class Fetch, class Put>
-AMV_HD void expand_tokens(Fetch fetch, const uint32_t *zq, Put put) {
-    int k = 0;
-    for (;;) {
-        const uint32_t t = fetch();
-        const int lvl = (int)((int32_t)(t << 20) >> 20);
-        const int run = (int)(t >> 12);
-        if (lvl == 0) {
-            if (run != 15) break;
-            k += 16;
-            if (k > 1024) break;
-            continue;
-        }
-        k += run + 1;
-        if (k > 63) break;
-        const uint32_t e = zq[k];
-        put((int)(e & 63), lvl * (int)(e >> 8));
-        if (k == 63) break;
-    }
-}
 
 }  // namespace amv

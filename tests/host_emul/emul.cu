@@ -43,11 +43,16 @@ static std::vector<uint8_t> unstuff(const uint8_t *pkt, uint32_t size, int *st) 
     return v;
 }
 
-struct CountSink { int dcv; void dc(int d) { dcv = d; } void ac(uint32_t) {} };
-struct VecSink {
-    std::vector<uint16_t> *tok; int dcv;
+struct CountSink { int dcv; void dc(int d) { dcv = d; } void ac(int, int) {} };
+// producer side of the token format: (column byte offset << 16) | int16 value, like k_vlc_tokens
+struct TokSink {
+    std::vector<uint32_t> *tok; const uint32_t *tz; int dcv; uint32_t nac;
     void dc(int d) { dcv = d; }
-    void ac(uint32_t t) { tok->push_back((uint16_t)t); }
+    void ac(int k, int level) {
+        const uint32_t z = tz[k];
+        tok->push_back((z & 0xffff0000u) | ((uint32_t)(level * (int)(z & 0xffffu)) & 0xffffu));
+        nac++;
+    }
 };
 
 static void walk(const uint32_t *words, uint32_t nwords, uint32_t sbit, uint32_t sph, uint32_t end_bit, LaneExit &ex) {
@@ -110,8 +115,8 @@ int emul_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h, uint8_t *
             first += ex[p].nblocks; d[0] += ex[p].dc[0]; d[1] += ex[p].dc[1]; d[2] += ex[p].dc[2];
         }
     }
-    // pass 1 (k_vlc_tokens): tokens + per-block offsets; pass 2 (k_idct): tokens -> pixels
-    std::vector<uint16_t> tok;
+    // pass 1 (k_vlc_tokens): tokens + per-block (count, offset); pass 2 (k_idct): tokens -> pixels
+    std::vector<uint32_t> tok;
     std::vector<uint32_t> boff(g.nblk, 0);
     std::vector<uint8_t> have(g.nblk, 0);
     for (int p = 0; p < P; p++) {
@@ -123,15 +128,16 @@ int emul_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h, uint8_t *
         BitReader br; br.init(words, nwords, starts[p].bitpos);
         int pred[3] = { starts[p].pred[0], starts[p].pred[1], starts[p].pred[2] };
         int b = first % 6;
-        VecSink sink; sink.tok = &tok;
         for (uint32_t i = 0; i < count; i++) {
             const int tq = b >= 4, comp = b < 4 ? 0 : b - 3;
-            boff[first + i] = (uint32_t)tok.size(); have[first + i] = 1;
+            const uint32_t start = (uint32_t)tok.size();
+            have[first + i] = 1;
             tok.push_back(0);
-            const size_t at = tok.size() - 1;
+            TokSink sink; sink.tok = &tok; sink.tz = g_dq.tz[tq]; sink.nac = 0;
             st |= walk_block(br, g_vlc.e, g_vlc.base, tq, sink);
             pred[comp] += sink.dcv * (int)(g_dq.zq[tq][0] >> 8);
-            tok[at] = (uint16_t)pred[comp];
+            tok[start] = (uint32_t)pred[comp] & 0xffffu;
+            boff[first + i] = (sink.nac << kTokCountShift) | start;
             if (++b == 6) b = 0;
         }
         if (count && br.bitpos() > U * 8u) st |= AMV_ST_OVERRUN;
@@ -140,12 +146,14 @@ int emul_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h, uint8_t *
     for (int blk = 0; blk < g.nblk; blk++) {
         if (!have[blk]) continue;
         const int mb = blk / 6, b = blk % 6, mx = mb % g.mbw, my = mb / g.mbw;
-        const int tq = b >= 4, comp = b < 4 ? 0 : b - 3;
+        const int comp = b < 4 ? 0 : b - 3;
         int16_t coef[64] = { 0 };
-        const uint16_t *tp = tok.data() + boff[blk];
-        coef[0] = (int16_t)tp[0];
-        int ti = 1;
-        expand_tokens([&]() { return (uint32_t)tp[ti++]; }, g_dq.zq[tq], [&](int j, int val) { coef[j] = (int16_t)val; });
+        const uint32_t *tp = tok.data() + (boff[blk] & ((1u << kTokCountShift) - 1u));
+        const uint32_t nac = boff[blk] >> kTokCountShift;
+        for (uint32_t a = 0; a <= nac; a++) {
+            const uint32_t t = tp[a], o = t >> 16;                      // column byte offset -> raster index
+            coef[(o / 128) * 2 + ((o % 128) >> 1)] = (int16_t)(t & 0xffffu);
+        }
         uint32_t c[32], o[16];
         for (int k = 0; k < 32; k++) c[k] = (uint16_t)coef[2 * k] | ((uint32_t)(uint16_t)coef[2 * k + 1] << 16);
         idct_put_block(c, o);
