@@ -69,7 +69,13 @@ AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : 
 #if defined(__CUDACC__)
 // Shared memory through explicit 32-bit shared-window addresses: keeps the hot loops free of
 // generic-address arithmetic (ptxas otherwise re-derives the shared window base inside them).
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    // opaque to the optimiser: otherwise ptxas re-derives the shared window base (S2R SR_CgaCtaId +
+    // LEA, a ~20-cycle special-register read) at every use inside the hot loops
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));

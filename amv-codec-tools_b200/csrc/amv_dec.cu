@@ -341,6 +341,7 @@ struct TokSmem {
     uint32_t lut[kVlcMaxEntries];
     uint32_t tz[2][64];          // zigzag position -> (consumer column byte offset << 16) | quantiser
     uint32_t ring[kTokThreads / 32][kRingWords * 32];
+    uint32_t tstage[kTokThreads / 32][4 * 32];      // [slot][lane]: four tokens per lane waiting for their 16-byte store
 };
 
 __global__ void __launch_bounds__(kTokThreads)
@@ -357,9 +358,10 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (int)(gt >> log2p);
     const int p = (int)(gt & (P - 1));
-    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(S.lut);
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&S.ring[wid][lane]);   // word w of this lane: + w*128
-    const uint32_t tz_s = (uint32_t)__cvta_generic_to_shared(&S.tz[0][0]);
+    const uint32_t lut_s = smem_addr(S.lut);
+    const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: + w*128
+    const uint32_t tz_s = smem_addr(&S.tz[0][0]);
+    const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: + c*128
     const uint32_t dc_base[2] = { (uint32_t)g_fast_vlc.base[0], (uint32_t)g_fast_vlc.base[1] };
     const uint32_t ac_base[2] = { (uint32_t)g_fast_vlc.base[2], (uint32_t)g_fast_vlc.base[3] };
     const int q0l = (int)(g_dec_tables.dq.zq[0][0] >> 8), q0c = (int)(g_dec_tables.dq.zq[1][0] >> 8);
@@ -396,14 +398,14 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     const uint32_t tok_cap = cap_words * 16u;                               // tokens in the region (16 B per scan byte)
     uint32_t tok_idx = ((bit >> 1) + 4u * (uint32_t)p + 3u) & ~3u;          // first token index of this lane (multiple of 4)
     uint32_t *tok_frame = tokens + so * 4;
-    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, tcount = 0;
+    uint32_t tcount = 0;                    // tokens staged (byte offset form: 0, 128, 256, 384)
     uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;
 
-    // ---- bit source: 64-bit window + shared-memory ring
-    uint32_t rd = bit >> 5;                 // next word to merge into the window
-    uint32_t wr = rd & ~3u;                 // next word the ring receives (16-byte groups)
-    uint64_t acc = 0;
-    int nb = 0;
+    // ---- bit source: absolute bit position + shared-memory ring; every symbol looks at the 32 bits
+    // starting at `bp` through one funnel shift of two ring words (a symbol is at most 26 bits), so
+    // there is no accumulator to refill and no divergent refill branch inside the symbol loop
+    uint32_t bp = bit;                      // next unread bit of the scan
+    uint32_t wr = (bit >> 5) & ~3u;         // next word the ring receives (16-byte groups); ring = words [wr-16, wr)
     uint4 pend = make_uint4(0, 0, 0, 0);
     bool have_pend = false;
     auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
@@ -422,32 +424,30 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         wr += 8;
         pend = load_group(wr);
         have_pend = true;
-        // prime the window at the (unaligned) start bit
-        const uint32_t w0 = lds32(ring_s + (rd & (kRingWords - 1)) * 128);
-        const uint32_t w1 = lds32(ring_s + ((rd + 1) & (kRingWords - 1)) * 128);
-        const uint32_t sh = bit & 31;
-        acc = (((uint64_t)w0 << 32) | w1) << sh;
-        nb = 64 - (int)sh;
-        rd += 2;
     }
-    auto refill = [&]() {
-        if (nb <= 32) {
-            uint32_t w;
-            if (rd < wr) w = lds32(ring_s + (rd & (kRingWords - 1)) * 128);
-            else w = rd < cap_words ? bswap32(__ldg(words + rd)) : 0u;     // ring ran dry inside a huge block
-            rd++;
-            acc |= (uint64_t)w << (32 - nb);
-            nb += 32;
+    auto window = [&]() -> uint32_t {       // the 32 bits at bp
+        const uint32_t w = bp >> 5;
+        uint32_t a, c;
+        if (w + 2 <= wr) {
+            a = lds32(ring_s + ((w & (kRingWords - 1)) << 7));
+            c = lds32(ring_s + (((w + 1) & (kRingWords - 1)) << 7));
+        } else {                            // ring ran dry inside a huge block: straight from memory
+            a = w < cap_words ? bswap32(__ldg(words + w)) : 0u;
+            c = w + 1 < cap_words ? bswap32(__ldg(words + w + 1)) : 0u;
         }
+        return __funnelshift_l(c, a, bp & 31);
+    };
+    auto flush4 = [&]() {
+        const uint4 q = make_uint4(lds32(tst_s), lds32(tst_s + 128), lds32(tst_s + 256), lds32(tst_s + 384));
+        if (tok_idx + 4 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = q;
+        else st |= AMV_ST_OVERRUN;
+        tok_idx += 4;
+        tcount = 0;
     };
     auto push = [&](uint32_t tok) {        // append one 32-bit token
-        t0 = t1; t1 = t2; t2 = t3; t3 = tok;
-        if (++tcount == 4) {
-            if (tok_idx + 4 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
-            else st |= AMV_ST_OVERRUN;
-            tok_idx += 4;
-            tcount = 0;
-        }
+        sts32(tst_s + tcount, tok);
+        tcount += 128;
+        if (tcount == 512) flush4();
     };
 
     uint32_t maxcount = count;
@@ -459,19 +459,20 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         const bool on = i < count;
         // ---- converged: ring top-up
         if (on) {
+            const uint32_t rd = bp >> 5;                                      // words below this one are dead
             if (rd > wr) { wr = rd & ~3u; have_pend = false; }                // the ring ran dry in the last block: restart it
             if (have_pend && (int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; have_pend = false; }
             if (!have_pend && (int)(wr - rd) <= kRingWords - 8) { pend = load_group(wr); have_pend = true; }
         }
         if (!on) continue;
         const int tq = b >= 4 ? 1 : 0;
-        const uint32_t blk_start = min(tok_idx + tcount, tok_cap);
+        const uint32_t blk_start = min(tok_idx + (tcount >> 7), tok_cap);
         const uint32_t tzq_s = tz_s + (uint32_t)tq * 256u;
+        const uint32_t dc_lut_s = lut_s + (tq ? dc_base[1] : dc_base[0]) * 4u, ac_lut_s = lut_s + (tq ? ac_base[1] : ac_base[0]) * 4u;
         // ---- DC (mjpeg_decode_dc, mjpegdec.c:358-373)
         {
-            refill();
-            const uint32_t hi = (uint32_t)(acc >> 32);
-            uint32_t e = lds32(lut_s + (dc_base[tq] + (hi >> (32 - kVlcFirstBits))) * 4);
+            const uint32_t hi = window();
+            uint32_t e = lds32(dc_lut_s + (hi >> (32 - kVlcFirstBits)) * 4);
             if ((e & 0xff) == 0) {
                 if (e & 0x100) { st |= AMV_ST_BADCODE; e = 1u | (32u << 8) | (1u << 16); }
                 else e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
@@ -481,7 +482,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             const uint32_t top = hi << len;
             const int sg = (int)(~top) >> 31;                                 // get_xbits: -1 if the first bit is 0
             const int diff = (int)((__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg);
-            acc <<= total; nb -= (int)total;
+            bp += total;
             int pr;
             if (b < 4) pr = (pred0 += diff * q0l);
             else if (b == 4) pr = (pred1 += diff * q0c);
@@ -492,17 +493,16 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         int k = 0;
         uint32_t nac = 0;
         for (;;) {
-            refill();
-            const uint32_t hi = (uint32_t)(acc >> 32);
-            uint32_t e = lds32(lut_s + (ac_base[tq] + (hi >> (32 - kVlcFirstBits))) * 4);
+            const uint32_t hi = window();
+            uint32_t e = lds32(ac_lut_s + (hi >> (32 - kVlcFirstBits)) * 4);
             if ((e & 0xff) == 0) {
                 if (!(e & 0x100))
                     e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
-                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; acc <<= 1; nb -= 1; break; }
+                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; bp += 1; break; }
             }
             const uint32_t len = e & 0xff, rsh = (e >> 8) & 0xff, total = (e >> 16) & 0xff, run = e >> 28;
             const uint32_t top = hi << len;
-            acc <<= total; nb -= (int)total;
+            bp += total;
             if (rsh == 32) {                                                   // size 0: EOB or ZRL
                 if (run != 15) break;
                 k += 16;
@@ -522,13 +522,9 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         if (++b == 6) b = 0;
     }
     // flush the partly filled group (unused upper tokens are don't-care, the group is ours alone)
-    if (count && tcount) {
-        for (uint32_t j = tcount; j < 4; j++) { t0 = t1; t1 = t2; t2 = t3; t3 = 0; }
-        if (tok_idx + 4 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = make_uint4(t0, t1, t2, t3);
-        else st |= AMV_ST_OVERRUN;
-    }
+    if (count && tcount) flush4();
     // a lane that owns no block just passes through; otherwise it must end inside the scan
-    if (count && rd * 32u - (uint32_t)nb > U * 8u) st |= AMV_ST_OVERRUN;
+    if (count && bp > U * 8u) st |= AMV_ST_OVERRUN;
     if (st && f < n) atomicOr(&status[f], (int32_t)st);
 }
 
