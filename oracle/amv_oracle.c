@@ -706,3 +706,230 @@ AMVO_API int amvo_adpcm_encode_chunks(const int16_t *pcm, const uint64_t *pcm_of
     }
     return n;
 }
+
+/* ========================================================================== *
+ * amvlib flavour: C-AMVDecoder/amvlib decodes the same packets with
+ * different arithmetic -- its own quantiser tables, a zigzag table with a typo, a
+ * Chen-Wang IDCT on 32-bit ints and a fixed-point YUV->BGR24 bottom-up store.
+ * Paths below are relative to C-AMVDecoder/amvlib/.
+ * PARITY PINNED by tests/test_oracle_vs_ref.py against oracle/_ref/libamvlibref.so
+ * (the unmodified amvlib compiled in place) on the fixture bin/AMV1.amv and on
+ * reference-encoded synthetic frames; vectors in tests/golden/amvlib_golden.npz.
+ * ========================================================================== */
+
+/* amv_luminance_quant_tbl / amv_chrominance_quant_tbl (AmvJpeg.c:30-39,52-61), indexed by
+ * zigzag position (IQtIZzBlock uses pQt[tag], tag = zigzag index, :1041-1046) */
+static const uint8_t kAmvlibQuant[2][64] = {
+  { 0x08, 0x06, 0x06, 0x07, 0x06, 0x05, 0x08, 0x07, 0x07, 0x07, 0x09, 0x09, 0x08, 0x0A, 0x0C, 0x14,
+    0x0D, 0x0C, 0x0B, 0x0B, 0x0C, 0x19, 0x12, 0x13, 0x0F, 0x14, 0x1D, 0x1A, 0x1F, 0x1E, 0x1D, 0x1A,
+    0x1C, 0x1C, 0x20, 0x24, 0x2E, 0x27, 0x20, 0x22, 0x2C, 0x27, 0x1C, 0x1C, 0x28, 0x37, 0x29, 0x2C,
+    0x30, 0x31, 0x34, 0x34, 0x34, 0x1F, 0x27, 0x39, 0x3D, 0x38, 0x32, 0x3C, 0x2E, 0x33, 0x34, 0x32 },
+  { 0x09, 0x09, 0x09, 0x0C, 0x0B, 0x0C, 0x18, 0x0D, 0x0D, 0x18, 0x32, 0x21, 0x1C, 0x21, 0x32, 0x32,
+    0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32,
+    0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32,
+    0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32, 0x32 },
+};
+
+/* Raster position -> zigzag index as amvlib has it (AmvJpeg.c:131-141): the standard scan except
+ * that raster (3,4) reads index 37 instead of 31 -- coefficient 31 is never used and coefficient 37
+ * lands in two places. */
+AMVO_API void amvo_amvlib_zigzag(uint8_t raster_to_zz[64])
+{
+    build_tables();
+    for (int k = 0; k < 64; k++) raster_to_zz[g_zz[k]] = (uint8_t)k;
+    raster_to_zz[3 * 8 + 4] = 37;
+}
+
+static inline int32_t wr32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }     /* 32-bit wrap */
+static inline int32_t shl32(int32_t v, int s) { return (int32_t)((uint32_t)v << s); }
+static inline int iclp(int32_t v) { return v < -256 ? -256 : (v > 255 ? 255 : v); }  /* Initialize_Fast_IDCT :1069-1076; the
+                                        table covers -512..511, beyond that the reference reads past it: we saturate */
+
+#define AW1 2841
+#define AW2 2676
+#define AW3 2408
+#define AW5 1609
+#define AW6 1108
+#define AW7 565
+
+/* idctrow (AmvJpeg.c:1078-1125) */
+static void amvlib_idct_row(int32_t *b)
+{
+    int32_t x0, x1, x2, x3, x4, x5, x6, x7, x8;
+    x1 = shl32(b[4], 11); x2 = b[6]; x3 = b[2]; x4 = b[1]; x5 = b[7]; x6 = b[5]; x7 = b[3];
+    if (!(x1 | x2 | x3 | x4 | x5 | x6 | x7)) { int32_t v = shl32(b[0], 3); for (int i = 0; i < 8; i++) b[i] = v; return; }
+    x0 = wr32((int64_t)shl32(b[0], 11) + 128);
+    x8 = wr32((int64_t)AW7 * wr32((int64_t)x4 + x5));
+    x4 = wr32(x8 + (int64_t)(AW1 - AW7) * x4);
+    x5 = wr32(x8 - (int64_t)(AW1 + AW7) * x5);
+    x8 = wr32((int64_t)AW3 * wr32((int64_t)x6 + x7));
+    x6 = wr32(x8 - (int64_t)(AW3 - AW5) * x6);
+    x7 = wr32(x8 - (int64_t)(AW3 + AW5) * x7);
+    x8 = wr32((int64_t)x0 + x1); x0 = wr32((int64_t)x0 - x1);
+    x1 = wr32((int64_t)AW6 * wr32((int64_t)x3 + x2));
+    x2 = wr32(x1 - (int64_t)(AW2 + AW6) * x2);
+    x3 = wr32(x1 + (int64_t)(AW2 - AW6) * x3);
+    x1 = wr32((int64_t)x4 + x6); x4 = wr32((int64_t)x4 - x6);
+    x6 = wr32((int64_t)x5 + x7); x5 = wr32((int64_t)x5 - x7);
+    x7 = wr32((int64_t)x8 + x3); x8 = wr32((int64_t)x8 - x3);
+    x3 = wr32((int64_t)x0 + x2); x0 = wr32((int64_t)x0 - x2);
+    x2 = wr32((int64_t)181 * wr32((int64_t)x4 + x5) + 128) >> 8;
+    x4 = wr32((int64_t)181 * wr32((int64_t)x4 - x5) + 128) >> 8;
+    b[0] = wr32((int64_t)x7 + x1) >> 8; b[1] = wr32((int64_t)x3 + x2) >> 8;
+    b[2] = wr32((int64_t)x0 + x4) >> 8; b[3] = wr32((int64_t)x8 + x6) >> 8;
+    b[4] = wr32((int64_t)x8 - x6) >> 8; b[5] = wr32((int64_t)x0 - x4) >> 8;
+    b[6] = wr32((int64_t)x3 - x2) >> 8; b[7] = wr32((int64_t)x7 - x1) >> 8;
+}
+
+/* idctcol (AmvJpeg.c:1127-1175) */
+static void amvlib_idct_col(int32_t *b)
+{
+    int32_t x0, x1, x2, x3, x4, x5, x6, x7, x8;
+    x1 = shl32(b[8 * 4], 8); x2 = b[8 * 6]; x3 = b[8 * 2]; x4 = b[8 * 1]; x5 = b[8 * 7]; x6 = b[8 * 5]; x7 = b[8 * 3];
+    if (!(x1 | x2 | x3 | x4 | x5 | x6 | x7)) {
+        int v = iclp(wr32((int64_t)b[0] + 32) >> 6);
+        for (int i = 0; i < 8; i++) b[8 * i] = v;
+        return;
+    }
+    x0 = wr32((int64_t)shl32(b[0], 8) + 8192);
+    x8 = wr32((int64_t)AW7 * wr32((int64_t)x4 + x5) + 4);
+    x4 = wr32(x8 + (int64_t)(AW1 - AW7) * x4) >> 3;
+    x5 = wr32(x8 - (int64_t)(AW1 + AW7) * x5) >> 3;
+    x8 = wr32((int64_t)AW3 * wr32((int64_t)x6 + x7) + 4);
+    x6 = wr32(x8 - (int64_t)(AW3 - AW5) * x6) >> 3;
+    x7 = wr32(x8 - (int64_t)(AW3 + AW5) * x7) >> 3;
+    x8 = wr32((int64_t)x0 + x1); x0 = wr32((int64_t)x0 - x1);
+    x1 = wr32((int64_t)AW6 * wr32((int64_t)x3 + x2) + 4);
+    x2 = wr32(x1 - (int64_t)(AW2 + AW6) * x2) >> 3;
+    x3 = wr32(x1 + (int64_t)(AW2 - AW6) * x3) >> 3;
+    x1 = wr32((int64_t)x4 + x6); x4 = wr32((int64_t)x4 - x6);
+    x6 = wr32((int64_t)x5 + x7); x5 = wr32((int64_t)x5 - x7);
+    x7 = wr32((int64_t)x8 + x3); x8 = wr32((int64_t)x8 - x3);
+    x3 = wr32((int64_t)x0 + x2); x0 = wr32((int64_t)x0 - x2);
+    x2 = wr32((int64_t)181 * wr32((int64_t)x4 + x5) + 128) >> 8;
+    x4 = wr32((int64_t)181 * wr32((int64_t)x4 - x5) + 128) >> 8;
+    b[8 * 0] = iclp(wr32((int64_t)x7 + x1) >> 14); b[8 * 1] = iclp(wr32((int64_t)x3 + x2) >> 14);
+    b[8 * 2] = iclp(wr32((int64_t)x0 + x4) >> 14); b[8 * 3] = iclp(wr32((int64_t)x8 + x6) >> 14);
+    b[8 * 4] = iclp(wr32((int64_t)x8 - x6) >> 14); b[8 * 5] = iclp(wr32((int64_t)x0 - x4) >> 14);
+    b[8 * 6] = iclp(wr32((int64_t)x3 - x2) >> 14); b[8 * 7] = iclp(wr32((int64_t)x7 - x1) >> 14);
+}
+
+/* Fast_IDCT (AmvJpeg.c:1050-1059) on dequantised raster coefficients, in place; values -256..255 */
+AMVO_API void amvo_amvlib_idct(int32_t blk[64])
+{
+    for (int i = 0; i < 8; i++) amvlib_idct_row(blk + 8 * i);
+    for (int i = 0; i < 8; i++) amvlib_idct_col(blk + i);
+}
+
+static inline uint8_t clip_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* StoreBuffer's colour conversion (AmvJpeg.c:808-810): y already carries its +128, u/v are centred */
+AMVO_API void amvo_amvlib_yuv_to_bgr(int y, int u, int v, uint8_t bgr[3])
+{
+    bgr[2] = clip_u8(((y << 8) + 18 * u + 367 * v) >> 8);
+    bgr[1] = clip_u8(((y << 8) - 159 * u - 220 * v) >> 8);
+    bgr[0] = clip_u8(((y << 8) + 411 * u - 29 * v) >> 8);
+}
+
+/* AmvVideoDecode -> AmvJpegDecode (AMVDec.c:259-286, AmvJpeg.c:1515-1539): one packet -> one
+ * bottom-up BGR24 bitmap with rows of line_bytes bytes (the reference: WIDTHBYTES(w*24)).
+ * Entropy layer: ReadByte (:1061-1069) drops the byte after every FF, DecodeElement (:842-936) is a
+ * canonical Huffman decode over the K.3 tables + JPEG sign extension, HufBlock (:938-976) fills 64
+ * coefficients in zigzag order, DecodeMCUBlock (:1177-1242) chains the DC per component from 0 in
+ * 16-bit arithmetic.  Pixels outside w x h are not stored; bytes of the bitmap that no pixel covers
+ * are left as the caller provided them (the reference memsets its buffer to 0 first).
+ * Returns 0 or a mask of AMVO_E_*; coef_dump (optional) receives the dequantised raster blocks. */
+AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,
+                                      uint8_t *bgr, int line_bytes, int32_t *coef_dump)
+{
+    build_tables();
+    int flags = 0;
+    if (size < 4) flags |= AMVO_E_SHORT;
+    uint8_t r2z[64];
+    amvo_amvlib_zigzag(r2z);
+    /* the byte reader: everything after SOI, dropping the byte that follows an FF */
+    uint8_t *scan = (uint8_t *)malloc((size_t)size + 16);
+    size_t nscan = 0;
+    for (size_t i = 2; i < size; i++) { scan[nscan++] = pkt[i]; if (pkt[i] == 0xff) i++; }
+    bitr br = { scan, nscan, 0, 0, 0, 0 };
+    int16_t pred[3] = { 0, 0, 0 };
+    const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
+    int nblk = 0;
+    for (int my = 0; my < mbh && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); my++)
+    for (int mx = 0; mx < mbw && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); mx++) {
+        int32_t px[6][64];
+        for (int b = 0; b < 6; b++, nblk++) {
+            const int comp = b < 4 ? 0 : b - 3, tq = comp ? 1 : 0;
+            int16_t zz[64] = { 0 };
+            int s = huff_get(&br, tq);
+            if (s < 0) { flags |= AMVO_E_BADCODE; break; }
+            pred[comp] = (int16_t)(pred[comp] + (int16_t)get_extend(&br, s));
+            zz[0] = pred[comp];
+            for (int k = 1; k < 64;) {
+                int rs = huff_get(&br, 2 + tq);
+                if (rs < 0) { flags |= AMVO_E_BADCODE; break; }
+                if (rs == 0x00) break;
+                k += rs >> 4;                                   /* run of zeros, then one value (0 for ZRL) */
+                int lv = get_extend(&br, rs & 15);
+                if (k > 63) { flags |= AMVO_E_COEFIDX; break; }  /* the reference writes past BlockBuffer here */
+                zz[k++] = (int16_t)lv;
+            }
+            if (flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)) break;
+            for (int i = 0; i < 64; i++) px[b][i] = (int32_t)zz[r2z[i]] * kAmvlibQuant[tq][r2z[i]];
+            if (coef_dump) memcpy(coef_dump + (size_t)nblk * 64, px[b], sizeof(px[b]));
+            amvo_amvlib_idct(px[b]);
+        }
+        if (flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)) break;
+        for (int i = 0; i < 16; i++) {
+            const int Y = my * 16 + i;
+            if (Y >= h) break;
+            uint8_t *row = bgr + (size_t)(h - 1 - Y) * line_bytes;
+            for (int j = 0; j < 16; j++) {
+                const int X = mx * 16 + j;
+                if (X >= w) break;
+                const int yv = px[(i >> 3) * 2 + (j >> 3)][(i & 7) * 8 + (j & 7)] + 128;
+                const int ci = (i >> 1) * 8 + (j >> 1);
+                amvo_amvlib_yuv_to_bgr(yv, px[4][ci], px[5][ci], row + 3 * X);
+            }
+        }
+    }
+    if (br_bits_used(&br) > nscan * 8) flags |= AMVO_E_OVERRUN;
+    free(scan);
+    return flags;
+}
+
+AMVO_API int amvo_amvlib_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size, int n,
+                                       int w, int h, uint8_t *bgr, int line_bytes, uint64_t frame_stride, int *status)
+{
+    for (int i = 0; i < n; i++) {
+        int st = amvo_amvlib_decode_frame(pkts + off[i], size[i], w, h, bgr + (size_t)i * frame_stride, line_bytes, NULL);
+        if (status) status[i] = st;
+    }
+    return n;
+}
+
+/* AmvAudioDecode (AMVDec.c:288-340) + AdpcmImaDecodeFrame (AdpcmIma.c:206-242): predictor = le16,
+ * step index = ONE byte (chunk[2]), data decoded in groups of four bytes, high nibble first -- so a
+ * chunk whose data length is not a multiple of 4 yields up to 6 samples from bytes past its end
+ * (taken as zero here, which is what the harness feeds the reference).  Returns samples written
+ * (8 * ceil((size-8)/4)) or -1. */
+AMVO_API int amvo_amvlib_audio_decode_chunk(const uint8_t *c, uint32_t size, int16_t *pcm)
+{
+    if (size <= 8) return -1;
+    int pred = (int16_t)(c[0] | (c[1] << 8)), idx = c[2];
+    if (idx > 88) return -1;                                   /* the reference indexes past step_table */
+    const uint32_t nd = size - 8, ng = (nd + 3) / 4;
+    int n = 0;
+    for (uint32_t i = 0; i < ng * 4; i++) {
+        const int byte = i < nd ? c[8 + i] : 0;
+        for (int half = 0; half < 2; half++) {
+            int nib = half ? (byte & 15) : (byte >> 4);
+            int step = kImaStep[idx];
+            idx = clampi(idx + kImaIdxAdj[nib & 7], 0, 88);
+            int diff = ((2 * (nib & 7) + 1) * step) >> 3;
+            pred = clampi(nib & 8 ? pred - diff : pred + diff, -32768, 32767);
+            pcm[n++] = (int16_t)pred;
+        }
+    }
+    return n;
+}

@@ -84,3 +84,65 @@ done
 gcc $CFLAGS -c "$HERE/ref_harness.c" -o "$OUT/obj/ref_harness.o"
 gcc -shared -o "$OUT/libamvref.so" "$OUT/obj/ref_harness.o" $objs -lm -Wl,--no-undefined
 echo "built $OUT/libamvref.so"
+
+# ---- amvlib (C-AMVDecoder/amvlib), compiled in place ------------------------
+# The library is Win32 code: AmvJpeg.c includes <windows.h>/<io.h> and "AmvDec.h" (the file is
+# AMVDec.h), and the sources assume a 32-bit `long` (AMVHeader.h:6 DWORD, AMVDec.c:154, AmvJpeg.c:431).
+# Instead of patching a copy, three generated shim headers stand in for the missing ones, and
+# amvlib_long32.h (force-included) pulls in the libc headers first and then makes `long` 32 bits
+# wide for the library's own code, which is what it was written for.
+AMVLIB="${AMV_REFERENCE_ROOT:-/root/reference}/C-AMVDecoder/amvlib"
+if [ -d "$AMVLIB" ]; then
+  SH="$OUT/cfg/amvlib_shim"
+  mkdir -p "$SH"
+  cat > "$SH/amvlib_long32.h" <<EOT
+/* written by oracle/build_ref.sh */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#define long int
+EOT
+  cat > "$SH/windows.h" <<EOT
+/* written by oracle/build_ref.sh: the few Win32 names AmvJpeg.c mentions (only its JPEG-file ->
+   BMP-file helper, which the tests never call, uses the file and Global* functions) */
+#ifndef AMVLIB_SHIM_WINDOWS_H
+#define AMVLIB_SHIM_WINDOWS_H
+#include <stdint.h>
+typedef uint32_t DWORD; typedef int32_t LONG; typedef uint16_t WORD; typedef uint8_t BYTE;
+typedef char *LPSTR; typedef int HFILE; typedef void *HGLOBAL; typedef int BOOL;
+#pragma pack(push, 2)
+typedef struct { WORD bfType; DWORD bfSize; WORD bfReserved1, bfReserved2; DWORD bfOffBits; } BITMAPFILEHEADER;
+#pragma pack(pop)
+typedef struct { DWORD biSize; LONG biWidth, biHeight; WORD biPlanes, biBitCount; DWORD biCompression, biSizeImage;
+                 LONG biXPelsPerMeter, biYPelsPerMeter; DWORD biClrUsed, biClrImportant; } BITMAPINFOHEADER, *LPBITMAPINFOHEADER;
+typedef struct { BYTE b, g, r, x; } RGBQUAD;
+#define HFILE_ERROR (-1)
+#define OF_READ 0
+#define GHND 0
+#define BI_RGB 0
+#define MAKEWORD(a, b) ((WORD)(((BYTE)(a)) | ((WORD)((BYTE)(b))) << 8))
+static inline HFILE _lopen(const char *n, int m) { (void)n; (void)m; return HFILE_ERROR; }
+static inline LONG _llseek(HFILE f, LONG o, int w) { (void)f; (void)o; (void)w; return 0; }
+static inline LONG _hread(HFILE f, void *b, LONG n) { (void)f; (void)b; (void)n; return 0; }
+static inline HFILE _lclose(HFILE f) { (void)f; return 0; }
+static inline HFILE _lcreat(const char *n, int a) { (void)n; (void)a; return HFILE_ERROR; }
+static inline LONG _lwrite(HFILE f, const char *b, LONG n) { (void)f; (void)b; (void)n; return 0; }
+static inline HGLOBAL GlobalAlloc(int f, DWORD n) { (void)f; return calloc(1, n ? n : 1); }
+static inline void *GlobalLock(HGLOBAL h) { return h; }
+static inline int GlobalUnlock(HGLOBAL h) { (void)h; return 0; }
+static inline HGLOBAL GlobalFree(HGLOBAL h) { free(h); return 0; }
+#endif
+EOT
+  echo "/* written by oracle/build_ref.sh */" > "$SH/io.h"
+  echo "#include \"$AMVLIB/AMVDec.h\"" > "$SH/AmvDec.h"
+  ACF="-O2 -fPIC -std=gnu99 -fcommon -fno-strict-aliasing -fwrapv -w -include $SH/amvlib_long32.h -I$SH -I$AMVLIB"
+  aobjs=""
+  for f in AMVDec AmvJpeg AdpcmIma; do
+    gcc $ACF -c "$AMVLIB/$f.c" -o "$OUT/obj/amvlib_$f.o"
+    aobjs="$aobjs $OUT/obj/amvlib_$f.o"
+  done
+  gcc $ACF -c "$HERE/amvlib_harness.c" -o "$OUT/obj/amvlib_harness.o"
+  gcc -shared -o "$OUT/libamvlibref.so" "$OUT/obj/amvlib_harness.o" $aobjs -lm -Wl,--no-undefined
+  echo "built $OUT/libamvlibref.so"
+fi
