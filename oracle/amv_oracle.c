@@ -742,8 +742,9 @@ AMVO_API void amvo_amvlib_zigzag(uint8_t raster_to_zz[64])
 
 static inline int32_t wr32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }     /* 32-bit wrap */
 static inline int32_t shl32(int32_t v, int s) { return (int32_t)((uint32_t)v << s); }
-static inline int iclp(int32_t v) { return v < -256 ? -256 : (v > 255 ? 255 : v); }  /* Initialize_Fast_IDCT :1069-1076; the
-                                        table covers -512..511, beyond that the reference reads past it: we saturate */
+/* Initialize_Fast_IDCT :1069-1076: the clamp table covers -512..511; beyond that the reference reads
+ * past it (undefined), we saturate and report it through *ud */
+static inline int iclp_u(int32_t v, uint8_t *ud) { if (ud && (v < -512 || v > 511)) *ud = 1; return v < -256 ? -256 : (v > 255 ? 255 : v); }
 
 #define AW1 2841
 #define AW2 2676
@@ -782,13 +783,14 @@ static void amvlib_idct_row(int32_t *b)
 }
 
 /* idctcol (AmvJpeg.c:1127-1175) */
-static void amvlib_idct_col(int32_t *b)
+static void amvlib_idct_col(int32_t *b, uint8_t *ud /* 8 flags with stride 8, or NULL */)
 {
+#define iclp(v, i) iclp_u((v), ud ? ud + 8 * (i) : NULL)
     int32_t x0, x1, x2, x3, x4, x5, x6, x7, x8;
     x1 = shl32(b[8 * 4], 8); x2 = b[8 * 6]; x3 = b[8 * 2]; x4 = b[8 * 1]; x5 = b[8 * 7]; x6 = b[8 * 5]; x7 = b[8 * 3];
     if (!(x1 | x2 | x3 | x4 | x5 | x6 | x7)) {
-        int v = iclp(wr32((int64_t)b[0] + 32) >> 6);
-        for (int i = 0; i < 8; i++) b[8 * i] = v;
+        const int32_t t = wr32((int64_t)b[0] + 32) >> 6;
+        for (int i = 0; i < 8; i++) b[8 * i] = iclp(t, i);
         return;
     }
     x0 = wr32((int64_t)shl32(b[0], 8) + 8192);
@@ -808,18 +810,21 @@ static void amvlib_idct_col(int32_t *b)
     x3 = wr32((int64_t)x0 + x2); x0 = wr32((int64_t)x0 - x2);
     x2 = wr32((int64_t)181 * wr32((int64_t)x4 + x5) + 128) >> 8;
     x4 = wr32((int64_t)181 * wr32((int64_t)x4 - x5) + 128) >> 8;
-    b[8 * 0] = iclp(wr32((int64_t)x7 + x1) >> 14); b[8 * 1] = iclp(wr32((int64_t)x3 + x2) >> 14);
-    b[8 * 2] = iclp(wr32((int64_t)x0 + x4) >> 14); b[8 * 3] = iclp(wr32((int64_t)x8 + x6) >> 14);
-    b[8 * 4] = iclp(wr32((int64_t)x8 - x6) >> 14); b[8 * 5] = iclp(wr32((int64_t)x0 - x4) >> 14);
-    b[8 * 6] = iclp(wr32((int64_t)x3 - x2) >> 14); b[8 * 7] = iclp(wr32((int64_t)x7 - x1) >> 14);
+    b[8 * 0] = iclp(wr32((int64_t)x7 + x1) >> 14, 0); b[8 * 1] = iclp(wr32((int64_t)x3 + x2) >> 14, 1);
+    b[8 * 2] = iclp(wr32((int64_t)x0 + x4) >> 14, 2); b[8 * 3] = iclp(wr32((int64_t)x8 + x6) >> 14, 3);
+    b[8 * 4] = iclp(wr32((int64_t)x8 - x6) >> 14, 4); b[8 * 5] = iclp(wr32((int64_t)x0 - x4) >> 14, 5);
+    b[8 * 6] = iclp(wr32((int64_t)x3 - x2) >> 14, 6); b[8 * 7] = iclp(wr32((int64_t)x7 - x1) >> 14, 7);
+#undef iclp
 }
 
 /* Fast_IDCT (AmvJpeg.c:1050-1059) on dequantised raster coefficients, in place; values -256..255 */
-AMVO_API void amvo_amvlib_idct(int32_t blk[64])
+AMVO_API void amvo_amvlib_idct_ex(int32_t blk[64], uint8_t ud[64] /* or NULL: 1 where the reference is undefined */)
 {
+    if (ud) memset(ud, 0, 64);
     for (int i = 0; i < 8; i++) amvlib_idct_row(blk + 8 * i);
-    for (int i = 0; i < 8; i++) amvlib_idct_col(blk + i);
+    for (int i = 0; i < 8; i++) amvlib_idct_col(blk + i, ud ? ud + i : NULL);
 }
+AMVO_API void amvo_amvlib_idct(int32_t blk[64]) { amvo_amvlib_idct_ex(blk, NULL); }
 
 static inline uint8_t clip_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
@@ -839,8 +844,9 @@ AMVO_API void amvo_amvlib_yuv_to_bgr(int y, int u, int v, uint8_t bgr[3])
  * 16-bit arithmetic.  Pixels outside w x h are not stored; bytes of the bitmap that no pixel covers
  * are left as the caller provided them (the reference memsets its buffer to 0 first).
  * Returns 0 or a mask of AMVO_E_*; coef_dump (optional) receives the dequantised raster blocks. */
-AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,
-                                      uint8_t *bgr, int line_bytes, int32_t *coef_dump)
+AMVO_API int amvo_amvlib_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int h,
+                                         uint8_t *bgr, int line_bytes, int32_t *coef_dump,
+                                         uint8_t *undef /* optional, laid out like bgr: 1 where the reference is undefined */)
 {
     build_tables();
     int flags = 0;
@@ -858,6 +864,7 @@ AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, 
     for (int my = 0; my < mbh && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); my++)
     for (int mx = 0; mx < mbw && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); mx++) {
         int32_t px[6][64];
+        uint8_t ud[6][64];
         for (int b = 0; b < 6; b++, nblk++) {
             const int comp = b < 4 ? 0 : b - 3, tq = comp ? 1 : 0;
             int16_t zz[64] = { 0 };
@@ -877,7 +884,7 @@ AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, 
             if (flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)) break;
             for (int i = 0; i < 64; i++) px[b][i] = (int32_t)zz[r2z[i]] * kAmvlibQuant[tq][r2z[i]];
             if (coef_dump) memcpy(coef_dump + (size_t)nblk * 64, px[b], sizeof(px[b]));
-            amvo_amvlib_idct(px[b]);
+            amvo_amvlib_idct_ex(px[b], ud[b]);
         }
         if (flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)) break;
         for (int i = 0; i < 16; i++) {
@@ -890,6 +897,8 @@ AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, 
                 const int yv = px[(i >> 3) * 2 + (j >> 3)][(i & 7) * 8 + (j & 7)] + 128;
                 const int ci = (i >> 1) * 8 + (j >> 1);
                 amvo_amvlib_yuv_to_bgr(yv, px[4][ci], px[5][ci], row + 3 * X);
+                if (undef) memset(undef + (size_t)(h - 1 - Y) * line_bytes + 3 * X,
+                                  ud[(i >> 3) * 2 + (j >> 3)][(i & 7) * 8 + (j & 7)] | ud[4][ci] | ud[5][ci], 3);
             }
         }
     }
@@ -898,11 +907,19 @@ AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, 
     return flags;
 }
 
+AMVO_API int amvo_amvlib_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,
+                                      uint8_t *bgr, int line_bytes, int32_t *coef_dump)
+{
+    return amvo_amvlib_decode_frame_ex(pkt, size, w, h, bgr, line_bytes, coef_dump, NULL);
+}
+
 AMVO_API int amvo_amvlib_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size, int n,
-                                       int w, int h, uint8_t *bgr, int line_bytes, uint64_t frame_stride, int *status)
+                                       int w, int h, uint8_t *bgr, int line_bytes, uint64_t frame_stride, int *status,
+                                       uint8_t *undef)
 {
     for (int i = 0; i < n; i++) {
-        int st = amvo_amvlib_decode_frame(pkts + off[i], size[i], w, h, bgr + (size_t)i * frame_stride, line_bytes, NULL);
+        int st = amvo_amvlib_decode_frame_ex(pkts + off[i], size[i], w, h, bgr + (size_t)i * frame_stride, line_bytes, NULL,
+                                             undef ? undef + (size_t)i * frame_stride : NULL);
         if (status) status[i] = st;
     }
     return n;

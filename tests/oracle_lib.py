@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libamvoracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libamvref.so")
+AMVLIB_REF_SO = os.path.join(ORACLE_DIR, "_ref", "libamvlibref.so")
 FIXTURE_AMV = "/root/reference/C-AMVDecoder/bin/AMV1.amv"
 
 
@@ -45,7 +46,61 @@ def offsets_of(sizes):
     return off
 
 
-class Oracle:
+def amvlib_line_bytes(w):
+    """WIDTHBYTES(w*24) of AmvJpeg.c:420,1526: bytes per bitmap row"""
+    return (w * 24 + 31) // 32 * 4
+
+
+class _AmvlibOracleMixin:
+    """amvlib flavour of the oracle"""
+
+    def amvlib_zigzag(self):
+        z = np.zeros(64, np.uint8)
+        self.lib.amvo_amvlib_zigzag(_p(z))
+        return z
+
+    def amvlib_idct(self, blocks):
+        b = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 64).copy()
+        for i in range(b.shape[0]):
+            self.lib.amvo_amvlib_idct(_p(b[i]))
+        return b
+
+    def amvlib_decode_frames(self, pkts, off, size, w, h, line_bytes=None, undef=False):
+        """-> bgr (n, h, line_bytes), status[, undef mask]: the mask is 1 where an IDCT output left the
+        reference's clamp table (-512..511), i.e. where amvlib itself reads foreign memory."""
+        n = len(size)
+        lb = line_bytes or amvlib_line_bytes(w)
+        bgr = np.zeros((n, h, lb), np.uint8)
+        um = np.zeros((n, h, lb), np.uint8) if undef else None
+        st = np.zeros(n, np.int32)
+        self.lib.amvo_amvlib_decode_frames(_p(np.ascontiguousarray(pkts, np.uint8)), _p(np.ascontiguousarray(off, np.uint64)),
+                                           _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(bgr), lb,
+                                           C.c_uint64(h * lb), _p(st), _p(um))
+        return (bgr, st, um) if undef else (bgr, st)
+
+    def amvlib_frame_coefs(self, pkt, w, h):
+        mbw, mbh = (w + 15) // 16, (h + 15) // 16
+        coef = np.zeros((mbw * mbh * 6, 64), np.int32)
+        lb = amvlib_line_bytes(w)
+        bgr = np.zeros((h, lb), np.uint8)
+        pk = np.ascontiguousarray(pkt, np.uint8)
+        st = self.lib.amvo_amvlib_decode_frame(_p(pk), len(pk), w, h, _p(bgr), lb, _p(coef))
+        return coef, bgr, st
+
+    def amvlib_audio_decode(self, chunks, off, size):
+        n = len(size)
+        ns = (np.maximum(np.asarray(size, np.int64) - 8, 0) + 3) // 4 * 8
+        poff = offsets_of(ns)
+        pcm = np.zeros(int(ns.sum()), np.int16)
+        st = np.zeros(n, np.int32)
+        ck = np.ascontiguousarray(chunks, np.uint8)
+        for i in range(n):
+            r = self.lib.amvo_amvlib_audio_decode_chunk(_p(ck[int(off[i]):]), int(size[i]), _p(pcm[int(poff[i]):]))
+            st[i] = 0 if r >= 0 else r
+        return pcm, poff, ns.astype(np.uint32), st
+
+
+class Oracle(_AmvlibOracleMixin):
     def __init__(self):
         self.lib = C.CDLL(build_oracle())
         L = self.lib
@@ -158,6 +213,41 @@ class Oracle:
         if r != n:
             raise RuntimeError("oracle adpcm encode failed: %d" % r)
         return out, ooff, osz.astype(np.uint32), step_out
+
+
+class AmvlibRef:
+    """The unmodified reference amvlib (C-AMVDecoder/amvlib), compiled in place by oracle/build_ref.sh."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(AMVLIB_REF_SO)
+
+    def __init__(self):
+        self.lib = C.CDLL(AMVLIB_REF_SO)
+
+    def video_decode(self, pkts, off, size, w, h):
+        n = len(size)
+        lb = self.lib.amvlibref_line_bytes(w)
+        bgr = np.zeros((n, h, lb), np.uint8)
+        ret = np.zeros(n, np.int32)
+        r = self.lib.amvlibref_video_decode(_p(np.ascontiguousarray(pkts, np.uint8)), _p(np.ascontiguousarray(off, np.uint64)),
+                                            _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(bgr), _p(ret))
+        if r != n:
+            raise RuntimeError("amvlib reference decode failed: %d" % r)
+        return bgr, ret
+
+    def audio_decode(self, chunks, off, size):
+        n = len(size)
+        ns = (np.maximum(np.asarray(size, np.int64) - 8, 0) + 3) // 4 * 8
+        poff = offsets_of(ns)
+        pcm = np.zeros(int(ns.sum()) + 16, np.int16)
+        nsamp = np.zeros(n, np.uint32)
+        ret = np.zeros(n, np.int32)
+        r = self.lib.amvlibref_audio_decode(_p(np.ascontiguousarray(chunks, np.uint8)), _p(np.ascontiguousarray(off, np.uint64)),
+                                            _p(np.ascontiguousarray(size, np.uint32)), n, _p(pcm), _p(poff), _p(nsamp), _p(ret))
+        if r != n:
+            raise RuntimeError("amvlib reference audio decode failed: %d" % r)
+        return pcm[: int(ns.sum())], poff, nsamp, ret
 
 
 class Ref:

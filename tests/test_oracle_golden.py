@@ -88,3 +88,35 @@ def test_error_statuses(oracle):
     bad = np.array([0, 0, 89, 0, 0, 0, 0, 0, 0x11], np.uint8)
     _, _, st = oracle.adpcm_decode(bad, np.array([0], np.uint64), np.array([9], np.uint32))
     assert st[0] < 0
+
+
+# ------------------------------------------------------------------ amvlib flavour
+GA = np.load(os.path.join(os.path.dirname(__file__), "golden", "amvlib_golden.npz"))
+AMVLIB_CASES = bytes(GA["video_cases"]).decode().split("\n")
+
+
+def test_amvlib_zigzag_typo(oracle):
+    z = oracle.amvlib_zigzag()                       # raster -> zigzag index (AmvJpeg.c:131-141)
+    assert z[3 * 8 + 4] == 37 and z[6 * 8 + 2] == 37 and 31 not in z.tolist()
+    std = np.zeros(64, np.uint8)
+    std[oracle.zigzag()] = np.arange(64)
+    assert (z != std).sum() == 1
+
+
+@pytest.mark.parametrize("case", AMVLIB_CASES)
+def test_amvlib_decode_matches_golden(oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    bgr, st, um = oracle.amvlib_decode_frames(GA[case + "/pk"], GA[case + "/off"], GA[case + "/sz"], w, h, undef=True)
+    assert (st == 0).all()
+    assert np.array_equal(bgr[um == 0], GA[case + "/bgr"][um == 0])
+    if kind == "sinus":
+        assert not um.any()
+
+
+def test_amvlib_fixture_head(oracle):
+    w, h, fps, n = GA["AMV1/dims"].tolist()
+    bgr, st = oracle.amvlib_decode_frames(GA["AMV1/pk"], GA["AMV1/off"], GA["AMV1/sz"], w, h)
+    assert (st == 0).all() and np.array_equal(bgr, GA["AMV1/bgr"])
+    pcm, _, ns, ast = oracle.amvlib_audio_decode(GA["AMV1/ak"], GA["AMV1/aoff"], GA["AMV1/asz"])
+    assert (ast == 0).all() and np.array_equal(ns, GA["AMV1/nsamp"]) and np.array_equal(pcm, GA["AMV1/pcm"])
