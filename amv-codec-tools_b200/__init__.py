@@ -32,7 +32,7 @@ EXPORTS = [
     "amv_create", "amv_destroy", "amv_set_stream", "amv_sync", "amv_strerror", "amv_last_error", "amv_version",
     "amv_launch_count", "amv_host_alloc", "amv_host_free", "amv_set_option", "amv_get_stat",
     "amv_qscale_from_quality", "amv_decode_frames", "amv_encode_frames", "amv_adpcm_dec_chunks",
-    "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams",
+    "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library(path=LIB_PATH):
     lib.amv_get_stat.restype = C.c_int64
     lib.amv_qscale_from_quality.argtypes = [i32, i32, i32]
     lib.amv_decode_frames.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, vp, i32]
+    lib.amv_decode_frames_bgr24.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, i32, u64, vp, i32]
     lib.amv_encode_frames.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, vp, vp, u64, u32, i32, vp, vp,
                                       vp, i32]
     lib.amv_adpcm_dec_chunks.argtypes = [vp, vp, u64, vp, vp, i32, vp, u64, vp, vp, i32]
@@ -100,6 +101,11 @@ def _ptr(a):
 
 def chroma_dims(w, h):
     return (w + 1) // 2, (h + 1) // 2
+
+
+def amvlib_line_bytes(w):
+    """bytes per bitmap row the reference amvlib uses: WIDTHBYTES(w*24) (amvlib/AmvJpeg.c:420,1526)"""
+    return (w * 24 + 31) // 32 * 4
 
 
 def offsets_of(sizes):
@@ -160,6 +166,10 @@ class AmvCuda:
         self._ck(self.lib.amv_decode_frames(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
                                             _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, _ptr(status), mem))
 
+    def decode_frames_bgr24_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, bgr, line_bytes, frame_stride, status, mem):
+        self._ck(self.lib.amv_decode_frames_bgr24(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
+                                                  _ptr(bgr), line_bytes, frame_stride, _ptr(status), mem))
+
     def encode_frames_raw(self, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, qscale, out, out_cap, pkt_cap, layout, out_off,
                           out_size, status, mem):
         self._ck(self.lib.amv_encode_frames(self.ctx, _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, n, w, h,
@@ -196,6 +206,19 @@ class AmvCuda:
         st = np.zeros(n, np.int32)
         self.decode_frames_raw(pkts, pkts.nbytes, pkt_off, pkt_size, n, w, h, y, u, v, w, cw, w * h, cw * ch, st, MEM_HOST)
         return y, u, v, st
+
+    def decode_frames_bgr24(self, pkts, pkt_off, pkt_size, w, h, line_bytes=None):
+        """amvlib flavour (AmvVideoDecode): numpy in / numpy out -> (bgr[n,h,line_bytes] bottom-up rows, status[n]);
+        line_bytes defaults to the reference's ((w*24+31)//32)*4"""
+        pkts = np.ascontiguousarray(pkts, np.uint8)
+        pkt_off = np.ascontiguousarray(pkt_off, np.uint64)
+        pkt_size = np.ascontiguousarray(pkt_size, np.uint32)
+        n = len(pkt_size)
+        lb = int(line_bytes or amvlib_line_bytes(w))
+        bgr = np.zeros((n, h, lb), np.uint8)
+        st = np.zeros(n, np.int32)
+        self.decode_frames_bgr24_raw(pkts, pkts.nbytes, pkt_off, pkt_size, n, w, h, bgr, lb, h * lb, st, MEM_HOST)
+        return bgr, st
 
     def encode_frames(self, y, u, v, qscale=None, pkt_cap=None, layout=LAYOUT_PACKED):
         """numpy planes [n,h,w] / [n,ch,cw] -> (packets, off[n], size[n], status[n])"""

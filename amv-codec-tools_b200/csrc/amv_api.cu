@@ -33,8 +33,8 @@ enum WsId {
 
 // optional per-kernel device timing (option "profile_events"): CUDA events recorded on the
 // context's stream right around the launch of each hot kernel
-enum KernelKind { KK_ENCODE, KK_IDCT, KK_UNSTUFF, KK_SYNC, KK_ADPCM_DEC, KK_ADPCM_ENC, KK_COMPACT, KK_TOKENS, KK_COUNT };
-static const char *const kKernelKindName[KK_COUNT] = { "encode", "idct", "unstuff", "sync", "adpcm_dec", "adpcm_enc", "compact", "tokens" };
+enum KernelKind { KK_ENCODE, KK_IDCT, KK_UNSTUFF, KK_SYNC, KK_ADPCM_DEC, KK_ADPCM_ENC, KK_COMPACT, KK_TOKENS, KK_IDCT_BGR, KK_COUNT };
+static const char *const kKernelKindName[KK_COUNT] = { "encode", "idct", "unstuff", "sync", "adpcm_dec", "adpcm_enc", "compact", "tokens", "idct_bgr" };
 struct EvPair { cudaEvent_t a, b; int kind; };
 
 struct amv_ctx {
@@ -131,11 +131,14 @@ int pick_log2p(const amv_ctx *ctx, int n) {
 }
 
 // ---------------------------------------------------------------------------------- device paths
-// payload_bytes: upper bound of the bytes of the n packets (pkts_bytes if unknown); sizes the scratch
-int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
-                  const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
-                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes) {
-    const Geom g = make_geom(w, h);
+// Front half shared by both decoder flavours: slot offsets, un-stuffing, (lane synchronisation,)
+// Huffman -> tokens.  payload_bytes: upper bound of the bytes of the n packets; sizes the scratch.
+struct DecodeFront {
+    uint64_t *slot_off; uint32_t *scan_len; uint32_t *tokens; uint32_t *blk_off; int32_t *st; int launches;
+};
+
+int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
+                 int n, const Geom &g, int32_t *status, uint64_t payload_bytes, bool amvlib, DecodeFront &F) {
     const int log2p = pick_log2p(ctx, n);
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
     uint32_t *rounds; uint32_t *tokens; uint32_t *blk_off;
@@ -156,15 +159,39 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     if (log2p) {
         CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
         { ScopedTimer tm(ctx, KK_SYNC);
-          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, ctx->stream); }
+          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, ctx->stream); }
         lc++;
     }
     { ScopedTimer tm(ctx, KK_TOKENS);
-      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, ctx->stream); }
+      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, ctx->stream); }
+    lc++;
+    F.slot_off = slot_off; F.scan_len = scan_len; F.tokens = tokens; F.blk_off = blk_off; F.st = st; F.launches = lc;
+    return AMV_OK;
+}
+
+int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                  const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
+                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes) {
+    const Geom g = make_geom(w, h);
+    DecodeFront F;
+    int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F);
+    if (r != AMV_OK) return r;
     { ScopedTimer tm(ctx, KK_IDCT);
-      launch_idct(tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
-    lc += 2;
-    return check_launch(ctx, "decode kernels", lc);
+      launch_idct(F.tokens, F.blk_off, F.slot_off, F.scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
+    return check_launch(ctx, "decode kernels", F.launches + 1);
+}
+
+// amvlib flavour: same front half with amvlib's quantisers / DC chain / zigzag, then Chen-Wang IDCT + BGR24
+int decode_bgr_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                      const uint32_t *pkt_size, int n, int w, int h, uint8_t *bgr, int line_bytes, uint64_t frame_stride,
+                      int32_t *status, uint64_t payload_bytes) {
+    const Geom g = make_geom(w, h);
+    DecodeFront F;
+    int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, true, F);
+    if (r != AMV_OK) return r;
+    { ScopedTimer tm(ctx, KK_IDCT_BGR);
+      launch_idct_bgr(F.tokens, F.blk_off, F.slot_off, F.scan_len, n, g, bgr, line_bytes, frame_stride, ctx->stream); }
+    return check_launch(ctx, "amvlib decode kernels", F.launches + 1);
 }
 
 bool encode_geometry_ok(int w, int h) {
@@ -642,6 +669,36 @@ AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_b
         return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes);
 
     return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status);
+}
+
+// -------------------------------------------------------------------------- decode, amvlib flavour
+AMV_API int amv_decode_frames_bgr24(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                                    const uint32_t *pkt_size, int n, int w, int h, uint8_t *bgr, int line_bytes,
+                                    uint64_t frame_stride, int32_t *status, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
+    if (n == 0) return AMV_OK;
+    if (!pkts || !pkt_off || !pkt_size || !bgr) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    if (line_bytes < 3 * w || frame_stride < (uint64_t)line_bytes * (h - 1) + 3 * (uint64_t)w)
+        return fail(ctx, AMV_ERR_ARG, "strides smaller than the bitmap");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE)
+        return decode_bgr_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, bgr, line_bytes, frame_stride, status, pkts_bytes);
+    // host buffers: staged copy in, kernels, copy out (bytes of the bitmaps that no pixel covers -- row
+    // padding -- are copied back as they came in, like the reference leaves them untouched)
+    uint8_t *d_pk, *d_bgr; uint64_t *d_off; uint32_t *d_sz; int32_t *d_st;
+    const uint64_t bgr_bytes = frame_stride * (uint64_t)(n - 1) + (uint64_t)line_bytes * (h - 1) + 3 * (uint64_t)w;
+    TO_DEVICE(WS_H_A, pkts, pkts_bytes, d_pk);
+    TO_DEVICE(WS_H_B, pkt_off, sizeof(uint64_t) * n, d_off);
+    TO_DEVICE(WS_H_C, pkt_size, sizeof(uint32_t) * n, d_sz);
+    TO_DEVICE(WS_H_D, bgr, bgr_bytes, d_bgr);
+    ENSURE(WS_H_E, sizeof(int32_t) * n, d_st);
+    int r = decode_bgr_device(ctx, d_pk, pkts_bytes, d_off, d_sz, n, w, h, d_bgr, line_bytes, frame_stride, d_st, pkts_bytes);
+    if (r != AMV_OK) return r;
+    CK(cudaMemcpyAsync(bgr, d_bgr, bgr_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
 }
 
 // ---------------------------------------------------------------------------------------- encode

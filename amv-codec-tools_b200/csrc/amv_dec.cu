@@ -269,7 +269,11 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
 struct DecTablesDev {
     VlcTables vlc;
     DequantTables dq;
+    AmvlibDequantTables adq;
 };
+// which reference decoder the arithmetic follows: the ffmpeg fork's (sp5xdec/mjpegdec/simple_idct)
+// or amvlib's (AmvJpeg.c) -- same bitstream, different quantisers, DC chain, zigzag and IDCT
+enum { kFlavorFfmpeg = 0, kFlavorAmvlib = 1 };
 __device__ DecTablesDev g_dec_tables;
 
 struct VlcSmem {
@@ -317,7 +321,7 @@ constexpr int kVlcThreads = 128;
 __global__ void __launch_bounds__(kVlcThreads)
 k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
            const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
-           uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */) {
+           uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */, int flavor) {
     __shared__ VlcSmem T;
     load_vlc_tables(T);
     const int P = 1 << log2p;
@@ -370,9 +374,13 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
         s.bitpos = start_bit;
         s.first_block = nb_inc - ex.nblocks;
         s.nblocks = ex.nblocks;
-        s.pred[0] = 1024 + T.q0[0] * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
-        s.pred[1] = 1024 + T.q0[1] * (d1 - ex.dc[1]);
-        s.pred[2] = 1024 + T.q0[1] * (d2 - ex.dc[2]);
+        if (flavor == kFlavorAmvlib) {                         // quantised units, 16-bit chain from 0 (AmvJpeg.c:1194-1196)
+            s.pred[0] = sext16(d0 - ex.dc[0]); s.pred[1] = sext16(d1 - ex.dc[1]); s.pred[2] = sext16(d2 - ex.dc[2]);
+        } else {
+            s.pred[0] = 1024 + T.q0[0] * (d0 - ex.dc[0]);      // last_dc starts at 1024 (mjpegdec.c:805-806)
+            s.pred[1] = 1024 + T.q0[1] * (d1 - ex.dc[1]);
+            s.pred[2] = 1024 + T.q0[1] * (d2 - ex.dc[2]);
+        }
         starts[gt] = s;
     }
     if (rounds_out && lane == 0) atomicMax(rounds_out, rounds);
@@ -410,6 +418,7 @@ struct TokSmem {
     uint32_t tstage[kTokThreads / 32][4 * 32];      // [slot][lane]: four tokens per lane waiting for their 16-byte store
 };
 
+template <int FLAVOR>
 __global__ void __launch_bounds__(kTokThreads)
 k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
@@ -417,7 +426,8 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
              uint32_t *__restrict__ blk_off, int32_t *__restrict__ status) {
     __shared__ TokSmem S;
     for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) S.lut[i] = g_fast_vlc.e[i];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&S.tz[0][0])[i] = (&g_dec_tables.dq.tz[0][0])[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x)
+        (&S.tz[0][0])[i] = FLAVOR == kFlavorAmvlib ? (&g_dec_tables.adq.tz[0][0])[i] : (&g_dec_tables.dq.tz[0][0])[i];
     __syncthreads();
     const int P = 1 << log2p;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -430,11 +440,13 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: + c*128
     const uint32_t dc_base[2] = { (uint32_t)g_fast_vlc.base[0], (uint32_t)g_fast_vlc.base[1] };
     const uint32_t ac_base[2] = { (uint32_t)g_fast_vlc.base[2], (uint32_t)g_fast_vlc.base[3] };
-    const int q0l = (int)(g_dec_tables.dq.zq[0][0] >> 8), q0c = (int)(g_dec_tables.dq.zq[1][0] >> 8);
+    const int q0l = FLAVOR == kFlavorAmvlib ? (int)(g_dec_tables.adq.tz[0][0] & 0xff) : (int)(g_dec_tables.dq.zq[0][0] >> 8);
+    const int q0c = FLAVOR == kFlavorAmvlib ? (int)(g_dec_tables.adq.tz[1][0] & 0xff) : (int)(g_dec_tables.dq.zq[1][0] >> 8);
+    constexpr int kPred0 = FLAVOR == kFlavorAmvlib ? 0 : 1024;   // last_dc (mjpegdec.c:805-806) / ycoef.. (AmvJpeg.c:1510)
 
     // ---- lane set-up (inactive lanes keep count = 0 and fall through the loops)
     uint32_t count = 0, first = 0, bit = 0, U = 0, st = 0;
-    int pred0 = 1024, pred1 = 1024, pred2 = 1024;       // last_dc per component (mjpegdec.c:805-806)
+    int pred0 = kPred0, pred1 = kPred0, pred2 = kPred0;
     const uint32_t *words = nullptr;
     uint32_t cap_words = 0;
     uint64_t so = 0;
@@ -550,10 +562,19 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             const int diff = (int)((__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg);
             bp += total;
             int pr;
-            if (b < 4) pr = (pred0 += diff * q0l);
-            else if (b == 4) pr = (pred1 += diff * q0c);
-            else pr = (pred2 += diff * q0c);
-            push((uint32_t)pr & 0xffffu);                                      // block[0] = (int16) val (mjpegdec.c:387-389)
+            if (FLAVOR == kFlavorAmvlib) {
+                // the chain runs in quantised units in a 16-bit variable (AmvJpeg.c:1194-1196); the product
+                // with the quantiser is a full int (IQtIZzBlock :1041-1046); raster position 0
+                if (b < 4) pr = (pred0 = sext16(pred0 + diff)) * q0l;
+                else if (b == 4) pr = (pred1 = sext16(pred1 + diff)) * q0c;
+                else pr = (pred2 = sext16(pred2 + diff)) * q0c;
+                push((uint32_t)pr & 0x03ffffffu);
+            } else {
+                if (b < 4) pr = (pred0 += diff * q0l);
+                else if (b == 4) pr = (pred1 += diff * q0c);
+                else pr = (pred2 += diff * q0c);
+                push((uint32_t)pr & 0xffffu);                                  // block[0] = (int16) val (mjpegdec.c:387-389)
+            }
         }
         // ---- AC (decode_block, mjpegdec.c:391-428)
         int k = 0;
@@ -580,8 +601,17 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             k += (int)run + 1;
             if (k > 63) { st |= AMV_ST_COEFIDX; break; }                      // "error count" (mjpegdec.c:423-424)
             const uint32_t z = lds32(tzq_s + (uint32_t)k * 4);
-            push((z & 0xffff0000u) | ((uint32_t)(lvl * (int)(z & 0xffffu)) & 0xffffu));   // level * quant_matrix[j] as int16 (:420,428)
-            nac++;
+            if (FLAVOR == kFlavorAmvlib) {
+                const uint32_t val = (uint32_t)(lvl * (int)(z & 0xffu)) & 0x03ffffffu;
+                if (!(z & kAmvlibTokSkip)) {
+                    push((z & 0xfc000000u) | val);
+                    nac++;
+                    if (z & kAmvlibTokDup) { push(((z << 16) & 0xfc000000u) | val); nac++; }
+                }
+            } else {
+                push((z & 0xffff0000u) | ((uint32_t)(lvl * (int)(z & 0xffffu)) & 0xffffu));   // level * quant_matrix[j] as int16 (:420,428)
+                nac++;
+            }
             if (k == 63) break;
         }
         boff[i] = (nac << kTokCountShift) | blk_start;
@@ -673,7 +703,7 @@ cudaError_t upload_dec_tables(cudaStream_t s) {
     static DecTablesDev h;      // built once; identical for every context
     static bool built = false;
     static FastVlcTables hf;
-    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); build_fast_vlc_tables(hf); built = true; }
+    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); build_amvlib_dequant_tables(h.adq); build_fast_vlc_tables(hf); built = true; }
     cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_vlc, &hf, sizeof(hf), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbolAsync(g_dec_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
@@ -696,19 +726,24 @@ void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pk
 }
 
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
-                     LaneStart *starts, uint32_t *rounds_out, cudaStream_t s) {
+                     LaneStart *starts, uint32_t *rounds_out, bool amvlib, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
-    k_vlc_sync<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out);
+    k_vlc_sync<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
+                                            amvlib ? kFlavorAmvlib : kFlavorFfmpeg);
 }
 
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, cudaStream_t s) {
+                       int32_t *status, bool amvlib, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
-    k_vlc_tokens<<<grid, kTokThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk, tokens, blk_off,
-                                              status);
+    if (amvlib)
+        k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+                                                                 tokens, blk_off, status);
+    else
+        k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+                                                                 tokens, blk_off, status);
 }
 
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,

@@ -22,13 +22,17 @@ void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pk
                     uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
                     int32_t *status, cudaStream_t s);
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
-                     LaneStart *starts, uint32_t *rounds_out, cudaStream_t s);
+                     LaneStart *starts, uint32_t *rounds_out, bool amvlib, cudaStream_t s);
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, cudaStream_t s);
+                       int32_t *status, bool amvlib, cudaStream_t s);
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
                  const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                  cudaStream_t s);
+
+// amvlib flavour (C-AMVDecoder/amvlib/AmvJpeg.c): Chen-Wang IDCT + fixed-point YUV->BGR24, bottom-up rows
+void launch_idct_bgr(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len,
+                     int n, const Geom &g, uint8_t *bgr, int line_bytes, uint64_t frame_stride, cudaStream_t s);
 
 // ---- encode
 cudaError_t upload_enc_tables(cudaStream_t s);

@@ -48,6 +48,18 @@ static const uint8_t kDecQuant[2][64] = {
     79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79,
     79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79, 79 } };
 
+// amvlib's decoder quantisers, zigzag order: amv_luminance_quant_tbl / amv_chrominance_quant_tbl
+// (C-AMVDecoder/amvlib/AmvJpeg.c:30-39,52-61)
+static const uint8_t kAmvlibQuant[2][64] = {
+  {  8,  6,  6,  7,  6,  5,  8,  7,  7,  7,  9,  9,  8, 10, 12, 20,
+    13, 12, 11, 11, 12, 25, 18, 19, 15, 20, 29, 26, 31, 30, 29, 26,
+    28, 28, 32, 36, 46, 39, 32, 34, 44, 39, 28, 28, 40, 55, 41, 44,
+    48, 49, 52, 52, 52, 31, 39, 57, 61, 56, 50, 60, 46, 51, 52, 50 },
+  {  9,  9,  9, 12, 11, 12, 24, 13, 13, 24, 50, 33, 28, 33, 50, 50,
+    50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50,
+    50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50,
+    50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50, 50 } };
+
 // Encoder matrix base, raster order: ff_mpeg1_default_intra_matrix (mpeg12data.c:30-39)
 static const uint8_t kEncIntraBase[64] = {
      8, 16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37,
@@ -143,6 +155,16 @@ struct FastVlcTables {
 // tz: the same for the token producer: (column byte offset << 16) | quantiser
 struct DequantTables { uint32_t zq[2][64]; uint32_t tz[2][64]; };
 
+// amvlib flavour of the token producer's table.  amvlib's raster->zigzag table has a
+// typo (AmvJpeg.c:131-141: raster (3,4) reads index 37 instead of 31), so zigzag coefficient 31 is
+// never used and coefficient 37 lands at two raster positions.  Entry per zigzag position k:
+//   [7:0] quantiser   bit 8 = coefficient is dropped   bit 9 = second position valid
+//   [15:10] second raster position   [31:26] first raster position
+// amvlib tokens: [31:26] raster position, [25:0] coefficient * quantiser (two's complement, 26 bits:
+// the product of a 16-bit level and an 8-bit quantiser always fits).
+struct AmvlibDequantTables { uint32_t tz[2][64]; };
+constexpr uint32_t kAmvlibTokSkip = 1u << 8, kAmvlibTokDup = 1u << 9;
+
 // Encoder: symbol -> (code << 5 | length).  Index: DC-luma 0..15, DC-chroma 16..31,
 // AC-luma 32..287, AC-chroma 288..543.
 constexpr int kEncDcLuma = 0, kEncDcChroma = 16, kEncAcLuma = 32, kEncAcChroma = 288, kEncHuffEntries = 544;
@@ -234,6 +256,16 @@ inline void build_dequant_tables(DequantTables &D) {
             const uint32_t j = kZigzag[k];
             D.zq[c][k] = j | ((uint32_t)kDecQuant[c][k] << 8);
             D.tz[c][k] = (((j >> 1) * 128u + (j & 1u) * 2u) << 16) | (uint32_t)kDecQuant[c][k];
+        }
+}
+
+inline void build_amvlib_dequant_tables(AmvlibDequantTables &D) {
+    for (int c = 0; c < 2; c++)
+        for (int k = 0; k < 64; k++) {
+            uint32_t e = (uint32_t)kAmvlibQuant[c][k] | ((uint32_t)kZigzag[k] << 26);
+            if (k == 31) e |= kAmvlibTokSkip;                                // no raster position reads index 31
+            if (k == 37) e |= kAmvlibTokDup | ((uint32_t)(3 * 8 + 4) << 10);  // (3,4) reads 37 as well
+            D.tz[c][k] = e;
         }
 }
 

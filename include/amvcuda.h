@@ -108,7 +108,7 @@ AMV_API void        amv_host_free(void *p);
  *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose) */
 AMV_API int         amv_set_option(amv_ctx *ctx, const char *key, int64_t value);
 /* "decode_sync_rounds": rounds the last multi-lane decode needed to self-synchronise (max over warps)
- * "<k>_kernel_launches", then "<k>_kernel_ns" (k = encode|decode|unstuff|sync|compact|adpcm_dec|adpcm_enc):
+ * "<k>_kernel_launches", then "<k>_kernel_ns" (k = encode|idct|idct_bgr|tokens|unstuff|sync|compact|adpcm_dec|adpcm_enc):
  * launches and summed device time of that kernel since the last "_ns" query (needs profile_events) */
 AMV_API int64_t     amv_get_stat(amv_ctx *ctx, const char *key);
 
@@ -134,6 +134,24 @@ AMV_API int amv_decode_frames(amv_ctx *ctx,
                               uint8_t *y, uint8_t *u, uint8_t *v,
                               int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                               int32_t *status, int mem);
+
+/*
+ * amvlib flavour of the video decoder: what C-AMVDecoder/amvlib computes for the same packets --
+ * replaces AmvVideoDecode (amvlib/AMVDec.c:259-286) -> AmvJpegDecode (amvlib/AmvJpeg.c:1515-1539).
+ * amvlib is NOT bit-identical to the ffmpeg fork (own quantiser tables AmvJpeg.c:30-61, a zigzag
+ * table with a typo :131-141, Chen-Wang IDCT :1078-1175, DC chain from 0 :1177-1242), so it has its
+ * own kernels behind this call.  Output: one bottom-up BGR24 bitmap per frame (picture row y at
+ * bgr + i*frame_stride + (h-1-y)*line_bytes, 3 bytes B,G,R per pixel, StoreBuffer :789-840); the
+ * reference uses line_bytes = ((w*24+31)/32)*4.  Bytes no pixel covers are left untouched.
+ * Defined domain: FF bytes of the scan are followed by 00, IDCT results inside amvlib's clamp
+ * table (-512..511; outside it the reference reads foreign memory and this call saturates).
+ */
+AMV_API int amv_decode_frames_bgr24(amv_ctx *ctx,
+                                    const uint8_t *pkts, uint64_t pkts_bytes,
+                                    const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                                    int w, int h,
+                                    uint8_t *bgr, int line_bytes, uint64_t frame_stride,
+                                    int32_t *status, int mem);
 
 /*
  * Encode n YUVJ420P frames into AMV packets, byte-identical to amv_encoder.

@@ -375,3 +375,91 @@ def test_host_path_pinned_zero_copy_and_chunked(ctx, oracle):
         assert np.array_equal(qy, wy) and np.array_equal(qu, wu) and np.array_equal(qv, wv)
     finally:
         ctx.set_option("host_chunk_frames", 0)
+
+
+# ------------------------------------------------------------------ amvlib flavour
+GA = np.load(os.path.join(os.path.dirname(__file__), "golden", "amvlib_golden.npz"))
+AMVLIB_CASES = bytes(GA["video_cases"]).decode().split("\n")
+
+
+@pytest.mark.parametrize("log2p", [0, 1, 3, 5])
+@pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (320, 240, "sinus"), (208, 176, "noise"), (128, 96, "edges"),
+                                      (48, 40, "flat"), (16, 16, "sinus"), (72, 24, "noise"), (102, 56, "sinus")])
+def test_amvlib_decode_identical(ctx, oracle, w, h, kind, log2p):
+    """amv_decode_frames_bgr24 (AmvVideoDecode mirror) vs the amvlib oracle: every byte of the bottom-up BGR24
+    bitmaps, all lane counts, partial macroblocks, widths whose rows are padded (102*3 = 306 -> 308 bytes)"""
+    n = 5 if w * h > 40000 else 11
+    y, u, v = synth_frames(n, w, h, seed=71, kind=kind)
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 2 if kind == "sinus" else 7)
+    ctx.set_option("decode_log2_lanes", log2p)
+    try:
+        bgr, st = ctx.decode_frames_bgr24(pk, off, sz, w, h)
+    finally:
+        ctx.set_option("decode_log2_lanes", -1)
+    want, wst, um = oracle.amvlib_decode_frames(pk, off, sz, w, h, undef=True)
+    assert (st == 0).all() and (wst == 0).all()
+    # outside amvlib's clamp table the reference reads foreign memory; both sides saturate there, so the
+    # comparison holds on every byte (the mask only says where the REFERENCE is undefined)
+    assert np.array_equal(bgr, want)
+    if kind == "sinus":
+        assert not um.any()
+
+
+@pytest.mark.parametrize("case", AMVLIB_CASES)
+def test_amvlib_decode_golden(ctx, oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    bgr, st = ctx.decode_frames_bgr24(GA[case + "/pk"], GA[case + "/off"], GA[case + "/sz"], w, h)
+    assert (st == 0).all()
+    _, _, um = oracle.amvlib_decode_frames(GA[case + "/pk"], GA[case + "/off"], GA[case + "/sz"], w, h, undef=True)
+    assert np.array_equal(bgr[um == 0], GA[case + "/bgr"][um == 0])
+
+
+def test_amvlib_fixture_head_and_audio(ctx):
+    """First packets / chunks of the reference's AMV1.amv through the AmvVideoDecode / AmvAudioDecode mirrors.
+    amvlib's audio is the ffmpeg decode of the chunk (one-byte step index) followed by the samples of its
+    4-byte group padding: the chunk is handed over zero-padded to a multiple of four data bytes."""
+    w, h, fps, n = GA["AMV1/dims"].tolist()
+    bgr, st = ctx.decode_frames_bgr24(GA["AMV1/pk"], GA["AMV1/off"], GA["AMV1/sz"], w, h)
+    assert (st == 0).all() and np.array_equal(bgr, GA["AMV1/bgr"])
+    ak, aoff, asz = GA["AMV1/ak"], GA["AMV1/aoff"], GA["AMV1/asz"]
+    padded = []
+    for o, s in zip(aoff, asz):
+        c = bytearray(ak[int(o):int(o) + int(s)].tobytes())
+        c[3] = 0
+        c += bytes((-(int(s) - 8)) % 4)
+        padded.append(bytes(c))
+    pk, po, ps = pack(padded)
+    pcm, _, ast = ctx.adpcm_decode(pk, po, ps)
+    assert (ast == 0).all() and np.array_equal(pcm, GA["AMV1/pcm"])
+
+
+def test_amvlib_device_buffers_strides_and_corrupt(ctx, oracle):
+    import torch
+    w, h, n = 208, 176, 33
+    y, u, v = synth_frames(n, w, h, seed=72, kind="sinus")
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 3)
+    lb, fs = 3 * w + 40, (3 * w + 40) * h + 128            # padded rows and frames; padding must stay untouched
+    dev = torch.device("cuda", 0)
+    d_pk = torch.from_numpy(pk).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_sz = torch.from_numpy(sz.astype(np.int32)).to(dev)
+    d_bgr = torch.full((n * fs,), 0xA5, dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    ctx.decode_frames_bgr24_raw(d_pk, d_pk.numel(), d_off, d_sz, n, w, h, d_bgr, lb, fs, d_st, amv.MEM_DEVICE)
+    ctx.sync()
+    got = d_bgr.cpu().numpy().reshape(n, fs)
+    want, wst = oracle.amvlib_decode_frames(pk, off, sz, w, h, line_bytes=lb)
+    assert int(d_st.abs().sum()) == 0
+    img = got[:, : lb * h].reshape(n, h, lb)
+    assert np.array_equal(img[:, :, : 3 * w], want[:, :, : 3 * w])
+    assert (img[:, :, 3 * w:] == 0xA5).all() and (got[:, lb * h:] == 0xA5).all()
+    # corrupt packets are flagged, never fatal
+    bad = pk.copy()
+    bad[int(off[3]) + 40: int(off[3]) + 60] = 0xFF
+    cut_sz = sz.copy()
+    cut_sz[5] = 30
+    bgr, st = ctx.decode_frames_bgr24(bad, off, cut_sz, w, h)
+    assert st[3] != 0 and st[5] != 0 and (np.delete(st, [3, 5]) == 0).all()
+    ok = [i for i in range(n) if i not in (3, 5)]
+    assert np.array_equal(bgr[ok][:, :, : 3 * w], want[ok][:, :, : 3 * w])
