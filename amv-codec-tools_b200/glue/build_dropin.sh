@@ -19,3 +19,17 @@ OBJS=$(ls "$OBJ"/avc_*.o "$OBJ"/avu_*.o)
 gcc -o "$HERE/_build/dropin_check" "$HERE/_build/dropin_check.o" "$HERE/_build/amvcuda_codecs.o" $OBJS \
     -L"$HERE/../lib" -lamvcuda -Wl,-rpath,'$ORIGIN/../../lib' -lm
 echo "built $HERE/_build/dropin_check"
+
+# ---- amvlib binding: glue/amvlib/amvcuda_amvlib.c against amvlib's own header, checked next to the
+# reference's unmodified AmvVideoDecode / AmvAudioDecode (objects from oracle/build_ref.sh)
+AMVLIB="${AMV_REFERENCE_ROOT:-/root/reference}/C-AMVDecoder/amvlib"
+SH="$ROOT/oracle/_ref/cfg/amvlib_shim"
+if [ -d "$AMVLIB" ] && [ -f "$OBJ/amvlib_AMVDec.o" ]; then
+  ACF="-O2 -std=gnu99 -fcommon -w -DAMVLIB_LONG32 -I$AMVLIB -I$ROOT/include"
+  gcc $ACF -c "$HERE/amvlib/amvcuda_amvlib.c" -o "$HERE/_build/amvcuda_amvlib.o"
+  gcc $ACF -c "$HERE/amvlib/amvlib_dropin_check.c" -o "$HERE/_build/amvlib_dropin_check.o"
+  gcc -o "$HERE/_build/amvlib_dropin_check" "$HERE/_build/amvlib_dropin_check.o" "$HERE/_build/amvcuda_amvlib.o" \
+      "$OBJ/amvlib_AMVDec.o" "$OBJ/amvlib_AmvJpeg.o" "$OBJ/amvlib_AdpcmIma.o" \
+      -L"$HERE/../lib" -lamvcuda -Wl,-rpath,'$ORIGIN/../../lib' -lm
+  echo "built $HERE/_build/amvlib_dropin_check"
+fi

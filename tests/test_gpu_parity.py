@@ -463,3 +463,35 @@ def test_amvlib_device_buffers_strides_and_corrupt(ctx, oracle):
     assert st[3] != 0 and st[5] != 0 and (np.delete(st, [3, 5]) == 0).all()
     ok = [i for i in range(n) if i not in (3, 5)]
     assert np.array_equal(bgr[ok][:, :, : 3 * w], want[ok][:, :, : 3 * w])
+
+
+AMVLIB_DROPIN = os.path.join(amv.PKG_DIR, "glue", "_build", "amvlib_dropin_check")
+
+
+@pytest.mark.skipif(not os.path.exists(AMVLIB_DROPIN), reason="glue/_build/amvlib_dropin_check not built (needs the reference tree)")
+def test_amvlib_dropin_matches_reference_amvlib(oracle, tmp_path):
+    """The reference's own AmvVideoDecode / AmvAudioDecode (unmodified amvlib objects) next to the libamvcuda
+    bindings of the same two entry points (glue/amvlib/amvcuda_amvlib.c), driven through an AMVDecoder like
+    amvlib's callers do: identical bitmaps, PCM, lengths and return codes (glue/amvlib/amvlib_dropin_check.c)."""
+    import struct
+    import subprocess
+    w, h, fps, n = GA["AMV1/dims"].tolist()
+    units = [(w, h, [GA["AMV1/pk"][int(o):int(o) + int(s)].tobytes() for o, s in zip(GA["AMV1/off"], GA["AMV1/sz"])],
+              [GA["AMV1/ak"][int(o):int(o) + int(s)].tobytes() for o, s in zip(GA["AMV1/aoff"], GA["AMV1/asz"])])]
+    for (ww, hh) in ((160, 120), (320, 240), (208, 176)):
+        y, u, v = synth_frames(6, ww, hh, seed=81, kind="sinus")
+        pk, off, sz = oracle.encode_frames(y, u, v, ww, hh, 2)
+        pcm = synth_pcm(1378 * 4, seed=82)
+        ck, coff, csz, _ = oracle.adpcm_encode(pcm, np.arange(4, dtype=np.uint64) * 1378, np.full(4, 1378, np.uint32),
+                                               np.zeros(4, np.int16))
+        units.append((ww, hh, [pk[int(o):int(o) + int(s)].tobytes() for o, s in zip(off, sz)],
+                      [ck[int(o):int(o) + int(s)].tobytes() for o, s in zip(coff, csz)]))
+    for i, (ww, hh, vids, auds) in enumerate(units):
+        path = tmp_path / ("units%d.bin" % i)
+        with open(path, "wb") as f:
+            f.write(b"AMVP" + struct.pack("<4i", ww, hh, len(vids), len(auds)))
+            for b in vids + auds:
+                f.write(struct.pack("<I", len(b)) + b)
+        out = subprocess.run([AMVLIB_DROPIN, str(path)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "AMVLIB DROP-IN CHECK OK" in out.stdout
