@@ -33,6 +33,7 @@ EXPORTS = [
     "amv_launch_count", "amv_host_alloc", "amv_host_free", "amv_set_option", "amv_get_stat",
     "amv_qscale_from_quality", "amv_decode_frames", "amv_encode_frames", "amv_adpcm_dec_chunks",
     "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
+    "amv_file_index", "amv_file_mux",
 ]
 
 
@@ -48,6 +49,20 @@ def build(verbose=False):
     if verbose:
         print(out.stdout)
     return LIB_PATH
+
+
+class FileInfo(C.Structure):
+    """amv_file_info of include/amvcuda.h"""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps", C.c_int), ("sample_rate", C.c_int), ("channels", C.c_int),
+                ("us_per_frame", C.c_uint32), ("nb_frames_header", C.c_uint32), ("duration_s", C.c_uint32),
+                ("nvideo", C.c_uint32), ("naudio", C.c_uint32), ("movi_offset", C.c_uint64),
+                ("has_end_marker", C.c_int), ("truncated", C.c_int)]
+
+
+class MuxParams(C.Structure):
+    """amv_mux_params of include/amvcuda.h"""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("tb_num", C.c_int), ("tb_den", C.c_int), ("sample_rate", C.c_int),
+                ("video_bit_rate", C.c_int), ("audio_bit_rate", C.c_int)]
 
 
 class _Params(C.Structure):
@@ -80,6 +95,9 @@ def load_library(path=LIB_PATH):
     lib.amv_qscale_from_quality.argtypes = [i32, i32, i32]
     lib.amv_decode_frames.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, vp, i32]
     lib.amv_decode_frames_bgr24.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, i32, u64, vp, i32]
+    lib.amv_file_index.argtypes = [vp, u64, C.POINTER(FileInfo), vp, vp, vp, vp, u32]
+    lib.amv_file_mux.argtypes = [C.POINTER(MuxParams), i32, vp, vp, vp, vp, vp, vp, vp, u64]
+    lib.amv_file_mux.restype = C.c_int64
     lib.amv_encode_frames.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, vp, vp, u64, u32, i32, vp, vp,
                                       vp, i32]
     lib.amv_adpcm_dec_chunks.argtypes = [vp, vp, u64, vp, vp, i32, vp, u64, vp, vp, i32]
@@ -114,6 +132,44 @@ def offsets_of(sizes):
     if len(sizes) > 1:
         off[1:] = np.cumsum(sizes)[:-1]
     return off
+
+
+def file_index(data, lib=None):
+    """Index an AMV file held in memory (bytes / numpy uint8).  Host-only, needs no device.
+    -> (FileInfo, v_off, v_size, a_off, a_size): offsets point into `data`."""
+    lib = lib or load_library()
+    buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+    info = FileInfo()
+    r = lib.amv_file_index(buf.ctypes.data, buf.nbytes, C.byref(info), None, None, None, None, 0)
+    if r != 0:
+        raise AmvError("amv_file_index: not an AMV file (%d)" % r)
+    cap = max(info.nvideo, info.naudio, 1)
+    v_off, a_off = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+    v_size, a_size = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    lib.amv_file_index(buf.ctypes.data, buf.nbytes, C.byref(info), v_off.ctypes.data, v_size.ctypes.data, a_off.ctypes.data,
+                       a_size.ctypes.data, cap)
+    return info, v_off[: info.nvideo], v_size[: info.nvideo], a_off[: info.naudio], a_size[: info.naudio]
+
+
+def file_mux(width, height, fps, sample_rate, vpk, v_off, v_size, apk, a_off, a_size, video_bit_rate=0, audio_bit_rate=0,
+             lib=None):
+    """Write an AMV file (bytes) from n video packets and n audio chunks.  Host-only."""
+    lib = lib or load_library()
+    n = len(v_size)
+    assert len(a_size) == n
+    mp = MuxParams(width, height, 1, fps, sample_rate, video_bit_rate, audio_bit_rate)
+    vpk, apk = np.ascontiguousarray(vpk, np.uint8), np.ascontiguousarray(apk, np.uint8)
+    v_off, a_off = np.ascontiguousarray(v_off, np.uint64), np.ascontiguousarray(a_off, np.uint64)
+    v_size, a_size = np.ascontiguousarray(v_size, np.uint32), np.ascontiguousarray(a_size, np.uint32)
+    args = (vpk.ctypes.data, v_off.ctypes.data, v_size.ctypes.data, apk.ctypes.data, a_off.ctypes.data, a_size.ctypes.data)
+    need = -lib.amv_file_mux(C.byref(mp), n, *args, None, 0)
+    if need <= 0:
+        raise AmvError("amv_file_mux: bad arguments (%d)" % -need)
+    out = np.zeros(need, np.uint8)
+    got = lib.amv_file_mux(C.byref(mp), n, *args, out.ctypes.data, out.nbytes)
+    if got != need:
+        raise AmvError("amv_file_mux failed (%d)" % got)
+    return out.tobytes()
 
 
 class AmvCuda:

@@ -23,19 +23,36 @@ AMV_HD int clamp_u8(int v) {
 // W4 = 16383 (:50), row shift 11, column shift 20, column bias W4*32.
 struct IdctC { enum { W1 = 22725, W2 = 21407, W3 = 19266, W4 = 16383, W5 = 12873, W6 = 8867, W7 = 4520 }; };
 
-// 1-D butterfly shared by both passes: e0 is the pre-biased DC term.
+// 1-D butterfly shared by both passes: e0 is the pre-biased DC term.  Every product is taken with
+// K * W: the sums are linear mod 2^32, so the outputs are K times the reference's sums (mod 2^32).
+template <int K>
 AMV_HD void idct_1d(int e0, int x1, int x2, int x3, int x4, int x5, int x6, int x7, int (&s)[4], int (&d)[4]) {
-    const int t4 = IdctC::W4 * x4;
+    constexpr int W1 = IdctC::W1 * K, W2 = IdctC::W2 * K, W3 = IdctC::W3 * K, W4 = IdctC::W4 * K, W5 = IdctC::W5 * K,
+                  W6 = IdctC::W6 * K, W7 = IdctC::W7 * K;
+    const int t4 = W4 * x4;
     const int ea = e0 + t4, eb = e0 - t4;
-    const int g0 = IdctC::W2 * x2 + IdctC::W6 * x6;
-    const int g1 = IdctC::W6 * x2 - IdctC::W2 * x6;
+    const int g0 = W2 * x2 + W6 * x6;
+    const int g1 = W6 * x2 - W2 * x6;
     const int a0 = ea + g0, a1 = eb + g1, a2 = eb - g1, a3 = ea - g0;
-    const int b0 = IdctC::W1 * x1 + IdctC::W3 * x3 + IdctC::W5 * x5 + IdctC::W7 * x7;
-    const int b1 = IdctC::W3 * x1 - IdctC::W7 * x3 - IdctC::W1 * x5 - IdctC::W5 * x7;
-    const int b2 = IdctC::W5 * x1 - IdctC::W1 * x3 + IdctC::W7 * x5 + IdctC::W3 * x7;
-    const int b3 = IdctC::W7 * x1 - IdctC::W5 * x3 + IdctC::W3 * x5 - IdctC::W1 * x7;
+    const int b0 = W1 * x1 + W3 * x3 + W5 * x5 + W7 * x7;
+    const int b1 = W3 * x1 - W7 * x3 - W1 * x5 - W5 * x7;
+    const int b2 = W5 * x1 - W1 * x3 + W7 * x5 + W3 * x7;
+    const int b3 = W7 * x1 - W5 * x3 + W3 * x5 - W1 * x7;
     s[0] = a0 + b0; s[1] = a1 + b1; s[2] = a2 + b2; s[3] = a3 + b3;
     d[0] = a0 - b0; d[1] = a1 - b1; d[2] = a2 - b2; d[3] = a3 - b3;
+}
+
+// four results of the column pass -> four clamped pixels in one word (x0 in the lowest byte)
+AMV_HD uint32_t pack_pixels(int p0, int p1, int p2, int p3) {
+#if defined(__CUDA_ARCH__)
+    // cvt.pack.sat.u8.s32: d = { c[15:0], sat_u8(a), sat_u8(b) } -- clamp (ff_cropTbl) and pack, two pixels per instruction
+    uint32_t hi, w;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(p1), "r"(p0), "r"(hi));
+    return w;
+#else
+    return (uint32_t)clamp_u8(p0) | ((uint32_t)clamp_u8(p1) << 8) | ((uint32_t)clamp_u8(p2) << 16) | ((uint32_t)clamp_u8(p3) << 24);
+#endif
 }
 
 // in : c[32], word 4*r+i = coefficient (r,2i) in the low half, (r,2i+1) in the high half
@@ -49,32 +66,36 @@ AMV_HD void idct_put_block(const uint32_t (&c)[32], uint32_t (&o)[16]) {
         const int x2 = sext16((int)w1), x3 = (int)w1 >> 16;
         const int x4 = sext16((int)w2), x5 = (int)w2 >> 16;
         const int x6 = sext16((int)w3), x7 = (int)w3 >> 16;
-        // DC-only rows take (row[0] << 3) & 0xffff for every output (:98-103); feeding
-        // that value, pre-shifted, as the DC term makes the general path produce it.
+        // The row pass runs scaled by 32: the reference keeps (sum >> 11) truncated to int16, i.e. bits
+        // 11..26 of the sum -- which are the top half of 32 * sum, one arithmetic shift away, whatever
+        // the sum's upper bits do.  DC-only rows take (row[0] << 3) & 0xffff for every output (:98-103);
+        // feeding that value, pre-shifted, as the DC term makes the general path produce it.
         const bool dc_only = ((w0 >> 16) | w1 | w2 | w3) == 0;
-        const int e0 = dc_only ? (int)((uint32_t)sext16((int)((uint32_t)x0 << 3)) << 11)
-                               : IdctC::W4 * x0 + (1 << 10);
+        const int e0 = dc_only ? (int)((uint32_t)x0 << 19) : (IdctC::W4 * 32) * x0 + (1 << 15);
         int s[4], d[4];
-        idct_1d(e0, x1, x2, x3, x4, x5, x6, x7, s, d);
+        idct_1d<32>(e0, x1, x2, x3, x4, x5, x6, x7, s, d);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            m[8 * r + i]     = sext16(s[i] >> 11);
-            m[8 * r + 7 - i] = sext16(d[i] >> 11);
+            m[8 * r + i]     = s[i] >> 16;
+            m[8 * r + 7 - i] = d[i] >> 16;
         }
     }
-#pragma unroll
-    for (int i = 0; i < 16; i++) o[i] = 0;
+    int px[64];
 #pragma unroll
     for (int col = 0; col < 8; col++) {
         int s[4], d[4];
-        idct_1d(IdctC::W4 * (m[col] + 32), m[8 + col], m[16 + col], m[24 + col], m[32 + col], m[40 + col],
-                m[48 + col], m[56 + col], s, d);
-        const int sh = 8 * (col & 3), wsel = col >> 2;
+        idct_1d<1>(IdctC::W4 * (m[col] + 32), m[8 + col], m[16 + col], m[24 + col], m[32 + col], m[40 + col],
+                   m[48 + col], m[56 + col], s, d);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            o[2 * i + wsel]       += (uint32_t)clamp_u8(s[i] >> 20) << sh;
-            o[2 * (7 - i) + wsel] += (uint32_t)clamp_u8(d[i] >> 20) << sh;
+            px[8 * i + col]       = s[i] >> 20;
+            px[8 * (7 - i) + col] = d[i] >> 20;
         }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        o[2 * r]     = pack_pixels(px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3]);
+        o[2 * r + 1] = pack_pixels(px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
     }
 }
 

@@ -14,7 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "amvcuda.h"
-#ifdef AMVLIB_LONG32            /* amvlib was written for a 32-bit `long` (Win32); see oracle/build_ref.sh */
+#ifdef AMVLIB_LONG32            /* amvlib was written for a 32-bit `long` (Win32) */
 #define long int
 #endif
 #include "AMVDec.h"          /* the reference's own header */

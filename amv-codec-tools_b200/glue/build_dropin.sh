@@ -21,7 +21,7 @@ gcc -o "$HERE/_build/dropin_check" "$HERE/_build/dropin_check.o" "$HERE/_build/a
 echo "built $HERE/_build/dropin_check"
 
 # ---- amvlib binding: glue/amvlib/amvcuda_amvlib.c against amvlib's own header, checked next to the
-# reference's unmodified AmvVideoDecode / AmvAudioDecode (objects from oracle/build_ref.sh)
+# reference's unmodified AmvVideoDecode / AmvAudioDecode
 AMVLIB="${AMV_REFERENCE_ROOT:-/root/reference}/C-AMVDecoder/amvlib"
 SH="$ROOT/oracle/_ref/cfg/amvlib_shim"
 if [ -d "$AMVLIB" ] && [ -f "$OBJ/amvlib_AMVDec.o" ]; then

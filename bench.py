@@ -31,9 +31,16 @@ FRAME_BYTES = W * H * 3 // 2
 METRIC = "AMV 320x240 frames/sec enc+dec"
 PKT_CAP = 65536                     # per-frame packet capacity handed to the encoder
 KERNELS = ("encode", "compact", "unstuff", "sync", "tokens", "idct")
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/), scaled per frame; filled in after each profiling pass
-TRAFFIC = {}
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of each hot kernel from the committed ncu --set full capture
+    (profiles/traffic.json, bytes per frame of that capture); scaled to the frames one launch processes here."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
 
 
 def load_peaks():
@@ -388,13 +395,19 @@ def main():
     peak, peak_src = load_peaks()
     bytes_per_frame = FRAME_BYTES + pkt_bytes / n          # raw planes + packet, per direction
 
+    traffic = load_traffic()
+
     def roof_of(k):
         """algorithmic bytes of the frames one launch of kernel k processes / its mean launch duration"""
         ms = kern[k]["ms"] / max(1, kern[k]["launches"])
         frames = n * args.steps / max(1, kern[k]["launches"])
         gbs = bytes_per_frame * frames / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        tr = traffic.get(k, {}).get("dram_bytes_per_frame")
         return {"bound": "hbm", "kernel": "k_" + ("vlc_" + k if k in ("sync", "tokens") else k), "achieved": gbs,
-                "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src, "traffic": TRAFFIC.get(k),
+                "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+                "traffic": tr * frames if tr else None,
+                "traffic_note": "ncu dram bytes per frame (profiles/traffic.json) x frames per launch" if tr else None,
+                "algorithmic_bytes_per_launch": bytes_per_frame * frames, "frames_per_launch": frames,
                 "ms_per_launch": ms, "bytes_per_frame": bytes_per_frame}
 
     dom = max(("encode", "tokens", "idct"), key=lambda k: kern[k]["ms"])

@@ -207,6 +207,44 @@ AMV_API int amv_adpcm_enc_streams(amv_ctx *ctx,
                                   uint8_t *out, uint64_t out_bytes, const uint64_t *out_off,
                                   int32_t *status, int mem);
 
+/* ------------------------------------------------------------------ AMV container (host side) */
+typedef struct amv_file_info {
+    int      width, height, fps;       /* amvh (amvenc.c:131-178, amvlib/AMVHeader.h:18-40) */
+    int      sample_rate, channels;    /* audio strf (riff.c:240-289) */
+    uint32_t us_per_frame, nb_frames_header, duration_s;
+    uint32_t nvideo, naudio;           /* chunks found in movi */
+    uint64_t movi_offset;              /* file offset of the "movi" tag (0x138 in real and reference-muxed files) */
+    int      has_end_marker, truncated;
+} amv_file_info;
+
+/*
+ * Index an AMV file held in memory: per video packet / audio chunk its offset INTO `file` and its
+ * size, so `file` itself can be handed to amv_decode_frames / amv_adpcm_dec_chunks as the packet
+ * buffer (pinned -> read in place by the kernels).  Replaces, for AMV, avi_read_header /
+ * avi_read_packet (libavformat/avidec.c with the amvh hooks :237,283,320,429-434) and amvlib's
+ * AmvOpen / AmvReadNextFrame (amvlib/AMVDec.c:15-238).  Arrays hold up to `cap` entries (may be NULL
+ * to count); info->nvideo / naudio report what the file holds.
+ */
+AMV_API int amv_file_index(const uint8_t *file, uint64_t size, amv_file_info *info,
+                           uint64_t *v_off, uint32_t *v_size, uint64_t *a_off, uint32_t *a_size, uint32_t cap);
+
+typedef struct amv_mux_params {
+    int width, height;
+    int tb_num, tb_den;                /* video time base: 1 / fps */
+    int sample_rate;                   /* 22050 for the reference encoder */
+    int video_bit_rate, audio_bit_rate;/* 0 = the reference's defaults (200000 / 64000); only header fields */
+} amv_mux_params;
+
+/*
+ * Write an AMV file: n video packets and n audio chunks, alternating.  Byte-identical to the
+ * reference's amv_muxer (libavformat/amvenc.c) driven like ffmpeg.c drives it for `-f amv`.
+ * Returns the file size, or -(bytes needed) if cap is too small (call with out=NULL, cap=0 to size).
+ */
+AMV_API int64_t amv_file_mux(const amv_mux_params *mp, int n,
+                             const uint8_t *vpk, const uint64_t *v_off, const uint32_t *v_size,
+                             const uint8_t *apk, const uint64_t *a_off, const uint32_t *a_size,
+                             uint8_t *out, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,9 +47,13 @@ mkdir -p "$OUT/cfg" "$OUT/obj"
   echo "#define ENABLE_GPL 0"
   echo "#define EXTERN_PREFIX \"\""
   echo "#define restrict __restrict__"
+  echo "#define CONFIG_AMV_MUXER 1"
+  echo "#define CONFIG_AVI_DEMUXER 1"
   # every ENABLE_<codec>_{EN,DE}CODER the compiled files mention: 0 except the AMV path
   on="AMV_DECODER AMV_ENCODER MJPEG_DECODER MJPEG_ENCODER SP5X_DECODER ADPCM_IMA_AMV_DECODER ADPCM_IMA_AMV_ENCODER"
+  on="$on AMV_MUXER AVI_DEMUXER"
   grep -rhoE "ENABLE_[A-Z0-9_]+" "$REF"/libavcodec/*.c "$REF"/libavcodec/*.h "$REF"/libavutil/*.[ch] \
+       "$REF"/libavformat/utils.c "$REF"/libavformat/avidec.c "$REF"/libavformat/amvenc.c "$REF"/libavformat/riff.c "$REF"/libavformat/*.h \
     | sort -u | while read -r m; do
       n="${m#ENABLE_}"
       case "$n" in ENCODERS|DECODERS|SMALL|GRAY|GPL) continue;; esac
@@ -67,8 +71,10 @@ CFLAGS="-O3 -fPIC -std=gnu99 -fgnu89-inline -fcommon -fno-strict-aliasing -fwrap
 AVCODEC="utils opt imgconvert dsputil simple_idct jfdctint jfdctfst jrevdct faandct \
  mpegvideo mpegvideo_enc mpeg12data mjpeg mjpegenc mjpegdec sp5xdec adpcm bitstream \
  ratecontrol motion_est error_resilience eval h263 jpeglsdec jpegls golomb \
-"
-AVUTIL="mem log rational mathematics integer intfloat_readwrite crc fifo"
+ parser raw"
+AVUTIL="mem log rational mathematics integer intfloat_readwrite crc fifo string"
+# container layer: the AMV muxer, the AVI/AMV demuxer and what they stand on
+AVFORMAT="utils aviobuf avio riff amvenc avidec cutils"
 
 objs=""
 for f in $AVCODEC; do
@@ -81,8 +87,14 @@ for f in $AVUTIL; do
   gcc $CFLAGS -c "$REF/libavutil/$f.c" -o "$OUT/obj/avu_$f.o"
   objs="$objs $OUT/obj/avu_$f.o"
 done
+for f in $AVFORMAT; do
+  [ -f "$REF/libavformat/$f.c" ] || { echo "skip $f"; continue; }
+  gcc $CFLAGS -I"$REF/libavformat" -c "$REF/libavformat/$f.c" -o "$OUT/obj/avf_$f.o"
+  fobjs="${fobjs:-} $OUT/obj/avf_$f.o"
+done
 gcc $CFLAGS -c "$HERE/ref_harness.c" -o "$OUT/obj/ref_harness.o"
-gcc -shared -o "$OUT/libamvref.so" "$OUT/obj/ref_harness.o" $objs -lm -Wl,--no-undefined
+gcc $CFLAGS -I"$REF/libavformat" -c "$HERE/ref_container_harness.c" -o "$OUT/obj/ref_container_harness.o"
+gcc -shared -o "$OUT/libamvref.so" "$OUT/obj/ref_harness.o" "$OUT/obj/ref_container_harness.o" $objs $fobjs -lm -Wl,--no-undefined
 echo "built $OUT/libamvref.so"
 
 # ---- amvlib (C-AMVDecoder/amvlib), compiled in place ------------------------

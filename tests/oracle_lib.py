@@ -324,6 +324,35 @@ class Ref:
         self.lib.amvref_fdct_islow(_p(b), b.shape[0])
         return b
 
+    # -- container (libavformat amv_muxer / avi_demuxer, driven like ffmpeg.c does)
+    def mux(self, w, h, fps, sample_rate, vpk, voff, vsz, apk, aoff, asz):
+        n = len(vsz)
+        cap = int(np.sum(vsz, dtype=np.uint64) + np.sum(asz, dtype=np.uint64)) + 16 * n + 4096
+        out = np.zeros(cap, np.uint8)
+        self.lib.amvref_mux.restype = C.c_int64
+        r = self.lib.amvref_mux(w, h, fps, sample_rate, n, _p(np.ascontiguousarray(vpk, np.uint8)),
+                                _p(np.ascontiguousarray(voff, np.uint64)), _p(np.ascontiguousarray(vsz, np.uint32)),
+                                _p(np.ascontiguousarray(apk, np.uint8)), _p(np.ascontiguousarray(aoff, np.uint64)),
+                                _p(np.ascontiguousarray(asz, np.uint32)), _p(out), C.c_uint64(cap))
+        if r < 0:
+            raise RuntimeError("reference mux failed: %d" % r)
+        return out[:r].tobytes()
+
+    def demux(self, data):
+        """-> (info[w,h,fps,rate,nv,na], [video packets], [audio chunks]) as the reference demuxer reads them"""
+        fb = np.frombuffer(data, np.uint8).copy()
+        cap_units, cap_bytes = len(fb) // 8 + 16, len(fb) + 64
+        info = np.zeros(6, np.int32)
+        vd, ad = np.zeros(cap_bytes, np.uint8), np.zeros(cap_bytes, np.uint8)
+        vs, as_ = np.zeros(cap_units, np.uint32), np.zeros(cap_units, np.uint32)
+        r = self.lib.amvref_demux(_p(fb), C.c_uint64(len(fb)), _p(info), _p(vd), _p(vs), _p(ad), _p(as_), cap_units,
+                                  C.c_uint64(cap_bytes))
+        if r < 0:
+            raise RuntimeError("reference demux failed: %d" % r)
+        vo = np.concatenate([[0], np.cumsum(vs[: info[4]], dtype=np.int64)])
+        ao = np.concatenate([[0], np.cumsum(as_[: info[5]], dtype=np.int64)])
+        return info, [vd[vo[i]:vo[i + 1]].tobytes() for i in range(info[4])], [ad[ao[i]:ao[i + 1]].tobytes() for i in range(info[5])]
+
     def idct_put(self, blocks):
         b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64)
         out = np.zeros((b.shape[0], 64), np.uint8)
