@@ -41,7 +41,7 @@ __device__ EncTablesDev g_enc_tables;
 // per-warp working set (dynamic shared memory, one instance per warp)
 struct EncWarpSmem {
     union {                                 // never live at the same time (A,B use coef; D,E use seg)
-        uint32_t coef[32 * 32];             // word (k>>1)*32 + lane : zigzag coefficients k, k+1 of the lane's block
+        uint16_t coef[64 * 32];             // halfword k*32 + lane : zigzag coefficient k of the lane's block
         uint32_t seg[kSegWords];            // the segment's contiguous bit string
     } u;
     uint32_t stage[kStageWords * 32];       // word w*32 + lane : the lane's private bit string
@@ -103,7 +103,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
     // explicit shared addresses for the hot loops
     const uint32_t huff_dc_s = smem_addr(&S.huff[comp ? kEncDcChroma : kEncDcLuma]);
     const uint32_t huff_ac_s = smem_addr(&S.huff[comp ? kEncAcChroma : kEncAcLuma]);
-    const uint32_t coef_s = smem_addr(&W.u.coef[lane]);          // coefficient k: + (k>>1)*128 + (k&1)*2
+    const uint32_t coef_s = smem_addr(&W.u.coef[lane]);          // coefficient k: + k*64
     const uint32_t stage_s = smem_addr(&W.stage[lane]);          // word w: + w*128
     const uint32_t seg_s = smem_addr(&W.u.seg[0]);
     const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
@@ -168,11 +168,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                     if (q) { if (k < 32) mask_lo |= 1u << k; else mask_hi |= 1u << (k - 32); }
                 }
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const uint32_t lo = (uint32_t)v[zigzag_at(2 * i)] & 0xffffu;
-                    const uint32_t hi = (uint32_t)v[zigzag_at(2 * i + 1)] << 16;
-                    W.u.coef[i * 32 + lane] = lo | hi;
-                }
+                for (int k = 1; k < 64; k++) W.u.coef[k * 32 + lane] = (uint16_t)v[zigzag_at(k)];
                 W.dcq[sigma] = dc;
             }
             __syncwarp();
@@ -183,21 +179,22 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                 int pred;
                 if (comp == 0) pred = (b > 0) ? W.dcq[sigma - 1] : (mi > 0 ? W.dcq[sigma - 3] : W.carry_dc[0]);
                 else           pred = mi > 0 ? W.dcq[sigma - 6] : W.carry_dc[comp];
-                uint64_t acc = 0;                   // MSB-first accumulator
-                int fill = 0;
+                uint32_t acc = 0;                   // MSB-first accumulator: the top `fill` bits are valid
+                uint32_t fill = 0;
                 uint32_t wp = stage_s;              // next private word
-                auto put = [&](uint32_t code, int nbits) {       // nbits <= 27
-                    acc |= (uint64_t)code << (64 - fill - nbits);
-                    fill += nbits;
-                    len += nbits;
-                    if (fill >= 32) { sts32(wp, (uint32_t)(acc >> 32)); wp += 128; acc <<= 32; fill -= 32; }
+                auto put = [&](uint32_t code, uint32_t nbits) {  // 1 <= nbits <= 27
+                    const uint32_t t = code << (32 - nbits);     // left-aligned
+                    acc |= t >> fill;
+                    const uint32_t nf = fill + nbits;
+                    if (nf >= 32) { sts32(wp, acc); wp += 128; acc = t << (32 - fill); fill = nf - 32; }   // fill >= 5 here
+                    else fill = nf;
                 };
                 {   // DC (ff_mjpeg_encode_dc, mjpegenc.c:357-377)
                     const int diff = dc - pred;
                     const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
                     const uint32_t e = lds32(huff_dc_s + nb * 4);
                     const uint32_t mant = (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u);
-                    put(((e >> 5) << nb) | mant, (int)(e & 31) + nb);
+                    put(((e >> 5) << nb) | mant, (e & 31) + (uint32_t)nb);
                 }
                 const uint32_t ezrl = lds32(huff_ac_s + 0xf0 * 4), eeob = lds32(huff_ac_s);
                 int prevk = 0;
@@ -207,18 +204,19 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
                         m &= m - 1;
                         int run = k - prevk - 1;
                         prevk = k;
-                        const int cv = lds_s16(coef_s + (uint32_t)(k >> 1) * 128 + (uint32_t)(k & 1) * 2);
+                        const int cv = lds_s16(coef_s + (uint32_t)k * 64);
                         const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
-                        for (; run >= 16; run -= 16) put(ezrl >> 5, (int)(ezrl & 31));
+                        for (; run >= 16; run -= 16) put(ezrl >> 5, ezrl & 31);
                         const uint32_t e = lds32(huff_ac_s + (uint32_t)((run << 4) | cb) * 4);
                         const uint32_t mant = (uint32_t)(cv + (cv >> 31)) & ((1u << cb) - 1u);
-                        put(((e >> 5) << cb) | mant, (int)(e & 31) + cb);
+                        put(((e >> 5) << cb) | mant, (e & 31) + (uint32_t)cb);
                     }
                 };
                 ac_run(mask_lo, 0);
                 ac_run(mask_hi, 32);
-                if (prevk != 63) put(eeob >> 5, (int)(eeob & 31));          // EOB only if last_index < 63 (:432-434)
-                if (fill > 0) sts32(wp, (uint32_t)(acc >> 32));
+                if (prevk != 63) put(eeob >> 5, eeob & 31);                 // EOB only if last_index < 63 (:432-434)
+                if (fill > 0) sts32(wp, acc);
+                len = ((wp - stage_s) >> 7) * 32u + fill;
             }
             W.lens[sigma] = len;               // lanes 30/31 and inactive blocks write 0 (slot 31 is a dummy)
             __syncwarp();
