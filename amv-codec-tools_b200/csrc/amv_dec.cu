@@ -515,10 +515,16 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         }
         return __funnelshift_l(c, a, bp & 31);
     };
+    // Bounds are checked once per block, not per store: a block yields at most 66 tokens, so a lane whose
+    // next group lies within kTokBlockRoom of the end of its frame's region (only streams that are already
+    // broken get there: a sound block of b bits has at most b/2 tokens) is flagged and parked on the
+    // region's tail, where its remaining blocks overwrite each other -- memory-safe, and every block still
+    // gets a valid (count, offset) entry for the consumer.
+    constexpr uint32_t kTokBlockRoom = 80;
+    const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~3u;    // tok_cap >= 320 (kSlotPad)
     auto flush4 = [&]() {
         const uint4 q = make_uint4(lds32(tst_s), lds32(tst_s + 128), lds32(tst_s + 256), lds32(tst_s + 384));
-        if (tok_idx + 4 <= tok_cap) *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = q;
-        else st |= AMV_ST_OVERRUN;
+        *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = q;
         tok_idx += 4;
         tcount = 0;
     };
@@ -544,8 +550,10 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         }
         if (!on) continue;
         const int tq = b >= 4 ? 1 : 0;
-        const uint32_t blk_start = min(tok_idx + (tcount >> 7), tok_cap);
-        const uint32_t tzq_s = tz_s + (uint32_t)tq * 256u;
+        if (tok_idx > tpark) { st |= AMV_ST_OVERRUN; tok_idx = tpark; }      // see kTokBlockRoom
+        const uint32_t blk_start = tok_idx + (tcount >> 7);
+        uint32_t tzq_s = tz_s + (uint32_t)tq * 256u;
+        asm volatile("mov.u32 %0, %0;" : "+r"(tzq_s));           // keep the per-block table base in a register
         const uint32_t dc_lut_s = lut_s + (tq ? dc_base[1] : dc_base[0]) * 4u, ac_lut_s = lut_s + (tq ? ac_base[1] : ac_base[0]) * 4u;
         // ---- DC (mjpeg_decode_dc, mjpegdec.c:358-373)
         {
@@ -587,7 +595,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
                     e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
                 if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; bp += 1; break; }
             }
-            const uint32_t len = e & 0xff, rsh = (e >> 8) & 0xff, total = (e >> 16) & 0xff, run = e >> 28;
+            const uint32_t len = e & 0xff, rsh = __byte_perm(e, 0, 0x4441), total = __byte_perm(e, 0, 0x4442), run = e >> 28;
             const uint32_t top = hi << len;
             bp += total;
             if (rsh == 32) {                                                   // size 0: EOB or ZRL

@@ -166,6 +166,27 @@ def run_cpu_reference(frames_per_worker, rounds=1, workers=None):
             "kind": res[0][3], "pkt_bytes": sum(r[2] for r in res), "per_core_fps": frames / busy / workers}
 
 
+# stdout carries exactly ONE line, the JSON result: everything else any library prints there (NCCL's version
+# banner, torchrun notices) is diverted to stderr at the file-descriptor level for the whole run
+_RESULT_FD = None
+
+
+def protect_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -194,7 +215,7 @@ def reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -211,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--audit", type=int, default=64, help="frames checked against the oracle after the run")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -224,8 +246,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps the banner off stdout (one JSON line)
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
@@ -449,7 +469,7 @@ def main():
                                 "per_core": cb["per_core_fps"]}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
