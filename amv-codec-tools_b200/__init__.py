@@ -33,7 +33,7 @@ EXPORTS = [
     "amv_launch_count", "amv_host_alloc", "amv_host_free", "amv_set_option", "amv_get_stat",
     "amv_qscale_from_quality", "amv_decode_frames", "amv_encode_frames", "amv_adpcm_dec_chunks",
     "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
-    "amv_file_index", "amv_file_mux",
+    "amv_file_index", "amv_file_mux", "amv_decode_frames_sp5x",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library(path=LIB_PATH):
     lib.amv_get_stat.restype = C.c_int64
     lib.amv_qscale_from_quality.argtypes = [i32, i32, i32]
     lib.amv_decode_frames.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, vp, i32]
+    lib.amv_decode_frames_sp5x.argtypes = lib.amv_decode_frames.argtypes
     lib.amv_decode_frames_bgr24.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, i32, u64, vp, i32]
     lib.amv_file_index.argtypes = [vp, u64, C.POINTER(FileInfo), vp, vp, vp, vp, u32]
     lib.amv_file_mux.argtypes = [C.POINTER(MuxParams), i32, vp, vp, vp, vp, vp, vp, vp, u64]
@@ -218,8 +219,10 @@ class AmvCuda:
         return self.lib.amv_qscale_from_quality(int(quality), qmin, qmax)
 
     # ---------------------------------------------------------------- raw ABI calls (any memory kind)
-    def decode_frames_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem):
-        self._ck(self.lib.amv_decode_frames(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
+    def decode_frames_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem,
+                          sp5x=False):
+        fn = self.lib.amv_decode_frames_sp5x if sp5x else self.lib.amv_decode_frames
+        self._ck(fn(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
                                             _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, _ptr(status), mem))
 
     def decode_frames_bgr24_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, bgr, line_bytes, frame_stride, status, mem):
@@ -249,8 +252,9 @@ class AmvCuda:
                                                 _ptr(out), out_bytes, _ptr(out_off), _ptr(status), mem))
 
     # ---------------------------------------------------------------- host (numpy) convenience wrappers
-    def decode_frames(self, pkts, pkt_off, pkt_size, w, h):
-        """numpy in / numpy out through AMV_MEM_HOST. -> (y[n,h,w], u[n,ch,cw], v[n,ch,cw], status[n])"""
+    def decode_frames(self, pkts, pkt_off, pkt_size, w, h, sp5x=False):
+        """numpy in / numpy out through AMV_MEM_HOST. -> (y[n,h,w], u[n,ch,cw], v[n,ch,cw], status[n]);
+        sp5x=True decodes SP5X packets (amv_decode_frames_sp5x)"""
         pkts = np.ascontiguousarray(pkts, np.uint8)
         pkt_off = np.ascontiguousarray(pkt_off, np.uint64)
         pkt_size = np.ascontiguousarray(pkt_size, np.uint32)
@@ -260,7 +264,8 @@ class AmvCuda:
         u = np.zeros((n, ch, cw), np.uint8)
         v = np.zeros((n, ch, cw), np.uint8)
         st = np.zeros(n, np.int32)
-        self.decode_frames_raw(pkts, pkts.nbytes, pkt_off, pkt_size, n, w, h, y, u, v, w, cw, w * h, cw * ch, st, MEM_HOST)
+        self.decode_frames_raw(pkts, pkts.nbytes, pkt_off, pkt_size, n, w, h, y, u, v, w, cw, w * h, cw * ch, st, MEM_HOST,
+                               sp5x=sp5x)
         return y, u, v, st
 
     def decode_frames_bgr24(self, pkts, pkt_off, pkt_size, w, h, line_bytes=None):

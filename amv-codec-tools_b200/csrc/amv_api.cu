@@ -138,7 +138,7 @@ struct DecodeFront {
 };
 
 int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
-                 int n, const Geom &g, int32_t *status, uint64_t payload_bytes, bool amvlib, DecodeFront &F) {
+                 int n, const Geom &g, int32_t *status, uint64_t payload_bytes, bool amvlib, DecodeFront &F, bool sp5x = false) {
     const int log2p = pick_log2p(ctx, n);
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
     uint32_t *rounds; uint32_t *tokens; uint32_t *blk_off;
@@ -154,7 +154,7 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
 
     launch_scan_sizes(pkt_size, n, 15u, kSlotPad, slot_off, nullptr, ctx->stream);
     { ScopedTimer tm(ctx, KK_UNSTUFF);
-      launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, ctx->stream); }
+      launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, sp5x, ctx->stream); }
     int lc = 2;
     if (log2p) {
         CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
@@ -171,10 +171,11 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
 
 int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                   const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
-                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes) {
-    const Geom g = make_geom(w, h);
+                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes, bool sp5x = false) {
+    Geom g = make_geom(w, h);
+    if (sp5x) g.flip = 0;
     DecodeFront F;
-    int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F);
+    int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F, sp5x);
     if (r != AMV_OK) return r;
     { ScopedTimer tm(ctx, KK_IDCT);
       launch_idct(F.tokens, F.blk_off, F.slot_off, F.scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
@@ -369,7 +370,7 @@ void *device_view(const void *host_ptr) {
 
 int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
                 int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
-                int32_t *status) {
+                int32_t *status, bool sp5x = false) {
     const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
     const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
     const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
@@ -415,7 +416,7 @@ int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const ui
         }
         if (e_out.used[slot]) CK(cudaStreamWaitEvent(ctx->stream, e_out.e[slot], 0));      // ring slot drained?
         rc = decode_device(ctx, v_pk ? v_pk : d_pk, pkts_bytes, v_off + f0, v_sz + f0, m, w, h, d_y + ty * C * slot,
-                           d_u + tc * C * slot, d_v + tc * C * slot, w, cw, ty, tc, d_st + f0, payload);
+                           d_u + tc * C * slot, d_v + tc * C * slot, w, cw, ty, tc, d_st + f0, payload, sp5x);
         if (rc != AMV_OK) break;
         CK(cudaEventRecord(e_cmp.e[slot], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_out, e_cmp.e[slot], 0));
@@ -654,9 +655,9 @@ AMV_API int64_t amv_get_stat(amv_ctx *ctx, const char *key) {
 }
 
 // ---------------------------------------------------------------------------------------- decode
-AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
-                              const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
-                              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
+static int decode_frames_common(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                                const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
+                                int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem, bool sp5x) {
     if (!ctx) return AMV_ERR_ARG;
     if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
     if (n == 0) return AMV_OK;
@@ -666,9 +667,20 @@ AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_b
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
     CK(cudaSetDevice(ctx->device));
     if (mem == AMV_MEM_DEVICE)
-        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes);
+        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes, sp5x);
+    return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, sp5x);
+}
 
-    return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status);
+AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                              const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
+                              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
+    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, false);
+}
+
+AMV_API int amv_decode_frames_sp5x(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                                   const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
+                                   int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
+    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, true);
 }
 
 // -------------------------------------------------------------------------- decode, amvlib flavour

@@ -36,6 +36,7 @@ struct Geom {
     int mbw, mbh;      // macroblock grid, ceil(w/16) x ceil(h/16)
     int nblk;          // 6 * mbw * mbh
     int y0, c0;        // first (bottom-most stored) row of luma / chroma in flipped order
+    int flip;          // 1: rows are addressed bottom-up from y0 / c0 (AMV); 0: top-down (SP5X)
 };
 
 // Row the codec starts from before walking upwards: vs*(8*mb_h - ((h/2)&7)) - 1
@@ -53,6 +54,7 @@ AMV_HD Geom make_geom(int w, int h) {
     g.nblk = 6 * g.mbw * g.mbh;
     g.y0 = flip_start_row(h, 2);
     g.c0 = flip_start_row(h, 1);
+    g.flip = 1;
     return g;
 }
 

@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t *__restrict__ pkt_off,
           const uint32_t *__restrict__ pkt_size, int n, uint8_t *__restrict__ scratch,
           const uint64_t *__restrict__ slot_off, uint64_t scratch_bytes, uint32_t *__restrict__ scan_len,
-          int32_t *__restrict__ status) {
+          int32_t *__restrict__ status, int sp5x) {
+    // framing: AMV = FF D8 | stuffed scan | FF D9 (sp5xdec.c:75-77); SP5X = 14 header bytes | scan with LITERAL FF
+    // bytes to the end of the packet (the reference stuffs them itself before handing over, :78-84)
+    const uint32_t head = sp5x ? 14u : 2u, framing = sp5x ? 14u : 4u;
     constexpr int kUnstuffTile = kUnstuffThreads * 16;
     constexpr int kUnstuffStage = kUnstuffTile + 64;
     __shared__ __align__(16) uint8_t stage[kUnstuffStage];
@@ -110,11 +113,11 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
             if (tid == 0) { scan_len[f] = 0; status[f] = AMV_ST_RANGE; }
             continue;
         }
-        if (size < 4) st |= AMV_ST_SHORT;
-        // virtual stream: payload bytes pkt[2 .. size-2) followed by FF D9
-        const uint32_t npay = size >= 4 ? size - 4 : 0;
+        if (size < framing) st |= AMV_ST_SHORT;
+        // virtual stream: payload bytes pkt[head .. size-tail) followed by FF D9
+        const uint32_t npay = size >= framing ? size - framing : 0;
         const uint32_t V = npay + 2;
-        const uint8_t *pay = pkts + off + 2;
+        const uint8_t *pay = pkts + off + head;
         const uint32_t mis = (uint32_t)((uintptr_t)pay & 15);       // bytes before the payload in its first 16 B unit
         const uint8_t *abase = pay - mis;
         uint8_t *dst = scratch + slot;
@@ -137,7 +140,9 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
             uint32_t wv[4] = { qn.x, qn.y, qn.z, qn.w };
             qn = load_unit(t0 + kUnstuffTile);
             uint32_t keep = 0, term = 0;
-            if (i0 >= 1 && i0 + 16 <= (int64_t)npay) {
+            if (sp5x && i0 >= 0 && i0 + 16 <= (int64_t)npay) {
+                keep = 0xffffu;                   // literal bytes: nothing to drop, nothing terminates
+            } else if (!sp5x && i0 >= 1 && i0 + 16 <= (int64_t)npay) {
                 // ---- unit inside the payload: SIMD byte flags.  after_ff = the byte before is FF;
                 // drop = after_ff and (00 or FF); terminator = after_ff and not (00, FF, RSTn)
                 const uint32_t f0 = zero_bytes(~wv[0]), f1 = zero_bytes(~wv[1]), f2 = zero_bytes(~wv[2]), f3 = zero_bytes(~wv[3]);
@@ -167,7 +172,8 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
                     if (i == (int64_t)npay) x = 0xff;              // appended EOI
                     else if (i == (int64_t)npay + 1) x = 0xd9;
                     const bool valid = i >= 0 && i < (int64_t)V;
-                    const bool after_ff = prev == 0xff && i > 0;   // the byte before the payload is the SOS header's 00
+                    // the byte before the payload is the SOS header's 00; SP5X payload bytes are literal
+                    const bool after_ff = prev == 0xff && i > 0 && !(sp5x && i <= (int64_t)npay);
                     const bool drop = after_ff && (x == 0x00 || x == 0xff);
                     const bool is_term = after_ff && !(x == 0x00 || x == 0xff || (x >= 0xd0 && x <= 0xd7));
                     if (valid && !drop) keep |= 1u << b;
@@ -691,7 +697,7 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
     const int x0 = bx * 8, y0 = by * 8;
 #pragma unroll
     for (int yy = 0; yy < 8; yy++) {
-        const int row = r0 - (y0 + yy);
+        const int row = g.flip ? r0 - (y0 + yy) : y0 + yy;     // AMV pictures are stored bottom-up (mjpegdec.c:672-677), SP5X is not
         if (row < 0 || row >= vh) continue;
         uint8_t *d = pl + (int64_t)row * ls + x0;
         if (FAST) {
@@ -724,13 +730,13 @@ void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_
 
 void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
                     uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
-                    int32_t *status, cudaStream_t s) {
+                    int32_t *status, bool sp5x, cudaStream_t s) {
     // 64-thread CTAs (1 KB tiles): the tile loop is a chain of barriers, and small CTAs keep more
     // independent chains per SM (measured 2.6 / 2.1 / 1.9 ms per 100k frames at 256 / 128 / 64 threads)
     constexpr int kThreads = 64, kPerSM = 24;
     const int grid = n < kNumSMs * kPerSM ? n : kNumSMs * kPerSM;
     k_unstuff<kThreads><<<grid, kThreads, 0, s>>>(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes,
-                                                  scan_len, status);
+                                                  scan_len, status, sp5x ? 1 : 0);
 }
 
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,

@@ -20,7 +20,7 @@ void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_
                        uint64_t *carry_io, cudaStream_t s);
 void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
                     uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
-                    int32_t *status, cudaStream_t s);
+                    int32_t *status, bool sp5x, cudaStream_t s);
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, cudaStream_t s);
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,

@@ -136,6 +136,21 @@ AMV_API int amv_decode_frames(amv_ctx *ctx,
                               int32_t *status, int mem);
 
 /*
+ * The sibling codec behind the same reference entry point: SP5X ("Sunplus JPEG", sp5x_decoder,
+ * libavcodec/sp5xdec.c:33-188,190-201).  Same tables, Huffman and IDCT as AMV; the packet is a
+ * 14-byte header followed by the scan with LITERAL FF bytes to the end of the packet (:78-84),
+ * and the picture is stored top-down (no flip: mjpegdec.c:672-677 applies to AMV only).
+ * Arguments as amv_decode_frames.
+ */
+AMV_API int amv_decode_frames_sp5x(amv_ctx *ctx,
+                                   const uint8_t *pkts, uint64_t pkts_bytes,
+                                   const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                                   int w, int h,
+                                   uint8_t *y, uint8_t *u, uint8_t *v,
+                                   int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                                   int32_t *status, int mem);
+
+/*
  * amvlib flavour of the video decoder: what C-AMVDecoder/amvlib computes for the same packets --
  * replaces AmvVideoDecode (amvlib/AMVDec.c:259-286) -> AmvJpegDecode (amvlib/AmvJpeg.c:1515-1539).
  * amvlib is NOT bit-identical to the ffmpeg fork (own quantiser tables AmvJpeg.c:30-61, a zigzag

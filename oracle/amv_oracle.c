@@ -504,25 +504,17 @@ AMVO_API size_t amvo_unstuff(const uint8_t *pkt, uint32_t size, uint8_t *dst, in
     return n;
 }
 
-/* Decode one packet into three planes (strides in bytes).  Returns 0 or a mask
- * of AMVO_E_*; on error the picture content is unspecified (SURVEY 9.9).
- * sp5x_decode_frame (sp5xdec.c:33-93) -> ff_mjpeg_decode_frame
- * (mjpegdec.c:1106-1340) -> mjpeg_decode_scan (:660-736) -> decode_block
- * (:376-430) -> simple_idct_put. */
-AMVO_API int amvo_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int h,
-                                  uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
-                                  int16_t *coef_dump /* optional: 64*6*mbw*mbh dequantised coefs */,
-                                  uint8_t *uy, uint8_t *uu, uint8_t *uv /* optional: 1 where the reference is undefined */)
+/* the scan decoder shared by AMV and SP5X: `scan` is the un-stuffed entropy-coded segment; flip = AMV's
+ * bottom-up placement (mjpegdec.c:672-677), 0 for SP5X */
+static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int flip,
+                       uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
+                       int16_t *coef_dump, uint8_t *uy, uint8_t *uu, uint8_t *uv)
 {
     build_tables();
-    int flags = 0;
     const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
     const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
     int16_t q[2][64];                                       /* raster order (mjpegdec.c:131-134) */
     for (int t = 0; t < 2; t++) for (int k = 0; k < 64; k++) q[t][g_zz[k]] = kDecQuantZZ[t][k];
-
-    uint8_t *scan = (uint8_t *)malloc((size_t)size + 16);
-    size_t nscan = amvo_unstuff(pkt, size, scan, &flags);
     bitr br = { scan, nscan, 0, 0, 0, 0 };
     int pred[3] = { 1024, 1024, 1024 };                     /* mjpegdec.c:805-806 */
     const int y0 = flip_start_row(h, 2), c0 = flip_start_row(h, 1);
@@ -561,7 +553,7 @@ AMVO_API int amvo_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int 
         const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
         const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
         for (int yy = 0; yy < 8; yy++) {
-            int row = r0 - (by + yy);
+            int row = flip ? r0 - (by + yy) : by + yy;
             if (row < 0 || row >= vh) continue;
             for (int xx = 0; xx < 8; xx++)
                 if (bx + xx < vw) {
@@ -571,8 +563,56 @@ AMVO_API int amvo_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int 
         }
     }
     if (br_bits_used(&br) > nscan * 8) flags |= AMVO_E_OVERRUN;
+    return flags;
+}
+
+/* Decode one packet into three planes (strides in bytes).  Returns 0 or a mask
+ * of AMVO_E_*; on error the picture content is unspecified (SURVEY 9.9).
+ * sp5x_decode_frame (sp5xdec.c:33-93) -> ff_mjpeg_decode_frame
+ * (mjpegdec.c:1106-1340) -> mjpeg_decode_scan (:660-736) -> decode_block
+ * (:376-430) -> simple_idct_put. */
+AMVO_API int amvo_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int h,
+                                  uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
+                                  int16_t *coef_dump /* optional: 64*6*mbw*mbh dequantised coefs */,
+                                  uint8_t *uy, uint8_t *uu, uint8_t *uv /* optional: 1 where the reference is undefined */)
+{
+    int flags = 0;
+    uint8_t *scan = (uint8_t *)malloc((size_t)size + 16);
+    size_t nscan = amvo_unstuff(pkt, size, scan, &flags);
+    flags = decode_scan(scan, nscan, flags, w, h, 1, py, pu, pv, ls_y, ls_c, coef_dump, uy, uu, uv);
     free(scan);
     return flags;
+}
+
+/* SP5X (sp5x_decoder, sp5xdec.c:33-188 with codec_id != CODEC_ID_AMV): the scan is the packet from byte 14
+ * to its end; the reference stuffs every FF itself (:78-84) before the MJPEG decoder un-stuffs it again, so
+ * the bytes are literal, followed by the FF of the appended EOI (:87-88); no vertical flip. */
+AMVO_API int amvo_sp5x_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,
+                                    uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
+                                    uint8_t *uy, uint8_t *uu, uint8_t *uv /* optional undefined-domain masks */)
+{
+    int flags = size < 14 ? AMVO_E_SHORT : 0;
+    const size_t npay = size >= 14 ? size - 14 : 0;
+    uint8_t *scan = (uint8_t *)malloc(npay + 16);
+    if (npay) memcpy(scan, pkt + 14, npay);
+    scan[npay] = 0xff;
+    flags = decode_scan(scan, npay + 1, flags, w, h, 0, py, pu, pv, ls_y, ls_c, NULL, uy, uu, uv);
+    free(scan);
+    return flags;
+}
+
+AMVO_API int amvo_sp5x_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                                     int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int *status,
+                                     uint8_t *uy, uint8_t *uu, uint8_t *uv)
+{
+    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    for (int i = 0; i < n; i++) {
+        size_t yo = (size_t)i * w * h, co = (size_t)i * cw * chh;
+        int st = amvo_sp5x_decode_frame(pkts + off[i], size[i], w, h, y + yo, u + co, v + co, w, cw,
+                                        uy ? uy + yo : NULL, uu ? uu + co : NULL, uv ? uv + co : NULL);
+        if (status) status[i] = st;
+    }
+    return n;
 }
 
 AMVO_API int amvo_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,

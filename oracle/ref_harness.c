@@ -77,9 +77,29 @@ done:
 
 /* ---- video decode: n packets -> tightly packed planes ----
  * got[i] receives got_picture; ret_bytes[i] the decoder's return value (may be NULL). */
+extern AVCodec sp5x_decoder;
+static int decode_frames_with(AVCodec *codec, const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                              int n, int w, int h,
+                              uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes);
+
 int amvref_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
                          int n, int w, int h,
                          uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes)
+{
+    return decode_frames_with(&amv_decoder, pkts, off, size, n, w, h, y, u, v, got, ret_bytes);
+}
+
+/* same driver on the sibling codec of the same source file: sp5x_decoder (sp5xdec.c:190-201) */
+int amvref_sp5x_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                              int n, int w, int h,
+                              uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes)
+{
+    return decode_frames_with(&sp5x_decoder, pkts, off, size, n, w, h, y, u, v, got, ret_bytes);
+}
+
+static int decode_frames_with(AVCodec *codec, const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                              int n, int w, int h,
+                              uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes)
 {
     ref_init();
     AVCodecContext *c = avcodec_alloc_context();
@@ -90,7 +110,7 @@ int amvref_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_
     uint8_t *buf = av_mallocz(maxsz + FF_INPUT_BUFFER_PADDING_SIZE + 16);
     c->width = w; c->height = h;          /* container supplies dims: avidec.c:429-434 */
     c->coded_width = w; c->coded_height = h;
-    if (avcodec_open(c, &amv_decoder) < 0) { ret = -2; goto done; }
+    if (avcodec_open(c, codec) < 0) { ret = -2; goto done; }
     for (i = 0; i < n; i++) {
         int g = 0;
         memcpy(buf, pkts + off[i], size[i]);

@@ -168,6 +168,19 @@ class Oracle(_AmvlibOracleMixin):
                                     _p(m[0]), _p(m[1]), _p(m[2]))
         return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
 
+    def sp5x_decode_frames(self, pkts, off, size, w, h, undef=False):
+        n = len(size)
+        cw, ch = chroma_dims(w, h)
+        y = np.zeros((n, h, w), np.uint8)
+        u = np.zeros((n, ch, cw), np.uint8)
+        v = np.zeros((n, ch, cw), np.uint8)
+        m = [np.zeros_like(a) for a in (y, u, v)] if undef else [None] * 3
+        st = np.zeros(n, np.int32)
+        self.lib.amvo_sp5x_decode_frames(_p(np.ascontiguousarray(pkts, np.uint8)), _p(np.ascontiguousarray(off, np.uint64)),
+                                         _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v), _p(st),
+                                         _p(m[0]), _p(m[1]), _p(m[2]))
+        return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
+
     def decode_frame_coefs(self, pkt, w, h):
         """Dequantised coefficients of every block in bitstream order (raster inside a block)."""
         mbw, mbh = (w + 15) // 16, (h + 15) // 16
@@ -276,7 +289,7 @@ class Ref:
             raise RuntimeError("reference encode failed: %d" % r)
         return out[: int(size.sum())].copy(), off, size
 
-    def decode_frames(self, pkts, off, size, w, h):
+    def decode_frames(self, pkts, off, size, w, h, sp5x=False):
         n = len(size)
         cw, ch = chroma_dims(w, h)
         y = np.zeros((n, h, w), np.uint8)
@@ -284,7 +297,8 @@ class Ref:
         v = np.zeros((n, ch, cw), np.uint8)
         got = np.zeros(n, np.int32)
         rb = np.zeros(n, np.int32)
-        r = self.lib.amvref_decode_frames(_p(np.ascontiguousarray(pkts, np.uint8)),
+        fn = self.lib.amvref_sp5x_decode_frames if sp5x else self.lib.amvref_decode_frames
+        r = fn(_p(np.ascontiguousarray(pkts, np.uint8)),
                                           _p(np.ascontiguousarray(off, np.uint64)),
                                           _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v),
                                           _p(got), _p(rb))
@@ -430,6 +444,19 @@ def walk_amv(data):
         (vids if tag == b"00dc" else auds).append(data[p + 8:p + 8 + sz])
         p += 8 + sz
     return w, h, fps, vids, auds
+
+
+def sp5x_from_amv(oracle, pkts, off, size, header=None):
+    """SP5X packets carrying the scans of the given AMV packets: 14 header bytes (the decoder skips them,
+    sp5xdec.c:78) + the un-stuffed scan with literal FF bytes; no encoder for SP5X exists in the reference."""
+    hdr = bytes(header if header is not None else range(0xF1, 0xFF)) 
+    assert len(hdr) == 14
+    out = []
+    for o, s in zip(off, size):
+        scan, fl = oracle.unstuff(np.asarray(pkts[int(o):int(o) + int(s)]))
+        assert fl == 0 and scan[-1] == 0xFF
+        out.append(hdr + scan[:-1].tobytes())          # the trailing FF is the appended EOI's, not payload
+    return pack(out)
 
 
 def pack(chunks):

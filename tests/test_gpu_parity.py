@@ -495,3 +495,42 @@ def test_amvlib_dropin_matches_reference_amvlib(oracle, tmp_path):
         out = subprocess.run([AMVLIB_DROPIN, str(path)], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "AMVLIB DROP-IN CHECK OK" in out.stdout
+
+
+# ------------------------------------------------------------------ SP5X
+GS = np.load(os.path.join(os.path.dirname(__file__), "golden", "sp5x_golden.npz"))
+SP5X_CASES = bytes(GS["cases"]).decode().split("\n")
+
+
+@pytest.mark.parametrize("log2p", [0, 2, 5])
+@pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (320, 240, "sinus"), (208, 176, "noise"), (128, 96, "edges"),
+                                      (48, 40, "flat"), (16, 16, "sinus"), (72, 24, "noise"), (102, 56, "sinus")])
+def test_sp5x_decode_identical(ctx, oracle, w, h, kind, log2p):
+    """amv_decode_frames_sp5x vs the oracle: literal FF bytes in the scan (no un-stuffing), 14-byte header skipped,
+    top-down placement, partial macroblocks cropped; packets at unaligned offsets"""
+    from oracle_lib import sp5x_from_amv
+    n = 5 if w * h > 40000 else 11
+    y, u, v = synth_frames(n, w, h, seed=91, kind=kind)
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 2 if kind == "sinus" else 6)
+    sp, soff, ssz = sp5x_from_amv(oracle, pk, off, sz)
+    sp = np.concatenate([np.zeros(3, np.uint8), sp])           # shift every packet off its natural alignment
+    soff = soff + 3
+    ctx.set_option("decode_log2_lanes", log2p)
+    try:
+        dy, du, dv, st = ctx.decode_frames(sp, soff, ssz, w, h, sp5x=True)
+    finally:
+        ctx.set_option("decode_log2_lanes", -1)
+    wy, wu, wv, wst = oracle.sp5x_decode_frames(sp, soff, ssz, w, h)
+    assert (st == 0).all() and (wst == 0).all()
+    assert np.array_equal(dy, wy) and np.array_equal(du, wu) and np.array_equal(dv, wv)
+
+
+@pytest.mark.parametrize("case", SP5X_CASES)
+def test_sp5x_decode_golden(ctx, oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    dy, du, dv, st = ctx.decode_frames(GS[case + "/pk"], GS[case + "/off"], GS[case + "/sz"], w, h, sp5x=True)
+    assert (st == 0).all()
+    _, _, _, _, masks = oracle.sp5x_decode_frames(GS[case + "/pk"], GS[case + "/off"], GS[case + "/sz"], w, h, undef=True)
+    for got, want, m in zip((dy, du, dv), (GS[case + "/dy"], GS[case + "/du"], GS[case + "/dv"]), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])

@@ -120,3 +120,18 @@ def test_amvlib_fixture_head(oracle):
     assert (st == 0).all() and np.array_equal(bgr, GA["AMV1/bgr"])
     pcm, _, ns, ast = oracle.amvlib_audio_decode(GA["AMV1/ak"], GA["AMV1/aoff"], GA["AMV1/asz"])
     assert (ast == 0).all() and np.array_equal(ns, GA["AMV1/nsamp"]) and np.array_equal(pcm, GA["AMV1/pcm"])
+
+
+# ------------------------------------------------------------------ SP5X
+GS = np.load(os.path.join(os.path.dirname(__file__), "golden", "sp5x_golden.npz"))
+SP5X_CASES = bytes(GS["cases"]).decode().split("\n")
+
+
+@pytest.mark.parametrize("case", SP5X_CASES)
+def test_sp5x_decode_matches_golden(oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    y, u, v, st, masks = oracle.sp5x_decode_frames(GS[case + "/pk"], GS[case + "/off"], GS[case + "/sz"], w, h, undef=True)
+    assert (st == 0).all()
+    for got, want, m in zip((y, u, v), (GS[case + "/dy"], GS[case + "/du"], GS[case + "/dv"]), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])
