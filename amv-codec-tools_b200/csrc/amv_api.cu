@@ -55,6 +55,7 @@ struct amv_ctx {
     void *pinned_meta = nullptr;
     size_t pinned_meta_cap = 0;
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
+    bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
 };
 
 namespace {
@@ -387,7 +388,7 @@ int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const ui
     if (!v_sz) { memcpy(p_sz, pkt_size, sizeof(uint32_t) * n); v_sz = static_cast<const uint32_t *>(device_view(p_sz)); }
     int32_t *v_st = static_cast<int32_t *>(device_view(p_st));
     if (!v_off || !v_sz || !v_st) return fail(ctx, AMV_ERR_CUDA, "pinned bounce buffer is not device-mapped");
-    const uint8_t *v_pk = static_cast<const uint8_t *>(device_view(pkts));    // zero-copy packets if pinned
+    const uint8_t *v_pk = ctx->opt_zero_copy_packets ? static_cast<const uint8_t *>(device_view(pkts)) : nullptr;   // zero-copy packets if pinned
     uint8_t *d_pk = nullptr, *d_y, *d_u, *d_v; int32_t *d_st;
     if (!v_pk) ENSURE(WS_H_A, pkts_bytes ? pkts_bytes : 1, d_pk);
     ENSURE(WS_H_D, ty * C * kRing, d_y);
@@ -613,6 +614,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
+    if (!strcmp(key, "host_zero_copy_packets")) { ctx->opt_zero_copy_packets = value != 0; return AMV_OK; }
     return AMV_ERR_UNSUPPORTED;
 }
 
