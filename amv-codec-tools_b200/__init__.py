@@ -34,6 +34,7 @@ EXPORTS = [
     "amv_qscale_from_quality", "amv_decode_frames", "amv_encode_frames", "amv_adpcm_dec_chunks",
     "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
     "amv_file_index", "amv_file_mux", "amv_decode_frames_sp5x",
+    "amv_convert_range",
 ]
 
 
@@ -95,6 +96,7 @@ def load_library(path=LIB_PATH):
     lib.amv_qscale_from_quality.argtypes = [i32, i32, i32]
     lib.amv_decode_frames.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, vp, i32]
     lib.amv_decode_frames_sp5x.argtypes = lib.amv_decode_frames.argtypes
+    lib.amv_convert_range.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32]
     lib.amv_decode_frames_bgr24.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, i32, u64, vp, i32]
     lib.amv_file_index.argtypes = [vp, u64, C.POINTER(FileInfo), vp, vp, vp, vp, u32]
     lib.amv_file_mux.argtypes = [C.POINTER(MuxParams), i32, vp, vp, vp, vp, vp, vp, vp, u64]
@@ -224,6 +226,19 @@ class AmvCuda:
         fn = self.lib.amv_decode_frames_sp5x if sp5x else self.lib.amv_decode_frames
         self._ck(fn(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
                                             _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, _ptr(status), mem))
+
+    def convert_range_raw(self, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, direction, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, mem):
+        self._ck(self.lib.amv_convert_range(self.ctx, _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, n, w, h, direction,
+                                            _ptr(oy), _ptr(ou), _ptr(ov), ols_y, ols_c, ofs_y, ofs_c, mem))
+
+    def convert_range(self, y, u, v, direction):
+        """numpy planes [n,h,w] / [n,ch,cw]; direction 0: yuv420p -> yuvj420p, 1: yuvj420p -> yuv420p"""
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        n, h, w = y.shape
+        cw, ch = chroma_dims(w, h)
+        oy, ou, ov = np.zeros_like(y), np.zeros_like(u), np.zeros_like(v)
+        self.convert_range_raw(y, u, v, w, cw, w * h, cw * ch, n, w, h, direction, oy, ou, ov, w, cw, w * h, cw * ch, MEM_HOST)
+        return oy, ou, ov
 
     def decode_frames_bgr24_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, bgr, line_bytes, frame_stride, status, mem):
         self._ck(self.lib.amv_decode_frames_bgr24(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,

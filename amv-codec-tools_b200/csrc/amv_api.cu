@@ -715,6 +715,43 @@ AMV_API int amv_decode_frames_bgr24(amv_ctx *ctx, const uint8_t *pkts, uint64_t 
     return AMV_OK;
 }
 
+// ------------------------------------------------------------------------------- range conversion
+AMV_API int amv_convert_range(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
+                              uint64_t fs_y, uint64_t fs_c, int n, int w, int h, int dir, uint8_t *oy, uint8_t *ou,
+                              uint8_t *ov, int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem) || (dir != 0 && dir != 1))
+        return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem / dir");
+    if (n == 0) return AMV_OK;
+    if (!y || !u || !v || !oy || !ou || !ov) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    if (ls_y < w || ls_c < cw || ols_y < w || ols_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw ||
+        ofs_y < (uint64_t)ols_y * (h - 1) + w || ofs_c < (uint64_t)ols_c * (ch - 1) + cw)
+        return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE) {
+        launch_convert_range(y, u, v, oy, ou, ov, n, w, h, ls_y, ls_c, fs_y, fs_c, ols_y, ols_c, ofs_y, ofs_c, dir, ctx->stream);
+        return check_launch(ctx, "range conversion kernels", 3);
+    }
+    // host buffers: tight device copies in, kernels, tight copies out
+    const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    uint8_t *d_y, *d_u, *d_v;
+    ENSURE(WS_H_A, ty * n, d_y);
+    ENSURE(WS_H_B, tc * n, d_u);
+    ENSURE(WS_H_C, tc * n, d_v);
+    int r;
+    if ((r = copy_planes(ctx, d_y, const_cast<uint8_t *>(y), w, h, ls_y, fs_y, n, false)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_u, const_cast<uint8_t *>(u), cw, ch, ls_c, fs_c, n, false)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_v, const_cast<uint8_t *>(v), cw, ch, ls_c, fs_c, n, false)) != AMV_OK) return r;
+    launch_convert_range(d_y, d_u, d_v, d_y, d_u, d_v, n, w, h, w, cw, ty, tc, w, cw, ty, tc, dir, ctx->stream);
+    if ((r = check_launch(ctx, "range conversion kernels", 3)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_y, oy, w, h, ols_y, ofs_y, n, true)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_u, ou, cw, ch, ols_c, ofs_c, n, true)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_v, ov, cw, ch, ols_c, ofs_c, n, true)) != AMV_OK) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
 // ---------------------------------------------------------------------------------------- encode
 AMV_API int amv_encode_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
                               uint64_t fs_y, uint64_t fs_c, int n, int w, int h, const int32_t *qscale, uint8_t *out,

@@ -34,6 +34,11 @@ void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t
 void launch_idct_bgr(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len,
                      int n, const Geom &g, uint8_t *bgr, int line_bytes, uint64_t frame_stride, cudaStream_t s);
 
+// range conversion yuv420p <-> yuvj420p (imgconvert.c img_apply_table); dir 0: CCIR -> JPEG, 1: JPEG -> CCIR
+void launch_convert_range(const uint8_t *y, const uint8_t *u, const uint8_t *v, uint8_t *oy, uint8_t *ou, uint8_t *ov, int n,
+                          int w, int h, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int ols_y, int ols_c, uint64_t ofs_y,
+                          uint64_t ofs_c, int dir, cudaStream_t s);
+
 // ---- encode
 cudaError_t upload_enc_tables(cudaStream_t s);
 int  encode_grid(int n);

@@ -169,6 +169,20 @@ AMV_API int amv_decode_frames_bgr24(amv_ctx *ctx,
                                     int32_t *status, int mem);
 
 /*
+ * The pre/post stage the reference's ffmpeg.c puts next to the codec: range conversion between
+ * yuv420p (CCIR 601 range) and the codec's yuvj420p (full range) -- img_convert -> img_apply_table
+ * with y/c_ccir_to_jpeg resp. y/c_jpeg_to_ccir (libavcodec/imgconvert.c:1216-1260,2492-2510,
+ * colorspace.h:69-84).  dir 0: CCIR -> JPEG (before amv_encode_frames), dir 1: JPEG -> CCIR
+ * (after amv_decode_frames).  Planes / strides as in amv_decode_frames; output may alias input.
+ */
+AMV_API int amv_convert_range(amv_ctx *ctx,
+                              const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                              int n, int w, int h, int dir,
+                              uint8_t *oy, uint8_t *ou, uint8_t *ov,
+                              int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int mem);
+
+/*
  * Encode n YUVJ420P frames into AMV packets, byte-identical to amv_encoder.
  *   y,u,v, ls_*, fs_*        as above (source planes)
  *   qscale                   per-frame quantiser scale 2..31 (NULL = 2, the reference default;

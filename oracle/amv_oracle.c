@@ -990,3 +990,26 @@ AMVO_API int amvo_amvlib_audio_decode_chunk(const uint8_t *c, uint32_t size, int
     }
     return n;
 }
+
+/* ========================================================================== *
+ * Range conversion next to the codec: what img_convert does between yuv420p (CCIR 601
+ * range) and yuvj420p (full range): img_apply_table (imgconvert.c:1236-1260, 2492-2510) with the
+ * tables of img_convert_init (:1221-1233) = colorspace.h:69-84, SCALEBITS 10, FIX(x) = (int)(x*1024+0.5).
+ * dir 0: CCIR -> JPEG, dir 1: JPEG -> CCIR.  In place allowed.
+ * ========================================================================== */
+static inline uint8_t range_y(int y, int dir)
+{
+    if (dir) return (uint8_t)((y * 879 + (512 + (16 << 10))) >> 10);                       /* Y_JPEG_TO_CCIR */
+    return clip_u8((y * 1192 + (512 - 16 * 1192)) >> 10);                                   /* Y_CCIR_TO_JPEG, clamped by cm[] */
+}
+static inline uint8_t range_c(int c, int dir)
+{
+    if (dir) { int v = ((c - 128) * 903 + (512 + (128 << 10))) >> 10; return (uint8_t)(v < 16 ? 16 : v); }   /* C_JPEG_TO_CCIR */
+    return clip_u8(((c - 128) * 1161 + (512 + (128 << 10))) >> 10);                         /* C_CCIR_TO_JPEG */
+}
+AMVO_API void amvo_convert_range(const uint8_t *y, const uint8_t *u, const uint8_t *v, size_t ny, size_t nc, int dir,
+                                 uint8_t *oy, uint8_t *ou, uint8_t *ov)
+{
+    for (size_t i = 0; i < ny; i++) oy[i] = range_y(y[i], dir);
+    for (size_t i = 0; i < nc; i++) { ou[i] = range_c(u[i], dir); ov[i] = range_c(v[i], dir); }
+}

@@ -210,3 +210,26 @@ void amvref_simple_idct_put(const int16_t *blocks, int nblocks, uint8_t *dest /*
         simple_idct_put(dest + 64 * i, 8, tmp);
     }
 }
+
+/* ---- pre/post stage next to the codec: the range conversion ffmpeg.c inserts through img_convert
+ * when the source is yuv420p (CCIR range) and the AMV encoder wants yuvj420p (ffmpeg.c:do_video_out ->
+ * img_convert, imgconvert.c:2379-2510 -> img_apply_table with y/c_ccir_to_jpeg, :1216-1260; colorspace.h:69-84).
+ * dir 0: YUV420P -> YUVJ420P, dir 1: YUVJ420P -> YUV420P.  Tight planes. */
+int amvref_convert_range(const uint8_t *y, const uint8_t *u, const uint8_t *v, int n, int w, int h, int dir,
+                         uint8_t *oy, uint8_t *ou, uint8_t *ov)
+{
+    ref_init();
+    int cw = (w + 1) >> 1, ch = (h + 1) >> 1, i;
+    for (i = 0; i < n; i++) {
+        AVPicture src, dst;
+        src.data[0] = (uint8_t *)y + (size_t)i * w * h; src.data[1] = (uint8_t *)u + (size_t)i * cw * ch;
+        src.data[2] = (uint8_t *)v + (size_t)i * cw * ch; src.data[3] = NULL;
+        src.linesize[0] = w; src.linesize[1] = cw; src.linesize[2] = cw; src.linesize[3] = 0;
+        dst.data[0] = oy + (size_t)i * w * h; dst.data[1] = ou + (size_t)i * cw * ch;
+        dst.data[2] = ov + (size_t)i * cw * ch; dst.data[3] = NULL;
+        dst.linesize[0] = w; dst.linesize[1] = cw; dst.linesize[2] = cw; dst.linesize[3] = 0;
+        if (img_convert(&dst, dir ? PIX_FMT_YUV420P : PIX_FMT_YUVJ420P, &src, dir ? PIX_FMT_YUVJ420P : PIX_FMT_YUV420P, w, h) < 0)
+            return -1;
+    }
+    return n;
+}

@@ -168,6 +168,12 @@ class Oracle(_AmvlibOracleMixin):
                                     _p(m[0]), _p(m[1]), _p(m[2]))
         return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
 
+    def convert_range(self, y, u, v, direction):
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        oy, ou, ov = np.zeros_like(y), np.zeros_like(u), np.zeros_like(v)
+        self.lib.amvo_convert_range(_p(y), _p(u), _p(v), C.c_size_t(y.size), C.c_size_t(u.size), int(direction), _p(oy), _p(ou), _p(ov))
+        return oy, ou, ov
+
     def sp5x_decode_frames(self, pkts, off, size, w, h, undef=False):
         n = len(size)
         cw, ch = chroma_dims(w, h)
@@ -337,6 +343,16 @@ class Ref:
         b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64).copy()
         self.lib.amvref_fdct_islow(_p(b), b.shape[0])
         return b
+
+    def convert_range(self, y, u, v, direction):
+        """img_convert between PIX_FMT_YUV420P and PIX_FMT_YUVJ420P (tight planes [n,h,w] / [n,ch,cw])"""
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        n, h, w = y.shape
+        oy, ou, ov = np.zeros_like(y), np.zeros_like(u), np.zeros_like(v)
+        r = self.lib.amvref_convert_range(_p(y), _p(u), _p(v), n, w, h, int(direction), _p(oy), _p(ou), _p(ov))
+        if r != n:
+            raise RuntimeError("reference img_convert failed: %d" % r)
+        return oy, ou, ov
 
     # -- container (libavformat amv_muxer / avi_demuxer, driven like ffmpeg.c does)
     def mux(self, w, h, fps, sample_rate, vpk, voff, vsz, apk, aoff, asz):

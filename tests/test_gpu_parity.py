@@ -534,3 +534,34 @@ def test_sp5x_decode_golden(ctx, oracle, case):
     _, _, _, _, masks = oracle.sp5x_decode_frames(GS[case + "/pk"], GS[case + "/off"], GS[case + "/sz"], w, h, undef=True)
     for got, want, m in zip((dy, du, dv), (GS[case + "/dy"], GS[case + "/du"], GS[case + "/dv"]), masks):
         assert np.array_equal(got[m == 0], want[m == 0])
+
+
+# ------------------------------------------------------------------ range conversion
+@pytest.mark.parametrize("direction", [0, 1])
+@pytest.mark.parametrize("w,h", [(320, 240), (208, 176), (102, 56), (16, 16)])
+def test_range_conversion_identical(ctx, oracle, direction, w, h):
+    import torch
+    rng = np.random.default_rng(12)
+    cw, ch = chroma_dims(w, h)
+    n = 5
+    y = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    u = rng.integers(0, 256, (n, ch, cw), dtype=np.uint8)
+    v = rng.integers(0, 256, (n, ch, cw), dtype=np.uint8)
+    y[0].reshape(-1)[:256] = np.arange(256)
+    want = oracle.convert_range(y, u, v, direction)
+    got = ctx.convert_range(y, u, v, direction)                       # host buffers
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # device buffers, padded rows, in place
+    dev = torch.device("cuda", 0)
+    ls_y, ls_c = w + 16 - w % 16 + 16, cw + 16 - cw % 16 + 16
+    dY = torch.full((n, h, ls_y), 7, dtype=torch.uint8, device=dev); dY[:, :, :w] = torch.from_numpy(y).to(dev)
+    dU = torch.full((n, ch, ls_c), 7, dtype=torch.uint8, device=dev); dU[:, :, :cw] = torch.from_numpy(u).to(dev)
+    dV = torch.full((n, ch, ls_c), 7, dtype=torch.uint8, device=dev); dV[:, :, :cw] = torch.from_numpy(v).to(dev)
+    torch.cuda.synchronize()
+    ctx.convert_range_raw(dY, dU, dV, ls_y, ls_c, h * ls_y, ch * ls_c, n, w, h, direction, dY, dU, dV, ls_y, ls_c, h * ls_y,
+                          ch * ls_c, amv.MEM_DEVICE)
+    ctx.sync()
+    for t, ww, wn in ((dY, w, want[0]), (dU, cw, want[1]), (dV, cw, want[2])):
+        a = t.cpu().numpy()
+        assert np.array_equal(a[:, :, :ww], wn) and (a[:, :, ww:] == 7).all()

@@ -135,3 +135,18 @@ def test_sp5x_decode_matches_golden(oracle, case):
     assert (st == 0).all()
     for got, want, m in zip((y, u, v), (GS[case + "/dy"], GS[case + "/du"], GS[case + "/dv"]), masks):
         assert np.array_equal(got[m == 0], want[m == 0])
+
+
+def test_range_conversion_tables(oracle):
+    """known answers of the four tables (colorspace.h:69-84 with SCALEBITS 10): ends, mid points, clamps"""
+    v = np.arange(256, dtype=np.uint8).reshape(1, 16, 16)
+    c = np.concatenate([np.arange(0, 256, 4), np.arange(3, 256, 4)]).astype(np.uint8).reshape(1, 8, 16)
+    jy, ju, _ = oracle.convert_range(v, c, c, 0)
+    cy, cu, _ = oracle.convert_range(v, c, c, 1)
+    jy, cy = jy.reshape(-1), cy.reshape(-1)
+    assert jy[16] == 0 and jy[235] == 255 and jy[0] == 0 and jy[255] == 255 and jy[126] == 128
+    assert cy[0] == 16 and cy[255] == 235 and cy[128] == 126
+    lut_ju = dict(zip(c.reshape(-1).tolist(), ju.reshape(-1).tolist()))
+    lut_cu = dict(zip(c.reshape(-1).tolist(), cu.reshape(-1).tolist()))
+    assert lut_ju[128] == 128 and lut_ju[16] == 1 and lut_ju[240] == 255 and lut_ju[0] == 0
+    assert lut_cu[128] == 128 and lut_cu[0] == 16 and lut_cu[255] == 240

@@ -260,3 +260,19 @@ def test_sp5x_decode_identical(oracle, ref, w, h, kind):
         if kind in ("sinus", "flat"):
             assert not m.any()
     assert any(b"\xff" in sp[int(o) + 14:int(o) + int(s)].tobytes() for o, s in zip(soff, ssz)) or kind == "flat"
+
+
+# ------------------------------------------------------------------ range conversion
+@pytest.mark.parametrize("direction", [0, 1])
+def test_range_conversion_matches_img_convert(oracle, ref, direction):
+    """every byte value through both tables of both directions, plus picture shapes the reference accepts"""
+    rng = np.random.default_rng(11)
+    for (w, h) in ((32, 16), (160, 120), (208, 176)):
+        cw, ch = w // 2, h // 2
+        y = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+        u = rng.integers(0, 256, (2, ch, cw), dtype=np.uint8)
+        v = rng.integers(0, 256, (2, ch, cw), dtype=np.uint8)
+        y[0].reshape(-1)[:256] = np.arange(256)
+        u[0].reshape(-1)[:128] = np.arange(128); v[0].reshape(-1)[:128] = np.arange(128, 256)
+        for a, b in zip(ref.convert_range(y, u, v, direction), oracle.convert_range(y, u, v, direction)):
+            assert np.array_equal(a, b)
