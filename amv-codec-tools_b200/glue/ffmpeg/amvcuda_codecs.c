@@ -8,6 +8,7 @@
  * C ABI of include/amvcuda.h with n = 1.
  *
  *   amvcuda_amv_decoder            replaces amv_decoder            (sp5xdec.c:203-212)
+ *   amvcuda_sp5x_decoder           replaces sp5x_decoder           (sp5xdec.c:190-201; same callback, other framing)
  *   amvcuda_amv_encoder            replaces amv_encoder            (mjpegenc.c:485-494)
  *   amvcuda_adpcm_ima_amv_decoder  replaces adpcm_ima_amv_decoder  (adpcm.c:1535)
  *   amvcuda_adpcm_ima_amv_encoder  replaces adpcm_ima_amv_encoder  (adpcm.c:1535)
@@ -61,11 +62,14 @@ static int amvcuda_dec_frame(AVCodecContext *avctx, void *data, int *data_size, 
     if (avctx->get_buffer(avctx, &c->picture) < 0) return -1;
     c->picture.pict_type = FF_I_TYPE;
     c->picture.key_frame = 1;
-    if (amv_decode_frames(c->h, buf, (uint64_t)buf_size, &off, &size, 1, w, h,
-                          c->picture.data[0], c->picture.data[1], c->picture.data[2],
-                          c->picture.linesize[0], c->picture.linesize[1],
-                          (uint64_t)c->picture.linesize[0] * h, (uint64_t)c->picture.linesize[1] * ((h + 1) / 2),
-                          &status, AMV_MEM_HOST) != AMV_OK)
+    /* one callback serves both codecs, like sp5x_decode_frame: CODEC_ID_AMV takes the flipped, stuffed framing,
+     * CODEC_ID_SP5X the 14-byte header + literal bytes (sp5xdec.c:75-84); avcodec_open set codec_id (utils.c:862) */
+    if ((avctx->codec_id == CODEC_ID_SP5X ? amv_decode_frames_sp5x : amv_decode_frames)(
+            c->h, buf, (uint64_t)buf_size, &off, &size, 1, w, h,
+            c->picture.data[0], c->picture.data[1], c->picture.data[2],
+            c->picture.linesize[0], c->picture.linesize[1],
+            (uint64_t)c->picture.linesize[0] * h, (uint64_t)c->picture.linesize[1] * ((h + 1) / 2),
+            &status, AMV_MEM_HOST) != AMV_OK)
         return -1;
     /* scan errors are swallowed by the reference too (mjpegdec.c:1300): the picture is returned */
     *out = c->picture;
@@ -77,6 +81,11 @@ static int amvcuda_dec_frame(AVCodecContext *avctx, void *data, int *data_size, 
 
 AVCodec amvcuda_amv_decoder = {
     "amv", CODEC_TYPE_VIDEO, CODEC_ID_AMV, sizeof(AmvCudaVideoDec),
+    amvcuda_dec_init, NULL, amvcuda_dec_close, amvcuda_dec_frame,
+};
+
+AVCodec amvcuda_sp5x_decoder = {
+    "sp5x", CODEC_TYPE_VIDEO, CODEC_ID_SP5X, sizeof(AmvCudaVideoDec),
     amvcuda_dec_init, NULL, amvcuda_dec_close, amvcuda_dec_frame,
 };
 
@@ -228,6 +237,7 @@ void amvcuda_register_codecs(void)
 {
     register_avcodec(&amvcuda_amv_encoder);
     register_avcodec(&amvcuda_amv_decoder);
+    register_avcodec(&amvcuda_sp5x_decoder);
     register_avcodec(&amvcuda_adpcm_ima_amv_encoder);
     register_avcodec(&amvcuda_adpcm_ima_amv_decoder);
 }

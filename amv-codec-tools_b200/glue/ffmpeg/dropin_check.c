@@ -12,8 +12,9 @@
 #include <math.h>
 #include "avcodec.h"
 
-extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder;
-extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_decoder, amvcuda_adpcm_ima_amv_encoder;
+extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder, sp5x_decoder;
+extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_decoder, amvcuda_adpcm_ima_amv_encoder,
+               amvcuda_sp5x_decoder;
 void amvcuda_register_codecs(void);
 
 static unsigned rng_state = 12345;
@@ -114,7 +115,8 @@ int main(int argc, char **argv)
     amvcuda_register_codecs();                       /* first match wins ...                              */
     register_avcodec(&amv_encoder); register_avcodec(&amv_decoder);   /* ... then what avcodec_register_all adds */
     register_avcodec(&adpcm_ima_amv_encoder); register_avcodec(&adpcm_ima_amv_decoder);
-    if (avcodec_find_decoder(CODEC_ID_AMV) != &amvcuda_amv_decoder || avcodec_find_encoder(CODEC_ID_AMV) != &amvcuda_amv_encoder ||
+    register_avcodec(&sp5x_decoder);
+    if (avcodec_find_decoder(CODEC_ID_AMV) != &amvcuda_amv_decoder || avcodec_find_decoder(CODEC_ID_SP5X) != &amvcuda_sp5x_decoder || avcodec_find_encoder(CODEC_ID_AMV) != &amvcuda_amv_encoder ||
         avcodec_find_decoder(CODEC_ID_ADPCM_IMA_AMV) != &amvcuda_adpcm_ima_amv_decoder ||
         avcodec_find_encoder(CODEC_ID_ADPCM_IMA_AMV) != &amvcuda_adpcm_ima_amv_encoder) {
         printf("FAIL: lookup does not return the drop-in codecs\n");
@@ -140,6 +142,25 @@ int main(int argc, char **argv)
         if (ra || rb) { printf("FAIL: decode returned %d / %d\n", ra, rb); return 4; }
         if (memcmp(da, db, (size_t)n * fb)) { printf("FAIL: decoded planes differ (quality %d)\n", quality); fail = 1; }
         printf("video %dx%d x%d quality %d: packets and planes %s\n", w, h, n, quality, fail ? "DIFFER" : "identical");
+        {   /* SP5X: the same scans behind a 14-byte header with literal FF bytes (sp5xdec.c:78-84; the reference has no
+             * SP5X encoder).  Only packets whose FF count fits the reference's recode buffer (:51) are comparable. */
+            Packet *ps = calloc(n, sizeof(Packet));
+            int m = 0, j, k;
+            for (i = 0; i < n; i++) {
+                int ff = 0;
+                uint8_t *d = calloc(1, pb[i].size + 14 + FF_INPUT_BUFFER_PADDING_SIZE);
+                k = 14;
+                for (j = 2; j < pb[i].size - 2; j++) { d[k++] = pb[i].pk[j]; if (pb[i].pk[j] == 0xff) { ff++; j++; } }
+                if (ff <= 400) { ps[m].pk = d; ps[m].size = k; m++; } else free(d);
+            }
+            if (m) {
+                ra = decode_all(avcodec_find_decoder(CODEC_ID_SP5X), w, h, m, ps, da);
+                rb = decode_all(&sp5x_decoder, w, h, m, ps, db);
+                if (ra || rb) { printf("FAIL: sp5x decode returned %d / %d\n", ra, rb); return 6; }
+                if (memcmp(da, db, (size_t)m * fb)) { printf("FAIL: sp5x planes differ (quality %d)\n", quality); fail = 1; }
+            }
+            printf("sp5x  %dx%d x%d quality %d: planes %s\n", w, h, m, quality, fail ? "DIFFER" : "identical");
+        }
         free(da); free(db);
     }
     {
