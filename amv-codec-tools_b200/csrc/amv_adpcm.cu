@@ -249,6 +249,119 @@ k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// The `-trellis N` path of the reference encoder (adpcm_compress_trellis, adpcm.c:287-443, IMA branch
+// :383-395 with STORE_NODE :340-377): a beam search over decoder states with a frontier of F = 2^N nodes
+// kept sorted by accumulated squared error; candidates that decode to a sample already in the next
+// frontier are dropped, a full frontier recycles its worst node together with its path slot, and the
+// best path is frozen every 128 samples.  The search of one chunk is a chain of data-dependent
+// insertions, so the unit of parallelism stays the chunk (one thread per stream, chunks of a stream
+// chained through the step index); node pools, the sorted index lists and the F x 128 path table live
+// in per-thread local memory.  Samples are read and nibble bytes written straight from / to global
+// memory: the search, not the 3 KB of I/O per chunk, is what this kernel spends its time on.
+template <int F>
+__global__ void __launch_bounds__(128)
+k_adpcm_encode_trellis(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint64_t *__restrict__ pcm_off,
+                       const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams,
+                       const int16_t *__restrict__ step_in, int16_t *__restrict__ step_out, uint8_t *__restrict__ outb,
+                       uint64_t out_bytes, const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
+    constexpr int kFreeze = 128;
+    __shared__ uint16_t step_tab[96];
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) step_tab[i] = g_ima_step[i];
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const uint32_t c0 = first_chunk ? first_chunk[s] : (uint32_t)s, c1 = first_chunk ? first_chunk[s + 1] : (uint32_t)s + 1;
+    int idx = step_in ? step_in[s] : 0;
+    bool dead = idx < 0 || idx > 88;
+
+    struct Node { uint32_t ssd; int sample1; uint16_t path; uint8_t step; };
+    Node pool[2][F];
+    uint8_t cur[F], nxt[F];
+    uint16_t paths[F * kFreeze];            // [15:12] nibble, [11:0] previous path slot
+    uint8_t nibbuf[kFreeze];
+
+    for (uint32_t c = c0; c < c1; c++) {
+        if (dead) { status[c] = AMV_ST_RANGE; continue; }
+        const uint32_t ns = nsamples[c];
+        const uint64_t src = pcm_off[c], dst = out_off[c];
+        if ((ns & 1) || src + ns > pcm_samples || dst + 8 + ns / 2 > out_bytes) { status[c] = AMV_ST_RANGE; dead = true; continue; }
+        status[c] = 0;
+        const int prev0 = ns ? pcm[src] : 0;
+        uint8_t *h = outb + dst;
+        h[0] = (uint8_t)prev0; h[1] = (uint8_t)(prev0 >> 8);
+        h[2] = (uint8_t)idx;   h[3] = (uint8_t)(idx >> 8);
+        h[4] = (uint8_t)ns; h[5] = (uint8_t)(ns >> 8); h[6] = (uint8_t)(ns >> 16); h[7] = (uint8_t)(ns >> 24);
+        if (!ns) continue;
+        uint8_t *body = h + 8;
+
+        int ncur = 1, pathn = 0, froze = -1;
+        pool[1][0].ssd = 0; pool[1][0].path = 0; pool[1][0].step = (uint8_t)idx; pool[1][0].sample1 = prev0;
+        cur[0] = 0;
+        for (int i = 0; i < (int)ns; i++) {
+            Node *from = pool[(i & 1) ^ 1], *to = pool[i & 1];
+            const int sample = pcm[src + i];
+            int nnxt = 0, nalloc = 0;
+            for (int j = 0; j < ncur; j++) {
+                const Node p = from[cur[j]];
+                const int range = j < F / 2 ? 1 : 0;
+                const int st = step_tab[p.step];
+                const int div = (sample - p.sample1) * 4 / st;
+                int nmin = min(max(div - range, -7), 6), nmax = min(max(div + range, -6), 7);
+                if (nmin <= 0) nmin--;                                   // distinguish -0 from +0
+                if (nmax < 0) nmax--;
+                for (int nidx = nmin; nidx <= nmax; nidx++) {
+                    const int nibble = nidx < 0 ? 7 - nidx : nidx;
+                    const int mag = (st * (2 * (nibble & 7) + 1)) >> 3;  // (step * yamaha_difflookup[nibble]) / 8, magnitude part
+                    const int dec = min(max((nibble & 8) ? p.sample1 - mag : p.sample1 + mag, -32768), 32767);
+                    const int d = sample - dec;
+                    const uint32_t ssd = p.ssd + (uint32_t)d * (uint32_t)d;
+                    if (nnxt == F && ssd >= to[nxt[F - 1]].ssd) continue;
+                    bool dup = false;
+                    for (int k = 0; k < nnxt; k++) dup |= dec == to[nxt[k]].sample1;
+                    if (dup) continue;
+                    int k = 0;
+                    while (k < nnxt && ssd >= to[nxt[k]].ssd) k++;       // first slot whose node is worse
+                    int slot;
+                    if (nnxt == F) slot = nxt[F - 1];                    // recycle the evicted node and its path slot
+                    else { slot = nalloc++; to[slot].path = (uint16_t)pathn++; }
+                    to[slot].ssd = ssd;
+                    to[slot].step = (uint8_t)min(max((int)p.step + ima_index_adjust(nibble & 7), 0), 88);
+                    to[slot].sample1 = dec;
+                    paths[to[slot].path] = (uint16_t)((nibble << 12) | p.path);
+                    const int last = nnxt == F ? F - 1 : nnxt;
+                    for (int m = last; m > k; m--) nxt[m] = nxt[m - 1];
+                    nxt[k] = (uint8_t)slot;
+                    if (nnxt < F) nnxt++;
+                }
+            }
+            for (int k = 0; k < nnxt; k++) cur[k] = nxt[k];
+            ncur = nnxt;
+            if (to[cur[0]].ssd > (1u << 28)) {                           // prevent overflow
+                const uint32_t base = to[cur[0]].ssd;
+                for (int j = 1; j < ncur; j++) to[cur[j]].ssd -= base;
+                to[cur[0]].ssd = 0;
+            }
+            if (i == froze + kFreeze) {                                  // merge old paths to save memory
+                int pp = to[cur[0]].path;
+                for (int k = kFreeze - 1; k >= 0; k--) { nibbuf[k] = (uint8_t)(paths[pp] >> 12); pp = paths[pp] & 0xfff; }
+                uint8_t *o = body + ((froze + 1) >> 1);                  // froze + 1 is a multiple of 128
+                for (int k = 0; k < kFreeze / 2; k++) o[k] = (uint8_t)((nibbuf[2 * k] << 4) | nibbuf[2 * k + 1]);
+                froze = i; pathn = 0;
+                ncur = 1;                                                // "just kill them all"
+            }
+        }
+        const Node best = pool[(ns - 1) & 1][cur[0]];
+        const int rest = (int)ns - 1 - froze;                            // even: ns is even, froze + 1 a multiple of 128
+        int pp = best.path;
+        for (int k = rest - 1; k >= 0; k--) { nibbuf[k] = (uint8_t)(paths[pp] >> 12); pp = paths[pp] & 0xfff; }
+        uint8_t *o = body + ((froze + 1) >> 1);
+        for (int k = 0; k < rest / 2; k++) o[k] = (uint8_t)((nibbuf[2 * k] << 4) | nibbuf[2 * k + 1]);
+        idx = best.step;
+    }
+    if (step_out) step_out[s] = (int16_t)idx;
+}
+
+// ------------------------------------------------------------------------------------------------
 cudaError_t upload_adpcm_tables(cudaStream_t s) {
     static uint16_t h[96];
     for (int i = 0; i < 96; i++) h[i] = kImaStep[i < 89 ? i : 88];
@@ -270,7 +383,19 @@ void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uin
 
 void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
                          const uint32_t *first_chunk, int nstreams, const int16_t *step_in, int16_t *step_out,
-                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, cudaStream_t s) {
+                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, cudaStream_t s) {
+    if (trellis > 0) {
+        const int grid = (nstreams + 127) / 128;
+#define AMV_TRELLIS_CASE(T)                                                                                              \
+        case T: k_adpcm_encode_trellis<(1 << T)><<<grid, 128, 0, s>>>(pcm, pcm_samples, pcm_off, nsamples, first_chunk,   \
+                                                                      nstreams, step_in, step_out, out, out_bytes, out_off, status); break;
+        switch (trellis) {
+            AMV_TRELLIS_CASE(1) AMV_TRELLIS_CASE(2) AMV_TRELLIS_CASE(3) AMV_TRELLIS_CASE(4) AMV_TRELLIS_CASE(5)
+            default: break;
+        }
+#undef AMV_TRELLIS_CASE
+        return;
+    }
     k_adpcm_encode<<<adpcm_grid(nstreams), kAdpcmThreads, 0, s>>>(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams,
                                                                   step_in, step_out, out, out_bytes, out_off, status);
 }

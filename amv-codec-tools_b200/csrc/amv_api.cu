@@ -55,6 +55,7 @@ struct amv_ctx {
     void *pinned_meta = nullptr;
     size_t pinned_meta_cap = 0;
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
+    int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
 };
 
@@ -614,6 +615,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
+    if (!strcmp(key, "adpcm_trellis")) {
+        if (value < 0 || value > 5) return AMV_ERR_UNSUPPORTED;
+        ctx->opt_trellis = (int)value;
+        return AMV_OK;
+    }
     if (!strcmp(key, "host_zero_copy_packets")) { ctx->opt_zero_copy_packets = value != 0; return AMV_OK; }
     return AMV_ERR_UNSUPPORTED;
 }
@@ -823,7 +829,7 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * nchunks, st);
         { ScopedTimer tm(ctx, KK_ADPCM_ENC);
           launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, step_in, step_out, out, out_bytes,
-                              out_off, st, ctx->stream); }
+                              out_off, st, ctx->opt_trellis, ctx->stream); }
         return check_launch(ctx, "adpcm encode kernel");
     }
     int16_t *d_pcm; uint64_t *d_poff, *d_ooff; uint32_t *d_ns, *d_fc = nullptr; int16_t *d_si = nullptr, *d_so; uint8_t *d_out;
@@ -838,7 +844,8 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
     ENSURE(WS_H_H, out_bytes ? out_bytes : 1, d_out);
     ENSURE(WS_H_I, sizeof(int32_t) * nchunks, d_st);
     CK(cudaMemsetAsync(d_st, 0, sizeof(int32_t) * nchunks, ctx->stream));
-    launch_adpcm_encode(d_pcm, pcm_samples, d_poff, d_ns, d_fc, nstreams, d_si, d_so, d_out, out_bytes, d_ooff, d_st, ctx->stream);
+    launch_adpcm_encode(d_pcm, pcm_samples, d_poff, d_ns, d_fc, nstreams, d_si, d_so, d_out, out_bytes, d_ooff, d_st,
+                        ctx->opt_trellis, ctx->stream);
     int r = check_launch(ctx, "adpcm encode kernel");
     if (r != AMV_OK) return r;
     CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));

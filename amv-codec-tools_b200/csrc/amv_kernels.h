@@ -57,6 +57,6 @@ void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uin
                          int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s);
 void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
                          const uint32_t *first_chunk, int nstreams, const int16_t *step_in, int16_t *step_out,
-                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, cudaStream_t s);
+                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, cudaStream_t s);
 
 }  // namespace amv

@@ -163,11 +163,14 @@ static int amvcuda_adpcm_init(AVCodecContext *avctx)
 {
     AmvCudaAudio *c = avctx->priv_data;
     if (avctx->codec->encode) {                                           /* adpcm.c:190-199 */
-        if (avctx->channels != 1 || avctx->sample_rate != 22050 || avctx->trellis > 0) return -1;
+        if (avctx->channels != 1 || avctx->sample_rate != 22050 || avctx->trellis < 0 || avctx->trellis > 5) return -1;
         avctx->coded_frame = &c->coded;
         c->coded.key_frame = 1;
     } else if (avctx->channels > 2) return -1;
-    return amv_create(NULL, &c->h) == AMV_OK ? 0 : -1;
+    if (amv_create(NULL, &c->h) != AMV_OK) return -1;
+    /* -trellis N selects adpcm_compress_trellis in the reference (adpcm.c:481-488); same switch here */
+    if (avctx->codec->encode && avctx->trellis > 0 && amv_set_option(c->h, "adpcm_trellis", avctx->trellis) != AMV_OK) return -1;
+    return 0;
 }
 
 static int amvcuda_adpcm_close(AVCodecContext *avctx)

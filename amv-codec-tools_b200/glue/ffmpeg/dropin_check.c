@@ -80,6 +80,7 @@ static int decode_all(AVCodec *codec, int w, int h, int n, Packet *pk, uint8_t *
     return 0;
 }
 
+static int g_trellis;
 static int audio_roundtrip(AVCodec *enc, AVCodec *dec, const int16_t *pcm, int total, int frame_size,
                            uint8_t *chunks, int *chunk_bytes, int16_t *out_pcm, int *out_samples)
 {
@@ -87,7 +88,7 @@ static int audio_roundtrip(AVCodec *enc, AVCodec *dec, const int16_t *pcm, int t
     int pos = 0, cb = 0, os = 0;
     uint8_t buf[FF_MIN_BUFFER_SIZE + 65536];
     int16_t *tmp = av_malloc(AVCODEC_MAX_AUDIO_FRAME_SIZE * 2);
-    e->channels = 1; e->sample_rate = 22050; e->frame_size = frame_size;
+    e->channels = 1; e->sample_rate = 22050; e->frame_size = frame_size; e->trellis = g_trellis;
     d->channels = 1; d->sample_rate = 22050;
     if (avcodec_open(e, enc) < 0 || avcodec_open(d, dec) < 0) return -1;
     e->frame_size = frame_size;
@@ -163,7 +164,7 @@ int main(int argc, char **argv)
         }
         free(da); free(db);
     }
-    {
+    for (g_trellis = 0; g_trellis <= 3; g_trellis += 3) {      /* plain encoder, then -trellis 3 */
         const int total = 22050 * 2 + 999, fs = 1378;
         int16_t *pcm = malloc(total * 2), *oa = malloc(total * 4), *ob = malloc(total * 4);
         uint8_t *ca = malloc(total), *cb = malloc(total);
@@ -174,7 +175,7 @@ int main(int argc, char **argv)
         int rb = audio_roundtrip(&adpcm_ima_amv_encoder, &adpcm_ima_amv_decoder, pcm, total, fs, cb, &cbb, ob, &sb);
         if (ra || rb) { printf("FAIL: audio returned %d / %d\n", ra, rb); return 5; }
         if (cba != cbb || memcmp(ca, cb, cba) || sa != sb || memcmp(oa, ob, sa * 2)) { printf("FAIL: audio differs\n"); fail = 1; }
-        printf("audio %d samples: %d chunk bytes, %d decoded samples %s\n", total, cba, sa, fail ? "DIFFER" : "identical");
+        printf("audio %d samples (trellis %d): %d chunk bytes, %d decoded samples %s\n", total, g_trellis, cba, sa, fail ? "DIFFER" : "identical");
     }
     printf(fail ? "DROP-IN CHECK FAILED\n" : "DROP-IN CHECK OK\n");
     return fail;

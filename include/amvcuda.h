@@ -105,7 +105,11 @@ AMV_API void        amv_host_free(void *p);
  *   "decode_log2_lanes"            0..5: decode lanes (subsequences) per frame = 1 << value; -1 = from batch size
  *   "encode_slot_workspace_bytes"  cap of the packed-layout staging workspace (frames are sub-batched to fit)
  *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream
- *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose) */
+ *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose)
+ *   "host_zero_copy_packets"       0 = DMA pinned decoder input into a device copy instead of reading it in place
+ * One option DOES select an algorithm, like the reference's AVCodecContext.trellis does:
+ *   "adpcm_trellis"                0 (default) = adpcm_ima_compress_sample (adpcm.c:219-227);
+ *                                  1..5 = the -trellis N beam search (adpcm_compress_trellis, adpcm.c:287-443) */
 AMV_API int         amv_set_option(amv_ctx *ctx, const char *key, int64_t value);
 /* "decode_sync_rounds": rounds the last multi-lane decode needed to self-synchronise (max over warps)
  * "<k>_kernel_launches", then "<k>_kernel_ns" (k = encode|idct|idct_bgr|tokens|unstuff|sync|compact|adpcm_dec|adpcm_enc):

@@ -677,6 +677,94 @@ AMVO_API int amvo_adpcm_encode_chunk(const int16_t *pcm, uint32_t nsamples, int 
     return 8 + (int)(nsamples >> 1);
 }
 
+/* The `-trellis N` path of the same encoder: adpcm_compress_trellis (adpcm.c:287-443, IMA branch :383-395 with
+ * STORE_NODE :340-377) -- a beam search over the decoder states with a frontier of 2^N nodes kept sorted by
+ * accumulated squared error, states with the same decoded sample collapsed, the best path frozen every 128 samples.
+ * Restated with explicit arrays: `ord` is the sorted frontier (indices into the node pool of the current step), the
+ * pool of a step has `frontier` slots and evicted nodes are recycled together with their path slot, exactly like
+ * the reference recycles `nodes_next[frontier-1]`.  trellis 1..5. */
+typedef struct { uint32_t ssd; int path, sample1, step; } tnode;
+AMVO_API int amvo_adpcm_encode_chunk_trellis(const int16_t *pcm, uint32_t nsamples, int step_index_in, int trellis,
+                                             uint8_t *out, int *step_index_out)
+{
+    static const int8_t difflookup[16] = { 1, 3, 5, 7, 9, 11, 13, 15, -1, -3, -5, -7, -9, -11, -13, -15 };
+    if ((nsamples & 1) || step_index_in < 0 || step_index_in > 88 || trellis < 1 || trellis > 5) return -1;
+    enum { FREEZE = 128, FMAX = 32 };
+    const int frontier = 1 << trellis;
+    const int prev0 = nsamples ? pcm[0] : 0;
+    out[0] = (uint8_t)prev0; out[1] = (uint8_t)(prev0 >> 8);
+    out[2] = (uint8_t)step_index_in; out[3] = (uint8_t)(step_index_in >> 8);
+    out[4] = (uint8_t)nsamples; out[5] = (uint8_t)(nsamples >> 8); out[6] = (uint8_t)(nsamples >> 16); out[7] = (uint8_t)(nsamples >> 24);
+    uint8_t *nib = (uint8_t *)malloc(nsamples + 1);
+    static tnode pool[2][FMAX];
+    static struct { uint8_t nibble; int prev; } paths[FMAX * FREEZE];
+    int cur[FMAX], nxt[FMAX], ncur = 1, pathn = 0, froze = -1;         /* sorted frontiers: slots of pool[(i-1)&1] / pool[i&1] */
+    pool[1][0].ssd = 0; pool[1][0].path = 0; pool[1][0].step = step_index_in; pool[1][0].sample1 = prev0;
+    cur[0] = 0;
+    for (int i = 0; i < (int)nsamples; i++) {
+        tnode *from = pool[(i & 1) ^ 1], *to = pool[i & 1];
+        const int sample = pcm[i];
+        int nnxt = 0, nalloc = 0;
+        for (int j = 0; j < ncur; j++) {
+            const tnode *p = &from[cur[j]];
+            const int range = j < frontier / 2 ? 1 : 0;
+            const int st = kImaStep[p->step];
+            const int div = (sample - p->sample1) * 4 / st;
+            int nmin = clampi(div - range, -7, 6), nmax = clampi(div + range, -6, 7);
+            if (nmin <= 0) nmin--;                                   /* distinguish -0 from +0 */
+            if (nmax < 0) nmax--;
+            for (int nidx = nmin; nidx <= nmax; nidx++) {
+                const int nibble = nidx < 0 ? 7 - nidx : nidx;
+                const int dec = clampi(p->sample1 + (st * difflookup[nibble]) / 8, -32768, 32767);
+                const int d = sample - dec;
+                const uint32_t ssd = p->ssd + (uint32_t)d * (uint32_t)d;
+                if (nnxt == frontier && ssd >= to[nxt[frontier - 1]].ssd) continue;
+                int k, dup = 0;
+                for (k = 0; k < nnxt; k++) if (dec == to[nxt[k]].sample1) { dup = 1; break; }
+                if (dup) continue;
+                for (k = 0; k < frontier; k++) {
+                    if (k >= nnxt || ssd < to[nxt[k]].ssd) {
+                        int slot;
+                        if (nnxt == frontier) slot = nxt[frontier - 1];              /* recycle the evicted node and its path slot */
+                        else { slot = nalloc++; to[slot].path = pathn++; }
+                        to[slot].ssd = ssd;
+                        to[slot].step = clampi(p->step + kImaIdxAdj[nibble & 7], 0, 88);
+                        to[slot].sample1 = dec;
+                        paths[to[slot].path].nibble = (uint8_t)nibble;
+                        paths[to[slot].path].prev = p->path;
+                        const int last = nnxt == frontier ? frontier - 1 : nnxt;    /* memmove(&next[k+1], &next[k], ...) */
+                        for (int m = last; m > k; m--) nxt[m] = nxt[m - 1];
+                        nxt[k] = slot;
+                        if (nnxt < frontier) nnxt++;
+                        break;
+                    }
+                }
+            }
+        }
+        memcpy(cur, nxt, sizeof(cur)); ncur = nnxt;
+        tnode *now = to;
+        if (now[cur[0]].ssd > (1u << 28)) {                               /* prevent overflow */
+            for (int j = 1; j < ncur; j++) now[cur[j]].ssd -= now[cur[0]].ssd;
+            now[cur[0]].ssd = 0;
+        }
+        if (i == froze + FREEZE) {                                        /* merge old paths to save memory */
+            int pp = now[cur[0]].path;
+            for (int k = i; k > froze; k--) { nib[k] = paths[pp].nibble; pp = paths[pp].prev; }
+            froze = i; pathn = 0;
+            ncur = 1;                                                     /* "just kill them all" */
+        }
+    }
+    const tnode *best = &pool[(nsamples - 1) & 1][cur[0]];
+    if (nsamples) {
+        int pp = best->path;
+        for (int i = (int)nsamples - 1; i > froze; i--) { nib[i] = paths[pp].nibble; pp = paths[pp].prev; }
+    }
+    for (uint32_t i = 0; i < nsamples / 2; i++) out[8 + i] = (uint8_t)((nib[2 * i] << 4) | nib[2 * i + 1]);
+    if (step_index_out) *step_index_out = nsamples ? best->step : step_index_in;
+    free(nib);
+    return 8 + (int)(nsamples >> 1);
+}
+
 /* How many samples (2n) the reference encoder puts in the next chunk
  * (adpcm.c:468-477): host-side bookkeeping of the AVCodec shim. */
 AMVO_API uint32_t amvo_adpcm_next_chunk_samples(int frame_size, int sample_rate,

@@ -167,9 +167,20 @@ done:
  * encoder wrote into the chunk header (bytes 4..7); the harness advances by
  * that (ffmpeg.c itself advances by frame_size -- SURVEY §9.10).
  * Returns number of chunks written. consumed[i] = samples consumed by chunk i. */
+int amvref_adpcm_encode_stream_trellis(const int16_t *pcm, uint64_t total_samples, int frame_size, int trellis,
+                                       uint8_t *out, uint64_t *off, uint32_t *size,
+                                       uint32_t *consumed, int max_chunks, uint64_t cap);
 int amvref_adpcm_encode_stream(const int16_t *pcm, uint64_t total_samples, int frame_size,
                                uint8_t *out, uint64_t *off, uint32_t *size,
                                uint32_t *consumed, int max_chunks, uint64_t cap)
+{
+    return amvref_adpcm_encode_stream_trellis(pcm, total_samples, frame_size, 0, out, off, size, consumed, max_chunks, cap);
+}
+
+/* trellis > 0: the `-trellis N` path of the same encoder (adpcm_compress_trellis, adpcm.c:287-443) */
+int amvref_adpcm_encode_stream_trellis(const int16_t *pcm, uint64_t total_samples, int frame_size, int trellis,
+                                       uint8_t *out, uint64_t *off, uint32_t *size,
+                                       uint32_t *consumed, int max_chunks, uint64_t cap)
 {
     ref_init();
     AVCodecContext *c = avcodec_alloc_context();
@@ -177,6 +188,7 @@ int amvref_adpcm_encode_stream(const int16_t *pcm, uint64_t total_samples, int f
     uint64_t pos = 0, opos = 0;
     uint8_t *buf = av_malloc(FF_MIN_BUFFER_SIZE + 4 * frame_size + 65536);
     c->channels = 1; c->sample_rate = 22050; c->frame_size = frame_size;
+    c->trellis = trellis;
     if (avcodec_open(c, &adpcm_ima_amv_encoder) < 0) { k = -2; goto done; }
     c->frame_size = frame_size;
     while (k < max_chunks && pos + 2 * (uint64_t)frame_size + 2 <= total_samples) {

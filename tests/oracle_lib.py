@@ -218,6 +218,24 @@ class Oracle(_AmvlibOracleMixin):
                                           _p(np.ascontiguousarray(size, np.uint32)), n, _p(pcm), _p(poff), _p(st))
         return pcm, poff, st
 
+    def adpcm_encode_trellis(self, pcm, pcm_off, nsamples, step_in, trellis):
+        """chunks encoded independently with the -trellis N beam search (adpcm.c:287-443)"""
+        n = len(nsamples)
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        osz = 8 + np.asarray(nsamples, np.uint64) // 2
+        ooff = offsets_of(osz)
+        out = np.zeros(int(osz.sum()), np.uint8)
+        step_out = np.zeros(n, np.int16)
+        for i in range(n):
+            so = C.c_int(0)
+            a, m = int(pcm_off[i]), int(nsamples[i])
+            r = self.lib.amvo_adpcm_encode_chunk_trellis(_p(pcm[a:a + m].copy()), m, int(step_in[i]), int(trellis),
+                                                         _p(out[int(ooff[i]):]), C.byref(so))
+            if r != int(osz[i]):
+                raise RuntimeError("oracle trellis encode failed: %d" % r)
+            step_out[i] = so.value
+        return out, ooff, osz.astype(np.uint32), step_out
+
     def adpcm_encode(self, pcm, pcm_off, nsamples, step_in):
         n = len(nsamples)
         nsamples = np.ascontiguousarray(nsamples, np.uint32)
@@ -325,7 +343,7 @@ class Ref:
             raise RuntimeError("reference adpcm decode failed: %d" % r)
         return pcm, poff, nsamp
 
-    def adpcm_encode_stream(self, pcm, frame_size, max_chunks=1 << 20):
+    def adpcm_encode_stream(self, pcm, frame_size, max_chunks=1 << 20, trellis=0):
         pcm = np.ascontiguousarray(pcm, np.int16)
         cap = len(pcm) + 16 * (len(pcm) // max(frame_size, 1) + 4) + 65536
         out = np.zeros(cap, np.uint8)
@@ -333,8 +351,8 @@ class Ref:
         off = np.zeros(mc, np.uint64)
         size = np.zeros(mc, np.uint32)
         cons = np.zeros(mc, np.uint32)
-        k = self.lib.amvref_adpcm_encode_stream(_p(pcm), C.c_uint64(len(pcm)), int(frame_size), _p(out), _p(off),
-                                                _p(size), _p(cons), mc, C.c_uint64(cap))
+        k = self.lib.amvref_adpcm_encode_stream_trellis(_p(pcm), C.c_uint64(len(pcm)), int(frame_size), int(trellis), _p(out),
+                                                        _p(off), _p(size), _p(cons), mc, C.c_uint64(cap))
         if k < 0:
             raise RuntimeError("reference adpcm encode failed: %d" % k)
         return out[: int(size[:k].sum())].copy(), off[:k], size[:k], cons[:k]

@@ -565,3 +565,48 @@ def test_range_conversion_identical(ctx, oracle, direction, w, h):
     for t, ww, wn in ((dY, w, want[0]), (dU, cw, want[1]), (dV, cw, want[2])):
         a = t.cpu().numpy()
         assert np.array_equal(a[:, :, :ww], wn) and (a[:, :, ww:] == 7).all()
+
+
+# ------------------------------------------------------------------ ADPCM -trellis N
+@pytest.mark.parametrize("trellis", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kind", ["tones", "noise", "square"])
+def test_adpcm_trellis_vs_oracle(ctx, oracle, kind, trellis):
+    """option adpcm_trellis = N: independent chunks (ragged lengths, start states) and chained streams"""
+    rng = np.random.default_rng(41)
+    ns = np.array([1378, 1378, 2, 0, 130, 256, 258, 4000, 64, 1378] * 4, np.uint32)
+    pcm = synth_pcm(int(ns.sum()), seed=42, kind=kind)
+    poff = offsets_of(ns)
+    step_in = rng.integers(0, 89, len(ns)).astype(np.int16)
+    ctx.set_option("adpcm_trellis", trellis)
+    try:
+        eo, eoff, esz, so, st = ctx.adpcm_encode(pcm, poff, ns, step_in)
+        first = np.array([0, 7, 8, 20, len(ns)], np.uint32)
+        co, coff, csz, cso, cst = ctx.adpcm_encode_streams(pcm, poff, ns, first, step_in[:4])
+    finally:
+        ctx.set_option("adpcm_trellis", 0)
+    wo, woff, wsz, wso = oracle.adpcm_encode_trellis(pcm, poff, ns, step_in, trellis)
+    assert (st == 0).all() and np.array_equal(esz, wsz) and np.array_equal(eo, wo) and np.array_equal(so, wso)
+    # chained: the state after a chunk feeds the next chunk of its stream
+    want = np.zeros_like(co)
+    for sidx in range(4):
+        state = int(step_in[sidx])
+        for c in range(int(first[sidx]), int(first[sidx + 1])):
+            o1, _, _, s1 = oracle.adpcm_encode_trellis(pcm, poff[c:c + 1], ns[c:c + 1], np.array([state], np.int16), trellis)
+            want[int(coff[c]):int(coff[c]) + len(o1)] = o1
+            state = int(s1[0])
+        assert int(cso[sidx]) == state
+    assert (cst == 0).all() and np.array_equal(co, want)
+
+
+@pytest.mark.parametrize("case", sorted(set(k.split("/")[0] for k in np.load(os.path.join(os.path.dirname(__file__), "golden", "adpcm_trellis_golden.npz")).files)))
+def test_adpcm_trellis_golden(ctx, case):
+    GT = np.load(os.path.join(os.path.dirname(__file__), "golden", "adpcm_trellis_golden.npz"))
+    trellis = int(case[1])
+    out, off, sz, cons = (GT[case + "/" + k] for k in ("out", "off", "sz", "cons"))
+    first = np.array([0, len(cons)], np.uint32)
+    ctx.set_option("adpcm_trellis", trellis)
+    try:
+        eo, _, esz, _, st = ctx.adpcm_encode_streams(GT[case + "/src"], offsets_of(cons), cons, first, np.zeros(1, np.int16))
+    finally:
+        ctx.set_option("adpcm_trellis", 0)
+    assert (st == 0).all() and np.array_equal(esz, sz) and np.array_equal(eo, out)

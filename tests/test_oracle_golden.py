@@ -150,3 +150,17 @@ def test_range_conversion_tables(oracle):
     lut_cu = dict(zip(c.reshape(-1).tolist(), cu.reshape(-1).tolist()))
     assert lut_ju[128] == 128 and lut_ju[16] == 1 and lut_ju[240] == 255 and lut_ju[0] == 0
     assert lut_cu[128] == 128 and lut_cu[0] == 16 and lut_cu[255] == 240
+
+
+# ------------------------------------------------------------------ ADPCM -trellis N
+GT = np.load(os.path.join(os.path.dirname(__file__), "golden", "adpcm_trellis_golden.npz"))
+TRELLIS_CASES = sorted(set(k.split("/")[0] for k in GT.files))
+
+
+@pytest.mark.parametrize("case", TRELLIS_CASES)
+def test_adpcm_trellis_matches_golden(oracle, case):
+    trellis = int(case[1])
+    out, off, sz, cons = (GT[case + "/" + k] for k in ("out", "off", "sz", "cons"))
+    step_in = np.array([int(out[int(o) + 2]) | (int(out[int(o) + 3]) << 8) for o in off], np.int16)
+    eo, _, esz, _ = oracle.adpcm_encode_trellis(GT[case + "/src"], offsets_of(cons), cons, step_in, trellis)
+    assert np.array_equal(esz, sz) and np.array_equal(eo, out)

@@ -276,3 +276,28 @@ def test_range_conversion_matches_img_convert(oracle, ref, direction):
         u[0].reshape(-1)[:128] = np.arange(128); v[0].reshape(-1)[:128] = np.arange(128, 256)
         for a, b in zip(ref.convert_range(y, u, v, direction), oracle.convert_range(y, u, v, direction)):
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ ADPCM -trellis N
+@pytest.mark.parametrize("trellis", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kind", ["tones", "noise", "square", "silence"])
+def test_adpcm_trellis_matches_reference(oracle, ref, kind, trellis):
+    """the reference encoder with avctx->trellis = N (adpcm_compress_trellis) against the oracle's restatement of
+    the beam search, chunk by chunk with the step index chained like the reference chains it"""
+    pcm = synth_pcm(1378 * 5 + 100, seed=31, kind=kind)
+    out, off, size, cons = ref.adpcm_encode_stream(pcm, 1378, trellis=trellis)
+    assert len(size) >= 4
+    pos = 0
+    for i in range(len(size)):
+        chunk = out[int(off[i]):int(off[i]) + int(size[i])]
+        step_in = int(chunk[2]) | (int(chunk[3]) << 8)
+        mine, _, _, so = oracle.adpcm_encode_trellis(pcm, np.array([pos], np.uint64), np.array([cons[i]], np.uint32),
+                                                     np.array([step_in], np.int16), trellis)
+        assert np.array_equal(mine, chunk)
+        if i + 1 < len(size):
+            nxt = out[int(off[i + 1]):]
+            assert int(so[0]) == (int(nxt[2]) | (int(nxt[3]) << 8))
+        pos += int(cons[i])
+    # and the decoder reads it back (any trellis output is an ordinary chunk)
+    dp, _, st = oracle.adpcm_decode(out, off, size)
+    assert (st == 0).all() and len(dp) == int(cons.sum())
