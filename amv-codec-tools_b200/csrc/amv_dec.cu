@@ -401,28 +401,49 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 // scan byte and a lane that starts at bit s writes from token s/2 (+4 per lane of slack for 16-byte
 // alignment) without ever meeting its neighbour.
 //
-// The symbol loop is the serial heart of the decoder, so it is written for issue slots:
-//  * bits come from a per-lane 16-word ring in shared memory ([word][lane], conflict-free) that is
-//    topped up with one 128-bit global load per lane at BLOCK boundaries, where the warp is
-//    converged: the load issued at one boundary is parked in registers and stored to the ring at
-//    the next, so its latency never sits inside the divergent symbol loop (a load into a register
-//    that other lanes still have in flight would stall the whole warp there);
-//  * one table lookup per symbol (byte-field entries, explicit shared-memory addresses), then
-//    straight-line field extraction, JPEG sign extension and token assembly -- no per-symbol
-//    divergence except EOB/ZRL/second-level codes;
-//  * tokens collect four at a time in registers and leave as 16-byte stores.
+// The symbol loop is the serial heart of the decoder.  It is FLAT: one iteration = one Huffman
+// symbol of whatever kind, for every lane that still has blocks left, so lanes never wait for the
+// longest block of the warp (the block-structured first version ran with 20 of 32 lanes active):
+//  * DC and AC symbols share the code path.  A block starts with k = -1; every table entry says by
+//    how much k advances (DC 1, coefficient run+1, ZRL 16, EOB 128), the dequant table at k = 0
+//    holds the DC quantiser, the DC predictor is added under a select, and "k >= 63" ends the block.
+//    The only per-block work is a short tail (offset entry, next block's tables from a 6-entry
+//    shared table, predictor rotation Y -> Cb -> Cr -> Y).
+//  * bits come from a per-lane 16-word ring in shared memory ([word][lane], conflict-free, 2 KB
+//    aligned per warp so a slot address is one LOP3) and are looked at through one funnel shift of
+//    two ring words; the ring is topped up with one 128-bit global load per lane at warp-uniform
+//    service points every kTokPeriod symbols (<= 124 bits), the load issued at one service point
+//    being stored at the next, so its latency never sits inside the symbol code and the window
+//    needs no "ring ran dry" branch;
+//  * one 12-bit (AC) / 10-bit (DC) first-level lookup per symbol, byte-field entries; longer codes
+//    (2 % of the symbols with 10 bits, < 0.3 % with 12) take a second lookup;
+//  * tokens are staged in an 8-slot per-lane shared ring and leave as 16-byte stores at the
+//    service points.
 // ------------------------------------------------------------------------------------------------
-__device__ FastVlcTables g_fast_vlc;
+__device__ FlatVlcTables g_flat_vlc;
 
-constexpr int kTokThreads = 128;
+constexpr int kTokThreads = 256;
+constexpr int kTokWarps = kTokThreads / 32;
 constexpr int kRingWords = 16;
+constexpr int kTokStage = 8;          // staged tokens per lane
+constexpr int kTokPeriod = 4;         // symbols between two service points
+// flag on the dequant entries of zigzag positions past 63, in a bit that reaches neither the product nor the token
+constexpr uint32_t kTzErr = 1u << 15, kTzErrAmvlib = 1u << 16;
 
 struct TokSmem {
-    uint32_t lut[kVlcMaxEntries];
-    uint32_t tz[2][64];          // zigzag position -> (consumer column byte offset << 16) | quantiser
-    uint32_t ring[kTokThreads / 32][kRingWords * 32];
-    uint32_t tstage[kTokThreads / 32][4 * 32];      // [slot][lane]: four tokens per lane waiting for their 16-byte store
+    uint32_t ring[kTokWarps][kRingWords * 32];     // 2 KB per warp, 2 KB aligned
+    uint32_t tstage[kTokWarps][kTokStage * 32];    // 1 KB per warp, 1 KB aligned
+    uint32_t tz[2][128];                           // kb = zigzag position + 1 -> (consumer column byte offset << 16) | quantiser; 512 B aligned
+    uint4    bstate[8];                            // per block-in-MCU: DC table, AC table, dequant table, next entry | predictor rotation
+    uint32_t lut[kFlatMaxEntries];
 };
+constexpr size_t kTokSmemBytes = sizeof(TokSmem) + 2048;
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
 
 template <int FLAVOR>
 __global__ void __launch_bounds__(kTokThreads)
@@ -430,27 +451,40 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
              const LaneStart *__restrict__ starts, int nblk, uint32_t *__restrict__ tokens,
              uint32_t *__restrict__ blk_off, int32_t *__restrict__ status) {
-    __shared__ TokSmem S;
-    for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) S.lut[i] = g_fast_vlc.e[i];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x)
-        (&S.tz[0][0])[i] = FLAVOR == kFlavorAmvlib ? (&g_dec_tables.adq.tz[0][0])[i] : (&g_dec_tables.dq.tz[0][0])[i];
+    extern __shared__ uint8_t tok_smem_raw[];
+    const uint32_t raw_s = smem_addr(tok_smem_raw);
+    TokSmem &S = *reinterpret_cast<TokSmem *>(tok_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
+    const int nlut = g_flat_vlc.count;
+    for (int i = threadIdx.x; i < nlut; i += blockDim.x) S.lut[i] = g_flat_vlc.e[i];
+    {   // dequant table indexed by kb; positions past 64 (only broken streams get there) alias the last one
+        const int c = threadIdx.x >> 7, kb = threadIdx.x & 127, kk = kb == 0 ? 0 : (kb > 64 ? 63 : kb - 1);
+        const uint32_t z = FLAVOR == kFlavorAmvlib ? g_dec_tables.adq.tz[c][kk] : g_dec_tables.dq.tz[c][kk];
+        S.tz[c][kb] = z | (kb > 64 ? (FLAVOR == kFlavorAmvlib ? kTzErrAmvlib : kTzErr) : 0u);
+    }
+    const uint32_t lut_s = smem_addr(S.lut);
+    const uint32_t bstate_s = smem_addr(&S.bstate[0]);
+    if (threadIdx.x < 6) {
+        // block b of the MCU (Y Y Y Y Cb Cr): its tables, the entry of the block after it, and whether the
+        // component changes on entering it
+        const uint32_t bq = threadIdx.x, tq = bq >= 4 ? 1 : 0;
+        uint4 bs;
+        bs.x = ((lut_s + (uint32_t)g_flat_vlc.base[tq] * 4u) << 8) | (32u - kFlatDcBits);
+        bs.y = ((lut_s + (uint32_t)g_flat_vlc.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | ((bq == 0 || bq >= 4) ? 0x80u : 0u);
+        bs.z = smem_addr(&S.tz[tq][0]);
+        bs.w = bstate_s + (bq == 5 ? 0u : bq + 1u) * 16u;
+        S.bstate[bq] = bs;
+    }
     __syncthreads();
     const int P = 1 << log2p;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (int)(gt >> log2p);
     const int p = (int)(gt & (P - 1));
-    const uint32_t lut_s = smem_addr(S.lut);
-    const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: + w*128
-    const uint32_t tz_s = smem_addr(&S.tz[0][0]);
-    const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: + c*128
-    const uint32_t dc_base[2] = { (uint32_t)g_fast_vlc.base[0], (uint32_t)g_fast_vlc.base[1] };
-    const uint32_t ac_base[2] = { (uint32_t)g_fast_vlc.base[2], (uint32_t)g_fast_vlc.base[3] };
-    const int q0l = FLAVOR == kFlavorAmvlib ? (int)(g_dec_tables.adq.tz[0][0] & 0xff) : (int)(g_dec_tables.dq.zq[0][0] >> 8);
-    const int q0c = FLAVOR == kFlavorAmvlib ? (int)(g_dec_tables.adq.tz[1][0] & 0xff) : (int)(g_dec_tables.dq.zq[1][0] >> 8);
+    const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
+    const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: | (c & 7) << 7
     constexpr int kPred0 = FLAVOR == kFlavorAmvlib ? 0 : 1024;   // last_dc (mjpegdec.c:805-806) / ycoef.. (AmvJpeg.c:1510)
 
-    // ---- lane set-up (inactive lanes keep count = 0 and fall through the loops)
+    // ---- lane set-up (inactive lanes keep count = 0 and never enter the symbol code)
     uint32_t count = 0, first = 0, bit = 0, U = 0, st = 0;
     int pred0 = kPred0, pred1 = kPred0, pred2 = kPred0;
     const uint32_t *words = nullptr;
@@ -478,161 +512,148 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             }
         }
     }
-    // token output: groups of four 32-bit tokens (16 bytes) inside the frame's region
-    const uint32_t tok_cap = cap_words * 16u;                               // tokens in the region (16 B per scan byte)
-    uint32_t tok_idx = ((bit >> 1) + 4u * (uint32_t)p + 3u) & ~3u;          // first token index of this lane (multiple of 4)
+    // token output: the lane's tokens are numbered from 0 and live at tok_first + number inside the
+    // frame's region (16 B per scan byte); they leave in groups of four (16-byte stores)
+    const uint32_t tok_cap = cap_words * 16u;
+    uint32_t tok_first = ((bit >> 1) + 4u * (uint32_t)p + 3u) & ~3u;
     uint32_t *tok_frame = tokens + so * 4;
-    uint32_t tcount = 0;                    // tokens staged (byte offset form: 0, 128, 256, 384)
-    uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;
-
-    // ---- bit source: absolute bit position + shared-memory ring; every symbol looks at the 32 bits
-    // starting at `bp` through one funnel shift of two ring words (a symbol is at most 26 bits), so
-    // there is no accumulator to refill and no divergent refill branch inside the symbol loop
-    uint32_t bp = bit;                      // next unread bit of the scan
-    uint32_t wr = (bit >> 5) & ~3u;         // next word the ring receives (16-byte groups); ring = words [wr-16, wr)
-    uint4 pend = make_uint4(0, 0, 0, 0);
-    bool have_pend = false;
-    auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
-        if (w + 4 <= cap_words) return __ldg(reinterpret_cast<const uint4 *>(words + w));
-        return make_uint4(0, 0, 0, 0);
-    };
-    auto ring_put = [&](uint32_t w, const uint4 &q) {
-        sts32(ring_s + ((w + 0) & (kRingWords - 1)) * 128, bswap32(q.x));
-        sts32(ring_s + ((w + 1) & (kRingWords - 1)) * 128, bswap32(q.y));
-        sts32(ring_s + ((w + 2) & (kRingWords - 1)) * 128, bswap32(q.z));
-        sts32(ring_s + ((w + 3) & (kRingWords - 1)) * 128, bswap32(q.w));
-    };
-    if (count) {
-        ring_put(wr, load_group(wr));
-        ring_put(wr + 4, load_group(wr + 4));
-        wr += 8;
-        pend = load_group(wr);
-        have_pend = true;
-    }
-    auto window = [&]() -> uint32_t {       // the 32 bits at bp
-        const uint32_t w = bp >> 5;
-        uint32_t a, c;
-        if (w + 2 <= wr) {
-            a = lds32(ring_s + ((w & (kRingWords - 1)) << 7));
-            c = lds32(ring_s + (((w + 1) & (kRingWords - 1)) << 7));
-        } else {                            // ring ran dry inside a huge block: straight from memory
-            a = w < cap_words ? bswap32(__ldg(words + w)) : 0u;
-            c = w + 1 < cap_words ? bswap32(__ldg(words + w + 1)) : 0u;
-        }
-        return __funnelshift_l(c, a, bp & 31);
-    };
+    uint32_t flushed = 0, blk0 = 0;
+    uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;       // the lane's (count, offset) entries
+    uint32_t bi = 0;                                                           // blocks finished
     // Bounds are checked once per block, not per store: a block yields at most 66 tokens, so a lane whose
-    // next group lies within kTokBlockRoom of the end of its frame's region (only streams that are already
+    // next token lies within kTokBlockRoom of the end of its frame's region (only streams that are already
     // broken get there: a sound block of b bits has at most b/2 tokens) is flagged and parked on the
     // region's tail, where its remaining blocks overwrite each other -- memory-safe, and every block still
     // gets a valid (count, offset) entry for the consumer.
     constexpr uint32_t kTokBlockRoom = 80;
     const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~3u;    // tok_cap >= 320 (kSlotPad)
-    auto flush4 = [&]() {
-        const uint4 q = make_uint4(lds32(tst_s), lds32(tst_s + 128), lds32(tst_s + 256), lds32(tst_s + 384));
-        *reinterpret_cast<uint4 *>(tok_frame + tok_idx) = q;
-        tok_idx += 4;
-        tcount = 0;
+
+    // ---- bit source
+    uint32_t bp = bit;                      // next unread bit of the scan
+    uint32_t wr = (bit >> 5) & ~3u;         // next word the ring receives (16-byte groups); ring = words [wr-16, wr)
+    uint4 pend = make_uint4(0, 0, 0, 0);    // the group at wr, requested at the previous service point
+    auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
+        if (w + 4 <= cap_words) return __ldg(reinterpret_cast<const uint4 *>(words + w));
+        return make_uint4(0, 0, 0, 0);
     };
-    auto push = [&](uint32_t tok) {        // append one 32-bit token
-        sts32(tst_s + tcount, tok);
-        tcount += 128;
-        if (tcount == 512) flush4();
+    auto ring_put = [&](uint32_t w, const uint4 &q) {   // w is a multiple of 4
+        const uint32_t a = ring_s | ((w << 7) & 0x780u);
+        sts32(a, bswap32(q.x)); sts32(a + 128, bswap32(q.y)); sts32(a + 256, bswap32(q.z)); sts32(a + 384, bswap32(q.w));
+    };
+    auto flush_group = [&]() {
+        const uint32_t a = tst_s | ((flushed << 7) & 0x200u);
+        const uint4 q = make_uint4(lds32(a), lds32(a + 128), lds32(a + 256), lds32(a + 384));
+        *reinterpret_cast<uint4 *>(tok_frame + (tok_first + flushed)) = q;
+        flushed += 4;
     };
 
-    uint32_t maxcount = count;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, d));
-    int b = (int)(first % 6u);
+    bool on = count > 0;
+    // kt = tokens emitted by this lane << 8 | kb, kb = zigzag position of the last symbol + 1 (0: the DC comes
+    // next).  One add per symbol moves both: table entries hold (token? << 8 | advance) in their top 9 bits.
+    // kb <= 127 before a symbol (else the block has ended) and the advance is <= 128: no carry into the count.
+    uint32_t kt = 0;
+    uint32_t desc = 0, acd = 0, tzp = 0, nxt_s = bstate_s;
+    uint32_t zacc = 0;                                           // dequant entries seen at block ends (error flag)
+    int predA = pred0, predB = pred1, predC = pred2;             // predA: the current block's component
+    if (on) {
+        ring_put(wr, load_group(wr));
+        ring_put(wr + 4, load_group(wr + 4));
+        wr += 8;
+        pend = load_group(wr);
+    }
+    {   // every lane gets valid tables, also the ones without work: they run the symbol code with frozen state
+        const uint32_t b = first % 6u;
+        const uint4 bs = S.bstate[b];
+        desc = bs.x; acd = bs.y; tzp = bs.z; nxt_s = bs.w;
+        if (b == 4) { predA = pred1; predB = pred2; predC = pred0; }
+        if (b == 5) { predA = pred2; predB = pred0; predC = pred1; }
+    }
 
-    for (uint32_t i = 0; i < maxcount; i++) {
-        const bool on = i < count;
-        // ---- converged: ring top-up
+    while (__any_sync(0xffffffffu, on)) {
+        // ---- service point (warp-uniform): ring top-up, token flush, room check
         if (on) {
-            const uint32_t rd = bp >> 5;                                      // words below this one are dead
-            if (rd > wr) { wr = rd & ~3u; have_pend = false; }                // the ring ran dry in the last block: restart it
-            if (have_pend && (int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; have_pend = false; }
-            if (!have_pend && (int)(wr - rd) <= kRingWords - 8) { pend = load_group(wr); have_pend = true; }
+            const uint32_t rd = bp >> 5;                                       // words below this one are dead
+            if ((int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; pend = load_group(wr); }
+            if (FLAVOR == kFlavorAmvlib) { while ((kt >> 8) - flushed >= 4) flush_group(); }
+            else if ((kt >> 8) - flushed >= 4) flush_group();
+            if (tok_first + (kt >> 8) > tpark) { st |= AMV_ST_OVERRUN; tok_first = (tpark - (kt >> 8)) & ~3u; }   // see kTokBlockRoom
         }
-        if (!on) continue;
-        const int tq = b >= 4 ? 1 : 0;
-        if (tok_idx > tpark) { st |= AMV_ST_OVERRUN; tok_idx = tpark; }      // see kTokBlockRoom
-        const uint32_t blk_start = tok_idx + (tcount >> 7);
-        uint32_t tzq_s = tz_s + (uint32_t)tq * 256u;
-        asm volatile("mov.u32 %0, %0;" : "+r"(tzq_s));           // keep the per-block table base in a register
-        const uint32_t dc_lut_s = lut_s + (tq ? dc_base[1] : dc_base[0]) * 4u, ac_lut_s = lut_s + (tq ? ac_base[1] : ac_base[0]) * 4u;
-        // ---- DC (mjpeg_decode_dc, mjpegdec.c:358-373)
-        {
-            const uint32_t hi = window();
-            uint32_t e = lds32(dc_lut_s + (hi >> (32 - kVlcFirstBits)) * 4);
-            if ((e & 0xff) == 0) {
-                if (e & 0x100) { st |= AMV_ST_BADCODE; e = 1u | (32u << 8) | (1u << 16); }
-                else e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
-                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; e = 1u | (32u << 8) | (1u << 16); }
+        // ---- kTokPeriod symbols, straight-line: everything but the long-code lookup is predicated, so the
+        // four symbol bodies interleave freely.  A lane that has finished keeps executing with its state frozen
+        // (its loads stay inside the tables and its own ring, its stores are predicated off).
+#pragma unroll
+        for (int u = 0; u < kTokPeriod; u++) {
+            // ---- the 32 bits at bp
+            const uint32_t x = bp << 2;
+            const uint32_t wa = lds32(ring_s | (x & 0x780u)), wc = lds32(ring_s | ((x + 128u) & 0x780u));
+            const uint32_t hi = __funnelshift_l(wc, wa, bp);
+            // ---- symbol (mjpeg_decode_dc mjpegdec.c:358-373 / decode_block :391-428)
+            uint32_t e = lds32((desc >> 8) + (__funnelshift_r(hi, 0u, desc) << 2));
+            if ((e & 31u) == 0) {
+                if (!(e & kFlatBad)) {
+                    const uint32_t fb = 32u - (desc & 31u), sb = e >> 24;
+                    e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << fb) >> (32u - sb))) << 2));
+                }
+                if ((e & 31u) == 0) {       // no such code: a bad DC reads as difference 0, a bad AC ends the block
+                    if (on) st |= AMV_ST_BADCODE;
+                    e = 1u | (1u << 8) | ((kt & 0xffu) ? (kFlatAdvEob << 23) : ((1u << 23) | (1u << 31)));
+                }
             }
-            const uint32_t len = e & 0xff, rsh = (e >> 8) & 0xff, total = (e >> 16) & 0xff;
-            const uint32_t top = hi << len;
-            const int sg = (int)(~top) >> 31;                                 // get_xbits: -1 if the first bit is 0
-            const int diff = (int)((__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg);
-            bp += total;
-            int pr;
+            const uint32_t slot = tst_s | ((kt >> 1) & 0x380u);                // staging slot of the token, if one comes
+            const uint32_t top = hi << (e & 31u);
+            if (on) { bp += __byte_perm(e, 0, 0x4441); kt += e >> 23; }
+            const int sg = (int)(~top) >> 31;                                  // get_xbits: -1 if the first bit is 0
+            // the size bits under the code, sign-extended; the shift count is the entry's bits [20:16] (wrap mode ignores the rest)
+            const int lvl = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
+            const uint32_t z = lds32(tzp | ((kt << 2) & 0x1fcu));
+            const uint32_t kb = kt & 0xffu;
+            const bool isdc = kb == 1u;
+            uint32_t tok;
             if (FLAVOR == kFlavorAmvlib) {
-                // the chain runs in quantised units in a 16-bit variable (AmvJpeg.c:1194-1196); the product
-                // with the quantiser is a full int (IQtIZzBlock :1041-1046); raster position 0
-                if (b < 4) pr = (pred0 = sext16(pred0 + diff)) * q0l;
-                else if (b == 4) pr = (pred1 = sext16(pred1 + diff)) * q0c;
-                else pr = (pred2 = sext16(pred2 + diff)) * q0c;
-                push((uint32_t)pr & 0x03ffffffu);
-            } else {
-                if (b < 4) pr = (pred0 += diff * q0l);
-                else if (b == 4) pr = (pred1 += diff * q0c);
-                else pr = (pred2 += diff * q0c);
-                push((uint32_t)pr & 0xffffu);                                  // block[0] = (int16) val (mjpegdec.c:387-389)
-            }
-        }
-        // ---- AC (decode_block, mjpegdec.c:391-428)
-        int k = 0;
-        uint32_t nac = 0;
-        for (;;) {
-            const uint32_t hi = window();
-            uint32_t e = lds32(ac_lut_s + (hi >> (32 - kVlcFirstBits)) * 4);
-            if ((e & 0xff) == 0) {
-                if (!(e & 0x100))
-                    e = lds32(lut_s + ((e >> 16) + ((hi >> (32 - kVlcFirstBits - kVlcSecondBits)) & ((1u << kVlcSecondBits) - 1u))) * 4);
-                if ((e & 0xff) == 0) { st |= AMV_ST_BADCODE; bp += 1; break; }
-            }
-            const uint32_t len = e & 0xff, rsh = __byte_perm(e, 0, 0x4441), total = __byte_perm(e, 0, 0x4442), run = e >> 28;
-            const uint32_t top = hi << len;
-            bp += total;
-            if (rsh == 32) {                                                   // size 0: EOB or ZRL
-                if (run != 15) break;
-                k += 16;
-                if (k > 1024) break;                                           // only garbage lanes get here
-                continue;
-            }
-            const int sg = (int)(~top) >> 31;
-            const int lvl = (int)((__funnelshift_rc(top ^ (uint32_t)sg, 0u, rsh) ^ (uint32_t)sg) - (uint32_t)sg);
-            k += (int)run + 1;
-            if (k > 63) { st |= AMV_ST_COEFIDX; break; }                      // "error count" (mjpegdec.c:423-424)
-            const uint32_t z = lds32(tzq_s + (uint32_t)k * 4);
-            if (FLAVOR == kFlavorAmvlib) {
-                const uint32_t val = (uint32_t)(lvl * (int)(z & 0xffu)) & 0x03ffffffu;
-                if (!(z & kAmvlibTokSkip)) {
-                    push((z & 0xfc000000u) | val);
-                    nac++;
-                    if (z & kAmvlibTokDup) { push(((z << 16) & 0xfc000000u) | val); nac++; }
+                // the DC chain runs in quantised units in a 16-bit variable (AmvJpeg.c:1194-1196); the product
+                // with the quantiser is a full int (IQtIZzBlock :1041-1046)
+                const int dcv = sext16(predA + lvl);
+                const int c = isdc ? dcv : lvl;
+                predA = isdc ? dcv : predA;
+                tok = (z & 0xfc000000u) | ((uint32_t)(c * (int)(z & 0xffu)) & 0x03ffffffu);
+                sts32(slot, tok);
+                if ((z & (kAmvlibTokSkip | kAmvlibTokDup)) && (int)e < 0 && on) {      // the zigzag typo (AmvJpeg.c:131-141)
+                    if (z & kAmvlibTokSkip) kt -= 256u;                        // coefficient 31 is never read
+                    else { sts32(tst_s | ((kt >> 1) & 0x380u), ((z << 16) & 0xfc000000u) | (tok & 0x03ffffffu)); kt += 256u; }
                 }
             } else {
-                push((z & 0xffff0000u) | ((uint32_t)(lvl * (int)(z & 0xffffu)) & 0xffffu));   // level * quant_matrix[j] as int16 (:420,428)
-                nac++;
+                // level * quant_matrix[j] as int16 (:420,428); block[0] = (int16)(last_dc += diff * q0) (:387-389)
+                const int prod = lvl * (int)(z & 0xffu);
+                const int val = prod + (isdc ? predA : 0);
+                predA = isdc ? val : predA;
+                tok = __byte_perm((uint32_t)val, z, 0x7610);
+                sts32(slot, tok);
             }
-            if (k == 63) break;
+            // ---- end of block: EOB, coefficient 63, or a coefficient index > 63 ("error count", :423-424; those
+            // positions carry kTzErr in the dequant table)
+            const bool nz = lvl != 0;
+            const bool endp = on && kb >= 64u && (nz || kb >= 128u);
+            const uint32_t tc = kt >> 8;
+            // (AC token count << 24) + index of the DC token; the sum is < 2^24 whatever tok_first wrapped to
+            if (endp) boff[bi] = ((tc - blk0 - 1u) << kTokCountShift) + (tok_first + blk0);
+            const uint4 bs = lds128(nxt_s);
+            zacc |= (endp && nz) ? z : 0u;
+            bi += endp ? 1u : 0u;
+            const bool rot = endp && (bs.y & 0x80u);
+            const int nA = rot ? predB : predA, nB = rot ? predC : predB, nC = rot ? predA : predC;
+            predA = nA; predB = nB; predC = nC;
+            desc = endp ? bs.x : (isdc ? acd : desc);
+            acd = endp ? bs.y : acd;
+            tzp = endp ? bs.z : tzp;
+            nxt_s = endp ? bs.w : nxt_s;
+            kt = endp ? (kt & ~0xffu) : kt;
+            blk0 = endp ? tc : blk0;
+            on = on && bi != count;
         }
-        boff[i] = (nac << kTokCountShift) | blk_start;
-        if (++b == 6) b = 0;
     }
-    // flush the partly filled group (unused upper tokens are don't-care, the group is ours alone)
-    if (count && tcount) flush4();
+    if (zacc & (FLAVOR == kFlavorAmvlib ? kTzErrAmvlib : kTzErr)) st |= AMV_ST_COEFIDX;
+    // flush what is still staged (unused upper tokens of the last group are don't-care, the group is ours alone)
+    while (flushed < (kt >> 8)) flush_group();
     // a lane that owns no block just passes through; otherwise it must end inside the scan
     if (count && bp > U * 8u) st |= AMV_ST_OVERRUN;
     if (st && f < n) atomicOr(&status[f], (int32_t)st);
@@ -716,9 +737,10 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 cudaError_t upload_dec_tables(cudaStream_t s) {
     static DecTablesDev h;      // built once; identical for every context
     static bool built = false;
-    static FastVlcTables hf;
-    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); build_amvlib_dequant_tables(h.adq); build_fast_vlc_tables(hf); built = true; }
-    cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_vlc, &hf, sizeof(hf), 0, cudaMemcpyHostToDevice, s);
+    static FlatVlcTables hf;
+    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); build_amvlib_dequant_tables(h.adq); build_flat_vlc_tables(hf); built = true; }
+    if (hf.count > kFlatMaxEntries) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemcpyToSymbolAsync(g_flat_vlc, &hf, sizeof(hf), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbolAsync(g_dec_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
@@ -752,11 +774,17 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                        int32_t *status, bool amvlib, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+        cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+        attr_set = true;
+    }
     if (amvlib)
-        k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+        k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                  tokens, blk_off, status);
     else
-        k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, 0, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+        k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                  tokens, blk_off, status);
 }
 

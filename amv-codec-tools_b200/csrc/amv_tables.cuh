@@ -141,16 +141,6 @@ struct VlcTables {
     int      count;          // entries used
 };
 
-// Second view of the same codes for the token kernel's straight-line symbol decode: byte fields,
-// so every field is one PRMT/LOP away.
-//   [7:0] code length  [15:8] 32 - size  [23:16] length + size (bits to consume)  [31:28] run
-//   length 0 marks a special entry: bit 8 set = no such code, else [31:16] = second-level index
-struct FastVlcTables {
-    uint32_t e[kVlcMaxEntries];
-    int      base[4];
-    int      count;
-};
-
 // zigzag position -> (raster index | quantiser << 8), per component class (luma, chroma);
 // tz: the same for the token producer: (column byte offset << 16) | quantiser
 struct DequantTables { uint32_t zq[2][64]; uint32_t tz[2][64]; };
@@ -234,20 +224,75 @@ inline void build_vlc_tables(VlcTables &T) {
     T.count = used;
 }
 
-inline void build_fast_vlc_tables(FastVlcTables &F) {
-    VlcTables T;
-    build_vlc_tables(T);
-    F.count = T.count;
-    for (int t = 0; t < 4; t++) F.base[t] = T.base[t];
-    for (int i = 0; i < kVlcMaxEntries; i++) {
-        const uint32_t e = T.e[i];
-        if (e & kVlcBad) F.e[i] = 0x100u;
-        else if (e & kVlcPtr) F.e[i] = (e & 0x1fffu) << 16;
-        else {
-            const uint32_t len = e & 31, size = (e >> 5) & 15, run = (e >> 9) & 15;
-            F.e[i] = len | ((32 - size) << 8) | ((len + size) << 16) | (run << 28);
+// Second view of the same codes, for the flat (one symbol per iteration, no DC/AC branch) token
+// kernel.  DC and AC symbols go through the same code: a block starts with kb = 0 (kb = zigzag
+// position + 1), every entry carries the amount kb advances by and whether the symbol yields a
+// token, and the end of a block shows as kb >= 64.
+//   direct entry : [4:0] code length (>= 1)  [15:8] bits to consume  [20:16] size
+//                  [30:23] advance of kb  [31] symbol yields a token
+//                  advance: DC 1, AC coefficient run + 1, ZRL 16, EOB 128
+//   [4:0] == 0   : bit 5 = no such code, else [23:8] = index of the second-level table, [31:24] its index bits
+// First level: kFlatDcBits / kFlatAcBits index bits; second level: the remaining bits up to 16.
+constexpr int kFlatDcBits = 10, kFlatAcBits = 12;
+constexpr int kFlatSecondCap = 1024;
+constexpr int kFlatMaxEntries = 2 * (1 << kFlatDcBits) + 2 * (1 << kFlatAcBits) + kFlatSecondCap;
+constexpr uint32_t kFlatBad = 1u << 5;
+constexpr uint32_t kFlatAdvEob = 128;
+struct FlatVlcTables {
+    uint32_t e[kFlatMaxEntries];
+    int      base[4];        // DC-luma, DC-chroma, AC-luma, AC-chroma
+    int      count;          // entries used; > kFlatMaxEntries: the codes do not fit (never for the fixed tables)
+};
+
+// generic over the code specification (counts per length 1..16, symbols in code order), so tables
+// read from a DHT segment build the same way as the fixed ones
+inline bool build_flat_vlc_table(FlatVlcTables &F, int t, const uint8_t counts[16], const uint8_t *syms, int &used) {
+    const bool dc = t < 2;
+    const int fb = dc ? kFlatDcBits : kFlatAcBits, sb = 16 - fb;
+    F.base[t] = used;
+    used += 1 << fb;
+    if (used > kFlatMaxEntries) return false;
+    for (int i = 0; i < (1 << fb); i++) F.e[F.base[t] + i] = kFlatBad;
+    unsigned next = 0;
+    int k = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int j = 0; j < counts[l - 1]; j++, k++) {
+            const unsigned code = next++;
+            const int s = syms[k];
+            const int run = dc ? 0 : (s >> 4), size = dc ? s : (s & 15);
+            if (dc && size > 16) return false;
+            uint32_t adv = dc ? 1u : (uint32_t)run + 1u;
+            if (!dc && size == 0) adv = run == 15 ? 16u : kFlatAdvEob;          // ZRL / EOB (other run,0 symbols: treated as EOB)
+            const uint32_t emit = (dc || size) ? 1u : 0u;
+            const uint32_t ent = (uint32_t)l | ((uint32_t)(l + size) << 8) | ((uint32_t)size << 16) | (adv << 23) | (emit << 31);
+            if (l <= fb) {
+                const int spare = fb - l;
+                for (int i = 0; i < (1 << spare); i++) F.e[F.base[t] + (code << spare) + i] = ent;
+            } else {
+                const unsigned pre = code >> (l - fb);
+                uint32_t &slot = F.e[F.base[t] + pre];
+                if (slot == kFlatBad) {
+                    if (used + (1 << sb) > kFlatMaxEntries) return false;
+                    slot = ((uint32_t)used << 8) | ((uint32_t)sb << 24);
+                    for (int i = 0; i < (1 << sb); i++) F.e[used + i] = kFlatBad;
+                    used += 1 << sb;
+                }
+                const int sub = (slot >> 8) & 0xffff;
+                const int rest = l - fb;
+                const int lo = (code & ((1u << rest) - 1u)) << (sb - rest);
+                for (int i = 0; i < (1 << (sb - rest)); i++) F.e[sub + lo + i] = ent;
+            }
         }
+        next <<= 1;
     }
+    return true;
+}
+
+inline void build_flat_vlc_tables(FlatVlcTables &F) {
+    int used = 0;
+    bool ok = true;
+    for (int t = 0; t < 4; t++) ok = build_flat_vlc_table(F, t, kHuffCount[t], huff_symbols(t), used) && ok;
+    F.count = ok ? used : kFlatMaxEntries + 1;
 }
 
 inline void build_dequant_tables(DequantTables &D) {
