@@ -57,10 +57,19 @@ AMV_HD uint32_t pack_pixels(int p0, int p1, int p2, int p3) {
 
 // in : c[32], word 4*r+i = coefficient (r,2i) in the low half, (r,2i+1) in the high half
 // out: o[16], words 2*r and 2*r+1 = the 8 pixels of row r, column 0 in the lowest byte
+// ROWS: the caller guarantees that coefficient rows ROWS..7 are all zero.  Such a row leaves the row
+// pass as zeros (idctRowCondDC's DC-only shortcut yields row[0] << 3 = 0), so it is not evaluated and the
+// column pass folds its terms away at compile time -- the result is identical to the full transform.
+template <int ROWS = 8>
 AMV_HD void idct_put_block(const uint32_t (&c)[32], uint32_t (&o)[16]) {
     int m[64];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
+        if (r >= ROWS) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) m[8 * r + i] = 0;
+            continue;
+        }
         const uint32_t w0 = c[4 * r], w1 = c[4 * r + 1], w2 = c[4 * r + 2], w3 = c[4 * r + 3];
         const int x0 = sext16((int)w0), x1 = (int)w0 >> 16;
         const int x2 = sext16((int)w1), x3 = (int)w1 >> 16;

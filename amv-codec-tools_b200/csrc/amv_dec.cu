@@ -710,7 +710,13 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
     uint32_t c[32], o[16];
 #pragma unroll
     for (int k = 0; k < 32; k++) c[k] = slot[k * 32];
-    idct_put_block(c, o);
+    // Smooth content (chroma planes almost always) has nothing below the second coefficient row: when that holds
+    // for the whole warp, take the transform specialised for it (same results, a quarter of the arithmetic).
+    uint32_t lower = 0;
+#pragma unroll
+    for (int k = 8; k < 32; k++) lower |= c[k];
+    if (__all_sync(__activemask(), lower == 0)) idct_put_block<2>(c, o);
+    else idct_put_block<8>(c, o);
 
     uint8_t *pl = comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c;
     const int ls = comp ? ls_c : ls_y;

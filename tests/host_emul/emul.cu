@@ -174,7 +174,9 @@ void emul_idct(const int16_t *blocks, int n, uint8_t *out) {
     for (int i = 0; i < n; i++) {
         uint32_t c[32], o[16];
         for (int k = 0; k < 32; k++) c[k] = (uint16_t)blocks[64 * i + 2 * k] | ((uint32_t)(uint16_t)blocks[64 * i + 2 * k + 1] << 16);
-        idct_put_block(c, o);
+        uint32_t lower = 0;                              // the kernel's choice: nothing below the second row -> short transform
+        for (int k = 8; k < 32; k++) lower |= c[k];
+        if (lower == 0) idct_put_block<2>(c, o); else idct_put_block<8>(c, o);
         memcpy(out + 64 * i, o, 64);
     }
 }

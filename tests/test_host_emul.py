@@ -62,7 +62,10 @@ def test_idct_registers(emul, oracle):
         sparse[i, 0] = rng.integers(-3000, 6000)
     extreme = rng.choice(np.array([-32768, -1, 0, 1, 32767], np.int16), (2000, 64))
     dense = rng.integers(-32768, 32768, (2000, 64)).astype(np.int16)
-    blocks = np.ascontiguousarray(np.concatenate([sparse, extreme, dense]))
+    tworows = dense.copy()                       # only coefficient rows 0 and 1: the short transform of k_idct
+    tworows[:, 16:] = 0
+    tworows[::3, 8:] = 0
+    blocks = np.ascontiguousarray(np.concatenate([sparse, extreme, dense, tworows]))
     out = np.zeros((blocks.shape[0], 64), np.uint8)
     emul.emul_idct(_p(blocks), blocks.shape[0], _p(out))
     assert np.array_equal(out, oracle.idct_put(blocks))
