@@ -26,7 +26,7 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "amvcuda.h")
 MEM_HOST, MEM_DEVICE = 0, 1
 LAYOUT_PACKED, LAYOUT_SLOTS = 0, 1
 
-ST_SHORT, ST_BADCODE, ST_COEFIDX, ST_MARKER, ST_OVERRUN, ST_RANGE, ST_NOSPACE = (1 << i for i in range(7))
+ST_SHORT, ST_BADCODE, ST_COEFIDX, ST_MARKER, ST_OVERRUN, ST_RANGE, ST_NOSPACE, ST_HEADER = (1 << i for i in range(8))
 
 EXPORTS = [
     "amv_create", "amv_destroy", "amv_set_stream", "amv_sync", "amv_strerror", "amv_last_error", "amv_version",
@@ -34,7 +34,7 @@ EXPORTS = [
     "amv_qscale_from_quality", "amv_decode_frames", "amv_encode_frames", "amv_adpcm_dec_chunks",
     "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
     "amv_file_index", "amv_file_mux", "amv_decode_frames_sp5x",
-    "amv_convert_range",
+    "amv_convert_range", "amv_mjpeg_configure", "amv_decode_frames_mjpeg",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library(path=LIB_PATH):
     lib.amv_qscale_from_quality.argtypes = [i32, i32, i32]
     lib.amv_decode_frames.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, vp, i32]
     lib.amv_decode_frames_sp5x.argtypes = lib.amv_decode_frames.argtypes
+    lib.amv_decode_frames_mjpeg.argtypes = lib.amv_decode_frames.argtypes
+    lib.amv_mjpeg_configure.argtypes = [vp, vp, C.c_uint32, vp, vp]
     lib.amv_convert_range.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32]
     lib.amv_decode_frames_bgr24.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, i32, u64, vp, i32]
     lib.amv_file_index.argtypes = [vp, u64, C.POINTER(FileInfo), vp, vp, vp, vp, u32]
@@ -222,8 +224,10 @@ class AmvCuda:
 
     # ---------------------------------------------------------------- raw ABI calls (any memory kind)
     def decode_frames_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem,
-                          sp5x=False):
+                          sp5x=False, mjpeg=False):
         fn = self.lib.amv_decode_frames_sp5x if sp5x else self.lib.amv_decode_frames
+        if mjpeg:
+            fn = self.lib.amv_decode_frames_mjpeg
         self._ck(fn(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,
                                             _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, _ptr(status), mem))
 
@@ -267,9 +271,17 @@ class AmvCuda:
                                                 _ptr(out), out_bytes, _ptr(out_off), _ptr(status), mem))
 
     # ---------------------------------------------------------------- host (numpy) convenience wrappers
-    def decode_frames(self, pkts, pkt_off, pkt_size, w, h, sp5x=False):
+    def mjpeg_configure(self, jpeg):
+        """reads the tables / frame header of one sample JPEG frame (host bytes). -> (w, h)"""
+        buf = np.ascontiguousarray(np.frombuffer(bytes(jpeg), np.uint8) if not isinstance(jpeg, np.ndarray) else jpeg, np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.amv_mjpeg_configure(self.ctx, _ptr(buf), buf.nbytes, C.addressof(w), C.addressof(h)))
+        return w.value, h.value
+
+    def decode_frames(self, pkts, pkt_off, pkt_size, w, h, sp5x=False, mjpeg=False):
         """numpy in / numpy out through AMV_MEM_HOST. -> (y[n,h,w], u[n,ch,cw], v[n,ch,cw], status[n]);
-        sp5x=True decodes SP5X packets (amv_decode_frames_sp5x)"""
+        sp5x=True decodes SP5X packets (amv_decode_frames_sp5x); mjpeg=True decodes plain JPEG frames
+        (amv_decode_frames_mjpeg, after mjpeg_configure)"""
         pkts = np.ascontiguousarray(pkts, np.uint8)
         pkt_off = np.ascontiguousarray(pkt_off, np.uint64)
         pkt_size = np.ascontiguousarray(pkt_size, np.uint32)
@@ -280,7 +292,7 @@ class AmvCuda:
         v = np.zeros((n, ch, cw), np.uint8)
         st = np.zeros(n, np.int32)
         self.decode_frames_raw(pkts, pkts.nbytes, pkt_off, pkt_size, n, w, h, y, u, v, w, cw, w * h, cw * ch, st, MEM_HOST,
-                               sp5x=sp5x)
+                               sp5x=sp5x, mjpeg=mjpeg)
         return y, u, v, st
 
     def decode_frames_bgr24(self, pkts, pkt_off, pkt_size, w, h, line_bytes=None):

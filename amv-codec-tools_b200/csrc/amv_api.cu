@@ -23,7 +23,7 @@ struct DevBuf {
 };
 
 enum WsId {
-    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS, WS_TOKENS, WS_BLKOFF,
+    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS, WS_TOKENS, WS_BLKOFF, WS_QTAB,
     // device mirrors of host arguments (AMV_MEM_HOST calls)
     WS_H_A, WS_H_B, WS_H_C, WS_H_D, WS_H_E, WS_H_F, WS_H_G, WS_H_H, WS_H_I,
     WS_COUNT
@@ -57,7 +57,28 @@ struct amv_ctx {
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
+    // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
+    void *mj_tables = nullptr;          // DecTableSet in device memory
+    uint8_t *mj_hdr = nullptr;          // device copy of the sample's bytes up to the end of the SOS header
+    uint32_t mj_hdr_len = 0;
+    uint32_t mj_qpos[2] = { 0, 0 };     // where the 64 quantisers of component 0 / components 1, 2 sit in a frame
+    int mj_w = 0, mj_h = 0;
+    bool mj_sync_ok = false;            // the lane-synchronisation table could be built (else one lane per frame)
 };
+
+// how a packet is framed and which tables its scan uses
+struct DecMode {
+    uint32_t head = 2;                  // bytes in front of the scan
+    bool literal = false;               // SP5X: scan bytes are literal and run to the end of the packet
+    bool flip = true;                   // AMV stores the picture bottom-up
+    const amv::DecTableSet *tables = nullptr;   // nullptr: the fixed AMV / SP5X (or amvlib) set
+    const uint8_t *hdr = nullptr;       // plain JPEG: required header bytes (device)
+    uint32_t hdr_len = 0;
+    uint32_t qpos[2] = { 0, 0 };        // plain JPEG: offsets of the per-frame quantisers
+    bool allow_sync = true;
+};
+static const DecMode kModeAmv;
+static DecMode mode_sp5x() { DecMode m; m.head = 14; m.literal = true; m.flip = false; return m; }
 
 namespace {
 
@@ -140,8 +161,11 @@ struct DecodeFront {
 };
 
 int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
-                 int n, const Geom &g, int32_t *status, uint64_t payload_bytes, bool amvlib, DecodeFront &F, bool sp5x = false) {
-    const int log2p = pick_log2p(ctx, n);
+                 int n, const Geom &g, int32_t *status, uint64_t payload_bytes, bool amvlib, DecodeFront &F,
+                 const DecMode &mode = kModeAmv) {
+    const int log2p = mode.allow_sync ? pick_log2p(ctx, n) : 0;
+    const DecTableSet *tabs = mode.tables ? mode.tables : fixed_dec_tables(amvlib);
+    if (!tabs) return fail(ctx, AMV_ERR_CUDA, "decoder tables are not on the device");
     uint64_t *slot_off; uint32_t *scan_len; int32_t *st = status; LaneStart *starts = nullptr; uint8_t *scratch;
     uint32_t *rounds; uint32_t *tokens; uint32_t *blk_off;
     const uint64_t scratch_bytes = payload_bytes + (uint64_t)(kSlotPad + 16) * n + 64;
@@ -156,16 +180,24 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
 
     launch_scan_sizes(pkt_size, n, 15u, kSlotPad, slot_off, nullptr, ctx->stream);
     { ScopedTimer tm(ctx, KK_UNSTUFF);
-      launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, sp5x, ctx->stream); }
+      launch_unstuff(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes, scan_len, st, mode.head,
+                     mode.literal, ctx->stream); }
     int lc = 2;
+    uint8_t *qtab = nullptr;
+    if (mode.hdr) {
+        ENSURE(WS_QTAB, (size_t)n * 128, qtab);
+        launch_mjpeg_check(pkts, pkts_bytes, pkt_off, pkt_size, n, mode.hdr, mode.hdr_len, mode.qpos[0], mode.qpos[1], qtab,
+                           scan_len, st, ctx->stream);
+        lc++;
+    }
     if (log2p) {
         CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
         { ScopedTimer tm(ctx, KK_SYNC);
-          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, ctx->stream); }
+          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, tabs, qtab, ctx->stream); }
         lc++;
     }
     { ScopedTimer tm(ctx, KK_TOKENS);
-      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, ctx->stream); }
+      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, ctx->stream); }
     lc++;
     F.slot_off = slot_off; F.scan_len = scan_len; F.tokens = tokens; F.blk_off = blk_off; F.st = st; F.launches = lc;
     return AMV_OK;
@@ -173,11 +205,11 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
 
 int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                   const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
-                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes, bool sp5x = false) {
+                  uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes, const DecMode &mode = kModeAmv) {
     Geom g = make_geom(w, h);
-    if (sp5x) g.flip = 0;
+    if (!mode.flip) g.flip = 0;
     DecodeFront F;
-    int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F, sp5x);
+    int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F, mode);
     if (r != AMV_OK) return r;
     { ScopedTimer tm(ctx, KK_IDCT);
       launch_idct(F.tokens, F.blk_off, F.slot_off, F.scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
@@ -288,6 +320,8 @@ int ensure_pipeline(amv_ctx *ctx, size_t meta_bytes) {
     if (meta_bytes > ctx->pinned_meta_cap) {
         CK(cudaStreamSynchronize(ctx->s_out));
         if (ctx->pinned_meta) cudaFreeHost(ctx->pinned_meta);
+    if (ctx->mj_tables) cudaFree(ctx->mj_tables);
+    if (ctx->mj_hdr) cudaFree(ctx->mj_hdr);
         ctx->pinned_meta = nullptr; ctx->pinned_meta_cap = 0;
         CK(cudaMallocHost(&ctx->pinned_meta, meta_bytes + 4096));
         ctx->pinned_meta_cap = meta_bytes + 4096;
@@ -372,7 +406,7 @@ void *device_view(const void *host_ptr) {
 
 int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
                 int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
-                int32_t *status, bool sp5x = false) {
+                int32_t *status, const DecMode &mode = kModeAmv) {
     const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
     const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
     const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
@@ -418,7 +452,7 @@ int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const ui
         }
         if (e_out.used[slot]) CK(cudaStreamWaitEvent(ctx->stream, e_out.e[slot], 0));      // ring slot drained?
         rc = decode_device(ctx, v_pk ? v_pk : d_pk, pkts_bytes, v_off + f0, v_sz + f0, m, w, h, d_y + ty * C * slot,
-                           d_u + tc * C * slot, d_v + tc * C * slot, w, cw, ty, tc, d_st + f0, payload, sp5x);
+                           d_u + tc * C * slot, d_v + tc * C * slot, w, cw, ty, tc, d_st + f0, payload, mode);
         if (rc != AMV_OK) break;
         CK(cudaEventRecord(e_cmp.e[slot], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_out, e_cmp.e[slot], 0));
@@ -591,6 +625,8 @@ AMV_API void amv_destroy(amv_ctx *ctx) {
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->pinned_meta) cudaFreeHost(ctx->pinned_meta);
+    if (ctx->mj_tables) cudaFree(ctx->mj_tables);
+    if (ctx->mj_hdr) cudaFree(ctx->mj_hdr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -665,7 +701,7 @@ AMV_API int64_t amv_get_stat(amv_ctx *ctx, const char *key) {
 // ---------------------------------------------------------------------------------------- decode
 static int decode_frames_common(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                                 const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
-                                int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem, bool sp5x) {
+                                int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem, const DecMode &mode) {
     if (!ctx) return AMV_ERR_ARG;
     if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
     if (n == 0) return AMV_OK;
@@ -675,20 +711,134 @@ static int decode_frames_common(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
     CK(cudaSetDevice(ctx->device));
     if (mem == AMV_MEM_DEVICE)
-        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes, sp5x);
-    return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, sp5x);
+        return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes, mode);
+    return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mode);
 }
 
 AMV_API int amv_decode_frames(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                               const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
                               int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
-    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, false);
+    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, kModeAmv);
 }
 
 AMV_API int amv_decode_frames_sp5x(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                                    const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
                                    int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
-    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, true);
+    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, mode_sp5x());
+}
+
+// ------------------------------------------------------------------------------ decode, plain JPEG
+// Host-side walk over the marker segments of the sample frame (find_marker + the segment parsers of
+// mjpegdec.c, see include/amvcuda.h).  No pixel arithmetic here: the tables go to the device, the scan to the kernels.
+AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, int *w_out, int *h_out) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (!p || size < 4 || p[0] != 0xff || p[1] != 0xd8) return fail(ctx, AMV_ERR_ARG, "not a JPEG (no SOI)");
+    uint8_t q[4][64], hc[2][4][16], hs[2][4][256];
+    bool have_q[4] = { false, false, false, false }, have_h[2][4] = { { false } };
+    int comp_id[3] = { 0, 0, 0 }, comp_q[3] = { 0, 0, 0 }, w = 0, h = 0;
+    bool have_sof = false;
+    uint32_t i = 2, scan_start = 0, qofs[4] = { 0, 0, 0, 0 };
+    int td[3] = { 0, 0, 0 }, ta[3] = { 0, 0, 0 };
+    auto bad = [&](const char *what) { return fail(ctx, AMV_ERR_UNSUPPORTED, what); };
+    while (i + 4 <= size && !scan_start) {
+        if (p[i] != 0xff) { i++; continue; }
+        const int m = p[i + 1];
+        if (m < 0xc0 || m == 0xff) { i++; continue; }                       // find_marker: FF followed by C0..FE
+        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7)) { i += 2; continue; }
+        if (m == 0xd9) return bad("EOI before the scan");
+        const uint32_t len = ((uint32_t)p[i + 2] << 8) | p[i + 3];
+        if (len < 2 || i + 2 + len > size) return bad("marker segment runs past the frame");
+        const uint8_t *d = p + i + 4;
+        uint32_t n = len - 2;
+        if (m == 0xdb) {                                                     // DQT
+            while (n >= 65) {
+                if (d[0] >> 4) return bad("16-bit quantiser table");
+                const int id = d[0] & 15;
+                if (id >= 4) return bad("quantiser table index");
+                memcpy(q[id], d + 1, 64); have_q[id] = true;
+                qofs[id] = (uint32_t)(d + 1 - p);
+                d += 65; n -= 65;
+            }
+        } else if (m == 0xc4) {                                              // DHT
+            while (n > 0) {
+                if (n < 17) return bad("short DHT");
+                const int cls = d[0] >> 4, id = d[0] & 15;
+                uint32_t tot = 0;
+                if (cls >= 2 || id >= 4) return bad("Huffman table class / index");
+                for (int k = 0; k < 16; k++) tot += d[1 + k];
+                if (tot > 256 || n < 17 + tot) return bad("short DHT");
+                memcpy(hc[cls][id], d + 1, 16); memset(hs[cls][id], 0, 256); memcpy(hs[cls][id], d + 17, tot);
+                have_h[cls][id] = true;
+                d += 17 + tot; n -= 17 + tot;
+            }
+        } else if (m == 0xc0) {                                              // SOF0
+            if (n < 15 || d[0] != 8 || d[5] != 3) return bad("not 8-bit, three components");
+            h = (d[1] << 8) | d[2]; w = (d[3] << 8) | d[4];
+            static const uint8_t want[3] = { 0x22, 0x11, 0x11 };
+            for (int c = 0; c < 3; c++) {
+                comp_id[c] = d[6 + 3 * c];
+                if (d[7 + 3 * c] != want[c]) return bad("sampling other than 2x2 / 1x1 / 1x1");
+                comp_q[c] = d[8 + 3 * c];
+                if (comp_q[c] >= 4) return bad("quantiser table index");
+            }
+            if (comp_q[1] != comp_q[2]) return bad("Cb and Cr use different quantiser tables");
+            have_sof = true;
+        } else if (m >= 0xc1 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
+            return bad("not a baseline (SOF0) frame");
+        } else if (m == 0xdd) {                                              // DRI
+            if (n < 2 || ((d[0] << 8) | d[1]) != 0) return bad("restart intervals");
+        } else if (m == 0xda) {                                              // SOS
+            if (!have_sof || n < 10 || d[0] != 3 || len != 6 + 2 * 3) return bad("scan header");
+            for (int c = 0; c < 3; c++) {
+                if (d[1 + 2 * c] != comp_id[c]) return bad("scan components out of frame order");
+                td[c] = d[2 + 2 * c] >> 4; ta[c] = d[2 + 2 * c] & 15;
+                if (td[c] >= 4 || ta[c] >= 4 || !have_h[0][td[c]] || !have_h[1][ta[c]]) return bad("missing Huffman table");
+            }
+            if (td[1] != td[2] || ta[1] != ta[2]) return bad("Cb and Cr use different Huffman tables");
+            if (d[7] != 0 || d[8] != 63 || d[9] != 0) return bad("not a sequential scan");
+            if (!have_q[comp_q[0]] || !have_q[comp_q[1]]) return bad("missing quantiser table");
+            scan_start = i + 2 + len;
+        }
+        i += 2 + len;
+    }
+    if (!scan_start) return bad("no scan");
+    if (w <= 0 || h <= 0 || w > 16384 || h > 16384) return bad("picture size");
+    uint8_t counts[4][16], syms[4][256], qzz[2][64];
+    for (int c = 0; c < 2; c++) {
+        memcpy(counts[c], hc[0][td[c]], 16);     memcpy(syms[c], hs[0][td[c]], 256);
+        memcpy(counts[2 + c], hc[1][ta[c]], 16); memcpy(syms[2 + c], hs[1][ta[c]], 256);
+        memcpy(qzz[c], q[comp_q[c]], 64);
+    }
+    std::vector<uint8_t> host(dec_table_set_bytes());
+    bool sync_ok = false;
+    if (!build_dec_table_set(host.data(), counts, syms, qzz, &sync_ok)) return bad("Huffman codes do not fit the lookup tables");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));                // nothing in flight may still use the previous configuration
+    if (!ctx->mj_tables) CK(cudaMalloc(&ctx->mj_tables, dec_table_set_bytes()));
+    if (ctx->mj_hdr) { cudaFree(ctx->mj_hdr); ctx->mj_hdr = nullptr; }
+    CK(cudaMalloc(reinterpret_cast<void **>(&ctx->mj_hdr), scan_start));
+    CK(cudaMemcpy(ctx->mj_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mj_hdr, p, scan_start, cudaMemcpyHostToDevice));
+    ctx->mj_hdr_len = scan_start; ctx->mj_w = w; ctx->mj_h = h; ctx->mj_sync_ok = sync_ok;
+    ctx->mj_qpos[0] = qofs[comp_q[0]]; ctx->mj_qpos[1] = qofs[comp_q[1]];
+    if (w_out) *w_out = w;
+    if (h_out) *h_out = h;
+    return AMV_OK;
+}
+
+AMV_API int amv_decode_frames_mjpeg(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
+                                    const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v,
+                                    int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int32_t *status, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (!ctx->mj_tables || !ctx->mj_hdr) return fail(ctx, AMV_ERR_ARG, "amv_mjpeg_configure has not been called");
+    if (w != ctx->mj_w || h != ctx->mj_h) return fail(ctx, AMV_ERR_ARG, "dimensions differ from the configured header");
+    DecMode m;
+    m.head = ctx->mj_hdr_len; m.flip = false;
+    m.tables = static_cast<const DecTableSet *>(ctx->mj_tables);
+    m.hdr = ctx->mj_hdr; m.hdr_len = ctx->mj_hdr_len;
+    m.qpos[0] = ctx->mj_qpos[0]; m.qpos[1] = ctx->mj_qpos[1];
+    m.allow_sync = ctx->mj_sync_ok;
+    return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, m);
 }
 
 // -------------------------------------------------------------------------- decode, amvlib flavour

@@ -19,6 +19,7 @@
 #define AMV_ST_OVERRUN  (1 << 4)
 #define AMV_ST_RANGE    (1 << 5)
 #define AMV_ST_NOSPACE  (1 << 6)
+#define AMV_ST_HEADER   (1 << 7)
 
 namespace amv {
 

@@ -89,10 +89,11 @@ __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t *__restrict__ pkt_off,
           const uint32_t *__restrict__ pkt_size, int n, uint8_t *__restrict__ scratch,
           const uint64_t *__restrict__ slot_off, uint64_t scratch_bytes, uint32_t *__restrict__ scan_len,
-          int32_t *__restrict__ status, int sp5x) {
-    // framing: AMV = FF D8 | stuffed scan | FF D9 (sp5xdec.c:75-77); SP5X = 14 header bytes | scan with LITERAL FF
-    // bytes to the end of the packet (the reference stuffs them itself before handing over, :78-84)
-    const uint32_t head = sp5x ? 14u : 2u, framing = sp5x ? 14u : 4u;
+          int32_t *__restrict__ status, uint32_t head, int sp5x) {
+    // framing: AMV = FF D8 | stuffed scan | FF D9 (sp5xdec.c:75-77), head 2; plain JPEG = the same with the marker
+    // segments up to the end of the SOS header in front, head = their length; SP5X = 14 header bytes | scan with
+    // LITERAL FF bytes to the end of the packet (the reference stuffs them itself before handing over, :78-84)
+    const uint32_t framing = sp5x ? head : head + 2u;
     constexpr int kUnstuffTile = kUnstuffThreads * 16;
     constexpr int kUnstuffStage = kUnstuffTile + 64;
     __shared__ __align__(16) uint8_t stage[kUnstuffStage];
@@ -272,15 +273,19 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
 // ------------------------------------------------------------------------------------------------
 // shared-memory tables for the VLC kernels
 // ------------------------------------------------------------------------------------------------
-struct DecTablesDev {
-    VlcTables vlc;
-    DequantTables dq;
-    AmvlibDequantTables adq;
+// Everything a scan needs besides its bits, in device memory: the fixed AMV / SP5X set, the amvlib
+// flavour's (same codes, amvlib's quantisers and zigzag), or one built from a JPEG's own DQT / DHT.
+struct DecTableSet {
+    FlatVlcTables flat;          // k_vlc_tokens
+    VlcTables vlc;               // k_vlc_sync
+    uint32_t tz[2][64];          // zigzag position -> token fields | quantiser (DequantTables::tz / AmvlibDequantTables::tz)
+    int q0[2];                   // DC quantisers of component 0 / components 1, 2
 };
 // which reference decoder the arithmetic follows: the ffmpeg fork's (sp5xdec/mjpegdec/simple_idct)
 // or amvlib's (AmvJpeg.c) -- same bitstream, different quantisers, DC chain, zigzag and IDCT
-enum { kFlavorFfmpeg = 0, kFlavorAmvlib = 1 };
-__device__ DecTablesDev g_dec_tables;
+// kFlavorJpeg: ffmpeg arithmetic with PER-FRAME quantisers (a plain JPEG's own DQT segment), see k_mjpeg_check
+enum { kFlavorFfmpeg = 0, kFlavorAmvlib = 1, kFlavorJpeg = 2 };
+__device__ DecTableSet g_dec_sets[2];
 
 struct VlcSmem {
     uint32_t lut[kVlcMaxEntries];
@@ -288,10 +293,10 @@ struct VlcSmem {
     int      q0[2];          // DC quantiser of luma / chroma
 };
 
-__device__ __forceinline__ void load_vlc_tables(VlcSmem &s) {
-    for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) s.lut[i] = g_dec_tables.vlc.e[i];
-    if (threadIdx.x < 4) s.base[threadIdx.x] = g_dec_tables.vlc.base[threadIdx.x];
-    if (threadIdx.x < 2) s.q0[threadIdx.x] = (int)(g_dec_tables.dq.zq[threadIdx.x][0] >> 8);
+__device__ __forceinline__ void load_vlc_tables(VlcSmem &s, const DecTableSet *__restrict__ T) {
+    for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) s.lut[i] = T->vlc.e[i];
+    if (threadIdx.x < 4) s.base[threadIdx.x] = T->vlc.base[threadIdx.x];
+    if (threadIdx.x < 2) s.q0[threadIdx.x] = T->q0[threadIdx.x];
     __syncthreads();
 }
 
@@ -327,9 +332,10 @@ constexpr int kVlcThreads = 128;
 __global__ void __launch_bounds__(kVlcThreads)
 k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
            const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
-           uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */, int flavor) {
+           uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */, int flavor,
+           const DecTableSet *__restrict__ tabs, const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */) {
     __shared__ VlcSmem T;
-    load_vlc_tables(T);
+    load_vlc_tables(T, tabs);
     const int P = 1 << log2p;
     const int lane = threadIdx.x & 31;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,9 +389,11 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
         if (flavor == kFlavorAmvlib) {                         // quantised units, 16-bit chain from 0 (AmvJpeg.c:1194-1196)
             s.pred[0] = sext16(d0 - ex.dc[0]); s.pred[1] = sext16(d1 - ex.dc[1]); s.pred[2] = sext16(d2 - ex.dc[2]);
         } else {
-            s.pred[0] = 1024 + T.q0[0] * (d0 - ex.dc[0]);      // last_dc starts at 1024 (mjpegdec.c:805-806)
-            s.pred[1] = 1024 + T.q0[1] * (d1 - ex.dc[1]);
-            s.pred[2] = 1024 + T.q0[1] * (d2 - ex.dc[2]);
+            const int q0l = flavor == kFlavorJpeg ? (int)qtab[(size_t)f * 128] : T.q0[0];
+            const int q0c = flavor == kFlavorJpeg ? (int)qtab[(size_t)f * 128 + 64] : T.q0[1];
+            s.pred[0] = 1024 + q0l * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
+            s.pred[1] = 1024 + q0c * (d1 - ex.dc[1]);
+            s.pred[2] = 1024 + q0c * (d2 - ex.dc[2]);
         }
         starts[gt] = s;
     }
@@ -420,7 +428,6 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 //  * tokens are staged in an 8-slot per-lane shared ring and leave as 16-byte stores at the
 //    service points.
 // ------------------------------------------------------------------------------------------------
-__device__ FlatVlcTables g_flat_vlc;
 
 constexpr int kTokThreads = 256;
 constexpr int kTokWarps = kTokThreads / 32;
@@ -450,15 +457,16 @@ __global__ void __launch_bounds__(kTokThreads)
 k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
              const LaneStart *__restrict__ starts, int nblk, uint32_t *__restrict__ tokens,
-             uint32_t *__restrict__ blk_off, int32_t *__restrict__ status) {
+             uint32_t *__restrict__ blk_off, int32_t *__restrict__ status, const DecTableSet *__restrict__ tabs,
+             const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */) {
     extern __shared__ uint8_t tok_smem_raw[];
     const uint32_t raw_s = smem_addr(tok_smem_raw);
     TokSmem &S = *reinterpret_cast<TokSmem *>(tok_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
-    const int nlut = g_flat_vlc.count;
-    for (int i = threadIdx.x; i < nlut; i += blockDim.x) S.lut[i] = g_flat_vlc.e[i];
+    const int nlut = tabs->flat.count;
+    for (int i = threadIdx.x; i < nlut; i += blockDim.x) S.lut[i] = tabs->flat.e[i];
     {   // dequant table indexed by kb; positions past 64 (only broken streams get there) alias the last one
         const int c = threadIdx.x >> 7, kb = threadIdx.x & 127, kk = kb == 0 ? 0 : (kb > 64 ? 63 : kb - 1);
-        const uint32_t z = FLAVOR == kFlavorAmvlib ? g_dec_tables.adq.tz[c][kk] : g_dec_tables.dq.tz[c][kk];
+        const uint32_t z = tabs->tz[c][kk];
         S.tz[c][kb] = z | (kb > 64 ? (FLAVOR == kFlavorAmvlib ? kTzErrAmvlib : kTzErr) : 0u);
     }
     const uint32_t lut_s = smem_addr(S.lut);
@@ -468,8 +476,8 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         // component changes on entering it
         const uint32_t bq = threadIdx.x, tq = bq >= 4 ? 1 : 0;
         uint4 bs;
-        bs.x = ((lut_s + (uint32_t)g_flat_vlc.base[tq] * 4u) << 8) | (32u - kFlatDcBits);
-        bs.y = ((lut_s + (uint32_t)g_flat_vlc.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | ((bq == 0 || bq >= 4) ? 0x80u : 0u);
+        bs.x = ((lut_s + (uint32_t)tabs->flat.base[tq] * 4u) << 8) | (32u - kFlatDcBits);
+        bs.y = ((lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | ((bq == 0 || bq >= 4) ? 0x80u : 0u);
         bs.z = smem_addr(&S.tz[tq][0]);
         bs.w = bstate_s + (bq == 5 ? 0u : bq + 1u) * 16u;
         S.bstate[bq] = bs;
@@ -482,6 +490,8 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     const int p = (int)(gt & (P - 1));
     const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
     const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: | (c & 7) << 7
+    const uint32_t tz_s = smem_addr(&S.tz[0][0]);
+    const uint8_t *qf = FLAVOR == kFlavorJpeg ? qtab + (size_t)(f < n ? f : 0) * 128 : nullptr;   // this frame's quantisers
     constexpr int kPred0 = FLAVOR == kFlavorAmvlib ? 0 : 1024;   // last_dc (mjpegdec.c:805-806) / ycoef.. (AmvJpeg.c:1510)
 
     // ---- lane set-up (inactive lanes keep count = 0 and never enter the symbol code)
@@ -623,7 +633,9 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
                 }
             } else {
                 // level * quant_matrix[j] as int16 (:420,428); block[0] = (int16)(last_dc += diff * q0) (:387-389)
-                const int prod = lvl * (int)(z & 0xffu);
+                int q = (int)(z & 0xffu);
+                if (FLAVOR == kFlavorJpeg) q = (int)__ldg(qf + (((tzp - tz_s) >> 3) + ((kb - 1u) & 63u)));   // tables are 512 B apart
+                const int prod = lvl * q;
                 const int val = prod + (isdc ? predA : 0);
                 predA = isdc ? val : predA;
                 tok = __byte_perm((uint32_t)val, z, 0x7610);
@@ -740,15 +752,53 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
+static bool fill_table_set(DecTableSet &T, const HuffSpec &H, const uint8_t qzz[2][64], bool *sync_ok) {
+    if (!build_flat_vlc_tables_from(T.flat, H)) return false;
+    const bool vs = build_vlc_tables_from(T.vlc, H);
+    if (sync_ok) *sync_ok = vs;
+    DequantTables dq;
+    build_dequant_tables_from(dq, qzz);
+    memcpy(T.tz, dq.tz, sizeof(T.tz));
+    T.q0[0] = qzz[0][0]; T.q0[1] = qzz[1][0];
+    return true;
+}
+
 cudaError_t upload_dec_tables(cudaStream_t s) {
-    static DecTablesDev h;      // built once; identical for every context
+    static DecTableSet h[2];      // built once; identical for every context
     static bool built = false;
-    static FlatVlcTables hf;
-    if (!built) { build_vlc_tables(h.vlc); build_dequant_tables(h.dq); build_amvlib_dequant_tables(h.adq); build_flat_vlc_tables(hf); built = true; }
-    if (hf.count > kFlatMaxEntries) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemcpyToSymbolAsync(g_flat_vlc, &hf, sizeof(hf), 0, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbolAsync(g_dec_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+    if (!built) {
+        HuffSpec H;
+        fixed_huff_spec(H);
+        if (!fill_table_set(h[0], H, kDecQuant, nullptr)) return cudaErrorInvalidValue;
+        h[1] = h[0];
+        AmvlibDequantTables adq;
+        build_amvlib_dequant_tables(adq);
+        memcpy(h[1].tz, adq.tz, sizeof(h[1].tz));
+        h[1].q0[0] = kAmvlibQuant[0][0]; h[1].q0[1] = kAmvlibQuant[1][0];
+        built = true;
+    }
+    return cudaMemcpyToSymbolAsync(g_dec_sets, h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+}
+
+const DecTableSet *fixed_dec_tables(bool amvlib) {
+    void *p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_dec_sets) != cudaSuccess) return nullptr;
+    return static_cast<const DecTableSet *>(p) + (amvlib ? 1 : 0);
+}
+
+size_t dec_table_set_bytes() { return sizeof(DecTableSet); }
+
+bool build_dec_table_set(void *host_buf, const uint8_t counts[4][16], const uint8_t syms[4][256], const uint8_t qzz[2][64],
+                         bool *sync_ok) {
+    HuffSpec H;
+    for (int t = 0; t < 4; t++) {
+        if (!huff_counts_valid(counts[t])) return false;
+        memcpy(H.counts[t], counts[t], 16);
+        memcpy(H.syms[t], syms[t], 256);
+    }
+    for (int t = 0; t < 2; t++)                        // DC categories above 16 bits cannot be coefficients of this path
+        for (int k = 0; k < 256; k++) if (H.syms[t][k] > 16) return false;
+    return fill_table_set(*static_cast<DecTableSet *>(host_buf), H, qzz, sync_ok);
 }
 
 void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_t pad, uint64_t *off,
@@ -758,40 +808,79 @@ void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_
 
 void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
                     uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
-                    int32_t *status, bool sp5x, cudaStream_t s) {
+                    int32_t *status, uint32_t head, bool literal, cudaStream_t s) {
     // 64-thread CTAs (1 KB tiles): the tile loop is a chain of barriers, and small CTAs keep more
     // independent chains per SM (measured 2.6 / 2.1 / 1.9 ms per 100k frames at 256 / 128 / 64 threads)
     constexpr int kThreads = 64, kPerSM = 24;
     const int grid = n < kNumSMs * kPerSM ? n : kNumSMs * kPerSM;
     k_unstuff<kThreads><<<grid, kThreads, 0, s>>>(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes,
-                                                  scan_len, status, sp5x ? 1 : 0);
+                                                  scan_len, status, head, literal ? 1 : 0);
+}
+
+// Plain JPEG frames are decoded with the Huffman tables and frame geometry of ONE header (amv_mjpeg_configure),
+// but each with the quantisers of its own DQT segment (an encoder under rate control rewrites them per frame):
+// the frame's marker segments must equal the sample's byte for byte outside the two 64-byte quantiser fields,
+// which are copied to qtab for the token kernel.  A frame that differs is not decoded and says so.
+__global__ void k_mjpeg_check(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t *__restrict__ pkt_off,
+                              const uint32_t *__restrict__ pkt_size, int n, const uint8_t *__restrict__ hdr, uint32_t hdr_len,
+                              uint32_t qpos0, uint32_t qpos1, uint8_t *__restrict__ qtab, uint32_t *__restrict__ scan_len,
+                              int32_t *__restrict__ status) {
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= n) return;
+    const uint64_t off = pkt_off[f];
+    const uint32_t size = pkt_size[f];
+    uint8_t *q = qtab + (size_t)f * 128;
+    if (off + size > pkts_bytes || size < hdr_len + 2u) {      // out of range: k_unstuff reported it; too short: no scan
+        for (int i = lane; i < 128; i += 32) q[i] = 1;
+        if (off + size <= pkts_bytes && lane == 0) { scan_len[f] = 0; atomicOr(&status[f], AMV_ST_HEADER); }
+        return;
+    }
+    bool diff = false;
+    for (uint32_t i = lane; i < hdr_len; i += 32) {
+        const bool quant = (i - qpos0 < 64u) || (i - qpos1 < 64u);
+        diff |= !quant && pkts[off + i] != hdr[i];
+    }
+    for (int i = lane; i < 64; i += 32) { q[i] = pkts[off + qpos0 + i]; q[64 + i] = pkts[off + qpos1 + i]; }
+    if (__any_sync(0xffffffffu, diff) && lane == 0) { scan_len[f] = 0; atomicOr(&status[f], AMV_ST_HEADER); }
+}
+
+void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                        const uint8_t *hdr, uint32_t hdr_len, uint32_t qpos0, uint32_t qpos1, uint8_t *qtab,
+                        uint32_t *scan_len, int32_t *status, cudaStream_t s) {
+    k_mjpeg_check<<<(n + 7) / 8, 256, 0, s>>>(pkts, pkts_bytes, pkt_off, pkt_size, n, hdr, hdr_len, qpos0, qpos1, qtab, scan_len,
+                                              status);
 }
 
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
-                     LaneStart *starts, uint32_t *rounds_out, bool amvlib, cudaStream_t s) {
+                     LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
+                     cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
     k_vlc_sync<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
-                                            amvlib ? kFlavorAmvlib : kFlavorFfmpeg);
+                                            amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab);
 }
 
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, bool amvlib, cudaStream_t s) {
+                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
     static bool attr_set = false;
     if (!attr_set) {
+        cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
         cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
         cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
         attr_set = true;
     }
     if (amvlib)
         k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                                 tokens, blk_off, status);
+                                                                 tokens, blk_off, status, tabs, nullptr);
+    else if (qtab)
+        k_vlc_tokens<kFlavorJpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+                                                               tokens, blk_off, status, tabs, qtab);
     else
         k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                                 tokens, blk_off, status);
+                                                                 tokens, blk_off, status, tabs, nullptr);
 }
 
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,

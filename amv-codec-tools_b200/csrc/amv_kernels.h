@@ -16,16 +16,34 @@ struct LaneStart {
 
 // ---- decode
 cudaError_t upload_dec_tables(cudaStream_t s);
+// The tables a scan is decoded with live in device memory as one DecTableSet (amv_dec.cu): the two fixed
+// sets (AMV / SP5X, amvlib flavour), or one built on the host from a JPEG's DQT / DHT content
+// (build_dec_table_set: false if the codes are malformed or do not fit the lookup tables; *sync_ok says whether
+// the lane-synchronisation kernel's smaller table could be built too) and copied to the device by the caller.
+struct DecTableSet;
+const DecTableSet *fixed_dec_tables(bool amvlib);
+size_t dec_table_set_bytes();
+bool build_dec_table_set(void *host_buf, const uint8_t counts[4][16], const uint8_t syms[4][256], const uint8_t qzz[2][64],
+                         bool *sync_ok);
 void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_t pad, uint64_t *off,
                        uint64_t *carry_io, cudaStream_t s);
+// head: bytes in front of the scan (AMV 2, SP5X 14, plain JPEG: everything up to the end of the SOS header);
+// literal: SP5X's un-stuffed scan that runs to the end of the packet
 void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
                     uint8_t *scratch, const uint64_t *slot_off, uint64_t scratch_bytes, uint32_t *scan_len,
-                    int32_t *status, bool sp5x, cudaStream_t s);
+                    int32_t *status, uint32_t head, bool literal, cudaStream_t s);
+// plain JPEG: compares each frame's marker segments with the configured header outside the two quantiser fields
+// (at qpos0 / qpos1) and copies those 2 x 64 quantisers to qtab[f]
+void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                        const uint8_t *hdr, uint32_t hdr_len, uint32_t qpos0, uint32_t qpos1, uint8_t *qtab,
+                        uint32_t *scan_len, int32_t *status, cudaStream_t s);
+// qtab != nullptr: per-frame quantisers (plain JPEG) instead of the table set's
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
-                     LaneStart *starts, uint32_t *rounds_out, bool amvlib, cudaStream_t s);
+                     LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
+                     cudaStream_t s);
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, bool amvlib, cudaStream_t s);
+                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, cudaStream_t s);
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
                  const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                  cudaStream_t s);

@@ -164,35 +164,59 @@ inline const uint8_t *huff_symbols(int t) {
     return t < 2 ? kHuffSymDC : (t == 2 ? kHuffSymACLuma : kHuffSymACChroma);
 }
 
-// canonical code assignment (ff_mjpeg_build_huffman_codes, mjpeg.c:129-147)
-inline void huff_codes(int t, uint8_t len[256], uint16_t code[256]) {
-    const uint8_t *sym = huff_symbols(t);
+// canonical code assignment (ff_mjpeg_build_huffman_codes, mjpeg.c:129-147) from a code specification:
+// codes per length 1..16 and the symbols in code order (what a DHT segment carries)
+inline void huff_codes_from(const uint8_t counts[16], const uint8_t *sym, uint8_t len[256], uint16_t code[256]) {
     memset(len, 0, 256);
     memset(code, 0, 512);
     unsigned next = 0;
     int k = 0;
     for (int l = 1; l <= 16; l++) {
-        for (int j = 0; j < kHuffCount[t][l - 1]; j++, k++) {
+        for (int j = 0; j < counts[l - 1] && k < 256; j++, k++) {
             len[sym[k]] = (uint8_t)l;
             code[sym[k]] = (uint16_t)next++;
         }
         next <<= 1;
     }
 }
+// a specification is usable if its codes fit their lengths (no over-subscription) and it has at most 256 symbols
+inline bool huff_counts_valid(const uint8_t counts[16]) {
+    unsigned next = 0, total = 0;
+    for (int l = 1; l <= 16; l++) {
+        next += counts[l - 1];
+        total += counts[l - 1];
+        if (next > (1u << l)) return false;
+        next <<= 1;
+    }
+    return total <= 256;
+}
+inline void huff_codes(int t, uint8_t len[256], uint16_t code[256]) { huff_codes_from(kHuffCount[t], huff_symbols(t), len, code); }
+
+// the code specification of the four tables a scan uses: DC of component 0, DC of components 1/2, then the AC tables
+struct HuffSpec { uint8_t counts[4][16]; uint8_t syms[4][256]; };
+inline void fixed_huff_spec(HuffSpec &H) {
+    memset(&H, 0, sizeof(H));
+    for (int t = 0; t < 4; t++) {
+        memcpy(H.counts[t], kHuffCount[t], 16);
+        memcpy(H.syms[t], huff_symbols(t), t < 2 ? 12 : 162);
+    }
+}
 
 inline int jpeg_extend(int v, int size) { return size && v < (1 << (size - 1)) ? v - ((1 << size) - 1) : v; }
 
-inline void build_vlc_tables(VlcTables &T) {
+// false: more long-code prefixes than the second-level area holds (never for the fixed tables)
+inline bool build_vlc_tables_from(VlcTables &T, const HuffSpec &H) {
     for (int i = 0; i < kVlcMaxEntries; i++) T.e[i] = kVlcBad | 1;
     int used = 0;
     for (int t = 0; t < 4; t++) {
         uint8_t len[256]; uint16_t code[256];
-        huff_codes(t, len, code);
+        huff_codes_from(H.counts[t], H.syms[t], len, code);
         T.base[t] = used;
         used += 1 << kVlcFirstBits;
         for (int s = 0; s < 256; s++) {
             if (!len[s]) continue;
             const int run = t < 2 ? 0 : (s >> 4), size = t < 2 ? s : (s & 15);
+            if (size > 15) return false;                   // the entry's size field has four bits
             const uint32_t ent = (uint32_t)(len[s] | (size << 5) | (run << 9));
             if (len[s] <= kVlcFirstBits) {
                 const int spare = kVlcFirstBits - len[s];
@@ -211,6 +235,7 @@ inline void build_vlc_tables(VlcTables &T) {
                 const int pre = code[s] >> (len[s] - kVlcFirstBits);
                 uint32_t &slot = T.e[T.base[t] + pre];
                 if (!(slot & kVlcPtr)) {
+                    if (used + (1 << kVlcSecondBits) > kVlcMaxEntries) return false;
                     slot = kVlcPtr | (uint32_t)used;
                     used += 1 << kVlcSecondBits;
                 }
@@ -222,7 +247,9 @@ inline void build_vlc_tables(VlcTables &T) {
         }
     }
     T.count = used;
+    return true;
 }
+inline void build_vlc_tables(VlcTables &T) { HuffSpec H; fixed_huff_spec(H); build_vlc_tables_from(T, H); }
 
 // Second view of the same codes, for the flat (one symbol per iteration, no DC/AC branch) token
 // kernel.  DC and AC symbols go through the same code: a block starts with kb = 0 (kb = zigzag
@@ -288,21 +315,24 @@ inline bool build_flat_vlc_table(FlatVlcTables &F, int t, const uint8_t counts[1
     return true;
 }
 
-inline void build_flat_vlc_tables(FlatVlcTables &F) {
+inline bool build_flat_vlc_tables_from(FlatVlcTables &F, const HuffSpec &H) {
     int used = 0;
     bool ok = true;
-    for (int t = 0; t < 4; t++) ok = build_flat_vlc_table(F, t, kHuffCount[t], huff_symbols(t), used) && ok;
+    for (int t = 0; t < 4; t++) ok = ok && build_flat_vlc_table(F, t, H.counts[t], H.syms[t], used);
     F.count = ok ? used : kFlatMaxEntries + 1;
+    return ok;
 }
+inline void build_flat_vlc_tables(FlatVlcTables &F) { HuffSpec H; fixed_huff_spec(H); build_flat_vlc_tables_from(F, H); }
 
-inline void build_dequant_tables(DequantTables &D) {
+inline void build_dequant_tables_from(DequantTables &D, const uint8_t qzz[2][64]) {
     for (int c = 0; c < 2; c++)
         for (int k = 0; k < 64; k++) {
             const uint32_t j = kZigzag[k];
-            D.zq[c][k] = j | ((uint32_t)kDecQuant[c][k] << 8);
-            D.tz[c][k] = (((j >> 1) * 128u + (j & 1u) * 2u) << 16) | (uint32_t)kDecQuant[c][k];
+            D.zq[c][k] = j | ((uint32_t)qzz[c][k] << 8);
+            D.tz[c][k] = (((j >> 1) * 128u + (j & 1u) * 2u) << 16) | (uint32_t)qzz[c][k];
         }
 }
+inline void build_dequant_tables(DequantTables &D) { build_dequant_tables_from(D, kDecQuant); }
 
 inline void build_amvlib_dequant_tables(AmvlibDequantTables &D) {
     for (int c = 0; c < 2; c++)

@@ -9,6 +9,7 @@
  *
  *   amvcuda_amv_decoder            replaces amv_decoder            (sp5xdec.c:203-212)
  *   amvcuda_sp5x_decoder           replaces sp5x_decoder           (sp5xdec.c:190-201; same callback, other framing)
+ *   amvcuda_mjpeg_decoder          replaces mjpeg_decoder          (mjpegdec.c:1356-1367; baseline 4:2:0 frames only)
  *   amvcuda_amv_encoder            replaces amv_encoder            (mjpegenc.c:485-494)
  *   amvcuda_adpcm_ima_amv_decoder  replaces adpcm_ima_amv_decoder  (adpcm.c:1535)
  *   amvcuda_adpcm_ima_amv_encoder  replaces adpcm_ima_amv_encoder  (adpcm.c:1535)
@@ -25,6 +26,7 @@
 typedef struct AmvCudaVideoDec {
     amv_ctx *h;
     AVFrame picture;
+    int configured;                      /* plain MJPEG: amv_mjpeg_configure has seen a frame */
 } AmvCudaVideoDec;
 
 static int amvcuda_dec_init(AVCodecContext *avctx)
@@ -87,6 +89,61 @@ AVCodec amvcuda_amv_decoder = {
 AVCodec amvcuda_sp5x_decoder = {
     "sp5x", CODEC_TYPE_VIDEO, CODEC_ID_SP5X, sizeof(AmvCudaVideoDec),
     amvcuda_dec_init, NULL, amvcuda_dec_close, amvcuda_dec_frame,
+};
+
+/* plain MJPEG: ff_mjpeg_decode_frame (mjpegdec.c:1106-1340) for baseline 4:2:0 frames.  The frame's own marker
+ * segments say how to decode it: amv_mjpeg_configure reads them from the first packet and again whenever a packet
+ * does not fit the current configuration (AMV_ST_HEADER); the picture size comes from SOF0 as in
+ * ff_mjpeg_decode_sof (:215-251, avcodec_set_dimensions).  quality = FF_QP2LAMBDA * max over the DQT tables of
+ * max(q[1], q[8]) >> 1 (:137-139, :1283-1286). */
+static int amvcuda_mjpeg_frame(AVCodecContext *avctx, void *data, int *data_size, uint8_t *buf, int buf_size)
+{
+    AmvCudaVideoDec *c = avctx->priv_data;
+    AVFrame *out = data;
+    uint64_t off = 0;
+    uint32_t size = (uint32_t)buf_size;
+    int32_t status = 0;
+    int w = avctx->width, h = avctx->height, attempt, i, qmax = 0;
+
+    for (attempt = 0; attempt < 2; attempt++) {
+        if (attempt == 1 || !c->configured) {
+            if (amv_mjpeg_configure(c->h, buf, size, &w, &h) != AMV_OK) return -1;      /* not a frame this path covers */
+            c->configured = 1;
+            if (w != avctx->width || h != avctx->height) avcodec_set_dimensions(avctx, w, h);
+        }
+        avctx->pix_fmt = PIX_FMT_YUVJ420P;
+        if (c->picture.data[0]) avctx->release_buffer(avctx, &c->picture);
+        c->picture.reference = 0;
+        if (avctx->get_buffer(avctx, &c->picture) < 0) return -1;
+        c->picture.pict_type = FF_I_TYPE;
+        c->picture.key_frame = 1;
+        if (amv_decode_frames_mjpeg(c->h, buf, (uint64_t)buf_size, &off, &size, 1, w, h,
+                                    c->picture.data[0], c->picture.data[1], c->picture.data[2],
+                                    c->picture.linesize[0], c->picture.linesize[1],
+                                    (uint64_t)c->picture.linesize[0] * h, (uint64_t)c->picture.linesize[1] * ((h + 1) / 2),
+                                    &status, AMV_MEM_HOST) != AMV_OK)
+            return -1;
+        if (!(status & AMV_ST_HEADER)) break;
+        if (attempt == 1) return -1;
+    }
+    for (i = 2; i + 69 <= buf_size && i < 4096; i++)                  /* the DQT segments in front of the scan */
+        if (buf[i] == 0xff && buf[i + 1] == 0xdb) {
+            int len = (buf[i + 2] << 8) | buf[i + 3], k;
+            for (k = i + 4; k + 65 <= i + 2 + len && k + 65 <= buf_size; k += 65) {
+                int q = (buf[k + 2] > buf[k + 9] ? buf[k + 2] : buf[k + 9]) >> 1;
+                if (q > qmax) qmax = q;
+            }
+            i += 1 + len;
+        } else if (buf[i] == 0xff && buf[i + 1] == 0xda) break;
+    *out = c->picture;
+    out->quality = qmax * FF_QP2LAMBDA;
+    *data_size = sizeof(AVFrame);
+    return buf_size;
+}
+
+AVCodec amvcuda_mjpeg_decoder = {
+    "mjpeg", CODEC_TYPE_VIDEO, CODEC_ID_MJPEG, sizeof(AmvCudaVideoDec),
+    amvcuda_dec_init, NULL, amvcuda_dec_close, amvcuda_mjpeg_frame,
 };
 
 /* ------------------------------------------------------------------------------ video encode */
@@ -241,6 +298,7 @@ void amvcuda_register_codecs(void)
     register_avcodec(&amvcuda_amv_encoder);
     register_avcodec(&amvcuda_amv_decoder);
     register_avcodec(&amvcuda_sp5x_decoder);
+    register_avcodec(&amvcuda_mjpeg_decoder);
     register_avcodec(&amvcuda_adpcm_ima_amv_encoder);
     register_avcodec(&amvcuda_adpcm_ima_amv_decoder);
 }

@@ -12,9 +12,9 @@
 #include <math.h>
 #include "avcodec.h"
 
-extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder, sp5x_decoder;
+extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder, sp5x_decoder, mjpeg_decoder, mjpeg_encoder;
 extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_decoder, amvcuda_adpcm_ima_amv_encoder,
-               amvcuda_sp5x_decoder;
+               amvcuda_sp5x_decoder, amvcuda_mjpeg_decoder;
 void amvcuda_register_codecs(void);
 
 static unsigned rng_state = 12345;
@@ -116,8 +116,8 @@ int main(int argc, char **argv)
     amvcuda_register_codecs();                       /* first match wins ...                              */
     register_avcodec(&amv_encoder); register_avcodec(&amv_decoder);   /* ... then what avcodec_register_all adds */
     register_avcodec(&adpcm_ima_amv_encoder); register_avcodec(&adpcm_ima_amv_decoder);
-    register_avcodec(&sp5x_decoder);
-    if (avcodec_find_decoder(CODEC_ID_AMV) != &amvcuda_amv_decoder || avcodec_find_decoder(CODEC_ID_SP5X) != &amvcuda_sp5x_decoder || avcodec_find_encoder(CODEC_ID_AMV) != &amvcuda_amv_encoder ||
+    register_avcodec(&sp5x_decoder); register_avcodec(&mjpeg_decoder);
+    if (avcodec_find_decoder(CODEC_ID_AMV) != &amvcuda_amv_decoder || avcodec_find_decoder(CODEC_ID_SP5X) != &amvcuda_sp5x_decoder || avcodec_find_decoder(CODEC_ID_MJPEG) != &amvcuda_mjpeg_decoder || avcodec_find_encoder(CODEC_ID_AMV) != &amvcuda_amv_encoder ||
         avcodec_find_decoder(CODEC_ID_ADPCM_IMA_AMV) != &amvcuda_adpcm_ima_amv_decoder ||
         avcodec_find_encoder(CODEC_ID_ADPCM_IMA_AMV) != &amvcuda_adpcm_ima_amv_encoder) {
         printf("FAIL: lookup does not return the drop-in codecs\n");
@@ -161,6 +161,18 @@ int main(int argc, char **argv)
                 if (memcmp(da, db, (size_t)m * fb)) { printf("FAIL: sp5x planes differ (quality %d)\n", quality); fail = 1; }
             }
             printf("sp5x  %dx%d x%d quality %d: planes %s\n", w, h, m, quality, fail ? "DIFFER" : "identical");
+        }
+        {   /* plain MJPEG: full JPEG frames from the reference's mjpeg_encoder (its rate control rewrites the DQT
+             * segment from frame to frame), decoded by the drop-in and by the reference's mjpeg_decoder */
+            Packet *pm = calloc(n, sizeof(Packet));
+            int mfail = 0;
+            ra = encode_all(&mjpeg_encoder, w, h, n, quality, ys, us, vs, pm);
+            if (ra) { printf("FAIL: reference mjpeg encode returned %d\n", ra); return 7; }
+            ra = decode_all(avcodec_find_decoder(CODEC_ID_MJPEG), w, h, n, pm, da);
+            rb = decode_all(&mjpeg_decoder, w, h, n, pm, db);
+            if (ra || rb) { printf("FAIL: mjpeg decode returned %d / %d\n", ra, rb); return 8; }
+            if (memcmp(da, db, (size_t)n * fb)) { printf("FAIL: mjpeg planes differ (quality %d)\n", quality); fail = 1; mfail = 1; }
+            printf("mjpeg %dx%d x%d quality %d: planes %s\n", w, h, n, quality, mfail ? "DIFFER" : "identical");
         }
         free(da); free(db);
     }

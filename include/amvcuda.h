@@ -73,7 +73,8 @@ enum {
     AMV_ST_MARKER    = 1 << 3,  /* FF xx marker inside the scan data cut it short (mjpegdec.c:1153-1157) */
     AMV_ST_OVERRUN   = 1 << 4,  /* decoder needed more bits than the packet holds */
     AMV_ST_RANGE     = 1 << 5,  /* offset/size outside the supplied buffer, or ADPCM step index > 88 */
-    AMV_ST_NOSPACE   = 1 << 6   /* encoder: packet does not fit the per-frame capacity */
+    AMV_ST_NOSPACE   = 1 << 6,  /* encoder: packet does not fit the per-frame capacity */
+    AMV_ST_HEADER    = 1 << 7   /* plain JPEG: the frame's marker segments differ from the configured header */
 };
 
 typedef struct amv_params {
@@ -153,6 +154,34 @@ AMV_API int amv_decode_frames_sp5x(amv_ctx *ctx,
                                    uint8_t *y, uint8_t *u, uint8_t *v,
                                    int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                                    int32_t *status, int mem);
+
+/*
+ * Plain baseline MJPEG: the `mjpeg_decoder` of the same source file (libavcodec/mjpegdec.c:1356-1367,
+ * ff_mjpeg_decode_frame :1106-1340) -- full JPEG frames that carry their own tables: DQT
+ * (ff_mjpeg_decode_dqt :113-145), DHT (ff_mjpeg_decode_dht :148-192), SOF0 (ff_mjpeg_decode_sof :194-345),
+ * SOS (ff_mjpeg_decode_sos :738-856).  The scan goes through the same kernels as AMV with those tables;
+ * the picture is stored top-down.
+ *
+ * amv_mjpeg_configure reads the marker segments of ONE sample frame (a HOST pointer; the AVCodec shim
+ * hands it the first packet): 8-bit SOF0, three components sampled 2x2 / 1x1 / 1x1 (YUVJ420P), components
+ * 1 and 2 sharing their quantiser and Huffman tables, sequential scan, no restart interval.  Anything else
+ * is AMV_ERR_UNSUPPORTED.  *w / *h receive the picture size (may be NULL).
+ *
+ * amv_decode_frames_mjpeg then decodes frames whose bytes up to the end of the SOS header equal the sample's
+ * outside the quantiser values: every frame is dequantised with the tables of its OWN DQT segment (the
+ * reference's mjpeg_encoder rewrites them whenever rate control moves the quantiser), while Huffman tables,
+ * geometry and segment layout must be the sample's.  Any other frame is left undecoded with AMV_ST_HEADER so
+ * the caller can group frames by header.  w, h must be the configured size.  Other arguments as
+ * amv_decode_frames.
+ */
+AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *jpeg, uint32_t size, int *w, int *h);
+AMV_API int amv_decode_frames_mjpeg(amv_ctx *ctx,
+                                    const uint8_t *pkts, uint64_t pkts_bytes,
+                                    const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
+                                    int w, int h,
+                                    uint8_t *y, uint8_t *u, uint8_t *v,
+                                    int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                                    int32_t *status, int mem);
 
 /*
  * amvlib flavour of the video decoder: what C-AMVDecoder/amvlib computes for the same packets --

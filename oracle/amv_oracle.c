@@ -451,16 +451,37 @@ static inline uint32_t br_peek(bitr *r, int n) { br_fill(r); return n ? (uint32_
 static inline void br_skip(bitr *r, int n) { r->acc <<= n; r->nacc -= n; }
 static inline size_t br_bits_used(const bitr *r) { return r->pos * 8 - (size_t)r->nacc; }
 
+/* the tables a scan is decoded with: the fixed AMV/SP5X ones (sp5x.h templates) or what a JPEG's own DQT /
+ * DHT segments carry.  Huffman slot t: 0 DC of component 0, 1 DC of components 1/2, 2/3 the AC tables. */
+typedef struct {
+    uint8_t cnt[4][16];      /* codes per length 1..16 */
+    uint8_t sym[4][256];     /* symbols in code order */
+    uint8_t qzz[2][64];      /* quantisers in zigzag (DQT) order: component 0, components 1/2 */
+} scan_tables;
+
+static const scan_tables *fixed_tables(void)
+{
+    static scan_tables T; static int ready;
+    if (!ready) {
+        memcpy(T.cnt, kCnt, sizeof(T.cnt));
+        memcpy(T.sym[0], kSymDC, 12); memcpy(T.sym[1], kSymDC, 12);
+        memcpy(T.sym[2], kSymACL, 162); memcpy(T.sym[3], kSymACC, 162);
+        memcpy(T.qzz, kDecQuantZZ, sizeof(T.qzz));
+        ready = 1;
+    }
+    return &T;
+}
+
 /* canonical decode: find the shortest length whose code range contains the
  * next bits (what the 9-bit two-level VLC of bitstream.h:813-839 resolves to) */
-static int huff_get(bitr *r, int t)
+static int huff_get(bitr *r, const scan_tables *T, int t)
 {
     uint32_t v = br_peek(r, 16);
     unsigned first = 0; int k = 0;
-    const uint8_t *sym = t < 2 ? kSymDC : (t == 2 ? kSymACL : kSymACC);
+    const uint8_t *sym = T->sym[t];
     for (int len = 1; len <= 16; len++) {
         unsigned c = v >> (16 - len);
-        int cnt = kCnt[t][len - 1];
+        int cnt = T->cnt[t][len - 1];
         if (c >= first && c < first + cnt) { br_skip(r, len); return sym[k + (c - first)]; }
         k += cnt;
         first = (first + cnt) << 1;
@@ -508,13 +529,14 @@ AMVO_API size_t amvo_unstuff(const uint8_t *pkt, uint32_t size, uint8_t *dst, in
  * bottom-up placement (mjpegdec.c:672-677), 0 for SP5X */
 static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int flip,
                        uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
-                       int16_t *coef_dump, uint8_t *uy, uint8_t *uu, uint8_t *uv)
+                       int16_t *coef_dump, uint8_t *uy, uint8_t *uu, uint8_t *uv, const scan_tables *T)
 {
     build_tables();
+    if (!T) T = fixed_tables();
     const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
     const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
     int16_t q[2][64];                                       /* raster order (mjpegdec.c:131-134) */
-    for (int t = 0; t < 2; t++) for (int k = 0; k < 64; k++) q[t][g_zz[k]] = kDecQuantZZ[t][k];
+    for (int t = 0; t < 2; t++) for (int k = 0; k < 64; k++) q[t][g_zz[k]] = T->qzz[t][k];
     bitr br = { scan, nscan, 0, 0, 0, 0 };
     int pred[3] = { 1024, 1024, 1024 };                     /* mjpegdec.c:805-806 */
     const int y0 = flip_start_row(h, 2), c0 = flip_start_row(h, 1);
@@ -525,12 +547,12 @@ static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int
     for (int b = 0; b < 6; b++, nblk++) {
         const int comp = b < 4 ? 0 : b - 3, tq = comp ? 1 : 0;
         int16_t blk[64] = { 0 };
-        int s = huff_get(&br, tq);
+        int s = huff_get(&br, T, tq);
         if (s < 0) { flags |= AMVO_E_BADCODE; break; }
         pred[comp] += get_extend(&br, s) * q[tq][0];
         blk[0] = (int16_t)pred[comp];
         for (int k = 0;;) {
-            int rs = huff_get(&br, 2 + tq);
+            int rs = huff_get(&br, T, 2 + tq);
             if (rs < 0) { flags |= AMVO_E_BADCODE; break; }
             if (rs == 0x00) break;                           /* EOB */
             if (rs == 0xf0) { k += 16; continue; }           /* ZRL: no range check (:400-401) */
@@ -579,7 +601,7 @@ AMVO_API int amvo_decode_frame_ex(const uint8_t *pkt, uint32_t size, int w, int 
     int flags = 0;
     uint8_t *scan = (uint8_t *)malloc((size_t)size + 16);
     size_t nscan = amvo_unstuff(pkt, size, scan, &flags);
-    flags = decode_scan(scan, nscan, flags, w, h, 1, py, pu, pv, ls_y, ls_c, coef_dump, uy, uu, uv);
+    flags = decode_scan(scan, nscan, flags, w, h, 1, py, pu, pv, ls_y, ls_c, coef_dump, uy, uu, uv, NULL);
     free(scan);
     return flags;
 }
@@ -596,7 +618,7 @@ AMVO_API int amvo_sp5x_decode_frame(const uint8_t *pkt, uint32_t size, int w, in
     uint8_t *scan = (uint8_t *)malloc(npay + 16);
     if (npay) memcpy(scan, pkt + 14, npay);
     scan[npay] = 0xff;
-    flags = decode_scan(scan, npay + 1, flags, w, h, 0, py, pu, pv, ls_y, ls_c, NULL, uy, uu, uv);
+    flags = decode_scan(scan, npay + 1, flags, w, h, 0, py, pu, pv, ls_y, ls_c, NULL, uy, uu, uv, NULL);
     free(scan);
     return flags;
 }
@@ -610,6 +632,130 @@ AMVO_API int amvo_sp5x_decode_frames(const uint8_t *pkts, const uint64_t *off, c
         size_t yo = (size_t)i * w * h, co = (size_t)i * cw * chh;
         int st = amvo_sp5x_decode_frame(pkts + off[i], size[i], w, h, y + yo, u + co, v + co, w, cw,
                                         uy ? uy + yo : NULL, uu ? uu + co : NULL, uv ? uv + co : NULL);
+        if (status) status[i] = st;
+    }
+    return n;
+}
+
+/* ---- plain baseline MJPEG: the `mjpeg_decoder` of the same source (ff_mjpeg_decode_frame mjpegdec.c:1106-1340)
+ * on a full JPEG whose tables travel in the stream.  Header walk: find_marker (:1076-1104) + the segment parsers
+ * ff_mjpeg_decode_dqt (:113-145, 8-bit tables, zigzag order), ff_mjpeg_decode_dht (:148-192), ff_mjpeg_decode_sof
+ * (:194-345, 8 bits, pix_fmt_id 0x221111 = 4:2:0), ff_mjpeg_decode_sos (:738-856; last_dc = 1024 :805-806,
+ * 16x16 MCUs :808-811), mjpeg_decode_dri (:858-867).  Supported: SOF0, three components sampled 2x2 / 1x1 / 1x1,
+ * components 1 and 2 sharing their quantiser and Huffman tables, no restart interval; anything else is
+ * AMVO_E_HEADER.  The scan is un-stuffed and decoded exactly like AMV's (same functions), top-down. */
+enum { AMVO_E_HEADER = 128 };
+typedef struct { int w, h; uint32_t scan_start; scan_tables T; } mjpeg_header;
+
+static int mjpeg_parse(const uint8_t *p, uint32_t size, mjpeg_header *H)
+{
+    uint8_t q[4][64]; int have_q[4] = { 0, 0, 0, 0 };
+    uint8_t hc[2][4][16], hs[2][4][256]; int have_h[2][4] = { { 0 } };
+    int comp_id[3], comp_q[3], have_sof = 0;
+    uint32_t i = 0;
+    if (size < 4 || p[0] != 0xff || p[1] != 0xd8) return -1;
+    i = 2;
+    while (i + 4 <= size) {
+        if (p[i] != 0xff) { i++; continue; }
+        const int m = p[i + 1];
+        if (m < 0xc0 || m == 0xff) { i++; continue; }                   /* find_marker: FF followed by C0..FE */
+        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7)) { i += 2; continue; }
+        if (m == 0xd9) return -1;                                        /* EOI before any scan */
+        const uint32_t len = ((uint32_t)p[i + 2] << 8) | p[i + 3];
+        if (len < 2 || i + 2 + len > size) return -1;
+        const uint8_t *d = p + i + 4; uint32_t n = len - 2;
+        if (m == 0xdb) {                                                 /* DQT */
+            while (n >= 65) {
+                if (d[0] >> 4) return -1;                                /* 16-bit tables (:121-125) */
+                const int id = d[0] & 15; if (id >= 4) return -1;
+                memcpy(q[id], d + 1, 64); have_q[id] = 1;
+                d += 65; n -= 65;
+            }
+        } else if (m == 0xc4) {                                          /* DHT */
+            while (n > 0) {
+                if (n < 17) return -1;
+                const int cls = d[0] >> 4, id = d[0] & 15; int tot = 0;
+                if (cls >= 2 || id >= 4) return -1;
+                for (int k = 0; k < 16; k++) tot += d[1 + k];
+                if (tot > 256 || n < 17u + (uint32_t)tot) return -1;
+                memcpy(hc[cls][id], d + 1, 16); memset(hs[cls][id], 0, 256); memcpy(hs[cls][id], d + 17, tot);
+                have_h[cls][id] = 1;
+                d += 17 + tot; n -= 17 + tot;
+            }
+        } else if (m == 0xc0) {                                          /* SOF0 */
+            if (n < 15 || d[0] != 8 || d[5] != 3) return -1;
+            H->h = (d[1] << 8) | d[2]; H->w = (d[3] << 8) | d[4];
+            static const uint8_t want[3] = { 0x22, 0x11, 0x11 };
+            for (int c = 0; c < 3; c++) {
+                comp_id[c] = d[6 + 3 * c];
+                if (d[7 + 3 * c] != want[c]) return -1;
+                comp_q[c] = d[8 + 3 * c]; if (comp_q[c] >= 4) return -1;
+            }
+            if (comp_q[1] != comp_q[2]) return -1;
+            have_sof = 1;
+        } else if (m >= 0xc1 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
+            return -1;                                                   /* other SOFn: not baseline */
+        } else if (m == 0xdd) {                                          /* DRI */
+            if (n < 2 || ((d[0] << 8) | d[1]) != 0) return -1;
+        } else if (m == 0xda) {                                          /* SOS */
+            if (!have_sof || n < 10 || d[0] != 3 || len != 6 + 2 * 3) return -1;
+            int td[3], ta[3];
+            for (int c = 0; c < 3; c++) {
+                if (d[1 + 2 * c] != comp_id[c]) return -1;               /* components in frame order */
+                td[c] = d[2 + 2 * c] >> 4; ta[c] = d[2 + 2 * c] & 15;
+                if (td[c] >= 4 || ta[c] >= 4 || !have_h[0][td[c]] || !have_h[1][ta[c]]) return -1;
+            }
+            if (td[1] != td[2] || ta[1] != ta[2]) return -1;
+            if (d[7] != 0 || d[8] != 63 || d[9] != 0) return -1;         /* Ss, Se, Ah/Al of a sequential scan */
+            if (!have_q[comp_q[0]] || !have_q[comp_q[1]]) return -1;
+            for (int c = 0; c < 2; c++) {
+                memcpy(H->T.cnt[c], hc[0][td[c]], 16);     memcpy(H->T.sym[c], hs[0][td[c]], 256);
+                memcpy(H->T.cnt[2 + c], hc[1][ta[c]], 16); memcpy(H->T.sym[2 + c], hs[1][ta[c]], 256);
+                memcpy(H->T.qzz[c], q[comp_q[c]], 64);
+            }
+            H->scan_start = i + 2 + len;
+            return 0;
+        }
+        i += 2 + len;
+    }
+    return -1;
+}
+
+AMVO_API int amvo_mjpeg_header(const uint8_t *pkt, uint32_t size, int *w, int *h, uint32_t *scan_start)
+{
+    mjpeg_header H;
+    if (mjpeg_parse(pkt, size, &H)) return -1;
+    if (w) *w = H.w;
+    if (h) *h = H.h;
+    if (scan_start) *scan_start = H.scan_start;
+    return 0;
+}
+
+AMVO_API int amvo_mjpeg_decode_frame(const uint8_t *pkt, uint32_t size, int w, int h,
+                                     uint8_t *py, uint8_t *pu, uint8_t *pv, int ls_y, int ls_c,
+                                     uint8_t *uy, uint8_t *uu, uint8_t *uv /* optional undefined-domain masks */)
+{
+    mjpeg_header H;
+    if (mjpeg_parse(pkt, size, &H) || H.w != w || H.h != h) return AMVO_E_HEADER;
+    /* the scan runs from the end of the SOS header to the next marker (:1137-1160); amvo_unstuff works on
+     * pkt[2 .. size-2) ++ FF D9, so hand it the packet from two bytes before the scan */
+    int flags = 0;
+    uint8_t *scan = (uint8_t *)malloc((size_t)size + 16);
+    size_t nscan = amvo_unstuff(pkt + H.scan_start - 2, size - (H.scan_start - 2), scan, &flags);
+    flags = decode_scan(scan, nscan, flags, w, h, 0, py, pu, pv, ls_y, ls_c, NULL, uy, uu, uv, &H.T);
+    free(scan);
+    return flags;
+}
+
+AMVO_API int amvo_mjpeg_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                                      int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int *status,
+                                      uint8_t *uy, uint8_t *uu, uint8_t *uv)
+{
+    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    for (int i = 0; i < n; i++) {
+        size_t yo = (size_t)i * w * h, co = (size_t)i * cw * chh;
+        int st = amvo_mjpeg_decode_frame(pkts + off[i], size[i], w, h, y + yo, u + co, v + co, w, cw,
+                                         uy ? uy + yo : NULL, uu ? uu + co : NULL, uv ? uv + co : NULL);
         if (status) status[i] = st;
     }
     return n;
@@ -986,6 +1132,7 @@ AMVO_API int amvo_amvlib_decode_frame_ex(const uint8_t *pkt, uint32_t size, int 
     size_t nscan = 0;
     for (size_t i = 2; i < size; i++) { scan[nscan++] = pkt[i]; if (pkt[i] == 0xff) i++; }
     bitr br = { scan, nscan, 0, 0, 0, 0 };
+    const scan_tables *T = fixed_tables();
     int16_t pred[3] = { 0, 0, 0 };
     const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
     int nblk = 0;
@@ -996,12 +1143,12 @@ AMVO_API int amvo_amvlib_decode_frame_ex(const uint8_t *pkt, uint32_t size, int 
         for (int b = 0; b < 6; b++, nblk++) {
             const int comp = b < 4 ? 0 : b - 3, tq = comp ? 1 : 0;
             int16_t zz[64] = { 0 };
-            int s = huff_get(&br, tq);
+            int s = huff_get(&br, T, tq);
             if (s < 0) { flags |= AMVO_E_BADCODE; break; }
             pred[comp] = (int16_t)(pred[comp] + (int16_t)get_extend(&br, s));
             zz[0] = pred[comp];
             for (int k = 1; k < 64;) {
-                int rs = huff_get(&br, 2 + tq);
+                int rs = huff_get(&br, T, 2 + tq);
                 if (rs < 0) { flags |= AMVO_E_BADCODE; break; }
                 if (rs == 0x00) break;
                 k += rs >> 4;                                   /* run of zeros, then one value (0 for ZRL) */

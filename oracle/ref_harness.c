@@ -38,9 +38,30 @@ const char *amvref_version(void) { return "amv-codec-tools AMVmuxer libavcodec "
  * quality = AVFrame.quality (lambda; 0 => reference default qscale 2).
  * Packets are written back to back into out[0..cap); off[i]/size[i] locate them.
  * Returns number of frames encoded, or a negative error. */
+static int encode_frames_with(AVCodec *codec, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                              int n, int w, int h, int quality,
+                              uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap);
+
 int amvref_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
                          int n, int w, int h, int quality,
                          uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
+{
+    return encode_frames_with(&amv_encoder, y, u, v, n, w, h, quality, out, off, size, cap);
+}
+
+/* the plain MJPEG codecs of the same source files (mjpegenc.c:474-483, mjpegdec.c:1361-1372): full JPEG
+ * frames with their tables in the stream, top-down pictures */
+extern AVCodec mjpeg_encoder, mjpeg_decoder;
+int amvref_mjpeg_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                               int n, int w, int h, int quality,
+                               uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
+{
+    return encode_frames_with(&mjpeg_encoder, y, u, v, n, w, h, quality, out, off, size, cap);
+}
+
+static int encode_frames_with(AVCodec *codec, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                              int n, int w, int h, int quality,
+                              uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
 {
     ref_init();
     AVCodecContext *c = avcodec_alloc_context();
@@ -52,7 +73,7 @@ int amvref_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
     c->width = w; c->height = h;
     c->time_base.num = 1; c->time_base.den = 16;
     c->pix_fmt = PIX_FMT_YUVJ420P;
-    if (avcodec_open(c, &amv_encoder) < 0) { ret = -2; goto done; }
+    if (avcodec_open(c, codec) < 0) { ret = -2; goto done; }
     for (i = 0; i < n; i++) {
         /* amv_encode_picture mutates data[]/linesize[] (mjpegenc.c:467-470): refill every frame */
         pic->data[0] = (uint8_t *)y + (size_t)i * w * h;
@@ -95,6 +116,13 @@ int amvref_sp5x_decode_frames(const uint8_t *pkts, const uint64_t *off, const ui
                               uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes)
 {
     return decode_frames_with(&sp5x_decoder, pkts, off, size, n, w, h, y, u, v, got, ret_bytes);
+}
+
+int amvref_mjpeg_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
+                               int n, int w, int h,
+                               uint8_t *y, uint8_t *u, uint8_t *v, int *got, int *ret_bytes)
+{
+    return decode_frames_with(&mjpeg_decoder, pkts, off, size, n, w, h, y, u, v, got, ret_bytes);
 }
 
 static int decode_frames_with(AVCodec *codec, const uint8_t *pkts, const uint64_t *off, const uint32_t *size,

@@ -187,6 +187,27 @@ class Oracle(_AmvlibOracleMixin):
                                          _p(m[0]), _p(m[1]), _p(m[2]))
         return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
 
+    def mjpeg_header(self, pkt):
+        """-> (w, h, scan_start) of a baseline 4:2:0 JPEG the path supports, or None"""
+        pk = np.ascontiguousarray(pkt, np.uint8)
+        w, h, ss = C.c_int(0), C.c_int(0), C.c_uint32(0)
+        if self.lib.amvo_mjpeg_header(_p(pk), len(pk), C.byref(w), C.byref(h), C.byref(ss)):
+            return None
+        return w.value, h.value, ss.value
+
+    def mjpeg_decode_frames(self, pkts, off, size, w, h, undef=False):
+        n = len(size)
+        cw, ch = chroma_dims(w, h)
+        y = np.zeros((n, h, w), np.uint8)
+        u = np.zeros((n, ch, cw), np.uint8)
+        v = np.zeros((n, ch, cw), np.uint8)
+        m = [np.zeros_like(a) for a in (y, u, v)] if undef else [None] * 3
+        st = np.zeros(n, np.int32)
+        self.lib.amvo_mjpeg_decode_frames(_p(np.ascontiguousarray(pkts, np.uint8)), _p(np.ascontiguousarray(off, np.uint64)),
+                                          _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v), _p(st),
+                                          _p(m[0]), _p(m[1]), _p(m[2]))
+        return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
+
     def decode_frame_coefs(self, pkt, w, h):
         """Dequantised coefficients of every block in bitstream order (raster inside a block)."""
         mbw, mbh = (w + 15) // 16, (h + 15) // 16
@@ -313,7 +334,20 @@ class Ref:
             raise RuntimeError("reference encode failed: %d" % r)
         return out[: int(size.sum())].copy(), off, size
 
-    def decode_frames(self, pkts, off, size, w, h, sp5x=False):
+    def mjpeg_encode_frames(self, y, u, v, w, h, quality=0, cap=None):
+        """the reference's plain MJPEG encoder (full JPEG frames, tables in the stream)"""
+        n = y.shape[0]
+        cap = cap or n * (w * h * 3 + 4096)
+        out = np.zeros(cap, np.uint8)
+        off = np.zeros(n, np.uint64)
+        size = np.zeros(n, np.uint32)
+        r = self.lib.amvref_mjpeg_encode_frames(_p(y), _p(u), _p(v), n, w, h, int(quality), _p(out), _p(off), _p(size),
+                                                C.c_uint64(cap))
+        if r != n:
+            raise RuntimeError("reference mjpeg encode failed: %d" % r)
+        return out[: int(size.sum())].copy(), off, size
+
+    def decode_frames(self, pkts, off, size, w, h, sp5x=False, mjpeg=False):
         n = len(size)
         cw, ch = chroma_dims(w, h)
         y = np.zeros((n, h, w), np.uint8)
@@ -322,6 +356,8 @@ class Ref:
         got = np.zeros(n, np.int32)
         rb = np.zeros(n, np.int32)
         fn = self.lib.amvref_sp5x_decode_frames if sp5x else self.lib.amvref_decode_frames
+        if mjpeg:
+            fn = self.lib.amvref_mjpeg_decode_frames
         r = fn(_p(np.ascontiguousarray(pkts, np.uint8)),
                                           _p(np.ascontiguousarray(off, np.uint64)),
                                           _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v),
@@ -491,6 +527,19 @@ def sp5x_from_amv(oracle, pkts, off, size, header=None):
         assert fl == 0 and scan[-1] == 0xFF
         out.append(hdr + scan[:-1].tobytes())          # the trailing FF is the appended EOI's, not payload
     return pack(out)
+
+
+def mjpeg_with_dqt(pkts, off, size, seed):
+    """the same JPEG frames with the 64 quantisers of their (first) DQT segment replaced by seeded values 1..60:
+    same scan, other dequantisation -- every frame gets the same table, so the headers stay identical"""
+    out = np.array(pkts, np.uint8, copy=True)
+    q = np.random.default_rng(seed).integers(1, 61, 64).astype(np.uint8)
+    for o, s in zip(off, size):
+        d = out[int(o): int(o) + int(s)]
+        j = bytes(d[:1024]).find(b"\xff\xdb")
+        assert j > 0 and d[j + 4] == 0
+        d[j + 5: j + 5 + 64] = q
+    return out
 
 
 def pack(chunks):

@@ -536,6 +536,94 @@ def test_sp5x_decode_golden(ctx, oracle, case):
         assert np.array_equal(got[m == 0], want[m == 0])
 
 
+# ------------------------------------------------------------------ plain MJPEG
+GMJ = np.load(os.path.join(os.path.dirname(__file__), "golden", "mjpeg_golden.npz"))
+MJPEG_CASES = bytes(GMJ["cases"]).decode().split("\n")
+
+
+@pytest.mark.parametrize("case", MJPEG_CASES)
+@pytest.mark.parametrize("log2p", [0, 3])
+def test_mjpeg_decode_golden(ctx, oracle, case, log2p):
+    """amv_mjpeg_configure + amv_decode_frames_mjpeg vs what the reference's mjpeg_decoder made of the same frames
+    (tables from the stream's own DQT / DHT segments, some with non-standard quantisers)"""
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    pk, off, sz = GMJ[case + "/pk"], GMJ[case + "/off"], GMJ[case + "/sz"]
+    assert ctx.mjpeg_configure(pk[int(off[0]): int(off[0]) + int(sz[0])]) == (w, h)
+    ctx.set_option("decode_log2_lanes", log2p)
+    try:
+        dy, du, dv, st = ctx.decode_frames(pk, off, sz, w, h, mjpeg=True)
+    finally:
+        ctx.set_option("decode_log2_lanes", -1)
+    assert (st == 0).all()
+    _, _, _, _, masks = oracle.mjpeg_decode_frames(pk, off, sz, w, h, undef=True)
+    for got, want, m in zip((dy, du, dv), (GMJ[case + "/dy"], GMJ[case + "/du"], GMJ[case + "/dv"]), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])
+
+
+def test_mjpeg_device_buffers_mixed_headers_and_errors(ctx, oracle):
+    """device-resident packets at unaligned offsets; a frame with another header is flagged, not decoded;
+    unsupported headers are refused by amv_mjpeg_configure"""
+    import torch
+    a, b = "sinus_160x120_dx", "sinus_208x176_d3"
+    w, h = 160, 120
+    pk, off, sz = GMJ[a + "/pk"], GMJ[a + "/off"], GMJ[a + "/sz"]
+    other = GMJ[b + "/pk"][: int(GMJ[b + "/sz"][0])]
+    frames = [pk[int(o): int(o) + int(s)].tobytes() for o, s in zip(off, sz)]
+    bk, boff, bsz = pack([b"\x00" * 5 + frames[0], other.tobytes(), frames[1], frames[0][:300]])
+    boff[0] += 5; bsz[0] -= 5
+    assert ctx.mjpeg_configure(frames[0]) == (w, h)
+    n = 4
+    cw, ch = chroma_dims(w, h)
+    Y = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+    U = torch.zeros((n, ch, cw), dtype=torch.uint8, device="cuda")
+    V = torch.zeros((n, ch, cw), dtype=torch.uint8, device="cuda")
+    st = torch.zeros(n, dtype=torch.int32, device="cuda")
+    dk = torch.from_numpy(bk.copy()).cuda()
+    doff, dsz = torch.from_numpy(boff.astype(np.int64)).cuda(), torch.from_numpy(bsz.astype(np.int32)).cuda()
+    ctx.decode_frames_raw(dk, dk.numel(), doff, dsz, n, w, h, Y, U, V, w, cw, w * h, cw * ch, st, amv.MEM_DEVICE, mjpeg=True)
+    ctx.sync()
+    st = st.cpu().numpy()
+    assert st[0] == 0 and st[2] == 0 and st[1] & amv.ST_HEADER and st[3] != 0
+    assert np.array_equal(Y[0].cpu().numpy(), GMJ[a + "/dy"][0]) and np.array_equal(Y[2].cpu().numpy(), GMJ[a + "/dy"][1])
+    assert np.array_equal(V[2].cpu().numpy(), GMJ[a + "/dv"][1])
+    # wrong dimensions for the configured header; headers outside the contract
+    with pytest.raises(amv.AmvError):
+        ctx.decode_frames(bk, boff, bsz, w + 16, h, mjpeg=True)
+    good = np.frombuffer(frames[0], np.uint8)
+    j = frames[0].find(b"\xff\xc0")
+    for pos, val in ((j + 4, 12), (j + 11, 0x21), (j + 1, 0xc2)):
+        bad = good.copy()
+        bad[pos] = val
+        with pytest.raises(amv.AmvError):
+            ctx.mjpeg_configure(bad)
+    with pytest.raises(amv.AmvError):
+        ctx.mjpeg_configure(good[:100])
+
+
+@pytest.mark.parametrize("w,h,kind", [(320, 240, "sinus"), (208, 176, "noise"), (102, 56, "edges")])
+def test_mjpeg_decode_vs_oracle_larger_batch(ctx, oracle, w, h, kind):
+    """JPEG frames assembled from the oracle's AMV scans behind a reference-made header with the fixed AMV tables
+    replaced by the stream's own: checks the table path against the oracle on more frames than the golden set holds"""
+    case = "sinus_160x120_dx"
+    hdr_src = GMJ[case + "/pk"][: int(GMJ[case + "/sz"][0])]
+    ow, oh, start = oracle.mjpeg_header(hdr_src)
+    hdr = hdr_src[:start].copy()
+    j = hdr.tobytes().find(b"\xff\xc0")
+    hdr[j + 5], hdr[j + 6], hdr[j + 7], hdr[j + 8] = h >> 8, h & 255, w >> 8, w & 255
+    n = 24
+    y, u, v = synth_frames(n, w, h, seed=95, kind=kind)
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 3)
+    frames = [hdr.tobytes() + pk[int(o) + 2: int(o) + int(s)].tobytes() for o, s in zip(off, sz)]   # header | scan | EOI
+    mk, moff, msz = pack(frames)
+    assert ctx.mjpeg_configure(frames[0]) == (w, h)
+    dy, du, dv, st = ctx.decode_frames(mk, moff, msz, w, h, mjpeg=True)
+    wy, wu, wv, wst, masks = oracle.mjpeg_decode_frames(mk, moff, msz, w, h, undef=True)
+    assert (st == 0).all() and (wst == 0).all()
+    for got, want, m in zip((dy, du, dv), (wy, wu, wv), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])
+
+
 # ------------------------------------------------------------------ range conversion (SURVEY 8f-3)
 @pytest.mark.parametrize("direction", [0, 1])
 @pytest.mark.parametrize("w,h", [(320, 240), (208, 176), (102, 56), (16, 16)])

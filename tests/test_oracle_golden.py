@@ -137,6 +137,21 @@ def test_sp5x_decode_matches_golden(oracle, case):
         assert np.array_equal(got[m == 0], want[m == 0])
 
 
+# ------------------------------------------------------------------ plain MJPEG
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "mjpeg_golden.npz"))
+MJPEG_CASES = bytes(GM["cases"]).decode().split("\n")
+
+
+@pytest.mark.parametrize("case", MJPEG_CASES)
+def test_mjpeg_decode_matches_golden(oracle, case):
+    kind, dims, q = case.split("_")
+    w, h = map(int, dims.split("x"))
+    y, u, v, st, masks = oracle.mjpeg_decode_frames(GM[case + "/pk"], GM[case + "/off"], GM[case + "/sz"], w, h, undef=True)
+    assert (st == 0).all()
+    for got, want, m in zip((y, u, v), (GM[case + "/dy"], GM[case + "/du"], GM[case + "/dv"]), masks):
+        assert np.array_equal(got[m == 0], want[m == 0])
+
+
 def test_range_conversion_tables(oracle):
     """known answers of the four tables (colorspace.h:69-84 with SCALEBITS 10): ends, mid points, clamps"""
     v = np.arange(256, dtype=np.uint8).reshape(1, 16, 16)

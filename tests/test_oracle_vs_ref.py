@@ -301,3 +301,41 @@ def test_adpcm_trellis_matches_reference(oracle, ref, kind, trellis):
     # and the decoder reads it back (any trellis output is an ordinary chunk)
     dp, _, st = oracle.adpcm_decode(out, off, size)
     assert (st == 0).all() and len(dp) == int(cons.sum())
+
+
+# ------------------------------------------------------------------ plain MJPEG (mjpeg_decoder of mjpegdec.c)
+from oracle_lib import mjpeg_with_dqt  # noqa: E402
+
+
+@pytest.mark.parametrize("dqt_seed", [None, 7])
+@pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (320, 240, "sinus"), (208, 176, "noise"), (128, 96, "edges"),
+                                      (48, 40, "flat"), (16, 16, "sinus"), (72, 24, "noise"), (102, 56, "sinus")])
+def test_mjpeg_decode_identical(oracle, ref, w, h, kind, dqt_seed):
+    """full JPEG frames from the reference's mjpeg_encoder (COM, DQT, DHT, SOF0, SOS in every frame), also with the
+    quantiser table overwritten: the reference's mjpeg_decoder vs the oracle's header walk + scan decode"""
+    n = 3 if w * h > 40000 else 6
+    y, u, v = synth_frames(n, w, h, seed=33, kind=kind)
+    pk, off, sz = ref.mjpeg_encode_frames(y, u, v, w, h)
+    if dqt_seed is not None:
+        pk = mjpeg_with_dqt(pk, off, sz, dqt_seed)
+    hw, hh, start = oracle.mjpeg_header(pk[int(off[0]): int(off[0]) + int(sz[0])])
+    assert (hw, hh) == (w, h) and 500 < start < 700
+    ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h, mjpeg=True)
+    oy, ou, ov, st, masks = oracle.mjpeg_decode_frames(pk, off, sz, w, h, undef=True)
+    assert (got != 0).all() and (st == 0).all()
+    for a, b, m in zip((oy, ou, ov), (ry, ru, rv), masks):
+        assert np.array_equal(a[m == 0], b[m == 0])
+
+
+def test_mjpeg_header_rejects_what_the_path_does_not_cover(oracle, ref):
+    w, h = 32, 32
+    y, u, v = synth_frames(1, w, h, seed=34, kind="sinus")
+    pk, off, sz = ref.mjpeg_encode_frames(y, u, v, w, h)
+    good = pk[: int(sz[0])]
+    assert oracle.mjpeg_header(good) is not None
+    j = bytes(good).find(b"\xff\xc0")
+    for edit in ((j + 4, 12), (j + 11, 0x21), (j + 1, 0xc2)):        # 12-bit samples, 4:2:2 sampling, progressive SOF2
+        bad = good.copy()
+        bad[edit[0]] = edit[1]
+        assert oracle.mjpeg_header(bad) is None
+    assert oracle.mjpeg_header(good[:100]) is None and oracle.mjpeg_header(good[2:]) is None
