@@ -320,8 +320,6 @@ int ensure_pipeline(amv_ctx *ctx, size_t meta_bytes) {
     if (meta_bytes > ctx->pinned_meta_cap) {
         CK(cudaStreamSynchronize(ctx->s_out));
         if (ctx->pinned_meta) cudaFreeHost(ctx->pinned_meta);
-    if (ctx->mj_tables) cudaFree(ctx->mj_tables);
-    if (ctx->mj_hdr) cudaFree(ctx->mj_hdr);
         ctx->pinned_meta = nullptr; ctx->pinned_meta_cap = 0;
         CK(cudaMallocHost(&ctx->pinned_meta, meta_bytes + 4096));
         ctx->pinned_meta_cap = meta_bytes + 4096;
@@ -662,6 +660,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
 
 AMV_API int64_t amv_get_stat(amv_ctx *ctx, const char *key) {
     if (!ctx || !key) return -1;
+    // what amv_mjpeg_configure read: bytes in front of the scan, where the per-frame quantisers sit
+    if (!strcmp(key, "mjpeg_header_bytes")) return ctx->mj_hdr_len;
+    if (!strcmp(key, "mjpeg_quant_offset_0")) return ctx->mj_qpos[0];
+    if (!strcmp(key, "mjpeg_quant_offset_1")) return ctx->mj_qpos[1];
+    if (!strcmp(key, "mjpeg_sync_table")) return ctx->mj_sync_ok ? 1 : 0;
     // "<kernel>_kernel_ns" / "<kernel>_kernel_launches": device time and launch count of one hot kernel
     // accumulated since the last query of that key pair (needs option profile_events = 1)
     for (int k = 0; k < KK_COUNT; k++) {
