@@ -23,7 +23,7 @@ struct DevBuf {
 };
 
 enum WsId {
-    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS, WS_TOKENS, WS_BLKOFF, WS_QTAB,
+    WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS, WS_TOKENS, WS_BLKOFF, WS_QTAB, WS_REDO,
     // device mirrors of host arguments (AMV_MEM_HOST calls)
     WS_H_A, WS_H_B, WS_H_C, WS_H_D, WS_H_E, WS_H_F, WS_H_G, WS_H_H, WS_H_I,
     WS_COUNT
@@ -55,6 +55,7 @@ struct amv_ctx {
     void *pinned_meta = nullptr;
     size_t pinned_meta_cap = 0;
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
+    bool opt_encode_rounds = true;      // encoder: k_encode16 (homogeneous rounds) + k_encode for the frames it hands back
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
     // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
@@ -244,12 +245,15 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
     const Geom g = make_geom(w, h);
     int32_t *st = status;
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
+    int32_t *redo = nullptr;
+    if (ctx->opt_encode_rounds) ENSURE(WS_REDO, sizeof(int32_t) * n, redo);
+    const int enc_launches = redo ? 2 : 1;
     if (layout == AMV_LAYOUT_SLOTS) {
         if (slot_base + (uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
         { ScopedTimer tm(ctx, KK_ENCODE);
-          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out + slot_base, pkt_cap, pkt_cap, out_size, st, ctx->stream); }
+          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out + slot_base, pkt_cap, pkt_cap, out_size, st, redo, ctx->stream); }
         launch_slot_offsets(out_off, n, pkt_cap, slot_base, ctx->stream);
-        return check_launch(ctx, "encode kernels", 2);
+        return check_launch(ctx, "encode kernels", 1 + enc_launches);
     }
     // packed: encode into 16-byte aligned workspace slots, scan the sizes, compact
     const uint64_t stride = ((uint64_t)pkt_cap + 15) & ~15ull;
@@ -265,11 +269,11 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
         const int m = n - f0 < sub ? n - f0 : sub;
         { ScopedTimer tm(ctx, KK_ENCODE);
           launch_encode(y + fs_y * f0, u + fs_c * f0, v + fs_c * f0, ls_y, ls_c, fs_y, fs_c, m, g, qscale ? qscale + f0 : nullptr,
-                        slots, stride, pkt_cap, out_size + f0, st + f0, ctx->stream); }
+                        slots, stride, pkt_cap, out_size + f0, st + f0, redo ? redo + f0 : nullptr, ctx->stream); }
         launch_scan_sizes(out_size + f0, m, 0u, 0u, out_off + f0, carry, ctx->stream);
         { ScopedTimer tm(ctx, KK_COMPACT);
           launch_compact(slots, stride, out_size + f0, out_off + f0, m, out, out_cap, st + f0, ctx->stream); }
-        lc += 3;
+        lc += 2 + enc_launches;
     }
     return check_launch(ctx, "encode kernels", lc);
 }
@@ -649,6 +653,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
+    if (!strcmp(key, "encode_rounds")) { ctx->opt_encode_rounds = value != 0; return AMV_OK; }
     if (!strcmp(key, "adpcm_trellis")) {
         if (value < 0 || value > 5) return AMV_ERR_UNSUPPORTED;
         ctx->opt_trellis = (int)value;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kEncThreads)
 k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
          int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
          uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
-         int32_t *__restrict__ status) {
+         int32_t *__restrict__ status, const int32_t *__restrict__ only /* optional: encode frame f only if only[f] != 0 */) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -109,6 +109,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
     const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
 
     for (int f = gw; f < n; f += nw_total) {
+        if (only && !only[f]) continue;
         const int qs = qscale ? qscale[f] : 2;
         __syncwarp();
         for (int t = lane; t < 64; t += 32) {
@@ -303,6 +304,296 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_encode16: the same encoder with HOMOGENEOUS rounds.  k_encode puts 20 luma and 10 chroma blocks of
+// 5 macroblocks on one warp; a luma block of ordinary content carries ~17 non-zero coefficients, a chroma
+// block ~2, so its Huffman loop runs with 13 of 32 lanes busy.  Here a segment is 16 macroblocks done in
+// three rounds of 32 like blocks: all 32 chroma blocks (16 Cb, 16 Cr), then the 32 luma blocks of
+// macroblocks 0..7, then those of 8..15; each luma round scans, packs and outputs its half of the segment
+// together with the chroma strings of the same macroblocks, which wait in their own staging columns.
+// The strings are staged at sizes that fit ordinary content (768 bits per luma block, 384 per chroma
+// block; the worst case is 1658) so the working set stays what it was: a frame with a longer block is
+// not finished here -- it is flagged in `redo` and encoded by k_encode right after (launch_encode).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWL = 24, kWC = 12;                               // staging words per luma / chroma block
+constexpr int kSeg16Words = 32 * kWL + 16 * kWC + 8;            // half a segment: 32 luma + 16 chroma strings
+
+struct Enc16WarpSmem {
+    union {                                 // never live at the same time (A,B use coef; D,E use seg)
+        uint16_t coef[64 * 32];             // halfword k*32 + lane : zigzag coefficient k of the lane's block
+        uint32_t seg[kSeg16Words];          // the half segment's contiguous bit string
+    } u;
+    uint32_t stageL[kWL * 32];              // word w*32 + lane : the lane's luma string of this round
+    uint32_t stageC[kWC * 32];              // the lane's chroma string of this segment
+    uint32_t qm10[64];
+    uint32_t lenC[32];                      // chroma string lengths: Cb of macroblock j at j, Cr at 16 + j
+    uint32_t cpre[20];                      // exclusive prefix over the macroblocks of lenCb + lenCr
+    int      carry_dc[4];                   // last DC of each component so far
+};
+struct Enc16Smem {
+    uint32_t huff[kEncHuffEntries];
+    Enc16WarpSmem w[kEncWarps];
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kEncThreads)
+k_encode16(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
+           int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
+           uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
+           int32_t *__restrict__ status, int32_t *__restrict__ redo) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Enc16Smem &S = *reinterpret_cast<Enc16Smem *>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kEncHuffEntries; i += kEncThreads) S.huff[i] = g_enc_tables.huff.e[i];
+    __syncthreads();
+    Enc16WarpSmem &W = S.w[wid];
+    const int total_mb = g.mbw * g.mbh;
+    const uint32_t coef_s = smem_addr(&W.u.coef[lane]);          // coefficient k: + k*64
+    const uint32_t stageL_s = smem_addr(&W.stageL[lane]), stageC_s = smem_addr(&W.stageC[lane]);   // word w: + w*128
+    const uint32_t seg_s = smem_addr(&W.u.seg[0]);
+    const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
+
+    for (int f = gw; f < n; f += nw_total) {
+        const int qs = qscale ? qscale[f] : 2;
+        __syncwarp();
+        for (int t = lane; t < 64; t += 32) {
+            // intra_matrix / q_intra_matrix for this frame (mpegvideo_enc.c:2866-2877, ff_convert_matrix :69-91)
+            int m = 8;
+            if (t) m = min(max(((int)g_enc_tables.intra_base[t] * qs) >> 3, 1), 255);
+            W.qm10[t] = ((1u << 22) / (uint32_t)(8 * m)) << 10;
+        }
+        if (lane < 3) W.carry_dc[lane] = 128;            // last_dc init (mpegvideo_enc.c:2033-2036)
+        uint32_t overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0;      // qscale domain: SURVEY 9.13
+        uint32_t carry_word = 0;                        // partial word carried into the next half segment
+        uint8_t *pkt = slots + (uint64_t)f * slot_stride;
+        uint32_t G = 2;                                 // bytes written so far (SOI)
+        uint32_t r = 0;                                 // carried bits (sit in carry_word, MSB side)
+        bool too_big = false;                           // a string outgrew its staging column (warp-uniform)
+        if (lane == 0 && pkt_cap >= 2) { pkt[0] = 0xff; pkt[1] = 0xd8; }
+        __syncwarp();
+
+        for (int m0 = 0; m0 < total_mb && !too_big; m0 += 16) {
+            const int nmb = min(16, total_mb - m0);
+            const bool last_seg = m0 + 16 >= total_mb;
+            uint32_t lenC_own = 0;                       // this lane's chroma string of the segment
+
+            for (int rd = 0; rd < 3 && !too_big; rd++) {
+                const int hh = rd - 1;                   // which half of the segment a luma round covers
+                if (rd && 8 * hh >= nmb) break;
+                // ---- the lane's block in this round
+                const int comp = rd ? 0 : 1 + (lane >> 4);
+                const int mbi = rd ? 8 * hh + (lane >> 2) : (lane & 15);
+                const int b = rd ? (lane & 3) : 0;
+                const bool active = mbi < nmb;
+                const int vw = comp ? (g.w >> 1) : g.w, vh = comp ? (g.h >> 1) : g.h, r0 = comp ? g.c0 : g.y0;
+                const int ls = comp ? ls_c : ls_y;
+                const uint8_t *pl = (comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c);
+                const uint32_t huff_dc_s = smem_addr(&S.huff[comp ? kEncDcChroma : kEncDcLuma]);
+                const uint32_t huff_ac_s = smem_addr(&S.huff[comp ? kEncAcChroma : kEncAcLuma]);
+                const uint32_t stage_s = rd ? stageL_s : stageC_s;
+                const uint32_t cap_words = rd ? kWL : kWC;
+                uint32_t mask_lo = 0, mask_hi = 0;          // non-zero AC positions (zigzag) of this block
+                int dc = 0;
+
+                // ---------------- A: load, FDCT, quantise
+                if (active) {
+                    const int mb = m0 + mbi;
+                    const int mx = mb % g.mbw, my = mb / g.mbw;
+                    const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
+                    const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+                    int v[64];
+#pragma unroll
+                    for (int yy = 0; yy < 8; yy++) {
+                        const int Y = min(by + yy, vh - 1);                 // bottom edge replication
+                        const uint8_t *row = pl + (int64_t)(r0 - Y) * ls;
+                        if (FAST) {
+                            const uint2 q = *reinterpret_cast<const uint2 *>(row + bx);
+#pragma unroll
+                            for (int xx = 0; xx < 4; xx++) {
+                                v[yy * 8 + xx]     = (q.x >> (8 * xx)) & 0xff;
+                                v[yy * 8 + 4 + xx] = (q.y >> (8 * xx)) & 0xff;
+                            }
+                        } else {
+#pragma unroll
+                            for (int xx = 0; xx < 8; xx++) v[yy * 8 + xx] = row[min(bx + xx, vw - 1)];   // right edge replication
+                        }
+                    }
+                    fdct_block(v);
+                    dc = quant_dc(v[0]);
+                    // raster order so the multiplier loads vectorise; mask bit = zigzag position
+#pragma unroll
+                    for (int j = 1; j < 64; j++) {
+                        const int q = quant_ac(v[j], W.qm10[j]);
+                        v[j] = q;
+                        const int k = zigzag_inv_at(j);
+                        if (q) { if (k < 32) mask_lo |= 1u << k; else mask_hi |= 1u << (k - 32); }
+                    }
+#pragma unroll
+                    for (int k = 1; k < 64; k++) W.u.coef[k * 32 + lane] = (uint16_t)v[zigzag_at(k)];
+                }
+                // DC predictor: the previous block of the component is the previous lane (Y0..Y3 of a macroblock and
+                // the macroblocks themselves are consecutive lanes; Cb and Cr each fill 16 consecutive lanes)
+                const int dc_prev = __shfl_up_sync(0xffffffffu, dc, 1);
+                const bool first_of_comp = rd ? lane == 0 : (lane & 15) == 0;
+                const int pred = first_of_comp ? W.carry_dc[comp] : dc_prev;
+                __syncwarp();
+
+                // ---------------- B: Huffman-code the block into the lane's private bit string
+                uint32_t len = 0;
+                if (active) {
+                    uint32_t acc = 0;                   // MSB-first accumulator: the top `fill` bits are valid
+                    uint32_t fill = 0;
+                    uint32_t wp = stage_s;              // next private word
+                    const uint32_t wend = stage_s + cap_words * 128u;
+                    auto put = [&](uint32_t code, uint32_t nbits) {  // 1 <= nbits <= 27
+                        const uint32_t t = code << (32 - nbits);     // left-aligned
+                        acc |= t >> fill;
+                        const uint32_t nf = fill + nbits;
+                        if (nf >= 32) { if (wp < wend) sts32(wp, acc); wp += 128; acc = t << (32 - fill); fill = nf - 32; }   // fill >= 5 here
+                        else fill = nf;
+                    };
+                    {   // DC (ff_mjpeg_encode_dc, mjpegenc.c:357-377)
+                        const int diff = dc - pred;
+                        const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
+                        const uint32_t e = lds32(huff_dc_s + nb * 4);
+                        const uint32_t mant = (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u);
+                        put(((e >> 5) << nb) | mant, (e & 31) + (uint32_t)nb);
+                    }
+                    const uint32_t ezrl = lds32(huff_ac_s + 0xf0 * 4), eeob = lds32(huff_ac_s);
+                    int prevk = 0;
+                    auto ac_run = [&](uint32_t m, int base) {        // encode_block's AC loop (mjpegenc.c:403-430)
+                        while (m) {
+                            const int k = base + __ffs((int)m) - 1;
+                            m &= m - 1;
+                            int run = k - prevk - 1;
+                            prevk = k;
+                            const int cv = lds_s16(coef_s + (uint32_t)k * 64);
+                            const int cb = bit_width((uint32_t)(cv < 0 ? -cv : cv));
+                            for (; run >= 16; run -= 16) put(ezrl >> 5, ezrl & 31);
+                            const uint32_t e = lds32(huff_ac_s + (uint32_t)((run << 4) | cb) * 4);
+                            const uint32_t mant = (uint32_t)(cv + (cv >> 31)) & ((1u << cb) - 1u);
+                            put(((e >> 5) << cb) | mant, (e & 31) + (uint32_t)cb);
+                        }
+                    };
+                    ac_run(mask_lo, 0);
+                    ac_run(mask_hi, 32);
+                    if (prevk != 63) put(eeob >> 5, eeob & 31);                 // EOB only if last_index < 63 (:432-434)
+                    if (fill > 0 && wp < wend) sts32(wp, acc);
+                    len = ((wp - stage_s) >> 7) * 32u + fill;
+                }
+                if (__any_sync(0xffffffffu, len > cap_words * 32u)) { too_big = true; break; }
+                // DC predictors for what follows: the last active block of each component in this round
+                {
+                    const int na = rd ? min(32, 4 * (nmb - 8 * hh)) : min(16, nmb);       // active lanes (per component)
+                    if (active && (rd ? lane : (lane & 15)) == na - 1) W.carry_dc[comp] = dc;
+                }
+                if (rd == 0) {
+                    // chroma round: keep the strings, publish their lengths and the per-macroblock prefix
+                    lenC_own = len;
+                    W.lenC[lane] = len;
+                    __syncwarp();
+                    const uint32_t cj = lane < 16 ? W.lenC[lane] + W.lenC[16 + lane] : 0u;
+                    const uint32_t cinc = warp_incl_scan(cj, lane);
+                    if (lane < 16) W.cpre[lane + 1] = cinc;
+                    if (lane == 0) W.cpre[0] = 0;
+                    __syncwarp();
+                    continue;
+                }
+
+                // ---------------- C: bit offsets of the half segment's strings in bitstream order
+                // (per macroblock: Y0 Y1 Y2 Y3 Cb Cr)
+                const uint32_t linc = warp_incl_scan(len, lane);
+                const uint32_t cbase = W.cpre[8 * hh];
+                const uint32_t luma_off = (linc - len) + (W.cpre[8 * hh + (lane >> 2)] - cbase);
+                // chroma strings of this half are packed by the lanes that made them: Cb of macroblock 8*hh + j by
+                // lane 8*hh + j, Cr by lane 16 + 8*hh + j
+                const int cj = lane & 7;
+                const uint32_t luma_end = __shfl_sync(0xffffffffu, linc, 4 * cj + 3);
+                const bool cpack = (((lane & 15) >> 3) == hh) && ((lane & 15) < nmb);
+                const uint32_t chroma_off = luma_end + (W.cpre[8 * hh + cj] - cbase) + (lane >= 16 ? W.lenC[lane - 16] : 0u);
+                const uint32_t T = __shfl_sync(0xffffffffu, linc, 31) + (W.cpre[min(8 * hh + 8, 16)] - cbase);
+                const bool last_half = last_seg && (hh == 1 || nmb <= 8);
+                __syncwarp();
+                uint32_t R = r + T;                              // bits in the buffer after this half
+                // clear the words this half will OR into; word 0 starts with the carried bits
+                const uint32_t used_words = (R + 7 + 31) >> 5;
+                for (uint32_t i = 1 + lane; i <= used_words; i += 32) W.u.seg[i] = 0;
+                if (lane == 0) W.u.seg[0] = carry_word;
+                __syncwarp();
+
+                // ---------------- D: bit packer -- shift the private strings to their scanned bit offsets
+                {
+                    auto pack = [&](uint32_t src, uint32_t nbits, uint32_t o) {
+                        const uint32_t sh = o & 31;
+                        uint32_t dst = seg_s + (o >> 5) * 4;
+                        const uint32_t nsrc = (nbits + 31) >> 5;
+                        uint32_t prev = 0;
+                        for (uint32_t j = 0; j < nsrc; j++) {
+                            const uint32_t v = lds32(src);
+                            red_or_shared(dst, __funnelshift_r(v, prev, sh));      // (prev:v) >> sh
+                            prev = v; src += 128; dst += 4;
+                        }
+                        const uint32_t tail = sh ? prev << (32 - sh) : 0u;
+                        if (tail) red_or_shared(dst, tail);
+                    };
+                    if (len) pack(stageL_s, len, r + luma_off);
+                    if (cpack && lenC_own) pack(stageC_s, lenC_own, r + chroma_off);
+                }
+                __syncwarp();
+                if (last_half) {
+                    // pad to a byte with ones (ff_mjpeg_encode_stuffing, mjpegenc.c:338-343)
+                    const uint32_t pad = (0u - R) & 7u;
+                    if (lane == 0 && pad) W.u.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
+                    R += pad;
+                    __syncwarp();
+                }
+
+                // ---------------- E: FF00 stuffing + output of the complete bytes
+                const uint32_t B = last_half ? (R >> 3) : ((R >> 5) << 2);     // bytes leaving the buffer now
+                const uint32_t nw = (B + 3) >> 2;
+                const uint32_t per = (nw + 31) >> 5;
+                const uint32_t w0 = min((uint32_t)lane * per, nw), w1 = min(w0 + per, nw);
+                // bytes past B in the last word are zero bits, never FF: no masking needed for the count
+                uint32_t ffc = 0;
+                for (uint32_t w = w0; w < w1; w++) ffc += __popc(ff_bytes(W.u.seg[w]));
+                const uint32_t inc = warp_incl_scan(ffc, lane);
+                const uint32_t ff_total = __shfl_sync(0xffffffffu, inc, 31);
+                const uint32_t ff_before = inc - ffc;
+                const bool fits = (uint64_t)G + B + ff_total + 2 <= pkt_cap && !overflow;
+                if (fits) {
+                    uint8_t *o = pkt + G + w0 * 4 + ff_before;
+                    for (uint32_t w = w0; w < w1; w++) {
+                        const uint32_t v = W.u.seg[w];
+                        const uint32_t nvalid = min(4u, B - w * 4);
+                        if (nvalid == 4 && ff_bytes(v) == 0) {
+                            o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v;
+                            o += 4;
+                        } else {
+                            for (uint32_t k = 0; k < nvalid; k++) {
+                                const uint8_t by = (uint8_t)(v >> (24 - 8 * k));
+                                *o++ = by;
+                                if (by == 0xff) *o++ = 0;
+                            }
+                        }
+                    }
+                } else if (!overflow) overflow = AMV_ST_NOSPACE;
+                carry_word = last_half ? 0 : W.u.seg[R >> 5];                 // carry the partial word (same for all lanes)
+                G += B + ff_total;
+                r = last_half ? 0 : (R & 31);
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            redo[f] = too_big ? 1 : 0;
+            if (!too_big) {
+                if (!overflow) { pkt[G] = 0xff; pkt[G + 1] = 0xd9; }      // EOI (mjpegenc.c:354)
+                out_size[f] = overflow ? 0 : G + 2;
+                status[f] = (int32_t)overflow;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // packed layout: copy each packet from its slot to its scanned offset
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -362,8 +653,8 @@ cudaError_t upload_enc_tables(cudaStream_t s) {
     return cudaMemcpyToSymbolAsync(g_enc_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 
-int encode_grid(int n) {
-    const int per_sm = 4;                              // CTAs per SM (shared memory bound): 16 independent warps
+int encode_grid(int n, int per_sm) {
+    // CTAs per SM: k_encode 4 (shared memory and registers: 16 independent warps), k_encode16 5 (registers)
     const int cap = kNumSMs * per_sm;
     const int need = (n + kEncWarps - 1) / kEncWarps;  // one frame per warp at a time
     return need < 1 ? 1 : (need < cap ? need : cap);
@@ -371,21 +662,33 @@ int encode_grid(int n) {
 
 void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                    int n, const Geom &g, const int32_t *qscale, uint8_t *slots, uint64_t slot_stride, uint32_t pkt_cap,
-                   uint32_t *out_size, int32_t *status, cudaStream_t s) {
+                   uint32_t *out_size, int32_t *status, int32_t *redo, cudaStream_t s) {
     const bool fast = (g.w % 16 == 0) &&
                       ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
         cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+        cudaFuncSetAttribute(k_encode16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
+        cudaFuncSetAttribute(k_encode16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
         attr_set = true;
     }
+    // redo == nullptr: the plain one-kernel path.  Else: k_encode16 first (homogeneous rounds, strings staged at
+    // ordinary-content sizes), then k_encode for the frames it flagged because a block's string outgrew its column.
+    if (redo) {
+        if (fast)
+            k_encode16<true><<<encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                                                    slot_stride, pkt_cap, out_size, status, redo);
+        else
+            k_encode16<false><<<encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                                                     slot_stride, pkt_cap, out_size, status, redo);
+    }
     if (fast)
-        k_encode<true><<<encode_grid(n), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                                            slot_stride, pkt_cap, out_size, status);
+        k_encode<true><<<encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                                            slot_stride, pkt_cap, out_size, status, redo);
     else
-        k_encode<false><<<encode_grid(n), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                                             slot_stride, pkt_cap, out_size, status);
+        k_encode<false><<<encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+                                                                             slot_stride, pkt_cap, out_size, status, redo);
 }
 
 void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
