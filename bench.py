@@ -430,7 +430,9 @@ def main():
         frames = n * args.steps / max(1, kern[k]["launches"])
         gbs = bytes_per_frame * frames / (ms / 1e3) / 1e9 if ms > 0 else 0.0
         tr = traffic.get(k, {}).get("dram_bytes_per_frame")
-        return {"bound": "hbm", "kernel": "k_" + ("vlc_" + k if k in ("sync", "tokens") else k), "achieved": gbs,
+        names = {"encode": "k_encode16 (+ k_encode for the frames it hands back; one pair per launch)", "tokens": "k_vlc_tokens",
+                 "sync": "k_vlc_sync", "idct": "k_idct"}
+        return {"bound": "hbm", "kernel": names.get(k, "k_" + k), "achieved": gbs,
                 "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
                 "traffic": tr * frames if tr else None,
                 "traffic_note": "ncu dram bytes per frame (profiles/traffic.json) x frames per launch" if tr else None,
