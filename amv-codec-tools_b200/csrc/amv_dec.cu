@@ -276,8 +276,7 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
 // Everything a scan needs besides its bits, in device memory: the fixed AMV / SP5X set, the amvlib
 // flavour's (same codes, amvlib's quantisers and zigzag), or one built from a JPEG's own DQT / DHT.
 struct DecTableSet {
-    FlatVlcTables flat;          // k_vlc_tokens
-    VlcTables vlc;               // k_vlc_sync
+    FlatVlcTables flat;          // k_vlc_sync, k_vlc_tokens
     uint32_t tz[2][64];          // zigzag position -> token fields | quantiser (DequantTables::tz / AmvlibDequantTables::tz)
     int q0[2];                   // DC quantisers of component 0 / components 1, 2
 };
@@ -287,68 +286,67 @@ struct DecTableSet {
 enum { kFlavorFfmpeg = 0, kFlavorAmvlib = 1, kFlavorJpeg = 2 };
 __device__ DecTableSet g_dec_sets[2];
 
-struct VlcSmem {
-    uint32_t lut[kVlcMaxEntries];
-    int      base[4];
-    int      q0[2];          // DC quantiser of luma / chroma
-};
-
-__device__ __forceinline__ void load_vlc_tables(VlcSmem &s, const DecTableSet *__restrict__ T) {
-    for (int i = threadIdx.x; i < kVlcMaxEntries; i += blockDim.x) s.lut[i] = T->vlc.e[i];
-    if (threadIdx.x < 4) s.base[threadIdx.x] = T->vlc.base[threadIdx.x];
-    if (threadIdx.x < 2) s.q0[threadIdx.x] = T->q0[threadIdx.x];
-    __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------------
-// k_vlc_sync
+// k_vlc_sync: self-synchronising subsequence decode.  The P lanes of a frame (P = 2..32 consecutive
+// lanes of a warp) each walk one P-th of the scan from a guessed state (the subsequence's first bit
+// taken as a block boundary, block 0 of a macroblock), hand their exit state -- where the first block
+// at or behind the subsequence's end starts, and which block of the macroblock it is -- to the right
+// neighbour with __shfl_up, and walk again from the state they are handed until a __ballot shows that
+// no entry state changed (JPEG's Huffman codes re-synchronise within a few symbols, so this is two
+// walks for almost every lane).  A segmented shuffle scan then gives every lane its first block index
+// and DC predictors.
+//
+// The walk is the flat symbol loop of k_vlc_tokens without the token side: one iteration = one symbol
+// for every lane that is still inside its subsequence, bits through the same shared-memory ring with
+// service points every kTokPeriod symbols, DC and AC through the same predicated code; per block only
+// the block count, the next block's tables and the rotation of the three DC sums.
 // ------------------------------------------------------------------------------------------------
-struct CountSink {
-    int dcv;
-    __device__ __forceinline__ void dc(int d) { dcv = d; }
-    __device__ __forceinline__ void ac(int, int) {}
+constexpr int kTokThreads = 256;
+constexpr int kTokWarps = kTokThreads / 32;
+constexpr int kRingWords = 16;
+constexpr int kTokPeriod = 4;         // symbols between two service points
+
+struct SyncSmem {
+    uint32_t ring[kTokWarps][kRingWords * 32];     // 2 KB per warp, 2 KB aligned
+    uint2    bstate[8];                            // per block-in-MCU: DC table, AC table | component change on entering it
+    uint32_t lut[kFlatMaxEntries];
 };
+constexpr size_t kSyncSmemBytes = sizeof(SyncSmem) + 2048;
 
-__device__ __forceinline__ void walk_subsequence(const uint32_t *words, uint32_t nwords, uint32_t start_bit,
-                                                 uint32_t start_phase, uint32_t end_bit, const VlcSmem &T,
-                                                 LaneExit &ex) {
-    BitReader br;
-    br.init(words, nwords, start_bit);
-    uint32_t phase = start_phase, nb = 0;
-    int dc0 = 0, dc1 = 0, dc2 = 0;
-    CountSink sink;
-    while (br.bitpos() < end_bit) {
-        walk_block(br, T.lut, T.base, phase >= 4 ? 1 : 0, sink);
-        if (phase < 4) dc0 += sink.dcv; else if (phase == 4) dc1 += sink.dcv; else dc2 += sink.dcv;
-        phase = phase == 5 ? 0 : phase + 1;
-        nb++;
-    }
-    ex.bitpos = br.bitpos(); ex.phase = phase; ex.nblocks = nb;
-    ex.dc[0] = dc0; ex.dc[1] = dc1; ex.dc[2] = dc2;
-}
-
-constexpr int kVlcThreads = 128;
-
-__global__ void __launch_bounds__(kVlcThreads)
+__global__ void __launch_bounds__(kTokThreads)
 k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
            const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
            uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */, int flavor,
            const DecTableSet *__restrict__ tabs, const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */) {
-    __shared__ VlcSmem T;
-    load_vlc_tables(T, tabs);
+    extern __shared__ uint8_t sync_smem_raw[];
+    const uint32_t raw_s = smem_addr(sync_smem_raw);
+    SyncSmem &S = *reinterpret_cast<SyncSmem *>(sync_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
+    const int nlut = tabs->flat.count;
+    for (int i = threadIdx.x; i < nlut; i += blockDim.x) S.lut[i] = tabs->flat.e[i];
+    const uint32_t lut_s = smem_addr(S.lut);
+    if (threadIdx.x < 6) {
+        const uint32_t bq = threadIdx.x, tq = bq >= 4 ? 1 : 0;
+        uint2 bs;
+        bs.x = ((lut_s + (uint32_t)tabs->flat.base[tq] * 4u) << 8) | (32u - kFlatDcBits);
+        bs.y = ((lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | ((bq == 0 || bq >= 4) ? 0x80u : 0u);
+        S.bstate[bq] = bs;
+    }
+    __syncthreads();
     const int P = 1 << log2p;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (int)(gt >> log2p);
     const int p = (int)(gt & (P - 1));
     const bool active = f < n;
+    const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
+    const uint32_t bstate_s = smem_addr(&S.bstate[0]);
 
     const uint32_t *words = nullptr;
-    uint32_t nwords = 0, end_bit = 0, total_bits = 0, L = 0;
+    uint32_t cap_words = 0, end_bit = 0, total_bits = 0, L = 0;
     if (active) {
         const uint32_t U = scan_len[f];
         words = reinterpret_cast<const uint32_t *>(scratch + slot_off[f]);
-        nwords = (U + 3) >> 2;
+        cap_words = (((U + 15u) & ~15u) + kSlotPad) >> 2;       // inside the zero-padded slot (U <= packet size)
         total_bits = U * 8u;
         L = (((total_bits + P - 1) >> log2p) + 31u) & ~31u;
         const uint64_t e = (uint64_t)(p + 1) * L;
@@ -356,20 +354,93 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
     }
     uint32_t start_bit = active ? (uint32_t)min((uint64_t)p * L, (uint64_t)total_bits) : 0u, start_phase = 0;
     LaneExit ex = { 0, 0, 0, { 0, 0, 0 } };
-    if (active) walk_subsequence(words, nwords, start_bit, start_phase, end_bit, T, ex);
+    auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
+        if (w + 4 <= cap_words) return __ldg(reinterpret_cast<const uint4 *>(words + w));
+        return make_uint4(0, 0, 0, 0);
+    };
+    auto ring_put = [&](uint32_t w, const uint4 &q) {   // w is a multiple of 4
+        const uint32_t a = ring_s | ((w << 7) & 0x780u);
+        sts32(a, bswap32(q.x)); sts32(a + 128, bswap32(q.y)); sts32(a + 256, bswap32(q.z)); sts32(a + 384, bswap32(q.w));
+    };
 
-    uint32_t rounds = 1;
-    for (int r = 0; r < P; r++) {
-        // entry state = left neighbour's exit state (lane 0 of a frame starts the scan)
-        uint32_t nbit = __shfl_up_sync(0xffffffffu, ex.bitpos, 1);
-        uint32_t nph = __shfl_up_sync(0xffffffffu, ex.phase, 1);
-        if (p == 0) { nbit = 0; nph = 0; }
-        const bool changed = active && (nbit != start_bit || nph != start_phase);
-        if (!__ballot_sync(0xffffffffu, changed)) break;
+    uint32_t rounds = 0;
+    bool need = active;                     // this lane walks in the coming round
+    for (int r = 0; r <= P; r++) {
+        if (r > 0) {
+            // entry state = left neighbour's exit state (lane 0 of a frame starts the scan)
+            uint32_t nbit = __shfl_up_sync(0xffffffffu, ex.bitpos, 1);
+            uint32_t nph = __shfl_up_sync(0xffffffffu, ex.phase, 1);
+            if (p == 0) { nbit = 0; nph = 0; }
+            need = active && (nbit != start_bit || nph != start_phase);
+            if (!__ballot_sync(0xffffffffu, need)) break;
+            if (need) { start_bit = nbit; start_phase = nph; }
+        }
         rounds++;
-        if (changed) {
-            start_bit = nbit; start_phase = nph;
-            walk_subsequence(words, nwords, start_bit, start_phase, end_bit, T, ex);
+        // ---- walk the subsequence from (start_bit, start_phase): blocks that START before end_bit
+        uint32_t bp = start_bit;
+        uint32_t wr = (start_bit >> 5) & ~3u;           // next word the ring receives; ring = words [wr-16, wr)
+        uint4 pend = make_uint4(0, 0, 0, 0);
+        bool on = need && start_bit < end_bit;
+        uint32_t kb = 0;                                // zigzag position of the last symbol + 1; 0: the DC comes next
+        uint32_t b = start_phase, nb = 0;
+        int dA = 0, dB = 0, dC = 0;                     // sums of DC differences; dA: the current block's component
+        uint32_t desc = 0, acd = 0;
+        {
+            const uint2 bs = S.bstate[b];
+            desc = bs.x; acd = bs.y;
+        }
+        if (on) {
+            ring_put(wr, load_group(wr));
+            ring_put(wr + 4, load_group(wr + 4));
+            wr += 8;
+            pend = load_group(wr);
+        }
+        while (__any_sync(0xffffffffu, on)) {
+            if (on) {       // service point: ring top-up
+                const uint32_t rd = bp >> 5;
+                if ((int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; pend = load_group(wr); }
+            }
+#pragma unroll
+            for (int u = 0; u < kTokPeriod; u++) {
+                const uint32_t x = bp << 2;
+                const uint32_t wa = lds32(ring_s | (x & 0x780u)), wc = lds32(ring_s | ((x + 128u) & 0x780u));
+                const uint32_t hi = __funnelshift_l(wc, wa, bp);
+                uint32_t e = lds32((desc >> 8) + (__funnelshift_r(hi, 0u, desc) << 2));
+                if ((e & 31u) == 0) {
+                    if (!(e & kFlatBad)) {
+                        const uint32_t fb = 32u - (desc & 31u), sb = e >> 24;
+                        e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << fb) >> (32u - sb))) << 2));
+                    }
+                    if ((e & 31u) == 0)     // no such code: a bad DC reads as difference 0, a bad AC ends the block
+                        e = 1u | (1u << 8) | (kb ? (kFlatAdvEob << 23) : ((1u << 23) | (1u << 31)));
+                }
+                const uint32_t top = hi << (e & 31u);
+                if (on) { bp += __byte_perm(e, 0, 0x4441); kb += (e >> 23) & 0xffu; }
+                const int sg = (int)(~top) >> 31;
+                const int lvl = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
+                const bool isdc = kb == 1u;
+                dA += (isdc && on) ? lvl : 0;
+                const bool nz = (int)e < 0;             // the symbol carries a value (for AC symbols: size != 0)
+                const bool endp = on && kb >= 64u && (nz || kb >= 128u);
+                b = endp ? (b == 5u ? 0u : b + 1u) : b;
+                nb += endp ? 1u : 0u;
+                const uint2 bs = S.bstate[b];            // after the step: the next block's tables at a block end
+                const bool rot = endp && (bs.y & 0x80u);
+                const int tA = rot ? dB : dA, tB = rot ? dC : dB, tC = rot ? dA : dC;
+                dA = tA; dB = tB; dC = tC;
+                desc = endp ? bs.x : ((isdc && on) ? acd : desc);
+                acd = endp ? bs.y : acd;
+                kb = endp ? 0u : kb;
+                on = on && !(endp && bp >= end_bit);
+            }
+        }
+        if (need) {
+            // the sums sit rotated to the component of the block that comes next
+            const int c = b < 4u ? 0 : (int)b - 3;
+            ex.bitpos = bp; ex.phase = b; ex.nblocks = nb;
+            ex.dc[0] = c == 0 ? dA : (c == 1 ? dC : dB);
+            ex.dc[1] = c == 0 ? dB : (c == 1 ? dA : dC);
+            ex.dc[2] = c == 0 ? dC : (c == 1 ? dB : dA);
         }
     }
     // segmented (width P) exclusive scans: first block index and DC difference sums
@@ -389,8 +460,8 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
         if (flavor == kFlavorAmvlib) {                         // quantised units, 16-bit chain from 0 (AmvJpeg.c:1194-1196)
             s.pred[0] = sext16(d0 - ex.dc[0]); s.pred[1] = sext16(d1 - ex.dc[1]); s.pred[2] = sext16(d2 - ex.dc[2]);
         } else {
-            const int q0l = flavor == kFlavorJpeg ? (int)qtab[(size_t)f * 128] : T.q0[0];
-            const int q0c = flavor == kFlavorJpeg ? (int)qtab[(size_t)f * 128 + 64] : T.q0[1];
+            const int q0l = flavor == kFlavorJpeg ? (int)qtab[(size_t)f * 128] : tabs->q0[0];
+            const int q0c = flavor == kFlavorJpeg ? (int)qtab[(size_t)f * 128 + 64] : tabs->q0[1];
             s.pred[0] = 1024 + q0l * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
             s.pred[1] = 1024 + q0c * (d1 - ex.dc[1]);
             s.pred[2] = 1024 + q0c * (d2 - ex.dc[2]);
@@ -429,11 +500,7 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 //    service points.
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kTokThreads = 256;
-constexpr int kTokWarps = kTokThreads / 32;
-constexpr int kRingWords = 16;
 constexpr int kTokStage = 8;          // staged tokens per lane
-constexpr int kTokPeriod = 4;         // symbols between two service points
 // flag on the dequant entries of zigzag positions past 63, in a bit that reaches neither the product nor the token
 constexpr uint32_t kTzErr = 1u << 15, kTzErrAmvlib = 1u << 16;
 
@@ -761,8 +828,7 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 // ------------------------------------------------------------------------------------------------
 static bool fill_table_set(DecTableSet &T, const HuffSpec &H, const uint8_t qzz[2][64], bool *sync_ok) {
     if (!build_flat_vlc_tables_from(T.flat, H)) return false;
-    const bool vs = build_vlc_tables_from(T.vlc, H);
-    if (sync_ok) *sync_ok = vs;
+    if (sync_ok) *sync_ok = true;          // the synchronisation pass uses the same table
     DequantTables dq;
     build_dequant_tables_from(dq, qzz);
     memcpy(T.tz, dq.tz, sizeof(T.tz));
@@ -862,8 +928,13 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
                      cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
-    const int grid = (int)((lanes + kVlcThreads - 1) / kVlcThreads);
-    k_vlc_sync<<<grid, kVlcThreads, 0, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
+    const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_vlc_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes);
+        attr_set = true;
+    }
+    k_vlc_sync<<<grid, kTokThreads, kSyncSmemBytes, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
                                             amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab);
 }
 
