@@ -287,6 +287,8 @@ class AmvCuda:
         pkt_size = np.ascontiguousarray(pkt_size, np.uint32)
         n = len(pkt_size)
         cw, ch = chroma_dims(w, h)
+        if mjpeg:       # 4:2:2 / 4:4:4 frames have larger chroma planes: the configured header says
+            cw, ch = self.get_stat("mjpeg_chroma_width"), self.get_stat("mjpeg_chroma_height")
         y = np.zeros((n, h, w), np.uint8)
         u = np.zeros((n, ch, cw), np.uint8)
         v = np.zeros((n, ch, cw), np.uint8)

@@ -62,6 +62,7 @@ struct amv_ctx {
     void *mj_tables = nullptr;          // DecTableSet in device memory
     uint8_t *mj_hdr = nullptr;          // device copy of the sample's bytes up to the end of the SOS header
     uint32_t mj_hdr_len = 0;
+    int mj_samp[4] = { 1, 1, 0, 0 };    // log2 sampling of the configured header: luma h, v; chroma h, v
     uint32_t mj_qpos[2] = { 0, 0 };     // where the 64 quantisers of component 0 / components 1, 2 sit in a frame
     int mj_w = 0, mj_h = 0;
     bool mj_sync_ok = false;            // the lane-synchronisation table could be built (else one lane per frame)
@@ -76,6 +77,8 @@ struct DecMode {
     const uint8_t *hdr = nullptr;       // plain JPEG: required header bytes (device)
     uint32_t hdr_len = 0;
     uint32_t qpos[2] = { 0, 0 };        // plain JPEG: offsets of the per-frame quantisers
+    int samp[4] = { 1, 1, 0, 0 };       // log2 sampling: luma h, v; chroma h, v (AMV / SP5X: 4:2:0)
+    Geom geom(int w, int h) const { Geom g = make_geom_sampled(w, h, samp[0], samp[1], samp[2], samp[3]); if (!flip) g.flip = 0; return g; }
     bool allow_sync = true;
 };
 static const DecMode kModeAmv;
@@ -194,11 +197,11 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
     if (log2p) {
         CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
         { ScopedTimer tm(ctx, KK_SYNC);
-          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, tabs, qtab, ctx->stream); }
+          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, tabs, qtab, g.nl, g.nc, ctx->stream); }
         lc++;
     }
     { ScopedTimer tm(ctx, KK_TOKENS);
-      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, ctx->stream); }
+      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, g.nl, g.nc, ctx->stream); }
     lc++;
     F.slot_off = slot_off; F.scan_len = scan_len; F.tokens = tokens; F.blk_off = blk_off; F.st = st; F.launches = lc;
     return AMV_OK;
@@ -207,8 +210,7 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
 int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off,
                   const uint32_t *pkt_size, int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c,
                   uint64_t fs_y, uint64_t fs_c, int32_t *status, uint64_t payload_bytes, const DecMode &mode = kModeAmv) {
-    Geom g = make_geom(w, h);
-    if (!mode.flip) g.flip = 0;
+    const Geom g = mode.geom(w, h);
     DecodeFront F;
     int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F, mode);
     if (r != AMV_OK) return r;
@@ -409,7 +411,8 @@ void *device_view(const void *host_ptr) {
 int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
                 int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                 int32_t *status, const DecMode &mode = kModeAmv) {
-    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const Geom gm = mode.geom(w, h);
+    const int cw = gm.cw, ch = gm.ch;
     const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
     const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
     // pinned bounce: status (4) + offsets (8) + sizes (4) per frame
@@ -670,6 +673,10 @@ AMV_API int64_t amv_get_stat(amv_ctx *ctx, const char *key) {
     if (!strcmp(key, "mjpeg_quant_offset_0")) return ctx->mj_qpos[0];
     if (!strcmp(key, "mjpeg_quant_offset_1")) return ctx->mj_qpos[1];
     if (!strcmp(key, "mjpeg_sync_table")) return ctx->mj_sync_ok ? 1 : 0;
+    if (!strcmp(key, "mjpeg_chroma_width") || !strcmp(key, "mjpeg_chroma_height")) {
+        const Geom g = make_geom_sampled(ctx->mj_w, ctx->mj_h, ctx->mj_samp[0], ctx->mj_samp[1], ctx->mj_samp[2], ctx->mj_samp[3]);
+        return key[13] == 'w' ? g.cw : g.ch;
+    }
     // "<kernel>_kernel_ns" / "<kernel>_kernel_launches": device time and launch count of one hot kernel
     // accumulated since the last query of that key pair (needs option profile_events = 1)
     for (int k = 0; k < KK_COUNT; k++) {
@@ -714,7 +721,8 @@ static int decode_frames_common(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts
     if (n < 0 || w <= 0 || h <= 0 || w > 16384 || h > 16384 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
     if (n == 0) return AMV_OK;
     if (!pkts || !pkt_off || !pkt_size || !y || !u || !v) return fail(ctx, AMV_ERR_ARG, "null buffer");
-    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const Geom gm = mode.geom(w, h);
+    const int cw = gm.cw, ch = gm.ch;
     if (ls_y < w || ls_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw)
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
     CK(cudaSetDevice(ctx->device));
@@ -743,7 +751,7 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
     if (!p || size < 4 || p[0] != 0xff || p[1] != 0xd8) return fail(ctx, AMV_ERR_ARG, "not a JPEG (no SOI)");
     uint8_t q[4][64], hc[2][4][16], hs[2][4][256];
     bool have_q[4] = { false, false, false, false }, have_h[2][4] = { { false } };
-    int comp_id[3] = { 0, 0, 0 }, comp_q[3] = { 0, 0, 0 }, w = 0, h = 0;
+    int comp_id[3] = { 0, 0, 0 }, comp_q[3] = { 0, 0, 0 }, w = 0, h = 0, samp[4] = { 1, 1, 0, 0 };
     bool have_sof = false;
     uint32_t i = 2, scan_start = 0, qofs[4] = { 0, 0, 0, 0 };
     int td[3] = { 0, 0, 0 }, ta[3] = { 0, 0, 0 };
@@ -782,12 +790,19 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
         } else if (m == 0xc0) {                                              // SOF0
             if (n < 15 || d[0] != 8 || d[5] != 3) return bad("not 8-bit, three components");
             h = (d[1] << 8) | d[2]; w = (d[3] << 8) | d[4];
-            static const uint8_t want[3] = { 0x22, 0x11, 0x11 };
             for (int c = 0; c < 3; c++) {
                 comp_id[c] = d[6 + 3 * c];
-                if (d[7 + 3 * c] != want[c]) return bad("sampling other than 2x2 / 1x1 / 1x1");
                 comp_q[c] = d[8 + 3 * c];
                 if (comp_q[c] >= 4) return bad("quantiser table index");
+            }
+            // pix_fmt_id of ff_mjpeg_decode_sof (:283-311): 4:2:0, 4:2:2 in both layouts (the reference's own
+            // encoder writes 2x2 / 1x2 / 1x2), 4:4:4
+            switch ((d[7] << 16) | (d[10] << 8) | d[13]) {
+                case 0x221111: samp[0] = 1; samp[1] = 1; samp[2] = 0; samp[3] = 0; break;
+                case 0x211111: samp[0] = 1; samp[1] = 0; samp[2] = 0; samp[3] = 0; break;
+                case 0x221212: samp[0] = 1; samp[1] = 1; samp[2] = 0; samp[3] = 1; break;
+                case 0x111111: samp[0] = 0; samp[1] = 0; samp[2] = 0; samp[3] = 0; break;
+                default: return bad("sampling other than 4:2:0, 4:2:2, 4:4:4");
             }
             if (comp_q[1] != comp_q[2]) return bad("Cb and Cr use different quantiser tables");
             have_sof = true;
@@ -829,6 +844,7 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
     CK(cudaMemcpy(ctx->mj_hdr, p, scan_start, cudaMemcpyHostToDevice));
     ctx->mj_hdr_len = scan_start; ctx->mj_w = w; ctx->mj_h = h; ctx->mj_sync_ok = sync_ok;
     ctx->mj_qpos[0] = qofs[comp_q[0]]; ctx->mj_qpos[1] = qofs[comp_q[1]];
+    for (int k = 0; k < 4; k++) ctx->mj_samp[k] = samp[k];
     if (w_out) *w_out = w;
     if (h_out) *h_out = h;
     return AMV_OK;
@@ -845,6 +861,7 @@ AMV_API int amv_decode_frames_mjpeg(amv_ctx *ctx, const uint8_t *pkts, uint64_t 
     m.tables = static_cast<const DecTableSet *>(ctx->mj_tables);
     m.hdr = ctx->mj_hdr; m.hdr_len = ctx->mj_hdr_len;
     m.qpos[0] = ctx->mj_qpos[0]; m.qpos[1] = ctx->mj_qpos[1];
+    for (int k = 0; k < 4; k++) m.samp[k] = ctx->mj_samp[k];
     m.allow_sync = ctx->mj_sync_ok;
     return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, m);
 }

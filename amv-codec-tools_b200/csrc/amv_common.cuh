@@ -34,8 +34,12 @@ constexpr uint32_t kSlotPad = 80;
 struct Geom {
     int w, h;          // luma size
     int cw, ch;        // chroma plane size, ceil(w/2) x ceil(h/2)
-    int mbw, mbh;      // macroblock grid, ceil(w/16) x ceil(h/16)
-    int nblk;          // 6 * mbw * mbh
+    int mbw, mbh;      // MCU grid, ceil(w / (8 lh)) x ceil(h / (8 lv)): 16x16 macroblocks for 4:2:0
+    int nblk;          // nb * mbw * mbh
+    // sampling: blocks per MCU across / down as log2 -- luma (llh, llv), each chroma component (lch, lcv) --
+    // and the counts derived from them.  AMV / SP5X / 4:2:0 JPEG: 2x2 luma, 1x1 chroma, 6 blocks per MCU
+    int llh, llv, lch, lcv;
+    int nl, nc, nb;    // luma blocks, blocks of one chroma component, all blocks of an MCU
     int y0, c0;        // first (bottom-most stored) row of luma / chroma in flipped order
     int flip;          // 1: rows are addressed bottom-up from y0 / c0 (AMV); 0: top-down (SP5X)
 };
@@ -47,17 +51,22 @@ AMV_HD int flip_start_row(int h, int vs) {
     return vs * (8 * mbh - ((h >> 1) & 7)) - 1;
 }
 
-AMV_HD Geom make_geom(int w, int h) {
+// sampling factors as log2: (1,1,0,0) = 4:2:0, (1,0,0,0) = 4:2:2 as 2x1 / 1x1, (1,1,0,1) = 4:2:2 as 2x2 / 1x2 (what the
+// reference's mjpeg_encoder writes), (0,0,0,0) = 4:4:4
+AMV_HD Geom make_geom_sampled(int w, int h, int llh, int llv, int lch, int lcv) {
     Geom g;
     g.w = w; g.h = h;
-    g.cw = (w + 1) >> 1; g.ch = (h + 1) >> 1;
-    g.mbw = (w + 15) >> 4; g.mbh = (h + 15) >> 4;
-    g.nblk = 6 * g.mbw * g.mbh;
+    g.llh = llh; g.llv = llv; g.lch = lch; g.lcv = lcv;
+    g.nl = 1 << (llh + llv); g.nc = 1 << (lch + lcv); g.nb = g.nl + 2 * g.nc;
+    g.cw = ((w << lch) + (1 << llh) - 1) >> llh; g.ch = ((h << lcv) + (1 << llv) - 1) >> llv;
+    g.mbw = (w + (8 << llh) - 1) / (8 << llh); g.mbh = (h + (8 << llv) - 1) / (8 << llv);
+    g.nblk = g.nb * g.mbw * g.mbh;
     g.y0 = flip_start_row(h, 2);
     g.c0 = flip_start_row(h, 1);
     g.flip = 1;
     return g;
 }
+AMV_HD Geom make_geom(int w, int h) { return make_geom_sampled(w, h, 1, 1, 0, 0); }
 
 AMV_HD uint32_t bswap32(uint32_t v) {
 #if defined(__CUDA_ARCH__)

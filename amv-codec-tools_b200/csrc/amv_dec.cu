@@ -317,18 +317,21 @@ __global__ void __launch_bounds__(kTokThreads)
 k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
            const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
            uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */, int flavor,
-           const DecTableSet *__restrict__ tabs, const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */) {
+           const DecTableSet *__restrict__ tabs, const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */,
+           int nl, int nc /* blocks per MCU: luma, one chroma component */) {
     extern __shared__ uint8_t sync_smem_raw[];
     const uint32_t raw_s = smem_addr(sync_smem_raw);
     SyncSmem &S = *reinterpret_cast<SyncSmem *>(sync_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
     const int nlut = tabs->flat.count;
     for (int i = threadIdx.x; i < nlut; i += blockDim.x) S.lut[i] = tabs->flat.e[i];
     const uint32_t lut_s = smem_addr(S.lut);
-    if (threadIdx.x < 6) {
-        const uint32_t bq = threadIdx.x, tq = bq >= 4 ? 1 : 0;
+    const uint32_t nbm = (uint32_t)(nl + 2 * nc);               // blocks per MCU (<= 8): nl luma, nc Cb, nc Cr
+    if (threadIdx.x < nbm) {
+        const uint32_t bq = threadIdx.x, tq = bq >= (uint32_t)nl ? 1 : 0;
+        const bool enters = bq == 0 || bq == (uint32_t)nl || bq == (uint32_t)(nl + nc);   // first block of a component
         uint2 bs;
         bs.x = ((lut_s + (uint32_t)tabs->flat.base[tq] * 4u) << 8) | (32u - kFlatDcBits);
-        bs.y = ((lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | ((bq == 0 || bq >= 4) ? 0x80u : 0u);
+        bs.y = ((lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | (enters ? 0x80u : 0u);
         S.bstate[bq] = bs;
     }
     __syncthreads();
@@ -422,7 +425,7 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
                 dA += (isdc && on) ? lvl : 0;
                 const bool nz = (int)e < 0;             // the symbol carries a value (for AC symbols: size != 0)
                 const bool endp = on && kb >= 64u && (nz || kb >= 128u);
-                b = endp ? (b == 5u ? 0u : b + 1u) : b;
+                b = endp ? (b + 1u == nbm ? 0u : b + 1u) : b;
                 nb += endp ? 1u : 0u;
                 const uint2 bs = S.bstate[b];            // after the step: the next block's tables at a block end
                 const bool rot = endp && (bs.y & 0x80u);
@@ -436,7 +439,7 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
         }
         if (need) {
             // the sums sit rotated to the component of the block that comes next
-            const int c = b < 4u ? 0 : (int)b - 3;
+            const int c = b < (uint32_t)nl ? 0 : (b < (uint32_t)(nl + nc) ? 1 : 2);
             ex.bitpos = bp; ex.phase = b; ex.nblocks = nb;
             ex.dc[0] = c == 0 ? dA : (c == 1 ? dC : dB);
             ex.dc[1] = c == 0 ? dB : (c == 1 ? dA : dC);
@@ -525,7 +528,8 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
              const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
              const LaneStart *__restrict__ starts, int nblk, uint32_t *__restrict__ tokens,
              uint32_t *__restrict__ blk_off, int32_t *__restrict__ status, const DecTableSet *__restrict__ tabs,
-             const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */) {
+             const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */,
+             int nl, int nc /* blocks per MCU: luma, one chroma component */) {
     extern __shared__ uint8_t tok_smem_raw[];
     const uint32_t raw_s = smem_addr(tok_smem_raw);
     TokSmem &S = *reinterpret_cast<TokSmem *>(tok_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
@@ -538,15 +542,17 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     }
     const uint32_t lut_s = smem_addr(S.lut);
     const uint32_t bstate_s = smem_addr(&S.bstate[0]);
-    if (threadIdx.x < 6) {
-        // block b of the MCU (Y Y Y Y Cb Cr): its tables, the entry of the block after it, and whether the
-        // component changes on entering it
-        const uint32_t bq = threadIdx.x, tq = bq >= 4 ? 1 : 0;
+    const uint32_t nbm = (uint32_t)(nl + 2 * nc);               // blocks per MCU (<= 8): nl luma, nc Cb, nc Cr
+    if (threadIdx.x < nbm) {
+        // block b of the MCU (Y.. Cb.. Cr..; Y Y Y Y Cb Cr for AMV): its tables, the entry of the block after it, and
+        // whether the component changes on entering it
+        const uint32_t bq = threadIdx.x, tq = bq >= (uint32_t)nl ? 1 : 0;
+        const bool enters = bq == 0 || bq == (uint32_t)nl || bq == (uint32_t)(nl + nc);
         uint4 bs;
         bs.x = ((lut_s + (uint32_t)tabs->flat.base[tq] * 4u) << 8) | (32u - kFlatDcBits);
-        bs.y = ((lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | ((bq == 0 || bq >= 4) ? 0x80u : 0u);
+        bs.y = ((lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u) << 8) | (32u - kFlatAcBits) | (enters ? 0x80u : 0u);
         bs.z = smem_addr(&S.tz[tq][0]);
-        bs.w = bstate_s + (bq == 5 ? 0u : bq + 1u) * 16u;
+        bs.w = bstate_s + (bq + 1u == nbm ? 0u : bq + 1u) * 16u;
         S.bstate[bq] = bs;
     }
     __syncthreads();
@@ -639,11 +645,11 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         pend = load_group(wr);
     }
     {   // every lane gets valid tables, also the ones without work: they run the symbol code with frozen state
-        const uint32_t b = first % 6u;
+        const uint32_t b = first % nbm;
         const uint4 bs = S.bstate[b];
         desc = bs.x; acd = bs.y; tzp = bs.z; nxt_s = bs.w;
-        if (b == 4) { predA = pred1; predB = pred2; predC = pred0; }
-        if (b == 5) { predA = pred2; predB = pred0; predC = pred1; }
+        if (b >= (uint32_t)nl && b < (uint32_t)(nl + nc)) { predA = pred1; predB = pred2; predC = pred0; }
+        if (b >= (uint32_t)(nl + nc)) { predA = pred2; predB = pred0; predC = pred1; }
     }
 
     while (__any_sync(0xffffffffu, on)) {
@@ -758,18 +764,23 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
     if (f >= n) return;
     if (scan_len[f] == 0) return;
     const int i = (int)(gt - (int64_t)f * g.nblk);
-    const int nluma = 4 * g.mbw * g.mbh, nchroma = g.mbw * g.mbh;
+    // blocks are enumerated in plane raster order (all of Y, then Cb, then Cr); blk = the block's index in
+    // bitstream order: MCU by MCU, inside an MCU component by component, v x h blocks in raster order
+    const int nluma = g.nl * g.mbw * g.mbh, nchroma = g.nc * g.mbw * g.mbh;
     int comp, bx, by, blk;
     if (i < nluma) {
         comp = 0;
-        by = i / (2 * g.mbw); bx = i - by * 2 * g.mbw;
-        blk = ((by >> 1) * g.mbw + (bx >> 1)) * 6 + (by & 1) * 2 + (bx & 1);
+        const int rowb = g.mbw << g.llh;
+        by = i / rowb; bx = i - by * rowb;
+        blk = ((by >> g.llv) * g.mbw + (bx >> g.llh)) * g.nb + ((by & ((1 << g.llv) - 1)) << g.llh) + (bx & ((1 << g.llh) - 1));
     } else {
         const int j = i - nluma;
         comp = j < nchroma ? 1 : 2;
         const int jj = comp == 1 ? j : j - nchroma;
-        by = jj / g.mbw; bx = jj - by * g.mbw;
-        blk = jj * 6 + 3 + comp;
+        const int rowb = g.mbw << g.lch;
+        by = jj / rowb; bx = jj - by * rowb;
+        blk = ((by >> g.lcv) * g.mbw + (bx >> g.lch)) * g.nb + g.nl + (comp - 1) * g.nc +
+              ((by & ((1 << g.lcv) - 1)) << g.lch) + (bx & ((1 << g.lch) - 1));
     }
     const uint32_t bo = blk_off[(uint64_t)f * g.nblk + blk];
     const uint32_t *tf = tokens + slot_off[f] * 4;                         // the frame's token region (16-byte aligned)
@@ -926,7 +937,7 @@ void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t
 
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
-                     cudaStream_t s) {
+                     int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
     static bool attr_set = false;
@@ -935,12 +946,13 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
         attr_set = true;
     }
     k_vlc_sync<<<grid, kTokThreads, kSyncSmemBytes, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
-                                            amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab);
+                                            amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab, nl, nc);
 }
 
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, cudaStream_t s) {
+                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, int nl, int nc,
+                       cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
     static bool attr_set = false;
@@ -952,13 +964,13 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
     }
     if (amvlib)
         k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                                 tokens, blk_off, status, tabs, nullptr);
+                                                                 tokens, blk_off, status, tabs, nullptr, nl, nc);
     else if (qtab)
         k_vlc_tokens<kFlavorJpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                               tokens, blk_off, status, tabs, qtab);
+                                                               tokens, blk_off, status, tabs, qtab, nl, nc);
     else
         k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                                 tokens, blk_off, status, tabs, nullptr);
+                                                                 tokens, blk_off, status, tabs, nullptr, nl, nc);
 }
 
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,

@@ -40,10 +40,11 @@ void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t
 // qtab != nullptr: per-frame quantisers (plain JPEG) instead of the table set's
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
-                     cudaStream_t s);
+                     int nl, int nc /* blocks per MCU: luma, one chroma component */, cudaStream_t s);
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, cudaStream_t s);
+                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, int nl, int nc,
+                       cudaStream_t s);
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
                  const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                  cudaStream_t s);

@@ -111,18 +111,21 @@ static int amvcuda_mjpeg_frame(AVCodecContext *avctx, void *data, int *data_size
             c->configured = 1;
             if (w != avctx->width || h != avctx->height) avcodec_set_dimensions(avctx, w, h);
         }
-        avctx->pix_fmt = PIX_FMT_YUVJ420P;
-        if (c->picture.data[0]) avctx->release_buffer(avctx, &c->picture);
-        c->picture.reference = 0;
-        if (avctx->get_buffer(avctx, &c->picture) < 0) return -1;
-        c->picture.pict_type = FF_I_TYPE;
-        c->picture.key_frame = 1;
-        if (amv_decode_frames_mjpeg(c->h, buf, (uint64_t)buf_size, &off, &size, 1, w, h,
-                                    c->picture.data[0], c->picture.data[1], c->picture.data[2],
-                                    c->picture.linesize[0], c->picture.linesize[1],
-                                    (uint64_t)c->picture.linesize[0] * h, (uint64_t)c->picture.linesize[1] * ((h + 1) / 2),
-                                    &status, AMV_MEM_HOST) != AMV_OK)
-            return -1;
+        {   /* pix_fmt from the sampling, as ff_mjpeg_decode_sof does (mjpegdec.c:283-311) */
+            const int cw = (int)amv_get_stat(c->h, "mjpeg_chroma_width"), ch = (int)amv_get_stat(c->h, "mjpeg_chroma_height");
+            avctx->pix_fmt = ch < h ? PIX_FMT_YUVJ420P : (cw < w ? PIX_FMT_YUVJ422P : PIX_FMT_YUVJ444P);
+            if (c->picture.data[0]) avctx->release_buffer(avctx, &c->picture);
+            c->picture.reference = 0;
+            if (avctx->get_buffer(avctx, &c->picture) < 0) return -1;
+            c->picture.pict_type = FF_I_TYPE;
+            c->picture.key_frame = 1;
+            if (amv_decode_frames_mjpeg(c->h, buf, (uint64_t)buf_size, &off, &size, 1, w, h,
+                                        c->picture.data[0], c->picture.data[1], c->picture.data[2],
+                                        c->picture.linesize[0], c->picture.linesize[1],
+                                        (uint64_t)c->picture.linesize[0] * h, (uint64_t)c->picture.linesize[1] * ch,
+                                        &status, AMV_MEM_HOST) != AMV_OK)
+                return -1;
+        }
         if (!(status & AMV_ST_HEADER)) break;
         if (attempt == 1) return -1;
     }

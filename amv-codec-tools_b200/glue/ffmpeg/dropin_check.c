@@ -17,6 +17,7 @@ extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_d
                amvcuda_sp5x_decoder, amvcuda_mjpeg_decoder;
 void amvcuda_register_codecs(void);
 
+static int g_pix_fmt = PIX_FMT_YUVJ420P;      /* input / output layout of encode_all / decode_all */
 static unsigned rng_state = 12345;
 static unsigned rnd(void) { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
 
@@ -41,10 +42,10 @@ static int encode_all(AVCodec *codec, int w, int h, int n, int quality, uint8_t 
     AVFrame *pic = avcodec_alloc_frame();
     int i, bufsz = w * h * 6 + 262144, cw = (w + 1) / 2;
     uint8_t *buf = av_malloc(bufsz);
-    c->width = w; c->height = h; c->time_base.num = 1; c->time_base.den = 16; c->pix_fmt = PIX_FMT_YUVJ420P;
+    c->width = w; c->height = h; c->time_base.num = 1; c->time_base.den = 16; c->pix_fmt = g_pix_fmt;
     if (avcodec_open(c, codec) < 0) return -1;
     for (i = 0; i < n; i++) {
-        pic->data[0] = ys[i]; pic->data[1] = us[i]; pic->data[2] = vs[i];
+        pic->data[0] = ys[i]; pic->data[1] = us[i]; pic->data[2] = vs[i];      /* 4:2:2: the caller passes full-height chroma */
         pic->linesize[0] = w; pic->linesize[1] = cw; pic->linesize[2] = cw;
         pic->quality = quality; pic->pts = i;
         int sz = avcodec_encode_video(c, buf, bufsz, pic);
@@ -61,14 +62,14 @@ static int decode_all(AVCodec *codec, int w, int h, int n, Packet *pk, uint8_t *
 {
     AVCodecContext *c = avcodec_alloc_context();
     AVFrame *pic = avcodec_alloc_frame();
-    int i, r, cw = (w + 1) / 2, ch = (h + 1) / 2;
+    int i, r, cw = (w + 1) / 2, ch = g_pix_fmt == PIX_FMT_YUVJ422P ? h : (h + 1) / 2;
     c->width = w; c->height = h; c->coded_width = w; c->coded_height = h;
     if (avcodec_open(c, codec) < 0) return -1;
     for (i = 0; i < n; i++) {
         int got = 0;
         int ret = avcodec_decode_video(c, pic, &got, pk[i].pk, pk[i].size);
         if (ret < 0 || !got) return -2;
-        if (!pic->key_frame || pic->pict_type != FF_I_TYPE || c->pix_fmt != PIX_FMT_YUVJ420P) return -3;
+        if (!pic->key_frame || pic->pict_type != FF_I_TYPE || c->pix_fmt != g_pix_fmt) return -3;
         uint8_t *d = planes + (size_t)i * (w * h + 2 * cw * ch);
         for (r = 0; r < h; r++) memcpy(d + r * w, pic->data[0] + r * pic->linesize[0], w);
         for (r = 0; r < ch; r++) {
@@ -173,6 +174,24 @@ int main(int argc, char **argv)
             if (ra || rb) { printf("FAIL: mjpeg decode returned %d / %d\n", ra, rb); return 8; }
             if (memcmp(da, db, (size_t)n * fb)) { printf("FAIL: mjpeg planes differ (quality %d)\n", quality); fail = 1; mfail = 1; }
             printf("mjpeg %dx%d x%d quality %d: planes %s\n", w, h, n, quality, mfail ? "DIFFER" : "identical");
+            {   /* the same through YUVJ422P (the encoder writes 2x2 / 1x2 / 1x2 sampling; chroma planes cw x h) */
+                uint8_t **u2 = malloc(n * sizeof(*u2)), **v2 = malloc(n * sizeof(*v2));
+                uint8_t *ea = malloc((size_t)n * (w * h + 2 * cw * h)), *eb = malloc((size_t)n * (w * h + 2 * cw * h));
+                int r2, f2 = 0;
+                for (i = 0; i < n; i++) {
+                    u2[i] = malloc(cw * h); v2[i] = malloc(cw * h);
+                    for (r2 = 0; r2 < h; r2++) { memcpy(u2[i] + r2 * cw, us[i] + (r2 / 2) * cw, cw); memcpy(v2[i] + r2 * cw, vs[i] + (r2 / 2) * cw, cw); }
+                }
+                g_pix_fmt = PIX_FMT_YUVJ422P;
+                ra = encode_all(&mjpeg_encoder, w, h, n, quality, ys, u2, v2, pm);
+                if (!ra) ra = decode_all(avcodec_find_decoder(CODEC_ID_MJPEG), w, h, n, pm, ea);
+                rb = decode_all(&mjpeg_decoder, w, h, n, pm, eb);
+                g_pix_fmt = PIX_FMT_YUVJ420P;
+                if (ra || rb) { printf("FAIL: mjpeg 4:2:2 returned %d / %d\n", ra, rb); return 9; }
+                if (memcmp(ea, eb, (size_t)n * (w * h + 2 * cw * h))) { printf("FAIL: mjpeg 4:2:2 planes differ (quality %d)\n", quality); fail = 1; f2 = 1; }
+                printf("mjpeg 4:2:2 %dx%d x%d quality %d: planes %s\n", w, h, n, quality, f2 ? "DIFFER" : "identical");
+                free(ea); free(eb);
+            }
         }
         free(da); free(db);
     }

@@ -163,9 +163,11 @@ AMV_API int amv_decode_frames_sp5x(amv_ctx *ctx,
  * the picture is stored top-down.
  *
  * amv_mjpeg_configure reads the marker segments of ONE sample frame (a HOST pointer; the AVCodec shim
- * hands it the first packet): 8-bit SOF0, three components sampled 2x2 / 1x1 / 1x1 (YUVJ420P), components
+ * hands it the first packet): 8-bit SOF0, three components sampled 4:2:0 (2x2 / 1x1 / 1x1, YUVJ420P), 4:2:2
+ * (2x1 / 1x1 / 1x1 or the reference encoder's 2x2 / 1x2 / 1x2, YUVJ422P) or 4:4:4 (YUVJ444P), components
  * 1 and 2 sharing their quantiser and Huffman tables, sequential scan, no restart interval.  Anything else
- * is AMV_ERR_UNSUPPORTED.  *w / *h receive the picture size (may be NULL).
+ * is AMV_ERR_UNSUPPORTED.  *w / *h receive the picture size (may be NULL).  The chroma planes of the decode
+ * call are ceil(w * hc / hmax) x ceil(h * vc / vmax) -- amv_get_stat "mjpeg_chroma_width" / "mjpeg_chroma_height".
  *
  * amv_decode_frames_mjpeg then decodes frames whose bytes up to the end of the SOS header equal the sample's
  * outside the quantiser values: every frame is dequantised with the tables of its OWN DQT segment (the

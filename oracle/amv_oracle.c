@@ -457,6 +457,7 @@ typedef struct {
     uint8_t cnt[4][16];      /* codes per length 1..16 */
     uint8_t sym[4][256];     /* symbols in code order */
     uint8_t qzz[2][64];      /* quantisers in zigzag (DQT) order: component 0, components 1/2 */
+    uint8_t hs[3], vs[3];    /* sampling factors of the three components (SOF0); all zero = 2x2, 1x1, 1x1 */
 } scan_tables;
 
 static const scan_tables *fixed_tables(void)
@@ -467,6 +468,7 @@ static const scan_tables *fixed_tables(void)
         memcpy(T.sym[0], kSymDC, 12); memcpy(T.sym[1], kSymDC, 12);
         memcpy(T.sym[2], kSymACL, 162); memcpy(T.sym[3], kSymACC, 162);
         memcpy(T.qzz, kDecQuantZZ, sizeof(T.qzz));
+        T.hs[0] = T.vs[0] = 2; T.hs[1] = T.vs[1] = T.hs[2] = T.vs[2] = 1;
         ready = 1;
     }
     return &T;
@@ -533,8 +535,16 @@ static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int
 {
     build_tables();
     if (!T) T = fixed_tables();
-    const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
-    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    /* interleaved scan (mjpeg_decode_scan mjpegdec.c:660-736): per MCU, per component, v x h blocks in raster
+     * order (:700-722); the MCU covers 8*h_max x 8*v_max pixels (ff_mjpeg_decode_sos :808-811); component c's
+     * plane is ceil(w * h_c / h_max) x ceil(h * v_c / v_max) */
+    const int hmax = T->hs[0] > T->hs[1] ? T->hs[0] : T->hs[1], vmax = T->vs[0] > T->vs[1] ? T->vs[0] : T->vs[1];
+    const int mbw = (w + 8 * hmax - 1) / (8 * hmax), mbh = (h + 8 * vmax - 1) / (8 * vmax);
+    int pw[3], ph[3];
+    for (int c = 0; c < 3; c++) {
+        pw[c] = (w * T->hs[c] + hmax - 1) / hmax;
+        ph[c] = (h * T->vs[c] + vmax - 1) / vmax;
+    }
     int16_t q[2][64];                                       /* raster order (mjpegdec.c:131-134) */
     for (int t = 0; t < 2; t++) for (int k = 0; k < 64; k++) q[t][g_zz[k]] = T->qzz[t][k];
     bitr br = { scan, nscan, 0, 0, 0, 0 };
@@ -544,8 +554,9 @@ static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int
 
     for (int my = 0; my < mbh && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); my++)
     for (int mx = 0; mx < mbw && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); mx++)
-    for (int b = 0; b < 6; b++, nblk++) {
-        const int comp = b < 4 ? 0 : b - 3, tq = comp ? 1 : 0;
+    for (int comp = 0; comp < 3 && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); comp++)
+    for (int b = 0; b < T->hs[comp] * T->vs[comp]; b++, nblk++) {
+        const int tq = comp ? 1 : 0;
         int16_t blk[64] = { 0 };
         int s = huff_get(&br, T, tq);
         if (s < 0) { flags |= AMVO_E_BADCODE; break; }
@@ -567,13 +578,13 @@ static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int
 
         uint8_t px[64], ud[64];
         amvo_idct_put_ex(blk, px, ud);
-        /* bottom-up placement (mjpegdec.c:672-677,710-716), clipped to the picture */
+        /* placement (mjpegdec.c:672-677,710-716; bottom-up for AMV), clipped to the picture */
         uint8_t *pl = comp == 0 ? py : (comp == 1 ? pu : pv);
         uint8_t *um = comp == 0 ? uy : (comp == 1 ? uu : uv);
-        const int ls = comp ? ls_c : ls_y, vw = comp ? cw : w, vh = comp ? chh : h;
+        const int ls = comp ? ls_c : ls_y, vw = pw[comp], vh = ph[comp];
         const int r0 = comp ? c0 : y0;
-        const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
-        const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+        const int bx = (T->hs[comp] * mx + b % T->hs[comp]) * 8;
+        const int by = (T->vs[comp] * my + b / T->hs[comp]) * 8;
         for (int yy = 0; yy < 8; yy++) {
             int row = flip ? r0 - (by + yy) : by + yy;
             if (row < 0 || row >= vh) continue;
@@ -685,11 +696,14 @@ static int mjpeg_parse(const uint8_t *p, uint32_t size, mjpeg_header *H)
         } else if (m == 0xc0) {                                          /* SOF0 */
             if (n < 15 || d[0] != 8 || d[5] != 3) return -1;
             H->h = (d[1] << 8) | d[2]; H->w = (d[3] << 8) | d[4];
-            static const uint8_t want[3] = { 0x22, 0x11, 0x11 };
             for (int c = 0; c < 3; c++) {
                 comp_id[c] = d[6 + 3 * c];
-                if (d[7 + 3 * c] != want[c]) return -1;
+                H->T.hs[c] = d[7 + 3 * c] >> 4; H->T.vs[c] = d[7 + 3 * c] & 15;
                 comp_q[c] = d[8 + 3 * c]; if (comp_q[c] >= 4) return -1;
+            }
+            {   /* 4:2:0 (0x221111), 4:2:2 as 0x211111 or the encoder's 0x221212, 4:4:4 (0x111111): ff_mjpeg_decode_sof :283-311 */
+                const unsigned id = (d[7] << 16) | (d[10] << 8) | d[13];
+                if (id != 0x221111 && id != 0x211111 && id != 0x221212 && id != 0x111111) return -1;
             }
             if (comp_q[1] != comp_q[2]) return -1;
             have_sof = 1;
@@ -721,13 +735,25 @@ static int mjpeg_parse(const uint8_t *p, uint32_t size, mjpeg_header *H)
     return -1;
 }
 
-AMVO_API int amvo_mjpeg_header(const uint8_t *pkt, uint32_t size, int *w, int *h, uint32_t *scan_start)
+static void mjpeg_chroma_dims(const mjpeg_header *H, int *cw, int *ch)
+{
+    const int hmax = H->T.hs[0], vmax = H->T.vs[0];
+    *cw = (H->w * H->T.hs[1] + hmax - 1) / hmax;
+    *ch = (H->h * H->T.vs[1] + vmax - 1) / vmax;
+}
+
+/* -> picture size, where the scan starts, and the chroma plane size the sampling gives (any pointer may be NULL) */
+AMVO_API int amvo_mjpeg_header(const uint8_t *pkt, uint32_t size, int *w, int *h, uint32_t *scan_start, int *cw, int *ch)
 {
     mjpeg_header H;
+    int a, b;
     if (mjpeg_parse(pkt, size, &H)) return -1;
+    mjpeg_chroma_dims(&H, &a, &b);
     if (w) *w = H.w;
     if (h) *h = H.h;
     if (scan_start) *scan_start = H.scan_start;
+    if (cw) *cw = a;
+    if (ch) *ch = b;
     return 0;
 }
 
@@ -747,11 +773,11 @@ AMVO_API int amvo_mjpeg_decode_frame(const uint8_t *pkt, uint32_t size, int w, i
     return flags;
 }
 
+/* cw x chh: the chroma plane size of the frames' sampling (amvo_mjpeg_header) */
 AMVO_API int amvo_mjpeg_decode_frames(const uint8_t *pkts, const uint64_t *off, const uint32_t *size,
-                                      int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int *status,
+                                      int n, int w, int h, int cw, int chh, uint8_t *y, uint8_t *u, uint8_t *v, int *status,
                                       uint8_t *uy, uint8_t *uu, uint8_t *uv)
 {
-    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
     for (int i = 0; i < n; i++) {
         size_t yo = (size_t)i * w * h, co = (size_t)i * cw * chh;
         int st = amvo_mjpeg_decode_frame(pkts + off[i], size[i], w, h, y + yo, u + co, v + co, w, cw,

@@ -38,7 +38,7 @@ const char *amvref_version(void) { return "amv-codec-tools AMVmuxer libavcodec "
  * quality = AVFrame.quality (lambda; 0 => reference default qscale 2).
  * Packets are written back to back into out[0..cap); off[i]/size[i] locate them.
  * Returns number of frames encoded, or a negative error. */
-static int encode_frames_with(AVCodec *codec, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+static int encode_frames_with(AVCodec *codec, int pix_fmt, const uint8_t *y, const uint8_t *u, const uint8_t *v,
                               int n, int w, int h, int quality,
                               uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap);
 
@@ -46,33 +46,35 @@ int amvref_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
                          int n, int w, int h, int quality,
                          uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
 {
-    return encode_frames_with(&amv_encoder, y, u, v, n, w, h, quality, out, off, size, cap);
+    return encode_frames_with(&amv_encoder, PIX_FMT_YUVJ420P, y, u, v, n, w, h, quality, out, off, size, cap);
 }
 
 /* the plain MJPEG codecs of the same source files (mjpegenc.c:474-483, mjpegdec.c:1361-1372): full JPEG
  * frames with their tables in the stream, top-down pictures */
 extern AVCodec mjpeg_encoder, mjpeg_decoder;
+/* chroma_rows == h: the planes are YUVJ422P (chroma ceil(w/2) x h), else YUVJ420P */
 int amvref_mjpeg_encode_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v,
-                               int n, int w, int h, int quality,
+                               int n, int w, int h, int chroma_rows, int quality,
                                uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
 {
-    return encode_frames_with(&mjpeg_encoder, y, u, v, n, w, h, quality, out, off, size, cap);
+    return encode_frames_with(&mjpeg_encoder, chroma_rows == h ? PIX_FMT_YUVJ422P : PIX_FMT_YUVJ420P, y, u, v, n, w, h, quality,
+                              out, off, size, cap);
 }
 
-static int encode_frames_with(AVCodec *codec, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+static int encode_frames_with(AVCodec *codec, int pix_fmt, const uint8_t *y, const uint8_t *u, const uint8_t *v,
                               int n, int w, int h, int quality,
                               uint8_t *out, uint64_t *off, uint32_t *size, uint64_t cap)
 {
     ref_init();
     AVCodecContext *c = avcodec_alloc_context();
     AVFrame *pic = avcodec_alloc_frame();
-    int cw = (w + 1) >> 1, ch = (h + 1) >> 1, i, ret = 0;
+    int cw = (w + 1) >> 1, ch = pix_fmt == PIX_FMT_YUVJ422P ? h : (h + 1) >> 1, i, ret = 0;
     int bufsz = w * h * 6 + 262144;
     uint8_t *buf = av_malloc(bufsz);
     uint64_t pos = 0;
     c->width = w; c->height = h;
     c->time_base.num = 1; c->time_base.den = 16;
-    c->pix_fmt = PIX_FMT_YUVJ420P;
+    c->pix_fmt = pix_fmt;
     if (avcodec_open(c, codec) < 0) { ret = -2; goto done; }
     for (i = 0; i < n; i++) {
         /* amv_encode_picture mutates data[]/linesize[] (mjpegenc.c:467-470): refill every frame */
@@ -147,6 +149,9 @@ static int decode_frames_with(AVCodec *codec, const uint8_t *pkts, const uint64_
         if (got) got[i] = g;
         if (ret_bytes) ret_bytes[i] = r;
         if (r < 0 || !g) continue;
+        /* chroma plane size by what the decoder says it decoded (mjpegdec.c:283-311); planes are packed at that size */
+        if (c->pix_fmt == PIX_FMT_YUVJ422P) { ch = h; }
+        else if (c->pix_fmt == PIX_FMT_YUVJ444P) { ch = h; cw = w; }
         for (r = 0; r < h; r++)
             memcpy(y + (size_t)i * w * h + (size_t)r * w, pic->data[0] + r * pic->linesize[0], w);
         for (r = 0; r < ch; r++) {

@@ -187,24 +187,27 @@ class Oracle(_AmvlibOracleMixin):
                                          _p(m[0]), _p(m[1]), _p(m[2]))
         return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
 
-    def mjpeg_header(self, pkt):
-        """-> (w, h, scan_start) of a baseline 4:2:0 JPEG the path supports, or None"""
+    def mjpeg_header(self, pkt, chroma=False):
+        """-> (w, h, scan_start[, cw, ch]) of a baseline JPEG the path supports, or None"""
         pk = np.ascontiguousarray(pkt, np.uint8)
-        w, h, ss = C.c_int(0), C.c_int(0), C.c_uint32(0)
-        if self.lib.amvo_mjpeg_header(_p(pk), len(pk), C.byref(w), C.byref(h), C.byref(ss)):
+        w, h, ss, cw, ch = C.c_int(0), C.c_int(0), C.c_uint32(0), C.c_int(0), C.c_int(0)
+        if self.lib.amvo_mjpeg_header(_p(pk), len(pk), C.byref(w), C.byref(h), C.byref(ss), C.byref(cw), C.byref(ch)):
             return None
-        return w.value, h.value, ss.value
+        return (w.value, h.value, ss.value, cw.value, ch.value) if chroma else (w.value, h.value, ss.value)
 
     def mjpeg_decode_frames(self, pkts, off, size, w, h, undef=False):
+        """chroma planes come at the size the frames' sampling gives (first frame's header)"""
         n = len(size)
-        cw, ch = chroma_dims(w, h)
+        pk0 = np.ascontiguousarray(pkts, np.uint8)[int(off[0]): int(off[0]) + int(size[0])]
+        hd = self.mjpeg_header(pk0, chroma=True)
+        cw, ch = (hd[3], hd[4]) if hd else chroma_dims(w, h)
         y = np.zeros((n, h, w), np.uint8)
         u = np.zeros((n, ch, cw), np.uint8)
         v = np.zeros((n, ch, cw), np.uint8)
         m = [np.zeros_like(a) for a in (y, u, v)] if undef else [None] * 3
         st = np.zeros(n, np.int32)
         self.lib.amvo_mjpeg_decode_frames(_p(np.ascontiguousarray(pkts, np.uint8)), _p(np.ascontiguousarray(off, np.uint64)),
-                                          _p(np.ascontiguousarray(size, np.uint32)), n, w, h, _p(y), _p(u), _p(v), _p(st),
+                                          _p(np.ascontiguousarray(size, np.uint32)), n, w, h, cw, ch, _p(y), _p(u), _p(v), _p(st),
                                           _p(m[0]), _p(m[1]), _p(m[2]))
         return (y, u, v, st, tuple(m)) if undef else (y, u, v, st)
 
@@ -341,15 +344,16 @@ class Ref:
         out = np.zeros(cap, np.uint8)
         off = np.zeros(n, np.uint64)
         size = np.zeros(n, np.uint32)
-        r = self.lib.amvref_mjpeg_encode_frames(_p(y), _p(u), _p(v), n, w, h, int(quality), _p(out), _p(off), _p(size),
-                                                C.c_uint64(cap))
+        r = self.lib.amvref_mjpeg_encode_frames(_p(y), _p(u), _p(v), n, w, h, int(u.shape[1]), int(quality), _p(out), _p(off),
+                                                _p(size), C.c_uint64(cap))
         if r != n:
             raise RuntimeError("reference mjpeg encode failed: %d" % r)
         return out[: int(size.sum())].copy(), off, size
 
-    def decode_frames(self, pkts, off, size, w, h, sp5x=False, mjpeg=False):
+    def decode_frames(self, pkts, off, size, w, h, sp5x=False, mjpeg=False, chroma=None):
+        """chroma = (cw, ch): chroma plane size of 4:2:2 / 4:4:4 JPEG frames (default: 4:2:0)"""
         n = len(size)
-        cw, ch = chroma_dims(w, h)
+        cw, ch = chroma if chroma else chroma_dims(w, h)
         y = np.zeros((n, h, w), np.uint8)
         u = np.zeros((n, ch, cw), np.uint8)
         v = np.zeros((n, ch, cw), np.uint8)
@@ -540,6 +544,102 @@ def mjpeg_with_dqt(pkts, off, size, seed):
         assert j > 0 and d[j + 4] == 0
         d[j + 5: j + 5 + 64] = q
     return out
+
+
+def jpeg_encode_simple(oracle, y, u, v, sampling, q=(16, 24)):
+    """A minimal baseline JPEG writer (test input only; what it means is defined by the reference DECODER):
+    sampling = ((hY, vY), (hC, vC)); flat quantisers q[0] (component 0) / q[1] (components 1, 2), standard Huffman
+    tables, float DCT.  y is [h, w]; u, v are the chroma planes at the size the sampling implies."""
+    from scipy.fft import dctn
+    (hy, vy), (hc, vc) = sampling
+    h, w = y.shape
+    mbw, mbh = -(-w // (8 * hy)), -(-h // (8 * vy))
+    zz = oracle.zigzag()
+    huff = [oracle.huff(t) for t in range(4)]
+    bits = []
+
+    def put(val, n):
+        if n:
+            bits.append((int(val) & ((1 << n) - 1), n))
+
+    def category(vv):
+        a = abs(int(vv))
+        return a.bit_length()
+
+    def pad(p, ph, pw):
+        return np.pad(p, ((0, ph - p.shape[0]), (0, pw - p.shape[1])), mode="edge")
+
+    planes = [pad(y, mbh * 8 * vy, mbw * 8 * hy), pad(u, mbh * 8 * vc, mbw * 8 * hc), pad(v, mbh * 8 * vc, mbw * 8 * hc)]
+    fac = [(hy, vy), (hc, vc), (hc, vc)]
+    pred = [0, 0, 0]
+    for my in range(mbh):
+        for mx in range(mbw):
+            for c in range(3):
+                hh, vv = fac[c]
+                for b in range(hh * vv):
+                    bx, by = (hh * mx + b % hh) * 8, (vv * my + b // hh) * 8
+                    blk = planes[c][by:by + 8, bx:bx + 8].astype(np.float64) - 128.0
+                    co = np.rint(dctn(blk, norm="ortho") / (q[0] if c == 0 else q[1])).astype(int).reshape(-1)[zz]
+                    tq = 0 if c == 0 else 1
+                    d = int(co[0]) - pred[c]
+                    pred[c] = int(co[0])
+                    n = category(d)
+                    put(huff[tq][1][n], int(huff[tq][0][n]))
+                    put(d if d >= 0 else d - 1, n)
+                    run = 0
+                    last = max([k for k in range(1, 64) if co[k]] or [0])
+                    for k in range(1, last + 1):
+                        if co[k] == 0:
+                            run += 1
+                            continue
+                        while run >= 16:
+                            put(huff[2 + tq][1][0xF0], int(huff[2 + tq][0][0xF0]))
+                            run -= 16
+                        n = category(co[k])
+                        sym = (run << 4) | n
+                        put(huff[2 + tq][1][sym], int(huff[2 + tq][0][sym]))
+                        put(co[k] if co[k] >= 0 else co[k] - 1, n)
+                        run = 0
+                    if last < 63:
+                        put(huff[2 + tq][1][0], int(huff[2 + tq][0][0]))
+    acc, nacc, scan = 0, 0, bytearray()
+    for val, n in bits:
+        acc = (acc << n) | val
+        nacc += n
+        while nacc >= 8:
+            byte = (acc >> (nacc - 8)) & 0xFF
+            scan.append(byte)
+            if byte == 0xFF:
+                scan.append(0)
+            nacc -= 8
+    if nacc:
+        byte = ((acc << (8 - nacc)) | ((1 << (8 - nacc)) - 1)) & 0xFF
+        scan.append(byte)
+        if byte == 0xFF:
+            scan.append(0)
+    out = bytearray(b"\xff\xd8")
+    for tid, qq in ((0, q[0]), (1, q[1])):
+        out += b"\xff\xdb" + (67).to_bytes(2, "big") + bytes([tid]) + bytes([qq] * 64)
+    dht = bytearray()
+    for t, (cls, tid) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        ln, cd = huff[t]
+        syms = sorted([sm for sm in range(256) if ln[sm]], key=lambda sm: (int(ln[sm]), int(cd[sm])))
+        counts = [sum(1 for sm in syms if ln[sm] == L) for L in range(1, 17)]
+        dht += bytes([(cls << 4) | tid]) + bytes(counts) + bytes(syms)
+    out += b"\xff\xc4" + (2 + len(dht)).to_bytes(2, "big") + dht
+    out += b"\xff\xc0" + (17).to_bytes(2, "big") + bytes([8]) + h.to_bytes(2, "big") + w.to_bytes(2, "big") + bytes([3])
+    out += bytes([1, (hy << 4) | vy, 0, 2, (hc << 4) | vc, 1, 3, (hc << 4) | vc, 1])
+    out += b"\xff\xda" + (12).to_bytes(2, "big") + bytes([3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0])
+    out += scan + b"\xff\xd9"
+    return np.frombuffer(bytes(out), np.uint8)
+
+
+def resample_chroma(a, w, h, sampling):
+    """4:2:0 chroma planes [n, ch, cw] -> planes at the size `sampling` implies (nearest neighbour; test input only)"""
+    (hy, vy), (hc, vc) = sampling
+    cw, ch = -(-w * hc // hy), -(-h * vc // vy)
+    full = np.repeat(np.repeat(a, 2, axis=1), 2, axis=2)[:, :h, :w]
+    return full[:, ::(vy // vc), ::(hy // hc)][:, :ch, :cw].copy()
 
 
 def pack(chunks):

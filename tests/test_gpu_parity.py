@@ -592,7 +592,7 @@ def test_mjpeg_device_buffers_mixed_headers_and_errors(ctx, oracle):
         ctx.decode_frames(bk, boff, bsz, w + 16, h, mjpeg=True)
     good = np.frombuffer(frames[0], np.uint8)
     j = frames[0].find(b"\xff\xc0")
-    for pos, val in ((j + 4, 12), (j + 11, 0x21), (j + 1, 0xc2)):
+    for pos, val in ((j + 4, 12), (j + 11, 0x41), (j + 1, 0xc2)):
         bad = good.copy()
         bad[pos] = val
         with pytest.raises(amv.AmvError):

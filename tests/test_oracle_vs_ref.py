@@ -334,8 +334,46 @@ def test_mjpeg_header_rejects_what_the_path_does_not_cover(oracle, ref):
     good = pk[: int(sz[0])]
     assert oracle.mjpeg_header(good) is not None
     j = bytes(good).find(b"\xff\xc0")
-    for edit in ((j + 4, 12), (j + 11, 0x21), (j + 1, 0xc2)):        # 12-bit samples, 4:2:2 sampling, progressive SOF2
+    for edit in ((j + 4, 12), (j + 11, 0x41), (j + 1, 0xc2)):        # 12-bit samples, 4:1:1 sampling, progressive SOF2
         bad = good.copy()
         bad[edit[0]] = edit[1]
         assert oracle.mjpeg_header(bad) is None
     assert oracle.mjpeg_header(good[:100]) is None and oracle.mjpeg_header(good[2:]) is None
+
+
+@pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (208, 176, "noise"), (72, 24, "edges"), (102, 56, "sinus"), (16, 16, "flat")])
+def test_mjpeg_422_decode_identical(oracle, ref, w, h, kind):
+    """YUVJ422P through the reference's mjpeg_encoder (it writes the 2x2 / 1x2 / 1x2 sampling: eight blocks per MCU)
+    and mjpeg_decoder vs the oracle's generic MCU walk; chroma planes are ceil(w/2) x h"""
+    n = 3
+    y, u, v = synth_frames(n, w, h, seed=35, kind=kind)
+    u, v = (np.repeat(a, 2, axis=1)[:, :h, :].copy() for a in (u, v))
+    v[:, ::2, :] = np.clip(v[:, ::2, :].astype(int) - 5, 0, 255).astype(np.uint8)
+    pk, off, sz = ref.mjpeg_encode_frames(y, u, v, w, h)
+    hw, hh, start, cw, ch = oracle.mjpeg_header(pk[: int(sz[0])], chroma=True)
+    assert (hw, hh, cw, ch) == (w, h, (w + 1) // 2, h)
+    ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h, mjpeg=True, chroma=(cw, ch))
+    oy, ou, ov, st, masks = oracle.mjpeg_decode_frames(pk, off, sz, w, h, undef=True)
+    assert (got != 0).all() and (st == 0).all() and ou.shape == (n, h, (w + 1) // 2)
+    for a, b, m in zip((oy, ou, ov), (ry, ru, rv), masks):
+        assert np.array_equal(a[m == 0], b[m == 0])
+
+
+@pytest.mark.parametrize("samp", [((2, 1), (1, 1)), ((1, 1), (1, 1)), ((2, 2), (1, 1))])
+@pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (72, 24, "edges"), (102, 56, "noise")])
+def test_mjpeg_other_samplings_identical(oracle, ref, w, h, kind, samp):
+    """4:2:2 as 2x1 / 1x1 / 1x1 and 4:4:4 (and 4:2:0 with two quantiser tables in separate DQT segments): frames from a
+    minimal JPEG writer, the reference's mjpeg_decoder vs the oracle"""
+    from oracle_lib import jpeg_encode_simple, pack, resample_chroma
+    n = 2
+    y, u, v = synth_frames(n, w, h, seed=36, kind=kind)
+    U, V = resample_chroma(u, w, h, samp), resample_chroma(v, w, h, samp)
+    pk, off, sz = pack([jpeg_encode_simple(oracle, y[i], U[i], V[i], samp).tobytes() for i in range(n)])
+    hw, hh, start, cw, ch = oracle.mjpeg_header(pk[: int(sz[0])], chroma=True)
+    assert (hw, hh, cw, ch) == (w, h, U.shape[2], U.shape[1])
+    ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h, mjpeg=True, chroma=(cw, ch))
+    oy, ou, ov, st, masks = oracle.mjpeg_decode_frames(pk, off, sz, w, h, undef=True)
+    assert (got != 0).all() and (st == 0).all()
+    for a, b, m in zip((oy, ou, ov), (ry, ru, rv), masks):
+        assert np.array_equal(a[m == 0], b[m == 0])
+    assert np.abs(ry.astype(int) - y).mean() < 8            # and it is the picture that went in
