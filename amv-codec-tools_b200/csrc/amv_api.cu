@@ -149,11 +149,14 @@ struct ScopedTimer {
 
 int pick_log2p(const amv_ctx *ctx, int n) {
     if (ctx->opt_log2p >= 0) return ctx->opt_log2p > 5 ? 5 : ctx->opt_log2p;
-    // enough lanes to give every SM ~16 warps; beyond that one lane per frame has no
-    // synchronisation overhead at all
-    const int64_t want = (int64_t)kNumSMs * 16 * 32 / 2;
-    int l = 0;
-    while (l < 5 && ((int64_t)n << l) < want) l++;
+    // Splitting a frame into P lanes costs the synchronisation pass: two walks of every subsequence for a token pass
+    // that gets P times shorter, so P = 2 never pays and P >= 4 pays only while one lane per frame leaves the GPU
+    // short of warps.  Measured on 320x240 (decode ms, 1 / 4 / 8 / 16 lanes): 4096 frames 5.5 / 3.9 / 2.5 / 2.3,
+    // 8192: 6.0 / 4.3 / 3.3 / 3.8, 16384: 6.8 / 6.2 / 6.8 / 6.4, 25000: 7.7 / 9.3 / 8.9 / 9.3 -- i.e. aim at ~64 k lanes
+    // below ~20 k frames, one lane per frame above.
+    if (n >= 20000) return 0;
+    int l = 2;
+    while (l < 5 && ((int64_t)n << l) < 65536) l++;
     return l;
 }
 
