@@ -62,6 +62,7 @@ struct amv_ctx {
     void *mj_tables = nullptr;          // DecTableSet in device memory
     uint8_t *mj_hdr = nullptr;          // device copy of the sample's bytes up to the end of the SOS header
     uint32_t mj_hdr_len = 0;
+    int mj_restart = 0;                 // restart interval of the configured header (0: none, or one the reference ignores)
     int mj_samp[4] = { 1, 1, 0, 0 };    // log2 sampling of the configured header: luma h, v; chroma h, v
     uint32_t mj_qpos[2] = { 0, 0 };     // where the 64 quantisers of component 0 / components 1, 2 sit in a frame
     int mj_w = 0, mj_h = 0;
@@ -78,6 +79,7 @@ struct DecMode {
     uint32_t hdr_len = 0;
     uint32_t qpos[2] = { 0, 0 };        // plain JPEG: offsets of the per-frame quantisers
     int samp[4] = { 1, 1, 0, 0 };       // log2 sampling: luma h, v; chroma h, v (AMV / SP5X: 4:2:0)
+    int restart = 0;                    // plain JPEG: MCUs per restart interval
     Geom geom(int w, int h) const { Geom g = make_geom_sampled(w, h, samp[0], samp[1], samp[2], samp[3]); if (!flip) g.flip = 0; return g; }
     bool allow_sync = true;
 };
@@ -204,7 +206,7 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
         lc++;
     }
     { ScopedTimer tm(ctx, KK_TOKENS);
-      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, g.nl, g.nc, ctx->stream); }
+      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, g.nl, g.nc, mode.restart, ctx->stream); }
     lc++;
     F.slot_off = slot_off; F.scan_len = scan_len; F.tokens = tokens; F.blk_off = blk_off; F.st = st; F.launches = lc;
     return AMV_OK;
@@ -754,7 +756,7 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
     if (!p || size < 4 || p[0] != 0xff || p[1] != 0xd8) return fail(ctx, AMV_ERR_ARG, "not a JPEG (no SOI)");
     uint8_t q[4][64], hc[2][4][16], hs[2][4][256];
     bool have_q[4] = { false, false, false, false }, have_h[2][4] = { { false } };
-    int comp_id[3] = { 0, 0, 0 }, comp_q[3] = { 0, 0, 0 }, w = 0, h = 0, samp[4] = { 1, 1, 0, 0 };
+    int comp_id[3] = { 0, 0, 0 }, comp_q[3] = { 0, 0, 0 }, w = 0, h = 0, samp[4] = { 1, 1, 0, 0 }, restart = 0;
     bool have_sof = false;
     uint32_t i = 2, scan_start = 0, qofs[4] = { 0, 0, 0, 0 };
     int td[3] = { 0, 0, 0 }, ta[3] = { 0, 0, 0 };
@@ -811,8 +813,9 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
             have_sof = true;
         } else if (m >= 0xc1 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
             return bad("not a baseline (SOF0) frame");
-        } else if (m == 0xdd) {                                              // DRI
-            if (n < 2 || ((d[0] << 8) | d[1]) != 0) return bad("restart intervals");
+        } else if (m == 0xdd) {                                              // DRI (mjpeg_decode_dri :858-867)
+            if (len != 4) return bad("DRI segment");
+            restart = (d[0] << 8) | d[1];
         } else if (m == 0xda) {                                              // SOS
             if (!have_sof || n < 10 || d[0] != 3 || len != 6 + 2 * 3) return bad("scan header");
             for (int c = 0; c < 3; c++) {
@@ -848,6 +851,9 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
     ctx->mj_hdr_len = scan_start; ctx->mj_w = w; ctx->mj_h = h; ctx->mj_sync_ok = sync_ok;
     ctx->mj_qpos[0] = qofs[comp_q[0]]; ctx->mj_qpos[1] = qofs[comp_q[1]];
     for (int k = 0; k < 4; k++) ctx->mj_samp[k] = samp[k];
+    // the reference honours a restart interval only below 1350 MCUs (mjpegdec.c:726 "buggy workaround"): a larger one
+    // leaves the markers in the scan as data, there as here
+    ctx->mj_restart = restart < 1350 ? restart : 0;
     if (w_out) *w_out = w;
     if (h_out) *h_out = h;
     return AMV_OK;
@@ -865,7 +871,8 @@ AMV_API int amv_decode_frames_mjpeg(amv_ctx *ctx, const uint8_t *pkts, uint64_t 
     m.hdr = ctx->mj_hdr; m.hdr_len = ctx->mj_hdr_len;
     m.qpos[0] = ctx->mj_qpos[0]; m.qpos[1] = ctx->mj_qpos[1];
     for (int k = 0; k < 4; k++) m.samp[k] = ctx->mj_samp[k];
-    m.allow_sync = ctx->mj_sync_ok;
+    m.restart = ctx->mj_restart;
+    m.allow_sync = ctx->mj_sync_ok && !ctx->mj_restart;      // restart intervals: one lane per frame (the lane hand-over carries no restart state)
     return decode_frames_common(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mem, m);
 }
 

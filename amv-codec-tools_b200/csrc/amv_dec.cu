@@ -283,7 +283,8 @@ struct DecTableSet {
 // which reference decoder the arithmetic follows: the ffmpeg fork's (sp5xdec/mjpegdec/simple_idct)
 // or amvlib's (AmvJpeg.c) -- same bitstream, different quantisers, DC chain, zigzag and IDCT
 // kFlavorJpeg: ffmpeg arithmetic with PER-FRAME quantisers (a plain JPEG's own DQT segment), see k_mjpeg_check
-enum { kFlavorFfmpeg = 0, kFlavorAmvlib = 1, kFlavorJpeg = 2 };
+// kFlavorJpegDri: the same with a restart interval (RSTn markers in the scan)
+enum { kFlavorFfmpeg = 0, kFlavorAmvlib = 1, kFlavorJpeg = 2, kFlavorJpegDri = 3 };
 __device__ DecTableSet g_dec_sets[2];
 
 // ------------------------------------------------------------------------------------------------
@@ -529,7 +530,10 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
              const LaneStart *__restrict__ starts, int nblk, uint32_t *__restrict__ tokens,
              uint32_t *__restrict__ blk_off, int32_t *__restrict__ status, const DecTableSet *__restrict__ tabs,
              const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */,
-             int nl, int nc /* blocks per MCU: luma, one chroma component */) {
+             int nl, int nc /* blocks per MCU: luma, one chroma component */, int restart /* kFlavorJpegDri: MCUs per interval */) {
+    constexpr bool kPerFrameQ = FLAVOR == kFlavorJpeg || FLAVOR == kFlavorJpegDri;
+    // a restart can add 23 bits (alignment + the marker) to what the symbols of a period consume: service twice as often
+    constexpr int kPeriod = FLAVOR == kFlavorJpegDri ? 2 : kTokPeriod;
     extern __shared__ uint8_t tok_smem_raw[];
     const uint32_t raw_s = smem_addr(tok_smem_raw);
     TokSmem &S = *reinterpret_cast<TokSmem *>(tok_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
@@ -564,7 +568,8 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
     const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: | (c & 7) << 7
     const uint32_t tz_s = smem_addr(&S.tz[0][0]);
-    const uint8_t *qf = FLAVOR == kFlavorJpeg ? qtab + (size_t)(f < n ? f : 0) * 128 : nullptr;   // this frame's quantisers
+    const uint8_t *qf = kPerFrameQ ? qtab + (size_t)(f < n ? f : 0) * 128 : nullptr;   // this frame's quantisers
+    int rst_count = restart;                                     // MCUs until the next restart (mjpegdec.c:682-683,726-732)
     constexpr int kPred0 = FLAVOR == kFlavorAmvlib ? 0 : 1024;   // last_dc (mjpegdec.c:805-806) / ycoef.. (AmvJpeg.c:1510)
 
     // ---- lane set-up (inactive lanes keep count = 0 and never enter the symbol code)
@@ -665,7 +670,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
         // four symbol bodies interleave freely.  A lane that has finished keeps executing with its state frozen
         // (its loads stay inside the tables and its own ring, its stores are predicated off).
 #pragma unroll
-        for (int u = 0; u < kTokPeriod; u++) {
+        for (int u = 0; u < kPeriod; u++) {
             // ---- the 32 bits at bp
             const uint32_t x = bp << 2;
             const uint32_t wa = lds32(ring_s | (x & 0x780u)), wc = lds32(ring_s | ((x + 128u) & 0x780u));
@@ -707,7 +712,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             } else {
                 // level * quant_matrix[j] as int16 (:420,428); block[0] = (int16)(last_dc += diff * q0) (:387-389)
                 int q = (int)(z & 0xffu);
-                if (FLAVOR == kFlavorJpeg) q = (int)__ldg(qf + (((tzp - tz_s) >> 3) + ((kb - 1u) & 63u)));   // tables are 512 B apart
+                if (kPerFrameQ) q = (int)__ldg(qf + (((tzp - tz_s) >> 3) + ((kb - 1u) & 63u)));   // tables are 512 B apart
                 const int prod = lvl * q;
                 const int val = prod + (isdc ? predA : 0);
                 predA = isdc ? val : predA;
@@ -722,6 +727,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             // (AC token count << 24) + index of the DC token; the sum is < 2^24 whatever tok_first wrapped to
             if (endp) boff[bi] = ((tc - blk0 - 1u) << kTokCountShift) + (tok_first + blk0);
             const uint4 bs = lds128(nxt_s);
+            const bool next_is_first = nxt_s == bstate_s;                      // the coming block opens an MCU
             zacc |= (endp && nz) ? z : 0u;
             bi += endp ? 1u : 0u;
             const bool rot = endp && (bs.y & 0x80u);
@@ -734,6 +740,17 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
             kt = endp ? (kt & ~0xffu) : kt;
             blk0 = endp ? tc : blk0;
             on = on && bi != count;
+            if (FLAVOR == kFlavorJpegDri) {
+                // end of an MCU (the coming block is block 0): count it; at the end of a restart interval the reader
+                // skips to the next byte boundary and over the RSTn marker (un-stuffing keeps FF Dn), and the DC
+                // predictors start over (mjpegdec.c:726-732).  Nothing follows the last MCU.
+                const bool mcu_end = endp && next_is_first;
+                rst_count -= mcu_end ? 1 : 0;
+                if (mcu_end && rst_count == 0) {
+                    rst_count = restart;
+                    if (on) { bp = ((bp + 7u) & ~7u) + 16u; predA = 1024; predB = 1024; predC = 1024; }
+                }
+            }
         }
     }
     if (zacc & (FLAVOR == kFlavorAmvlib ? kTzErrAmvlib : kTzErr)) st |= AMV_ST_COEFIDX;
@@ -951,26 +968,30 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
 
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
-                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, int nl, int nc,
+                       int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, int nl, int nc, int restart,
                        cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+        cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
         cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
         cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
         attr_set = true;
     }
     if (amvlib)
         k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                                 tokens, blk_off, status, tabs, nullptr, nl, nc);
+                                                                 tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
+    else if (qtab && restart)
+        k_vlc_tokens<kFlavorJpegDri><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts,
+                                                                  nblk, tokens, blk_off, status, tabs, qtab, nl, nc, restart);
     else if (qtab)
         k_vlc_tokens<kFlavorJpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                               tokens, blk_off, status, tabs, qtab, nl, nc);
+                                                               tokens, blk_off, status, tabs, qtab, nl, nc, 0);
     else
         k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-                                                                 tokens, blk_off, status, tabs, nullptr, nl, nc);
+                                                                 tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
 }
 
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,

@@ -165,7 +165,8 @@ AMV_API int amv_decode_frames_sp5x(amv_ctx *ctx,
  * amv_mjpeg_configure reads the marker segments of ONE sample frame (a HOST pointer; the AVCodec shim
  * hands it the first packet): 8-bit SOF0, three components sampled 4:2:0 (2x2 / 1x1 / 1x1, YUVJ420P), 4:2:2
  * (2x1 / 1x1 / 1x1 or the reference encoder's 2x2 / 1x2 / 1x2, YUVJ422P) or 4:4:4 (YUVJ444P), components
- * 1 and 2 sharing their quantiser and Huffman tables, sequential scan, no restart interval.  Anything else
+ * 1 and 2 sharing their quantiser and Huffman tables, one interleaved sequential scan, with or without a restart
+ * interval (DRI; honoured below 1350 MCUs like mjpegdec.c:726 does).  Anything else
  * is AMV_ERR_UNSUPPORTED.  *w / *h receive the picture size (may be NULL).  The chroma planes of the decode
  * call are ceil(w * hc / hmax) x ceil(h * vc / vmax) -- amv_get_stat "mjpeg_chroma_width" / "mjpeg_chroma_height".
  *

@@ -458,6 +458,7 @@ typedef struct {
     uint8_t sym[4][256];     /* symbols in code order */
     uint8_t qzz[2][64];      /* quantisers in zigzag (DQT) order: component 0, components 1/2 */
     uint8_t hs[3], vs[3];    /* sampling factors of the three components (SOF0); all zero = 2x2, 1x1, 1x1 */
+    int restart_interval;    /* DRI (mjpeg_decode_dri mjpegdec.c:858-867); 0 = none */
 } scan_tables;
 
 static const scan_tables *fixed_tables(void)
@@ -469,6 +470,7 @@ static const scan_tables *fixed_tables(void)
         memcpy(T.sym[2], kSymACL, 162); memcpy(T.sym[3], kSymACC, 162);
         memcpy(T.qzz, kDecQuantZZ, sizeof(T.qzz));
         T.hs[0] = T.vs[0] = 2; T.hs[1] = T.vs[1] = T.hs[2] = T.vs[2] = 1;
+        T.restart_interval = 0;
         ready = 1;
     }
     return &T;
@@ -552,8 +554,10 @@ static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int
     const int y0 = flip_start_row(h, 2), c0 = flip_start_row(h, 1);
     int nblk = 0;
 
+    int restart_count = 0;
     for (int my = 0; my < mbh && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); my++)
-    for (int mx = 0; mx < mbw && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); mx++)
+    for (int mx = 0; mx < mbw && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); mx++) {
+    if (T->restart_interval && !restart_count) restart_count = T->restart_interval;          /* :682-683 */
     for (int comp = 0; comp < 3 && !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)); comp++)
     for (int b = 0; b < T->hs[comp] * T->vs[comp]; b++, nblk++) {
         const int tq = comp ? 1 : 0;
@@ -594,6 +598,17 @@ static int decode_scan(uint8_t *scan, size_t nscan, int flags, int w, int h, int
                     if (um) um[(ptrdiff_t)row * ls + bx + xx] = ud[yy * 8 + xx];
                 }
         }
+    }
+    /* restart: byte-align, skip the RSTn marker (un-stuffing keeps FF Dn, :1151-1152), reset the predictors
+     * (:726-732, including the reference's "< 1350" condition: larger intervals are never honoured) */
+    if (T->restart_interval && T->restart_interval < 1350 && !--restart_count &&
+        !(flags & (AMVO_E_BADCODE | AMVO_E_COEFIDX)) && !(my == mbh - 1 && mx == mbw - 1) /* nothing follows the last MCU */) {
+        br_fill(&br);
+        br_skip(&br, (int)((8 - (br_bits_used(&br) & 7)) & 7));
+        br_fill(&br);
+        br_skip(&br, 16);
+        pred[0] = pred[1] = pred[2] = 1024;
+    }
     }
     if (br_bits_used(&br) > nscan * 8) flags |= AMVO_E_OVERRUN;
     return flags;
@@ -664,6 +679,7 @@ static int mjpeg_parse(const uint8_t *p, uint32_t size, mjpeg_header *H)
     uint8_t hc[2][4][16], hs[2][4][256]; int have_h[2][4] = { { 0 } };
     int comp_id[3], comp_q[3], have_sof = 0;
     uint32_t i = 0;
+    H->T.restart_interval = 0;                                          /* reset at SOI (:1225) */
     if (size < 4 || p[0] != 0xff || p[1] != 0xd8) return -1;
     i = 2;
     while (i + 4 <= size) {
@@ -710,7 +726,8 @@ static int mjpeg_parse(const uint8_t *p, uint32_t size, mjpeg_header *H)
         } else if (m >= 0xc1 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
             return -1;                                                   /* other SOFn: not baseline */
         } else if (m == 0xdd) {                                          /* DRI */
-            if (n < 2 || ((d[0] << 8) | d[1]) != 0) return -1;
+            if (len != 4) return -1;
+            H->T.restart_interval = (d[0] << 8) | d[1];
         } else if (m == 0xda) {                                          /* SOS */
             if (!have_sof || n < 10 || d[0] != 3 || len != 6 + 2 * 3) return -1;
             int td[3], ta[3];

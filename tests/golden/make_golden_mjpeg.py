@@ -47,6 +47,18 @@ def main():
             names.append(key)
             for nm, a in (("pk", pk), ("off", off), ("sz", sz), ("dy", dy), ("du", du), ("dv", dv)):
                 out["%s/%s" % (key, nm)] = a
+    # restart intervals (DRI + RSTn), again from the minimal writer and the reference decoder
+    for tag, samp, restart in (("r1", ((2, 2), (1, 1)), 1), ("r5", ((2, 2), (1, 1)), 5), ("r3s211", ((2, 1), (1, 1)), 3)):
+        for kind, w, h, n in (("sinus", 160, 120, 2), ("noise", 72, 40, 2)):
+            y, u, v = synth_frames(n, w, h, seed=29, kind=kind)
+            U, V = resample_chroma(u, w, h, samp), resample_chroma(v, w, h, samp)
+            pk, off, sz = pack([jpeg_encode_simple(o, y[i], U[i], V[i], samp, restart=restart).tobytes() for i in range(n)])
+            dy, du, dv, got, _ = ref.decode_frames(pk, off, sz, w, h, mjpeg=True, chroma=(U.shape[2], U.shape[1]))
+            assert (got != 0).all()
+            key = "%s_%dx%d_dx%s" % (kind, w, h, tag)
+            names.append(key)
+            for nm, a in (("pk", pk), ("off", off), ("sz", sz), ("dy", dy), ("du", du), ("dv", dv)):
+                out["%s/%s" % (key, nm)] = a
     out["cases"] = np.frombuffer("\n".join(names).encode(), np.uint8)
     path = os.path.join(HERE, "mjpeg_golden.npz")
     np.savez_compressed(path, **out)

@@ -546,10 +546,11 @@ def mjpeg_with_dqt(pkts, off, size, seed):
     return out
 
 
-def jpeg_encode_simple(oracle, y, u, v, sampling, q=(16, 24)):
+def jpeg_encode_simple(oracle, y, u, v, sampling, q=(16, 24), restart=0):
     """A minimal baseline JPEG writer (test input only; what it means is defined by the reference DECODER):
     sampling = ((hY, vY), (hC, vC)); flat quantisers q[0] (component 0) / q[1] (components 1, 2), standard Huffman
-    tables, float DCT.  y is [h, w]; u, v are the chroma planes at the size the sampling implies."""
+    tables, float DCT; restart = MCUs per restart interval (DRI + RSTn markers), 0 for none.
+    y is [h, w]; u, v are the chroma planes at the size the sampling implies."""
     from scipy.fft import dctn
     (hy, vy), (hc, vc) = sampling
     h, w = y.shape
@@ -572,8 +573,14 @@ def jpeg_encode_simple(oracle, y, u, v, sampling, q=(16, 24)):
     planes = [pad(y, mbh * 8 * vy, mbw * 8 * hy), pad(u, mbh * 8 * vc, mbw * 8 * hc), pad(v, mbh * 8 * vc, mbw * 8 * hc)]
     fac = [(hy, vy), (hc, vc), (hc, vc)]
     pred = [0, 0, 0]
+    nmcu, rst = 0, 0
     for my in range(mbh):
         for mx in range(mbw):
+            if restart and nmcu and nmcu % restart == 0:
+                bits.append(("rst", rst))            # pad to a byte with ones, FF D0+n, predictors start over
+                rst = (rst + 1) & 7
+                pred = [0, 0, 0]
+            nmcu += 1
             for c in range(3):
                 hh, vv = fac[c]
                 for b in range(hh * vv):
@@ -604,6 +611,15 @@ def jpeg_encode_simple(oracle, y, u, v, sampling, q=(16, 24)):
                         put(huff[2 + tq][1][0], int(huff[2 + tq][0][0]))
     acc, nacc, scan = 0, 0, bytearray()
     for val, n in bits:
+        if val == "rst":
+            if nacc:
+                byte = ((acc << (8 - nacc)) | ((1 << (8 - nacc)) - 1)) & 0xFF
+                scan.append(byte)
+                if byte == 0xFF:
+                    scan.append(0)
+            acc, nacc = 0, 0
+            scan += bytes([0xFF, 0xD0 + n])
+            continue
         acc = (acc << n) | val
         nacc += n
         while nacc >= 8:
@@ -629,6 +645,8 @@ def jpeg_encode_simple(oracle, y, u, v, sampling, q=(16, 24)):
     out += b"\xff\xc4" + (2 + len(dht)).to_bytes(2, "big") + dht
     out += b"\xff\xc0" + (17).to_bytes(2, "big") + bytes([8]) + h.to_bytes(2, "big") + w.to_bytes(2, "big") + bytes([3])
     out += bytes([1, (hy << 4) | vy, 0, 2, (hc << 4) | vc, 1, 3, (hc << 4) | vc, 1])
+    if restart:
+        out += b"\xff\xdd" + (4).to_bytes(2, "big") + int(restart).to_bytes(2, "big")
     out += b"\xff\xda" + (12).to_bytes(2, "big") + bytes([3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0])
     out += scan + b"\xff\xd9"
     return np.frombuffer(bytes(out), np.uint8)

@@ -377,3 +377,24 @@ def test_mjpeg_other_samplings_identical(oracle, ref, w, h, kind, samp):
     for a, b, m in zip((oy, ou, ov), (ry, ru, rv), masks):
         assert np.array_equal(a[m == 0], b[m == 0])
     assert np.abs(ry.astype(int) - y).mean() < 8            # and it is the picture that went in
+
+
+@pytest.mark.parametrize("restart", [1, 3, 7, 2000])
+@pytest.mark.parametrize("samp", [((2, 2), (1, 1)), ((2, 1), (1, 1))])
+def test_mjpeg_restart_intervals_identical(oracle, ref, samp, restart):
+    """DRI + RSTn markers (a minimal JPEG writer makes the frames): byte alignment, marker skip and predictor reset
+    as mjpeg_decode_scan does them, including its "interval < 1350" condition (2000: the markers are never honoured,
+    reference and oracle decode the same garbage-free prefix and whatever follows, identically)"""
+    from oracle_lib import jpeg_encode_simple, pack, resample_chroma
+    for w, h, kind in ((64, 48, "sinus"), (102, 56, "noise")):
+        y, u, v = synth_frames(2, w, h, seed=37, kind=kind)
+        U, V = resample_chroma(u, w, h, samp), resample_chroma(v, w, h, samp)
+        pk, off, sz = pack([jpeg_encode_simple(oracle, y[i], U[i], V[i], samp, restart=restart).tobytes() for i in range(2)])
+        hd = oracle.mjpeg_header(pk[: int(sz[0])], chroma=True)
+        ry, ru, rv, got, _ = ref.decode_frames(pk, off, sz, w, h, mjpeg=True, chroma=(hd[3], hd[4]))
+        oy, ou, ov, st, masks = oracle.mjpeg_decode_frames(pk, off, sz, w, h, undef=True)
+        assert (got != 0).all()
+        if restart < 1350:
+            assert (st == 0).all() and np.abs(ry.astype(int) - y).mean() < 8
+        for a, b, m in zip((oy, ou, ov), (ry, ru, rv), masks):
+            assert np.array_equal(a[m == 0], b[m == 0])
