@@ -35,6 +35,7 @@ EXPORTS = [
     "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
     "amv_file_index", "amv_file_mux", "amv_decode_frames_sp5x",
     "amv_convert_range", "amv_mjpeg_configure", "amv_decode_frames_mjpeg",
+    "amv_scale_frames", "amv_audio_resample", "amv_audio_resample_count", "amv_scale_banks", "amv_audio_resample_bank",
 ]
 
 
@@ -99,6 +100,12 @@ def load_library(path=LIB_PATH):
     lib.amv_decode_frames_mjpeg.argtypes = lib.amv_decode_frames.argtypes
     lib.amv_mjpeg_configure.argtypes = [vp, vp, C.c_uint32, vp, vp]
     lib.amv_convert_range.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32]
+    lib.amv_scale_frames.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32]
+    lib.amv_audio_resample.argtypes = [vp, vp, u64, i32, i32, i32, vp, u64, vp, i32]
+    lib.amv_audio_resample_count.argtypes = [u64, i32, i32]
+    lib.amv_audio_resample_count.restype = u64
+    lib.amv_scale_banks.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.amv_audio_resample_bank.argtypes = [i32, i32, vp, u64]
     lib.amv_decode_frames_bgr24.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, vp, i32, u64, vp, i32]
     lib.amv_file_index.argtypes = [vp, u64, C.POINTER(FileInfo), vp, vp, vp, vp, u32]
     lib.amv_file_mux.argtypes = [C.POINTER(MuxParams), i32, vp, vp, vp, vp, vp, vp, vp, u64]
@@ -137,6 +144,28 @@ def offsets_of(sizes):
     if len(sizes) > 1:
         off[1:] = np.cumsum(sizes)[:-1]
     return off
+
+
+def scale_banks(iw, ih, ow, oh, lib=None):
+    """(h_bank[16,4], v_bank[16,4], h_incr, v_incr) the scaler runs on (host-side filter design, no device)"""
+    lib = lib or load_library()
+    hb, vb = np.zeros((16, 4), np.int16), np.zeros((16, 4), np.int16)
+    hi, vi = C.c_int32(0), C.c_int32(0)
+    r = lib.amv_scale_banks(iw, ih, ow, oh, hb.ctypes.data, vb.ctypes.data, C.addressof(hi), C.addressof(vi))
+    if r < 0:
+        raise AmvError("amv_scale_banks: %d" % r)
+    return hb, vb, hi.value, vi.value
+
+
+def audio_resample_bank(in_rate, out_rate=22050, lib=None):
+    """the [1024, filter_length] polyphase bank of the audio resampler (host-side filter design, no device)"""
+    lib = lib or load_library()
+    n = lib.amv_audio_resample_bank(in_rate, out_rate, None, 0)
+    if n < 0:
+        raise AmvError("amv_audio_resample_bank: %d" % n)
+    bank = np.zeros((1024, n), np.int16)
+    lib.amv_audio_resample_bank(in_rate, out_rate, bank.ctypes.data, bank.size)
+    return bank
 
 
 def file_index(data, lib=None):
@@ -243,6 +272,42 @@ class AmvCuda:
         oy, ou, ov = np.zeros_like(y), np.zeros_like(u), np.zeros_like(v)
         self.convert_range_raw(y, u, v, w, cw, w * h, cw * ch, n, w, h, direction, oy, ou, ov, w, cw, w * h, cw * ch, MEM_HOST)
         return oy, ou, ov
+
+    def scale_frames_raw(self, y, u, v, ls_y, ls_c, fs_y, fs_c, n, iw, ih, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, ow, oh, mem):
+        self._ck(self.lib.amv_scale_frames(self.ctx, _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, n, iw, ih,
+                                           _ptr(oy), _ptr(ou), _ptr(ov), ols_y, ols_c, ofs_y, ofs_c, ow, oh, mem))
+
+    def scale_frames(self, y, u, v, ow, oh, fill=0):
+        """numpy planes [n,ih,iw] / [n,ich,icw] -> [n,oh,ow] / [n,och,ocw] as the reference's img_resample scales them
+        (chroma at sizes >> 1; output bytes the reference does not write keep `fill`)"""
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        n, ih, iw = y.shape
+        icw, ich = chroma_dims(iw, ih)
+        ocw, och = chroma_dims(ow, oh)
+        oy = np.full((n, oh, ow), fill, np.uint8)
+        ou = np.full((n, och, ocw), fill, np.uint8)
+        ov = np.full((n, och, ocw), fill, np.uint8)
+        self.scale_frames_raw(y, u, v, iw, icw, iw * ih, icw * ich, n, iw, ih, oy, ou, ov, ow, ocw, ow * oh, ocw * och, ow, oh,
+                              MEM_HOST)
+        return oy, ou, ov
+
+    def audio_resample_count(self, n_in, in_rate, out_rate=22050):
+        return int(self.lib.amv_audio_resample_count(int(n_in), int(in_rate), int(out_rate)))
+
+    def audio_resample_raw(self, pcm, n_in, in_channels, in_rate, out_rate, out, out_cap, mem):
+        k = C.c_uint64(0)
+        self._ck(self.lib.amv_audio_resample(self.ctx, _ptr(pcm), int(n_in), int(in_channels), int(in_rate), int(out_rate),
+                                             _ptr(out), int(out_cap), C.addressof(k), mem))
+        return int(k.value)
+
+    def audio_resample(self, pcm, in_channels, in_rate, out_rate=22050):
+        """interleaved int16 samples -> mono int16 at out_rate, as the reference's audio_resample produces over the stream"""
+        pcm = np.ascontiguousarray(pcm, np.int16).reshape(-1)
+        n_in = pcm.size // in_channels
+        cap = self.audio_resample_count(n_in, in_rate, out_rate)
+        out = np.zeros(max(cap, 1), np.int16)
+        k = self.audio_resample_raw(pcm, n_in, in_channels, in_rate, out_rate, out, cap, MEM_HOST)
+        return out[:k]
 
     def decode_frames_bgr24_raw(self, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, bgr, line_bytes, frame_stride, status, mem):
         self._ck(self.lib.amv_decode_frames_bgr24(self.ctx, _ptr(pkts), pkts_bytes, _ptr(pkt_off), _ptr(pkt_size), n, w, h,

@@ -26,6 +26,7 @@ enum WsId {
     WS_SLOT_OFF, WS_SCAN_LEN, WS_STATUS, WS_STARTS, WS_SCRATCH, WS_SLOTS, WS_CARRY, WS_ROUNDS, WS_TOKENS, WS_BLKOFF, WS_QTAB, WS_REDO,
     // device mirrors of host arguments (AMV_MEM_HOST calls)
     WS_H_A, WS_H_B, WS_H_C, WS_H_D, WS_H_E, WS_H_F, WS_H_G, WS_H_H, WS_H_I,
+    WS_RS_BANK,     // the audio resampler's polyphase bank
     WS_COUNT
 };
 
@@ -66,6 +67,7 @@ struct amv_ctx {
     int mj_samp[4] = { 1, 1, 0, 0 };    // log2 sampling of the configured header: luma h, v; chroma h, v
     uint32_t mj_qpos[2] = { 0, 0 };     // where the 64 quantisers of component 0 / components 1, 2 sit in a frame
     int mj_w = 0, mj_h = 0;
+    int rs_in_rate = 0, rs_out_rate = 0; // rate pair WS_RS_BANK was built for
     bool mj_sync_ok = false;            // the lane-synchronisation table could be built (else one lane per frame)
 };
 
@@ -940,6 +942,137 @@ AMV_API int amv_convert_range(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, 
     if ((r = copy_planes(ctx, d_u, ou, cw, ch, ols_c, ofs_c, n, true)) != AMV_OK) return r;
     if ((r = copy_planes(ctx, d_v, ov, cw, ch, ols_c, ofs_c, n, true)) != AMV_OK) return r;
     CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+// ------------------------------------------------------------------------------- picture scaler
+AMV_API int amv_scale_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
+                             uint64_t fs_y, uint64_t fs_c, int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov,
+                             int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int ow, int oh, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (n < 0 || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0 || iw > 16384 || ih > 16384 || ow > 16384 || oh > 16384 || bad_mem(mem))
+        return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
+    if (n == 0) return AMV_OK;
+    if (!y || !u || !v || !oy || !ou || !ov) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    // the reference scales planes 1 and 2 at (w >> 1) x (h >> 1) (imgresample.c:494-505)
+    const int icw = iw >> 1, ich = ih >> 1, ocw = ow >> 1, och = oh >> 1;
+    if (ocw > 0 && och > 0 && (icw == 0 || ich == 0))
+        return fail(ctx, AMV_ERR_UNSUPPORTED, "a 1-pixel-wide or -high source has no chroma to scale (the reference reads outside the plane)");
+    if (ls_y < iw || ls_c < icw || ols_y < ow || ols_c < ocw || fs_y < (uint64_t)ls_y * (ih - 1) + iw ||
+        (ich > 0 && fs_c < (uint64_t)ls_c * (ich - 1) + icw) || ofs_y < (uint64_t)ols_y * (oh - 1) + ow ||
+        (och > 0 && ofs_c < (uint64_t)ols_c * (och - 1) + ocw))
+        return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
+    ScaleBanks banks;
+    build_scale_banks(iw, ih, ow, oh, &banks);
+    CK(cudaSetDevice(ctx->device));
+    if (mem == AMV_MEM_DEVICE) {
+        const int k = launch_scale_frames(y, u, v, ls_y, ls_c, fs_y, fs_c, n, iw, ih, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, ow, oh,
+                                          banks, ctx->stream);
+        return check_launch(ctx, "scaler kernels", k);
+    }
+    // host buffers: tight device copies in, kernels, tight copies out (only the bytes the reference writes)
+    const uint64_t ty = (uint64_t)iw * ih, tc = (uint64_t)icw * ich, oty = (uint64_t)ow * oh, otc = (uint64_t)ocw * och;
+    uint8_t *d_y, *d_u, *d_v, *d_oy, *d_ou, *d_ov;
+    ENSURE(WS_H_A, ty * n, d_y);
+    ENSURE(WS_H_B, tc * n + 1, d_u);
+    ENSURE(WS_H_C, tc * n + 1, d_v);
+    ENSURE(WS_H_D, oty * n, d_oy);
+    ENSURE(WS_H_E, otc * n + 4, d_ou);
+    ENSURE(WS_H_F, otc * n + 4, d_ov);
+    int r;
+    const bool chroma = icw > 0 && ich > 0 && ocw > 0 && och > 0;
+    if ((r = copy_planes(ctx, d_y, const_cast<uint8_t *>(y), iw, ih, ls_y, fs_y, n, false)) != AMV_OK) return r;
+    if (chroma) {
+        if ((r = copy_planes(ctx, d_u, const_cast<uint8_t *>(u), icw, ich, ls_c, fs_c, n, false)) != AMV_OK) return r;
+        if ((r = copy_planes(ctx, d_v, const_cast<uint8_t *>(v), icw, ich, ls_c, fs_c, n, false)) != AMV_OK) return r;
+    }
+    const int k = launch_scale_frames(d_y, d_u, d_v, iw, icw, ty, tc, n, iw, ih, d_oy, d_ou, d_ov, ow, ocw, oty, otc, ow, oh, banks,
+                                      ctx->stream);
+    if ((r = check_launch(ctx, "scaler kernels", k)) != AMV_OK) return r;
+    if ((r = copy_planes(ctx, d_oy, oy, ow, oh, ols_y, ofs_y, n, true)) != AMV_OK) return r;
+    if (chroma) {
+        if ((r = copy_planes(ctx, d_ou, ou, ocw, och, ols_c, ofs_c, n, true)) != AMV_OK) return r;
+        if ((r = copy_planes(ctx, d_ov, ov, ocw, och, ols_c, ofs_c, n, true)) != AMV_OK) return r;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMV_OK;
+}
+
+// the filter banks both stages run on, as the host builds them (init-time work, no device involved)
+AMV_API int amv_scale_banks(int iw, int ih, int ow, int oh, int16_t *h_bank, int16_t *v_bank, int32_t *h_incr, int32_t *v_incr) {
+    if (iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0 || iw > 16384 || ih > 16384 || ow > 16384 || oh > 16384 || !h_bank || !v_bank)
+        return AMV_ERR_ARG;
+    ScaleBanks b;
+    build_scale_banks(iw, ih, ow, oh, &b);
+    memcpy(h_bank, b.h, sizeof(b.h));
+    memcpy(v_bank, b.v, sizeof(b.v));
+    if (h_incr) *h_incr = b.h_incr;
+    if (v_incr) *v_incr = b.v_incr;
+    return AMV_OK;
+}
+AMV_API int amv_audio_resample_bank(int in_rate, int out_rate, int16_t *bank, uint64_t bank_cap) {
+    if (in_rate <= 0 || out_rate <= 0 || in_rate > (1 << 21) || out_rate > (1 << 21)) return AMV_ERR_ARG;
+    const int len = resample_filter_length(in_rate, out_rate);
+    if (len > 4096) return AMV_ERR_UNSUPPORTED;
+    if (bank) {
+        if (bank_cap < (uint64_t)len * 1024) return AMV_ERR_ARG;
+        build_resample_bank(in_rate, out_rate, bank);
+    }
+    return len;
+}
+
+// ------------------------------------------------------------------------------- audio resampler
+AMV_API uint64_t amv_audio_resample_count(uint64_t n_in, int in_rate, int out_rate) {
+    if (in_rate <= 0 || out_rate <= 0 || n_in == 0 || n_in > (1ull << 40)) return 0;
+    return (uint64_t)resample_output_count((int64_t)n_in, in_rate, out_rate);
+}
+
+AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, int in_channels, int in_rate, int out_rate,
+                               int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem) {
+    if (!ctx) return AMV_ERR_ARG;
+    if (bad_mem(mem) || (in_channels != 1 && in_channels != 2) || in_rate <= 0 || out_rate <= 0 || in_rate > (1 << 21) ||
+        out_rate > (1 << 21) || n_in > (1ull << 40))
+        return fail(ctx, AMV_ERR_ARG, "bad mem / channels / rates / length");
+    if (!n_out) return fail(ctx, AMV_ERR_ARG, "null n_out");
+    *n_out = 0;
+    if (n_in == 0) return AMV_OK;
+    if (!in || !out) return fail(ctx, AMV_ERR_ARG, "null buffer");
+    const int len = resample_filter_length(in_rate, out_rate);
+    if (len > 4096) return fail(ctx, AMV_ERR_UNSUPPORTED, "rate ratio needs more than 4096 filter taps");
+    const int64_t k = resample_output_count((int64_t)n_in, in_rate, out_rate);
+    if ((uint64_t)k > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap smaller than the resampled stream (see amv_audio_resample_count)");
+    if (mem == AMV_MEM_DEVICE && (((uintptr_t)in & (in_channels == 2 ? 3 : 1)) || ((uintptr_t)out & 1)))
+        return fail(ctx, AMV_ERR_ARG, "misaligned sample pointer");
+    CK(cudaSetDevice(ctx->device));
+    // the polyphase bank of this rate pair (kept until the rates change)
+    if (ctx->rs_in_rate != in_rate || ctx->rs_out_rate != out_rate) {
+        std::vector<int16_t> bank((size_t)len * 1024);
+        build_resample_bank(in_rate, out_rate, bank.data());
+        void *p = nullptr;
+        int r = ensure(ctx, WS_RS_BANK, bank.size() * sizeof(int16_t), &p);
+        if (r != AMV_OK) return r;
+        ctx->rs_in_rate = ctx->rs_out_rate = 0;
+        CK(cudaMemcpyAsync(p, bank.data(), bank.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->rs_in_rate = in_rate; ctx->rs_out_rate = out_rate;
+    }
+    const int16_t *d_bank = reinterpret_cast<const int16_t *>(ctx->ws[WS_RS_BANK].p);
+    if (mem == AMV_MEM_DEVICE) {
+        launch_audio_resample(in, (int64_t)n_in, in_channels, d_bank, len, in_rate, out_rate, out, k, ctx->stream);
+        *n_out = (uint64_t)k;
+        return k > 0 ? check_launch(ctx, "audio resampler kernel", 1) : AMV_OK;
+    }
+    int16_t *d_in, *d_out;
+    TO_DEVICE(WS_H_A, in, sizeof(int16_t) * n_in * in_channels, d_in);
+    ENSURE(WS_H_B, sizeof(int16_t) * (k > 0 ? k : 1), d_out);
+    if (k > 0) {
+        launch_audio_resample(d_in, (int64_t)n_in, in_channels, d_bank, len, in_rate, out_rate, d_out, k, ctx->stream);
+        int r = check_launch(ctx, "audio resampler kernel", 1);
+        if (r != AMV_OK) return r;
+        CK(cudaMemcpyAsync(out, d_out, sizeof(int16_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_out = (uint64_t)k;
     return AMV_OK;
 }
 

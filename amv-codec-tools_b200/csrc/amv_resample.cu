@@ -1,0 +1,225 @@
+// amv_resample.cu -- the two resampling stages ffmpeg.c runs in front of the AMV encoders:
+//   * the picture scaler of `-s WxH`: sws_scale of the fork's libavcodec emulation (imgresample.c:515-690) ->
+//     img_resample_init / img_resample (:433-507) -> component_resample (:362-431), h_resample (:289-360),
+//     v_resample (:119-153): separable 4-tap / 16-phase filter in 16.16 source positions, 8-bit coefficients,
+//     the horizontal result clamped to a byte before the vertical pass, edges repeated;
+//   * the audio resampler of do_audio_out (ffmpeg.c:501-505): audio_resample (resample.c:131-235; two channels
+//     averaged to one, :53-75) -> av_resample (resample2.c:234-323): filter_length taps of a 1024-phase bank,
+//     32-bit accumulator, >> 15 with rounding, saturation.
+// Both banks come from av_build_filter (resample2.c:93-141), double arithmetic rounded through lrintf: built on
+// the host (build_scale_banks / build_resample_bank below, operand order as in the reference so the
+// coefficients are bit-identical) and handed to the kernels as data.
+// Every output pixel / sample depends only on the input: one thread per 4 output pixels resp. per output sample,
+// HBM-bound work (the taps of neighbouring outputs overlap and come from L1 / L2).
+#include <cmath>
+#include <vector>
+#include "amv_common.cuh"
+#include "amv_kernels.h"
+
+namespace amv {
+
+// ------------------------------------------------------------------------------------------ banks (host)
+namespace {
+double bessel_i0(double x) {
+    double v = 1, t = 1;
+    x = x * x / 4;
+    for (int i = 1; i < 50; i++) { t *= x / (i * i); v += t; }
+    return v;
+}
+// type 0: cubic, first derivative -0.5 (the scaler); type >= 2: Kaiser-windowed sinc with beta = type (audio: 9)
+void build_bank(int16_t *bank, double factor, int taps, int phases, int scale, int type) {
+    const int center = (taps - 1) / 2;
+    std::vector<double> tab((size_t)taps);
+    if (factor > 1.0) factor = 1.0;
+    for (int ph = 0; ph < phases; ph++) {
+        double norm = 0;
+        for (int i = 0; i < taps; i++) {
+            double x = M_PI * ((double)(i - center) - (double)ph / phases) * factor, y, w;
+            if (type == 0) {
+                const float d = -0.5;
+                x = fabs(((double)(i - center) - (double)ph / phases) * factor);
+                if (x < 1.0) y = 1 - 3 * x * x + 2 * x * x * x + d * (-x * x + x * x * x);
+                else         y = d * (-4 + 8 * x - 5 * x * x + x * x * x);
+            } else {
+                y = x == 0 ? 1.0 : sin(x) / x;
+                w = 2.0 * x / (factor * taps * M_PI);
+                y *= bessel_i0(type * sqrt(1 - w * w > 0 ? 1 - w * w : 0));
+            }
+            tab[(size_t)i] = y;
+            norm += y;
+        }
+        for (int i = 0; i < taps; i++) {
+            const long c = lrintf((float)(tab[(size_t)i] * scale / norm));
+            bank[ph * taps + i] = (int16_t)(c < -32768 ? -32768 : c > 32767 ? 32767 : c);
+        }
+    }
+}
+}  // namespace
+
+void build_scale_banks(int iw, int ih, int ow, int oh, ScaleBanks *b) {
+    build_bank(b->h, (float)ow / (float)iw, 4, 16, 256, 0);
+    build_bank(b->v, (float)oh / (float)ih, 4, 16, 256, 0);
+    b->h_incr = (int)(((int64_t)iw * 65536) / ow);
+    b->v_incr = (int)(((int64_t)ih * 65536) / oh);
+}
+
+int resample_filter_length(int in_rate, int out_rate) {
+    double factor = out_rate * 0.8 / in_rate;
+    if (factor > 1.0) factor = 1.0;
+    const int len = (int)ceil(16 / factor);
+    return len < 1 ? 1 : len;
+}
+void build_resample_bank(int in_rate, int out_rate, int16_t *bank) {
+    double factor = out_rate * 0.8 / in_rate;
+    if (factor > 1.0) factor = 1.0;
+    build_bank(bank, factor, resample_filter_length(in_rate, out_rate), 1024, 1 << 15, 9);
+}
+// outputs the reference produces from n_in samples: first(k) = (index0 + floor(k * in_rate * 1024 / out_rate)) >> 10; every k
+// whose taps start left of sample 0 (they mirror, no end check, resample2.c:256-258), then every k with
+// first(k) + len <= n_in (:259-260)
+int64_t resample_output_count(int64_t n_in, int in_rate, int out_rate) {
+    const int len = resample_filter_length(in_rate, out_rate);
+    const int64_t index0 = -1024 * (int64_t)((len - 1) / 2);
+    if (n_in <= 0) return 0;
+    const __int128 D = (__int128)in_rate * 1024, S = out_rate;
+    const int64_t mirrored = (int64_t)(((__int128)(-index0) * S + D - 1) / D);      // k with floor(k*D/S) < -index0
+    // largest index with (index >> 10) + len <= n_in is ((n_in - len + 1) << 10) - 1
+    const int64_t lim = ((n_in - len + 1) * 1024) - 1 - index0;      // floor(k*D/S) <= lim
+    if (lim < 0) return mirrored;
+    int64_t k = (int64_t)((((__int128)lim + 1) * S - 1) / D);         // largest k with k*D < (lim+1)*S
+    while ((int64_t)(((__int128)(k + 1) * D) / S) <= lim) k++;
+    while (k >= 0 && (int64_t)(((__int128)k * D) / S) > lim) k--;
+    return k + 1 > mirrored ? k + 1 : mirrored;
+}
+
+// ------------------------------------------------------------------------------------------ picture scaler
+struct ScaleArgs {
+    const uint8_t *src; uint8_t *dst;
+    int iw, ih, ow, oh, ils, ols;
+    uint64_t ifs, ofs;
+    int n, h_incr, v_incr;
+};
+
+__device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }
+
+// one thread: 4 neighbouring output pixels of one row (VEC: one 32-bit store)
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_scale_plane(ScaleArgs a, ScaleBanks banks) {
+    __shared__ int2 s_h[16], s_v[16];               // a phase's 4 coefficients as two packed pairs
+    if (threadIdx.x < 16) {
+        const int16_t *h = banks.h + 4 * threadIdx.x, *v = banks.v + 4 * threadIdx.x;
+        s_h[threadIdx.x] = make_int2((uint16_t)h[0] | ((int)h[1] << 16), (uint16_t)h[2] | ((int)h[3] << 16));
+        s_v[threadIdx.x] = make_int2((uint16_t)v[0] | ((int)v[1] << 16), (uint16_t)v[2] | ((int)v[3] << 16));
+    }
+    __syncthreads();
+    const int units = (a.ow + 3) >> 2;
+    const int64_t total = (int64_t)units * a.oh * a.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ux = (int)(i % units);
+        const int64_t ry = i / units;
+        const int y = (int)(ry % a.oh), f = (int)(ry / a.oh);
+        const uint8_t *in = a.src + (uint64_t)f * a.ifs;
+        const int sy = 2 * 65536 + y * a.v_incr, bottom = sy >> 16;
+        const int2 fv = s_v[(sy >> 12) & 15];
+        const int fv0 = (int16_t)fv.x, fv1 = fv.x >> 16, fv2 = (int16_t)fv.y, fv3 = fv.y >> 16;
+        const uint8_t *r0 = in + (int64_t)a.ils * min(max(bottom - 3, 0), a.ih - 1);
+        const uint8_t *r1 = in + (int64_t)a.ils * min(max(bottom - 2, 0), a.ih - 1);
+        const uint8_t *r2 = in + (int64_t)a.ils * min(max(bottom - 1, 0), a.ih - 1);
+        const uint8_t *r3 = in + (int64_t)a.ils * min(max(bottom, 0), a.ih - 1);
+        uint32_t word = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int x = ux * 4 + p;
+            const int sx = -65536 + x * a.h_incr, left = sx >> 16;
+            const int2 fh = s_h[(sx >> 12) & 15];
+            const int h0 = (int16_t)fh.x, h1 = fh.x >> 16, h2 = (int16_t)fh.y, h3 = fh.y >> 16;
+            int c0, c1, c2, c3;
+            if (left >= 0 && left + 3 < a.iw) { c0 = left; c1 = left + 1; c2 = left + 2; c3 = left + 3; }
+            else {
+                c0 = min(max(left, 0), a.iw - 1); c1 = min(max(left + 1, 0), a.iw - 1);
+                c2 = min(max(left + 2, 0), a.iw - 1); c3 = min(max(left + 3, 0), a.iw - 1);
+            }
+            const int a0 = clip255((__ldg(r0 + c0) * h0 + __ldg(r0 + c1) * h1 + __ldg(r0 + c2) * h2 + __ldg(r0 + c3) * h3) >> 8);
+            const int a1 = clip255((__ldg(r1 + c0) * h0 + __ldg(r1 + c1) * h1 + __ldg(r1 + c2) * h2 + __ldg(r1 + c3) * h3) >> 8);
+            const int a2 = clip255((__ldg(r2 + c0) * h0 + __ldg(r2 + c1) * h1 + __ldg(r2 + c2) * h2 + __ldg(r2 + c3) * h3) >> 8);
+            const int a3 = clip255((__ldg(r3 + c0) * h0 + __ldg(r3 + c1) * h1 + __ldg(r3 + c2) * h2 + __ldg(r3 + c3) * h3) >> 8);
+            const uint32_t px = (uint32_t)clip255((a0 * fv0 + a1 * fv1 + a2 * fv2 + a3 * fv3) >> 8);
+            if (VEC) word |= px << (8 * p);
+            else if (x < a.ow) a.dst[(uint64_t)f * a.ofs + (int64_t)y * a.ols + x] = (uint8_t)px;
+        }
+        if (VEC) *reinterpret_cast<uint32_t *>(a.dst + (uint64_t)f * a.ofs + (int64_t)y * a.ols + ux * 4) = word;
+    }
+}
+
+static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih, int ow, int oh, int ils, int ols, uint64_t ifs,
+                               uint64_t ofs, int n, const ScaleBanks &b, cudaStream_t s) {
+    if (iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return;       // a 1-pixel-wide picture has no chroma to scale
+    ScaleArgs a{ src, dst, iw, ih, ow, oh, ils, ols, ifs, ofs, n, b.h_incr, b.v_incr };
+    const bool vec = (ow & 3) == 0 && ((((uintptr_t)dst | (uintptr_t)ols | ofs) & 3) == 0);
+    const int64_t total = (int64_t)((ow + 3) >> 2) * oh * n;
+    int64_t grid = (total + 255) / 256;
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    if (grid < 1) grid = 1;
+    if (vec) k_scale_plane<true><<<(unsigned)grid, 256, 0, s>>>(a, b);
+    else     k_scale_plane<false><<<(unsigned)grid, 256, 0, s>>>(a, b);
+}
+
+int launch_scale_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                        int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov, int ols_y, int ols_c, uint64_t ofs_y,
+                        uint64_t ofs_c, int ow, int oh, const ScaleBanks &b, cudaStream_t s) {
+    int launches = 1;
+    launch_scale_plane(y, oy, iw, ih, ow, oh, ls_y, ols_y, fs_y, ofs_y, n, b, s);
+    if ((iw >> 1) > 0 && (ih >> 1) > 0 && (ow >> 1) > 0 && (oh >> 1) > 0) {
+        launch_scale_plane(u, ou, iw >> 1, ih >> 1, ow >> 1, oh >> 1, ls_c, ols_c, fs_c, ofs_c, n, b, s);
+        launch_scale_plane(v, ov, iw >> 1, ih >> 1, ow >> 1, oh >> 1, ls_c, ols_c, fs_c, ofs_c, n, b, s);
+        launches += 2;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------ audio resampler
+template <int CH>
+__device__ __forceinline__ int mono_at(const int16_t *in, int64_t i) {
+    if (CH == 1) return __ldg(in + i);
+    const uint32_t lr = __ldg(reinterpret_cast<const uint32_t *>(in) + i);      // interleaved pair, 4-byte aligned
+    return (int)(int16_t)(((int)(int16_t)(lr & 0xffff) + ((int)lr >> 16)) >> 1);
+}
+
+// one thread per output sample k; index(k) = index0 + floor(k * in_rate * 1024 / out_rate)
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_audio_resample(const int16_t *__restrict__ in, int64_t n_in, const int16_t *__restrict__ bank, int len, int64_t index0,
+                 uint64_t dst_incr /* in_rate * 1024 */, uint32_t src_incr /* out_rate */, int16_t *__restrict__ out, int64_t n_out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_out; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t index = index0 + (int64_t)(((uint64_t)k * dst_incr) / src_incr);
+        const int64_t first = index >> 10;
+        const int16_t *f = bank + (size_t)len * (size_t)(index & 1023);
+        uint32_t acc = 0;
+        if (first >= 0) {
+            for (int i = 0; i < len; i++) acc += (uint32_t)(mono_at<CH>(in, first + i) * (int)__ldg(f + i));
+        } else {
+            for (int i = 0; i < len; i++) {                       // left of sample 0 the reference mirrors: src[|i| % src_size]
+                int64_t p = first + i;
+                if (p < 0) p = -p;
+                acc += (uint32_t)(mono_at<CH>(in, p % n_in) * (int)__ldg(f + i));
+            }
+        }
+        const int val = ((int)(acc + (1u << 14))) >> 15;
+        out[k] = (int16_t)max(-32768, min(32767, val));
+    }
+}
+
+void launch_audio_resample(const int16_t *in, int64_t n_in, int in_ch, const int16_t *bank, int len, int in_rate, int out_rate,
+                           int16_t *out, int64_t n_out, cudaStream_t s) {
+    if (n_out <= 0) return;
+    const int64_t index0 = -1024 * (int64_t)((len - 1) / 2);
+    int64_t grid = (n_out + 255) / 256;
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    if (in_ch == 2)
+        k_audio_resample<2><<<(unsigned)grid, 256, 0, s>>>(in, n_in, bank, len, index0, (uint64_t)in_rate * 1024, (uint32_t)out_rate, out, n_out);
+    else
+        k_audio_resample<1><<<(unsigned)grid, 256, 0, s>>>(in, n_in, bank, len, index0, (uint64_t)in_rate * 1024, (uint32_t)out_rate, out, n_out);
+}
+
+}  // namespace amv

@@ -219,6 +219,53 @@ AMV_API int amv_convert_range(amv_ctx *ctx,
                               int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int mem);
 
 /*
+ * The picture scaler the reference's ffmpeg.c runs in front of the encoder for `-s WxH`: sws_getContext /
+ * sws_scale of the fork's libavcodec emulation (libavcodec/imgresample.c:515-690), i.e.
+ * img_resample_init(ow, oh, iw, ih) + img_resample per frame (:433-507; component_resample :362-431,
+ * h_resample :289-360, v_resample :119-153; banks from av_build_filter, resample2.c:93-141).
+ * Input planes / strides as in amv_decode_frames for an iw x ih picture, output planes likewise for
+ * ow x oh.  As in the reference the chroma planes are scaled at (iw>>1) x (ih>>1) -> (ow>>1) x (oh>>1)
+ * with the luma step sizes; bytes outside that area are neither read nor written.
+ */
+AMV_API int amv_scale_frames(amv_ctx *ctx,
+                             const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                             int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                             int n, int iw, int ih,
+                             uint8_t *oy, uint8_t *ou, uint8_t *ov,
+                             int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c,
+                             int ow, int oh, int mem);
+
+/*
+ * The audio resampler of the reference's do_audio_out (ffmpeg.c:501-505) in front of the ADPCM encoder
+ * (which takes 22050 Hz mono only, adpcm.c:190-199): audio_resample_init(1, in_channels, out_rate, in_rate)
+ * + audio_resample (libavcodec/resample.c:93-235; two channels are averaged, :53-75) -> av_resample
+ * (resample2.c:234-323; 16-tap / cutoff 0.8 / 1024-phase Kaiser bank of av_resample_init :185-206).
+ *   in        n_in samples per channel, interleaved int16 (4-byte aligned for 2 channels)
+ *   out       mono int16, out_cap samples; *n_out receives the count written
+ * The result is the concatenation of what the reference returns when the stream is fed to
+ * audio_resample in calls of any size >= the filter length (it carries the unconsumed tail from call to
+ * call and never flushes it): amv_audio_resample_count(n_in, in_rate, out_rate) samples, all those whose
+ * taps lie inside the stream.  Index arithmetic is 64-bit (the reference's int index restarts per call).
+ */
+AMV_API uint64_t amv_audio_resample_count(uint64_t n_in, int in_rate, int out_rate);
+AMV_API int amv_audio_resample(amv_ctx *ctx,
+                               const int16_t *in, uint64_t n_in, int in_channels,
+                               int in_rate, int out_rate,
+                               int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem);
+
+/*
+ * The filter banks the two stages above run on, as built on the host at call time (no device involved):
+ * av_build_filter (resample2.c:93-141) with the arguments of img_resample_init (imgresample.c:476-479:
+ * 4 taps x 16 phases, scale 256, cubic; h_incr / v_incr :473-474) resp. av_resample_init
+ * (resample2.c:185-206: filter_length taps x 1024 phases, scale 1 << 15, Kaiser beta 9).
+ * amv_scale_banks fills 64 coefficients each; amv_audio_resample_bank returns filter_length (>= 1) and, when
+ * bank != NULL, fills filter_length * 1024 coefficients (bank_cap in coefficients).
+ */
+AMV_API int amv_scale_banks(int iw, int ih, int ow, int oh, int16_t *h_bank, int16_t *v_bank,
+                            int32_t *h_incr, int32_t *v_incr);
+AMV_API int amv_audio_resample_bank(int in_rate, int out_rate, int16_t *bank, uint64_t bank_cap);
+
+/*
  * Encode n YUVJ420P frames into AMV packets, byte-identical to amv_encoder.
  *   y,u,v, ls_*, fs_*        as above (source planes)
  *   qscale                   per-frame quantiser scale 2..31 (NULL = 2, the reference default;

@@ -20,6 +20,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define AMVO_API __attribute__((visibility("default")))
 
@@ -1290,4 +1291,160 @@ AMVO_API void amvo_convert_range(const uint8_t *y, const uint8_t *u, const uint8
 {
     for (size_t i = 0; i < ny; i++) oy[i] = range_y(y[i], dir);
     for (size_t i = 0; i < nc; i++) { ou[i] = range_c(u[i], dir); ov[i] = range_c(v[i], dir); }
+}
+
+/* ========================================================================== *
+ * Pre stages next to the codec (second part): the picture scaler and the audio resampler
+ * ffmpeg.c runs in front of the encoders.  Both stand on one polyphase bank builder.
+ * ========================================================================== */
+
+/* av_build_filter (resample2.c:93-141).  type 0: the cubic with first derivative -0.5 the scaler asks for
+ * (:108-113); type >= 2: Kaiser-windowed sinc, beta = type (:118-121, bessel :77-87).  Every phase is
+ * normalised to `scale` and rounded through lrintf, i.e. after a conversion to float (:131).  The floating
+ * point expressions keep the reference's operand order: the coefficients must come out bit-identical. */
+static double bessel_i0(double x)
+{
+    double v = 1, t = 1;
+    x = x * x / 4;
+    for (int i = 1; i < 50; i++) { t *= x / (i * i); v += t; }
+    return v;
+}
+static void build_bank(int16_t *bank, double factor, int taps, int phases, int scale, int type)
+{
+    const int center = (taps - 1) / 2;
+    double *tab = (double *)malloc(sizeof(double) * (size_t)taps);
+    if (factor > 1.0) factor = 1.0;
+    for (int ph = 0; ph < phases; ph++) {
+        double norm = 0;
+        for (int i = 0; i < taps; i++) {
+            double x = M_PI * ((double)(i - center) - (double)ph / phases) * factor, y, w;
+            if (type == 0) {
+                const float d = -0.5;
+                x = fabs(((double)(i - center) - (double)ph / phases) * factor);
+                if (x < 1.0) y = 1 - 3 * x * x + 2 * x * x * x + d * (-x * x + x * x * x);
+                else         y = d * (-4 + 8 * x - 5 * x * x + x * x * x);
+            } else {
+                y = x == 0 ? 1.0 : sin(x) / x;
+                w = 2.0 * x / (factor * taps * M_PI);
+                y *= bessel_i0(type * sqrt(1 - w * w > 0 ? 1 - w * w : 0));
+            }
+            tab[i] = y;
+            norm += y;
+        }
+        for (int i = 0; i < taps; i++) {
+            long c = lrintf(tab[i] * scale / norm);
+            bank[ph * taps + i] = (int16_t)(c < -32768 ? -32768 : c > 32767 ? 32767 : c);
+        }
+    }
+    free(tab);
+}
+
+/* ---- picture scaler: img_resample_init (imgresample.c:433-485: 4 taps, 16 phases, 8-bit coefficients,
+ * h_incr / v_incr in 16.16 from the LUMA sizes, cubic banks for factor (float)out/(float)in) and img_resample
+ * (:487-507: planes 1 and 2 at sizes >> 1) -> component_resample (:362-431).  Per output row the filter's
+ * bottom tap sits at source row (2*65536 + y*v_incr) >> 16, per output column the first tap at
+ * (-65536 + x*h_incr) >> 16; taps outside the plane repeat the edge (h_resample_slow :289-323, row clamp
+ * :381-386); the horizontal result is clamped and kept as a byte (the line buffer) before the vertical pass. */
+static void scale_plane(const uint8_t *in, int iw, int ih, int ils, uint8_t *out, int ow, int oh, int ols,
+                        int h_incr, int v_incr, const int16_t *hf, const int16_t *vf)
+{
+    for (int y = 0; y < oh; y++) {
+        const int sy = 2 * 65536 + y * v_incr, bottom = sy >> 16;
+        const int16_t *fv = vf + 4 * ((sy >> 12) & 15);
+        for (int x = 0; x < ow; x++) {
+            const int sx = -65536 + x * h_incr, left = sx >> 16;
+            const int16_t *fh = hf + 4 * ((sx >> 12) & 15);
+            int acc = 0;
+            for (int j = 0; j < 4; j++) {
+                const uint8_t *row = in + (size_t)ils * (size_t)clampi(bottom - 3 + j, 0, ih - 1);
+                int hs = 0;
+                for (int t = 0; t < 4; t++) hs += row[clampi(left + t, 0, iw - 1)] * fh[t];
+                acc += clip_u8(hs >> 8) * fv[j];
+            }
+            out[(size_t)ols * y + x] = clip_u8(acc >> 8);
+        }
+    }
+}
+/* tight planes [n][h][w], chroma stored (w+1)/2 x (h+1)/2; the reference writes (ow>>1) x (oh>>1) of them */
+AMVO_API int amvo_scale_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v, int n, int iw, int ih, int ow, int oh,
+                               uint8_t *oy, uint8_t *ou, uint8_t *ov)
+{
+    if (iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return -1;
+    int16_t hf[64], vf[64];
+    build_bank(hf, (float)ow / (float)iw, 4, 16, 256, 0);
+    build_bank(vf, (float)oh / (float)ih, 4, 16, 256, 0);
+    const int h_incr = (iw * 65536) / ow, v_incr = (ih * 65536) / oh;
+    const int icw = (iw + 1) >> 1, ich = (ih + 1) >> 1, ocw = (ow + 1) >> 1, och = (oh + 1) >> 1;
+    for (int i = 0; i < n; i++) {
+        scale_plane(y + (size_t)i * iw * ih, iw, ih, iw, oy + (size_t)i * ow * oh, ow, oh, ow, h_incr, v_incr, hf, vf);
+        scale_plane(u + (size_t)i * icw * ich, iw >> 1, ih >> 1, icw, ou + (size_t)i * ocw * och, ow >> 1, oh >> 1, ocw, h_incr, v_incr, hf, vf);
+        scale_plane(v + (size_t)i * icw * ich, iw >> 1, ih >> 1, icw, ov + (size_t)i * ocw * och, ow >> 1, oh >> 1, ocw, h_incr, v_incr, hf, vf);
+    }
+    return n;
+}
+AMVO_API void amvo_scale_banks(int iw, int ih, int ow, int oh, int16_t *hf, int16_t *vf)
+{
+    build_bank(hf, (float)ow / (float)iw, 4, 16, 256, 0);
+    build_bank(vf, (float)oh / (float)ih, 4, 16, 256, 0);
+}
+
+/* ---- audio resampler: audio_resample_init(1 output channel, in_ch, out_rate, in_rate) (resample.c:93-129:
+ * 16 taps, 1024 phases, not linear, cutoff 0.8) -> av_resample_init (resample2.c:185-206: filter_length =
+ * ceil(16 / min(out*0.8/in, 1)), Kaiser beta 9, coefficients scaled to 1 << 15, first output centred on sample
+ * 0: index = -1024 * ((len - 1) / 2)); audio_resample (resample.c:131-235): two input channels are averaged
+ * (stereo_to_mono :53-75, (l + r) >> 1) before av_resample (resample2.c:234-323).
+ * The reference walks `index` by in_rate*1024 / out_rate per output with the remainder kept in `frac`
+ * (:290-296), carries unconsumed samples from call to call (resample.c:214-216) and never flushes; over the
+ * whole stream output k therefore starts at index0 + floor(k * in_rate * 1024 / out_rate), which this
+ * restatement evaluates directly (64-bit), for any split of the stream into calls (calls of at least
+ * filter_length samples; the taps left of sample 0 mirror: src[|i| % src_size], :256-258).
+ * The sum is the reference's 32-bit accumulator (wrapping), rounded >> 15 and saturated (:274-275).
+ * Returns the samples written (all outputs whose taps lie inside the n_in samples), -1 if out_cap is short. */
+AMVO_API int amvo_resample_filter_length(int in_rate, int out_rate)
+{
+    double factor = out_rate * 0.8 / in_rate;
+    if (factor > 1.0) factor = 1.0;
+    int len = (int)ceil(16 / factor);
+    return len < 1 ? 1 : len;
+}
+AMVO_API int amvo_resample_bank(int in_rate, int out_rate, int16_t *bank /* len * 1024 */)
+{
+    double factor = out_rate * 0.8 / in_rate;
+    if (factor > 1.0) factor = 1.0;
+    const int len = amvo_resample_filter_length(in_rate, out_rate);
+    build_bank(bank, factor, len, 1024, 1 << 15, 9);
+    return len;
+}
+AMVO_API int64_t amvo_audio_resample(const int16_t *in, int64_t n_in, int in_ch, int in_rate, int out_rate,
+                                     int16_t *out, int64_t out_cap)
+{
+    if (n_in <= 0 || in_rate <= 0 || out_rate <= 0 || (in_ch != 1 && in_ch != 2)) return -1;
+    const int len = amvo_resample_filter_length(in_rate, out_rate);
+    int16_t *bank = (int16_t *)malloc(sizeof(int16_t) * (size_t)len * 1024);
+    int16_t *mono = (int16_t *)malloc(sizeof(int16_t) * (size_t)n_in);
+    amvo_resample_bank(in_rate, out_rate, bank);
+    for (int64_t i = 0; i < n_in; i++) mono[i] = in_ch == 2 ? (int16_t)((in[2 * i] + in[2 * i + 1]) >> 1) : in[i];
+    const int64_t index0 = -1024 * (int64_t)((len - 1) / 2);
+    int64_t k = 0;
+    for (;; k++) {
+        const int64_t index = index0 + (k * (int64_t)in_rate * 1024) / out_rate;
+        const int64_t first = index >> 10;
+        const int16_t *f = bank + (size_t)len * (size_t)(index & 1023);
+        uint32_t acc = 0;
+        if (first < 0) {
+            for (int i = 0; i < len; i++) {
+                int64_t a = first + i; if (a < 0) a = -a;
+                acc += (uint32_t)(mono[a % n_in] * f[i]);
+            }
+        } else if (first + len > n_in) {
+            break;
+        } else {
+            for (int i = 0; i < len; i++) acc += (uint32_t)(mono[first + i] * f[i]);
+        }
+        if (k >= out_cap) { k = -1; break; }
+        int32_t val = ((int32_t)(acc + (1u << 14))) >> 15;
+        out[k] = (int16_t)(val < -32768 ? -32768 : val > 32767 ? 32767 : val);
+    }
+    free(bank); free(mono);
+    return k;
 }

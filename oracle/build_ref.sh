@@ -66,12 +66,12 @@ mkdir -p "$OUT/cfg" "$OUT/obj"
 
 CFLAGS="-O3 -fPIC -std=gnu99 -fgnu89-inline -fcommon -fno-strict-aliasing -fwrapv -w \
  -DHAVE_AV_CONFIG_H -D_ISOC9X_SOURCE -D_GNU_SOURCE \
- -I$OUT/cfg -I$REF -I$REF/libavcodec -I$REF/libavutil"
+ -I$OUT/cfg -I$REF -I$REF/libavcodec -I$REF/libavutil -I$REF/libswscale"
 
 AVCODEC="utils opt imgconvert dsputil simple_idct jfdctint jfdctfst jrevdct faandct \
  mpegvideo mpegvideo_enc mpeg12data mjpeg mjpegenc mjpegdec sp5xdec adpcm bitstream \
  ratecontrol motion_est error_resilience eval h263 jpeglsdec jpegls golomb \
- parser raw"
+ parser raw imgresample resample resample2"
 AVUTIL="mem log rational mathematics integer intfloat_readwrite crc fifo string"
 # container layer: the AMV muxer, the AVI/AMV demuxer and what they stand on
 AVFORMAT="utils aviobuf avio riff amvenc avidec cutils"

@@ -278,3 +278,67 @@ int amvref_convert_range(const uint8_t *y, const uint8_t *u, const uint8_t *v, i
     }
     return n;
 }
+
+/* ---- pre stages next to the codec: the picture scaler ffmpeg.c reaches through sws_getContext /
+ * sws_scale (imgresample.c:515-690 -> img_resample_init / img_resample, :433-507) for `-s WxH`, and the audio
+ * resampler of do_audio_out (ffmpeg.c:501-505 -> audio_resample, resample.c:131-235 -> av_resample, resample2.c).
+ * Tight planes; chroma planes are stored with the rounded-up size the rest of the harness uses, the reference
+ * itself touches only (w>>1) x (h>>1) of them. */
+int amvref_img_resample(const uint8_t *y, const uint8_t *u, const uint8_t *v, int n, int iw, int ih, int ow, int oh,
+                        uint8_t *oy, uint8_t *ou, uint8_t *ov)
+{
+    ref_init();
+    int icw = (iw + 1) >> 1, ich = (ih + 1) >> 1, ocw = (ow + 1) >> 1, och = (oh + 1) >> 1, i;
+    ImgReSampleContext *s = img_resample_init(ow, oh, iw, ih);
+    if (!s) return -1;
+    for (i = 0; i < n; i++) {
+        AVPicture src, dst;
+        src.data[0] = (uint8_t *)y + (size_t)i * iw * ih; src.data[1] = (uint8_t *)u + (size_t)i * icw * ich;
+        src.data[2] = (uint8_t *)v + (size_t)i * icw * ich; src.data[3] = NULL;
+        src.linesize[0] = iw; src.linesize[1] = icw; src.linesize[2] = icw; src.linesize[3] = 0;
+        dst.data[0] = oy + (size_t)i * ow * oh; dst.data[1] = ou + (size_t)i * ocw * och;
+        dst.data[2] = ov + (size_t)i * ocw * och; dst.data[3] = NULL;
+        dst.linesize[0] = ow; dst.linesize[1] = ocw; dst.linesize[2] = ocw; dst.linesize[3] = 0;
+        img_resample(s, &dst, &src);
+    }
+    img_resample_close(s);
+    return n;
+}
+
+/* in: interleaved int16, n_in samples per channel, fed to audio_resample `chunk` samples per call (as ffmpeg.c
+ * feeds it one decoded packet at a time); output mono.  Returns the samples written, -1 on error. */
+int64_t amvref_audio_resample(const int16_t *in, int64_t n_in, int in_ch, int in_rate, int out_rate, int chunk,
+                              int16_t *out, int64_t out_cap)
+{
+    ref_init();
+    ReSampleContext *s = audio_resample_init(1, in_ch, out_rate, in_rate);
+    if (!s) return -1;
+    int64_t done = 0, pos = 0;
+    int lenmax = (int)(4.0 * chunk * ((double)out_rate / in_rate + 1.0)) + 64;
+    short *tmp = av_malloc(sizeof(short) * lenmax);
+    while (pos < n_in) {
+        int nb = (int)(n_in - pos < chunk ? n_in - pos : chunk);
+        int k = audio_resample(s, tmp, (short *)in + pos * in_ch, nb);
+        if (k < 0 || done + k > out_cap) { done = -1; break; }
+        memcpy(out + done, tmp, sizeof(short) * k);
+        done += k; pos += nb;
+    }
+    av_free(tmp);
+    audio_resample_close(s);
+    return done;
+}
+
+/* the polyphase bank av_resample_init builds (resample2.c:185-206 -> av_build_filter :93-141): `len` receives
+ * filter_length, bank receives filter_length * ((1<<phase_shift) + 1) coefficients */
+struct AmvrefResampleCtxView { int16_t *filter_bank; int filter_length; };
+int amvref_resample_bank(int out_rate, int in_rate, int16_t *bank, int cap, int *len)
+{
+    struct AVResampleContext *c = av_resample_init(out_rate, in_rate, 16, 10, 0, 0.8);
+    struct AmvrefResampleCtxView *vw = (struct AmvrefResampleCtxView *)c;
+    int total = vw->filter_length * 1025;
+    *len = vw->filter_length;
+    if (total > cap) { av_resample_close(c); return -1; }
+    memcpy(bank, vw->filter_bank, sizeof(int16_t) * total);
+    av_resample_close(c);
+    return total;
+}

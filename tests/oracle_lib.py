@@ -174,6 +174,38 @@ class Oracle(_AmvlibOracleMixin):
         self.lib.amvo_convert_range(_p(y), _p(u), _p(v), C.c_size_t(y.size), C.c_size_t(u.size), int(direction), _p(oy), _p(ou), _p(ov))
         return oy, ou, ov
 
+    def scale_frames(self, y, u, v, ow, oh, fill=0):
+        """img_resample on tight planes [n,ih,iw] / [n,ich,icw]; bytes the reference leaves alone keep `fill`"""
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        n, ih, iw = y.shape
+        ocw, och = chroma_dims(ow, oh)
+        oy, ou, ov = np.full((n, oh, ow), fill, np.uint8), np.full((n, och, ocw), fill, np.uint8), np.full((n, och, ocw), fill, np.uint8)
+        if self.lib.amvo_scale_frames(_p(y), _p(u), _p(v), n, iw, ih, ow, oh, _p(oy), _p(ou), _p(ov)) != n:
+            raise RuntimeError("oracle scaler failed")
+        return oy, ou, ov
+
+    def scale_banks(self, iw, ih, ow, oh):
+        hb, vb = np.zeros((16, 4), np.int16), np.zeros((16, 4), np.int16)
+        self.lib.amvo_scale_banks(iw, ih, ow, oh, _p(hb), _p(vb))
+        return hb, vb
+
+    def resample_bank(self, in_rate, out_rate=22050):
+        n = self.lib.amvo_resample_filter_length(in_rate, out_rate)
+        bank = np.zeros((1024, n), np.int16)
+        self.lib.amvo_resample_bank(in_rate, out_rate, _p(bank))
+        return bank
+
+    def audio_resample(self, pcm, in_channels, in_rate, out_rate=22050):
+        pcm = np.ascontiguousarray(pcm, np.int16).reshape(-1)
+        n_in = pcm.size // in_channels
+        cap = int(n_in * out_rate / in_rate) + 64
+        out = np.zeros(cap, np.int16)
+        self.lib.amvo_audio_resample.restype = C.c_int64
+        k = self.lib.amvo_audio_resample(_p(pcm), C.c_int64(n_in), in_channels, in_rate, out_rate, _p(out), C.c_int64(cap))
+        if k < 0:
+            raise RuntimeError("oracle resampler failed")
+        return out[:k].copy()
+
     def sp5x_decode_frames(self, pkts, off, size, w, h, undef=False):
         n = len(size)
         cw, ch = chroma_dims(w, h)
@@ -411,6 +443,36 @@ class Ref:
         if r != n:
             raise RuntimeError("reference img_convert failed: %d" % r)
         return oy, ou, ov
+
+    def scale_frames(self, y, u, v, ow, oh, fill=0):
+        """img_resample_init + img_resample (what sws_scale of the fork calls) on tight planes"""
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        n, ih, iw = y.shape
+        ocw, och = chroma_dims(ow, oh)
+        oy, ou, ov = np.full((n, oh, ow), fill, np.uint8), np.full((n, och, ocw), fill, np.uint8), np.full((n, och, ocw), fill, np.uint8)
+        if self.lib.amvref_img_resample(_p(y), _p(u), _p(v), n, iw, ih, ow, oh, _p(oy), _p(ou), _p(ov)) != n:
+            raise RuntimeError("reference img_resample failed")
+        return oy, ou, ov
+
+    def audio_resample(self, pcm, in_channels, in_rate, out_rate=22050, chunk=4096):
+        """audio_resample_init(1, in_channels, out_rate, in_rate) + audio_resample fed `chunk` samples per call"""
+        pcm = np.ascontiguousarray(pcm, np.int16).reshape(-1)
+        n_in = pcm.size // in_channels
+        cap = int(n_in * out_rate / in_rate) + 64
+        out = np.zeros(cap, np.int16)
+        self.lib.amvref_audio_resample.restype = C.c_int64
+        k = self.lib.amvref_audio_resample(_p(pcm), C.c_int64(n_in), in_channels, in_rate, out_rate, int(chunk), _p(out), C.c_int64(cap))
+        if k < 0:
+            raise RuntimeError("reference audio_resample failed")
+        return out[:k].copy()
+
+    def resample_bank(self, in_rate, out_rate=22050):
+        """filter bank of av_resample_init(out_rate, in_rate, 16, 10, 0, 0.8): [1024, filter_length]"""
+        buf = np.zeros(1025 * 8192, np.int16)
+        ln = C.c_int(0)
+        if self.lib.amvref_resample_bank(out_rate, in_rate, _p(buf), buf.size, C.byref(ln)) < 0:
+            raise RuntimeError("reference av_resample_init failed")
+        return buf[: 1024 * ln.value].reshape(1024, ln.value).copy()
 
     # -- container (libavformat amv_muxer / avi_demuxer, driven like ffmpeg.c does)
     def mux(self, w, h, fps, sample_rate, vpk, voff, vsz, apk, aoff, asz):

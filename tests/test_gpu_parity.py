@@ -698,3 +698,125 @@ def test_adpcm_trellis_golden(ctx, case):
     finally:
         ctx.set_option("adpcm_trellis", 0)
     assert (st == 0).all() and np.array_equal(esz, sz) and np.array_equal(eo, out)
+
+
+# ------------------------------------------------------------------ picture scaler / audio resampler
+GR = np.load(os.path.join(os.path.dirname(__file__), "golden", "resample_golden.npz"))
+
+
+@pytest.mark.parametrize("case", sorted(set(k.split("/")[0] for k in GR.files if k.startswith("scale_"))))
+def test_scaler_matches_golden(ctx, case):
+    """amv_scale_frames against pictures the reference's img_resample produced"""
+    ow, oh = map(int, case.split("_")[2].split("x"))
+    got = ctx.scale_frames(GR[case + "/y"], GR[case + "/u"], GR[case + "/v"], ow, oh, fill=7)
+    for a, nm in zip(got, ("oy", "ou", "ov")):
+        assert np.array_equal(a, GR[case + "/" + nm])
+
+
+@pytest.mark.parametrize("dims", [(640, 480, 320, 240), (352, 288, 208, 176), (160, 120, 320, 240), (321, 243, 160, 120),
+                                  (1280, 720, 128, 96), (100, 100, 101, 99), (720, 576, 208, 176), (64, 48, 640, 360),
+                                  (16, 16, 2, 2), (5, 3, 17, 9), (320, 240, 320, 120), (2, 2, 8, 8), (8, 8, 1, 1)])
+def test_scaler_identical(ctx, oracle, dims):
+    """host buffers and padded device planes; down, up, odd sizes (chroma at sizes >> 1), extreme ratios"""
+    import torch
+    iw, ih, ow, oh = dims
+    rng = np.random.default_rng(iw * 7 + oh)
+    n = 3
+    icw, ich = chroma_dims(iw, ih)
+    ocw, och = chroma_dims(ow, oh)
+    y = rng.integers(0, 256, (n, ih, iw), dtype=np.uint8)
+    u = rng.integers(0, 256, (n, ich, icw), dtype=np.uint8)
+    v = rng.integers(0, 256, (n, ich, icw), dtype=np.uint8)
+    y[1] = np.where(rng.random((ih, iw)) < 0.5, 0, 255)
+    want = oracle.scale_frames(y, u, v, ow, oh, fill=9)
+    got = ctx.scale_frames(y, u, v, ow, oh, fill=9)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    dev = torch.device("cuda", 0)
+    for pad in (16, 3):                                   # 4-byte aligned rows (32-bit stores) and odd pitches (byte stores)
+        ils_y, ils_c, ols_y, ols_c = iw + pad, icw + pad, ow + pad, ocw + pad
+        dY = torch.full((n, ih, ils_y), 5, dtype=torch.uint8, device=dev); dY[:, :, :iw] = torch.from_numpy(y).to(dev)
+        dU = torch.full((n, ich, ils_c), 5, dtype=torch.uint8, device=dev); dU[:, :, :icw] = torch.from_numpy(u).to(dev)
+        dV = torch.full((n, ich, ils_c), 5, dtype=torch.uint8, device=dev); dV[:, :, :icw] = torch.from_numpy(v).to(dev)
+        oY = torch.full((n, oh, ols_y), 9, dtype=torch.uint8, device=dev)
+        oU = torch.full((n, och, ols_c), 9, dtype=torch.uint8, device=dev)
+        oV = torch.full((n, och, ols_c), 9, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctx.scale_frames_raw(dY, dU, dV, ils_y, ils_c, ih * ils_y, ich * ils_c, n, iw, ih, oY, oU, oV, ols_y, ols_c, oh * ols_y,
+                             och * ols_c, ow, oh, amv.MEM_DEVICE)
+        ctx.sync()
+        for t, ww, wn in ((oY, ow, want[0]), (oU, ocw, want[1]), (oV, ocw, want[2])):
+            a = t.cpu().numpy()
+            assert np.array_equal(a[:, :, :ww], wn) and (a[:, :, ww:] == 9).all()
+
+
+def test_scaler_feeds_the_encoder(ctx, oracle):
+    """`-s 208x176` in front of the AMV encoder: scaled frames encode to the packets the oracle makes of the oracle's scaling"""
+    y, u, v = synth_frames(4, 352, 288, seed=5, kind="sinus")
+    sy, su, sv = ctx.scale_frames(y, u, v, 208, 176)
+    wy, wu, wv = oracle.scale_frames(y, u, v, 208, 176)
+    assert all(np.array_equal(a, b) for a, b in zip((sy, su, sv), (wy, wu, wv)))
+    pk, off, sz, st = ctx.encode_frames(sy, su, sv)
+    wpk, woff, wsz = oracle.encode_frames(wy, wu, wv, 208, 176)
+    assert (st == 0).all() and np.array_equal(sz, wsz) and np.array_equal(pk[: int(sz.sum())], wpk[: int(wsz.sum())])
+
+
+@pytest.mark.parametrize("case", sorted(set(k.split("/")[0] for k in GR.files if k.startswith("audio_"))))
+def test_audio_resampler_matches_golden(ctx, case):
+    """amv_audio_resample against streams the reference's audio_resample produced packet by packet"""
+    rate, ch = map(int, case.split("_")[1:])
+    assert np.array_equal(ctx.audio_resample(GR[case + "/pcm"], ch, rate, 22050), GR[case + "/out"])
+
+
+@pytest.mark.parametrize("rate,ch,n", [(44100, 2, 50000), (48000, 1, 70000), (8000, 1, 9000), (22050, 2, 30000), (11025, 1, 20000),
+                                        (32000, 2, 3000000), (44100, 1, 1000), (48000, 2, 100), (96000, 2, 40000), (16000, 1, 20),
+                                        (96000, 1, 50), (44100, 2, 1)])
+@pytest.mark.parametrize("kind", ["noise", "tones", "square"])
+def test_audio_resampler_identical(ctx, oracle, rate, ch, n, kind):
+    """host and device buffers; streams shorter than the filter (mirrored taps only), beyond 2^21 samples (64-bit positions),
+    full-scale square waves (32-bit accumulator, saturation)"""
+    import torch
+    pcm = synth_pcm(n * ch, seed=rate + n, kind=kind)
+    want = oracle.audio_resample(pcm, ch, rate, 22050)
+    assert ctx.audio_resample_count(n, rate, 22050) == len(want)
+    got = ctx.audio_resample(pcm, ch, rate, 22050)
+    assert np.array_equal(got, want)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(pcm).to(dev)
+    d_out = torch.full((len(want) + 8,), 77, dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()
+    k = ctx.audio_resample_raw(d_in, n, ch, rate, 22050, d_out, len(want), amv.MEM_DEVICE)
+    ctx.sync()
+    a = d_out.cpu().numpy()
+    assert k == len(want) and np.array_equal(a[:k], want) and (a[k:] == 77).all()
+
+
+def test_audio_resampler_feeds_the_adpcm_encoder(ctx, oracle):
+    """44.1 kHz stereo -> 22050 Hz mono -> ADPCM chunks, as do_audio_out chains them"""
+    pcm = synth_pcm(2 * 44100, seed=9, kind="tones")
+    mono = ctx.audio_resample(pcm, 2, 44100, 22050)
+    assert np.array_equal(mono, oracle.audio_resample(pcm, 2, 44100, 22050))
+    nchunks = len(mono) // 1378
+    ns = np.full(nchunks, 1378, np.uint32)
+    off = offsets_of(ns)
+    out, ooff, osz, so, st = ctx.adpcm_encode_streams(mono[: nchunks * 1378], off, ns, np.array([0, nchunks], np.uint32))
+    assert (st == 0).all()
+    # the chunks decode back to something close to the resampled stream (the codec is lossy; the parity of each stage
+    # is pinned by its own tests)
+    back = ctx.adpcm_decode(out, ooff, osz)[0]
+    assert len(back) == nchunks * 1378
+
+
+def test_resample_argument_errors(ctx):
+    y = np.zeros((1, 16, 16), np.uint8); c = np.zeros((1, 8, 8), np.uint8)
+    with pytest.raises(amv.AmvError):
+        ctx.scale_frames(y, c, c, 0, 16)
+    with pytest.raises(amv.AmvError):
+        ctx.scale_frames(y, c, c, 20000, 16)
+    with pytest.raises(amv.AmvError):                     # no chroma samples to scale from: outside the reference's defined domain
+        ctx.scale_frames(y[:, :1, :1], c[:, :1, :1], c[:, :1, :1], 8, 8)
+    with pytest.raises(amv.AmvError):
+        ctx.audio_resample(np.zeros(30, np.int16), 3, 44100, 22050)
+    with pytest.raises(amv.AmvError):
+        ctx.audio_resample_raw(np.zeros(1000, np.int16), 1000, 1, 44100, 22050, np.zeros(10, np.int16), 10, amv.MEM_HOST)
+    assert len(ctx.audio_resample(np.zeros(0, np.int16), 1, 44100, 22050)) == 0

@@ -179,3 +179,49 @@ def test_adpcm_trellis_matches_golden(oracle, case):
     step_in = np.array([int(out[int(o) + 2]) | (int(out[int(o) + 3]) << 8) for o in off], np.int16)
     eo, _, esz, _ = oracle.adpcm_encode_trellis(GT[case + "/src"], offsets_of(cons), cons, step_in, trellis)
     assert np.array_equal(esz, sz) and np.array_equal(eo, out)
+
+
+# ------------------------------------------------------------------ picture scaler / audio resampler
+GR = np.load(os.path.join(os.path.dirname(__file__), "golden", "resample_golden.npz"))
+SCALE_CASES = sorted(set(k.split("/")[0] for k in GR.files if k.startswith("scale_")))
+AUDIO_CASES = sorted(set(k.split("/")[0] for k in GR.files if k.startswith("audio_")))
+
+
+@pytest.mark.parametrize("case", SCALE_CASES)
+def test_scaler_matches_golden(oracle, case):
+    """img_resample of the reference on small pictures (down, up, odd sizes, one axis only)"""
+    ow, oh = map(int, case.split("_")[2].split("x"))
+    got = oracle.scale_frames(GR[case + "/y"], GR[case + "/u"], GR[case + "/v"], ow, oh, fill=7)
+    for a, nm in zip(got, ("oy", "ou", "ov")):
+        assert np.array_equal(a, GR[case + "/" + nm])
+
+
+@pytest.mark.parametrize("case", AUDIO_CASES)
+def test_audio_resampler_matches_golden(oracle, case):
+    """audio_resample of the reference fed in packets against the oracle's one-shot closed form"""
+    rate, ch = map(int, case.split("_")[1:])
+    got = oracle.audio_resample(GR[case + "/pcm"], ch, rate, 22050)
+    assert np.array_equal(got, GR[case + "/out"])
+    assert np.array_equal(oracle.resample_bank(rate, 22050)[[0, 1, 511, 512, 1023]], GR[case + "/bank_rows"])
+
+
+def test_host_filter_banks_match_golden_and_oracle(oracle):
+    """libamvcuda's host-side filter design (amv_scale_banks / amv_audio_resample_bank; no device involved)"""
+    import amv_codec_tools_b200 as amv
+    lib = amv.load_library()
+    for case in AUDIO_CASES:
+        rate = int(case.split("_")[1])
+        bank = amv.audio_resample_bank(rate, 22050, lib=lib)
+        assert np.array_equal(bank, oracle.resample_bank(rate, 22050))
+        assert np.array_equal(bank[[0, 1, 511, 512, 1023]], GR[case + "/bank_rows"])
+    for case in SCALE_CASES:
+        iw, ih = map(int, case.split("_")[1].split("x"))
+        ow, oh = map(int, case.split("_")[2].split("x"))
+        hb, vb, hi, vi = amv.scale_banks(iw, ih, ow, oh, lib=lib)
+        ohb, ovb = oracle.scale_banks(iw, ih, ow, oh)
+        assert np.array_equal(hb, ohb) and np.array_equal(vb, ovb)
+        assert hi == iw * 65536 // ow and vi == ih * 65536 // oh
+    # how many samples the reference returns over a stream: a closed form in the ABI, counted by the oracle
+    for rate, n in ((44100, 5000), (48000, 777), (8000, 100), (22050, 1378), (32000, 31), (96000, 50)):
+        pcm = np.zeros(n, np.int16)
+        assert lib.amv_audio_resample_count(n, rate, 22050) == len(oracle.audio_resample(pcm, 1, rate, 22050))

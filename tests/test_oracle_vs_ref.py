@@ -398,3 +398,32 @@ def test_mjpeg_restart_intervals_identical(oracle, ref, samp, restart):
             assert (st == 0).all() and np.abs(ry.astype(int) - y).mean() < 8
         for a, b, m in zip((oy, ou, ov), (ry, ru, rv), masks):
             assert np.array_equal(a[m == 0], b[m == 0])
+
+
+# ------------------------------------------------------------------ picture scaler / audio resampler
+@pytest.mark.parametrize("dims", [(640, 480, 320, 240), (352, 288, 208, 176), (160, 120, 320, 240), (321, 243, 160, 120),
+                                  (1280, 720, 128, 96), (100, 100, 101, 99), (720, 576, 208, 176), (64, 48, 640, 360),
+                                  (16, 16, 2, 2), (5, 3, 17, 9)])
+def test_scaler_matches_img_resample(oracle, ref, dims):
+    """img_resample_init + img_resample (the fork's sws_scale) against the oracle: down, up, odd sizes, extreme ratios"""
+    iw, ih, ow, oh = dims
+    rng = np.random.default_rng(iw * 7 + oh)
+    icw, ich = (iw + 1) // 2, (ih + 1) // 2
+    y = rng.integers(0, 256, (2, ih, iw), dtype=np.uint8)
+    u = rng.integers(0, 256, (2, ich, icw), dtype=np.uint8)
+    v = rng.integers(0, 256, (2, ich, icw), dtype=np.uint8)
+    y[1] = np.where(rng.random((ih, iw)) < 0.5, 0, 255)                # the clamps of both passes
+    for a, b in zip(ref.scale_frames(y, u, v, ow, oh, fill=9), oracle.scale_frames(y, u, v, ow, oh, fill=9)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("rate,ch,n,chunk", [(44100, 2, 50000, 4096), (48000, 1, 70000, 1152), (8000, 1, 9000, 320),
+                                              (22050, 2, 30000, 1024), (11025, 1, 20000, 8192), (32000, 2, 600000, 4608),
+                                              (44100, 1, 1000, 1000), (48000, 2, 100, 100), (96000, 2, 40000, 2048),
+                                              (16000, 1, 20, 20)])
+@pytest.mark.parametrize("kind", ["noise", "tones", "square"])
+def test_audio_resampler_matches_audio_resample(oracle, ref, rate, ch, n, chunk, kind):
+    """the reference fed packet by packet (tail carried between calls) against the oracle's closed form over the stream"""
+    pcm = synth_pcm(n * ch, seed=rate + n, kind=kind)
+    assert np.array_equal(ref.audio_resample(pcm, ch, rate, 22050, chunk=chunk), oracle.audio_resample(pcm, ch, rate, 22050))
+    assert np.array_equal(ref.resample_bank(rate, 22050), oracle.resample_bank(rate, 22050))
