@@ -24,6 +24,7 @@ LIB_PATH = os.path.join(PKG_DIR, "lib", "libamvcuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "amvcuda.h")
 
 MEM_HOST, MEM_DEVICE = 0, 1
+SCALE_IN_JPEG_RANGE, SCALE_OUT_JPEG_RANGE = 1, 2
 LAYOUT_PACKED, LAYOUT_SLOTS = 0, 1
 
 ST_SHORT, ST_BADCODE, ST_COEFIDX, ST_MARKER, ST_OVERRUN, ST_RANGE, ST_NOSPACE, ST_HEADER = (1 << i for i in range(8))
@@ -35,7 +36,7 @@ EXPORTS = [
     "amv_adpcm_enc_chunks", "amv_adpcm_enc_streams", "amv_decode_frames_bgr24",
     "amv_file_index", "amv_file_mux", "amv_decode_frames_sp5x",
     "amv_convert_range", "amv_mjpeg_configure", "amv_decode_frames_mjpeg",
-    "amv_scale_frames", "amv_audio_resample", "amv_audio_resample_count", "amv_scale_banks", "amv_audio_resample_bank",
+    "amv_scale_frames", "amv_audio_resample", "amv_audio_resample_count", "amv_scale_banks", "amv_audio_resample_bank", "amv_audio_resample_from", "amv_audio_resample_first_tap", "amv_scale_frames_ex",
 ]
 
 
@@ -101,7 +102,11 @@ def load_library(path=LIB_PATH):
     lib.amv_mjpeg_configure.argtypes = [vp, vp, C.c_uint32, vp, vp]
     lib.amv_convert_range.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32]
     lib.amv_scale_frames.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32]
+    lib.amv_scale_frames_ex.argtypes = [vp, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, vp, vp, vp, i32, i32, u64, u64, i32, i32, i32, i32]
     lib.amv_audio_resample.argtypes = [vp, vp, u64, i32, i32, i32, vp, u64, vp, i32]
+    lib.amv_audio_resample_from.argtypes = [vp, vp, u64, u64, i32, i32, i32, u64, vp, u64, vp, i32]
+    lib.amv_audio_resample_first_tap.argtypes = [u64, i32, i32]
+    lib.amv_audio_resample_first_tap.restype = C.c_int64
     lib.amv_audio_resample_count.argtypes = [u64, i32, i32]
     lib.amv_audio_resample_count.restype = u64
     lib.amv_scale_banks.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
@@ -273,11 +278,12 @@ class AmvCuda:
         self.convert_range_raw(y, u, v, w, cw, w * h, cw * ch, n, w, h, direction, oy, ou, ov, w, cw, w * h, cw * ch, MEM_HOST)
         return oy, ou, ov
 
-    def scale_frames_raw(self, y, u, v, ls_y, ls_c, fs_y, fs_c, n, iw, ih, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, ow, oh, mem):
-        self._ck(self.lib.amv_scale_frames(self.ctx, _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, n, iw, ih,
-                                           _ptr(oy), _ptr(ou), _ptr(ov), ols_y, ols_c, ofs_y, ofs_c, ow, oh, mem))
+    def scale_frames_raw(self, y, u, v, ls_y, ls_c, fs_y, fs_c, n, iw, ih, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, ow, oh, mem,
+                         flags=0):
+        self._ck(self.lib.amv_scale_frames_ex(self.ctx, _ptr(y), _ptr(u), _ptr(v), ls_y, ls_c, fs_y, fs_c, n, iw, ih,
+                                              _ptr(oy), _ptr(ou), _ptr(ov), ols_y, ols_c, ofs_y, ofs_c, ow, oh, flags, mem))
 
-    def scale_frames(self, y, u, v, ow, oh, fill=0):
+    def scale_frames(self, y, u, v, ow, oh, fill=0, flags=0):
         """numpy planes [n,ih,iw] / [n,ich,icw] -> [n,oh,ow] / [n,och,ocw] as the reference's img_resample scales them
         (chroma at sizes >> 1; output bytes the reference does not write keep `fill`)"""
         y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
@@ -288,7 +294,7 @@ class AmvCuda:
         ou = np.full((n, och, ocw), fill, np.uint8)
         ov = np.full((n, och, ocw), fill, np.uint8)
         self.scale_frames_raw(y, u, v, iw, icw, iw * ih, icw * ich, n, iw, ih, oy, ou, ov, ow, ocw, ow * oh, ocw * och, ow, oh,
-                              MEM_HOST)
+                              MEM_HOST, flags)
         return oy, ou, ov
 
     def audio_resample_count(self, n_in, in_rate, out_rate=22050):
@@ -299,6 +305,32 @@ class AmvCuda:
         self._ck(self.lib.amv_audio_resample(self.ctx, _ptr(pcm), int(n_in), int(in_channels), int(in_rate), int(out_rate),
                                              _ptr(out), int(out_cap), C.addressof(k), mem))
         return int(k.value)
+
+    def audio_resample_from_raw(self, pcm, in_base, n_in, in_channels, in_rate, out_rate, k_start, out, out_cap, mem):
+        k = C.c_uint64(0)
+        self._ck(self.lib.amv_audio_resample_from(self.ctx, _ptr(pcm), int(in_base), int(n_in), int(in_channels), int(in_rate),
+                                                  int(out_rate), int(k_start), _ptr(out), int(out_cap), C.addressof(k), mem))
+        return int(k.value)
+
+    def audio_resample_packets(self, packets, in_channels, in_rate, out_rate=22050):
+        """feed a stream packet by packet, keeping only the tail the next outputs still need (what the reference's
+        audio_resample carries from call to call); returns the list of per-packet outputs"""
+        outs, k_next, base = [], 0, 0
+        buf = np.zeros(0, np.int16)
+        for pk in packets:
+            buf = np.concatenate([buf, np.ascontiguousarray(pk, np.int16).reshape(-1)])
+            n_buf = buf.size // in_channels
+            cap = max(self.audio_resample_count(base + n_buf, in_rate, out_rate) - k_next, 0)
+            out = np.zeros(max(cap, 1), np.int16)
+            k = self.audio_resample_from_raw(buf, base, n_buf, in_channels, in_rate, out_rate, k_next, out, cap, MEM_HOST) if n_buf else 0
+            outs.append(out[:k])
+            k_next += k
+            keep_from = max(int(self.lib.amv_audio_resample_first_tap(k_next, in_rate, out_rate)), 0)
+            if keep_from > base:
+                drop = min(keep_from - base, n_buf)
+                buf = buf[drop * in_channels:]
+                base += drop
+        return outs
 
     def audio_resample(self, pcm, in_channels, in_rate, out_rate=22050):
         """interleaved int16 samples -> mono int16 at out_rate, as the reference's audio_resample produces over the stream"""

@@ -946,12 +946,13 @@ AMV_API int amv_convert_range(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, 
 }
 
 // ------------------------------------------------------------------------------- picture scaler
-AMV_API int amv_scale_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
-                             uint64_t fs_y, uint64_t fs_c, int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov,
-                             int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int ow, int oh, int mem) {
+AMV_API int amv_scale_frames_ex(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
+                                uint64_t fs_y, uint64_t fs_c, int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov,
+                                int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int ow, int oh, int flags, int mem) {
     if (!ctx) return AMV_ERR_ARG;
-    if (n < 0 || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0 || iw > 16384 || ih > 16384 || ow > 16384 || oh > 16384 || bad_mem(mem))
-        return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / mem");
+    if (n < 0 || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0 || iw > 16384 || ih > 16384 || ow > 16384 || oh > 16384 || bad_mem(mem) ||
+        (flags & ~(AMV_SCALE_IN_JPEG_RANGE | AMV_SCALE_OUT_JPEG_RANGE)))
+        return fail(ctx, AMV_ERR_ARG, "bad n / dimensions / flags / mem");
     if (n == 0) return AMV_OK;
     if (!y || !u || !v || !oy || !ou || !ov) return fail(ctx, AMV_ERR_ARG, "null buffer");
     // the reference scales planes 1 and 2 at (w >> 1) x (h >> 1) (imgresample.c:494-505)
@@ -965,37 +966,74 @@ AMV_API int amv_scale_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, c
     ScaleBanks banks;
     build_scale_banks(iw, ih, ow, oh, &banks);
     CK(cudaSetDevice(ctx->device));
-    if (mem == AMV_MEM_DEVICE) {
-        const int k = launch_scale_frames(y, u, v, ls_y, ls_c, fs_y, fs_c, n, iw, ih, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, ow, oh,
-                                          banks, ctx->stream);
-        return check_launch(ctx, "scaler kernels", k);
-    }
-    // host buffers: tight device copies in, kernels, tight copies out (only the bytes the reference writes)
-    const uint64_t ty = (uint64_t)iw * ih, tc = (uint64_t)icw * ich, oty = (uint64_t)ow * oh, otc = (uint64_t)ocw * och;
-    uint8_t *d_y, *d_u, *d_v, *d_oy, *d_ou, *d_ov;
-    ENSURE(WS_H_A, ty * n, d_y);
-    ENSURE(WS_H_B, tc * n + 1, d_u);
-    ENSURE(WS_H_C, tc * n + 1, d_v);
-    ENSURE(WS_H_D, oty * n, d_oy);
-    ENSURE(WS_H_E, otc * n + 4, d_ou);
-    ENSURE(WS_H_F, otc * n + 4, d_ov);
-    int r;
     const bool chroma = icw > 0 && ich > 0 && ocw > 0 && och > 0;
-    if ((r = copy_planes(ctx, d_y, const_cast<uint8_t *>(y), iw, ih, ls_y, fs_y, n, false)) != AMV_OK) return r;
-    if (chroma) {
-        if ((r = copy_planes(ctx, d_u, const_cast<uint8_t *>(u), icw, ich, ls_c, fs_c, n, false)) != AMV_OK) return r;
-        if ((r = copy_planes(ctx, d_v, const_cast<uint8_t *>(v), icw, ich, ls_c, fs_c, n, false)) != AMV_OK) return r;
+    const bool host = mem == AMV_MEM_HOST, pre = (flags & AMV_SCALE_IN_JPEG_RANGE) != 0, post = (flags & AMV_SCALE_OUT_JPEG_RANGE) != 0;
+    const uint64_t ty = (uint64_t)iw * ih, tc = (uint64_t)icw * ich, oty = (uint64_t)ow * oh, otc = (uint64_t)ocw * och;
+    // what the scaler reads and writes: the caller's device planes, or tight device copies (host buffers; a
+    // range-converted input never overwrites the caller's planes)
+    const uint8_t *sy = y, *su = u, *sv = v;
+    int sls_y = ls_y, sls_c = ls_c;
+    uint64_t sfs_y = fs_y, sfs_c = fs_c;
+    uint8_t *dy = oy, *du = ou, *dv = ov;
+    int dls_y = ols_y, dls_c = ols_c;
+    uint64_t dfs_y = ofs_y, dfs_c = ofs_c;
+    int launches = 0, r;
+    if (host || pre) {
+        uint8_t *t_y, *t_u, *t_v;
+        ENSURE(WS_H_A, ty * n, t_y);
+        ENSURE(WS_H_B, tc * n + 1, t_u);
+        ENSURE(WS_H_C, tc * n + 1, t_v);
+        if (host) {
+            if ((r = copy_planes(ctx, t_y, const_cast<uint8_t *>(y), iw, ih, ls_y, fs_y, n, false)) != AMV_OK) return r;
+            if (chroma) {
+                if ((r = copy_planes(ctx, t_u, const_cast<uint8_t *>(u), icw, ich, ls_c, fs_c, n, false)) != AMV_OK) return r;
+                if ((r = copy_planes(ctx, t_v, const_cast<uint8_t *>(v), icw, ich, ls_c, fs_c, n, false)) != AMV_OK) return r;
+            }
+            sy = t_y; su = t_u; sv = t_v; sls_y = iw; sls_c = icw; sfs_y = ty; sfs_c = tc;
+        }
+        if (pre) {      // img_convert YUVJ420P -> YUV420P in front of the scaler (imgresample.c:617-636)
+            launch_convert_range_plane(sy, t_y, iw, ih, n, sls_y, iw, sfs_y, ty, 1, false, ctx->stream);
+            launches++;
+            if (chroma) {
+                launch_convert_range_plane(su, t_u, icw, ich, n, sls_c, icw, sfs_c, tc, 1, true, ctx->stream);
+                launch_convert_range_plane(sv, t_v, icw, ich, n, sls_c, icw, sfs_c, tc, 1, true, ctx->stream);
+                launches += 2;
+            }
+            sy = t_y; su = t_u; sv = t_v; sls_y = iw; sls_c = icw; sfs_y = ty; sfs_c = tc;
+        }
     }
-    const int k = launch_scale_frames(d_y, d_u, d_v, iw, icw, ty, tc, n, iw, ih, d_oy, d_ou, d_ov, ow, ocw, oty, otc, ow, oh, banks,
-                                      ctx->stream);
-    if ((r = check_launch(ctx, "scaler kernels", k)) != AMV_OK) return r;
-    if ((r = copy_planes(ctx, d_oy, oy, ow, oh, ols_y, ofs_y, n, true)) != AMV_OK) return r;
+    if (host) {
+        ENSURE(WS_H_D, oty * n, dy);
+        ENSURE(WS_H_E, otc * n + 4, du);
+        ENSURE(WS_H_F, otc * n + 4, dv);
+        dls_y = ow; dls_c = ocw; dfs_y = oty; dfs_c = otc;
+    }
+    launches += launch_scale_frames(sy, su, sv, sls_y, sls_c, sfs_y, sfs_c, n, iw, ih, dy, du, dv, dls_y, dls_c, dfs_y, dfs_c, ow, oh,
+                                    banks, ctx->stream);
+    if (post) {         // img_convert YUV420P -> YUVJ420P behind it (:671-682), over the area the scaler wrote
+        launch_convert_range_plane(dy, dy, ow, oh, n, dls_y, dls_y, dfs_y, dfs_y, 0, false, ctx->stream);
+        launches++;
+        if (chroma) {
+            launch_convert_range_plane(du, du, ocw, och, n, dls_c, dls_c, dfs_c, dfs_c, 0, true, ctx->stream);
+            launch_convert_range_plane(dv, dv, ocw, och, n, dls_c, dls_c, dfs_c, dfs_c, 0, true, ctx->stream);
+            launches += 2;
+        }
+    }
+    if ((r = check_launch(ctx, "scaler kernels", launches)) != AMV_OK) return r;
+    if (!host) return AMV_OK;
+    if ((r = copy_planes(ctx, dy, oy, ow, oh, ols_y, ofs_y, n, true)) != AMV_OK) return r;
     if (chroma) {
-        if ((r = copy_planes(ctx, d_ou, ou, ocw, och, ols_c, ofs_c, n, true)) != AMV_OK) return r;
-        if ((r = copy_planes(ctx, d_ov, ov, ocw, och, ols_c, ofs_c, n, true)) != AMV_OK) return r;
+        if ((r = copy_planes(ctx, du, ou, ocw, och, ols_c, ofs_c, n, true)) != AMV_OK) return r;
+        if ((r = copy_planes(ctx, dv, ov, ocw, och, ols_c, ofs_c, n, true)) != AMV_OK) return r;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return AMV_OK;
+}
+
+AMV_API int amv_scale_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c,
+                             uint64_t fs_y, uint64_t fs_c, int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov,
+                             int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c, int ow, int oh, int mem) {
+    return amv_scale_frames_ex(ctx, y, u, v, ls_y, ls_c, fs_y, fs_c, n, iw, ih, oy, ou, ov, ols_y, ols_c, ofs_y, ofs_c, ow, oh, 0, mem);
 }
 
 // the filter banks both stages run on, as the host builds them (init-time work, no device involved)
@@ -1027,11 +1065,11 @@ AMV_API uint64_t amv_audio_resample_count(uint64_t n_in, int in_rate, int out_ra
     return (uint64_t)resample_output_count((int64_t)n_in, in_rate, out_rate);
 }
 
-AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, int in_channels, int in_rate, int out_rate,
-                               int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem) {
+AMV_API int amv_audio_resample_from(amv_ctx *ctx, const int16_t *in, uint64_t in_base, uint64_t n_in, int in_channels, int in_rate,
+                                    int out_rate, uint64_t k_start, int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem) {
     if (!ctx) return AMV_ERR_ARG;
     if (bad_mem(mem) || (in_channels != 1 && in_channels != 2) || in_rate <= 0 || out_rate <= 0 || in_rate > (1 << 21) ||
-        out_rate > (1 << 21) || n_in > (1ull << 40))
+        out_rate > (1 << 21) || n_in > (1ull << 40) || in_base > (1ull << 40) || k_start > (1ull << 40))
         return fail(ctx, AMV_ERR_ARG, "bad mem / channels / rates / length");
     if (!n_out) return fail(ctx, AMV_ERR_ARG, "null n_out");
     *n_out = 0;
@@ -1039,15 +1077,24 @@ AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, i
     if (!in || !out) return fail(ctx, AMV_ERR_ARG, "null buffer");
     const int len = resample_filter_length(in_rate, out_rate);
     if (len > 4096) return fail(ctx, AMV_ERR_UNSUPPORTED, "rate ratio needs more than 4096 filter taps");
-    const int64_t k = resample_output_count((int64_t)n_in, in_rate, out_rate);
+    const int64_t total = resample_output_count((int64_t)(in_base + n_in), in_rate, out_rate);
+    const int64_t k = total > (int64_t)k_start ? total - (int64_t)k_start : 0;
     if ((uint64_t)k > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap smaller than the resampled stream (see amv_audio_resample_count)");
+    if (k > 0) {
+        const int64_t first = resample_first_tap((int64_t)k_start, in_rate, out_rate);
+        if (first < 0 ? in_base != 0 : first < (int64_t)in_base)
+            return fail(ctx, AMV_ERR_ARG, "output k_start needs samples in front of in_base");
+    }
     if (mem == AMV_MEM_DEVICE && (((uintptr_t)in & (in_channels == 2 ? 3 : 1)) || ((uintptr_t)out & 1)))
         return fail(ctx, AMV_ERR_ARG, "misaligned sample pointer");
     CK(cudaSetDevice(ctx->device));
     // the polyphase bank of this rate pair (kept until the rates change)
     if (ctx->rs_in_rate != in_rate || ctx->rs_out_rate != out_rate) {
-        std::vector<int16_t> bank((size_t)len * 1024);
-        build_resample_bank(in_rate, out_rate, bank.data());
+        std::vector<int16_t> rows((size_t)len * 1024);
+        build_resample_bank(in_rate, out_rate, rows.data());
+        const int len8 = (len + 7) & ~7;             // device rows are zero-padded to 8 coefficients (amv_resample.cu)
+        std::vector<int16_t> bank((size_t)len8 * 1024, 0);
+        for (int ph = 0; ph < 1024; ph++) memcpy(&bank[(size_t)ph * len8], &rows[(size_t)ph * len], sizeof(int16_t) * len);
         void *p = nullptr;
         int r = ensure(ctx, WS_RS_BANK, bank.size() * sizeof(int16_t), &p);
         if (r != AMV_OK) return r;
@@ -1058,7 +1105,8 @@ AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, i
     }
     const int16_t *d_bank = reinterpret_cast<const int16_t *>(ctx->ws[WS_RS_BANK].p);
     if (mem == AMV_MEM_DEVICE) {
-        launch_audio_resample(in, (int64_t)n_in, in_channels, d_bank, len, in_rate, out_rate, out, k, ctx->stream);
+        launch_audio_resample(in, (int64_t)n_in, (int64_t)in_base, in_channels, d_bank, len, in_rate, out_rate, (int64_t)k_start, out, k,
+                              ctx->stream);
         *n_out = (uint64_t)k;
         return k > 0 ? check_launch(ctx, "audio resampler kernel", 1) : AMV_OK;
     }
@@ -1066,7 +1114,8 @@ AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, i
     TO_DEVICE(WS_H_A, in, sizeof(int16_t) * n_in * in_channels, d_in);
     ENSURE(WS_H_B, sizeof(int16_t) * (k > 0 ? k : 1), d_out);
     if (k > 0) {
-        launch_audio_resample(d_in, (int64_t)n_in, in_channels, d_bank, len, in_rate, out_rate, d_out, k, ctx->stream);
+        launch_audio_resample(d_in, (int64_t)n_in, (int64_t)in_base, in_channels, d_bank, len, in_rate, out_rate, (int64_t)k_start, d_out,
+                              k, ctx->stream);
         int r = check_launch(ctx, "audio resampler kernel", 1);
         if (r != AMV_OK) return r;
         CK(cudaMemcpyAsync(out, d_out, sizeof(int16_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1074,6 +1123,16 @@ AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, i
     CK(cudaStreamSynchronize(ctx->stream));
     *n_out = (uint64_t)k;
     return AMV_OK;
+}
+
+AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, int in_channels, int in_rate, int out_rate,
+                               int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem) {
+    return amv_audio_resample_from(ctx, in, 0, n_in, in_channels, in_rate, out_rate, 0, out, out_cap, n_out, mem);
+}
+
+AMV_API int64_t amv_audio_resample_first_tap(uint64_t k, int in_rate, int out_rate) {
+    if (in_rate <= 0 || out_rate <= 0 || k > (1ull << 40)) return 0;
+    return resample_first_tap((int64_t)k, in_rate, out_rate);
 }
 
 // ---------------------------------------------------------------------------------------- encode

@@ -59,6 +59,9 @@ void launch_convert_range(const uint8_t *y, const uint8_t *u, const uint8_t *v, 
                           int w, int h, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int ols_y, int ols_c, uint64_t ofs_y,
                           uint64_t ofs_c, int dir, cudaStream_t s);
 
+void launch_convert_range_plane(const uint8_t *src, uint8_t *dst, int width, int rows, int n, int ls_in, int ls_out, uint64_t fs_in,
+                                uint64_t fs_out, int dir, bool chroma, cudaStream_t s);
+
 // picture scaler (imgresample.c img_resample) and audio resampler (resample.c audio_resample -> resample2.c av_resample);
 // the banks are built on the host exactly as av_build_filter does and passed as data
 struct ScaleBanks { int16_t h[64]; int16_t v[64]; int h_incr, v_incr; };     // 16 phases x 4 taps each; 16.16 source steps
@@ -69,8 +72,10 @@ int  launch_scale_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v, i
 int  resample_filter_length(int in_rate, int out_rate);
 void build_resample_bank(int in_rate, int out_rate, int16_t *bank /* filter_length * 1024 */);
 int64_t resample_output_count(int64_t n_in, int in_rate, int out_rate);
-void launch_audio_resample(const int16_t *in, int64_t n_in, int in_ch, const int16_t *bank, int len, int in_rate, int out_rate,
-                           int16_t *out, int64_t n_out, cudaStream_t s);
+int64_t resample_first_tap(int64_t k, int in_rate, int out_rate);
+// in holds the stream's samples [in_base, in_base + n_in); outputs k_base .. k_base + n_out - 1 go to out[0 ..]
+void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int in_ch, const int16_t *bank, int len, int in_rate,
+                           int out_rate, int64_t k_base, int16_t *out, int64_t n_out, cudaStream_t s);
 
 // ---- encode
 cudaError_t upload_enc_tables(cudaStream_t s);

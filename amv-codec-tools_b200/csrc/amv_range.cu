@@ -66,6 +66,16 @@ static void launch_plane(const uint8_t *src, uint8_t *dst, int width, int rows, 
     k_range<DIR, CHROMA><<<(unsigned)grid, 256, 0, s>>>(src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, vec ? 1 : 0);
 }
 
+// one plane of `width` x `rows` bytes (chroma: the two chroma tables)
+void launch_convert_range_plane(const uint8_t *src, uint8_t *dst, int width, int rows, int n, int ls_in, int ls_out, uint64_t fs_in,
+                                uint64_t fs_out, int dir, bool chroma, cudaStream_t s) {
+    if (width <= 0 || rows <= 0 || n <= 0) return;
+    if (dir == 0) { if (chroma) launch_plane<0, true>(src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, s);
+                    else        launch_plane<0, false>(src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, s); }
+    else          { if (chroma) launch_plane<1, true>(src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, s);
+                    else        launch_plane<1, false>(src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, s); }
+}
+
 void launch_convert_range(const uint8_t *y, const uint8_t *u, const uint8_t *v, uint8_t *oy, uint8_t *ou, uint8_t *ov, int n,
                           int w, int h, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int ols_y, int ols_c, uint64_t ofs_y,
                           uint64_t ofs_c, int dir, cudaStream_t s) {

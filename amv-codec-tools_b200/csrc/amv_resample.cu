@@ -92,6 +92,14 @@ int64_t resample_output_count(int64_t n_in, int in_rate, int out_rate) {
     return k + 1 > mirrored ? k + 1 : mirrored;
 }
 
+// first input sample output k reads (negative: the mirrored head)
+int64_t resample_first_tap(int64_t k, int in_rate, int out_rate) {
+    const int len = resample_filter_length(in_rate, out_rate);
+    const int64_t index0 = -1024 * (int64_t)((len - 1) / 2);
+    const int64_t index = index0 + (int64_t)(((__int128)k * in_rate * 1024) / out_rate);
+    return index >> 10;
+}
+
 // ------------------------------------------------------------------------------------------ picture scaler
 struct ScaleArgs {
     const uint8_t *src; uint8_t *dst;
@@ -102,7 +110,7 @@ struct ScaleArgs {
 
 __device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }
 
-// one thread: 4 neighbouring output pixels of one row (VEC: one 32-bit store)
+// Direct form: one thread computes 4 neighbouring output pixels of one row from global memory (VEC: one 32-bit store).
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_scale_plane(ScaleArgs a, ScaleBanks banks) {
@@ -152,11 +160,85 @@ k_scale_plane(ScaleArgs a, ScaleBanks banks) {
     }
 }
 
+// Tiled form (the one that normally runs): a block owns a 64 x 16 tile of the output.  Pass 1 filters every source
+// row the tile's vertical taps touch horizontally, once, into shared memory (what the reference keeps in its ring
+// of line buffers); pass 2 runs the vertical filter from there, 4 pixels per thread.  Against the direct form this
+// drops the horizontal work from 4 rows per output row to (rows touched) / 16 and turns 16 byte loads per pixel
+// into (rows touched) / 4 of them plus one 32-bit shared-memory read.
+constexpr int kTileW = 64, kTileH = 16, kTileRowsMax = 192;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y) {
+    __shared__ int2 s_h[16], s_v[16];
+    __shared__ __align__(16) uint8_t s_line[kTileRowsMax][kTileW];
+    if (threadIdx.x < 16) {
+        const int16_t *h = banks.h + 4 * threadIdx.x, *v = banks.v + 4 * threadIdx.x;
+        s_h[threadIdx.x] = make_int2((uint16_t)h[0] | ((int)h[1] << 16), (uint16_t)h[2] | ((int)h[3] << 16));
+        s_v[threadIdx.x] = make_int2((uint16_t)v[0] | ((int)v[1] << 16), (uint16_t)v[2] | ((int)v[3] << 16));
+    }
+    __syncthreads();
+    const int tx = blockIdx.x % tiles_x, tyf = blockIdx.x / tiles_x;
+    const int ty = tyf % tiles_y, f = tyf / tiles_y;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int y_last = min(y0 + kTileH, a.oh) - 1;
+    const int r_lo = ((2 * 65536 + y0 * a.v_incr) >> 16) - 3;
+    const int nrows = ((2 * 65536 + y_last * a.v_incr) >> 16) - r_lo + 1;          // <= kTileRowsMax (checked by the launcher)
+    const uint8_t *in = a.src + (uint64_t)f * a.ifs;
+    {   // pass 1: column `col` of the tile for rows threadIdx.x / 64, + 4, + 8, ...
+        const int col = threadIdx.x & (kTileW - 1);
+        const int sx = -65536 + (x0 + col) * a.h_incr, left = sx >> 16;
+        const int2 fh = s_h[(sx >> 12) & 15];
+        const int h0 = (int16_t)fh.x, h1 = fh.x >> 16, h2 = (int16_t)fh.y, h3 = fh.y >> 16;
+        const int c0 = min(max(left, 0), a.iw - 1), c1 = min(max(left + 1, 0), a.iw - 1);
+        const int c2 = min(max(left + 2, 0), a.iw - 1), c3 = min(max(left + 3, 0), a.iw - 1);
+#pragma unroll 4
+        for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
+            const uint8_t *row = in + (int64_t)a.ils * min(max(r_lo + r, 0), a.ih - 1);
+            s_line[r][col] = (uint8_t)clip255((__ldg(row + c0) * h0 + __ldg(row + c1) * h1 + __ldg(row + c2) * h2 + __ldg(row + c3) * h3) >> 8);
+        }
+    }
+    __syncthreads();
+    {   // pass 2
+        const int y = y0 + (threadIdx.x >> 4), cx = (threadIdx.x & 15) * 4;
+        if (y > y_last || x0 + cx >= a.ow) return;
+        const int sy = 2 * 65536 + y * a.v_incr;
+        const int2 fv = s_v[(sy >> 12) & 15];
+        const int fv0 = (int16_t)fv.x, fv1 = fv.x >> 16, fv2 = (int16_t)fv.y, fv3 = fv.y >> 16;
+        const int r = (sy >> 16) - 3 - r_lo;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&s_line[r][cx]), w1 = *reinterpret_cast<const uint32_t *>(&s_line[r + 1][cx]);
+        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(&s_line[r + 2][cx]), w3 = *reinterpret_cast<const uint32_t *>(&s_line[r + 3][cx]);
+        uint32_t word = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int v = (int)((w0 >> (8 * p)) & 0xff) * fv0 + (int)((w1 >> (8 * p)) & 0xff) * fv1 +
+                          (int)((w2 >> (8 * p)) & 0xff) * fv2 + (int)((w3 >> (8 * p)) & 0xff) * fv3;
+            word |= (uint32_t)clip255(v >> 8) << (8 * p);
+        }
+        uint8_t *d = a.dst + (uint64_t)f * a.ofs + (int64_t)y * a.ols + x0 + cx;
+        if (VEC) *reinterpret_cast<uint32_t *>(d) = word;
+        else {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (x0 + cx + p < a.ow) d[p] = (uint8_t)(word >> (8 * p));
+        }
+    }
+}
+
 static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih, int ow, int oh, int ils, int ols, uint64_t ifs,
                                uint64_t ofs, int n, const ScaleBanks &b, cudaStream_t s) {
     if (iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return;       // a 1-pixel-wide picture has no chroma to scale
     ScaleArgs a{ src, dst, iw, ih, ow, oh, ils, ols, ifs, ofs, n, b.h_incr, b.v_incr };
     const bool vec = (ow & 3) == 0 && ((((uintptr_t)dst | (uintptr_t)ols | ofs) & 3) == 0);
+    const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + kTileH - 1) / kTileH;
+    const int64_t tiles = (int64_t)tiles_x * tiles_y * n;
+    const int64_t rows_touched = (((int64_t)(kTileH - 1) * b.v_incr) >> 16) + 5;
+    if (rows_touched <= kTileRowsMax && tiles <= 0x7fffffff) {
+        if (vec) k_scale_tile<true><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y);
+        else     k_scale_tile<false><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y);
+        return;
+    }
+    // extreme reductions (more than 12 source rows per output row): the direct form
     const int64_t total = (int64_t)((ow + 3) >> 2) * oh * n;
     int64_t grid = (total + 255) / 256;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
@@ -186,40 +268,102 @@ __device__ __forceinline__ int mono_at(const int16_t *in, int64_t i) {
     return (int)(int16_t)(((int)(int16_t)(lr & 0xffff) + ((int)lr >> 16)) >> 1);
 }
 
-// one thread per output sample k; index(k) = index0 + floor(k * in_rate * 1024 / out_rate)
+// The device bank holds every phase row padded with zero coefficients to a multiple of 8 (len8), so a row starts on a
+// 16-byte boundary and is fetched 8 coefficients at a time.
+__device__ __forceinline__ int16_t round_sat(uint32_t acc) {
+    const int val = ((int)(acc + (1u << 14))) >> 15;
+    return (int16_t)max(-32768, min(32767, val));
+}
+
+// Direct form: one thread per output sample k straight from global memory; index(k) = index0 + floor(k * in_rate * 1024 / out_rate).
+template <int CH>
+__device__ __forceinline__ uint32_t taps_direct(const int16_t *__restrict__ in, int64_t n_in, const int16_t *__restrict__ f, int len,
+                                                int64_t first, int64_t in_base) {
+    uint32_t acc = 0;
+    if (first >= 0) {
+        for (int i = 0; i < len; i++) acc += (uint32_t)(mono_at<CH>(in, first - in_base + i) * (int)__ldg(f + i));
+    } else {
+        for (int i = 0; i < len; i++) {                       // left of sample 0 the reference mirrors: src[|i| % src_size]
+            int64_t p = first + i;
+            if (p < 0) p = -p;
+            acc += (uint32_t)(mono_at<CH>(in, p % n_in) * (int)__ldg(f + i));
+        }
+    }
+    return acc;
+}
 template <int CH>
 __global__ void __launch_bounds__(256)
-k_audio_resample(const int16_t *__restrict__ in, int64_t n_in, const int16_t *__restrict__ bank, int len, int64_t index0,
-                 uint64_t dst_incr /* in_rate * 1024 */, uint32_t src_incr /* out_rate */, int16_t *__restrict__ out, int64_t n_out) {
+k_audio_resample(const int16_t *__restrict__ in, int64_t n_in, int64_t in_base, const int16_t *__restrict__ bank, int len, int len8,
+                 int64_t index0, uint64_t dst_incr /* in_rate * 1024 */, uint32_t src_incr /* out_rate */, int64_t k_base,
+                 int16_t *__restrict__ out, int64_t n_out) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_out; k += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t index = index0 + (int64_t)(((uint64_t)k * dst_incr) / src_incr);
-        const int64_t first = index >> 10;
-        const int16_t *f = bank + (size_t)len * (size_t)(index & 1023);
-        uint32_t acc = 0;
-        if (first >= 0) {
-            for (int i = 0; i < len; i++) acc += (uint32_t)(mono_at<CH>(in, first + i) * (int)__ldg(f + i));
-        } else {
-            for (int i = 0; i < len; i++) {                       // left of sample 0 the reference mirrors: src[|i| % src_size]
-                int64_t p = first + i;
-                if (p < 0) p = -p;
-                acc += (uint32_t)(mono_at<CH>(in, p % n_in) * (int)__ldg(f + i));
-            }
-        }
-        const int val = ((int)(acc + (1u << 14))) >> 15;
-        out[k] = (int16_t)max(-32768, min(32767, val));
+        const int64_t index = index0 + (int64_t)(((uint64_t)(k_base + k) * dst_incr) / src_incr);
+        out[k] = round_sat(taps_direct<CH>(in, n_in, bank + (size_t)len8 * (size_t)(index & 1023), len, index >> 10, in_base));
     }
 }
 
-void launch_audio_resample(const int16_t *in, int64_t n_in, int in_ch, const int16_t *bank, int len, int in_rate, int out_rate,
-                           int16_t *out, int64_t n_out, cudaStream_t s) {
+// Tiled form (the one that normally runs): a block owns 256 consecutive outputs.  Their taps cover one contiguous
+// stretch of the input, which the block loads once, coalesced and already mixed down to one channel, into shared
+// memory as 32-bit samples; each thread then walks its phase row 8 coefficients per 128-bit load.
+constexpr int kWinMax = 6144;          // samples of shared memory (24 KB)
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_audio_resample_tile(const int16_t *__restrict__ in, int64_t n_in, int64_t in_base, const int16_t *__restrict__ bank, int len, int len8,
+                      int64_t index0, uint64_t dst_incr, uint32_t src_incr, uint32_t step_q, uint32_t step_r, int64_t k_base,
+                      int16_t *__restrict__ out, int64_t n_out) {
+    __shared__ int s_win[kWinMax];
+    const int64_t k0 = (int64_t)blockIdx.x * 256, k = k0 + threadIdx.x;
+    const int t_hi = (int)min((int64_t)255, n_out - 1 - k0);
+    // index(k0 + t) = index(k0) + t*q + floor((rem + t*r) / S) with dst_incr = q*S + r: one 64-bit division per block,
+    // 32-bit ones per thread (rem < S <= 2^21, t*r < 2^29)
+    const uint64_t p0 = (uint64_t)(k_base + k0) * dst_incr, base = p0 / src_incr;
+    const uint32_t rem = (uint32_t)(p0 - base * src_incr);
+    const int64_t index_lo = index0 + (int64_t)base;
+    const int t = min((int)threadIdx.x, t_hi);
+    const int64_t index = index_lo + (int64_t)t * step_q + (rem + (uint32_t)t * step_r) / src_incr;
+    const int64_t first_lo = index_lo >> 10;
+    const int64_t first_hi = (index_lo + (int64_t)t_hi * step_q + (rem + (uint32_t)t_hi * step_r) / src_incr) >> 10;
+    const int16_t *f = bank + (size_t)len8 * (size_t)(index & 1023);
+    if (first_lo < 0) {                 // the block that holds the mirrored head of the stream
+        if (k < n_out) out[k] = round_sat(taps_direct<CH>(in, n_in, f, len, index >> 10, in_base));
+        return;
+    }
+    const int wlen = (int)(first_hi - first_lo) + len8;          // <= kWinMax (checked by the launcher)
+    for (int j = threadIdx.x; j < wlen; j += 256)
+        s_win[j] = first_lo - in_base + j < n_in ? mono_at<CH>(in, first_lo - in_base + j) : 0;       // only zero coefficients reach past the end
+    __syncthreads();
+    if (k >= n_out) return;
+    const int *w = s_win + (int)((index >> 10) - first_lo);
+    uint32_t acc = 0;
+    for (int i = 0; i < len8; i += 8) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(f + i));
+        acc += (uint32_t)(w[i] * (int)(int16_t)c.x) + (uint32_t)(w[i + 1] * ((int)c.x >> 16));
+        acc += (uint32_t)(w[i + 2] * (int)(int16_t)c.y) + (uint32_t)(w[i + 3] * ((int)c.y >> 16));
+        acc += (uint32_t)(w[i + 4] * (int)(int16_t)c.z) + (uint32_t)(w[i + 5] * ((int)c.z >> 16));
+        acc += (uint32_t)(w[i + 6] * (int)(int16_t)c.w) + (uint32_t)(w[i + 7] * ((int)c.w >> 16));
+    }
+    out[k] = round_sat(acc);
+}
+
+void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int in_ch, const int16_t *bank, int len, int in_rate,
+                           int out_rate, int64_t k_base, int16_t *out, int64_t n_out, cudaStream_t s) {
     if (n_out <= 0) return;
+    const int len8 = (len + 7) & ~7;
     const int64_t index0 = -1024 * (int64_t)((len - 1) / 2);
-    int64_t grid = (n_out + 255) / 256;
+    const uint64_t D = (uint64_t)in_rate * 1024;
+    const uint32_t S = (uint32_t)out_rate;
+    const int64_t span = (int64_t)((255 * D) / S >> 10) + 2 + len8;        // input samples 256 consecutive outputs touch
+    const int64_t blocks = (n_out + 255) / 256;
+    if (span <= kWinMax && blocks <= 0x7fffffff) {
+        if (in_ch == 2) k_audio_resample_tile<2><<<(unsigned)blocks, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
+        else            k_audio_resample_tile<1><<<(unsigned)blocks, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
+        return;
+    }
+    int64_t grid = blocks;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    if (in_ch == 2)
-        k_audio_resample<2><<<(unsigned)grid, 256, 0, s>>>(in, n_in, bank, len, index0, (uint64_t)in_rate * 1024, (uint32_t)out_rate, out, n_out);
-    else
-        k_audio_resample<1><<<(unsigned)grid, 256, 0, s>>>(in, n_in, bank, len, index0, (uint64_t)in_rate * 1024, (uint32_t)out_rate, out, n_out);
+    if (in_ch == 2) k_audio_resample<2><<<(unsigned)grid, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, k_base, out, n_out);
+    else            k_audio_resample<1><<<(unsigned)grid, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, k_base, out, n_out);
 }
 
 }  // namespace amv

@@ -11,12 +11,13 @@ OBJ="$ROOT/oracle/_ref/obj"
 [ -d "$OBJ" ] || "$ROOT/oracle/build_ref.sh" > /dev/null
 mkdir -p "$HERE/_build"
 CFLAGS="-O2 -std=gnu99 -fgnu89-inline -fcommon -w -DHAVE_AV_CONFIG_H -D_GNU_SOURCE \
- -I$ROOT/oracle/_ref/cfg -I$REF -I$REF/libavcodec -I$REF/libavutil -I$ROOT/include"
+ -I$ROOT/oracle/_ref/cfg -I$REF -I$REF/libavcodec -I$REF/libavutil -I$REF/libswscale -I$ROOT/include"
 gcc $CFLAGS -c "$HERE/ffmpeg/amvcuda_codecs.c" -o "$HERE/_build/amvcuda_codecs.o"
+gcc $CFLAGS -c "$HERE/ffmpeg/amvcuda_resample.c" -o "$HERE/_build/amvcuda_resample.o"
 # the checker is an API *user* of libavcodec (no HAVE_AV_CONFIG_H: that poisons printf/malloc)
 gcc ${CFLAGS/-DHAVE_AV_CONFIG_H/} -c "$HERE/ffmpeg/dropin_check.c" -o "$HERE/_build/dropin_check.o"
 OBJS=$(ls "$OBJ"/avc_*.o "$OBJ"/avu_*.o)
-gcc -o "$HERE/_build/dropin_check" "$HERE/_build/dropin_check.o" "$HERE/_build/amvcuda_codecs.o" $OBJS \
+gcc -o "$HERE/_build/dropin_check" "$HERE/_build/dropin_check.o" "$HERE/_build/amvcuda_codecs.o" "$HERE/_build/amvcuda_resample.o" $OBJS \
     -L"$HERE/../lib" -lamvcuda -Wl,-rpath,'$ORIGIN/../../lib' -lm
 echo "built $HERE/_build/dropin_check"
 

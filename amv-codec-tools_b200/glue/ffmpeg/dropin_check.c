@@ -11,6 +11,15 @@
 #include <string.h>
 #include <math.h>
 #include "avcodec.h"
+#include "swscale.h"
+
+struct SwsContext *amvcuda_sws_getContext(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
+                                          SwsFilter *srcFilter, SwsFilter *dstFilter, double *param);
+void amvcuda_sws_freeContext(struct SwsContext *ctx);
+int amvcuda_sws_scale(struct SwsContext *ctx, uint8_t *src[], int srcStride[], int srcSliceY, int srcSliceH, uint8_t *dst[], int dstStride[]);
+ReSampleContext *amvcuda_audio_resample_init(int output_channels, int input_channels, int output_rate, int input_rate);
+int amvcuda_audio_resample(ReSampleContext *s, short *output, short *input, int nb_samples);
+void amvcuda_audio_resample_close(ReSampleContext *s);
 
 extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder, sp5x_decoder, mjpeg_decoder, mjpeg_encoder;
 extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_decoder, amvcuda_adpcm_ima_amv_encoder,
@@ -207,6 +216,63 @@ int main(int argc, char **argv)
         if (ra || rb) { printf("FAIL: audio returned %d / %d\n", ra, rb); return 5; }
         if (cba != cbb || memcmp(ca, cb, cba) || sa != sb || memcmp(oa, ob, sa * 2)) { printf("FAIL: audio differs\n"); fail = 1; }
         printf("audio %d samples (trellis %d): %d chunk bytes, %d decoded samples %s\n", total, g_trellis, cba, sa, fail ? "DIFFER" : "identical");
+    }
+    {   /* the `-s WxH` scaler the way ffmpeg.c drives it: sws_getContext once, sws_scale per frame (ffmpeg.c:757,1684) */
+        static const int dims[][4] = { { 352, 288, 208, 176 }, { 160, 120, 320, 240 }, { 322, 244, 160, 120 }, { 208, 176, 208, 176 } };
+        int d, t, p, fm;
+        for (fm = 0; fm < 4; fm++)
+        for (d = 0; d < 4; d++) {
+            const int sf = fm & 1 ? PIX_FMT_YUVJ420P : PIX_FMT_YUV420P, df = fm & 2 ? PIX_FMT_YUVJ420P : PIX_FMT_YUV420P;
+            const int iw = dims[d][0], ih = dims[d][1], ow = dims[d][2], oh = dims[d][3];
+            const int icw = (iw + 1) / 2, ich = (ih + 1) / 2, ocw = (ow + 1) / 2, och = (oh + 1) / 2, ils = iw + 32, ols = ow + 16;
+            uint8_t *src[4] = { malloc(ils * ih), malloc((ils / 2) * ich), malloc((ils / 2) * ich), NULL };
+            uint8_t *da[4] = { malloc(ols * oh), malloc((ols / 2) * och), malloc((ols / 2) * och), NULL };
+            uint8_t *db[4] = { malloc(ols * oh), malloc((ols / 2) * och), malloc((ols / 2) * och), NULL };
+            int sst[4] = { ils, ils / 2, ils / 2, 0 }, dst[4] = { ols, ols / 2, ols / 2, 0 }, sfail = 0;
+            struct SwsContext *ca = amvcuda_sws_getContext(iw, ih, sf, ow, oh, df, SWS_BICUBIC, NULL, NULL, NULL);
+            struct SwsContext *cb = sws_getContext(iw, ih, sf, ow, oh, df, SWS_BICUBIC, NULL, NULL, NULL);
+            if (!ca || !cb) { printf("FAIL: sws_getContext\n"); return 10; }
+            for (t = 0; t < 3; t++) {
+                for (p = 0; p < 3; p++) {
+                    int k, nb = sst[p] * (p ? ich : ih);
+                    for (k = 0; k < nb; k++) src[p][k] = (uint8_t)(t == 2 ? (rnd() & 1) * 255 : rnd());
+                    memset(da[p], 0x55, dst[p] * (p ? och : oh)); memset(db[p], 0x55, dst[p] * (p ? och : oh));
+                }
+                if (amvcuda_sws_scale(ca, src, sst, 0, ih, da, dst) || sws_scale(cb, src, sst, 0, ih, db, dst)) { printf("FAIL: sws_scale\n"); return 10; }
+                for (p = 0; p < 3; p++) if (memcmp(da[p], db[p], dst[p] * (p ? och : oh))) sfail = 1;
+            }
+            printf("scale %dx%d %s -> %dx%d %s x3: planes %s\n", iw, ih, fm & 1 ? "yuvj420p" : "yuv420p", ow, oh, fm & 2 ? "yuvj420p" : "yuv420p",
+                   sfail ? "DIFFER" : "identical");
+            if (sfail) fail = 1;
+            amvcuda_sws_freeContext(ca); sws_freeContext(cb);
+            (void)icw; (void)ocw;
+        }
+    }
+    {   /* the audio resampler the way do_audio_out drives it: one call per decoded packet, ragged packet sizes */
+        static const int cfg[][3] = { { 44100, 2, 1152 }, { 48000, 1, 1024 }, { 8000, 1, 160 }, { 32000, 2, 4608 }, { 22050, 2, 7 } };
+        int d, k;
+        for (d = 0; d < 5; d++) {
+            const int rate = cfg[d][0], ch = cfg[d][1], pkt = cfg[d][2], total = pkt * 37 + 13;
+            short *pcm = malloc(sizeof(short) * total * ch), *oa = malloc(sizeof(short) * (total * 3 + 4096)), *ob = malloc(sizeof(short) * (total * 3 + 4096));
+            short *ta = malloc(sizeof(short) * (pkt * 16 + 4096)), *tb = malloc(sizeof(short) * (pkt * 16 + 4096));
+            ReSampleContext *ra = amvcuda_audio_resample_init(1, ch, 22050, rate), *rb = audio_resample_init(1, ch, 22050, rate);
+            int na = 0, nb = 0, pos = 0, afail = 0, call = 0;
+            if (!ra || !rb) { printf("FAIL: audio_resample_init\n"); return 11; }
+            for (k = 0; k < total * ch; k++) pcm[k] = (short)(k % 97 < 3 ? (rnd() & 1 ? 32767 : -32768) : 9000 * sin(k * 0.0731) + (int)(rnd() % 3000) - 1500);
+            while (pos < total) {
+                int n = call % 5 == 4 ? pkt / 3 + 1 : pkt, ka, kb;        /* every fifth packet is a short one */
+                if (n > total - pos) n = total - pos;
+                ka = amvcuda_audio_resample(ra, ta, pcm + pos * ch, n);
+                kb = audio_resample(rb, tb, pcm + pos * ch, n);
+                if (ka != kb || ka < 0 || memcmp(ta, tb, sizeof(short) * ka)) afail = 1;
+                if (ka > 0) { memcpy(oa + na, ta, sizeof(short) * ka); na += ka; }
+                if (kb > 0) { memcpy(ob + nb, tb, sizeof(short) * kb); nb += kb; }
+                pos += n; call++;
+            }
+            printf("resample %d Hz x%d -> 22050 mono, %d calls: %d samples, per-call counts and samples %s\n", rate, ch, call, nb, afail ? "DIFFER" : "identical");
+            if (afail) fail = 1;
+            amvcuda_audio_resample_close(ra); audio_resample_close(rb);
+        }
     }
     printf(fail ? "DROP-IN CHECK FAILED\n" : "DROP-IN CHECK OK\n");
     return fail;

@@ -236,6 +236,25 @@ AMV_API int amv_scale_frames(amv_ctx *ctx,
                              int ow, int oh, int mem);
 
 /*
+ * The same with the pixel-format handling of the fork's sws_scale around it (imgresample.c:599-690): the
+ * scaler itself only knows PIX_FMT_YUV420P, so a YUVJ420P source is first taken to YUV420P and a YUVJ420P
+ * destination is produced from the scaled YUV420P picture, both through img_convert (= amv_convert_range,
+ * dir 1 resp. dir 0).  The AMV encoder takes YUVJ420P, so `ffmpeg -s WxH ... -f amv` always runs the second
+ * conversion, and the first one too when the source decoder outputs YUVJ420P (mjpeg, amv).
+ * flags: AMV_SCALE_IN_JPEG_RANGE (source is YUVJ420P), AMV_SCALE_OUT_JPEG_RANGE (destination is YUVJ420P).
+ * The conversions cover the area the scaler reads / writes.  The source planes are never modified.
+ */
+#define AMV_SCALE_IN_JPEG_RANGE  1
+#define AMV_SCALE_OUT_JPEG_RANGE 2
+AMV_API int amv_scale_frames_ex(amv_ctx *ctx,
+                                const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                                int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                                int n, int iw, int ih,
+                                uint8_t *oy, uint8_t *ou, uint8_t *ov,
+                                int ols_y, int ols_c, uint64_t ofs_y, uint64_t ofs_c,
+                                int ow, int oh, int flags, int mem);
+
+/*
  * The audio resampler of the reference's do_audio_out (ffmpeg.c:501-505) in front of the ADPCM encoder
  * (which takes 22050 Hz mono only, adpcm.c:190-199): audio_resample_init(1, in_channels, out_rate, in_rate)
  * + audio_resample (libavcodec/resample.c:93-235; two channels are averaged, :53-75) -> av_resample
@@ -252,6 +271,21 @@ AMV_API int amv_audio_resample(amv_ctx *ctx,
                                const int16_t *in, uint64_t n_in, int in_channels,
                                int in_rate, int out_rate,
                                int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem);
+/*
+ * The same resampler over a window of a longer stream, for callers that feed it packet by packet the way
+ * ffmpeg.c feeds audio_resample (which keeps the unconsumed tail in ReSampleContext.temp and the position in
+ * AVResampleContext.index / frac, resample.c:214-216, resample2.c:303-313): `in` holds the stream's samples
+ * [in_base, in_base + n_in) and the call writes outputs k_start, k_start + 1, ... up to the last one whose taps
+ * end inside the window, i.e. amv_audio_resample_count(in_base + n_in, ...) - k_start samples.
+ * amv_audio_resample_first_tap(k, ...) is the first input sample output k reads (negative for the mirrored head
+ * of the stream, which needs in_base == 0): a caller may drop everything in front of first_tap(next k).
+ * glue/ffmpeg/amvcuda_codecs.c builds its audio_resample replacement on these two.
+ */
+AMV_API int amv_audio_resample_from(amv_ctx *ctx,
+                                    const int16_t *in, uint64_t in_base, uint64_t n_in, int in_channels,
+                                    int in_rate, int out_rate, uint64_t k_start,
+                                    int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem);
+AMV_API int64_t amv_audio_resample_first_tap(uint64_t k, int in_rate, int out_rate);
 
 /*
  * The filter banks the two stages above run on, as built on the host at call time (no device involved):

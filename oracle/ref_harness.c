@@ -342,3 +342,25 @@ int amvref_resample_bank(int out_rate, int in_rate, int16_t *bank, int cap, int 
     av_resample_close(c);
     return total;
 }
+
+/* the same through the fork's sws_getContext / sws_scale (imgresample.c:515-690), the entry ffmpeg.c uses: with
+ * jpeg_in / jpeg_out the source / destination format is PIX_FMT_YUVJ420P instead of PIX_FMT_YUV420P, which makes
+ * sws_scale wrap the scaler in img_convert steps.  Tight planes, even sizes. */
+#include "swscale.h"
+int amvref_sws_scale(const uint8_t *y, const uint8_t *u, const uint8_t *v, int n, int iw, int ih, int ow, int oh,
+                     int jpeg_in, int jpeg_out, uint8_t *oy, uint8_t *ou, uint8_t *ov)
+{
+    ref_init();
+    int icw = (iw + 1) >> 1, ich = (ih + 1) >> 1, ocw = (ow + 1) >> 1, och = (oh + 1) >> 1, i;
+    struct SwsContext *c = sws_getContext(iw, ih, jpeg_in ? PIX_FMT_YUVJ420P : PIX_FMT_YUV420P, ow, oh,
+                                          jpeg_out ? PIX_FMT_YUVJ420P : PIX_FMT_YUV420P, SWS_BICUBIC, NULL, NULL, NULL);
+    if (!c) return -1;
+    for (i = 0; i < n; i++) {
+        uint8_t *src[4] = { (uint8_t *)y + (size_t)i * iw * ih, (uint8_t *)u + (size_t)i * icw * ich, (uint8_t *)v + (size_t)i * icw * ich, NULL };
+        uint8_t *dst[4] = { oy + (size_t)i * ow * oh, ou + (size_t)i * ocw * och, ov + (size_t)i * ocw * och, NULL };
+        int sst[4] = { iw, icw, icw, 0 }, dstr[4] = { ow, ocw, ocw, 0 };
+        if (sws_scale(c, src, sst, 0, ih, dst, dstr) < 0) { sws_freeContext(c); return -2; }
+    }
+    sws_freeContext(c);
+    return n;
+}

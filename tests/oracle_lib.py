@@ -184,6 +184,16 @@ class Oracle(_AmvlibOracleMixin):
             raise RuntimeError("oracle scaler failed")
         return oy, ou, ov
 
+    def sws_scale(self, y, u, v, ow, oh, jpeg_in, jpeg_out):
+        """the fork's sws_scale as a composition of the restated stages (imgresample.c:617-682): img_convert to
+        YUV420P in front of the scaler for a YUVJ420P source, img_convert to YUVJ420P behind it (even sizes)"""
+        if jpeg_in:
+            y, u, v = self.convert_range(y, u, v, 1)
+        y, u, v = self.scale_frames(y, u, v, ow, oh)
+        if jpeg_out:
+            y, u, v = self.convert_range(y, u, v, 0)
+        return y, u, v
+
     def scale_banks(self, iw, ih, ow, oh):
         hb, vb = np.zeros((16, 4), np.int16), np.zeros((16, 4), np.int16)
         self.lib.amvo_scale_banks(iw, ih, ow, oh, _p(hb), _p(vb))
@@ -452,6 +462,16 @@ class Ref:
         oy, ou, ov = np.full((n, oh, ow), fill, np.uint8), np.full((n, och, ocw), fill, np.uint8), np.full((n, och, ocw), fill, np.uint8)
         if self.lib.amvref_img_resample(_p(y), _p(u), _p(v), n, iw, ih, ow, oh, _p(oy), _p(ou), _p(ov)) != n:
             raise RuntimeError("reference img_resample failed")
+        return oy, ou, ov
+
+    def sws_scale(self, y, u, v, ow, oh, jpeg_in, jpeg_out):
+        """sws_getContext + sws_scale of the fork (what ffmpeg.c calls for -s): YUV420P / YUVJ420P on either side"""
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        n, ih, iw = y.shape
+        ocw, och = chroma_dims(ow, oh)
+        oy, ou, ov = np.zeros((n, oh, ow), np.uint8), np.zeros((n, och, ocw), np.uint8), np.zeros((n, och, ocw), np.uint8)
+        if self.lib.amvref_sws_scale(_p(y), _p(u), _p(v), n, iw, ih, ow, oh, int(jpeg_in), int(jpeg_out), _p(oy), _p(ou), _p(ov)) != n:
+            raise RuntimeError("reference sws_scale failed")
         return oy, ou, ov
 
     def audio_resample(self, pcm, in_channels, in_rate, out_rate=22050, chunk=4096):

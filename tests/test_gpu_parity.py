@@ -750,6 +750,34 @@ def test_scaler_identical(ctx, oracle, dims):
             assert np.array_equal(a[:, :, :ww], wn) and (a[:, :, ww:] == 9).all()
 
 
+@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("dims", [(352, 288, 208, 176), (160, 120, 320, 240)])
+def test_scaler_with_range_steps(ctx, oracle, dims, flags):
+    """amv_scale_frames_ex: the img_convert steps the fork's sws_scale puts around the scaler for YUVJ420P sides;
+    host buffers and device planes (the source planes stay as they were)"""
+    import torch
+    iw, ih, ow, oh = dims
+    rng = np.random.default_rng(ow + flags)
+    n = 3
+    y = rng.integers(0, 256, (n, ih, iw), dtype=np.uint8)
+    u = rng.integers(0, 256, (n, ih // 2, iw // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (n, ih // 2, iw // 2), dtype=np.uint8)
+    want = oracle.sws_scale(y, u, v, ow, oh, flags & 1, flags & 2)
+    got = ctx.scale_frames(y, u, v, ow, oh, flags=flags)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    dev = torch.device("cuda", 0)
+    dY, dU, dV = (torch.from_numpy(a).to(dev) for a in (y, u, v))
+    oY = torch.zeros((n, oh, ow), dtype=torch.uint8, device=dev)
+    oU = torch.zeros((n, oh // 2, ow // 2), dtype=torch.uint8, device=dev)
+    oV = torch.zeros((n, oh // 2, ow // 2), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    ctx.scale_frames_raw(dY, dU, dV, iw, iw // 2, iw * ih, iw * ih // 4, n, iw, ih, oY, oU, oV, ow, ow // 2, ow * oh, ow * oh // 4,
+                         ow, oh, amv.MEM_DEVICE, flags)
+    ctx.sync()
+    assert all(np.array_equal(t.cpu().numpy(), b) for t, b in zip((oY, oU, oV), want))
+    assert all(np.array_equal(t.cpu().numpy(), b) for t, b in zip((dY, dU, dV), (y, u, v)))
+
+
 def test_scaler_feeds_the_encoder(ctx, oracle):
     """`-s 208x176` in front of the AMV encoder: scaled frames encode to the packets the oracle makes of the oracle's scaling"""
     y, u, v = synth_frames(4, 352, 288, seed=5, kind="sinus")
@@ -789,6 +817,21 @@ def test_audio_resampler_identical(ctx, oracle, rate, ch, n, kind):
     ctx.sync()
     a = d_out.cpu().numpy()
     assert k == len(want) and np.array_equal(a[:k], want) and (a[k:] == 77).all()
+
+
+@pytest.mark.parametrize("rate,ch", [(44100, 2), (48000, 1), (8000, 1), (96000, 2)])
+def test_audio_resampler_packet_feed(ctx, oracle, rate, ch):
+    """amv_audio_resample_from over a sliding window (what the audio_resample shim of glue/ffmpeg does): ragged packets,
+    some shorter than the filter, give the stream's outputs in order, each exactly once"""
+    rng = np.random.default_rng(rate)
+    pcm = synth_pcm(60000 * ch, seed=rate, kind="noise")
+    cuts = np.sort(rng.choice(np.arange(1, 60000), 40, replace=False))
+    # the first packet covers the mirrored taps of the stream's head (the reference mirrors modulo the first call's size)
+    cuts = np.concatenate([[0, 100, 105, 109], cuts[cuts > 109], [60000]])
+    cuts = np.unique(cuts)
+    packets = [pcm[a * ch:b * ch] for a, b in zip(cuts[:-1], cuts[1:])]
+    outs = ctx.audio_resample_packets(packets, ch, rate, 22050)
+    assert np.array_equal(np.concatenate(outs), oracle.audio_resample(pcm, ch, rate, 22050))
 
 
 def test_audio_resampler_feeds_the_adpcm_encoder(ctx, oracle):

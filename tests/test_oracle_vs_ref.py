@@ -427,3 +427,16 @@ def test_audio_resampler_matches_audio_resample(oracle, ref, rate, ch, n, chunk,
     pcm = synth_pcm(n * ch, seed=rate + n, kind=kind)
     assert np.array_equal(ref.audio_resample(pcm, ch, rate, 22050, chunk=chunk), oracle.audio_resample(pcm, ch, rate, 22050))
     assert np.array_equal(ref.resample_bank(rate, 22050), oracle.resample_bank(rate, 22050))
+
+
+@pytest.mark.parametrize("jpeg_in,jpeg_out", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("dims", [(352, 288, 208, 176), (160, 120, 320, 240), (640, 480, 320, 240)])
+def test_sws_scale_is_convert_scale_convert(oracle, ref, dims, jpeg_in, jpeg_out):
+    """the entry ffmpeg.c calls: sws_scale scales in YUV420P only and wraps YUVJ420P sides in img_convert"""
+    iw, ih, ow, oh = dims
+    rng = np.random.default_rng(ow + jpeg_in)
+    y = rng.integers(0, 256, (2, ih, iw), dtype=np.uint8)
+    u = rng.integers(0, 256, (2, ih // 2, iw // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (2, ih // 2, iw // 2), dtype=np.uint8)
+    for a, b in zip(ref.sws_scale(y, u, v, ow, oh, jpeg_in, jpeg_out), oracle.sws_scale(y, u, v, ow, oh, jpeg_in, jpeg_out)):
+        assert np.array_equal(a, b)
