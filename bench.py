@@ -223,11 +223,12 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)      # the e2e leg is a two-stage pipeline over the steps: K + 1 stage times for K steps
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="amvcuda", choices=["amvcuda", "reference"])
     ap.add_argument("--frames", type=int, default=100000, help="frames per GPU per step (BASELINE config 2: 100k)")
     ap.add_argument("--e2e-frames", type=int, default=16384, help="frames per GPU per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-sub", type=int, default=1, help="sub-batches a step of the e2e leg travels in (measured: 1 is best, every host call has a fixed ~2 ms)")
     ap.add_argument("--ref-frames-per-worker", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--audit", type=int, default=64, help="frames re-checked after the run (golden vectors + self round trip)")
@@ -328,29 +329,37 @@ def main():
     del DY, DU, DV
     torch.cuda.empty_cache()
 
-    # Two contexts, one per host thread, form a two-stage pipeline over the steps: while step k's packets
-    # are decoded (D2H-heavy) step k+1 is already being encoded (H2D-heavy), so both PCIe directions stay
-    # busy.  Every step still copies its own inputs in and its own results out inside the timed region;
-    # packets / offsets / sizes are double-buffered between the stages.
+    # Two contexts, one per host thread, form a two-stage pipeline: the step's frames travel in `nsub` sub-batches,
+    # and while sub-batch j's packets are decoded (D2H-heavy) sub-batch j+1 is already being encoded (H2D-heavy),
+    # so both PCIe directions stay busy.  Every step still copies all of its own inputs in and all of its own
+    # results out inside the timed region; packets / offsets / sizes travel between the stages through a ring of
+    # three buffers.  (With whole steps as the pipeline's unit the fill and drain cost one stage in K + 1.)
     import threading
     ctx2 = amv.AmvCuda(device=dev.index)
-    hcap = ne * 24 * 1024
-    bufs = [dict(pk=torch.empty(hcap, dtype=torch.uint8).pin_memory(), off=torch.zeros(ne, dtype=torch.int64).pin_memory(),
-                 sz=torch.zeros(ne, dtype=torch.int32).pin_memory(), st=torch.zeros(ne, dtype=torch.int32).pin_memory(),
-                 full=threading.Semaphore(0), free=threading.Semaphore(1)) for _ in range(2)]
+    nsub = max(1, min(args.e2e_sub, ne))
+    while ne % nsub:
+        nsub -= 1
+    ns_ = ne // nsub
+    hcap = ns_ * 24 * 1024
+    bufs = [dict(pk=torch.empty(hcap, dtype=torch.uint8).pin_memory(), off=torch.zeros(ns_, dtype=torch.int64).pin_memory(),
+                 sz=torch.zeros(ns_, dtype=torch.int32).pin_memory(), st=torch.zeros(ns_, dtype=torch.int32).pin_memory(),
+                 full=threading.Semaphore(0), free=threading.Semaphore(1)) for _ in range(3)]
     hst2 = torch.zeros(ne, dtype=torch.int32).pin_memory()
     hpk, hsz = bufs[0]["pk"], bufs[0]["sz"]
+    step_pkt_bytes = [0]
 
-    def run_steps(k):
+    def run_steps(k, count_bytes=False):
         err = []
 
         def enc():
             try:
-                for s_ in range(k):
-                    b = bufs[s_ % 2]
+                for s_ in range(k * nsub):
+                    b = bufs[s_ % 3]
+                    j = s_ % nsub
                     b["free"].acquire()
-                    ctx.encode_frames_raw(hY, hU, hV, W, CW, W * H, CW * CH, ne, W, H, None, b["pk"], hcap, PKT_CAP,
-                                          amv.LAYOUT_PACKED, b["off"], b["sz"], b["st"], amv.MEM_HOST)
+                    ctx.encode_frames_raw(hY[j * ns_:(j + 1) * ns_], hU[j * ns_:(j + 1) * ns_], hV[j * ns_:(j + 1) * ns_], W, CW, W * H,
+                                          CW * CH, ns_, W, H, None, b["pk"], hcap, PKT_CAP, amv.LAYOUT_PACKED, b["off"], b["sz"],
+                                          b["st"], amv.MEM_HOST)
                     b["full"].release()
             except Exception as e:          # noqa: BLE001
                 err.append(e)
@@ -359,22 +368,26 @@ def main():
 
         th = threading.Thread(target=enc)
         th.start()
-        for s_ in range(k):
-            b = bufs[s_ % 2]
+        for s_ in range(k * nsub):
+            b = bufs[s_ % 3]
+            j = s_ % nsub
             b["full"].acquire()
             if err:
                 break
-            ctx2.decode_frames_raw(b["pk"], hcap, b["off"], b["sz"], ne, W, H, hDY, hDU, hDV, W, CW, W * H, CW * CH, hst2,
-                                   amv.MEM_HOST)
+            if count_bytes:
+                assert int(b["st"].abs().sum().item()) == 0, "codec reported errors (host path, encode)"
+                if s_ < nsub:
+                    step_pkt_bytes[0] += int(b["sz"].to(torch.int64).sum().item())
+            ctx2.decode_frames_raw(b["pk"], hcap, b["off"], b["sz"], ns_, W, H, hDY[j * ns_:(j + 1) * ns_], hDU[j * ns_:(j + 1) * ns_],
+                                   hDV[j * ns_:(j + 1) * ns_], W, CW, W * H, CW * CH, hst2[j * ns_:(j + 1) * ns_], amv.MEM_HOST)
             b["free"].release()
         th.join()
         if err:
             raise err[0]
 
-    run_steps(2)
-    assert all(int(b["st"].abs().sum().item()) == 0 for b in bufs) and int(hst2.abs().sum().item()) == 0, \
-        "codec reported errors (host path)"
-    e_pkt = int(hsz.to(torch.int64).sum().item())
+    run_steps(2, count_bytes=True)
+    assert int(hst2.abs().sum().item()) == 0, "codec reported errors (host path)"
+    e_pkt = step_pkt_bytes[0]
     barrier()
     t0 = time.perf_counter()
     run_steps(args.steps)
@@ -384,6 +397,8 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    assert all(int(b["st"].abs().sum().item()) == 0 for b in bufs) and int(hst2.abs().sum().item()) == 0, \
+        "codec reported errors (host path, timed run)"
     e2e_value = world * ne * args.steps / e2e_s
     h2d = ne * FRAME_BYTES + e_pkt + ne * 12          # frames (encode in) + packets, offsets, sizes (decode in)
     d2h = e_pkt + ne * (8 + 4 + 4) + ne * FRAME_BYTES + ne * 4
@@ -402,8 +417,11 @@ def main():
             ay, au, av, dst = ctx2.decode_frames(G[case + "/pk"], G[case + "/off"], G[case + "/sz"], 160, 120)
             ok = ok and bool((dst == 0).all()) and np.array_equal(ay, G[case + "/dy"]) and np.array_equal(au, G[case + "/du"]) \
                 and np.array_equal(av, G[case + "/dv"])
-            # the bench frames themselves: decoding the timed run's packets again gives the timed run's planes
-            na = min(args.audit, ne)
+            # the bench frames themselves: their packets (encoded once more, outside the timed region) decode to the planes the
+            # timed run wrote
+            na = min(args.audit, ns_)
+            ctx.encode_frames_raw(hY[:ns_], hU[:ns_], hV[:ns_], W, CW, W * H, CW * CH, ns_, W, H, None, bufs[0]["pk"], hcap, PKT_CAP,
+                                  amv.LAYOUT_PACKED, bufs[0]["off"], bufs[0]["sz"], bufs[0]["st"], amv.MEM_HOST)
             sub_sz = hsz[:na].numpy().astype(np.uint32)
             sub_off = bufs[0]["off"][:na].numpy().astype(np.uint64)
             sub_pk = hpk[: int(sub_off[-1]) + int(sub_sz[-1])].numpy()
@@ -465,7 +483,7 @@ def main():
         "roofline": roof,
         "roofline_by_kernel": {k: roof_of(k) for k in ("encode", "tokens", "idct") if k != dom},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "frames_per_step_per_gpu": ne, "api": "amv_encode_frames + amv_decode_frames, AMV_MEM_HOST, pinned buffers; two contexts pipeline the steps (encode of step k+1 overlaps decode of step k)"},
+                "frames_per_step_per_gpu": ne, "api": "amv_encode_frames + amv_decode_frames, AMV_MEM_HOST, pinned buffers; two contexts pipeline each step's %d sub-batches (encode of sub-batch j+1 overlaps decode of sub-batch j)" % nsub},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "audit": audit,
