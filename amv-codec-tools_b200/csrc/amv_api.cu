@@ -56,6 +56,7 @@ struct amv_ctx {
     void *pinned_meta = nullptr;
     size_t pinned_meta_cap = 0;
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
+    int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
     bool opt_encode_rounds = true;      // encoder: k_encode16 (homogeneous rounds) + k_encode for the frames it hands back
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
@@ -664,6 +665,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_rounds")) { ctx->opt_encode_rounds = value != 0; return AMV_OK; }
+    if (!strcmp(key, "scale_form")) {
+        if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
+        ctx->opt_scale_form = (int)value;
+        return AMV_OK;
+    }
     if (!strcmp(key, "adpcm_trellis")) {
         if (value < 0 || value > 5) return AMV_ERR_UNSUPPORTED;
         ctx->opt_trellis = (int)value;
@@ -1009,7 +1015,7 @@ AMV_API int amv_scale_frames_ex(amv_ctx *ctx, const uint8_t *y, const uint8_t *u
         dls_y = ow; dls_c = ocw; dfs_y = oty; dfs_c = otc;
     }
     launches += launch_scale_frames(sy, su, sv, sls_y, sls_c, sfs_y, sfs_c, n, iw, ih, dy, du, dv, dls_y, dls_c, dfs_y, dfs_c, ow, oh,
-                                    banks, ctx->stream);
+                                    banks, ctx->opt_scale_form, ctx->stream);
     if (post) {         // img_convert YUV420P -> YUVJ420P behind it (:671-682), over the area the scaler wrote
         launch_convert_range_plane(dy, dy, ow, oh, n, dls_y, dls_y, dfs_y, dfs_y, 0, false, ctx->stream);
         launches++;

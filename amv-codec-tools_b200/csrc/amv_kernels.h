@@ -68,7 +68,8 @@ struct ScaleBanks { int16_t h[64]; int16_t v[64]; int h_incr, v_incr; };     // 
 void build_scale_banks(int iw, int ih, int ow, int oh, ScaleBanks *b);
 int  launch_scale_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                          int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov, int ols_y, int ols_c, uint64_t ofs_y,
-                         uint64_t ofs_c, int ow, int oh, const ScaleBanks &b, cudaStream_t s);      // returns the launches made
+                         uint64_t ofs_c, int ow, int oh, const ScaleBanks &b, int form /* 2 staged tiles, 1 tiles, 0 direct */,
+                         cudaStream_t s);      // returns the launches made
 int  resample_filter_length(int in_rate, int out_rate);
 void build_resample_bank(int in_rate, int out_rate, int16_t *bank /* filter_length * 1024 */);
 int64_t resample_output_count(int64_t n_in, int in_rate, int out_rate);

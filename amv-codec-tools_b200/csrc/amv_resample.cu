@@ -160,7 +160,7 @@ k_scale_plane(ScaleArgs a, ScaleBanks banks) {
     }
 }
 
-// Tiled form (the one that normally runs): a block owns a 64 x 16 tile of the output.  Pass 1 filters every source
+// Tiled form: a block owns a 64 x 16 tile of the output.  Pass 1 filters every source
 // row the tile's vertical taps touch horizontally, once, into shared memory (what the reference keeps in its ring
 // of line buffers); pass 2 runs the vertical filter from there, 4 pixels per thread.  Against the direct form this
 // drops the horizontal work from 4 rows per output row to (rows touched) / 16 and turns 16 byte loads per pixel
@@ -225,15 +225,111 @@ k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y) {
     }
 }
 
+// Staged form of the tile kernel (the one that normally runs): the stretch of every source row the tile's taps touch is first
+// copied into shared memory -- 32-bit loads when the plane's base and pitches allow (WORDS), bytes otherwise -- so
+// pass 1 reads its 4 taps per item from shared memory instead of issuing 4 byte loads to L1 each.
+// Dynamic shared memory: rows_max x (pitch + 64) bytes.
+template <bool VEC, bool WORDS>
+__global__ void __launch_bounds__(256)
+k_scale_tile_staged(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int rows_max, int pitch) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ int2 s_h[16], s_v[16];
+    uint8_t *s_src = s_dyn;                                   // [rows_max][pitch]
+    uint8_t *s_line = s_dyn + (size_t)rows_max * pitch;       // [rows_max][64]
+    if (threadIdx.x < 16) {
+        const int16_t *h = banks.h + 4 * threadIdx.x, *v = banks.v + 4 * threadIdx.x;
+        s_h[threadIdx.x] = make_int2((uint16_t)h[0] | ((int)h[1] << 16), (uint16_t)h[2] | ((int)h[3] << 16));
+        s_v[threadIdx.x] = make_int2((uint16_t)v[0] | ((int)v[1] << 16), (uint16_t)v[2] | ((int)v[3] << 16));
+    }
+    const int tx = blockIdx.x % tiles_x, tyf = blockIdx.x / tiles_x;
+    const int ty = tyf % tiles_y, f = tyf / tiles_y;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int y_last = min(y0 + kTileH, a.oh) - 1, x_last = min(x0 + kTileW, a.ow) - 1;
+    const int r_lo = ((2 * 65536 + y0 * a.v_incr) >> 16) - 3;
+    const int nrows = ((2 * 65536 + y_last * a.v_incr) >> 16) - r_lo + 1;
+    // source columns the tile's taps touch (clamped), start rounded down to a word
+    const int c_lo = min(max((-65536 + x0 * a.h_incr) >> 16, 0), a.iw - 1) & ~3;
+    const int c_hi = min(max(((-65536 + x_last * a.h_incr) >> 16) + 3, 0), a.iw - 1);
+    const uint8_t *in = a.src + (uint64_t)f * a.ifs;
+    if (WORDS) {
+        const int wpr = ((c_hi - c_lo) >> 2) + 1;             // words per row (iw is a multiple of 4: none reaches past the row)
+        for (int i = threadIdx.x; i < nrows * wpr; i += 256) {
+            const int r = i / wpr, c = i - r * wpr;
+            const uint8_t *row = in + (int64_t)a.ils * min(max(r_lo + r, 0), a.ih - 1);
+            *reinterpret_cast<uint32_t *>(s_src + (size_t)r * pitch + 4 * c) = __ldg(reinterpret_cast<const uint32_t *>(row + c_lo) + c);
+        }
+    } else {
+        const int bpr = c_hi - c_lo + 1;
+        for (int i = threadIdx.x; i < nrows * bpr; i += 256) {
+            const int r = i / bpr, c = i - r * bpr;
+            const uint8_t *row = in + (int64_t)a.ils * min(max(r_lo + r, 0), a.ih - 1);
+            s_src[(size_t)r * pitch + c] = __ldg(row + c_lo + c);
+        }
+    }
+    __syncthreads();
+    {   // pass 1 from shared memory: column `col` of the tile for rows threadIdx.x / 64, + 4, + 8, ...
+        const int col = threadIdx.x & (kTileW - 1);
+        const int sx = -65536 + min(x0 + col, x_last) * a.h_incr, left = sx >> 16;
+        const int2 fh = s_h[(sx >> 12) & 15];
+        const int h0 = (int16_t)fh.x, h1 = fh.x >> 16, h2 = (int16_t)fh.y, h3 = fh.y >> 16;
+        const int c0 = min(max(left, 0), a.iw - 1) - c_lo, c1 = min(max(left + 1, 0), a.iw - 1) - c_lo;
+        const int c2 = min(max(left + 2, 0), a.iw - 1) - c_lo, c3 = min(max(left + 3, 0), a.iw - 1) - c_lo;
+#pragma unroll 4
+        for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
+            const uint8_t *row = s_src + (size_t)r * pitch;
+            s_line[r * kTileW + col] = (uint8_t)clip255((row[c0] * h0 + row[c1] * h1 + row[c2] * h2 + row[c3] * h3) >> 8);
+        }
+    }
+    __syncthreads();
+    {   // pass 2
+        const int y = y0 + (threadIdx.x >> 4), cx = (threadIdx.x & 15) * 4;
+        if (y > y_last || x0 + cx >= a.ow) return;
+        const int sy = 2 * 65536 + y * a.v_incr;
+        const int2 fv = s_v[(sy >> 12) & 15];
+        const int fv0 = (int16_t)fv.x, fv1 = fv.x >> 16, fv2 = (int16_t)fv.y, fv3 = fv.y >> 16;
+        const uint8_t *l = s_line + ((sy >> 16) - 3 - r_lo) * kTileW + cx;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(l), w1 = *reinterpret_cast<const uint32_t *>(l + kTileW);
+        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(l + 2 * kTileW), w3 = *reinterpret_cast<const uint32_t *>(l + 3 * kTileW);
+        uint32_t word = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int v = (int)((w0 >> (8 * p)) & 0xff) * fv0 + (int)((w1 >> (8 * p)) & 0xff) * fv1 +
+                          (int)((w2 >> (8 * p)) & 0xff) * fv2 + (int)((w3 >> (8 * p)) & 0xff) * fv3;
+            word |= (uint32_t)clip255(v >> 8) << (8 * p);
+        }
+        uint8_t *d = a.dst + (uint64_t)f * a.ofs + (int64_t)y * a.ols + x0 + cx;
+        if (VEC) *reinterpret_cast<uint32_t *>(d) = word;
+        else {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (x0 + cx + p < a.ow) d[p] = (uint8_t)(word >> (8 * p));
+        }
+    }
+}
+
 static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih, int ow, int oh, int ils, int ols, uint64_t ifs,
-                               uint64_t ofs, int n, const ScaleBanks &b, cudaStream_t s) {
+                               uint64_t ofs, int n, const ScaleBanks &b, int form, cudaStream_t s) {
     if (iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return;       // a 1-pixel-wide picture has no chroma to scale
     ScaleArgs a{ src, dst, iw, ih, ow, oh, ils, ols, ifs, ofs, n, b.h_incr, b.v_incr };
     const bool vec = (ow & 3) == 0 && ((((uintptr_t)dst | (uintptr_t)ols | ofs) & 3) == 0);
     const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + kTileH - 1) / kTileH;
     const int64_t tiles = (int64_t)tiles_x * tiles_y * n;
     const int64_t rows_touched = (((int64_t)(kTileH - 1) * b.v_incr) >> 16) + 5;
-    if (rows_touched <= kTileRowsMax && tiles <= 0x7fffffff) {
+    const int64_t cols_touched = (((int64_t)(kTileW - 1) * b.h_incr) >> 16) + 5 + 3;      // + word alignment of the first column
+    const int64_t pitch = (cols_touched + 3 + 15) & ~(int64_t)15;
+    const int64_t smem = rows_touched * (pitch + kTileW);
+    // 32-bit staging loads: word-aligned rows of a whole number of words (no load reaches past a row's last pixel)
+    const bool words = ((((uintptr_t)src | (uintptr_t)ils | ifs) & 3) == 0) && (iw & 3) == 0;
+    if (form >= 2 && rows_touched <= kTileRowsMax && smem <= 40 * 1024 && tiles <= 0x7fffffff) {
+        const unsigned g = (unsigned)tiles;
+        const int rm = (int)rows_touched, pt = (int)pitch;
+        if (vec && words)       k_scale_tile_staged<true, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
+        else if (vec)           k_scale_tile_staged<true, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
+        else if (words)         k_scale_tile_staged<false, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
+        else                    k_scale_tile_staged<false, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
+        return;
+    }
+    if (form >= 1 && rows_touched <= kTileRowsMax && tiles <= 0x7fffffff) {  // strong reductions: taps straight from global memory
         if (vec) k_scale_tile<true><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y);
         else     k_scale_tile<false><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y);
         return;
@@ -249,12 +345,12 @@ static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih,
 
 int launch_scale_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                         int n, int iw, int ih, uint8_t *oy, uint8_t *ou, uint8_t *ov, int ols_y, int ols_c, uint64_t ofs_y,
-                        uint64_t ofs_c, int ow, int oh, const ScaleBanks &b, cudaStream_t s) {
+                        uint64_t ofs_c, int ow, int oh, const ScaleBanks &b, int form, cudaStream_t s) {
     int launches = 1;
-    launch_scale_plane(y, oy, iw, ih, ow, oh, ls_y, ols_y, fs_y, ofs_y, n, b, s);
+    launch_scale_plane(y, oy, iw, ih, ow, oh, ls_y, ols_y, fs_y, ofs_y, n, b, form, s);
     if ((iw >> 1) > 0 && (ih >> 1) > 0 && (ow >> 1) > 0 && (oh >> 1) > 0) {
-        launch_scale_plane(u, ou, iw >> 1, ih >> 1, ow >> 1, oh >> 1, ls_c, ols_c, fs_c, ofs_c, n, b, s);
-        launch_scale_plane(v, ov, iw >> 1, ih >> 1, ow >> 1, oh >> 1, ls_c, ols_c, fs_c, ofs_c, n, b, s);
+        launch_scale_plane(u, ou, iw >> 1, ih >> 1, ow >> 1, oh >> 1, ls_c, ols_c, fs_c, ofs_c, n, b, form, s);
+        launch_scale_plane(v, ov, iw >> 1, ih >> 1, ow >> 1, oh >> 1, ls_c, ols_c, fs_c, ofs_c, n, b, form, s);
         launches += 2;
     }
     return launches;

@@ -149,7 +149,18 @@ def _ref_worker(args):
             pk, off, sz = codec.encode_frames(y, u, v, W, H, 2)
             codec.decode_frames(pk, off, sz, W, H)
         nbytes += int(sz.sum())
-    return nframes * rounds, time.perf_counter() - t, nbytes, kind
+    dt = time.perf_counter() - t
+    # amvlib (C-AMVDecoder) timed the same way, decode only, packets in memory (it has no encoder)
+    lib_s = None
+    if kind == "reference":
+        from oracle_lib import AmvlibRef
+        if AmvlibRef.available():
+            al = AmvlibRef()
+            t = time.perf_counter()
+            for _ in range(rounds):
+                al.video_decode(pk, off, sz, W, H)
+            lib_s = time.perf_counter() - t
+    return nframes * rounds, dt, nbytes, kind, lib_s
 
 
 def run_cpu_reference(frames_per_worker, rounds=1, workers=None):
@@ -162,8 +173,11 @@ def run_cpu_reference(frames_per_worker, rounds=1, workers=None):
     wall = time.perf_counter() - t
     frames = sum(r[0] for r in res)
     busy = max(r[1] for r in res)                      # codec time of the slowest worker (excludes spawn/synthesis)
-    return {"frames": frames, "seconds": busy, "wall": wall, "fps": frames / busy, "workers": workers,
-            "kind": res[0][3], "pkt_bytes": sum(r[2] for r in res), "per_core_fps": frames / busy / workers}
+    out = {"frames": frames, "seconds": busy, "wall": wall, "fps": frames / busy, "workers": workers,
+           "kind": res[0][3], "pkt_bytes": sum(r[2] for r in res), "per_core_fps": frames / busy / workers}
+    if all(r[4] for r in res):
+        out["amvlib_seconds"] = max(r[4] for r in res)
+    return out
 
 
 # stdout carries exactly ONE line, the JSON result: everything else any library prints there (NCCL's version
@@ -215,6 +229,11 @@ def reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if all("amvlib_seconds" in v for v in vals):      # the reference's second decoder (C-AMVDecoder/amvlib), decode only
+        lib_s = sum(v["amvlib_seconds"] for v in vals)
+        line["amvlib"] = {"value": total_frames / lib_s, "unit": "frames/s", "cores": vals[0]["workers"], "kind": "reference",
+                          "what": "AmvVideoDecode of the same packets to BGR24, packets in memory, one process per core",
+                          "per_core": total_frames / lib_s / vals[0]["workers"]}
     emit(line)
     return 0
 

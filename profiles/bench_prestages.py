@@ -61,10 +61,14 @@ def main():
         ou = torch.empty((n, och, ocw), dtype=torch.uint8, device=dev)
         ov = torch.empty((n, och, ocw), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
-        ms = timed(lambda: ctx.scale_frames_raw(y, u, v, iw, icw, iw * ih, icw * ich, n, iw, ih, oy, ou, ov, ow, ocw, ow * oh,
-                                                ocw * och, ow, oh, amv.MEM_DEVICE))
         nbytes = n * (iw * ih + 2 * icw * ich + ow * oh + 2 * ocw * och)
-        line("scale", n, "frames/s", ms, nbytes, dict(config="%dx%d->%dx%d x %d" % (iw, ih, ow, oh, n)))
+        for form in (1, 2):
+            ctx.set_option("scale_form", form)
+            ms = timed(lambda: ctx.scale_frames_raw(y, u, v, iw, icw, iw * ih, icw * ich, n, iw, ih, oy, ou, ov, ow, ocw, ow * oh,
+                                                    ocw * och, ow, oh, amv.MEM_DEVICE))
+            line("scale", n, "frames/s", ms, nbytes, dict(config="%dx%d->%dx%d x %d" % (iw, ih, ow, oh, n),
+                                                          form={1: "tiles", 2: "staged tiles"}[form]))
+        ctx.set_option("scale_form", 1)
         del y, u, v, oy, ou, ov
     # ---- range conversion at 320x240
     n, w, h = 32768, 320, 240

@@ -716,10 +716,20 @@ def test_scaler_matches_golden(ctx, case):
 @pytest.mark.parametrize("dims", [(640, 480, 320, 240), (352, 288, 208, 176), (160, 120, 320, 240), (321, 243, 160, 120),
                                   (1280, 720, 128, 96), (100, 100, 101, 99), (720, 576, 208, 176), (64, 48, 640, 360),
                                   (16, 16, 2, 2), (5, 3, 17, 9), (320, 240, 320, 120), (2, 2, 8, 8), (8, 8, 1, 1)])
-def test_scaler_identical(ctx, oracle, dims):
-    """host buffers and padded device planes; down, up, odd sizes (chroma at sizes >> 1), extreme ratios"""
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_scaler_identical(ctx, oracle, dims, form):
+    """host buffers and padded device planes; down, up, odd sizes (chroma at sizes >> 1), extreme ratios; every kernel
+    form (option scale_form: direct, tiles, tiles with staged source rows)"""
     import torch
     iw, ih, ow, oh = dims
+    ctx.set_option("scale_form", form)
+    try:
+        _scaler_identical(ctx, oracle, torch, iw, ih, ow, oh)
+    finally:
+        ctx.set_option("scale_form", 1)
+
+
+def _scaler_identical(ctx, oracle, torch, iw, ih, ow, oh):
     rng = np.random.default_rng(iw * 7 + oh)
     n = 3
     icw, ich = chroma_dims(iw, ih)
