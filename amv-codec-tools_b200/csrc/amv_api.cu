@@ -1084,8 +1084,8 @@ AMV_API int amv_audio_resample_from(amv_ctx *ctx, const int16_t *in, uint64_t in
     const int len = resample_filter_length(in_rate, out_rate);
     if (len > 4096) return fail(ctx, AMV_ERR_UNSUPPORTED, "rate ratio needs more than 4096 filter taps");
     const int64_t total = resample_output_count((int64_t)(in_base + n_in), in_rate, out_rate);
-    const int64_t k = total > (int64_t)k_start ? total - (int64_t)k_start : 0;
-    if ((uint64_t)k > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap smaller than the resampled stream (see amv_audio_resample_count)");
+    int64_t k = total > (int64_t)k_start ? total - (int64_t)k_start : 0;
+    if ((uint64_t)k > out_cap) k = (int64_t)out_cap;          // like av_resample's dst_size: the rest comes with a later call
     if (k > 0) {
         const int64_t first = resample_first_tap((int64_t)k_start, in_rate, out_rate);
         if (first < 0 ? in_base != 0 : first < (int64_t)in_base)
@@ -1133,6 +1133,11 @@ AMV_API int amv_audio_resample_from(amv_ctx *ctx, const int16_t *in, uint64_t in
 
 AMV_API int amv_audio_resample(amv_ctx *ctx, const int16_t *in, uint64_t n_in, int in_channels, int in_rate, int out_rate,
                                int16_t *out, uint64_t out_cap, uint64_t *n_out, int mem) {
+    if (ctx && in_rate > 0 && out_rate > 0 && n_in <= (1ull << 40) && n_in > 0 &&
+        (uint64_t)resample_output_count((int64_t)n_in, in_rate, out_rate) > out_cap) {
+        if (n_out) *n_out = 0;
+        return fail(ctx, AMV_ERR_ARG, "out_cap smaller than the resampled stream (see amv_audio_resample_count)");
+    }
     return amv_audio_resample_from(ctx, in, 0, n_in, in_channels, in_rate, out_rate, 0, out, out_cap, n_out, mem);
 }
 

@@ -88,8 +88,6 @@ typedef struct AmvCudaResample {
     short *buf;                  /* the stream's samples [base, base + n_buf), interleaved */
     int64_t base, n_buf, cap;
     int64_t k_next;              /* next output of the stream */
-    short *tmp;
-    int64_t tmp_cap;
 } AmvCudaResample;
 
 ReSampleContext *amvcuda_audio_resample_init(int output_channels, int input_channels, int output_rate, int input_rate)
@@ -109,7 +107,7 @@ void amvcuda_audio_resample_close(ReSampleContext *ctx)
     AmvCudaResample *s = (AmvCudaResample *)ctx;
     if (!s) return;
     amv_destroy(s->h);
-    av_free(s->buf); av_free(s->tmp); av_free(s);
+    av_free(s->buf); av_free(s);
 }
 
 int amvcuda_audio_resample(ReSampleContext *ctx, short *output, short *input, int nb_samples)
@@ -126,12 +124,10 @@ int amvcuda_audio_resample(ReSampleContext *ctx, short *output, short *input, in
     s->n_buf += nb_samples;
     avail = amv_audio_resample_count((uint64_t)(s->base + s->n_buf), s->in_rate, s->out_rate);
     avail = avail > (uint64_t)s->k_next ? avail - (uint64_t)s->k_next : 0;
-    if ((int64_t)avail > s->tmp_cap) { s->tmp_cap = (int64_t)avail + 64; s->tmp = av_realloc(s->tmp, sizeof(short) * s->tmp_cap); }
+    /* av_resample stops at dst_size = lenout (resample.c:154,202); the rest comes with the next call */
     if (avail && amv_audio_resample_from(s->h, s->buf, (uint64_t)s->base, (uint64_t)s->n_buf, s->in_ch, s->in_rate, s->out_rate,
-                                         (uint64_t)s->k_next, s->tmp, avail, &got, AMV_MEM_HOST) != AMV_OK)
+                                         (uint64_t)s->k_next, output, (uint64_t)lenout, &got, AMV_MEM_HOST) != AMV_OK)
         return -1;
-    if (got > (uint64_t)lenout) got = (uint64_t)lenout;      /* av_resample stops at dst_size; the rest comes with the next call */
-    memcpy(output, s->tmp, sizeof(short) * got);
     s->k_next += (int64_t)got;
     keep = amv_audio_resample_first_tap((uint64_t)s->k_next, s->in_rate, s->out_rate);   /* resample2.c:303: consumed */
     if (keep > s->base) {

@@ -7,6 +7,9 @@ communication is this module's gather of the per-rank (offset, size) packet tabl
 a few bytes per frame, over whatever torch.distributed backend the job uses (NCCL on the GPU box,
 gloo in the CPU tests) -- and, for ONE continuous audio stream split across ranks, the 2-byte
 encoder state handed from the end of one rank's range to the start of the next (adpcm.c:466).
+The audio resampler in front of the encoder shards by OUTPUT range: every output sample depends on a
+short window of the input only, so resample_shard gives each rank its outputs and the slice of the
+stream they read (neighbouring slices overlap by one filter length; nothing is exchanged).
 """
 import numpy as np
 
@@ -64,3 +67,27 @@ def chain_stream_state(encode_range, dist=None, initial_state=0, device="cpu"):
     if rank < world - 1:
         dist.send(torch.tensor([int(out)], dtype=torch.int64, device=device), dst=rank + 1)
     return out
+
+
+def resample_shard(n_in, in_rate, out_rate, rank, world, lib):
+    """ONE stream of n_in samples per channel resampled by `world` ranks: rank r computes outputs
+    [k_start, k_start + k_count) -- a contiguous, balanced share of the amv_audio_resample_count(n_in) outputs --
+    from the input samples [in_base, in_base + n_window), and calls
+    amv_audio_resample_from(ctx, pcm + in_base * channels, in_base, n_window, ..., k_start, out, k_count, ...).
+    The window ends where the rank's last output's taps end, so the call yields exactly k_count samples.
+    `lib` is the loaded libamvcuda (the two helpers used here are host arithmetic, no device involved).
+    Returns (k_start, k_count, in_base, n_window)."""
+    total = int(lib.amv_audio_resample_count(int(n_in), int(in_rate), int(out_rate)))
+    k_lo, k_hi = shard_range(total, rank, world)
+    if k_hi == k_lo:
+        return k_lo, 0, 0, 0
+    flen = int(lib.amv_audio_resample_bank(int(in_rate), int(out_rate), None, 0))
+    first = int(lib.amv_audio_resample_first_tap(k_lo, int(in_rate), int(out_rate)))
+    in_base = max(first, 0)                       # the mirrored head of the stream (first < 0) belongs to sample 0
+    # smallest stream length that still yields output k_hi - 1: its taps end at first_tap(k_hi - 1) + filter length;
+    # the mirrored head needs no such room (its outputs exist however short the stream is)
+    last = int(lib.amv_audio_resample_first_tap(k_hi - 1, int(in_rate), int(out_rate)))
+    end = int(n_in) if last < 0 else min(int(n_in), last + flen)
+    if rank == world - 1:
+        end = int(n_in)
+    return k_lo, k_hi - k_lo, in_base, end - in_base

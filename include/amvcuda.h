@@ -276,10 +276,12 @@ AMV_API int amv_audio_resample(amv_ctx *ctx,
  * ffmpeg.c feeds audio_resample (which keeps the unconsumed tail in ReSampleContext.temp and the position in
  * AVResampleContext.index / frac, resample.c:214-216, resample2.c:303-313): `in` holds the stream's samples
  * [in_base, in_base + n_in) and the call writes outputs k_start, k_start + 1, ... up to the last one whose taps
- * end inside the window, i.e. amv_audio_resample_count(in_base + n_in, ...) - k_start samples.
+ * end inside the window, i.e. amv_audio_resample_count(in_base + n_in, ...) - k_start samples, or out_cap of them
+ * if that is fewer (av_resample's dst_size; the rest comes with a later call).
  * amv_audio_resample_first_tap(k, ...) is the first input sample output k reads (negative for the mirrored head
  * of the stream, which needs in_base == 0): a caller may drop everything in front of first_tap(next k).
- * glue/ffmpeg/amvcuda_codecs.c builds its audio_resample replacement on these two.
+ * glue/ffmpeg/amvcuda_resample.c builds its audio_resample replacement on these two; sharding.resample_shard (Python
+ * host side) splits one stream across GPUs by output range with them.
  */
 AMV_API int amv_audio_resample_from(amv_ctx *ctx,
                                     const int16_t *in, uint64_t in_base, uint64_t n_in, int in_channels,

@@ -844,6 +844,29 @@ def test_audio_resampler_packet_feed(ctx, oracle, rate, ch):
     assert np.array_equal(np.concatenate(outs), oracle.audio_resample(pcm, ch, rate, 22050))
 
 
+@pytest.mark.parametrize("rate,ch,n,world", [(44100, 2, 200000, 4), (8000, 1, 50000, 8), (48000, 1, 3000, 3), (96000, 2, 60, 2)])
+def test_audio_resampler_sharded_stream(ctx, oracle, rate, ch, n, world):
+    """sharding.resample_shard: one stream split by output range as `world` GPUs would take it (here one after the
+    other on one GPU, device buffers): the pieces concatenate to the stream's output"""
+    import torch
+    pcm = synth_pcm(n * ch, seed=n, kind="noise")
+    want = oracle.audio_resample(pcm, ch, rate, 22050)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(pcm).to(dev)
+    pieces = []
+    for r in range(world):
+        k0, kc, base, nwin = amv.sharding.resample_shard(n, rate, 22050, r, world, ctx.lib)
+        assert k0 == sum(len(p) for p in pieces)
+        d_out = torch.full((kc + 4,), 77, dtype=torch.int16, device=dev)
+        torch.cuda.synchronize()
+        k = ctx.audio_resample_from_raw(d_in[base * ch:(base + nwin) * ch], base, nwin, ch, rate, 22050, k0, d_out, kc, amv.MEM_DEVICE) if kc else 0
+        ctx.sync()
+        a = d_out.cpu().numpy()
+        assert k == kc and (a[kc:] == 77).all()
+        pieces.append(a[:kc])
+    assert np.array_equal(np.concatenate(pieces), want)
+
+
 def test_audio_resampler_feeds_the_adpcm_encoder(ctx, oracle):
     """44.1 kHz stereo -> 22050 Hz mono -> ADPCM chunks, as do_audio_out chains them"""
     pcm = synth_pcm(2 * 44100, seed=9, kind="tones")

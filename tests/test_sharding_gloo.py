@@ -100,3 +100,70 @@ def test_two_rank_gather_and_chain():
         st = int(so[0])
     assert b"".join(r[5] for r in res) == b"".join(chunks)
     assert res[-1][6] == st
+
+
+# ------------------------------------------------------------------ one audio stream resampled by several ranks
+def _fir_window(win, in_base, k_start, k_count, rate_in, rate_out, bank):
+    """stand-in for amv_audio_resample_from on the CPU (the oracle's bank, the stream positions of resample2.c:290-296):
+    outputs k_start .. k_start + k_count - 1 from the mono window win = stream[in_base : in_base + len(win)]"""
+    flen = bank.shape[1]
+    index0 = -1024 * ((flen - 1) // 2)
+    out = np.zeros(k_count, np.int16)
+    for j in range(k_count):
+        index = index0 + ((k_start + j) * rate_in * 1024) // rate_out
+        first, f = index >> 10, bank[index & 1023].astype(np.int64)
+        pos = np.arange(first, first + flen)
+        if first < 0:
+            assert in_base == 0
+            pos = np.abs(pos) % len(win)
+        else:
+            pos = pos - in_base
+        acc = int((win[pos].astype(np.int64) * f).sum())
+        acc = ((acc + (1 << 31)) % (1 << 32)) - (1 << 31)              # the reference's 32-bit accumulator
+        out[j] = max(-32768, min(32767, (acc + (1 << 14)) >> 15))
+    return out
+
+
+def _resample_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle, lib = Oracle(), amv.load_library()
+        res = []
+        for rate, n in ((48000, 6000), (8000, 900), (44100, 40)):
+            pcm = synth_pcm(n, seed=rate, kind="noise")
+            k0, kc, base, nwin = amv.sharding.resample_shard(n, rate, 22050, rank, world, lib)
+            out = _fir_window(pcm[base:base + nwin], base, k0, kc, rate, 22050, oracle.resample_bank(rate, 22050))
+            # the window is exactly what the rank's outputs need: the ABI's own count over it is at least the share
+            assert kc == 0 or lib.amv_audio_resample_count(base + nwin, rate, 22050) - k0 >= kc
+            res.append((k0, out.tobytes()))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_resample_shards_concatenate_to_the_stream(world):
+    """every rank resamples its output range from its own window of the stream; the pieces, in rank order, are the
+    oracle's (= the reference's) output over the whole stream"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_resample_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    oracle = Oracle()
+    for i, (rate, n) in enumerate(((48000, 6000), (8000, 900), (44100, 40))):
+        want = oracle.audio_resample(synth_pcm(n, seed=rate, kind="noise"), 1, rate, 22050)
+        pos = 0
+        for rank, r in res:
+            k0, piece = r[i]
+            assert k0 == pos or len(piece) == 0
+            pos += len(piece) // 2
+        assert b"".join(r[i][1] for _, r in res) == want.tobytes()
