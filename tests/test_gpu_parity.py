@@ -808,11 +808,11 @@ def test_audio_resampler_matches_golden(ctx, case):
 
 @pytest.mark.parametrize("rate,ch,n", [(44100, 2, 50000), (48000, 1, 70000), (8000, 1, 9000), (22050, 2, 30000), (11025, 1, 20000),
                                         (32000, 2, 3000000), (44100, 1, 1000), (48000, 2, 100), (96000, 2, 40000), (16000, 1, 20),
-                                        (96000, 1, 50), (44100, 2, 1)])
+                                        (96000, 1, 50), (44100, 2, 1), (705600, 1, 300000), (705600, 2, 2000)])
 @pytest.mark.parametrize("kind", ["noise", "tones", "square"])
 def test_audio_resampler_identical(ctx, oracle, rate, ch, n, kind):
     """host and device buffers; streams shorter than the filter (mirrored taps only), beyond 2^21 samples (64-bit positions),
-    full-scale square waves (32-bit accumulator, saturation)"""
+    full-scale square waves (32-bit accumulator, saturation), a 32:1 reduction (640 taps: the direct kernel form)"""
     import torch
     pcm = synth_pcm(n * ch, seed=rate + n, kind=kind)
     want = oracle.audio_resample(pcm, ch, rate, 22050)

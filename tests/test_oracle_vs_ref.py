@@ -420,7 +420,7 @@ def test_scaler_matches_img_resample(oracle, ref, dims):
 @pytest.mark.parametrize("rate,ch,n,chunk", [(44100, 2, 50000, 4096), (48000, 1, 70000, 1152), (8000, 1, 9000, 320),
                                               (22050, 2, 30000, 1024), (11025, 1, 20000, 8192), (32000, 2, 600000, 4608),
                                               (44100, 1, 1000, 1000), (48000, 2, 100, 100), (96000, 2, 40000, 2048),
-                                              (16000, 1, 20, 20)])
+                                              (16000, 1, 20, 20), (705600, 1, 100000, 8192)])
 @pytest.mark.parametrize("kind", ["noise", "tones", "square"])
 def test_audio_resampler_matches_audio_resample(oracle, ref, rate, ch, n, chunk, kind):
     """the reference fed packet by packet (tail carried between calls) against the oracle's closed form over the stream"""
