@@ -160,16 +160,16 @@ k_scale_plane(ScaleArgs a, ScaleBanks banks) {
     }
 }
 
-// Tiled form: a block owns a 64 x 16 tile of the output.  Pass 1 filters every source
+// Tiled form (the one that normally runs): a block owns a 64 x tile_h tile of the output.  Pass 1 filters every source
 // row the tile's vertical taps touch horizontally, once, into shared memory (what the reference keeps in its ring
 // of line buffers); pass 2 runs the vertical filter from there, 4 pixels per thread.  Against the direct form this
 // drops the horizontal work from 4 rows per output row to (rows touched) / 16 and turns 16 byte loads per pixel
 // into (rows touched) / 4 of them plus one 32-bit shared-memory read.
-constexpr int kTileW = 64, kTileH = 16, kTileRowsMax = 192;
+constexpr int kTileW = 64, kTileRowsMax = 320;      // tile height: 128, 64, 32 or 16 output rows, the tallest whose source rows fit
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y) {
+k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int tile_h) {
     __shared__ int2 s_h[16], s_v[16];
     __shared__ __align__(16) uint8_t s_line[kTileRowsMax][kTileW];
     if (threadIdx.x < 16) {
@@ -180,8 +180,8 @@ k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y) {
     __syncthreads();
     const int tx = blockIdx.x % tiles_x, tyf = blockIdx.x / tiles_x;
     const int ty = tyf % tiles_y, f = tyf / tiles_y;
-    const int x0 = tx * kTileW, y0 = ty * kTileH;
-    const int y_last = min(y0 + kTileH, a.oh) - 1;
+    const int x0 = tx * kTileW, y0 = ty * tile_h;
+    const int y_last = min(y0 + tile_h, a.oh) - 1;
     const int r_lo = ((2 * 65536 + y0 * a.v_incr) >> 16) - 3;
     const int nrows = ((2 * 65536 + y_last * a.v_incr) >> 16) - r_lo + 1;          // <= kTileRowsMax (checked by the launcher)
     const uint8_t *in = a.src + (uint64_t)f * a.ifs;
@@ -199,9 +199,10 @@ k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y) {
         }
     }
     __syncthreads();
-    {   // pass 2
-        const int y = y0 + (threadIdx.x >> 4), cx = (threadIdx.x & 15) * 4;
-        if (y > y_last || x0 + cx >= a.ow) return;
+    // pass 2: rows threadIdx.x / 16, + 16, ... of the tile, 4 pixels each
+    const int cx = (threadIdx.x & 15) * 4;
+    if (x0 + cx >= a.ow) return;
+    for (int y = y0 + (threadIdx.x >> 4); y <= y_last; y += 16) {
         const int sy = 2 * 65536 + y * a.v_incr;
         const int2 fv = s_v[(sy >> 12) & 15];
         const int fv0 = (int16_t)fv.x, fv1 = fv.x >> 16, fv2 = (int16_t)fv.y, fv3 = fv.y >> 16;
@@ -225,13 +226,13 @@ k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y) {
     }
 }
 
-// Staged form of the tile kernel (the one that normally runs): the stretch of every source row the tile's taps touch is first
+// Staged form of the tile kernel (option scale_form 2; measured slower): the stretch of every source row the tile's taps touch is first
 // copied into shared memory -- 32-bit loads when the plane's base and pitches allow (WORDS), bytes otherwise -- so
 // pass 1 reads its 4 taps per item from shared memory instead of issuing 4 byte loads to L1 each.
 // Dynamic shared memory: rows_max x (pitch + 64) bytes.
 template <bool VEC, bool WORDS>
 __global__ void __launch_bounds__(256)
-k_scale_tile_staged(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int rows_max, int pitch) {
+k_scale_tile_staged(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int tile_h, int rows_max, int pitch) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ int2 s_h[16], s_v[16];
     uint8_t *s_src = s_dyn;                                   // [rows_max][pitch]
@@ -243,8 +244,8 @@ k_scale_tile_staged(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int
     }
     const int tx = blockIdx.x % tiles_x, tyf = blockIdx.x / tiles_x;
     const int ty = tyf % tiles_y, f = tyf / tiles_y;
-    const int x0 = tx * kTileW, y0 = ty * kTileH;
-    const int y_last = min(y0 + kTileH, a.oh) - 1, x_last = min(x0 + kTileW, a.ow) - 1;
+    const int x0 = tx * kTileW, y0 = ty * tile_h;
+    const int y_last = min(y0 + tile_h, a.oh) - 1, x_last = min(x0 + kTileW, a.ow) - 1;
     const int r_lo = ((2 * 65536 + y0 * a.v_incr) >> 16) - 3;
     const int nrows = ((2 * 65536 + y_last * a.v_incr) >> 16) - r_lo + 1;
     // source columns the tile's taps touch (clamped), start rounded down to a word
@@ -281,9 +282,10 @@ k_scale_tile_staged(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int
         }
     }
     __syncthreads();
-    {   // pass 2
-        const int y = y0 + (threadIdx.x >> 4), cx = (threadIdx.x & 15) * 4;
-        if (y > y_last || x0 + cx >= a.ow) return;
+    // pass 2: rows threadIdx.x / 16, + 16, ... of the tile, 4 pixels each
+    const int cx = (threadIdx.x & 15) * 4;
+    if (x0 + cx >= a.ow) return;
+    for (int y = y0 + (threadIdx.x >> 4); y <= y_last; y += 16) {
         const int sy = 2 * 65536 + y * a.v_incr;
         const int2 fv = s_v[(sy >> 12) & 15];
         const int fv0 = (int16_t)fv.x, fv1 = fv.x >> 16, fv2 = (int16_t)fv.y, fv3 = fv.y >> 16;
@@ -312,29 +314,35 @@ static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih,
     if (iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return;       // a 1-pixel-wide picture has no chroma to scale
     ScaleArgs a{ src, dst, iw, ih, ow, oh, ils, ols, ifs, ofs, n, b.h_incr, b.v_incr };
     const bool vec = (ow & 3) == 0 && ((((uintptr_t)dst | (uintptr_t)ols | ofs) & 3) == 0);
-    const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + kTileH - 1) / kTileH;
-    const int64_t tiles = (int64_t)tiles_x * tiles_y * n;
-    const int64_t rows_touched = (((int64_t)(kTileH - 1) * b.v_incr) >> 16) + 5;
+    // the tallest tile whose source rows fit the line buffer: taller tiles share more horizontally filtered rows between
+    // their output rows and spread the per-block set-up over more pixels (measured at 2:1: 4.19 / 3.36 / 3.27 ms for
+    // 16 / 64 / 128 rows; 1:3 enlargement: 7.2 / 4.15 / 3.56 ms)
+    int tile_h = 128;
     const int64_t cols_touched = (((int64_t)(kTileW - 1) * b.h_incr) >> 16) + 5 + 3;      // + word alignment of the first column
     const int64_t pitch = (cols_touched + 3 + 15) & ~(int64_t)15;
+    auto rows_of = [&](int th) { return (((int64_t)(th - 1) * b.v_incr) >> 16) + 5; };
+    while (tile_h > 16 && (rows_of(tile_h) > kTileRowsMax || (form >= 2 && rows_of(tile_h) * (pitch + kTileW) > 40 * 1024))) tile_h >>= 1;
+    const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + tile_h - 1) / tile_h;
+    const int64_t tiles = (int64_t)tiles_x * tiles_y * n;
+    const int64_t rows_touched = rows_of(tile_h);
     const int64_t smem = rows_touched * (pitch + kTileW);
     // 32-bit staging loads: word-aligned rows of a whole number of words (no load reaches past a row's last pixel)
     const bool words = ((((uintptr_t)src | (uintptr_t)ils | ifs) & 3) == 0) && (iw & 3) == 0;
     if (form >= 2 && rows_touched <= kTileRowsMax && smem <= 40 * 1024 && tiles <= 0x7fffffff) {
         const unsigned g = (unsigned)tiles;
         const int rm = (int)rows_touched, pt = (int)pitch;
-        if (vec && words)       k_scale_tile_staged<true, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
-        else if (vec)           k_scale_tile_staged<true, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
-        else if (words)         k_scale_tile_staged<false, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
-        else                    k_scale_tile_staged<false, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, rm, pt);
+        if (vec && words)       k_scale_tile_staged<true, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        else if (vec)           k_scale_tile_staged<true, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        else if (words)         k_scale_tile_staged<false, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        else                    k_scale_tile_staged<false, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
         return;
     }
-    if (form >= 1 && rows_touched <= kTileRowsMax && tiles <= 0x7fffffff) {  // strong reductions: taps straight from global memory
-        if (vec) k_scale_tile<true><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y);
-        else     k_scale_tile<false><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y);
+    if (form >= 1 && rows_touched <= kTileRowsMax && tiles <= 0x7fffffff) {  // taps straight from global memory (L1)
+        if (vec) k_scale_tile<true><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y, tile_h);
+        else     k_scale_tile<false><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y, tile_h);
         return;
     }
-    // extreme reductions (more than 12 source rows per output row): the direct form
+    // extreme reductions (the tile's rows exceed the line buffer): the direct form
     const int64_t total = (int64_t)((ow + 3) >> 2) * oh * n;
     int64_t grid = (total + 255) / 256;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;

@@ -26,7 +26,7 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    ctx = amv.AmvCuda(device=0)
+    ctx = amv.AmvCuda(device=0, lib_path=os.environ.get("AMV_LIB") or amv.LIB_PATH)      # AMV_LIB: a build variant to compare
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     peak, peak_src = bench.load_peaks()
