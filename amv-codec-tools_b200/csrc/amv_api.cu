@@ -56,6 +56,7 @@ struct amv_ctx {
     void *pinned_meta = nullptr;
     size_t pinned_meta_cap = 0;
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
+    int opt_resample_form = 2;          // audio resampler: 2 = phase rows (M outputs per coefficient row), 1 = tiles, 0 = direct form
     int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
     bool opt_encode_rounds = true;      // encoder: k_encode16 (homogeneous rounds) + k_encode for the frames it hands back
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
@@ -665,6 +666,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_rounds")) { ctx->opt_encode_rounds = value != 0; return AMV_OK; }
+    if (!strcmp(key, "resample_form")) {
+        if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
+        ctx->opt_resample_form = (int)value;
+        return AMV_OK;
+    }
     if (!strcmp(key, "scale_form")) {
         if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
         ctx->opt_scale_form = (int)value;
@@ -1112,7 +1118,7 @@ AMV_API int amv_audio_resample_from(amv_ctx *ctx, const int16_t *in, uint64_t in
     const int16_t *d_bank = reinterpret_cast<const int16_t *>(ctx->ws[WS_RS_BANK].p);
     if (mem == AMV_MEM_DEVICE) {
         launch_audio_resample(in, (int64_t)n_in, (int64_t)in_base, in_channels, d_bank, len, in_rate, out_rate, (int64_t)k_start, out, k,
-                              ctx->stream);
+                              ctx->opt_resample_form, ctx->stream);
         *n_out = (uint64_t)k;
         return k > 0 ? check_launch(ctx, "audio resampler kernel", 1) : AMV_OK;
     }
@@ -1121,7 +1127,7 @@ AMV_API int amv_audio_resample_from(amv_ctx *ctx, const int16_t *in, uint64_t in
     ENSURE(WS_H_B, sizeof(int16_t) * (k > 0 ? k : 1), d_out);
     if (k > 0) {
         launch_audio_resample(d_in, (int64_t)n_in, (int64_t)in_base, in_channels, d_bank, len, in_rate, out_rate, (int64_t)k_start, d_out,
-                              k, ctx->stream);
+                              k, ctx->opt_resample_form, ctx->stream);
         int r = check_launch(ctx, "audio resampler kernel", 1);
         if (r != AMV_OK) return r;
         CK(cudaMemcpyAsync(out, d_out, sizeof(int16_t) * k, cudaMemcpyDeviceToHost, ctx->stream));

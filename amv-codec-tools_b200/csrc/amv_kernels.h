@@ -76,7 +76,8 @@ int64_t resample_output_count(int64_t n_in, int in_rate, int out_rate);
 int64_t resample_first_tap(int64_t k, int in_rate, int out_rate);
 // in holds the stream's samples [in_base, in_base + n_in); outputs k_base .. k_base + n_out - 1 go to out[0 ..]
 void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int in_ch, const int16_t *bank, int len, int in_rate,
-                           int out_rate, int64_t k_base, int16_t *out, int64_t n_out, cudaStream_t s);
+                           int out_rate, int64_t k_base, int16_t *out, int64_t n_out, int form /* 2 phase rows, 1 tiles, 0 direct */,
+                           cudaStream_t s);
 
 // ---- encode
 cudaError_t upload_enc_tables(cudaStream_t s);

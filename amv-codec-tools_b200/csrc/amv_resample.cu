@@ -406,7 +406,7 @@ k_audio_resample(const int16_t *__restrict__ in, int64_t n_in, int64_t in_base, 
     }
 }
 
-// Tiled form (the one that normally runs): a block owns 256 consecutive outputs.  Their taps cover one contiguous
+// Tiled form: a block owns 256 consecutive outputs.  Their taps cover one contiguous
 // stretch of the input, which the block loads once, coalesced and already mixed down to one channel, into shared
 // memory as 32-bit samples; each thread then walks its phase row 8 coefficients per 128-bit load.
 constexpr int kWinMax = 6144;          // samples of shared memory (24 KB)
@@ -450,8 +450,78 @@ k_audio_resample_tile(const int16_t *__restrict__ in, int64_t n_in, int64_t in_b
     out[k] = round_sat(acc);
 }
 
+// Phase-row form (the one that normally runs): the filter phase of output k repeats with a period P2 that depends on the
+// rate pair only (147 outputs for 48 kHz -> 22 050 Hz, 1 for 44.1 kHz, 441 for 8 kHz).  A block of Q threads (Q = the
+// multiple of P2 next to 256) owns Q x M consecutive outputs; thread t computes outputs k0 + t + j Q, j < M, which all use
+// the same phase row: every 128-bit coefficient load, and the unpacking of its 8 coefficients, serves M outputs, and the
+// input stretch (first(k0 + t + j Q) = first(k0 + t) + j * step exactly) is staged in shared memory once as above.
+template <int CH, int M>
+__global__ void __launch_bounds__(1024)
+k_audio_resample_rows(const int16_t *__restrict__ in, int64_t n_in, int64_t in_base, const int16_t *__restrict__ bank, int len, int len8,
+                      int64_t index0, uint64_t dst_incr, uint32_t src_incr, uint32_t step_q, uint32_t step_r, int q_step /* samples per Q outputs */,
+                      int64_t k_base, int16_t *__restrict__ out, int64_t n_out) {
+    __shared__ int s_win[kWinMax];
+    const int Q = blockDim.x, t = threadIdx.x;
+    const int64_t k0 = (int64_t)blockIdx.x * Q * M;
+    const int64_t k_hi = min(k0 + (int64_t)Q * M, n_out) - 1;
+    const uint64_t p0 = (uint64_t)(k_base + k0) * dst_incr, base = p0 / src_incr;
+    const uint32_t rem = (uint32_t)(p0 - base * src_incr);
+    const int64_t index_lo = index0 + (int64_t)base;
+    const int64_t index = index_lo + (int64_t)t * step_q + (rem + (uint32_t)t * step_r) / src_incr;
+    const int64_t first_lo = index_lo >> 10;
+    const int64_t first_hi = (index0 + (int64_t)(((uint64_t)(k_base + k_hi) * dst_incr) / src_incr)) >> 10;
+    const int16_t *f = bank + (size_t)len8 * (size_t)(index & 1023);
+    if (first_lo < 0) {                 // the block that holds the mirrored head of the stream
+        for (int j = 0; j < M; j++) {
+            const int64_t k = k0 + t + (int64_t)j * Q;
+            if (k < n_out) out[k] = round_sat(taps_direct<CH>(in, n_in, f, len, (index >> 10) + (int64_t)j * q_step, in_base));
+        }
+        return;
+    }
+    const int wlen = (int)(first_hi - first_lo) + len8;          // <= kWinMax (checked by the launcher)
+    for (int j = t; j < wlen; j += Q)
+        s_win[j] = first_lo - in_base + j < n_in ? mono_at<CH>(in, first_lo - in_base + j) : 0;
+    __syncthreads();
+    if (k0 + t >= n_out) return;
+    const int *w = s_win + (int)((index >> 10) - first_lo);
+    uint32_t acc[M];
+#pragma unroll
+    for (int j = 0; j < M; j++) acc[j] = 0;
+    for (int i = 0; i < len8; i += 8) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(f + i));
+        const int c0 = (int16_t)c.x, c1 = (int)c.x >> 16, c2 = (int16_t)c.y, c3 = (int)c.y >> 16;
+        const int c4 = (int16_t)c.z, c5 = (int)c.z >> 16, c6 = (int16_t)c.w, c7 = (int)c.w >> 16;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            const int *v = w + j * q_step + i;          // outputs past n_out read staged or stale words; they are not stored
+            acc[j] += (uint32_t)(v[0] * c0) + (uint32_t)(v[1] * c1) + (uint32_t)(v[2] * c2) + (uint32_t)(v[3] * c3) +
+                      (uint32_t)(v[4] * c4) + (uint32_t)(v[5] * c5) + (uint32_t)(v[6] * c6) + (uint32_t)(v[7] * c7);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        const int64_t k = k0 + t + (int64_t)j * Q;
+        if (k < n_out) out[k] = round_sat(acc[j]);
+    }
+}
+
+template <int CH>
+static bool launch_rows(int m, unsigned blocks, int Q, const int16_t *in, int64_t n_in, int64_t in_base, const int16_t *bank, int len,
+                        int len8, int64_t index0, uint64_t D, uint32_t S, int q_step, int64_t k_base, int16_t *out, int64_t n_out,
+                        cudaStream_t s) {
+    const uint32_t sq = (uint32_t)(D / S), sr = (uint32_t)(D % S);
+    switch (m) {
+    case 8: k_audio_resample_rows<CH, 8><<<blocks, Q, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
+    case 4: k_audio_resample_rows<CH, 4><<<blocks, Q, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
+    case 2: k_audio_resample_rows<CH, 2><<<blocks, Q, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
+    default: return false;
+    }
+}
+
+static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; }
+
 void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int in_ch, const int16_t *bank, int len, int in_rate,
-                           int out_rate, int64_t k_base, int16_t *out, int64_t n_out, cudaStream_t s) {
+                           int out_rate, int64_t k_base, int16_t *out, int64_t n_out, int audio_form, cudaStream_t s) {
     if (n_out <= 0) return;
     const int len8 = (len + 7) & ~7;
     const int64_t index0 = -1024 * (int64_t)((len - 1) / 2);
@@ -459,7 +529,26 @@ void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int
     const uint32_t S = (uint32_t)out_rate;
     const int64_t span = (int64_t)((255 * D) / S >> 10) + 2 + len8;        // input samples 256 consecutive outputs touch
     const int64_t blocks = (n_out + 255) / 256;
-    if (span <= kWinMax && blocks <= 0x7fffffff) {
+    if (audio_form >= 2) {
+        // phase period: after P = S / gcd(D, S) outputs the position has advanced by exactly adv = D / gcd(D, S) (no remainder);
+        // the phase (position mod 1024) repeats after P2 = P * 1024 / gcd(adv, 1024) outputs
+        const uint64_t g = gcd_u64(D, S), P = S / g, adv = D / g;
+        const uint64_t P2 = P * (1024 / gcd_u64(adv, 1024));
+        if (P2 <= 1024) {
+            const int Q = (int)(P2 * ((256 + P2 - 1) / P2));                 // threads per block: a multiple of P2, >= 256
+            const uint64_t q_adv = (uint64_t)(Q / (int)P) * adv;            // position advance per Q outputs: a multiple of 1024
+            const int64_t q_step = (int64_t)(q_adv >> 10);
+            int m = 8;
+            while (m >= 2 && (int64_t)((((uint64_t)Q * m - 1) * D) / S >> 10) + 2 + len8 > kWinMax) m >>= 1;
+            const int64_t nb = (n_out + (int64_t)Q * m - 1) / ((int64_t)Q * m);
+            if (m >= 2 && q_step < (1 << 20) && nb <= 0x7fffffff) {
+                const bool ok = in_ch == 2 ? launch_rows<2>(m, (unsigned)nb, Q, in, n_in, in_base, bank, len, len8, index0, D, S, (int)q_step, k_base, out, n_out, s)
+                                           : launch_rows<1>(m, (unsigned)nb, Q, in, n_in, in_base, bank, len, len8, index0, D, S, (int)q_step, k_base, out, n_out, s);
+                if (ok) return;
+            }
+        }
+    }
+    if (audio_form >= 1 && span <= kWinMax && blocks <= 0x7fffffff) {
         if (in_ch == 2) k_audio_resample_tile<2><<<(unsigned)blocks, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
         else            k_audio_resample_tile<1><<<(unsigned)blocks, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
         return;

@@ -86,9 +86,13 @@ def main():
         k = ctx.audio_resample_count(nin, rate, 22050)
         out = torch.empty((k,), dtype=torch.int16, device=dev)
         torch.cuda.synchronize()
-        ms = timed(lambda: ctx.audio_resample_raw(pcm, nin, ch, rate, 22050, out, k, amv.MEM_DEVICE))
-        line("audio_resample", k, "output samples/s", ms, 2 * (nin * ch + k),
-             dict(config="%d Hz x %d ch -> 22050 Hz mono, %d input samples per channel" % (rate, ch, nin)))
+        for form in (1, 2):
+            ctx.set_option("resample_form", form)
+            ms = timed(lambda: ctx.audio_resample_raw(pcm, nin, ch, rate, 22050, out, k, amv.MEM_DEVICE))
+            line("audio_resample", k, "output samples/s", ms, 2 * (nin * ch + k),
+                 dict(config="%d Hz x %d ch -> 22050 Hz mono, %d input samples per channel" % (rate, ch, nin),
+                      form={1: "tiles", 2: "phase rows"}[form]))
+        ctx.set_option("resample_form", 2)
         del pcm, out
 
 

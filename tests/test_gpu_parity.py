@@ -808,9 +808,20 @@ def test_audio_resampler_matches_golden(ctx, case):
 
 @pytest.mark.parametrize("rate,ch,n", [(44100, 2, 50000), (48000, 1, 70000), (8000, 1, 9000), (22050, 2, 30000), (11025, 1, 20000),
                                         (32000, 2, 3000000), (44100, 1, 1000), (48000, 2, 100), (96000, 2, 40000), (16000, 1, 20),
-                                        (96000, 1, 50), (44100, 2, 1), (705600, 1, 300000), (705600, 2, 2000)])
+                                        (96000, 1, 50), (44100, 2, 1), (705600, 1, 300000), (705600, 2, 2000), (11025, 2, 30000), (47999, 1, 40000), (22049, 1, 30000),
+                                        (24000, 2, 50000)])
 @pytest.mark.parametrize("kind", ["noise", "tones", "square"])
-def test_audio_resampler_identical(ctx, oracle, rate, ch, n, kind):
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_audio_resampler_identical(ctx, oracle, rate, ch, n, kind, form):
+    """every kernel form (option resample_form: direct, tiles, phase rows)"""
+    ctx.set_option("resample_form", form)
+    try:
+        _audio_resampler_identical(ctx, oracle, rate, ch, n, kind)
+    finally:
+        ctx.set_option("resample_form", 2)
+
+
+def _audio_resampler_identical(ctx, oracle, rate, ch, n, kind):
     """host and device buffers; streams shorter than the filter (mirrored taps only), beyond 2^21 samples (64-bit positions),
     full-scale square waves (32-bit accumulator, saturation), a 32:1 reduction (640 taps: the direct kernel form)"""
     import torch
@@ -845,7 +856,16 @@ def test_audio_resampler_packet_feed(ctx, oracle, rate, ch):
 
 
 @pytest.mark.parametrize("rate,ch,n,world", [(44100, 2, 200000, 4), (8000, 1, 50000, 8), (48000, 1, 3000, 3), (96000, 2, 60, 2)])
-def test_audio_resampler_sharded_stream(ctx, oracle, rate, ch, n, world):
+@pytest.mark.parametrize("form", [1, 2])
+def test_audio_resampler_sharded_stream(ctx, oracle, rate, ch, n, world, form):
+    ctx.set_option("resample_form", form)
+    try:
+        _audio_resampler_sharded_stream(ctx, oracle, rate, ch, n, world)
+    finally:
+        ctx.set_option("resample_form", 2)
+
+
+def _audio_resampler_sharded_stream(ctx, oracle, rate, ch, n, world):
     """sharding.resample_shard: one stream split by output range as `world` GPUs would take it (here one after the
     other on one GPU, device buffers): the pieces concatenate to the stream's output"""
     import torch
