@@ -55,9 +55,32 @@ k_range(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, i
     }
 }
 
+// tight planes (pitch = width, frame stride = width * rows, 16-byte aligned ends): the batch is one linear array and the
+// index needs no division into (frame, row, column)
+template <int DIR, bool CHROMA>
+__global__ void __launch_bounds__(256)
+k_range_flat(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t units) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 q = src[i];
+        q.x = range_word<DIR, CHROMA>(q.x); q.y = range_word<DIR, CHROMA>(q.y);
+        q.z = range_word<DIR, CHROMA>(q.z); q.w = range_word<DIR, CHROMA>(q.w);
+        dst[i] = q;
+    }
+}
+
 template <int DIR, bool CHROMA>
 static void launch_plane(const uint8_t *src, uint8_t *dst, int width, int rows, int n, int ls_in, int ls_out, uint64_t fs_in,
                          uint64_t fs_out, cudaStream_t s) {
+    const uint64_t bytes = (uint64_t)width * rows * n;
+    if (ls_in == width && ls_out == width && fs_in == (uint64_t)width * rows && fs_out == fs_in && (bytes & 15) == 0 &&
+        ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0)) {
+        const int64_t units = (int64_t)(bytes >> 4);
+        int64_t grid = (units + 255) / 256;
+        if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+        if (grid < 1) grid = 1;
+        k_range_flat<DIR, CHROMA><<<(unsigned)grid, 256, 0, s>>>(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), units);
+        return;
+    }
     const bool vec = ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)ls_in | (uintptr_t)ls_out | fs_in | fs_out) & 15) == 0);
     const int64_t total = (int64_t)(vec ? (width + 15) >> 4 : width) * rows * n;
     int64_t grid = (total + 255) / 256;
