@@ -108,6 +108,9 @@ AMV_API void        amv_host_free(void *p);
  *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream
  *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose)
  *   "host_zero_copy_packets"       0 = DMA pinned decoder input into a device copy instead of reading it in place
+ *   "encode_rounds"                0 = the one-kernel encoder instead of k_encode16 + k_encode
+ *   "scale_form"                   scaler kernel: 1 (default) tiles, 2 tiles with staged source rows, 0 direct
+ *   "resample_form"                audio resampler kernel: 2 (default) phase rows, 1 tiles, 0 direct
  * One option DOES select an algorithm, like the reference's AVCodecContext.trellis does:
  *   "adpcm_trellis"                0 (default) = adpcm_ima_compress_sample (adpcm.c:219-227);
  *                                  1..5 = the -trellis N beam search (adpcm_compress_trellis, adpcm.c:287-443) */
