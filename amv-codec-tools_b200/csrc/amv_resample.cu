@@ -165,7 +165,7 @@ k_scale_plane(ScaleArgs a, ScaleBanks banks) {
 // of line buffers); pass 2 runs the vertical filter from there, 4 pixels per thread.  Against the direct form this
 // drops the horizontal work from 4 rows per output row to (rows touched) / 16 and turns 16 byte loads per pixel
 // into (rows touched) / 4 of them plus one 32-bit shared-memory read.
-constexpr int kTileW = 64, kTileRowsMax = 320;      // tile height: 128, 64, 32 or 16 output rows, the tallest whose source rows fit
+constexpr int kTileW = 64, kTileRowsMax = 320;      // tile height: 256, 128, 64, 32 or 16 output rows, the tallest whose source rows fit
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
@@ -316,8 +316,8 @@ static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih,
     const bool vec = (ow & 3) == 0 && ((((uintptr_t)dst | (uintptr_t)ols | ofs) & 3) == 0);
     // the tallest tile whose source rows fit the line buffer: taller tiles share more horizontally filtered rows between
     // their output rows and spread the per-block set-up over more pixels (measured at 2:1: 4.19 / 3.36 / 3.27 ms for
-    // 16 / 64 / 128 rows; 1:3 enlargement: 7.2 / 4.15 / 3.56 ms)
-    int tile_h = 128;
+    // 16 / 64 / 128 rows; 1:3 enlargement: 7.2 / 4.15 / 3.56 / 3.29 ms with 256)
+    int tile_h = 256;
     const int64_t cols_touched = (((int64_t)(kTileW - 1) * b.h_incr) >> 16) + 5 + 3;      // + word alignment of the first column
     const int64_t pitch = (cols_touched + 3 + 15) & ~(int64_t)15;
     auto rows_of = [&](int th) { return (((int64_t)(th - 1) * b.v_incr) >> 16) + 5; };
