@@ -377,7 +377,7 @@ static int adpcm_grid(int units) {
 
 void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *off, const uint32_t *size, int n,
                          int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s) {
-    k_adpcm_decode<<<adpcm_grid(n), kAdpcmThreads, 0, s>>>(chunks, chunks_bytes, off, size, n, pcm, pcm_samples, pcm_off,
+    AMV_LAUNCH(k_adpcm_decode, adpcm_grid(n), kAdpcmThreads, 0, s, chunks, chunks_bytes, off, size, n, pcm, pcm_samples, pcm_off,
                                                            status);
 }
 
@@ -387,8 +387,8 @@ void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_
     if (trellis > 0) {
         const int grid = (nstreams + 127) / 128;
 #define AMV_TRELLIS_CASE(T)                                                                                              \
-        case T: k_adpcm_encode_trellis<(1 << T)><<<grid, 128, 0, s>>>(pcm, pcm_samples, pcm_off, nsamples, first_chunk,   \
-                                                                      nstreams, step_in, step_out, out, out_bytes, out_off, status); break;
+        case T: AMV_LAUNCH((k_adpcm_encode_trellis<(1 << T)>), grid, 128, 0, s, pcm, pcm_samples, pcm_off, nsamples, first_chunk,   \
+                           nstreams, step_in, step_out, out, out_bytes, out_off, status); break;
         switch (trellis) {
             AMV_TRELLIS_CASE(1) AMV_TRELLIS_CASE(2) AMV_TRELLIS_CASE(3) AMV_TRELLIS_CASE(4) AMV_TRELLIS_CASE(5)
             default: break;
@@ -396,7 +396,7 @@ void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_
 #undef AMV_TRELLIS_CASE
         return;
     }
-    k_adpcm_encode<<<adpcm_grid(nstreams), kAdpcmThreads, 0, s>>>(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams,
+    AMV_LAUNCH(k_adpcm_encode, adpcm_grid(nstreams), kAdpcmThreads, 0, s, pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams,
                                                                   step_in, step_out, out, out_bytes, out_off, status);
 }
 

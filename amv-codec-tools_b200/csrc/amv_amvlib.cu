@@ -183,8 +183,8 @@ void launch_idct_bgr(const uint32_t *tokens, const uint32_t *blk_off, const uint
     const int64_t items = (int64_t)n * nseg;
     const unsigned grid = (unsigned)((items + kBgrWarps - 1) / kBgrWarps);
     const bool fast = (((uintptr_t)bgr | (uintptr_t)line_bytes | frame_stride) & 3) == 0;
-    if (fast) k_idct_bgr<true><<<grid, kBgrThreads, 0, s>>>(tokens, blk_off, slot_off, scan_len, n, g, nseg, bgr, line_bytes, frame_stride);
-    else      k_idct_bgr<false><<<grid, kBgrThreads, 0, s>>>(tokens, blk_off, slot_off, scan_len, n, g, nseg, bgr, line_bytes, frame_stride);
+    if (fast) AMV_LAUNCH(k_idct_bgr<true>, grid, kBgrThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, nseg, bgr, line_bytes, frame_stride);
+    else      AMV_LAUNCH(k_idct_bgr<false>, grid, kBgrThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, nseg, bgr, line_bytes, frame_stride);
 }
 
 }  // namespace amv

@@ -11,6 +11,16 @@
 #define AMV_D  inline
 #endif
 
+// Kernel launch and dynamic shared memory go through two macros so that tests/host_emul/simt can compile the very
+// same kernel sources as plain C++ and run them on the CPU (-DAMV_EMUL, tests only; the product is nvcc's build).
+#if defined(AMV_EMUL)
+#define AMV_LAUNCH(kernel, grid, block, smem, stream, ...) AMV_EMUL_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+#define AMV_EXTERN_SHARED(type, name, align) type *name = reinterpret_cast<type *>(simt::dyn_smem())
+#else
+#define AMV_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define AMV_EXTERN_SHARED(type, name, align) extern __shared__ __align__(align) type name[]
+#endif
+
 // per-unit status bits: keep in sync with include/amvcuda.h
 #define AMV_ST_SHORT    (1 << 0)
 #define AMV_ST_BADCODE  (1 << 1)
@@ -78,7 +88,22 @@ AMV_HD uint32_t bswap32(uint32_t v) {
 
 AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-#if defined(__CUDACC__)
+#if defined(AMV_EMUL)
+// emulator: "shared-window addresses" are offsets from a fixed origin below the emulator's static storage
+inline uint32_t smem_addr(const void *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) - simt::smem_base();
+    if (a >= (1u << 24)) abort();            // not a __shared__ object (or the emulator's window is misplaced)
+    return (uint32_t)a;
+}
+template <class T> inline T *smem_ptr(uint32_t saddr) { return reinterpret_cast<T *>(simt::smem_base() + saddr); }
+inline uint32_t lds32(uint32_t saddr) { return *smem_ptr<uint32_t>(saddr); }
+inline int lds_s16(uint32_t saddr) { return *smem_ptr<int16_t>(saddr); }
+inline uint4 lds128(uint32_t saddr) { return *smem_ptr<uint4>(saddr); }
+inline void sts32(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) = v; }
+inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (uint16_t)v; }
+inline void sts128(uint32_t saddr, const uint4 &v) { *smem_ptr<uint4>(saddr) = v; }
+inline void red_or_shared(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) |= v; }
+#elif defined(__CUDACC__)
 // Shared memory through explicit 32-bit shared-window addresses: keeps the hot loops free of
 // generic-address arithmetic (ptxas otherwise re-derives the shared window base inside them).
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
@@ -103,6 +128,17 @@ __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
 }
 __device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(saddr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 #endif
 

@@ -320,7 +320,7 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
            uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */, int flavor,
            const DecTableSet *__restrict__ tabs, const uint8_t *__restrict__ qtab /* kFlavorJpeg: 2 x 64 quantisers per frame */,
            int nl, int nc /* blocks per MCU: luma, one chroma component */) {
-    extern __shared__ uint8_t sync_smem_raw[];
+    AMV_EXTERN_SHARED(uint8_t, sync_smem_raw, 16);
     const uint32_t raw_s = smem_addr(sync_smem_raw);
     SyncSmem &S = *reinterpret_cast<SyncSmem *>(sync_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
     const int nlut = tabs->flat.count;
@@ -517,12 +517,6 @@ struct TokSmem {
 };
 constexpr size_t kTokSmemBytes = sizeof(TokSmem) + 2048;
 
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-    return v;
-}
-
 template <int FLAVOR>
 __global__ void __launch_bounds__(kTokThreads)
 k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
@@ -534,7 +528,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     constexpr bool kPerFrameQ = FLAVOR == kFlavorJpeg || FLAVOR == kFlavorJpegDri;
     // a restart can add 23 bits (alignment + the marker) to what the symbols of a period consume: service twice as often
     constexpr int kPeriod = FLAVOR == kFlavorJpegDri ? 2 : kTokPeriod;
-    extern __shared__ uint8_t tok_smem_raw[];
+    AMV_EXTERN_SHARED(uint8_t, tok_smem_raw, 16);
     const uint32_t raw_s = smem_addr(tok_smem_raw);
     TokSmem &S = *reinterpret_cast<TokSmem *>(tok_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
     const int nlut = tabs->flat.count;
@@ -817,7 +811,7 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (gi + j >= first && gi + j <= last)
-                asm volatile("st.shared.u16 [%0], %1;" :: "r"(slot_s + (tk[j] >> 16)), "h"((unsigned short)tk[j]) : "memory");
+                sts16(slot_s + (tk[j] >> 16), tk[j]);
         q = nq;
     }
 
@@ -904,7 +898,7 @@ bool build_dec_table_set(void *host_buf, const uint8_t counts[4][16], const uint
 
 void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_t pad, uint64_t *off,
                        uint64_t *carry_io, cudaStream_t s) {
-    k_scan_sizes<<<1, 1024, 0, s>>>(size, n, align_mask, pad, off, carry_io);
+    AMV_LAUNCH(k_scan_sizes, 1, 1024, 0, s, size, n, align_mask, pad, off, carry_io);
 }
 
 void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
@@ -914,7 +908,7 @@ void launch_unstuff(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pk
     // independent chains per SM (measured 2.6 / 2.1 / 1.9 ms per 100k frames at 256 / 128 / 64 threads)
     constexpr int kThreads = 64, kPerSM = 24;
     const int grid = n < kNumSMs * kPerSM ? n : kNumSMs * kPerSM;
-    k_unstuff<kThreads><<<grid, kThreads, 0, s>>>(pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes,
+    AMV_LAUNCH(k_unstuff<kThreads>, grid, kThreads, 0, s, pkts, pkts_bytes, pkt_off, pkt_size, n, scratch, slot_off, scratch_bytes,
                                                   scan_len, status, head, literal ? 1 : 0);
 }
 
@@ -948,7 +942,7 @@ __global__ void k_mjpeg_check(const uint8_t *__restrict__ pkts, uint64_t pkts_by
 void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size, int n,
                         const uint8_t *hdr, uint32_t hdr_len, uint32_t qpos0, uint32_t qpos1, uint8_t *qtab,
                         uint32_t *scan_len, int32_t *status, cudaStream_t s) {
-    k_mjpeg_check<<<(n + 7) / 8, 256, 0, s>>>(pkts, pkts_bytes, pkt_off, pkt_size, n, hdr, hdr_len, qpos0, qpos1, qtab, scan_len,
+    AMV_LAUNCH(k_mjpeg_check, (n + 7) / 8, 256, 0, s, pkts, pkts_bytes, pkt_off, pkt_size, n, hdr, hdr_len, qpos0, qpos1, qtab, scan_len,
                                               status);
 }
 
@@ -962,7 +956,7 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
         cudaFuncSetAttribute(k_vlc_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes);
         attr_set = true;
     }
-    k_vlc_sync<<<grid, kTokThreads, kSyncSmemBytes, s>>>(scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
+    AMV_LAUNCH(k_vlc_sync, grid, kTokThreads, kSyncSmemBytes, s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
                                             amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab, nl, nc);
 }
 
@@ -981,16 +975,16 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
         attr_set = true;
     }
     if (amvlib)
-        k_vlc_tokens<kFlavorAmvlib><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+        AMV_LAUNCH(k_vlc_tokens<kFlavorAmvlib>, grid, kTokThreads, kTokSmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                  tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
     else if (qtab && restart)
-        k_vlc_tokens<kFlavorJpegDri><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts,
+        AMV_LAUNCH(k_vlc_tokens<kFlavorJpegDri>, grid, kTokThreads, kTokSmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts,
                                                                   nblk, tokens, blk_off, status, tabs, qtab, nl, nc, restart);
     else if (qtab)
-        k_vlc_tokens<kFlavorJpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+        AMV_LAUNCH(k_vlc_tokens<kFlavorJpeg>, grid, kTokThreads, kTokSmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                tokens, blk_off, status, tabs, qtab, nl, nc, 0);
     else
-        k_vlc_tokens<kFlavorFfmpeg><<<grid, kTokThreads, kTokSmemBytes, s>>>(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+        AMV_LAUNCH(k_vlc_tokens<kFlavorFfmpeg>, grid, kTokThreads, kTokSmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                  tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
 }
 
@@ -1002,10 +996,10 @@ void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t
     const bool fast = (g.w % 16 == 0) &&
                       ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
     if (fast)
-        k_idct<true><<<(unsigned)grid, kIdctThreads, 0, s>>>(tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
+        AMV_LAUNCH(k_idct<true>, (unsigned)grid, kIdctThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
                                                              fs_y, fs_c);
     else
-        k_idct<false><<<(unsigned)grid, kIdctThreads, 0, s>>>(tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
+        AMV_LAUNCH(k_idct<false>, (unsigned)grid, kIdctThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
                                                               fs_y, fs_c);
 }
 

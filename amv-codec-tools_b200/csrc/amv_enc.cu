@@ -81,7 +81,7 @@ k_encode(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const u
          int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
          uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
          int32_t *__restrict__ status, const int32_t *__restrict__ only /* optional: encode frame f only if only[f] != 0 */) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    AMV_EXTERN_SHARED(uint8_t, smem_raw, 16);
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kEncHuffEntries; i += kEncThreads) S.huff[i] = g_enc_tables.huff.e[i];
@@ -340,7 +340,7 @@ k_encode16(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const
            int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
            uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
            int32_t *__restrict__ status, int32_t *__restrict__ redo) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    AMV_EXTERN_SHARED(uint8_t, smem_raw, 16);
     Enc16Smem &S = *reinterpret_cast<Enc16Smem *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kEncHuffEntries; i += kEncThreads) S.huff[i] = g_enc_tables.huff.e[i];
@@ -677,33 +677,33 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
     // ordinary-content sizes), then k_encode for the frames it flagged because a block's string outgrew its column.
     if (redo) {
         if (fast)
-            k_encode16<true><<<encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+            AMV_LAUNCH(k_encode16<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
                                                                                     slot_stride, pkt_cap, out_size, status, redo);
         else
-            k_encode16<false><<<encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+            AMV_LAUNCH(k_encode16<false>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
                                                                                      slot_stride, pkt_cap, out_size, status, redo);
     }
     if (fast)
-        k_encode<true><<<encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+        AMV_LAUNCH(k_encode<true>, encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
                                                                             slot_stride, pkt_cap, out_size, status, redo);
     else
-        k_encode<false><<<encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s>>>(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
+        AMV_LAUNCH(k_encode<false>, encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
                                                                              slot_stride, pkt_cap, out_size, status, redo);
 }
 
 void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
                     uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s) {
     const int grid = n < kNumSMs * 8 ? (n < 1 ? 1 : n) : kNumSMs * 8;
-    k_compact<<<grid, 256, 0, s>>>(slots, slot_stride, size, off, n, out, out_cap, status);
+    AMV_LAUNCH(k_compact, grid, 256, 0, s, slots, slot_stride, size, off, n, out, out_cap, status);
 }
 
 void launch_export_meta(const uint64_t *off, const uint32_t *sz, const int32_t *st, uint64_t *hoff, uint32_t *hsz, int32_t *hst,
                         int n, cudaStream_t s) {
-    k_export_meta<<<(n + 255) / 256, 256, 0, s>>>(off, sz, st, hoff, hsz, hst, n);
+    AMV_LAUNCH(k_export_meta, (n + 255) / 256, 256, 0, s, off, sz, st, hoff, hsz, hst, n);
 }
 
 void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, uint64_t base, cudaStream_t s) {
-    k_slot_offsets<<<(n + 255) / 256, 256, 0, s>>>(off, n, stride, base);
+    AMV_LAUNCH(k_slot_offsets, (n + 255) / 256, 256, 0, s, off, n, stride, base);
 }
 
 }  // namespace amv

@@ -78,7 +78,7 @@ static void launch_plane(const uint8_t *src, uint8_t *dst, int width, int rows, 
         int64_t grid = (units + 255) / 256;
         if (grid > kNumSMs * 32) grid = kNumSMs * 32;
         if (grid < 1) grid = 1;
-        k_range_flat<DIR, CHROMA><<<(unsigned)grid, 256, 0, s>>>(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), units);
+        AMV_LAUNCH((k_range_flat<DIR, CHROMA>), (unsigned)grid, 256, 0, s, reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), units);
         return;
     }
     const bool vec = ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)ls_in | (uintptr_t)ls_out | fs_in | fs_out) & 15) == 0);
@@ -86,7 +86,7 @@ static void launch_plane(const uint8_t *src, uint8_t *dst, int width, int rows, 
     int64_t grid = (total + 255) / 256;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
     if (grid < 1) grid = 1;
-    k_range<DIR, CHROMA><<<(unsigned)grid, 256, 0, s>>>(src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, vec ? 1 : 0);
+    AMV_LAUNCH((k_range<DIR, CHROMA>), (unsigned)grid, 256, 0, s, src, dst, width, rows, n, ls_in, ls_out, fs_in, fs_out, vec ? 1 : 0);
 }
 
 // one plane of `width` x `rows` bytes (chroma: the two chroma tables)

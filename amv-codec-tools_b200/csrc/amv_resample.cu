@@ -233,7 +233,7 @@ k_scale_tile(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int tile_h
 template <bool VEC, bool WORDS>
 __global__ void __launch_bounds__(256)
 k_scale_tile_staged(ScaleArgs a, ScaleBanks banks, int tiles_x, int tiles_y, int tile_h, int rows_max, int pitch) {
-    extern __shared__ __align__(16) uint8_t s_dyn[];
+    AMV_EXTERN_SHARED(uint8_t, s_dyn, 16);
     __shared__ int2 s_h[16], s_v[16];
     uint8_t *s_src = s_dyn;                                   // [rows_max][pitch]
     uint8_t *s_line = s_dyn + (size_t)rows_max * pitch;       // [rows_max][64]
@@ -331,15 +331,15 @@ static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih,
     if (form >= 2 && rows_touched <= kTileRowsMax && smem <= 40 * 1024 && tiles <= 0x7fffffff) {
         const unsigned g = (unsigned)tiles;
         const int rm = (int)rows_touched, pt = (int)pitch;
-        if (vec && words)       k_scale_tile_staged<true, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
-        else if (vec)           k_scale_tile_staged<true, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
-        else if (words)         k_scale_tile_staged<false, true><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
-        else                    k_scale_tile_staged<false, false><<<g, 256, (size_t)smem, s>>>(a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        if (vec && words)       AMV_LAUNCH((k_scale_tile_staged<true, true>), g, 256, (size_t)smem, s, a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        else if (vec)           AMV_LAUNCH((k_scale_tile_staged<true, false>), g, 256, (size_t)smem, s, a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        else if (words)         AMV_LAUNCH((k_scale_tile_staged<false, true>), g, 256, (size_t)smem, s, a, b, tiles_x, tiles_y, tile_h, rm, pt);
+        else                    AMV_LAUNCH((k_scale_tile_staged<false, false>), g, 256, (size_t)smem, s, a, b, tiles_x, tiles_y, tile_h, rm, pt);
         return;
     }
     if (form >= 1 && rows_touched <= kTileRowsMax && tiles <= 0x7fffffff) {  // taps straight from global memory (L1)
-        if (vec) k_scale_tile<true><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y, tile_h);
-        else     k_scale_tile<false><<<(unsigned)tiles, 256, 0, s>>>(a, b, tiles_x, tiles_y, tile_h);
+        if (vec) AMV_LAUNCH(k_scale_tile<true>, (unsigned)tiles, 256, 0, s, a, b, tiles_x, tiles_y, tile_h);
+        else     AMV_LAUNCH(k_scale_tile<false>, (unsigned)tiles, 256, 0, s, a, b, tiles_x, tiles_y, tile_h);
         return;
     }
     // extreme reductions (the tile's rows exceed the line buffer): the direct form
@@ -347,8 +347,8 @@ static void launch_scale_plane(const uint8_t *src, uint8_t *dst, int iw, int ih,
     int64_t grid = (total + 255) / 256;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
     if (grid < 1) grid = 1;
-    if (vec) k_scale_plane<true><<<(unsigned)grid, 256, 0, s>>>(a, b);
-    else     k_scale_plane<false><<<(unsigned)grid, 256, 0, s>>>(a, b);
+    if (vec) AMV_LAUNCH(k_scale_plane<true>, (unsigned)grid, 256, 0, s, a, b);
+    else     AMV_LAUNCH(k_scale_plane<false>, (unsigned)grid, 256, 0, s, a, b);
 }
 
 int launch_scale_frames(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
@@ -528,9 +528,9 @@ static bool launch_rows_m(int m, unsigned blocks, int Q, const int16_t *in, int6
                           cudaStream_t s) {
     const uint32_t sq = (uint32_t)(D / S), sr = (uint32_t)(D % S);
     switch (m) {
-    case 8: k_audio_resample_rows<CH, 8, SPLIT><<<blocks, Q, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
-    case 4: k_audio_resample_rows<CH, 4, SPLIT><<<blocks, Q, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
-    case 2: k_audio_resample_rows<CH, 2, SPLIT><<<blocks, Q, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
+    case 8: AMV_LAUNCH((k_audio_resample_rows<CH, 8, SPLIT>), blocks, Q, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
+    case 4: AMV_LAUNCH((k_audio_resample_rows<CH, 4, SPLIT>), blocks, Q, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
+    case 2: AMV_LAUNCH((k_audio_resample_rows<CH, 2, SPLIT>), blocks, Q, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, sq, sr, q_step, k_base, out, n_out); return true;
     default: return false;
     }
 }
@@ -575,14 +575,14 @@ void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int
         }
     }
     if (audio_form >= 1 && span <= kWinMax && blocks <= 0x7fffffff) {
-        if (in_ch == 2) k_audio_resample_tile<2><<<(unsigned)blocks, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
-        else            k_audio_resample_tile<1><<<(unsigned)blocks, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
+        if (in_ch == 2) AMV_LAUNCH(k_audio_resample_tile<2>, (unsigned)blocks, 256, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
+        else            AMV_LAUNCH(k_audio_resample_tile<1>, (unsigned)blocks, 256, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, (uint32_t)(D / S), (uint32_t)(D % S), k_base, out, n_out);
         return;
     }
     int64_t grid = blocks;
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    if (in_ch == 2) k_audio_resample<2><<<(unsigned)grid, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, k_base, out, n_out);
-    else            k_audio_resample<1><<<(unsigned)grid, 256, 0, s>>>(in, n_in, in_base, bank, len, len8, index0, D, S, k_base, out, n_out);
+    if (in_ch == 2) AMV_LAUNCH(k_audio_resample<2>, (unsigned)grid, 256, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, k_base, out, n_out);
+    else            AMV_LAUNCH(k_audio_resample<1>, (unsigned)grid, 256, 0, s, in, n_in, in_base, bank, len, len8, index0, D, S, k_base, out, n_out);
 }
 
 }  // namespace amv

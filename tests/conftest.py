@@ -14,8 +14,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "ref: needs the compiled reference oracle/_ref/libamvref.so")
 
 
+# Developer switch, never set by the driver: AMV_EMUL=1 points the GPU parity tests at tests/host_emul/simt's
+# libamvcuda_emul.so (the kernel sources compiled as C++ on the CPU SIMT emulator), so kernel changes can be checked
+# in a container without a GPU before GPU time is spent.  The product library and package are untouched by this.
+EMUL = os.environ.get("AMV_EMUL") == "1"
+if EMUL:
+    import subprocess
+    _so = subprocess.check_output([os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul", "simt", "build.sh")],
+                                  text=True).strip().splitlines()[-1]
+    import amv_codec_tools_b200 as _amv
+    _amv.AmvCuda.__init__.__defaults__ = (-1, None, _so)
+    _amv.load_library.__defaults__ = (_so,)
+
+
 def pytest_collection_modifyitems(config, items):
     # GPU tests must never silently pass on a box without a device
+    if EMUL:
+        return
     try:
         import torch
         has_gpu = torch.cuda.is_available()
