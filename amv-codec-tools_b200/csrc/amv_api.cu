@@ -58,7 +58,7 @@ struct amv_ctx {
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
     int opt_resample_form = 2;          // audio resampler: 2 = phase rows (M outputs per coefficient row), 1 = tiles, 0 = direct form
     int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
-    bool opt_encode_rounds = true;      // encoder: k_encode16 (homogeneous rounds) + k_encode for the frames it hands back
+    int opt_encode_rounds = 2;          // encoder: 2 = k_encode16v2, 1 = k_encode16 (each + k_encode for the frames it hands back), 0 = k_encode alone
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
     // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
@@ -262,7 +262,7 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
     if (layout == AMV_LAYOUT_SLOTS) {
         if (slot_base + (uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
         { ScopedTimer tm(ctx, KK_ENCODE);
-          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out + slot_base, pkt_cap, pkt_cap, out_size, st, redo, ctx->stream); }
+          launch_encode(y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, out + slot_base, pkt_cap, pkt_cap, out_size, st, redo, ctx->opt_encode_rounds, ctx->stream); }
         launch_slot_offsets(out_off, n, pkt_cap, slot_base, ctx->stream);
         return check_launch(ctx, "encode kernels", 1 + enc_launches);
     }
@@ -280,7 +280,7 @@ int encode_device(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_
         const int m = n - f0 < sub ? n - f0 : sub;
         { ScopedTimer tm(ctx, KK_ENCODE);
           launch_encode(y + fs_y * f0, u + fs_c * f0, v + fs_c * f0, ls_y, ls_c, fs_y, fs_c, m, g, qscale ? qscale + f0 : nullptr,
-                        slots, stride, pkt_cap, out_size + f0, st + f0, redo ? redo + f0 : nullptr, ctx->stream); }
+                        slots, stride, pkt_cap, out_size + f0, st + f0, redo ? redo + f0 : nullptr, ctx->opt_encode_rounds, ctx->stream); }
         launch_scan_sizes(out_size + f0, m, 0u, 0u, out_off + f0, carry, ctx->stream);
         { ScopedTimer tm(ctx, KK_COMPACT);
           launch_compact(slots, stride, out_size + f0, out_off + f0, m, out, out_cap, st + f0, ctx->stream); }
@@ -621,7 +621,11 @@ AMV_API int amv_create(const amv_params *params, amv_ctx **out_ctx) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AMV_ERR_CUDA; }
         ctx->own_stream = true;
     }
-    cudaError_t e = upload_dec_tables(ctx->stream);
+    // tables and function attributes are per device: set them up for this context's device (a process-wide
+    // "done" flag left every device after the first without the shared-memory opt-in)
+    cudaError_t e = encode_setup_device();
+    if (e == cudaSuccess) e = decode_setup_device();
+    if (e == cudaSuccess) e = upload_dec_tables(ctx->stream);
     if (e == cudaSuccess) e = upload_enc_tables(ctx->stream);
     if (e == cudaSuccess) e = upload_adpcm_tables(ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -665,7 +669,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "encode_slot_workspace_bytes")) { ctx->opt_slot_ws_bytes = (uint64_t)value; return AMV_OK; }
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
-    if (!strcmp(key, "encode_rounds")) { ctx->opt_encode_rounds = value != 0; return AMV_OK; }
+    if (!strcmp(key, "encode_rounds")) {
+        if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
+        ctx->opt_encode_rounds = (int)value;
+        return AMV_OK;
+    }
     if (!strcmp(key, "resample_form")) {
         if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
         ctx->opt_resample_form = (int)value;

@@ -88,6 +88,17 @@ AMV_HD uint32_t bswap32(uint32_t v) {
 
 AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// index of the most significant set bit (v != 0): one FLO
+AMV_HD int msb_index(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
 #if defined(AMV_EMUL)
 // emulator: "shared-window addresses" are offsets from a fixed origin below the emulator's static storage
 inline uint32_t smem_addr(const void *p) {
@@ -101,6 +112,7 @@ inline int lds_s16(uint32_t saddr) { return *smem_ptr<int16_t>(saddr); }
 inline uint4 lds128(uint32_t saddr) { return *smem_ptr<uint4>(saddr); }
 inline void sts32(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) = v; }
 inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (uint16_t)v; }
+inline void sts8(uint32_t saddr, uint32_t v) { *smem_ptr<uint8_t>(saddr) = (uint8_t)v; }
 inline void sts128(uint32_t saddr, const uint4 &v) { *smem_ptr<uint4>(saddr) = v; }
 inline void red_or_shared(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) |= v; }
 #elif defined(__CUDACC__)
@@ -136,6 +148,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" :: "r"(saddr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

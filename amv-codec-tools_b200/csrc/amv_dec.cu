@@ -896,6 +896,16 @@ bool build_dec_table_set(void *host_buf, const uint8_t counts[4][16], const uint
     return fill_table_set(*static_cast<DecTableSet *>(host_buf), H, qzz, sync_ok);
 }
 
+// opt-in to more than 48 KB of dynamic shared memory: per device, called from amv_create
+cudaError_t decode_setup_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_vlc_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+    return e;
+}
+
 void launch_scan_sizes(const uint32_t *size, int n, uint32_t align_mask, uint32_t pad, uint64_t *off,
                        uint64_t *carry_io, cudaStream_t s) {
     AMV_LAUNCH(k_scan_sizes, 1, 1024, 0, s, size, n, align_mask, pad, off, carry_io);
@@ -951,11 +961,6 @@ void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uin
                      int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_vlc_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes);
-        attr_set = true;
-    }
     AMV_LAUNCH(k_vlc_sync, grid, kTokThreads, kSyncSmemBytes, s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
                                             amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab, nl, nc);
 }
@@ -966,14 +971,6 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                        cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
-        cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
-        cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
-        cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
-        attr_set = true;
-    }
     if (amvlib)
         AMV_LAUNCH(k_vlc_tokens<kFlavorAmvlib>, grid, kTokThreads, kTokSmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                  tokens, blk_off, status, tabs, nullptr, nl, nc, 0);

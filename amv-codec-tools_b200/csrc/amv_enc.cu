@@ -594,6 +594,352 @@ k_encode16(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_encode16v2: k_encode16 with three cuts in the instruction stream (same rounds, same strings, same bytes).
+//  * The quantiser is not evaluated for the 63 AC coefficients of every block, only for the ones that survive it:
+//    a coefficient quantises to non-zero iff |c| * qmat >= 2^22, i.e. iff c * c >= T * T with T = ceil(2^22 / qmat),
+//    so the transform stage spends one multiply-add (c * c - T^2) and one funnel shift per coefficient to build the
+//    zigzag mask of survivors, stores the RAW coefficient, and the Huffman loop quantises what it is about to code
+//    (dct_quantize_c, mpegvideo_enc.c:3686-3716: level = |c| * qmat >> 22, sign restored).
+//  * The bit writer of the Huffman loop has no branch: the word under construction is stored every time and the
+//    pointer advances by a select.
+//  * Stuffed bytes are staged in shared memory (the luma staging columns are free by then) and leave as aligned
+//    128-bit stores; the bytes short of a 16-byte unit wait in registers (one per lane) for the next half segment.
+//    The packet slot must be 16-byte aligned (launch_encode checks; else the one-kernel path runs).
+// ------------------------------------------------------------------------------------------------
+struct Enc16v2WarpSmem {
+    union {                                 // never live at the same time (A,B use coef; D,E use seg)
+        uint16_t coef[64 * 32];             // halfword k*32 + lane : RAW zigzag coefficient k of the lane's block
+        uint32_t seg[kSeg16Words];          // the half segment's contiguous bit string
+    } u;
+    union {
+        uint32_t stageL[kWL * 32];          // word w*32 + lane : the lane's luma string of this round
+        uint8_t  obuf[kWL * 32 * 4];        // stage E: the stuffed bytes of the half segment, in packet order
+    } s;
+    uint32_t stageC[kWC * 32];              // the lane's chroma string of this segment
+    int32_t  nthr2z[64];                    // zigzag k: -(T*T), T = smallest |coefficient| that quantises to non-zero
+    uint32_t qm10z[64];                     // zigzag k: qmat << 10
+    uint32_t lenC[32];                      // chroma string lengths: Cb of macroblock j at j, Cr at 16 + j
+    uint32_t cpre[20];                      // exclusive prefix over the macroblocks of lenCb + lenCr
+    int      carry_dc[4];                   // last DC of each component so far
+};
+struct Enc16v2Smem {
+    uint32_t huff[kEncHuffEntries];
+    Enc16v2WarpSmem w[kEncWarps];
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kEncThreads, 5)
+k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
+             int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
+             uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
+             int32_t *__restrict__ status, int32_t *__restrict__ redo) {
+    AMV_EXTERN_SHARED(uint8_t, smem_raw, 16);
+    Enc16v2Smem &S = *reinterpret_cast<Enc16v2Smem *>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kEncHuffEntries; i += kEncThreads) {
+        // (code << 5 | length) -> code left-aligned in the word, length in the low five bits (codes have at most 16 bits)
+        const uint32_t e = g_enc_tables.huff.e[i], l = e & 31u;
+        S.huff[i] = l ? ((e >> 5) << (32u - l)) | l : 0u;
+    }
+    __syncthreads();
+    Enc16v2WarpSmem &W = S.w[wid];
+    const int total_mb = g.mbw * g.mbh;
+    const uint32_t coef_s = smem_addr(&W.u.coef[lane]);          // coefficient k: + k*64
+    const uint32_t stageL_s = smem_addr(&W.s.stageL[lane]), stageC_s = smem_addr(&W.stageC[lane]);   // word w: + w*128
+    const uint32_t seg_s = smem_addr(&W.u.seg[0]);
+    const uint32_t qm_s = smem_addr(&W.qm10z[0]);
+    const uint32_t nthr_s = smem_addr(&W.nthr2z[0]);
+    const uint32_t obuf_s = smem_addr(&W.s.obuf[0]);
+    const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
+    int cur_qs = -1;
+
+    for (int f = gw; f < n; f += nw_total) {
+        const int qs = qscale ? qscale[f] : 2;
+        __syncwarp();
+        if (qs != cur_qs) {
+            for (int k = lane; k < 64; k += 32) {
+                // intra_matrix / q_intra_matrix for this frame (mpegvideo_enc.c:2866-2877, ff_convert_matrix :69-91)
+                int m = 8;
+                if (k) m = min(max(((int)g_enc_tables.intra_base[g_enc_tables.zigzag[k]] * qs) >> 3, 1), 255);
+                const uint32_t qmat = (1u << 22) / (uint32_t)(8 * m);
+                const uint32_t T = ((1u << 22) + qmat - 1u) / qmat;
+                W.qm10z[k] = qmat << 10;
+                W.nthr2z[k] = -(int32_t)(T * T);
+            }
+            cur_qs = qs;
+        }
+        if (lane < 3) W.carry_dc[lane] = 128;            // last_dc init (mpegvideo_enc.c:2033-2036)
+        uint32_t overflow = (qs < 2 || qs > 31) ? AMV_ST_RANGE : 0;      // qscale domain: SURVEY 9.13
+        uint32_t carry_word = 0;                        // partial word carried into the next half segment
+        uint8_t *pkt = slots + (uint64_t)f * slot_stride;
+        uint32_t G = 2;                                 // bytes produced so far (SOI); the last `oc` of them wait in `cbyte`
+        uint32_t oc = 2;                                // bytes short of a 16-byte unit, lane i holds byte i
+        uint32_t cbyte = lane == 0 ? 0xffu : 0xd8u;     // SOI (mjpegenc.c:197-204)
+        uint32_t r = 0;                                 // carried bits (sit in carry_word, MSB side)
+        bool too_big = false;                           // a string outgrew its staging column (warp-uniform)
+        __syncwarp();
+
+        for (int m0 = 0; m0 < total_mb && !too_big; m0 += 16) {
+            const int nmb = min(16, total_mb - m0);
+            const bool last_seg = m0 + 16 >= total_mb;
+            uint32_t lenC_own = 0;                       // this lane's chroma string of the segment
+
+            for (int rd = 0; rd < 3 && !too_big; rd++) {
+                const int hh = rd - 1;                   // which half of the segment a luma round covers
+                if (rd && 8 * hh >= nmb) break;
+                // ---- the lane's block in this round
+                const int comp = rd ? 0 : 1 + (lane >> 4);
+                const int mbi = rd ? 8 * hh + (lane >> 2) : (lane & 15);
+                const int b = rd ? (lane & 3) : 0;
+                const bool active = mbi < nmb;
+                const int vw = comp ? (g.w >> 1) : g.w, vh = comp ? (g.h >> 1) : g.h, r0 = comp ? g.c0 : g.y0;
+                const int ls = comp ? ls_c : ls_y;
+                const uint8_t *pl = (comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c);
+                const uint32_t huff_dc_s = smem_addr(&S.huff[comp ? kEncDcChroma : kEncDcLuma]);
+                const uint32_t huff_ac_s = smem_addr(&S.huff[comp ? kEncAcChroma : kEncAcLuma]);
+                const uint32_t stage_s = rd ? stageL_s : stageC_s;
+                const uint32_t cap_words = rd ? kWL : kWC;
+                uint32_t mask_lo = 0, mask_hi = 0;          // AC positions (zigzag) that quantise to non-zero
+                int dc = 0;
+
+                // ---------------- A: load, FDCT, survivor mask
+                if (active) {
+                    const int mb = m0 + mbi;
+                    const int mx = mb % g.mbw, my = mb / g.mbw;
+                    const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
+                    const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
+                    int v[64];
+#pragma unroll
+                    for (int yy = 0; yy < 8; yy++) {
+                        const int Y = min(by + yy, vh - 1);                 // bottom edge replication
+                        const uint8_t *row = pl + (int64_t)(r0 - Y) * ls;
+                        if (FAST) {
+                            const uint2 q = *reinterpret_cast<const uint2 *>(row + bx);
+#pragma unroll
+                            for (int xx = 0; xx < 4; xx++) {
+                                v[yy * 8 + xx]     = (q.x >> (8 * xx)) & 0xff;
+                                v[yy * 8 + 4 + xx] = (q.y >> (8 * xx)) & 0xff;
+                            }
+                        } else {
+#pragma unroll
+                            for (int xx = 0; xx < 8; xx++) v[yy * 8 + xx] = row[min(bx + xx, vw - 1)];   // right edge replication
+                        }
+                    }
+                    fdct_block(v);
+                    dc = quant_dc(v[0]);
+                    // c * c - T * T is negative exactly for the coefficients that quantise to zero: its sign bit is shifted
+                    // into the (inverted) mask, highest zigzag position first so that bit k ends up at position k
+                    uint32_t inv_lo = 0, inv_hi = 0;
+#pragma unroll
+                    for (int k4 = 15; k4 >= 0; k4--) {
+                        const uint4 t4 = lds128(nthr_s + 16 * k4);       // -(T*T) of positions 4*k4 .. 4*k4 + 3
+                        const int nt[4] = { (int)t4.x, (int)t4.y, (int)t4.z, (int)t4.w };
+#pragma unroll
+                        for (int kk = 3; kk >= 0; kk--) {
+                            const int k = 4 * k4 + kk;
+                            if (k == 0) continue;                         // the DC
+                            const int c = v[zigzag_at(k)];
+                            if (k >= 32) inv_hi = __funnelshift_l((uint32_t)(c * c + nt[kk]), inv_hi, 1);
+                            else         inv_lo = __funnelshift_l((uint32_t)(c * c + nt[kk]), inv_lo, 1);
+                            W.u.coef[k * 32 + lane] = (uint16_t)c;
+                        }
+                    }
+                    mask_lo = ~(inv_lo << 1) & ~1u;             // position 0 is the DC
+                    mask_hi = ~inv_hi;
+                }
+                // DC predictor: the previous block of the component is the previous lane (Y0..Y3 of a macroblock and
+                // the macroblocks themselves are consecutive lanes; Cb and Cr each fill 16 consecutive lanes)
+                const int dc_prev = __shfl_up_sync(0xffffffffu, dc, 1);
+                const bool first_of_comp = rd ? lane == 0 : (lane & 15) == 0;
+                const int pred = first_of_comp ? W.carry_dc[comp] : dc_prev;
+                __syncwarp();
+
+                // ---------------- B: Huffman-code the block into the lane's private bit string
+                uint32_t len = 0;
+                if (active) {
+                    uint32_t acc = 0;                   // MSB-first accumulator: the top `fill` bits are valid
+                    uint32_t fill = 0;
+                    uint32_t wp = stage_s;              // the word under construction
+                    const uint32_t wlast = stage_s + (cap_words - 1u) * 128u;
+                    // branch-free: the word under construction is stored every time (a string that outgrows its column
+                    // keeps rewriting the last word and is caught by its length), the pointer moves by a select.
+                    // t: the code and its mantissa, left-aligned; 1 <= nbits <= 27
+                    auto put = [&](uint32_t t, uint32_t nbits) {
+                        acc |= t >> fill;
+                        const uint32_t nf = fill + nbits;
+                        sts32(min(wp, wlast), acc);
+                        const bool full = nf >= 32;                  // then fill >= 5
+                        acc = full ? __funnelshift_l(0u, t, 0u - fill) : acc;      // t << (32 - fill)
+                        wp += full ? 128u : 0u;
+                        fill = nf & 31u;
+                    };
+                    // table entries: code left-aligned | length.  The mantissa (low `size` bits of x) goes right under the code:
+                    // x << (32 - size) drops whatever sits above it, the funnel shift by the entry's low five bits moves it down
+                    {   // DC (ff_mjpeg_encode_dc, mjpegenc.c:357-377): negative differences send diff - 1
+                        const int diff = dc - pred;
+                        const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
+                        const uint32_t e = lds32(huff_dc_s + nb * 4);
+                        const uint32_t y = __funnelshift_l(0u, (uint32_t)(diff + (diff >> 31)), 0u - (uint32_t)nb);    // nb == 0: diff == 0
+                        put((e & ~31u) | __funnelshift_r(y, 0u, e), (e & 31u) + (uint32_t)nb);
+                    }
+                    const uint32_t ezrl = lds32(huff_ac_s + 0xf0 * 4), eeob = lds32(huff_ac_s);
+                    int prevk = 0;
+                    auto ac_run = [&](uint32_t m, int base) {        // encode_block's AC loop (mjpegenc.c:403-430)
+                        while (m) {
+                            const int k = base + __ffs((int)m) - 1;
+                            m &= m - 1;
+                            int run = k - prevk - 1;
+                            prevk = k;
+                            const int raw = lds_s16(coef_s + (uint32_t)k * 64);
+                            // level = |c| * qmat >> 22 (>= 1 here), sign restored (dct_quantize_c, mpegvideo_enc.c:3686-3716)
+                            const uint32_t q = __umulhi((uint32_t)(raw < 0 ? -raw : raw), lds32(qm_s + (uint32_t)k * 4));
+                            const uint32_t hb = (uint32_t)msb_index(q);                       // size - 1
+                            for (; run >= 16; run -= 16) put(ezrl & ~31u, ezrl & 31u);
+                            const uint32_t e = lds32(huff_ac_s + 4u + (((uint32_t)run << 4) + hb) * 4u);
+                            const uint32_t y = __funnelshift_l(0u, q ^ (uint32_t)(raw >> 31), ~hb);   // negative: level - 1 = ~|level|; << (32 - size)
+                            put((e & ~31u) | __funnelshift_r(y, 0u, e), (e & 31u) + hb + 1u);
+                        }
+                    };
+                    ac_run(mask_lo, 0);
+                    ac_run(mask_hi, 32);
+                    if (prevk != 63) put(eeob & ~31u, eeob & 31u);                 // EOB only if last_index < 63 (:432-434)
+                    if (fill > 0) sts32(min(wp, wlast), acc);
+                    len = ((wp - stage_s) >> 7) * 32u + fill;
+                }
+                if (__any_sync(0xffffffffu, len > cap_words * 32u)) { too_big = true; break; }
+                // DC predictors for what follows: the last active block of each component in this round
+                {
+                    const int na = rd ? min(32, 4 * (nmb - 8 * hh)) : min(16, nmb);       // active lanes (per component)
+                    if (active && (rd ? lane : (lane & 15)) == na - 1) W.carry_dc[comp] = dc;
+                }
+                if (rd == 0) {
+                    // chroma round: keep the strings, publish their lengths and the per-macroblock prefix
+                    lenC_own = len;
+                    W.lenC[lane] = len;
+                    __syncwarp();
+                    const uint32_t cj = lane < 16 ? W.lenC[lane] + W.lenC[16 + lane] : 0u;
+                    const uint32_t cinc = warp_incl_scan(cj, lane);
+                    if (lane < 16) W.cpre[lane + 1] = cinc;
+                    if (lane == 0) W.cpre[0] = 0;
+                    __syncwarp();
+                    continue;
+                }
+
+                // ---------------- C: bit offsets of the half segment's strings in bitstream order
+                // (per macroblock: Y0 Y1 Y2 Y3 Cb Cr)
+                const uint32_t linc = warp_incl_scan(len, lane);
+                const uint32_t cbase = W.cpre[8 * hh];
+                const uint32_t luma_off = (linc - len) + (W.cpre[8 * hh + (lane >> 2)] - cbase);
+                // chroma strings of this half are packed by the lanes that made them: Cb of macroblock 8*hh + j by
+                // lane 8*hh + j, Cr by lane 16 + 8*hh + j
+                const int cj = lane & 7;
+                const uint32_t luma_end = __shfl_sync(0xffffffffu, linc, 4 * cj + 3);
+                const bool cpack = (((lane & 15) >> 3) == hh) && ((lane & 15) < nmb);
+                const uint32_t chroma_off = luma_end + (W.cpre[8 * hh + cj] - cbase) + (lane >= 16 ? W.lenC[lane - 16] : 0u);
+                const uint32_t T = __shfl_sync(0xffffffffu, linc, 31) + (W.cpre[min(8 * hh + 8, 16)] - cbase);
+                const bool last_half = last_seg && (hh == 1 || nmb <= 8);
+                __syncwarp();
+                uint32_t R = r + T;                              // bits in the buffer after this half
+                // clear the words this half will OR into; word 0 starts with the carried bits
+                const uint32_t used_words = (R + 7 + 31) >> 5;
+                for (uint32_t i = 1 + lane; i <= used_words; i += 32) W.u.seg[i] = 0;
+                if (lane == 0) W.u.seg[0] = carry_word;
+                __syncwarp();
+
+                // ---------------- D: bit packer -- shift the private strings to their scanned bit offsets
+                {
+                    auto pack = [&](uint32_t src, uint32_t nbits, uint32_t o) {
+                        const uint32_t sh = o & 31;
+                        uint32_t dst = seg_s + (o >> 5) * 4;
+                        const uint32_t nsrc = (nbits + 31) >> 5;
+                        uint32_t prev = 0;
+                        for (uint32_t j = 0; j < nsrc; j++) {
+                            const uint32_t v = lds32(src);
+                            red_or_shared(dst, __funnelshift_r(v, prev, sh));      // (prev:v) >> sh
+                            prev = v; src += 128; dst += 4;
+                        }
+                        const uint32_t tail = sh ? prev << (32 - sh) : 0u;
+                        if (tail) red_or_shared(dst, tail);
+                    };
+                    if (len) pack(stageL_s, len, r + luma_off);
+                    if (cpack && lenC_own) pack(stageC_s, lenC_own, r + chroma_off);
+                }
+                __syncwarp();
+                if (last_half) {
+                    // pad to a byte with ones (ff_mjpeg_encode_stuffing, mjpegenc.c:338-343)
+                    const uint32_t pad = (0u - R) & 7u;
+                    if (lane == 0 && pad) W.u.seg[R >> 5] |= ((1u << pad) - 1u) << (32 - (R & 31) - pad);
+                    R += pad;
+                    __syncwarp();
+                }
+
+                // ---------------- E: FF00 stuffing (escape_FF, mjpegenc.c:282-336) into the byte stage, 128-bit stores
+                const uint32_t B = last_half ? (R >> 3) : ((R >> 5) << 2);     // bytes leaving the bit buffer now
+                const uint32_t nw = (B + 3) >> 2;
+                const uint32_t per = (nw + 31) >> 5;
+                const uint32_t w0 = min((uint32_t)lane * per, nw), w1 = min(w0 + per, nw);
+                // bytes past B in the last word are zero bits, never FF: no masking needed for the count
+                uint32_t ffc = 0;
+                for (uint32_t w = w0; w < w1; w++) ffc += __popc(ff_bytes(W.u.seg[w]));
+                const uint32_t inc = warp_incl_scan(ffc, lane);
+                const uint32_t ff_total = __shfl_sync(0xffffffffu, inc, 31);
+                const uint32_t ff_before = inc - ffc;
+                const uint32_t Bo = B + ff_total;                             // stuffed bytes of this half segment
+                const uint32_t tail_bytes = last_half ? 2u : 0u;              // EOI
+                if (oc + Bo + tail_bytes > sizeof(W.s.obuf)) { too_big = true; break; }      // never for ordinary content: k_encode takes the frame
+                const bool fits = (uint64_t)G + Bo + 2 <= pkt_cap && !overflow;
+                if (fits) {
+                    // the luma strings have been packed: their columns now stage the output bytes
+                    if ((uint32_t)lane < oc) W.s.obuf[lane] = (uint8_t)cbyte;
+                    uint32_t o = obuf_s + oc + w0 * 4 + ff_before;
+                    for (uint32_t w = w0; w < w1; w++) {
+                        const uint32_t v = W.u.seg[w];
+                        const uint32_t nvalid = min(4u, B - w * 4);
+                        if (nvalid == 4 && ff_bytes(v) == 0) {
+                            sts8(o, v >> 24); sts8(o + 1, v >> 16); sts8(o + 2, v >> 8); sts8(o + 3, v);
+                            o += 4;
+                        } else {
+                            for (uint32_t k = 0; k < nvalid; k++) {
+                                const uint32_t by = (v >> (24 - 8 * k)) & 0xffu;
+                                sts8(o++, by);
+                                if (by == 0xffu) sts8(o++, 0u);
+                            }
+                        }
+                    }
+                    uint32_t total = oc + Bo;
+                    if (last_half && lane == 0) { W.s.obuf[total] = 0xff; W.s.obuf[total + 1] = 0xd9; }     // EOI (mjpegenc.c:354)
+                    total += tail_bytes;
+                    __syncwarp();
+                    uint8_t *g0 = pkt + (G - oc);                             // 16-byte aligned: where obuf[0] goes
+                    const uint32_t nfull = total >> 4;
+                    for (uint32_t u = lane; u < nfull; u += 32)
+                        *reinterpret_cast<uint4 *>(g0 + 16 * u) = lds128(obuf_s + 16 * u);
+                    const uint32_t rem = total & 15u;
+                    if (last_half) {
+                        if ((uint32_t)lane < rem) g0[16 * nfull + lane] = W.s.obuf[16 * nfull + lane];
+                        oc = 0;
+                    } else {
+                        cbyte = (uint32_t)lane < rem ? W.s.obuf[16 * nfull + lane] : 0u;
+                        oc = rem;
+                    }
+                } else if (!overflow) overflow = AMV_ST_NOSPACE;
+                carry_word = last_half ? 0 : W.u.seg[R >> 5];                 // carry the partial word (same for all lanes)
+                G += Bo;
+                r = last_half ? 0 : (R & 31);
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            redo[f] = too_big ? 1 : 0;
+            if (!too_big) {
+                out_size[f] = overflow ? 0 : G + 2;
+                status[f] = (int32_t)overflow;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // packed layout: copy each packet from its slot to its scanned offset
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -653,6 +999,17 @@ cudaError_t upload_enc_tables(cudaStream_t s) {
     return cudaMemcpyToSymbolAsync(g_enc_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 
+// opt-in to more than 48 KB of dynamic shared memory: per device, called from amv_create
+cudaError_t encode_setup_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    return e;
+}
+
 int encode_grid(int n, int per_sm) {
     // CTAs per SM: k_encode 4 (shared memory and registers: 16 independent warps), k_encode16 5 (registers)
     const int cap = kNumSMs * per_sm;
@@ -662,33 +1019,29 @@ int encode_grid(int n, int per_sm) {
 
 void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                    int n, const Geom &g, const int32_t *qscale, uint8_t *slots, uint64_t slot_stride, uint32_t pkt_cap,
-                   uint32_t *out_size, int32_t *status, int32_t *redo, cudaStream_t s) {
+                   uint32_t *out_size, int32_t *status, int32_t *redo, int form, cudaStream_t s) {
     const bool fast = (g.w % 16 == 0) &&
                       ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-        cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-        cudaFuncSetAttribute(k_encode16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
-        cudaFuncSetAttribute(k_encode16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
-        attr_set = true;
+    // form 0 (or redo == nullptr): the plain one-kernel path.  Else a rounds kernel first (homogeneous rounds, strings staged at
+    // ordinary-content sizes) -- form 2: k_encode16v2, needs 16-byte aligned packet slots; form 1: k_encode16 -- then
+    // k_encode for the frames it flagged because a block's string outgrew its column.
+    if (!redo) form = 0;
+    if (form == 2 && ((((uintptr_t)slots | slot_stride) & 15) != 0)) form = 1;
+    if (form == 2) {
+        if (fast) AMV_LAUNCH(k_encode16v2<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
+        else      AMV_LAUNCH(k_encode16v2<false>, encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
+    } else if (form == 1) {
+        if (fast) AMV_LAUNCH(k_encode16<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
+        else      AMV_LAUNCH(k_encode16<false>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
     }
-    // redo == nullptr: the plain one-kernel path.  Else: k_encode16 first (homogeneous rounds, strings staged at
-    // ordinary-content sizes), then k_encode for the frames it flagged because a block's string outgrew its column.
-    if (redo) {
-        if (fast)
-            AMV_LAUNCH(k_encode16<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                                                    slot_stride, pkt_cap, out_size, status, redo);
-        else
-            AMV_LAUNCH(k_encode16<false>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                                                     slot_stride, pkt_cap, out_size, status, redo);
-    }
-    if (fast)
-        AMV_LAUNCH(k_encode<true>, encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                                            slot_stride, pkt_cap, out_size, status, redo);
-    else
-        AMV_LAUNCH(k_encode<false>, encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale, slots,
-                                                                             slot_stride, pkt_cap, out_size, status, redo);
+    if (fast) AMV_LAUNCH(k_encode<true>, encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale,
+                         slots, slot_stride, pkt_cap, out_size, status, form ? redo : nullptr);
+    else      AMV_LAUNCH(k_encode<false>, encode_grid(n, 4), kEncThreads, sizeof(EncSmem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, qscale,
+                         slots, slot_stride, pkt_cap, out_size, status, form ? redo : nullptr);
 }
 
 void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,

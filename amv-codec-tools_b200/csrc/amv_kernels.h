@@ -81,11 +81,13 @@ void launch_audio_resample(const int16_t *in, int64_t n_in, int64_t in_base, int
 
 // ---- encode
 cudaError_t upload_enc_tables(cudaStream_t s);
+cudaError_t encode_setup_device();      // per-device function attributes (dynamic shared memory opt-in)
+cudaError_t decode_setup_device();
 int  encode_grid(int n, int per_sm);
 void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                    int n, const Geom &g, const int32_t *qscale, uint8_t *slots, uint64_t slot_stride, uint32_t pkt_cap,
                    uint32_t *out_size, int32_t *status, int32_t *redo /* n flags of scratch, or nullptr: one-kernel path */,
-                   cudaStream_t s);
+                   int form /* 0 one kernel, 1 k_encode16 + k_encode, 2 k_encode16v2 + k_encode */, cudaStream_t s);
 void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
                     uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s);
 void launch_export_meta(const uint64_t *off, const uint32_t *sz, const int32_t *st, uint64_t *hoff, uint32_t *hsz, int32_t *hst,
