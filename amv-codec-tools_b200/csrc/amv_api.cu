@@ -60,6 +60,7 @@ struct amv_ctx {
     int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
     int opt_encode_rounds = 2;          // encoder: 2 = k_encode16v2, 1 = k_encode16 (each + k_encode for the frames it hands back), 0 = k_encode alone
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
+    bool opt_tokens16 = true;           // decode (AMV / SP5X): k_vlc_tokens16 + k_idct16 (16-bit tokens) instead of the 32-bit token pass
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
     // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
     void *mj_tables = nullptr;          // DecTableSet in device memory
@@ -171,6 +172,7 @@ int pick_log2p(const amv_ctx *ctx, int n) {
 // Huffman -> tokens.  payload_bytes: upper bound of the bytes of the n packets; sizes the scratch.
 struct DecodeFront {
     uint64_t *slot_off; uint32_t *scan_len; uint32_t *tokens; uint32_t *blk_off; int32_t *st; int launches;
+    bool tok16; const DecTableSet *tabs;
 };
 
 int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
@@ -209,10 +211,14 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
           launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, tabs, qtab, g.nl, g.nc, ctx->stream); }
         lc++;
     }
+    // fixed AMV / SP5X tables: the 16-bit token pass; amvlib flavour and plain JPEG (own tables, per-frame quantisers): 32-bit tokens
+    const bool tok16 = ctx->opt_tokens16 && !amvlib && !mode.tables && !mode.hdr;
     { ScopedTimer tm(ctx, KK_TOKENS);
-      launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, g.nl, g.nc, mode.restart, ctx->stream); }
+      if (tok16) launch_vlc_tokens16(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, reinterpret_cast<uint16_t *>(tokens), blk_off, st, tabs, g.nl, g.nc, ctx->stream);
+      else launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, g.nl, g.nc, mode.restart, ctx->stream); }
     lc++;
     F.slot_off = slot_off; F.scan_len = scan_len; F.tokens = tokens; F.blk_off = blk_off; F.st = st; F.launches = lc;
+    F.tok16 = tok16; F.tabs = tabs;
     return AMV_OK;
 }
 
@@ -224,7 +230,8 @@ int decode_device(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const 
     int r = decode_front(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, g, status, payload_bytes, false, F, mode);
     if (r != AMV_OK) return r;
     { ScopedTimer tm(ctx, KK_IDCT);
-      launch_idct(F.tokens, F.blk_off, F.slot_off, F.scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
+      if (F.tok16) launch_idct16(reinterpret_cast<const uint16_t *>(F.tokens), F.blk_off, F.slot_off, F.scan_len, n, g, F.tabs, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream);
+      else launch_idct(F.tokens, F.blk_off, F.slot_off, F.scan_len, n, g, y, u, v, ls_y, ls_c, fs_y, fs_c, ctx->stream); }
     return check_launch(ctx, "decode kernels", F.launches + 1);
 }
 
@@ -690,6 +697,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
         return AMV_OK;
     }
     if (!strcmp(key, "host_zero_copy_packets")) { ctx->opt_zero_copy_packets = value != 0; return AMV_OK; }
+    if (!strcmp(key, "decode_tokens16")) { ctx->opt_tokens16 = value != 0; return AMV_OK; }
     return AMV_ERR_UNSUPPORTED;
 }
 

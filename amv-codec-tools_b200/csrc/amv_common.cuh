@@ -11,8 +11,9 @@
 #define AMV_D  inline
 #endif
 
-// Kernel launch and dynamic shared memory go through two macros so that tests/host_emul/simt can compile the very
-// same kernel sources as plain C++ and run them on the CPU (-DAMV_EMUL, tests only; the product is nvcc's build).
+// Kernel launch and dynamic shared memory go through two macros so that the test suite's SIMT emulator can compile the
+// very same kernel sources as plain C++ and run them on the CPU (-DAMV_EMUL: a test build only, with its own stand-in
+// for the CUDA runtime header; the product is nvcc's build, which never defines it and has no CPU path).
 #if defined(AMV_EMUL)
 #define AMV_LAUNCH(kernel, grid, block, smem, stream, ...) AMV_EMUL_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
 #define AMV_EXTERN_SHARED(type, name, align) type *name = reinterpret_cast<type *>(simt::dyn_smem())
@@ -36,9 +37,10 @@ namespace amv {
 constexpr int kNumSMs = 148;              // B200
 
 // Every frame's un-stuffed scan lives in a 16-byte aligned scratch slot of align16(packet size) +
-// kSlotPad bytes (zero padded past the data); its token region is 8 bytes per slot byte, which
-// leaves 8 * kSlotPad bytes beyond the 1-token-per-2-bits bound for per-lane 16-byte alignment.
-constexpr uint32_t kSlotPad = 80;
+// kSlotPad bytes (zero padded past the data); its token region holds 4 tokens per slot byte, which
+// leaves 4 * kSlotPad = 640 tokens beyond the 1-token-per-2-bits bound: 16 per lane (32 lanes at most) for the
+// 16-byte alignment of every lane's first and last token group, plus the room the token kernels keep at the tail.
+constexpr uint32_t kSlotPad = 160;
 
 // Picture geometry shared by encoder and decoder kernels.
 struct Geom {
@@ -109,6 +111,7 @@ inline uint32_t smem_addr(const void *p) {
 template <class T> inline T *smem_ptr(uint32_t saddr) { return reinterpret_cast<T *>(simt::smem_base() + saddr); }
 inline uint32_t lds32(uint32_t saddr) { return *smem_ptr<uint32_t>(saddr); }
 inline int lds_s16(uint32_t saddr) { return *smem_ptr<int16_t>(saddr); }
+inline uint32_t lds_u16(uint32_t saddr) { return *smem_ptr<uint16_t>(saddr); }
 inline uint4 lds128(uint32_t saddr) { return *smem_ptr<uint4>(saddr); }
 inline void sts32(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) = v; }
 inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (uint16_t)v; }
@@ -133,6 +136,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
 __device__ __forceinline__ int lds_s16(uint32_t saddr) {
     int v;
     asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {

@@ -608,7 +608,7 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
     // region's tail, where its remaining blocks overwrite each other -- memory-safe, and every block still
     // gets a valid (count, offset) entry for the consumer.
     constexpr uint32_t kTokBlockRoom = 80;
-    const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~3u;    // tok_cap >= 320 (kSlotPad)
+    const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~3u;    // tok_cap >= 640 (kSlotPad)
 
     // ---- bit source
     uint32_t bp = bit;                      // next unread bit of the scan
@@ -756,6 +756,243 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_vlc_tokens16: the token pass for the fixed AMV / SP5X tables, restructured around what the flat loop above
+// spends its instructions on.  There, everything a block BOUNDARY needs (offset entry, next block's tables, predictor
+// rotation, the DC's own arithmetic, counters) is predicated code inside every symbol -- well over a third of its
+// ~78 instructions -- because 32 lanes end their blocks at 32 different symbols.  Here a lane that ends a block parks
+// until the next service point (every kTokPeriod symbols, warp-uniform), where the parked lanes do their block ends
+// AND decode the next block's DC together under one branch: the symbol body is AC-only and shrinks to what an AC
+// symbol needs, at the price of ~1.5 idle symbol slots per block.
+// Tokens are 16 bit: the DC token is the block's absolute dequantised DC, every other token is
+// (run << 12) | (level & 0xfff) -- the Huffman symbol in fixed width, ZRL included (run 15, level 0) -- and the
+// consumer (k_idct16) accumulates positions and multiplies by the quantiser.  The fixed tables code at most 10
+// magnitude bits, so a level always fits its 12-bit field; custom tables (plain JPEG) keep the 32-bit pass.
+// Region: 4 tokens per slot byte (8 B per scan byte, half of the 32-bit pass), lane p of a frame starts at token
+// (bit / 2 + 16 p) rounded up to 8, so groups of eight leave as aligned 16-byte stores.
+// Bits: per service period a lane consumes at most one DC (11 + 11 bits) and kTokPeriod AC symbols (16 + 10 each),
+// 126 bits, and receives up to 128.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTok16Stage = 16;       // staged 16-bit tokens per lane
+
+struct Tok16Smem {
+    uint32_t ring[kTokWarps][kRingWords * 32];             // 2 KB per warp, 2 KB aligned
+    uint16_t tstage[kTokWarps][kTok16Stage * 32];          // 1 KB per warp, 1 KB aligned: halfword c*32 + lane = staged token c of the lane
+    uint4    bstate[8];                                    // per block-in-MCU: DC table, AC table, DC quantiser, component change | next index
+    uint32_t lut[kFlatMaxEntries];                         // AC entries rewritten: advance - 1, bit 31 = yields a 16-bit token
+};
+constexpr size_t kTok16SmemBytes = sizeof(Tok16Smem) + 2048;
+
+__global__ void __launch_bounds__(kTokThreads)
+k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
+               const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
+               const LaneStart *__restrict__ starts, int nblk, uint16_t *__restrict__ tokens,
+               uint32_t *__restrict__ blk_off, int32_t *__restrict__ status, const DecTableSet *__restrict__ tabs,
+               int nl, int nc /* blocks per MCU: luma, one chroma component */) {
+    AMV_EXTERN_SHARED(uint8_t, tok16_smem_raw, 16);
+    const uint32_t raw_s = smem_addr(tok16_smem_raw);
+    Tok16Smem &S = *reinterpret_cast<Tok16Smem *>(tok16_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
+    const int nlut = tabs->flat.count, ac0 = tabs->flat.base[2];
+    for (int i = threadIdx.x; i < nlut; i += blockDim.x) {
+        uint32_t e = tabs->flat.e[i];
+        // everything from the first AC table on (the AC first levels and their second levels) feeds the symbol loop
+        if (i >= ac0 && (e & 31u)) e = ((e - (1u << 23)) & 0x7fffffffu) | ((e & kFlatTok16) << 24);
+        S.lut[i] = e;
+    }
+    const uint32_t lut_s = smem_addr(S.lut);
+    const uint32_t nbm = (uint32_t)(nl + 2 * nc);               // blocks per MCU (<= 8): nl luma, nc Cb, nc Cr
+    if (threadIdx.x < nbm) {
+        const uint32_t bq = threadIdx.x, tq = bq >= (uint32_t)nl ? 1 : 0;
+        const bool enters = bq == 0 || bq == (uint32_t)nl || bq == (uint32_t)(nl + nc);   // first block of a component
+        uint4 bs;
+        bs.x = lut_s + (uint32_t)tabs->flat.base[tq] * 4u;
+        bs.y = lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u;
+        bs.z = (uint32_t)tabs->q0[tq];
+        bs.w = (enters ? 0x80u : 0u) | (bq + 1u == nbm ? 0u : bq + 1u);
+        S.bstate[bq] = bs;
+    }
+    __syncthreads();
+    const int P = 1 << log2p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (int)(gt >> log2p);
+    const int p = (int)(gt & (P - 1));
+    const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
+    const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: | (c & 15) << 6
+    const uint32_t bstate_s = smem_addr(&S.bstate[0]);
+
+    // ---- lane set-up (inactive lanes keep count = 0 and never enter the symbol code), as in k_vlc_tokens
+    uint32_t count = 0, first = 0, bit = 0, U = 0, st = 0;
+    int pred0 = 1024, pred1 = 1024, pred2 = 1024;               // last_dc (mjpegdec.c:805-806)
+    const uint32_t *words = nullptr;
+    uint32_t cap_words = 0;
+    uint64_t so = 0;
+    if (f < n) {
+        U = scan_len[f];
+        so = slot_off[f];
+        words = reinterpret_cast<const uint32_t *>(scratch + so);
+        cap_words = (((pkt_size[f] + 15u) & ~15u) + kSlotPad) >> 2;
+        if (U) {       // U == 0: rejected by k_unstuff (status already says why)
+            count = (uint32_t)nblk;
+            if (log2p) {
+                const LaneStart s = starts[gt];
+                first = s.first_block; bit = s.bitpos; count = s.nblocks;
+                pred0 = s.pred[0]; pred1 = s.pred[1]; pred2 = s.pred[2];
+                if (first >= (uint32_t)nblk) count = 0;
+                else if (first + count > (uint32_t)nblk) count = nblk - first;
+                if (p == P - 1 && first + s.nblocks < (uint32_t)nblk) {
+                    // the scan ran out before the picture was complete: keep decoding (zeros) like a
+                    // sequential reader would, and say so
+                    count = nblk - first;
+                    st |= AMV_ST_OVERRUN;
+                }
+            }
+        }
+    }
+    const uint32_t tok_cap = cap_words * 16u;                   // 4 tokens per slot byte
+    // 16 tokens of slack per lane: the lane's first group is aligned up (<= 7) and its last group is written whole (<= 7
+    // don't-care tokens), and neither may reach the next lane's first group however short the subsequence is
+    uint32_t tok_first = ((bit >> 1) + 16u * (uint32_t)p + 7u) & ~7u;
+    uint16_t *tok_frame = tokens + so * 4;
+    uint32_t flushed = 0, blk0 = 0;
+    uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;       // the lane's (count, offset) entries
+    uint32_t bi = 0;                                                           // blocks finished
+    // room is checked once per service period (at most kTokPeriod + 1 new tokens, 7 more staged): a lane whose next token
+    // lies within kTokBlockRoom of the end of its frame's region (only streams that are already broken get there) is
+    // flagged and parked on the region's tail, where its remaining blocks overwrite each other -- memory-safe (the
+    // consumer's reads of such a block stay inside the token workspace), and every block still gets a (count, offset) entry
+    constexpr uint32_t kTokBlockRoom = 48;
+    const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~7u;    // tok_cap >= 640 (kSlotPad)
+
+    // ---- bit source (as in k_vlc_tokens)
+    uint32_t bp = bit;                      // next unread bit of the scan
+    uint32_t wr = (bit >> 5) & ~3u;         // next word the ring receives (16-byte groups); ring = words [wr-16, wr)
+    uint4 pend = make_uint4(0, 0, 0, 0);    // the group at wr, requested at the previous service point
+    auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
+        if (w + 4 <= cap_words) return __ldg(reinterpret_cast<const uint4 *>(words + w));
+        return make_uint4(0, 0, 0, 0);
+    };
+    auto ring_put = [&](uint32_t w, const uint4 &q) {   // w is a multiple of 4
+        const uint32_t a = ring_s | ((w << 7) & 0x780u);
+        sts32(a, bswap32(q.x)); sts32(a + 128, bswap32(q.y)); sts32(a + 256, bswap32(q.z)); sts32(a + 384, bswap32(q.w));
+    };
+    auto window = [&]() -> uint32_t {                   // the 32 bits at bp
+        const uint32_t x = bp << 2;
+        const uint32_t wa = lds32(ring_s | (x & 0x780u)), wc = lds32(ring_s | ((x + 128u) & 0x780u));
+        return __funnelshift_l(wc, wa, bp);
+    };
+    // kt = tokens emitted by this lane << 8 | kb, kb = zigzag position of the last symbol + 1.  One add per symbol moves
+    // both: the (rewritten) AC entries hold (token? << 8 | advance - 1) in their top 9 bits.  kb < 128 before a symbol
+    // (else the block has ended) and the advance is <= 128: no carry into the count.
+    uint32_t kt = 0;
+    auto stage_addr = [&](uint32_t c) -> uint32_t { return tst_s | ((c << 6) & 0x3c0u); };
+    auto flush_group = [&]() {              // staged tokens [flushed, flushed + 8)
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t lo = lds_u16(stage_addr(flushed + 2 * j)), hi16 = lds_u16(stage_addr(flushed + 2 * j + 1));
+            w[j] = lo | (hi16 << 16);
+        }
+        *reinterpret_cast<uint4 *>(tok_frame + (tok_first + flushed)) = make_uint4(w[0], w[1], w[2], w[3]);
+        flushed += 8;
+    };
+
+    bool live = count > 0;                  // the lane has blocks left
+    bool on = false;                        // ... and is inside one (its DC is read; not parked at a block end)
+    bool ended = false, endnz = false;      // parked at a block end; the block's last symbol carried a coefficient
+    uint32_t dct_s = 0, act_s = 0, bnext = 0;
+    int q0 = 0;
+    uint32_t cerr = 0;                      // a coefficient index ran past 63 ("error count", mjpegdec.c:423-424)
+    int predA = pred0, predB = pred1, predC = pred2;             // predA: the current block's component
+    if (live) {
+        ring_put(wr, load_group(wr));
+        ring_put(wr + 4, load_group(wr + 4));
+        wr += 8;
+        pend = load_group(wr);
+    }
+    {   // every lane gets valid tables, also the ones without work: they run the symbol code with frozen state
+        const uint32_t b = first % nbm;
+        const uint4 bs = S.bstate[b];
+        dct_s = bs.x; act_s = bs.y; q0 = (int)bs.z; bnext = bs.w & 0x7fu;
+        if (b >= (uint32_t)nl && b < (uint32_t)(nl + nc)) { predA = pred1; predB = pred2; predC = pred0; }
+        if (b >= (uint32_t)(nl + nc)) { predA = pred2; predB = pred0; predC = pred1; }
+    }
+
+    while (__any_sync(0xffffffffu, live)) {
+        // ---- service point (warp-uniform): block ends of the parked lanes, ring top-up, token flush, room check,
+        // and the DC of every lane that starts a block
+        if (ended) {
+            const uint32_t ntok = kt >> 8;
+            // (symbol token count << 24) + index of the DC token; the sum is < 2^24 whatever tok_first wrapped to
+            boff[bi] = ((ntok - blk0 - 1u) << kTokCountShift) + (tok_first + blk0);
+            bi++;
+            blk0 = ntok;
+            if (endnz && (kt & 0xffu) != 64u) cerr = 1;                  // the last coefficient sat past position 63
+            const uint4 bs = lds128(bstate_s + bnext * 16u);
+            if (bs.w & 0x80u) { const int t = predA; predA = predB; predB = predC; predC = t; }    // Y -> Cb -> Cr -> Y
+            dct_s = bs.x; act_s = bs.y; q0 = (int)bs.z; bnext = bs.w & 0x7fu;
+            ended = false;
+            live = bi != count;
+        }
+        if (live) {
+            const uint32_t rd = bp >> 5;                                       // words below this one are dead
+            if ((int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; pend = load_group(wr); }
+            if ((kt >> 8) - flushed >= 8) flush_group();
+            if (tok_first + (kt >> 8) > tpark) { st |= AMV_ST_OVERRUN; tok_first = (tpark - (kt >> 8)) & ~7u; }   // see kTokBlockRoom
+            if (!on) {
+                // ---- the block's DC (mjpeg_decode_dc, mjpegdec.c:358-373): block[0] = (int16)(last_dc += diff * q0) (:387-389)
+                const uint32_t hi = window();
+                uint32_t e = lds32(dct_s + ((hi >> (32 - kFlatDcBits)) << 2));
+                if ((e & 31u) == 0) {
+                    if (!(e & kFlatBad)) e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << kFlatDcBits) >> (32u - (e >> 24)))) << 2));
+                    if ((e & 31u) == 0) { st |= AMV_ST_BADCODE; e = 1u | (1u << 8); }        // no such code: reads as difference 0
+                }
+                const uint32_t top = __funnelshift_l(0u, hi, e);               // hi << code length
+                const int sg = (int)(~top) >> 31;                              // get_xbits: -1 if the first bit is 0
+                const int diff = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
+                bp += (e >> 8) & 0xffu;
+                predA += diff * q0;
+                sts16(stage_addr(kt >> 8), (uint32_t)predA);
+                kt = (kt & ~0xffu) + 0x101u;                                   // one token, position 0 done
+                on = true;
+            }
+        }
+        // ---- kTokPeriod AC symbols, straight-line and predicated (decode_block, mjpegdec.c:391-428): a lane that is parked
+        // or has finished keeps executing with its state frozen (its loads stay inside the tables and its own ring, its
+        // token lands in a dead staging slot)
+#pragma unroll
+        for (int u = 0; u < kTokPeriod; u++) {
+            const uint32_t hi = window();
+            uint32_t e = lds32(act_s + ((hi >> (32 - kFlatAcBits)) << 2));
+            if ((e & 31u) == 0) {
+                if (!(e & kFlatBad)) e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << kFlatAcBits) >> (32u - (e >> 24)))) << 2));
+                if ((e & 31u) == 0) {       // no such code: ends the block
+                    if (on) st |= AMV_ST_BADCODE;
+                    e = 1u | (1u << 8) | ((kFlatAdvEob - 1u) << 23);
+                }
+            }
+            const uint32_t top = __funnelshift_l(0u, hi, e);                   // hi << code length
+            const int sg = (int)(~top) >> 31;                                  // get_xbits: -1 if the first bit is 0
+            // the size bits under the code, sign-extended; the shift count is the entry's bits [20:16] (wrap mode ignores the rest)
+            const int lvl = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
+            // the symbol in fixed width: run = advance - 1 (15 for ZRL) over the level
+            sts16(stage_addr(kt >> 8), ((e >> 11) & 0xf000u) | ((uint32_t)lvl & 0xfffu));
+            if (on) { bp += (e >> 8) & 0xffu; kt += (e >> 23) + 1u; }
+            // ---- end of block: EOB (advance 128), coefficient 63, or a coefficient index > 63
+            const bool nz = lvl != 0;
+            const bool fin = (kt & 0xc0u) != 0 && (nz || (kt & 0x80u) != 0);
+            if (on && fin) { ended = true; endnz = nz; }
+            on = on && !fin;
+        }
+    }
+    if (cerr) st |= AMV_ST_COEFIDX;
+    // flush what is still staged (unused upper tokens of the last group are don't-care, the group is ours alone)
+    while (flushed < (kt >> 8)) flush_group();
+    // a lane that owns no block just passes through; otherwise it must end inside the scan
+    if (count && bp > U * 8u) st |= AMV_ST_OVERRUN;
+    if (st && f < n) atomicOr(&status[f], (int32_t)st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_idct: one thread per 8x8 block, blocks enumerated in PLANE raster order so that the 32 lanes
 // of a warp own 32 horizontally adjacent blocks: every pixel-row store of the warp is one
 // contiguous 256-byte run.  Tokens -> dequantised coefficients in a conflict-free shared-memory
@@ -846,6 +1083,105 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_idct16: k_idct for the 16-bit tokens of k_vlc_tokens16.  Same thread-per-block layout in plane raster order and
+// the same transform; the scatter loop walks the block's symbols -- position += run + 1, value = level x quantiser
+// truncated to int16 (decode_block, mjpegdec.c:420,428) -- eight tokens per 128-bit load.
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(kIdctThreads)
+k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off, const uint64_t *__restrict__ slot_off,
+         const uint32_t *__restrict__ scan_len, int n, Geom g, const DecTableSet *__restrict__ tabs, uint8_t *__restrict__ py,
+         uint8_t *__restrict__ pu, uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c) {
+    __shared__ uint32_t tile[kIdctThreads / 32][32 * 32];
+    __shared__ uint32_t tzs[2][64];             // zigzag position -> (column byte offset << 16) | quantiser
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < 128) tzs[threadIdx.x >> 6][threadIdx.x & 63] = tabs->tz[threadIdx.x >> 6][threadIdx.x & 63];
+    __syncthreads();
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (int)(gt / g.nblk);
+    if (f >= n) return;
+    if (scan_len[f] == 0) return;
+    const int i = (int)(gt - (int64_t)f * g.nblk);
+    // blocks are enumerated in plane raster order (all of Y, then Cb, then Cr); blk = the block's index in
+    // bitstream order: MCU by MCU, inside an MCU component by component, v x h blocks in raster order
+    const int nluma = g.nl * g.mbw * g.mbh, nchroma = g.nc * g.mbw * g.mbh;
+    int comp, bx, by, blk;
+    if (i < nluma) {
+        comp = 0;
+        const int rowb = g.mbw << g.llh;
+        by = i / rowb; bx = i - by * rowb;
+        blk = ((by >> g.llv) * g.mbw + (bx >> g.llh)) * g.nb + ((by & ((1 << g.llv) - 1)) << g.llh) + (bx & ((1 << g.llh) - 1));
+    } else {
+        const int j = i - nluma;
+        comp = j < nchroma ? 1 : 2;
+        const int jj = comp == 1 ? j : j - nchroma;
+        const int rowb = g.mbw << g.lch;
+        by = jj / rowb; bx = jj - by * rowb;
+        blk = ((by >> g.lcv) * g.mbw + (bx >> g.lch)) * g.nb + g.nl + (comp - 1) * g.nc +
+              ((by & ((1 << g.lcv) - 1)) << g.lch) + (bx & ((1 << g.lch) - 1));
+    }
+    const uint32_t bo = blk_off[(uint64_t)f * g.nblk + blk];
+    const uint16_t *tf = tokens + slot_off[f] * 4;                         // the frame's token region (16-byte aligned)
+    const uint32_t first = bo & ((1u << kTokCountShift) - 1u), last = first + (bo >> kTokCountShift);   // DC token .. last symbol token
+    uint32_t *slot = &tile[wid][lane];
+    const uint32_t slot_s = smem_addr(slot);
+    const uint32_t tz_s = smem_addr(&tzs[comp ? 1 : 0][0]);
+#pragma unroll
+    for (int k = 0; k < 32; k++) slot[k * 32] = 0;
+    // tokens are fetched as aligned groups of eight (one 128-bit load), one group ahead in flight; the tokens of a group
+    // that belong to the neighbouring blocks are skipped.  The look-ahead stays inside the region's slack.
+    uint32_t gi = first & ~7u;
+    uint4 q = __ldg(reinterpret_cast<const uint4 *>(tf + gi));
+    uint32_t k = 0;                                                        // zigzag position of the last symbol
+    for (; gi <= last; gi += 8) {
+        const uint4 nq = __ldg(reinterpret_cast<const uint4 *>(tf + gi + 8));
+        const uint32_t tw[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t idx = gi + j;
+            const uint32_t t = (j & 1) ? tw[j >> 1] >> 16 : tw[j >> 1] & 0xffffu;
+            if (idx == first) sts16(slot_s, t);                            // the DC: absolute, already dequantised
+            else if (idx > first && idx <= last) {
+                k = (k + (t >> 12) + 1u) & 63u;                            // past 63 only in streams the producer has flagged
+                const uint32_t z = lds32(tz_s + k * 4u);
+                const int lvl = (int)(t << 20) >> 20;
+                sts16(slot_s + (z >> 16), (uint32_t)(lvl * (int)(z & 0xffu)));
+            }
+        }
+        q = nq;
+    }
+
+    uint32_t c[32], o[16];
+#pragma unroll
+    for (int kk = 0; kk < 32; kk++) c[kk] = slot[kk * 32];
+    // Smooth content (chroma planes almost always) has nothing below the second coefficient row: when that holds
+    // for the whole warp, take the transform specialised for it (same results, a quarter of the arithmetic).
+    uint32_t lower = 0;
+#pragma unroll
+    for (int kk = 8; kk < 32; kk++) lower |= c[kk];
+    if (__all_sync(__activemask(), lower == 0)) idct_put_block<2>(c, o);
+    else idct_put_block<8>(c, o);
+
+    uint8_t *pl = comp == 0 ? py + (uint64_t)f * fs_y : (comp == 1 ? pu : pv) + (uint64_t)f * fs_c;
+    const int ls = comp ? ls_c : ls_y;
+    const int vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
+    const int x0 = bx * 8, y0 = by * 8;
+#pragma unroll
+    for (int yy = 0; yy < 8; yy++) {
+        const int row = g.flip ? r0 - (y0 + yy) : y0 + yy;     // AMV pictures are stored bottom-up (mjpegdec.c:672-677), SP5X is not
+        if (row < 0 || row >= vh) continue;
+        uint8_t *d = pl + (int64_t)row * ls + x0;
+        if (FAST) {
+            *reinterpret_cast<uint2 *>(d) = make_uint2(o[2 * yy], o[2 * yy + 1]);
+        } else {
+#pragma unroll
+            for (int xx = 0; xx < 8; xx++)
+                if (x0 + xx < vw) d[xx] = (uint8_t)(o[2 * yy + (xx >> 2)] >> (8 * (xx & 3)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 static bool fill_table_set(DecTableSet &T, const HuffSpec &H, const uint8_t qzz[2][64], bool *sync_ok) {
@@ -903,6 +1239,7 @@ cudaError_t decode_setup_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTok16SmemBytes);
     return e;
 }
 
@@ -983,6 +1320,26 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
     else
         AMV_LAUNCH(k_vlc_tokens<kFlavorFfmpeg>, grid, kTokThreads, kTokSmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
                                                                  tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
+}
+
+void launch_vlc_tokens16(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
+                         int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
+                         int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
+    const int64_t lanes = (int64_t)n << log2p;
+    const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
+    AMV_LAUNCH(k_vlc_tokens16, grid, kTokThreads, kTok16SmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk, tokens,
+               blk_off, status, tabs, nl, nc);
+}
+
+void launch_idct16(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
+                   const Geom &g, const DecTableSet *tabs, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
+                   uint64_t fs_c, cudaStream_t s) {
+    const int64_t threads = (int64_t)n * g.nblk;
+    const int64_t grid = (threads + kIdctThreads - 1) / kIdctThreads;
+    const bool fast = (g.w % 16 == 0) &&
+                      ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
+    if (fast) AMV_LAUNCH(k_idct16<true>, (unsigned)grid, kIdctThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, tabs, y, u, v, ls_y, ls_c, fs_y, fs_c);
+    else      AMV_LAUNCH(k_idct16<false>, (unsigned)grid, kIdctThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, tabs, y, u, v, ls_y, ls_c, fs_y, fs_c);
 }
 
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,

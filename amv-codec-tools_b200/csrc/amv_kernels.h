@@ -46,6 +46,13 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                        int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, int nl, int nc,
                        int restart /* plain JPEG with DRI: MCUs per restart interval (one lane per frame only), else 0 */,
                        cudaStream_t s);
+// the fixed-table (AMV / SP5X) pass with 16-bit tokens: (run << 12 | level), the consumer dequantises
+void launch_vlc_tokens16(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
+                         int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
+                         int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s);
+void launch_idct16(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
+                   const Geom &g, const DecTableSet *tabs, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
+                   uint64_t fs_c, cudaStream_t s);
 void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
                  const Geom &g, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
                  cudaStream_t s);

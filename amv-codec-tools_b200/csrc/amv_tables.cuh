@@ -255,7 +255,7 @@ inline void build_vlc_tables(VlcTables &T) { HuffSpec H; fixed_huff_spec(H); bui
 // kernel.  DC and AC symbols go through the same code: a block starts with kb = 0 (kb = zigzag
 // position + 1), every entry carries the amount kb advances by and whether the symbol yields a
 // token, and the end of a block shows as kb >= 64.
-//   direct entry : [4:0] code length (>= 1)  [15:8] bits to consume  [20:16] size
+//   direct entry : [4:0] code length (>= 1)  [7] yields a 16-bit token  [15:8] bits to consume  [20:16] size
 //                  [30:23] advance of kb  [31] symbol yields a token
 //                  advance: DC 1, AC coefficient run + 1, ZRL 16, EOB 128
 //   [4:0] == 0   : bit 5 = no such code, else [23:8] = index of the second-level table, [31:24] its index bits
@@ -264,6 +264,7 @@ constexpr int kFlatDcBits = 10, kFlatAcBits = 12;
 constexpr int kFlatSecondCap = 1024;
 constexpr int kFlatMaxEntries = 2 * (1 << kFlatDcBits) + 2 * (1 << kFlatAcBits) + kFlatSecondCap;
 constexpr uint32_t kFlatBad = 1u << 5;
+constexpr uint32_t kFlatTok16 = 1u << 7;        // direct entries: the symbol yields a 16-bit token (coefficients, DC and ZRL)
 constexpr uint32_t kFlatAdvEob = 128;
 struct FlatVlcTables {
     uint32_t e[kFlatMaxEntries];
@@ -291,7 +292,8 @@ inline bool build_flat_vlc_table(FlatVlcTables &F, int t, const uint8_t counts[1
             uint32_t adv = dc ? 1u : (uint32_t)run + 1u;
             if (!dc && size == 0) adv = run == 15 ? 16u : kFlatAdvEob;          // ZRL / EOB (other run,0 symbols: treated as EOB)
             const uint32_t emit = (dc || size) ? 1u : 0u;
-            const uint32_t ent = (uint32_t)l | ((uint32_t)(l + size) << 8) | ((uint32_t)size << 16) | (adv << 23) | (emit << 31);
+            const uint32_t tok16 = (emit || (!dc && size == 0 && run == 15)) ? kFlatTok16 : 0u;
+            const uint32_t ent = (uint32_t)l | tok16 | ((uint32_t)(l + size) << 8) | ((uint32_t)size << 16) | (adv << 23) | (emit << 31);
             if (l <= fb) {
                 const int spare = fb - l;
                 for (int i = 0; i < (1 << spare); i++) F.e[F.base[t] + (code << spare) + i] = ent;
