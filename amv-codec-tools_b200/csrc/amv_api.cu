@@ -60,7 +60,11 @@ struct amv_ctx {
     int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
     int opt_encode_rounds = 2;          // encoder: 2 = k_encode16v2, 1 = k_encode16 (each + k_encode for the frames it hands back), 0 = k_encode alone
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
-    bool opt_tokens16 = true;           // decode (AMV / SP5X): k_vlc_tokens16 + k_idct16 (16-bit tokens) instead of the 32-bit token pass
+    // decode (AMV / SP5X, fixed tables): 2 = lean pass with 16-bit tokens + k_idct16, 1 = lean pass with 32-bit tokens + k_idct,
+    // 0 = k_vlc_tokens (flat loop, 32-bit tokens) + k_idct.  Measured per 100 000 frames 320x240 (profiles/r5b_*): tokens + idct
+    // 9.16 + 9.31 / 12.38 + 8.01 / 12.33 + 8.01 ms -- the token pass is ALU-pipe bound and the 32-bit token's offset and
+    // product cost it more than they save the consumer.
+    int opt_token_pass = 2;
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
     // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
     void *mj_tables = nullptr;          // DecTableSet in device memory
@@ -212,9 +216,11 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
         lc++;
     }
     // fixed AMV / SP5X tables: the 16-bit token pass; amvlib flavour and plain JPEG (own tables, per-frame quantisers): 32-bit tokens
-    const bool tok16 = ctx->opt_tokens16 && !amvlib && !mode.tables && !mode.hdr;
+    const bool fixed = !amvlib && !mode.tables && !mode.hdr;
+    const bool tok16 = fixed && ctx->opt_token_pass == 2;
     { ScopedTimer tm(ctx, KK_TOKENS);
-      if (tok16) launch_vlc_tokens16(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, reinterpret_cast<uint16_t *>(tokens), blk_off, st, tabs, g.nl, g.nc, ctx->stream);
+      if (fixed && ctx->opt_token_pass == 1) launch_vlc_tokens_lean(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, tabs, g.nl, g.nc, ctx->stream);
+      else if (tok16) launch_vlc_tokens16(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, reinterpret_cast<uint16_t *>(tokens), blk_off, st, tabs, g.nl, g.nc, ctx->stream);
       else launch_vlc_tokens(scratch, slot_off, scan_len, pkt_size, n, log2p, starts, g.nblk, tokens, blk_off, st, amvlib, tabs, qtab, g.nl, g.nc, mode.restart, ctx->stream); }
     lc++;
     F.slot_off = slot_off; F.scan_len = scan_len; F.tokens = tokens; F.blk_off = blk_off; F.st = st; F.launches = lc;
@@ -677,7 +683,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_rounds")) {
-        if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
+        if (value < 0 || value > 3) return AMV_ERR_UNSUPPORTED;
         ctx->opt_encode_rounds = (int)value;
         return AMV_OK;
     }
@@ -697,7 +703,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
         return AMV_OK;
     }
     if (!strcmp(key, "host_zero_copy_packets")) { ctx->opt_zero_copy_packets = value != 0; return AMV_OK; }
-    if (!strcmp(key, "decode_tokens16")) { ctx->opt_tokens16 = value != 0; return AMV_OK; }
+    if (!strcmp(key, "decode_token_pass")) {
+        if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
+        ctx->opt_token_pass = (int)value;
+        return AMV_OK;
+    }
     return AMV_ERR_UNSUPPORTED;
 }
 

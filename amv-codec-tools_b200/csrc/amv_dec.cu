@@ -776,18 +776,26 @@ constexpr int kTok16Stage = 16;       // staged 16-bit tokens per lane
 
 struct Tok16Smem {
     uint32_t ring[kTokWarps][kRingWords * 32];             // 2 KB per warp, 2 KB aligned
-    uint16_t tstage[kTokWarps][kTok16Stage * 32];          // 1 KB per warp, 1 KB aligned: halfword c*32 + lane = staged token c of the lane
-    uint4    bstate[8];                                    // per block-in-MCU: DC table, AC table, DC quantiser, component change | next index
-    uint32_t lut[kFlatMaxEntries];                         // AC entries rewritten: advance - 1, bit 31 = yields a 16-bit token
+    // 1 KB per warp, 1 KB aligned.  16-bit tokens: halfword c*32 + lane = staged token c (of 16) of the lane;
+    // 32-bit tokens: word c*32 + lane = staged token c (of 8)
+    uint32_t tstage[kTokWarps][8 * 32];
+    uint32_t tz[2][128];                                   // 32-bit tokens: kb = zigzag position + 1 -> (consumer column byte offset << 16) | quantiser; 512 B aligned
+    uint4    bstate[8];                                    // per block-in-MCU: DC table, AC table, DC quantiser | dequant table, component change | next index
+    uint32_t lut[kFlatMaxEntries];                         // AC entries rewritten: advance - 1, bit 31 = yields a token
 };
 constexpr size_t kTok16SmemBytes = sizeof(Tok16Smem) + 2048;
 
+// T16: 16-bit (run << 12 | level) tokens for k_idct16; else 32-bit (column offset << 16 | level x quantiser) tokens, DC included
+// (offset 0, absolute DC), for k_idct.  Measured (ncu, 100 000 frames): 6.36 G warp instructions against 7.71 G -- the table
+// look-up, the product, the predicated store and twice the flushes -- on a pass that is bound by the ALU pipe (77 % / 67 %
+// active): 9.2 ms against 12.4 ms, which the 32-bit tokens' cheaper consumer (8.0 against 9.3 ms) does not win back.
+template <bool T16>
 __global__ void __launch_bounds__(kTokThreads)
-k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
-               const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
-               const LaneStart *__restrict__ starts, int nblk, uint16_t *__restrict__ tokens,
-               uint32_t *__restrict__ blk_off, int32_t *__restrict__ status, const DecTableSet *__restrict__ tabs,
-               int nl, int nc /* blocks per MCU: luma, one chroma component */) {
+k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
+                  const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
+                  const LaneStart *__restrict__ starts, int nblk, void *__restrict__ tokens_v,
+                  uint32_t *__restrict__ blk_off, int32_t *__restrict__ status, const DecTableSet *__restrict__ tabs,
+                  int nl, int nc /* blocks per MCU: luma, one chroma component */) {
     AMV_EXTERN_SHARED(uint8_t, tok16_smem_raw, 16);
     const uint32_t raw_s = smem_addr(tok16_smem_raw);
     Tok16Smem &S = *reinterpret_cast<Tok16Smem *>(tok16_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
@@ -795,8 +803,13 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
     for (int i = threadIdx.x; i < nlut; i += blockDim.x) {
         uint32_t e = tabs->flat.e[i];
         // everything from the first AC table on (the AC first levels and their second levels) feeds the symbol loop
-        if (i >= ac0 && (e & 31u)) e = ((e - (1u << 23)) & 0x7fffffffu) | ((e & kFlatTok16) << 24);
+        // (16-bit tokens carry ZRL as a token, 32-bit tokens only what has a value: bit 31 as it is)
+        if (i >= ac0 && (e & 31u)) e = T16 ? ((e - (1u << 23)) & 0x7fffffffu) | ((e & kFlatTok16) << 24) : e - (1u << 23);
         S.lut[i] = e;
+    }
+    if (!T16) {     // dequant table indexed by kb; positions past 64 (only broken streams get there) alias the last one
+        const int c = threadIdx.x >> 7, kb = threadIdx.x & 127, kk = kb == 0 ? 0 : (kb > 64 ? 63 : kb - 1);
+        S.tz[c][kb] = tabs->tz[c][kk];
     }
     const uint32_t lut_s = smem_addr(S.lut);
     const uint32_t nbm = (uint32_t)(nl + 2 * nc);               // blocks per MCU (<= 8): nl luma, nc Cb, nc Cr
@@ -806,7 +819,7 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
         uint4 bs;
         bs.x = lut_s + (uint32_t)tabs->flat.base[tq] * 4u;
         bs.y = lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u;
-        bs.z = (uint32_t)tabs->q0[tq];
+        bs.z = (uint32_t)tabs->q0[tq] | (smem_addr(&S.tz[tq][0]) << 8);
         bs.w = (enters ? 0x80u : 0u) | (bq + 1u == nbm ? 0u : bq + 1u);
         S.bstate[bq] = bs;
     }
@@ -817,8 +830,10 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
     const int f = (int)(gt >> log2p);
     const int p = (int)(gt & (P - 1));
     const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
-    const uint32_t tst_s = smem_addr(&S.tstage[wid][lane]);     // staged token c of this lane: | (c & 15) << 6
+    // staged token c of this lane: 16-bit | (c & 15) << 6, 32-bit | (c & 7) << 7
+    const uint32_t tst_s = T16 ? smem_addr(reinterpret_cast<uint16_t *>(&S.tstage[wid][0]) + lane) : smem_addr(&S.tstage[wid][lane]);
     const uint32_t bstate_s = smem_addr(&S.bstate[0]);
+    constexpr uint32_t kGroup = T16 ? 8u : 4u;                  // tokens per 16-byte store
 
     // ---- lane set-up (inactive lanes keep count = 0 and never enter the symbol code), as in k_vlc_tokens
     uint32_t count = 0, first = 0, bit = 0, U = 0, st = 0;
@@ -851,8 +866,9 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
     const uint32_t tok_cap = cap_words * 16u;                   // 4 tokens per slot byte
     // 16 tokens of slack per lane: the lane's first group is aligned up (<= 7) and its last group is written whole (<= 7
     // don't-care tokens), and neither may reach the next lane's first group however short the subsequence is
-    uint32_t tok_first = ((bit >> 1) + 16u * (uint32_t)p + 7u) & ~7u;
-    uint16_t *tok_frame = tokens + so * 4;
+    uint32_t tok_first = ((bit >> 1) + 2u * kGroup * (uint32_t)p + kGroup - 1u) & ~(kGroup - 1u);
+    uint16_t *tok_frame16 = static_cast<uint16_t *>(tokens_v) + so * 4;
+    uint32_t *tok_frame32 = static_cast<uint32_t *>(tokens_v) + so * 4;
     uint32_t flushed = 0, blk0 = 0;
     uint32_t *boff = blk_off + (uint64_t)(f < n ? f : 0) * nblk + first;       // the lane's (count, offset) entries
     uint32_t bi = 0;                                                           // blocks finished
@@ -861,7 +877,7 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
     // flagged and parked on the region's tail, where its remaining blocks overwrite each other -- memory-safe (the
     // consumer's reads of such a block stay inside the token workspace), and every block still gets a (count, offset) entry
     constexpr uint32_t kTokBlockRoom = 48;
-    const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~7u;    // tok_cap >= 640 (kSlotPad)
+    const uint32_t tpark = (tok_cap - kTokBlockRoom) & ~(kGroup - 1u);    // tok_cap >= 640 (kSlotPad)
 
     // ---- bit source (as in k_vlc_tokens)
     uint32_t bp = bit;                      // next unread bit of the scan
@@ -884,22 +900,25 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
     // both: the (rewritten) AC entries hold (token? << 8 | advance - 1) in their top 9 bits.  kb < 128 before a symbol
     // (else the block has ended) and the advance is <= 128: no carry into the count.
     uint32_t kt = 0;
-    auto stage_addr = [&](uint32_t c) -> uint32_t { return tst_s | ((c << 6) & 0x3c0u); };
-    auto flush_group = [&]() {              // staged tokens [flushed, flushed + 8)
+    auto stage_addr = [&](uint32_t c) -> uint32_t { return T16 ? tst_s | ((c << 6) & 0x3c0u) : tst_s | ((c << 7) & 0x380u); };
+    auto flush_group = [&]() {              // staged tokens [flushed, flushed + kGroup)
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t lo = lds_u16(stage_addr(flushed + 2 * j)), hi16 = lds_u16(stage_addr(flushed + 2 * j + 1));
-            w[j] = lo | (hi16 << 16);
+            if (T16) {
+                const uint32_t lo = lds_u16(stage_addr(flushed + 2 * j)), hi16 = lds_u16(stage_addr(flushed + 2 * j + 1));
+                w[j] = lo | (hi16 << 16);
+            } else w[j] = lds32(stage_addr(flushed + j));
         }
-        *reinterpret_cast<uint4 *>(tok_frame + (tok_first + flushed)) = make_uint4(w[0], w[1], w[2], w[3]);
-        flushed += 8;
+        if (T16) *reinterpret_cast<uint4 *>(tok_frame16 + (tok_first + flushed)) = make_uint4(w[0], w[1], w[2], w[3]);
+        else     *reinterpret_cast<uint4 *>(tok_frame32 + (tok_first + flushed)) = make_uint4(w[0], w[1], w[2], w[3]);
+        flushed += kGroup;
     };
 
     bool live = count > 0;                  // the lane has blocks left
     bool on = false;                        // ... and is inside one (its DC is read; not parked at a block end)
     bool ended = false, endnz = false;      // parked at a block end; the block's last symbol carried a coefficient
-    uint32_t dct_s = 0, act_s = 0, bnext = 0;
+    uint32_t dct_s = 0, act_s = 0, bnext = 0, tz_s = 0;
     int q0 = 0;
     uint32_t cerr = 0;                      // a coefficient index ran past 63 ("error count", mjpegdec.c:423-424)
     int predA = pred0, predB = pred1, predC = pred2;             // predA: the current block's component
@@ -912,7 +931,7 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
     {   // every lane gets valid tables, also the ones without work: they run the symbol code with frozen state
         const uint32_t b = first % nbm;
         const uint4 bs = S.bstate[b];
-        dct_s = bs.x; act_s = bs.y; q0 = (int)bs.z; bnext = bs.w & 0x7fu;
+        dct_s = bs.x; act_s = bs.y; q0 = (int)(bs.z & 0xffu); tz_s = bs.z >> 8; bnext = bs.w & 0x7fu;
         if (b >= (uint32_t)nl && b < (uint32_t)(nl + nc)) { predA = pred1; predB = pred2; predC = pred0; }
         if (b >= (uint32_t)(nl + nc)) { predA = pred2; predB = pred0; predC = pred1; }
     }
@@ -929,15 +948,16 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
             if (endnz && (kt & 0xffu) != 64u) cerr = 1;                  // the last coefficient sat past position 63
             const uint4 bs = lds128(bstate_s + bnext * 16u);
             if (bs.w & 0x80u) { const int t = predA; predA = predB; predB = predC; predC = t; }    // Y -> Cb -> Cr -> Y
-            dct_s = bs.x; act_s = bs.y; q0 = (int)bs.z; bnext = bs.w & 0x7fu;
+            dct_s = bs.x; act_s = bs.y; q0 = (int)(bs.z & 0xffu); tz_s = bs.z >> 8; bnext = bs.w & 0x7fu;
             ended = false;
             live = bi != count;
         }
         if (live) {
             const uint32_t rd = bp >> 5;                                       // words below this one are dead
             if ((int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; pend = load_group(wr); }
-            if ((kt >> 8) - flushed >= 8) flush_group();
-            if (tok_first + (kt >> 8) > tpark) { st |= AMV_ST_OVERRUN; tok_first = (tpark - (kt >> 8)) & ~7u; }   // see kTokBlockRoom
+            if (T16) { if ((kt >> 8) - flushed >= kGroup) flush_group(); }
+            else { while ((kt >> 8) - flushed >= kGroup) flush_group(); }       // at most 3 + 1 + kTokPeriod staged: twice at most
+            if (tok_first + (kt >> 8) > tpark) { st |= AMV_ST_OVERRUN; tok_first = (tpark - (kt >> 8)) & ~(kGroup - 1u); }   // see kTokBlockRoom
             if (!on) {
                 // ---- the block's DC (mjpeg_decode_dc, mjpegdec.c:358-373): block[0] = (int16)(last_dc += diff * q0) (:387-389)
                 const uint32_t hi = window();
@@ -951,7 +971,8 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
                 const int diff = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
                 bp += (e >> 8) & 0xffu;
                 predA += diff * q0;
-                sts16(stage_addr(kt >> 8), (uint32_t)predA);
+                if (T16) sts16(stage_addr(kt >> 8), (uint32_t)predA);
+                else     sts32(stage_addr(kt >> 8), (uint32_t)predA & 0xffffu);                 // column offset 0
                 kt = (kt & ~0xffu) + 0x101u;                                   // one token, position 0 done
                 on = true;
             }
@@ -974,9 +995,19 @@ k_vlc_tokens16(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__
             const int sg = (int)(~top) >> 31;                                  // get_xbits: -1 if the first bit is 0
             // the size bits under the code, sign-extended; the shift count is the entry's bits [20:16] (wrap mode ignores the rest)
             const int lvl = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
-            // the symbol in fixed width: run = advance - 1 (15 for ZRL) over the level
-            sts16(stage_addr(kt >> 8), ((e >> 11) & 0xf000u) | ((uint32_t)lvl & 0xfffu));
-            if (on) { bp += (e >> 8) & 0xffu; kt += (e >> 23) + 1u; }
+            if (T16) {
+                // the symbol in fixed width: run = advance - 1 (15 for ZRL) over the level
+                sts16(stage_addr(kt >> 8), ((e >> 11) & 0xf000u) | ((uint32_t)lvl & 0xfffu));
+                if (on) { bp += (e >> 8) & 0xffu; kt += (e >> 23) + 1u; }
+            } else {
+                // level * quant_matrix[j] as int16 over the consumer's column offset (:420,428); the token goes where the count
+                // stood before the symbol, and only if the symbol has a value (a ring of eight has no dead slot to spare)
+                const uint32_t slot = stage_addr(kt >> 8);
+                const bool emit = on && (int)e < 0;
+                if (on) { bp += (e >> 8) & 0xffu; kt += (e >> 23) + 1u; }
+                const uint32_t z = lds32(tz_s | ((kt << 2) & 0x1fcu));
+                if (emit) sts32(slot, __byte_perm((uint32_t)(lvl * (int)(z & 0xffu)), z, 0x7610));
+            }
             // ---- end of block: EOB (advance 128), coefficient 63, or a coefficient index > 63
             const bool nz = lvl != 0;
             const bool fin = (kt & 0xc0u) != 0 && (nz || (kt & 0x80u) != 0);
@@ -1093,7 +1124,7 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
          const uint32_t *__restrict__ scan_len, int n, Geom g, const DecTableSet *__restrict__ tabs, uint8_t *__restrict__ py,
          uint8_t *__restrict__ pu, uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c) {
     __shared__ uint32_t tile[kIdctThreads / 32][32 * 32];
-    __shared__ uint32_t tzs[2][64];             // zigzag position -> (column byte offset << 16) | quantiser
+    __shared__ __align__(256) uint32_t tzs[2][64];      // zigzag position -> (column byte offset << 16) | quantiser
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x < 128) tzs[threadIdx.x >> 6][threadIdx.x & 63] = tabs->tz[threadIdx.x >> 6][threadIdx.x & 63];
     __syncthreads();
@@ -1128,25 +1159,28 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
     const uint32_t tz_s = smem_addr(&tzs[comp ? 1 : 0][0]);
 #pragma unroll
     for (int k = 0; k < 32; k++) slot[k * 32] = 0;
-    // tokens are fetched as aligned groups of eight (one 128-bit load), one group ahead in flight; the tokens of a group
-    // that belong to the neighbouring blocks are skipped.  The look-ahead stays inside the region's slack.
-    uint32_t gi = first & ~7u;
+    // The DC token is absolute and already dequantised.  The symbol tokens behind it are fetched as aligned groups of eight
+    // (one 128-bit load), one group ahead in flight; the tokens of a group that belong to the neighbouring blocks are
+    // skipped by predicate (no branches: the slots of a group are straight-line code).  The look-ahead stays inside the
+    // region's slack.
+    sts16(slot_s, (uint32_t)__ldg(tf + first));
+    const uint32_t cnt = bo >> kTokCountShift;                             // symbol tokens: indices first + 1 .. first + cnt
+    uint32_t gi = (first + 1u) & ~7u;
     uint4 q = __ldg(reinterpret_cast<const uint4 *>(tf + gi));
     uint32_t k = 0;                                                        // zigzag position of the last symbol
-    for (; gi <= last; gi += 8) {
+    uint32_t rel = gi - first - 1u;                                        // index of the group's first token among the block's symbols (may be "negative")
+    for (; gi <= last; gi += 8, rel += 8) {
         const uint4 nq = __ldg(reinterpret_cast<const uint4 *>(tf + gi + 8));
         const uint32_t tw[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const uint32_t idx = gi + j;
-            const uint32_t t = (j & 1) ? tw[j >> 1] >> 16 : tw[j >> 1] & 0xffffu;
-            if (idx == first) sts16(slot_s, t);                            // the DC: absolute, already dequantised
-            else if (idx > first && idx <= last) {
-                k = (k + (t >> 12) + 1u) & 63u;                            // past 63 only in streams the producer has flagged
-                const uint32_t z = lds32(tz_s + k * 4u);
-                const int lvl = (int)(t << 20) >> 20;
-                sts16(slot_s + (z >> 16), (uint32_t)(lvl * (int)(z & 0xffu)));
-            }
+            const uint32_t w = tw[j >> 1];
+            const bool valid = rel + (uint32_t)j < cnt;                    // unsigned: also false in front of the block
+            const uint32_t run = (j & 1) ? w >> 28 : (w >> 12) & 15u;
+            const int lvl = (j & 1) ? (int)(w << 4) >> 20 : (int)(w << 20) >> 20;
+            k = valid ? k + run + 1u : k;
+            const uint32_t z = lds32(tz_s | ((k << 2) & 0xfcu));           // past 63 only in streams the producer has flagged
+            if (valid) sts16(slot_s + (z >> 16), (uint32_t)(lvl * (int)(z & 0xffu)));
         }
         q = nq;
     }
@@ -1239,7 +1273,8 @@ cudaError_t decode_setup_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTok16SmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTok16SmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTok16SmemBytes);
     return e;
 }
 
@@ -1327,8 +1362,17 @@ void launch_vlc_tokens16(const uint8_t *scratch, const uint64_t *slot_off, const
                          int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
-    AMV_LAUNCH(k_vlc_tokens16, grid, kTokThreads, kTok16SmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk, tokens,
-               blk_off, status, tabs, nl, nc);
+    AMV_LAUNCH(k_vlc_tokens_lean<true>, grid, kTokThreads, kTok16SmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+               tokens, blk_off, status, tabs, nl, nc);
+}
+
+void launch_vlc_tokens_lean(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
+                            int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
+                            int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
+    const int64_t lanes = (int64_t)n << log2p;
+    const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
+    AMV_LAUNCH(k_vlc_tokens_lean<false>, grid, kTokThreads, kTok16SmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
+               tokens, blk_off, status, tabs, nl, nc);
 }
 
 void launch_idct16(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,

@@ -627,8 +627,8 @@ struct Enc16v2Smem {
     Enc16v2WarpSmem w[kEncWarps];
 };
 
-template <bool FAST>
-__global__ void __launch_bounds__(kEncThreads, 5)
+template <bool FAST, int MINB>
+__global__ void __launch_bounds__(kEncThreads, MINB)
 k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
              uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t pkt_cap, uint32_t *__restrict__ out_size,
@@ -1005,8 +1005,10 @@ cudaError_t encode_setup_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
     return e;
 }
 
@@ -1026,11 +1028,16 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
     // ordinary-content sizes) -- form 2: k_encode16v2, needs 16-byte aligned packet slots; form 1: k_encode16 -- then
     // k_encode for the frames it flagged because a block's string outgrew its column.
     if (!redo) form = 0;
-    if (form == 2 && ((((uintptr_t)slots | slot_stride) & 15) != 0)) form = 1;
-    if (form == 2) {
-        if (fast) AMV_LAUNCH(k_encode16v2<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+    if (form >= 2 && ((((uintptr_t)slots | slot_stride) & 15) != 0)) form = 1;
+    if (form == 3) {            // experiment: 4 CTAs per SM (128 registers, no spills) instead of 5 (96 registers)
+        if (fast) AMV_LAUNCH((k_encode16v2<true, 4>), encode_grid(n, 4), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
                              qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
-        else      AMV_LAUNCH(k_encode16v2<false>, encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+        else      AMV_LAUNCH((k_encode16v2<false, 4>), encode_grid(n, 4), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
+    } else if (form == 2) {
+        if (fast) AMV_LAUNCH((k_encode16v2<true, 5>), encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
+        else      AMV_LAUNCH((k_encode16v2<false, 5>), encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
                              qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
     } else if (form == 1) {
         if (fast) AMV_LAUNCH(k_encode16<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,

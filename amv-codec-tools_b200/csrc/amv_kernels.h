@@ -50,6 +50,10 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
 void launch_vlc_tokens16(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                          int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
                          int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s);
+// the same lean pass with k_vlc_tokens' 32-bit (column offset, dequantised value) tokens: the consumer is k_idct
+void launch_vlc_tokens_lean(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
+                            int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
+                            int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s);
 void launch_idct16(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
                    const Geom &g, const DecTableSet *tabs, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
                    uint64_t fs_c, cudaStream_t s);

@@ -251,6 +251,8 @@ def main():
     ap.add_argument("--ref-frames-per-worker", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--audit", type=int, default=64, help="frames re-checked after the run (golden vectors + self round trip)")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="amv_set_option on every context (A/B runs of kernel variants, e.g. encode_rounds=1, decode_tokens16=0)")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":
@@ -278,6 +280,9 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_option("profile_events", 1)
+    opts = [(kv.split("=")[0], int(kv.split("=")[1])) for kv in args.opt]
+    for k_, v_ in opts:
+        ctx.set_option(k_, v_)
 
     # ---- device-resident workload: every rank its own frame range [rank*n, (rank+1)*n)
     Y, U, V = synth_frames_torch(n, rank * n, dev, seed=1 + rank)
@@ -355,6 +360,8 @@ def main():
     # three buffers.  (With whole steps as the pipeline's unit the fill and drain cost one stage in K + 1.)
     import threading
     ctx2 = amv.AmvCuda(device=dev.index)
+    for k_, v_ in opts:
+        ctx2.set_option(k_, v_)
     nsub = max(1, min(args.e2e_sub, ne))
     while ne % nsub:
         nsub -= 1
@@ -504,6 +511,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "frames_per_step_per_gpu": ne, "api": "amv_encode_frames + amv_decode_frames, AMV_MEM_HOST, pinned buffers; two contexts pipeline each step's %d sub-batches (encode of sub-batch j+1 overlaps decode of sub-batch j)" % nsub},
         "gpu_launches": int(launches),
+        "options": dict(opts),
         "clocks": clocks,
         "audit": audit,
     }

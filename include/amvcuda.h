@@ -108,7 +108,10 @@ AMV_API void        amv_host_free(void *p);
  *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream
  *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose)
  *   "host_zero_copy_packets"       0 = DMA pinned decoder input into a device copy instead of reading it in place
- *   "encode_rounds"                0 = the one-kernel encoder instead of k_encode16 + k_encode
+ *   "encode_rounds"                encoder kernels: 2 (default) k_encode16v2, 1 k_encode16 (each + k_encode for the frames it
+ *                                  hands back), 0 the one-kernel encoder, 3 = 2 at four instead of five CTAs per SM
+ *   "decode_token_pass"            AMV / SP5X token pass: 2 (default) lean pass with 16-bit tokens, 1 lean pass with 32-bit
+ *                                  tokens, 0 the flat symbol loop with 32-bit tokens
  *   "scale_form"                   scaler kernel: 1 (default) tiles, 2 tiles with staged source rows, 0 direct
  *   "resample_form"                audio resampler kernel: 2 (default) phase rows, 1 tiles, 0 direct
  * One option DOES select an algorithm, like the reference's AVCodecContext.trellis does:

@@ -16,6 +16,8 @@ log2p = int(sys.argv[2]) if len(sys.argv) > 2 else -1
 dev = torch.device("cuda", 0)
 ctx = amv.AmvCuda(device=0)
 ctx.set_option("decode_log2_lanes", log2p)
+for kv in sys.argv[3:]:                      # further options as key=value
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 W, H, CW, CH = bench.W, bench.H, bench.CW, bench.CH
 Y, U, V = bench.synth_frames_torch(n, 0, dev, 1)
 cap = n * 24 * 1024
