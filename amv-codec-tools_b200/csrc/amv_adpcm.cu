@@ -85,7 +85,7 @@ k_adpcm_decode(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, const 
             const uint32_t sz = size[c];
             dsts = pcm_off[c];
             if (sz < 8) st = AMV_ST_SHORT;
-            else if (o + sz > chunks_bytes || dsts + 2ull * (sz - 8) > pcm_samples) st = AMV_ST_RANGE;
+            else if (!range_ok(o, sz, chunks_bytes) || !range_ok(dsts, 2ull * (sz - 8), pcm_samples)) st = AMV_ST_RANGE;
             else {
                 const uint8_t *h = chunks + o;
                 pred = (int)(int16_t)(h[0] | (h[1] << 8));
@@ -148,7 +148,7 @@ k_adpcm_decode(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, const 
 // first_chunk == NULL every chunk is its own stream.
 __global__ void __launch_bounds__(kAdpcmThreads)
 k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint64_t *__restrict__ pcm_off,
-               const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams,
+               const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams, int nchunks,
                const int16_t *__restrict__ step_in, int16_t *__restrict__ step_out, uint8_t *__restrict__ outb,
                uint64_t out_bytes, const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
     __shared__ AdpcmSmem S;
@@ -166,6 +166,10 @@ k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint
         if (s < nstreams) {
             c0 = first_chunk ? first_chunk[s] : (uint32_t)s;
             c1 = first_chunk ? first_chunk[s + 1] : (uint32_t)s + 1;
+            // a table that is not monotonic or runs past the chunk arrays: the stream owns nothing (the host-memory
+            // entry point rejects such a table outright)
+            if (c1 > (uint32_t)nchunks) c1 = (uint32_t)nchunks;
+            if (c0 > c1) c0 = c1;
             idx = step_in ? step_in[s] : 0;
             if (idx < 0 || idx > 88) { dead = true; for (uint32_t c = c0; c < c1; c++) status[c] = AMV_ST_RANGE; }
         }
@@ -184,7 +188,7 @@ k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint
                 ns = nsamples[c]; src = pcm_off[c]; dst = out_off[c];
                 int st = 0;
                 if (ns & 1) st = AMV_ST_RANGE;
-                else if (src + ns > pcm_samples || dst + 8 + ns / 2 > out_bytes) st = AMV_ST_RANGE;
+                else if (!range_ok(src, ns, pcm_samples) || !range_ok(dst, 8ull + ns / 2, out_bytes)) st = AMV_ST_RANGE;
                 status[c] = st;
                 if (st) { dead = true; ns = 0; }
                 else {
@@ -261,7 +265,7 @@ k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint
 template <int F>
 __global__ void __launch_bounds__(128)
 k_adpcm_encode_trellis(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint64_t *__restrict__ pcm_off,
-                       const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams,
+                       const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams, int nchunks,
                        const int16_t *__restrict__ step_in, int16_t *__restrict__ step_out, uint8_t *__restrict__ outb,
                        uint64_t out_bytes, const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
     constexpr int kFreeze = 128;
@@ -270,7 +274,9 @@ k_adpcm_encode_trellis(const int16_t *__restrict__ pcm, uint64_t pcm_samples, co
     __syncthreads();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nstreams) return;
-    const uint32_t c0 = first_chunk ? first_chunk[s] : (uint32_t)s, c1 = first_chunk ? first_chunk[s + 1] : (uint32_t)s + 1;
+    uint32_t c0 = first_chunk ? first_chunk[s] : (uint32_t)s, c1 = first_chunk ? first_chunk[s + 1] : (uint32_t)s + 1;
+    if (c1 > (uint32_t)nchunks) c1 = (uint32_t)nchunks;
+    if (c0 > c1) c0 = c1;
     int idx = step_in ? step_in[s] : 0;
     bool dead = idx < 0 || idx > 88;
 
@@ -284,7 +290,7 @@ k_adpcm_encode_trellis(const int16_t *__restrict__ pcm, uint64_t pcm_samples, co
         if (dead) { status[c] = AMV_ST_RANGE; continue; }
         const uint32_t ns = nsamples[c];
         const uint64_t src = pcm_off[c], dst = out_off[c];
-        if ((ns & 1) || src + ns > pcm_samples || dst + 8 + ns / 2 > out_bytes) { status[c] = AMV_ST_RANGE; dead = true; continue; }
+        if ((ns & 1) || !range_ok(src, ns, pcm_samples) || !range_ok(dst, 8ull + ns / 2, out_bytes)) { status[c] = AMV_ST_RANGE; dead = true; continue; }
         status[c] = 0;
         const int prev0 = ns ? pcm[src] : 0;
         uint8_t *h = outb + dst;
@@ -382,13 +388,13 @@ void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uin
 }
 
 void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
-                         const uint32_t *first_chunk, int nstreams, const int16_t *step_in, int16_t *step_out,
+                         const uint32_t *first_chunk, int nstreams, int nchunks, const int16_t *step_in, int16_t *step_out,
                          uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, cudaStream_t s) {
     if (trellis > 0) {
         const int grid = (nstreams + 127) / 128;
 #define AMV_TRELLIS_CASE(T)                                                                                              \
         case T: AMV_LAUNCH((k_adpcm_encode_trellis<(1 << T)>), grid, 128, 0, s, pcm, pcm_samples, pcm_off, nsamples, first_chunk,   \
-                           nstreams, step_in, step_out, out, out_bytes, out_off, status); break;
+                           nstreams, nchunks, step_in, step_out, out, out_bytes, out_off, status); break;
         switch (trellis) {
             AMV_TRELLIS_CASE(1) AMV_TRELLIS_CASE(2) AMV_TRELLIS_CASE(3) AMV_TRELLIS_CASE(4) AMV_TRELLIS_CASE(5)
             default: break;
@@ -397,7 +403,7 @@ void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_
         return;
     }
     AMV_LAUNCH(k_adpcm_encode, adpcm_grid(nstreams), kAdpcmThreads, 0, s, pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams,
-                                                                  step_in, step_out, out, out_bytes, out_off, status);
+               nchunks, step_in, step_out, out, out_bytes, out_off, status);
 }
 
 }  // namespace amv

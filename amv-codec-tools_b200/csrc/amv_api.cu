@@ -105,6 +105,21 @@ int fail(amv_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
     return code;
 }
 
+// Entry points run on the context's device and put the caller's current device back when they return.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) { err = cudaSetDevice(dev); changed = err == cudaSuccess; }
+    }
+    ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(ctx)                                                            \
+    DeviceGuard dev_guard_((ctx)->device);                                        \
+    if (dev_guard_.err != cudaSuccess) return fail((ctx), AMV_ERR_CUDA, "cudaSetDevice", dev_guard_.err)
+
 #define CK(call)                                                                  \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -143,6 +158,7 @@ int check_launch(amv_ctx *ctx, const char *what, int count = 1) {
     return AMV_OK;
 }
 
+constexpr size_t kMaxProfileEvents = 4096;
 struct ScopedTimer {
     amv_ctx *c; EvPair e; bool on;
     ScopedTimer(amv_ctx *ctx, int kind) : c(ctx), on(ctx->opt_profile) {
@@ -154,6 +170,11 @@ struct ScopedTimer {
     ~ScopedTimer() {
         if (!on) return;
         cudaEventRecord(e.b, c->stream);
+        // nobody polls: keep the newest kMaxProfileEvents samples instead of growing without bound
+        if (c->evs.size() >= kMaxProfileEvents) {
+            cudaEventDestroy(c->evs.front().a); cudaEventDestroy(c->evs.front().b);
+            c->evs.erase(c->evs.begin());
+        }
         c->evs.push_back(e);
     }
 };
@@ -468,7 +489,7 @@ int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const ui
         for (int f = f0; f < f0 + m; f++) {
             const uint64_t a = pkt_off[f], b = a + pkt_size[f];
             payload += ((uint64_t)pkt_size[f] + 15) & ~15ull;
-            if (b > pkts_bytes || b < a) continue;        // reported per frame by the kernels
+            if (b > pkts_bytes || b < a) continue;        // reported per frame by the kernels (range_ok: no wrap for any offset)
             if (a < lo) lo = a;
             if (b > hi) hi = b;
         }
@@ -625,7 +646,8 @@ AMV_API int amv_create(const amv_params *params, amv_ctx **out_ctx) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return AMV_ERR_NODEVICE;
     if (prop.major != 10) return AMV_ERR_NODEVICE;     // kernels are built for sm_100a only
-    if (cudaSetDevice(dev) != cudaSuccess) return AMV_ERR_NODEVICE;
+    DeviceGuard guard(dev);
+    if (guard.err != cudaSuccess) return AMV_ERR_NODEVICE;
     amv_ctx *ctx = new (std::nothrow) amv_ctx();
     if (!ctx) return AMV_ERR_NOMEM;
     ctx->device = dev;
@@ -649,7 +671,7 @@ AMV_API int amv_create(const amv_params *params, amv_ctx **out_ctx) {
 
 AMV_API void amv_destroy(amv_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < WS_COUNT; i++) if (ctx->ws[i].p) cudaFree(ctx->ws[i].p);
     for (size_t i = 0; i < ctx->evs.size(); i++) { cudaEventDestroy(ctx->evs[i].a); cudaEventDestroy(ctx->evs[i].b); }
@@ -770,7 +792,7 @@ static int decode_frames_common(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts
     const int cw = gm.cw, ch = gm.ch;
     if (ls_y < w || ls_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw)
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (mem == AMV_MEM_DEVICE)
         return decode_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, pkts_bytes, mode);
     return decode_host(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mode);
@@ -881,7 +903,7 @@ AMV_API int amv_mjpeg_configure(amv_ctx *ctx, const uint8_t *p, uint32_t size, i
     std::vector<uint8_t> host(dec_table_set_bytes());
     bool sync_ok = false;
     if (!build_dec_table_set(host.data(), counts, syms, qzz, &sync_ok)) return bad("Huffman codes do not fit the lookup tables");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(cudaStreamSynchronize(ctx->stream));                // nothing in flight may still use the previous configuration
     if (!ctx->mj_tables) CK(cudaMalloc(&ctx->mj_tables, dec_table_set_bytes()));
     if (ctx->mj_hdr) { cudaFree(ctx->mj_hdr); ctx->mj_hdr = nullptr; }
@@ -926,7 +948,7 @@ AMV_API int amv_decode_frames_bgr24(amv_ctx *ctx, const uint8_t *pkts, uint64_t 
     if (!pkts || !pkt_off || !pkt_size || !bgr) return fail(ctx, AMV_ERR_ARG, "null buffer");
     if (line_bytes < 3 * w || frame_stride < (uint64_t)line_bytes * (h - 1) + 3 * (uint64_t)w)
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the bitmap");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (mem == AMV_MEM_DEVICE)
         return decode_bgr_device(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, bgr, line_bytes, frame_stride, status, pkts_bytes);
     // host buffers: staged copy in, kernels, copy out (bytes of the bitmaps that no pixel covers -- row
@@ -959,7 +981,7 @@ AMV_API int amv_convert_range(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, 
     if (ls_y < w || ls_c < cw || ols_y < w || ols_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw ||
         ofs_y < (uint64_t)ols_y * (h - 1) + w || ofs_c < (uint64_t)ols_c * (ch - 1) + cw)
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (mem == AMV_MEM_DEVICE) {
         launch_convert_range(y, u, v, oy, ou, ov, n, w, h, ls_y, ls_c, fs_y, fs_c, ols_y, ols_c, ofs_y, ofs_c, dir, ctx->stream);
         return check_launch(ctx, "range conversion kernels", 3);
@@ -1003,7 +1025,7 @@ AMV_API int amv_scale_frames_ex(amv_ctx *ctx, const uint8_t *y, const uint8_t *u
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
     ScaleBanks banks;
     build_scale_banks(iw, ih, ow, oh, &banks);
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     const bool chroma = icw > 0 && ich > 0 && ocw > 0 && och > 0;
     const bool host = mem == AMV_MEM_HOST, pre = (flags & AMV_SCALE_IN_JPEG_RANGE) != 0, post = (flags & AMV_SCALE_OUT_JPEG_RANGE) != 0;
     const uint64_t ty = (uint64_t)iw * ih, tc = (uint64_t)icw * ich, oty = (uint64_t)ow * oh, otc = (uint64_t)ocw * och;
@@ -1125,7 +1147,7 @@ AMV_API int amv_audio_resample_from(amv_ctx *ctx, const int16_t *in, uint64_t in
     }
     if (mem == AMV_MEM_DEVICE && (((uintptr_t)in & (in_channels == 2 ? 3 : 1)) || ((uintptr_t)out & 1)))
         return fail(ctx, AMV_ERR_ARG, "misaligned sample pointer");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     // the polyphase bank of this rate pair (kept until the rates change)
     if (ctx->rs_in_rate != in_rate || ctx->rs_out_rate != out_rate) {
         std::vector<int16_t> rows((size_t)len * 1024);
@@ -1194,7 +1216,7 @@ AMV_API int amv_encode_frames(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, 
     const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
     if (ls_y < w || ls_c < cw || fs_y < (uint64_t)ls_y * (h - 1) + w || fs_c < (uint64_t)ls_c * (ch - 1) + cw)
         return fail(ctx, AMV_ERR_ARG, "strides smaller than the picture");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (mem == AMV_MEM_DEVICE)
         return encode_device(ctx, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, qscale, out, out_cap, pkt_cap, layout, out_off,
                              out_size, status);
@@ -1211,7 +1233,7 @@ AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx, const uint8_t *chunks, uint64_t c
     if (n < 0 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / mem");
     if (n == 0) return AMV_OK;
     if (!chunks || !chunk_off || !chunk_size || !pcm || !pcm_off) return fail(ctx, AMV_ERR_ARG, "null buffer");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (mem == AMV_MEM_DEVICE) {
         int32_t *st = status;
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
@@ -1229,8 +1251,20 @@ AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx, const uint8_t *chunks, uint64_t c
     launch_adpcm_decode(d_c, chunks_bytes, d_off, d_sz, n, d_pcm, pcm_samples, d_poff, d_st, ctx->stream);
     int r = check_launch(ctx, "adpcm decode kernel");
     if (r != AMV_OK) return r;
-    CK(cudaMemcpyAsync(pcm, d_pcm, sizeof(int16_t) * pcm_samples, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    // Only what the kernel wrote goes home: samples no chunk covers, and the regions of rejected chunks, stay as the
+    // caller had them (like the device-memory path leaves them).  Neighbouring chunks travel as one copy.
+    std::vector<int32_t> hst((size_t)n);
+    CK(cudaMemcpyAsync(hst.data(), d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t lo = 0, hi = 0;
+    for (int i = 0; i <= n; i++) {
+        const bool wrote = i < n && hst[i] == 0 && chunk_size[i] > 8;
+        const uint64_t a = wrote ? pcm_off[i] : 0, len = wrote ? 2ull * (chunk_size[i] - 8) : 0;
+        if (wrote && hi > lo && a == hi) { hi += len; continue; }
+        if (hi > lo) CK(cudaMemcpyAsync(pcm + lo, d_pcm + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyDeviceToHost, ctx->stream));
+        lo = a; hi = a + len;
+    }
+    if (status) memcpy(status, hst.data(), sizeof(int32_t) * n);
     CK(cudaStreamSynchronize(ctx->stream));
     return AMV_OK;
 }
@@ -1243,14 +1277,19 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
     if (nstreams < 0 || nchunks < 0 || bad_mem(mem)) return fail(ctx, AMV_ERR_ARG, "bad n / mem");
     if (nstreams == 0 || nchunks == 0) return AMV_OK;
     if (!pcm || !pcm_off || !nsamples || !out || !out_off) return fail(ctx, AMV_ERR_ARG, "null buffer");
-    CK(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (mem == AMV_MEM_DEVICE) {
         int32_t *st = status;
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * nchunks, st);
         { ScopedTimer tm(ctx, KK_ADPCM_ENC);
-          launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, step_in, step_out, out, out_bytes,
+          launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, nchunks, step_in, step_out, out, out_bytes,
                               out_off, st, ctx->opt_trellis, ctx->stream); }
         return check_launch(ctx, "adpcm encode kernel");
+    }
+    if (first_chunk) {      // the stream table is on the host here: it must be monotonic and end inside the chunk arrays
+        for (int s_ = 0; s_ < nstreams; s_++)
+            if (first_chunk[s_] > first_chunk[s_ + 1]) return fail(ctx, AMV_ERR_ARG, "first_chunk is not monotonic");
+        if (first_chunk[nstreams] > (uint32_t)nchunks) return fail(ctx, AMV_ERR_ARG, "first_chunk runs past nchunks");
     }
     int16_t *d_pcm; uint64_t *d_poff, *d_ooff; uint32_t *d_ns, *d_fc = nullptr; int16_t *d_si = nullptr, *d_so; uint8_t *d_out;
     int32_t *d_st;
@@ -1264,13 +1303,24 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
     ENSURE(WS_H_H, out_bytes ? out_bytes : 1, d_out);
     ENSURE(WS_H_I, sizeof(int32_t) * nchunks, d_st);
     CK(cudaMemsetAsync(d_st, 0, sizeof(int32_t) * nchunks, ctx->stream));
-    launch_adpcm_encode(d_pcm, pcm_samples, d_poff, d_ns, d_fc, nstreams, d_si, d_so, d_out, out_bytes, d_ooff, d_st,
+    launch_adpcm_encode(d_pcm, pcm_samples, d_poff, d_ns, d_fc, nstreams, nchunks, d_si, d_so, d_out, out_bytes, d_ooff, d_st,
                         ctx->opt_trellis, ctx->stream);
     int r = check_launch(ctx, "adpcm encode kernel");
     if (r != AMV_OK) return r;
-    CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    // as in amv_adpcm_dec_chunks: only the chunks that were written travel back, neighbours as one copy
+    std::vector<int32_t> hst((size_t)nchunks);
+    CK(cudaMemcpyAsync(hst.data(), d_st, sizeof(int32_t) * nchunks, cudaMemcpyDeviceToHost, ctx->stream));
     if (step_out) CK(cudaMemcpyAsync(step_out, d_so, sizeof(int16_t) * nstreams, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * nchunks, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t lo = 0, hi = 0;
+    for (int c = 0; c <= nchunks; c++) {
+        const bool wrote = c < nchunks && hst[c] == 0;
+        const uint64_t a = wrote ? out_off[c] : 0, len = wrote ? 8ull + nsamples[c] / 2 : 0;
+        if (wrote && hi > lo && a == hi) { hi += len; continue; }
+        if (hi > lo) CK(cudaMemcpyAsync(out + lo, d_out + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->stream));
+        lo = a; hi = a + len;
+    }
+    if (status) memcpy(status, hst.data(), sizeof(int32_t) * nchunks);
     CK(cudaStreamSynchronize(ctx->stream));
     return AMV_OK;
 }

@@ -90,6 +90,9 @@ AMV_HD uint32_t bswap32(uint32_t v) {
 
 AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// [off, off + len) lies inside [0, total): written so that a hostile offset near 2^64 cannot wrap the sum
+AMV_HD bool range_ok(uint64_t off, uint64_t len, uint64_t total) { return off <= total && len <= total - off; }
+
 // index of the most significant set bit (v != 0): one FLO
 AMV_HD int msb_index(uint32_t v) {
 #if defined(__CUDA_ARCH__)

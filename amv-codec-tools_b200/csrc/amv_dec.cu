@@ -110,7 +110,7 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
         const uint32_t size = pkt_size[f];
         const uint64_t slot = slot_off[f];
         int32_t st = 0;
-        if (off + size > pkts_bytes || slot + ((size + 15u) & ~15u) + kSlotPad > scratch_bytes) {
+        if (!range_ok(off, size, pkts_bytes) || !range_ok(slot, (uint64_t)((size + 15u) & ~15u) + kSlotPad, scratch_bytes)) {
             if (tid == 0) { scan_len[f] = 0; status[f] = AMV_ST_RANGE; }
             continue;
         }
@@ -1307,9 +1307,10 @@ __global__ void k_mjpeg_check(const uint8_t *__restrict__ pkts, uint64_t pkts_by
     const uint64_t off = pkt_off[f];
     const uint32_t size = pkt_size[f];
     uint8_t *q = qtab + (size_t)f * 128;
-    if (off + size > pkts_bytes || size < hdr_len + 2u) {      // out of range: k_unstuff reported it; too short: no scan
+    const bool inside = range_ok(off, size, pkts_bytes);
+    if (!inside || size < hdr_len + 2u) {      // out of range: k_unstuff reported it; too short: no scan
         for (int i = lane; i < 128; i += 32) q[i] = 1;
-        if (off + size <= pkts_bytes && lane == 0) { scan_len[f] = 0; atomicOr(&status[f], AMV_ST_HEADER); }
+        if (inside && lane == 0) { scan_len[f] = 0; atomicOr(&status[f], AMV_ST_HEADER); }
         return;
     }
     bool diff = false;

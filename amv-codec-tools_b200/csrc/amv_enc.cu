@@ -943,13 +943,17 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
 // packed layout: copy each packet from its slot to its scanned offset
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_compact(const uint8_t *__restrict__ slots, uint64_t slot_stride, const uint32_t *__restrict__ size,
+k_compact(const uint8_t *__restrict__ slots, uint64_t slot_stride, uint32_t *__restrict__ size,
           const uint64_t *__restrict__ off, int n, uint8_t *__restrict__ out, uint64_t out_cap,
           int32_t *__restrict__ status) {
     for (int f = blockIdx.x; f < n; f += gridDim.x) {
         const uint32_t sz = size[f];
         const uint64_t o = off[f];
-        if (o + sz > out_cap) { if (threadIdx.x == 0) atomicOr(&status[f], AMV_ST_NOSPACE); continue; }
+        if (!range_ok(o, sz, out_cap)) {        // amvcuda.h: out_size is 0 wherever status is not (every thread has read size[f])
+            __syncthreads();
+            if (threadIdx.x == 0) { atomicOr(&status[f], AMV_ST_NOSPACE); size[f] = 0; }
+            continue;
+        }
         const uint8_t *src = slots + (uint64_t)f * slot_stride;
         uint8_t *dst = out + o;
         // head bytes up to 16-byte alignment of dst, then 128-bit stores fed by two aligned
@@ -1051,7 +1055,7 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
                          slots, slot_stride, pkt_cap, out_size, status, form ? redo : nullptr);
 }
 
-void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
+void launch_compact(const uint8_t *slots, uint64_t slot_stride, uint32_t *size, const uint64_t *off, int n,
                     uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s) {
     const int grid = n < kNumSMs * 8 ? (n < 1 ? 1 : n) : kNumSMs * 8;
     AMV_LAUNCH(k_compact, grid, 256, 0, s, slots, slot_stride, size, off, n, out, out_cap, status);

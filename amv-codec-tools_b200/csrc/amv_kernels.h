@@ -99,7 +99,7 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
                    int n, const Geom &g, const int32_t *qscale, uint8_t *slots, uint64_t slot_stride, uint32_t pkt_cap,
                    uint32_t *out_size, int32_t *status, int32_t *redo /* n flags of scratch, or nullptr: one-kernel path */,
                    int form /* 0 one kernel, 1 k_encode16 + k_encode, 2 k_encode16v2 + k_encode */, cudaStream_t s);
-void launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint32_t *size, const uint64_t *off, int n,
+void launch_compact(const uint8_t *slots, uint64_t slot_stride, uint32_t *size /* zeroed where the packet does not fit */, const uint64_t *off, int n,
                     uint8_t *out, uint64_t out_cap, int32_t *status, cudaStream_t s);
 void launch_export_meta(const uint64_t *off, const uint32_t *sz, const int32_t *st, uint64_t *hoff, uint32_t *hsz, int32_t *hst,
                         int n, cudaStream_t s);
@@ -110,7 +110,7 @@ cudaError_t upload_adpcm_tables(cudaStream_t s);
 void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *off, const uint32_t *size, int n,
                          int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s);
 void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
-                         const uint32_t *first_chunk, int nstreams, const int16_t *step_in, int16_t *step_out,
+                         const uint32_t *first_chunk, int nstreams, int nchunks, const int16_t *step_in, int16_t *step_out,
                          uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, cudaStream_t s);
 
 }  // namespace amv
