@@ -112,7 +112,10 @@ struct DeviceGuard {
     cudaError_t err = cudaSuccess;
     explicit DeviceGuard(int dev) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) { err = cudaSetDevice(dev); changed = err == cudaSuccess; }
+        // always set: on a host thread that has made no CUDA call yet this is what binds the device's context to the
+        // thread (without it cudaPointerGetAttributes reports no device pointer for pinned memory)
+        err = cudaSetDevice(dev);
+        changed = err == cudaSuccess && prev != dev;
     }
     ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
 };

@@ -26,8 +26,7 @@ import bench  # noqa: E402
 
 
 def synth(n, w, h, t0, dev, seed):
-    bench.W, bench.H, bench.CW, bench.CH = w, h, (w + 1) // 2, (h + 1) // 2
-    return bench.synth_frames_torch(n, t0, dev, seed)
+    return bench.synth_frames_torch(n, t0, dev, seed, w, h)
 
 
 def main():
