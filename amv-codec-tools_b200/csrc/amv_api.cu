@@ -55,6 +55,8 @@ struct amv_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     void *pinned_meta = nullptr;
     size_t pinned_meta_cap = 0;
+    void *pinned_small = nullptr;       // staging of small host calls (the AVCodec callbacks: one frame per call)
+    size_t pinned_small_cap = 0;
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
     int opt_resample_form = 2;          // audio resampler: 2 = phase rows (M outputs per coefficient row), 1 = tiles, 0 = direct form
     int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
@@ -65,6 +67,7 @@ struct amv_ctx {
     // 9.16 + 9.31 / 12.38 + 8.01 / 12.33 + 8.01 ms -- the token pass is ALU-pipe bound and the 32-bit token's offset and
     // product cost it more than they save the consumer.
     int opt_token_pass = 2;
+    bool opt_small_calls = true;        // host calls of a few frames: one pinned block, one stream, one synchronisation
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
     // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
     void *mj_tables = nullptr;          // DecTableSet in device memory
@@ -444,6 +447,131 @@ void *device_view(const void *host_ptr) {
     return nullptr;
 }
 
+// ------------------------------------------------------------------------------------ small host calls
+// A call that moves a few frames (the AVCodec callbacks hand over ONE frame or packet per call, ffmpeg.c:1083,814) does not
+// need the three-stream copy pipeline above, and cannot afford it: event rings, three stream synchronisations and
+// per-plane pageable copies cost ~2 ms per call.  Here everything rides the context's one stream: the caller's bytes are
+// gathered into one pinned block (a CPU memcpy), one H2D copy, the kernels, one D2H copy, ONE synchronisation, and a CPU
+// memcpy into the caller's (strided) buffers.
+constexpr size_t kSmallCallBytes = 8u << 20;
+
+int ensure_small(amv_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->pinned_small_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
+        ctx->pinned_small = nullptr; ctx->pinned_small_cap = 0;
+        const size_t want = bytes + bytes / 4 + 65536;
+        CK(cudaMallocHost(&ctx->pinned_small, want));
+        ctx->pinned_small_cap = want;
+    }
+    return AMV_OK;
+}
+
+inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
+
+void copy_rows(uint8_t *dst, size_t dst_ls, const uint8_t *src, size_t src_ls, int width, int rows) {
+    if (dst_ls == (size_t)width && src_ls == (size_t)width) { memcpy(dst, src, (size_t)width * rows); return; }
+    for (int r = 0; r < rows; r++) memcpy(dst + r * dst_ls, src + r * src_ls, width);
+}
+
+int decode_host_small(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t *pkt_off, const uint32_t *pkt_size,
+                      int n, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+                      int32_t *status, const DecMode &mode) {
+    const Geom gm = mode.geom(w, h);
+    const int cw = gm.cw, ch = gm.ch;
+    const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    // the byte range the packets span (frames whose range is outside the buffer keep their offsets: the kernels flag them)
+    uint64_t lo = UINT64_MAX, hi = 0, payload = 0;
+    for (int f = 0; f < n; f++) {
+        const uint64_t a = pkt_off[f], b = a + pkt_size[f];
+        payload += ((uint64_t)pkt_size[f] + 15) & ~15ull;
+        if (b > pkts_bytes || b < a) continue;
+        if (a < lo) lo = a;
+        if (b > hi) hi = b;
+    }
+    if (hi < lo) { lo = 0; hi = 0; }
+    const size_t span = (size_t)(hi - lo);
+    // pinned block: [packets][offsets][sizes] in, [status][planes] out
+    const size_t o_off = al256(span), o_sz = o_off + al256(8 * (size_t)n), in_bytes = o_sz + al256(4 * (size_t)n);
+    const size_t o_st = in_bytes, o_y = o_st + al256(4 * (size_t)n), o_u = o_y + ty * n, o_v = o_u + tc * n, all_bytes = al256(o_v + tc * n);
+    int r = ensure_small(ctx, all_bytes);
+    if (r != AMV_OK) return r;
+    uint8_t *pin = static_cast<uint8_t *>(ctx->pinned_small), *dev;
+    ENSURE(WS_H_A, all_bytes, dev);
+    if (span) memcpy(pin, pkts + lo, span);
+    uint64_t *p_off = reinterpret_cast<uint64_t *>(pin + o_off);
+    for (int f = 0; f < n; f++) {
+        const uint64_t a = pkt_off[f], b = a + pkt_size[f];
+        p_off[f] = (b > pkts_bytes || b < a) ? UINT64_MAX - 0xffff : a - lo;     // out of range stays out of range
+    }
+    memcpy(pin + o_sz, pkt_size, 4 * (size_t)n);
+    CK(cudaMemcpyAsync(dev, pin, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    r = decode_device(ctx, dev, span, reinterpret_cast<uint64_t *>(dev + o_off), reinterpret_cast<uint32_t *>(dev + o_sz), n, w, h,
+                      dev + o_y, dev + o_u, dev + o_v, w, cw, ty, tc, reinterpret_cast<int32_t *>(dev + o_st), payload, mode);
+    if (r != AMV_OK) return r;
+    CK(cudaMemcpyAsync(pin + o_st, dev + o_st, all_bytes - o_st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t *p_st = reinterpret_cast<const int32_t *>(pin + o_st);
+    for (int f = 0; f < n; f++) {
+        if (p_st[f] & (AMV_ST_RANGE | AMV_ST_HEADER)) continue;        // nothing was decoded for this frame: the caller's planes stay
+        copy_rows(y + fs_y * f, ls_y, pin + o_y + ty * f, w, w, h);
+        copy_rows(u + fs_c * f, ls_c, pin + o_u + tc * f, cw, cw, ch);
+        copy_rows(v + fs_c * f, ls_c, pin + o_v + tc * f, cw, cw, ch);
+    }
+    if (status) memcpy(status, p_st, 4 * (size_t)n);
+    return AMV_OK;
+}
+
+int encode_host_small(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_y, int ls_c, uint64_t fs_y,
+                      uint64_t fs_c, int n, int w, int h, const int32_t *qscale, uint8_t *out, uint64_t out_cap, uint32_t pkt_cap,
+                      int layout, uint64_t *out_off, uint32_t *out_size, int32_t *status) {
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    // a packet never exceeds 3000 bytes per macroblock in the reference (MAX_MB_BYTES, mpegvideo.h:75); the device-side slot
+    // is the smaller of the caller's pkt_cap and that bound, so a 1 MB bit buffer does not become 1 MB of D2H
+    const uint64_t mb_bound = 3000ull * (uint64_t)((w + 15) / 16) * ((h + 15) / 16) + 1024;
+    const uint32_t dcap = (uint32_t)((pkt_cap < mb_bound ? pkt_cap : mb_bound) + 15) & ~15u;
+    if (layout == AMV_LAYOUT_SLOTS && (uint64_t)pkt_cap * n > out_cap) return fail(ctx, AMV_ERR_ARG, "out_cap < n * pkt_cap");
+    const size_t o_u = ty * n, o_v = o_u + tc * n, o_q = al256(o_v + tc * n), in_bytes = o_q + al256(4 * (size_t)n);
+    const size_t o_off = in_bytes, o_sz = o_off + al256(8 * (size_t)n), o_st = o_sz + al256(4 * (size_t)n), o_pk = o_st + al256(4 * (size_t)n);
+    const size_t all_bytes = al256(o_pk + (size_t)dcap * n);
+    int r = ensure_small(ctx, all_bytes);
+    if (r != AMV_OK) return r;
+    uint8_t *pin = static_cast<uint8_t *>(ctx->pinned_small), *dev;
+    ENSURE(WS_H_A, all_bytes, dev);
+    for (int f = 0; f < n; f++) {
+        copy_rows(pin + ty * f, w, y + fs_y * f, ls_y, w, h);
+        copy_rows(pin + o_u + tc * f, cw, u + fs_c * f, ls_c, cw, ch);
+        copy_rows(pin + o_v + tc * f, cw, v + fs_c * f, ls_c, cw, ch);
+    }
+    if (qscale) memcpy(pin + o_q, qscale, 4 * (size_t)n);
+    CK(cudaMemcpyAsync(dev, pin, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    r = encode_device(ctx, dev, dev + o_u, dev + o_v, w, cw, ty, tc, n, w, h, qscale ? reinterpret_cast<int32_t *>(dev + o_q) : nullptr,
+                      dev + o_pk, (uint64_t)dcap * n, dcap, AMV_LAYOUT_SLOTS, reinterpret_cast<uint64_t *>(dev + o_off),
+                      reinterpret_cast<uint32_t *>(dev + o_sz), reinterpret_cast<int32_t *>(dev + o_st));
+    if (r != AMV_OK) return r;
+    // sizes and status first; then exactly the bytes that were produced
+    CK(cudaMemcpyAsync(pin + o_sz, dev + o_sz, o_pk - o_sz, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t *p_sz = reinterpret_cast<const uint32_t *>(pin + o_sz);
+    int32_t *p_st = reinterpret_cast<int32_t *>(pin + o_st);
+    for (int f = 0; f < n; f++)
+        if (p_sz[f]) CK(cudaMemcpyAsync(pin + o_pk + (size_t)dcap * f, dev + o_pk + (size_t)dcap * f, p_sz[f], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t pos = 0;
+    for (int f = 0; f < n; f++) {
+        uint32_t sz = p_sz[f];
+        // a packet that fits the device slot but not the caller's: "encoded frame too large"
+        const uint64_t dst = layout == AMV_LAYOUT_SLOTS ? (uint64_t)pkt_cap * f : pos;
+        if (p_st[f] == 0 && (sz > pkt_cap || dst + sz > out_cap)) { p_st[f] = AMV_ST_NOSPACE; sz = 0; }
+        if (sz) memcpy(out + dst, pin + o_pk + (size_t)dcap * f, sz);
+        out_off[f] = dst; out_size[f] = sz;
+        pos += sz;
+    }
+    if (status) memcpy(status, p_st, 4 * (size_t)n);
+    return AMV_OK;
+}
+
 // How the host path moves data:
 //  * bulk planes travel by DMA (cudaMemcpyAsync, in <= 16 MB pieces) on their own copy streams, in a
 //    3-deep ring of chunks that overlaps copy-in, kernels and copy-out;
@@ -460,6 +588,8 @@ int decode_host(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const ui
     const Geom gm = mode.geom(w, h);
     const int cw = gm.cw, ch = gm.ch;
     const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    if (ctx->opt_small_calls && (ty + 2 * tc) * n + pkts_bytes <= kSmallCallBytes)
+        return decode_host_small(ctx, pkts, pkts_bytes, pkt_off, pkt_size, n, w, h, y, u, v, ls_y, ls_c, fs_y, fs_c, status, mode);
     const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
     // pinned bounce: status (4) + offsets (8) + sizes (4) per frame
     int r = ensure_pipeline(ctx, 16 * (size_t)n);
@@ -528,6 +658,8 @@ int encode_host(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t 
                 int layout, uint64_t *out_off, uint32_t *out_size, int32_t *status) {
     const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
     const uint64_t ty = (uint64_t)w * h, tc = (uint64_t)cw * ch;
+    if (ctx->opt_small_calls && (ty + 2 * tc) * n <= kSmallCallBytes / 2)
+        return encode_host_small(ctx, y, u, v, ls_y, ls_c, fs_y, fs_c, n, w, h, qscale, out, out_cap, pkt_cap, layout, out_off, out_size, status);
     const int C = host_chunk_frames(ctx, n, (size_t)(ty + 2 * tc));
     // pinned metadata: offsets (8), sizes (4), status (4), qscale (4) per frame
     int r = ensure_pipeline(ctx, 20 * (size_t)n);
@@ -601,6 +733,7 @@ int encode_host(amv_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t 
     if (status) memcpy(status, p_st, sizeof(int32_t) * n);
     return AMV_OK;
 }
+
 
 bool bad_mem(int mem) { return mem != AMV_MEM_HOST && mem != AMV_MEM_DEVICE; }
 
@@ -681,6 +814,7 @@ AMV_API void amv_destroy(amv_ctx *ctx) {
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->pinned_meta) cudaFreeHost(ctx->pinned_meta);
+    if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
     if (ctx->mj_tables) cudaFree(ctx->mj_tables);
     if (ctx->mj_hdr) cudaFree(ctx->mj_hdr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -728,6 +862,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
         return AMV_OK;
     }
     if (!strcmp(key, "host_zero_copy_packets")) { ctx->opt_zero_copy_packets = value != 0; return AMV_OK; }
+    if (!strcmp(key, "host_small_calls")) { ctx->opt_small_calls = value != 0; return AMV_OK; }
     if (!strcmp(key, "decode_token_pass")) {
         if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
         ctx->opt_token_pass = (int)value;

@@ -9,15 +9,25 @@
  *
  *   amvcuda_amv_decoder            replaces amv_decoder            (sp5xdec.c:203-212)
  *   amvcuda_sp5x_decoder           replaces sp5x_decoder           (sp5xdec.c:190-201; same callback, other framing)
- *   amvcuda_mjpeg_decoder          replaces mjpeg_decoder          (mjpegdec.c:1356-1367; baseline 4:2:0 frames only)
+ *   amvcuda_mjpeg_decoder          replaces mjpeg_decoder          (mjpegdec.c:1356-1367; baseline frames, 4:2:0 / 4:2:2 / 4:4:4)
  *   amvcuda_amv_encoder            replaces amv_encoder            (mjpegenc.c:485-494)
  *   amvcuda_adpcm_ima_amv_decoder  replaces adpcm_ima_amv_decoder  (adpcm.c:1535)
  *   amvcuda_adpcm_ima_amv_encoder  replaces adpcm_ima_amv_encoder  (adpcm.c:1535)
+ *
+ *   amvcuda_amv_encoder_delay / amvcuda_amv_decoder_delay: the same two codecs with a look-ahead queue
+ *                                  (CODEC_CAP_DELAY, avcodec.h:446): the library is a BATCH codec and a call per frame
+ *                                  pays a fixed host cost; these queue AMVCUDA_LOOKAHEAD (default 64) frames / packets,
+ *                                  hand them to libamvcuda in one call and return results one per call, the encoder
+ *                                  answering 0 bytes and the decoder got_picture = 0 while the queue fills
+ *                                  (utils.c:910,938 call a delayed codec with NULL / no data to drain it, ffmpeg.c:1088
+ *                                  and its end-of-stream flush handle both).  Registered instead of the plain ones when
+ *                                  the environment sets AMVCUDA_LOOKAHEAD.
  *
  * avcodec_find_decoder/encoder return the FIRST registered match (utils.c:1023-1056), so
  * amvcuda_register_codecs() must run before avcodec_register_all() -- or the four
  * REGISTER_ENCDEC lines of allcodecs.c:64,255 are pointed at these symbols.
  */
+#include <stdlib.h>
 #include <string.h>
 #include "avcodec.h"
 #include "amvcuda.h"
@@ -210,6 +220,215 @@ AVCodec amvcuda_amv_encoder = {
     .pix_fmts = amvcuda_pix_fmts,
 };
 
+
+/* ------------------------------------------------------------------- look-ahead (delayed) video codecs */
+static int amvcuda_lookahead(void)
+{
+    const char *e = getenv("AMVCUDA_LOOKAHEAD");
+    int k = e ? atoi(e) : 64;
+    return k < 1 ? 1 : (k > 4096 ? 4096 : k);
+}
+
+typedef struct AmvCudaEncQueue {
+    amv_ctx *h;
+    AVFrame coded;
+    int depth, nq, w, h_, cw, ch;        /* queue depth, frames waiting */
+    uint8_t *y, *u, *v;                  /* depth frames, tight planes (pinned) */
+    int32_t *qscale;
+    int64_t *pts, *out_pts;
+    int *quality, *out_quality;
+    uint8_t *pk;                         /* the batch's packets (pinned), packed */
+    uint64_t pk_cap, *off;
+    uint32_t *size;
+    int32_t *status;
+    int nout, iout;                      /* packets of the last batch, next one to hand out */
+} AmvCudaEncQueue;
+
+static int amvcuda_encq_init(AVCodecContext *avctx)
+{
+    AmvCudaEncQueue *c = avctx->priv_data;
+    const int w = avctx->width, h = avctx->height, k = amvcuda_lookahead();
+    if (avctx->pix_fmt != PIX_FMT_YUVJ420P && avctx->pix_fmt != PIX_FMT_YUV420P) return -1;
+    if (avctx->thread_count > 1 || avctx->trellis || avctx->intra_dc_precision || (avctx->flags & CODEC_FLAG_GRAY)) return -1;
+    if (!avctx->time_base.num || !avctx->time_base.den) return -1;
+    if (amv_create(NULL, &c->h) != AMV_OK) return -1;
+    c->depth = k; c->w = w; c->h_ = h; c->cw = (w + 1) / 2; c->ch = (h + 1) / 2;
+    c->pk_cap = (uint64_t)k * (3000ull * ((w + 15) / 16) * ((h + 15) / 16) + 1024);      /* MAX_MB_BYTES per macroblock */
+    c->y = amv_host_alloc((size_t)k * w * h);
+    c->u = amv_host_alloc((size_t)k * c->cw * c->ch);
+    c->v = amv_host_alloc((size_t)k * c->cw * c->ch);
+    c->pk = amv_host_alloc(c->pk_cap);
+    c->qscale = av_malloc(k * sizeof(*c->qscale)); c->status = av_malloc(k * sizeof(*c->status));
+    c->pts = av_malloc(k * sizeof(*c->pts)); c->out_pts = av_malloc(k * sizeof(*c->out_pts));
+    c->quality = av_malloc(k * sizeof(int)); c->out_quality = av_malloc(k * sizeof(int));
+    c->off = av_malloc(k * sizeof(*c->off)); c->size = av_malloc(k * sizeof(*c->size));
+    if (!c->y || !c->u || !c->v || !c->pk || !c->qscale || !c->status || !c->pts || !c->out_pts || !c->off || !c->size) return -1;
+    avctx->coded_frame = &c->coded;
+    avctx->delay = k - 1;
+    return 0;
+}
+
+static int amvcuda_encq_close(AVCodecContext *avctx)
+{
+    AmvCudaEncQueue *c = avctx->priv_data;
+    amv_host_free(c->y); amv_host_free(c->u); amv_host_free(c->v); amv_host_free(c->pk);
+    av_free(c->qscale); av_free(c->status); av_free(c->pts); av_free(c->out_pts); av_free(c->quality); av_free(c->out_quality);
+    av_free(c->off); av_free(c->size);
+    amv_destroy(c->h);
+    c->h = NULL;
+    return 0;
+}
+
+static int amvcuda_encq_run(AmvCudaEncQueue *c)
+{
+    const int w = c->w, h = c->h_;
+    int i;
+    if (amv_encode_frames(c->h, c->y, c->u, c->v, w, c->cw, (uint64_t)w * h, (uint64_t)c->cw * c->ch, c->nq, w, h, c->qscale,
+                          c->pk, c->pk_cap, (uint32_t)(c->pk_cap / c->depth), AMV_LAYOUT_PACKED, c->off, c->size, c->status,
+                          AMV_MEM_HOST) != AMV_OK)
+        return -1;
+    for (i = 0; i < c->nq; i++) { c->out_pts[i] = c->pts[i]; c->out_quality[i] = c->quality[i]; }
+    c->nout = c->nq; c->iout = 0; c->nq = 0;
+    return 0;
+}
+
+/* one frame in (or NULL to drain), at most one packet out; 0 = nothing yet */
+static int amvcuda_encq_frame(AVCodecContext *avctx, uint8_t *buf, int buf_size, void *data)
+{
+    AmvCudaEncQueue *c = avctx->priv_data;
+    AVFrame *pic = data;
+    const int w = c->w, h = c->h_;
+    int r, i;
+    if (avctx->flags & CODEC_FLAG_EMU_EDGE) return -1;
+    if (pic) {
+        uint8_t *dy = c->y + (size_t)c->nq * w * h, *du = c->u + (size_t)c->nq * c->cw * c->ch, *dv = c->v + (size_t)c->nq * c->cw * c->ch;
+        for (r = 0; r < h; r++) memcpy(dy + r * w, pic->data[0] + r * pic->linesize[0], w);
+        for (r = 0; r < c->ch; r++) {
+            memcpy(du + r * c->cw, pic->data[1] + r * pic->linesize[1], c->cw);
+            memcpy(dv + r * c->cw, pic->data[2] + r * pic->linesize[2], c->cw);
+        }
+        c->qscale[c->nq] = amv_qscale_from_quality(pic->quality, avctx->qmin, avctx->qmax);
+        c->pts[c->nq] = pic->pts; c->quality[c->nq] = pic->quality;
+        c->nq++;
+    }
+    /* the previous batch is handed out one packet per call, so it is empty exactly when the queue is full again */
+    if (c->iout >= c->nout && c->nq > 0 && (c->nq == c->depth || !pic)) {
+        if (amvcuda_encq_run(c) < 0) return -1;
+    }
+    if (c->iout >= c->nout) return 0;
+    i = c->iout++;
+    if (c->status[i] || (int)c->size[i] > buf_size) return -1;       /* "encoded frame too large" (mpegvideo_enc.c:2077-2080) */
+    memcpy(buf, c->pk + c->off[i], c->size[i]);
+    c->coded.key_frame = 1;
+    c->coded.pict_type = FF_I_TYPE;
+    c->coded.quality = c->out_quality[i];
+    c->coded.pts = c->out_pts[i];
+    return (int)c->size[i];
+}
+
+AVCodec amvcuda_amv_encoder_delay = {
+    "amv", CODEC_TYPE_VIDEO, CODEC_ID_AMV, sizeof(AmvCudaEncQueue),
+    amvcuda_encq_init, amvcuda_encq_frame, amvcuda_encq_close, NULL, CODEC_CAP_DELAY,
+    .pix_fmts = amvcuda_pix_fmts,
+};
+
+typedef struct AmvCudaDecQueue {
+    amv_ctx *h;
+    AVFrame picture;
+    int depth, nq, w, h_, cw, ch;
+    uint8_t *pk;                         /* queued packets (pinned), back to back */
+    uint64_t pk_cap, pk_used, *off;
+    uint32_t *size;
+    int32_t *status;
+    uint8_t *y[2], *u[2], *v[2];         /* two batches of decoded planes: one being handed out, one being filled next */
+    int cur, nout, iout;
+} AmvCudaDecQueue;
+
+static int amvcuda_decq_init(AVCodecContext *avctx)
+{
+    AmvCudaDecQueue *c = avctx->priv_data;
+    avctx->pix_fmt = PIX_FMT_YUVJ420P;
+    c->depth = amvcuda_lookahead();
+    c->off = av_malloc(c->depth * sizeof(*c->off)); c->size = av_malloc(c->depth * sizeof(*c->size));
+    c->status = av_malloc(c->depth * sizeof(*c->status));
+    if (!c->off || !c->size || !c->status) return -1;
+    return amv_create(NULL, &c->h) == AMV_OK ? 0 : -1;
+}
+
+static int amvcuda_decq_close(AVCodecContext *avctx)
+{
+    AmvCudaDecQueue *c = avctx->priv_data;
+    int i;
+    for (i = 0; i < 2; i++) { amv_host_free(c->y[i]); amv_host_free(c->u[i]); amv_host_free(c->v[i]); }
+    amv_host_free(c->pk);
+    av_free(c->off); av_free(c->size); av_free(c->status);
+    amv_destroy(c->h);
+    c->h = NULL;
+    return 0;
+}
+
+static int amvcuda_decq_run(AmvCudaDecQueue *c)
+{
+    const int w = c->w, h = c->h_, b = c->cur ^ 1;
+    if (amv_decode_frames(c->h, c->pk, c->pk_used, c->off, c->size, c->nq, w, h, c->y[b], c->u[b], c->v[b], w, c->cw,
+                          (uint64_t)w * h, (uint64_t)c->cw * c->ch, c->status, AMV_MEM_HOST) != AMV_OK)
+        return -1;
+    c->cur = b; c->nout = c->nq; c->iout = 0; c->nq = 0; c->pk_used = 0;
+    return 0;
+}
+
+/* one packet in (or buf_size 0 to drain), at most one picture out.  The pictures are decoder-owned (planes of the batch,
+ * valid until the batch after next is decoded, i.e. for at least `depth` further calls). */
+static int amvcuda_decq_frame(AVCodecContext *avctx, void *data, int *data_size, uint8_t *buf, int buf_size)
+{
+    AmvCudaDecQueue *c = avctx->priv_data;
+    AVFrame *out = data;
+    const int w = avctx->width, h = avctx->height;
+    int i;
+    if (!w || !h) return -1;
+    if (!c->pk) {        /* first call: the dimensions are known now (avidec.c:429-434 sets them from the container) */
+        c->w = w; c->h_ = h; c->cw = (w + 1) / 2; c->ch = (h + 1) / 2;
+        c->pk_cap = (uint64_t)c->depth * (3000ull * ((w + 15) / 16) * ((h + 15) / 16) + 1024);
+        c->pk = amv_host_alloc(c->pk_cap);
+        for (i = 0; i < 2; i++) {
+            c->y[i] = amv_host_alloc((size_t)c->depth * w * h);
+            c->u[i] = amv_host_alloc((size_t)c->depth * c->cw * c->ch);
+            c->v[i] = amv_host_alloc((size_t)c->depth * c->cw * c->ch);
+            if (!c->y[i] || !c->u[i] || !c->v[i]) return -1;
+        }
+        if (!c->pk) return -1;
+    } else if (w != c->w || h != c->h_) return -1;
+    avctx->pix_fmt = PIX_FMT_YUVJ420P;
+    if (buf_size > 0) {
+        if (c->pk_used + (uint64_t)buf_size > c->pk_cap) return -1;
+        memcpy(c->pk + c->pk_used, buf, buf_size);
+        c->off[c->nq] = c->pk_used; c->size[c->nq] = (uint32_t)buf_size;
+        c->pk_used += (uint64_t)buf_size; c->nq++;
+    }
+    if (c->iout >= c->nout && c->nq > 0 && (c->nq == c->depth || buf_size == 0)) {
+        if (amvcuda_decq_run(c) < 0) return -1;
+    }
+    *data_size = 0;
+    if (c->iout >= c->nout) return buf_size;
+    i = c->iout++;
+    memset(&c->picture, 0, sizeof(c->picture));
+    c->picture.data[0] = c->y[c->cur] + (size_t)i * w * h;
+    c->picture.data[1] = c->u[c->cur] + (size_t)i * c->cw * c->ch;
+    c->picture.data[2] = c->v[c->cur] + (size_t)i * c->cw * c->ch;
+    c->picture.linesize[0] = w; c->picture.linesize[1] = c->cw; c->picture.linesize[2] = c->cw;
+    c->picture.pict_type = FF_I_TYPE;
+    c->picture.key_frame = 1;
+    c->picture.quality = 9 * FF_QP2LAMBDA;
+    *out = c->picture;
+    *data_size = sizeof(AVFrame);
+    return buf_size;
+}
+
+AVCodec amvcuda_amv_decoder_delay = {
+    "amv", CODEC_TYPE_VIDEO, CODEC_ID_AMV, sizeof(AmvCudaDecQueue),
+    amvcuda_decq_init, NULL, amvcuda_decq_close, amvcuda_decq_frame, CODEC_CAP_DELAY,
+};
+
 /* ------------------------------------------------------------------------------------- audio */
 typedef struct AmvCudaAudio {
     amv_ctx *h;
@@ -298,8 +517,9 @@ AVCodec amvcuda_adpcm_ima_amv_encoder = {
 /* Call before avcodec_register_all(): first match wins in avcodec_find_{en,de}coder. */
 void amvcuda_register_codecs(void)
 {
-    register_avcodec(&amvcuda_amv_encoder);
-    register_avcodec(&amvcuda_amv_decoder);
+    const int delayed = getenv("AMVCUDA_LOOKAHEAD") != NULL;        /* opt-in: the batch (look-ahead) video codecs */
+    register_avcodec(delayed ? &amvcuda_amv_encoder_delay : &amvcuda_amv_encoder);
+    register_avcodec(delayed ? &amvcuda_amv_decoder_delay : &amvcuda_amv_decoder);
     register_avcodec(&amvcuda_sp5x_decoder);
     register_avcodec(&amvcuda_mjpeg_decoder);
     register_avcodec(&amvcuda_adpcm_ima_amv_encoder);

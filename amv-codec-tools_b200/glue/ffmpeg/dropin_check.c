@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include "avcodec.h"
 #include "swscale.h"
 
@@ -23,7 +24,7 @@ void amvcuda_audio_resample_close(ReSampleContext *s);
 
 extern AVCodec amv_decoder, amv_encoder, adpcm_ima_amv_decoder, adpcm_ima_amv_encoder, sp5x_decoder, mjpeg_decoder, mjpeg_encoder;
 extern AVCodec amvcuda_amv_decoder, amvcuda_amv_encoder, amvcuda_adpcm_ima_amv_decoder, amvcuda_adpcm_ima_amv_encoder,
-               amvcuda_sp5x_decoder, amvcuda_mjpeg_decoder;
+               amvcuda_sp5x_decoder, amvcuda_mjpeg_decoder, amvcuda_amv_encoder_delay, amvcuda_amv_decoder_delay;
 void amvcuda_register_codecs(void);
 
 static int g_pix_fmt = PIX_FMT_YUVJ420P;      /* input / output layout of encode_all / decode_all */
@@ -44,6 +45,84 @@ static void make_frame(uint8_t *y, uint8_t *u, uint8_t *v, int w, int h, int t)
 }
 
 typedef struct { uint8_t *pk; int size; } Packet;
+
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+/* The per-frame loop of ffmpeg.c for codecs that may delay their output (CODEC_CAP_DELAY): a call may return nothing
+ * (ffmpeg.c:1088 `if (!got_picture) goto discard_packet`; the encoder side writes a packet only `if (ret > 0)`), and at
+ * the end of the stream the codec is called with no input until it has nothing left.  `reps` passes over the n frames are
+ * timed (codec calls only, open / close outside); the outputs of the first pass are kept. */
+static int encode_timed(AVCodec *codec, int w, int h, int n, int quality, uint8_t **ys, uint8_t **us, uint8_t **vs, Packet *out,
+                        int reps, double *fps)
+{
+    AVCodecContext *c = avcodec_alloc_context();
+    AVFrame *pic = avcodec_alloc_frame();
+    int i, r, got = 0, total = 0, bufsz = w * h * 6 + 262144, cw = (w + 1) / 2;
+    uint8_t *buf = av_malloc(bufsz);
+    double t0;
+    c->width = w; c->height = h; c->time_base.num = 1; c->time_base.den = 16; c->pix_fmt = g_pix_fmt;
+    if (avcodec_open(c, codec) < 0) return -1;
+    t0 = now_s();
+    for (r = 0; r < reps; r++)
+        for (i = 0; i <= n; i++) {
+            int sz;
+            if (i < n) {
+                pic->data[0] = ys[i]; pic->data[1] = us[i]; pic->data[2] = vs[i];
+                pic->linesize[0] = w; pic->linesize[1] = cw; pic->linesize[2] = cw;
+                pic->quality = quality; pic->pts = (int64_t)r * n + i;
+                sz = avcodec_encode_video(c, buf, bufsz, pic);
+            } else if (r == reps - 1 && (codec->capabilities & CODEC_CAP_DELAY)) {
+                sz = avcodec_encode_video(c, buf, bufsz, NULL);            /* drain */
+                if (sz > 0) i--;                                           /* ... until it answers 0 */
+            } else break;
+            if (sz < 0) return -2;
+            if (sz == 0) continue;
+            if (c->coded_frame->pts != total) return -4;                   /* packets come out in frame order with their own pts */
+            if (got < n) {
+                out[got].pk = malloc(sz + FF_INPUT_BUFFER_PADDING_SIZE); memset(out[got].pk, 0, sz + FF_INPUT_BUFFER_PADDING_SIZE);
+                memcpy(out[got].pk, buf, sz); out[got].size = sz; got++;
+            }
+            total++;
+        }
+    *fps = total / (now_s() - t0);
+    avcodec_close(c); av_free(c); av_free(pic); av_free(buf);
+    return total == reps * n ? 0 : -5;
+}
+
+static int decode_timed(AVCodec *codec, int w, int h, int n, Packet *pk, uint8_t *planes, int reps, double *fps)
+{
+    AVCodecContext *c = avcodec_alloc_context();
+    AVFrame *pic = avcodec_alloc_frame();
+    int i, r, rr, outn = 0, total = 0, cw = (w + 1) / 2, ch = (h + 1) / 2;
+    double t0;
+    c->width = w; c->height = h; c->coded_width = w; c->coded_height = h;
+    if (avcodec_open(c, codec) < 0) return -1;
+    t0 = now_s();
+    for (r = 0; r < reps; r++)
+        for (i = 0; i <= n; i++) {
+            int got = 0, ret;
+            if (i < n) ret = avcodec_decode_video(c, pic, &got, pk[i].pk, pk[i].size);
+            else if (r == reps - 1 && (codec->capabilities & CODEC_CAP_DELAY)) {
+                ret = avcodec_decode_video(c, pic, &got, NULL, 0);        /* drain (utils.c:938) */
+                if (got) i--;
+            } else break;
+            if (ret < 0) return -2;
+            if (!got) continue;
+            if (outn < n) {
+                uint8_t *d = planes + (size_t)outn * (w * h + 2 * cw * ch);
+                for (rr = 0; rr < h; rr++) memcpy(d + rr * w, pic->data[0] + rr * pic->linesize[0], w);
+                for (rr = 0; rr < ch; rr++) {
+                    memcpy(d + w * h + rr * cw, pic->data[1] + rr * pic->linesize[1], cw);
+                    memcpy(d + w * h + cw * ch + rr * cw, pic->data[2] + rr * pic->linesize[2], cw);
+                }
+                outn++;
+            }
+            total++;
+        }
+    *fps = total / (now_s() - t0);
+    avcodec_close(c); av_free(c); av_free(pic);
+    return total == reps * n ? 0 : -5;
+}
 
 static int encode_all(AVCodec *codec, int w, int h, int n, int quality, uint8_t **ys, uint8_t **us, uint8_t **vs, Packet *out)
 {
@@ -123,6 +202,7 @@ int main(int argc, char **argv)
     int i, fail = 0;
     avcodec_init();
     av_log_set_level(AV_LOG_QUIET);
+    unsetenv("AMVCUDA_LOOKAHEAD");                   /* the plain shims are the registered ones in this check */
     amvcuda_register_codecs();                       /* first match wins ...                              */
     register_avcodec(&amv_encoder); register_avcodec(&amv_decoder);   /* ... then what avcodec_register_all adds */
     register_avcodec(&adpcm_ima_amv_encoder); register_avcodec(&adpcm_ima_amv_decoder);
@@ -203,6 +283,32 @@ int main(int argc, char **argv)
             }
         }
         free(da); free(db);
+    }
+    {   /* what the drop-in costs per call, next to the callbacks it replaces: the same frames through the reference's CPU
+         * codecs, through the shims one frame per call, and through the look-ahead (CODEC_CAP_DELAY) shims that hand
+         * libamvcuda whole batches; outputs of all three must be the same bytes */
+        const int scale = argc > 4 ? atoi(argv[4]) : 100;      /* percent of the default timing effort */
+        if (argc > 5) setenv("AMVCUDA_LOOKAHEAD", argv[5], 1); /* queue depth of the look-ahead codecs (default 64) */
+        const int reps_ref = 1 + 2 * scale / n, reps = 1 + 20 * scale / n, reps_q = 1 + 200 * scale / n;
+        Packet *pr = calloc(n, sizeof(Packet)), *ps = calloc(n, sizeof(Packet)), *pq = calloc(n, sizeof(Packet));
+        uint8_t *dr = malloc((size_t)n * fb), *ds = malloc((size_t)n * fb), *dq = malloc((size_t)n * fb);
+        double f_er = 0, f_es = 0, f_eq = 0, f_dr = 0, f_ds = 0, f_dq = 0;
+        int r1 = encode_timed(&amv_encoder, w, h, n, 0, ys, us, vs, pr, reps_ref, &f_er);
+        int r2 = encode_timed(&amvcuda_amv_encoder, w, h, n, 0, ys, us, vs, ps, reps, &f_es);
+        int r3 = encode_timed(&amvcuda_amv_encoder_delay, w, h, n, 0, ys, us, vs, pq, reps_q, &f_eq);
+        if (r1 || r2 || r3) { printf("FAIL: timed encode returned %d / %d / %d\n", r1, r2, r3); return 12; }
+        for (i = 0; i < n; i++)
+            if (pr[i].size != ps[i].size || memcmp(pr[i].pk, ps[i].pk, pr[i].size) || pr[i].size != pq[i].size || memcmp(pr[i].pk, pq[i].pk, pr[i].size)) {
+                printf("FAIL: timed run, packet %d differs (shim %d, look-ahead %d, reference %d bytes)\n", i, ps[i].size, pq[i].size, pr[i].size); fail = 1;
+            }
+        r1 = decode_timed(&amv_decoder, w, h, n, pr, dr, reps_ref, &f_dr);
+        r2 = decode_timed(&amvcuda_amv_decoder, w, h, n, pr, ds, reps, &f_ds);
+        r3 = decode_timed(&amvcuda_amv_decoder_delay, w, h, n, pr, dq, reps_q, &f_dq);
+        if (r1 || r2 || r3) { printf("FAIL: timed decode returned %d / %d / %d\n", r1, r2, r3); return 13; }
+        if (memcmp(dr, ds, (size_t)n * fb) || memcmp(dr, dq, (size_t)n * fb)) { printf("FAIL: timed run, decoded planes differ\n"); fail = 1; }
+        printf("drop-in frames/s %dx%d (one host thread): encode reference %.0f | shim, one frame per call %.0f | shim, look-ahead queue %.0f ;"
+               " decode reference %.0f | shim %.0f | look-ahead %.0f ; outputs %s\n", w, h, f_er, f_es, f_eq, f_dr, f_ds, f_dq,
+               fail ? "DIFFER" : "identical");
     }
     for (g_trellis = 0; g_trellis <= 3; g_trellis += 3) {      /* plain encoder, then -trellis 3 */
         const int total = 22050 * 2 + 999, fs = 1378;

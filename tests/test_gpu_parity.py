@@ -327,15 +327,19 @@ DROPIN = os.path.join(amv.PKG_DIR, "glue", "_build", "dropin_check")
 
 
 @pytest.mark.skipif(not os.path.exists(DROPIN), reason="glue/_build/dropin_check not built (needs the reference tree)")
-@pytest.mark.parametrize("w,h,n", [(160, 120, 24), (320, 240, 6), (208, 176, 5)])
-def test_avcodec_dropin_matches_reference_codecs(w, h, n):
+@pytest.mark.parametrize("w,h,n,extra", [(160, 120, 24, []), (320, 240, 6, []), (208, 176, 5, []), (160, 120, 24, ["50", "7"]),
+                                         (320, 240, 150, ["100", "64"])])
+def test_avcodec_dropin_matches_reference_codecs(w, h, n, extra):
     """The reference's own libavcodec, driven like ffmpeg.c drives it, once with the libamvcuda AVCodec
     shims registered first (avcodec_find_* returns them) and once with its CPU codecs: identical
-    packets, planes, ADPCM chunks and PCM (glue/ffmpeg/dropin_check.c)."""
+    packets, planes, ADPCM chunks and PCM (glue/ffmpeg/dropin_check.c).  The same frames also go through the
+    look-ahead (CODEC_CAP_DELAY) shims -- extra = [timing effort %, queue depth]: depth 7 / 64 with more frames than
+    the queue holds runs the steady state (a batch handed out while the next one fills), the default depth the drain."""
     import subprocess
-    out = subprocess.run([DROPIN, str(w), str(h), str(n)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([DROPIN, str(w), str(h), str(n)] + extra, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "DROP-IN CHECK OK" in out.stdout
+    assert "DROP-IN CHECK OK" in out.stdout and "drop-in frames/s" in out.stdout
+    print([ln for ln in out.stdout.splitlines() if ln.startswith("drop-in frames/s")][0])
 
 
 def test_host_path_pinned_zero_copy_and_chunked(ctx, oracle):
