@@ -144,6 +144,153 @@ k_adpcm_decode(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_adpcm_decode_async: the decoder with per-lane ASYNCHRONOUS staging of its input.  k_adpcm_decode above fetches a
+// tile of 32 chunks x 32 nibble bytes with 32 warp-wide loads of one BYTE per lane (two shuffles each) -- as many
+// instructions as the 768 the tile's arithmetic needs.  Here every lane asks for its own chunk's next 64 bytes -- the
+// 16-byte aligned span around them, at most 80 bytes -- one tile ahead, decodes the previous tile out of its own
+// shared-memory row meanwhile, and only the PCM goes out cooperatively (one chunk row per store instruction: 128
+// contiguous bytes).  Every 16-byte unit the copy touches holds at least one byte of the chunk, so nothing outside the
+// caller's buffer's last unit is read.  Two ways of asking, same kernel otherwise:
+//   BULK   cp.async.bulk.shared.global on the warp's mbarrier (the TMA unit's 1-D copy, SASS UBLKCP).  Its operands are
+//          warp-uniform, so 32 lanes with 32 addresses issue one after the other (an ELECT / R2UR loop, ~10 instructions
+//          per lane and tile);
+//   else   cp.async 16-byte copies (SASS LDGSTS): per-thread addressing, five instructions per lane and tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkWarps = 4;
+constexpr int kBulkTile = 64;                        // nibble bytes per chunk per tile
+constexpr int kBulkRow = kBulkTile + 16;             // the aligned span of a tile
+constexpr int kBulkOutPitch = kBulkTile + 1;         // words: 64 sample pairs + 1 (conflict-free columns)
+
+struct AdpcmBulkWarp {
+    __align__(16) uint8_t in[2][32][kBulkRow];
+    uint32_t out[32 * kBulkOutPitch];
+    uint64_t dst[32];
+    uint32_t nb[32];
+    __align__(8) uint64_t bar[2];
+};
+struct AdpcmBulkSmem {
+    uint16_t step[96];
+    __align__(16) AdpcmBulkWarp w[kBulkWarps];
+};
+
+template <bool BULK>
+__global__ void __launch_bounds__(kBulkWarps * 32)
+k_adpcm_decode_async(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, const uint64_t *__restrict__ off,
+                     const uint32_t *__restrict__ size, int n, int16_t *__restrict__ pcm, uint64_t pcm_samples,
+                     const uint64_t *__restrict__ pcm_off, int32_t *__restrict__ status) {
+    AMV_EXTERN_SHARED(uint8_t, adpcm_smem_raw, 16);
+    AdpcmBulkSmem &S = *reinterpret_cast<AdpcmBulkSmem *>(adpcm_smem_raw);
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) S.step[i] = g_ima_step[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    AdpcmBulkWarp &W = S.w[wid];
+    const uint32_t bar0_s = smem_addr(&W.bar[0]);                       // stage b: + 8 b
+    const uint32_t row0_s = smem_addr(&W.in[0][lane][0]);               // stage b: + b * sizeof(W.in[0])
+    if (BULK && lane == 0) { mbar_init(bar0_s, 32); mbar_init(bar0_s + 8, 32); }
+    __syncthreads();
+    const int nwarps = (n + 31) >> 5;
+    uint32_t phases = 0;                                                // bit b: parity stage b's barrier completes next
+
+    for (int wg = blockIdx.x * kBulkWarps + wid; wg < nwarps; wg += gridDim.x * kBulkWarps) {
+        const int c = wg * 32 + lane;
+        uint64_t src = 0, dsts = 0;
+        uint32_t nbytes = 0;      // nibble bytes of this lane's chunk
+        int pred = 0, idx = 0, st = 0;
+        if (c < n) {
+            const uint64_t o = off[c];
+            const uint32_t sz = size[c];
+            dsts = pcm_off[c];
+            if (sz < 8) st = AMV_ST_SHORT;
+            else if (!range_ok(o, sz, chunks_bytes) || !range_ok(dsts, 2ull * (sz - 8), pcm_samples)) st = AMV_ST_RANGE;
+            else {
+                const uint8_t *h = chunks + o;
+                pred = (int)(int16_t)(h[0] | (h[1] << 8));
+                idx = (int)(int16_t)(h[2] | (h[3] << 8));
+                if (idx < 0 || idx > 88) st = AMV_ST_RANGE;   // the reference indexes step_table out of bounds here
+                else { src = o + 8; nbytes = sz - 8; }
+            }
+            status[c] = st;
+        }
+        W.dst[lane] = dsts;
+        W.nb[lane] = nbytes;
+        uint32_t maxb = nbytes;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, d));
+        const uint32_t ntiles = (maxb + kBulkTile - 1) / kBulkTile;
+        const uint8_t *base = chunks + src;
+        // the tile's aligned span goes to the lane's row of stage b; every lane takes part, with or without bytes
+        auto issue = [&](uint32_t t, uint32_t b) {
+            const uint32_t t0 = t * kBulkTile, row_s = row0_s + b * (uint32_t)sizeof(W.in[0]);
+            uint32_t bytes = 0;
+            uintptr_t a16 = 0;
+            if (t0 < nbytes) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(base + t0), e = a + min((uint32_t)kBulkTile, nbytes - t0);
+                a16 = a & ~uintptr_t(15);
+                bytes = (uint32_t)(((e + 15) & ~uintptr_t(15)) - a16);
+            }
+            if (BULK) {
+                if (bytes) {
+                    fence_proxy_async();               // the row was read (two tiles ago) through the generic proxy
+                    mbar_arrive_expect_tx(bar0_s + 8 * b, bytes);
+                    bulk_g2s(row_s, reinterpret_cast<const void *>(a16), bytes, bar0_s + 8 * b);
+                } else mbar_arrive_expect_tx(bar0_s + 8 * b, 0);
+            } else {
+                for (uint32_t k = 0; k < bytes; k += 16) cp_async16(row_s + k, reinterpret_cast<const void *>(a16 + k));
+                cp_async_commit();
+            }
+        };
+        __syncwarp();
+        if (ntiles) issue(0, 0);
+        for (uint32_t t = 0; t < ntiles; t++) {
+            const uint32_t b = t & 1u;
+            if (t + 1 < ntiles) issue(t + 1, b ^ 1u);
+            if (BULK) { mbar_wait(bar0_s + 8 * b, (phases >> b) & 1u); phases ^= 1u << b; }
+            else { if (t + 1 < ntiles) cp_async_wait<1>(); else cp_async_wait<0>(); }
+            const uint32_t t0 = t * kBulkTile;
+            if (t0 < nbytes) {
+                const uint32_t len = min((uint32_t)kBulkTile, nbytes - t0);
+                const uint32_t ra = row0_s + b * (uint32_t)sizeof(W.in[0]) + (uint32_t)(reinterpret_cast<uintptr_t>(base + t0) & 15);
+                uint32_t *orow = W.out + lane * kBulkOutPitch;
+                const uint32_t wa = ra & ~3u, sh = (ra & 3u) * 8u;
+                uint32_t lo = lds32(wa);
+                for (uint32_t w = 0; w * 4 < len; w++) {
+                    const uint32_t hi = lds32(wa + 4 * w + 4);
+                    const uint32_t v = __funnelshift_r(lo, hi, sh);
+                    lo = hi;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (w * 4 + k < len) {
+                            const int byte = (v >> (8 * k)) & 0xff;
+                            const int s0 = ima_expand(byte >> 4, pred, idx, S.step);      // high nibble first (:1281-1282)
+                            const int s1 = ima_expand(byte & 15, pred, idx, S.step);
+                            orow[w * 4 + k] = (uint32_t)(s0 & 0xffff) | ((uint32_t)s1 << 16);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // warp-cooperative store: chunk j's sample pairs, two 32-bit words per lane
+            for (int j = 0; j < 32; j++) {
+                const uint32_t nj = W.nb[j];
+                if (t0 >= nj) continue;
+                const uint32_t lenj = min((uint32_t)kBulkTile, nj - t0);
+                int16_t *d = pcm + W.dst[j] + 2ull * t0;
+                const bool al = (reinterpret_cast<uintptr_t>(d) & 3) == 0;
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const uint32_t wi = (uint32_t)lane + 32u * hh;
+                    if (wi < lenj) {
+                        const uint32_t v = W.out[j * kBulkOutPitch + wi];
+                        if (al) *reinterpret_cast<uint32_t *>(d + 2 * wi) = v;
+                        else { d[2 * wi] = (int16_t)(v & 0xffff); d[2 * wi + 1] = (int16_t)(v >> 16); }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One lane per stream; a stream is a run of chunks whose step index is chained.  With
 // first_chunk == NULL every chunk is its own stream.
 __global__ void __launch_bounds__(kAdpcmThreads)
@@ -244,6 +391,139 @@ k_adpcm_encode(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint
                     const uint32_t bytes_left = (nj - t0 + 1) / 2;
                     if ((uint32_t)lane < bytes_left)
                         outb[dj + 8 + t0 / 2 + lane] = reinterpret_cast<const uint8_t *>(nib + j * kNibPitch)[lane];
+                }
+                __syncwarp();
+            }
+        }
+        if (s < nstreams && step_out) step_out[s] = (int16_t)idx;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_adpcm_encode_async: the encoder with the same per-lane asynchronous input staging as k_adpcm_decode_async (cp.async,
+// 16-byte copies: the aligned span around the lane's next 64 samples, at most 144 bytes, one tile ahead) instead of 32
+// warp-wide loads of two samples per lane; nibble bytes still leave cooperatively, one chunk row per store instruction,
+// with the chunks' output offsets and sizes read from shared memory instead of shuffled.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEncRow = 2 * kTileSamples + 16;       // bytes: the aligned span of 64 samples
+struct AdpcmEncWarp {
+    __align__(16) uint8_t in[2][32][kEncRow];
+    uint32_t nib[32 * kNibPitch];
+    uint64_t dst[32];
+    uint32_t ns[32];
+};
+struct AdpcmEncSmem {
+    uint16_t step[96];
+    __align__(16) AdpcmEncWarp w[kBulkWarps];
+};
+
+__global__ void __launch_bounds__(kBulkWarps * 32)
+k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, const uint64_t *__restrict__ pcm_off,
+                     const uint32_t *__restrict__ nsamples, const uint32_t *__restrict__ first_chunk, int nstreams, int nchunks,
+                     const int16_t *__restrict__ step_in, int16_t *__restrict__ step_out, uint8_t *__restrict__ outb,
+                     uint64_t out_bytes, const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
+    AMV_EXTERN_SHARED(uint8_t, adpcm_enc_smem_raw, 16);
+    AdpcmEncSmem &S = *reinterpret_cast<AdpcmEncSmem *>(adpcm_enc_smem_raw);
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) S.step[i] = g_ima_step[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    AdpcmEncWarp &W = S.w[wid];
+    const uint32_t row0_s = smem_addr(&W.in[0][lane][0]);               // stage b: + b * sizeof(W.in[0])
+    const int nwarps = (nstreams + 31) >> 5;
+
+    for (int wg = blockIdx.x * kBulkWarps + wid; wg < nwarps; wg += gridDim.x * kBulkWarps) {
+        const int s = wg * 32 + lane;
+        uint32_t c0 = 0, c1 = 0;
+        int idx = 0;
+        bool dead = false;          // a bad chunk stops its stream
+        if (s < nstreams) {
+            c0 = first_chunk ? first_chunk[s] : (uint32_t)s;
+            c1 = first_chunk ? first_chunk[s + 1] : (uint32_t)s + 1;
+            if (c1 > (uint32_t)nchunks) c1 = (uint32_t)nchunks;
+            if (c0 > c1) c0 = c1;
+            idx = step_in ? step_in[s] : 0;
+            if (idx < 0 || idx > 88) { dead = true; for (uint32_t c = c0; c < c1; c++) status[c] = AMV_ST_RANGE; }
+        }
+        uint32_t maxc = c1 - c0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+
+        for (uint32_t k = 0; k < maxc; k++) {
+            const uint32_t c = c0 + k;
+            const bool have = !dead && c < c1;
+            if (dead && c < c1 && s < nstreams) status[c] = AMV_ST_RANGE;     // rest of a broken stream
+            uint64_t src = 0, dst = 0;
+            uint32_t ns = 0;
+            int prev = 0;
+            if (have) {
+                ns = nsamples[c]; src = pcm_off[c]; dst = out_off[c];
+                int st = 0;
+                if (ns & 1) st = AMV_ST_RANGE;
+                else if (!range_ok(src, ns, pcm_samples) || !range_ok(dst, 8ull + ns / 2, out_bytes)) st = AMV_ST_RANGE;
+                status[c] = st;
+                if (st) { dead = true; ns = 0; }
+                else {
+                    // header: first sample, step index carried in, sample count (adpcm.c:464-479)
+                    prev = ns ? pcm[src] : 0;
+                    uint8_t *h = outb + dst;
+                    h[0] = (uint8_t)prev; h[1] = (uint8_t)(prev >> 8);
+                    h[2] = (uint8_t)idx;  h[3] = (uint8_t)(idx >> 8);
+                    h[4] = (uint8_t)ns; h[5] = (uint8_t)(ns >> 8); h[6] = (uint8_t)(ns >> 16); h[7] = (uint8_t)(ns >> 24);
+                }
+            }
+            W.dst[lane] = dst;
+            W.ns[lane] = ns;
+            uint32_t maxs = ns;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) maxs = max(maxs, __shfl_xor_sync(0xffffffffu, maxs, d));
+            const uint32_t ntiles = (maxs + kTileSamples - 1) / kTileSamples;
+            const int16_t *base = pcm + src;
+            auto issue = [&](uint32_t t, uint32_t b) {
+                const uint32_t t0 = t * kTileSamples, row_s = row0_s + b * (uint32_t)sizeof(W.in[0]);
+                if (t0 < ns) {
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(base + t0), e = a + 2u * min((uint32_t)kTileSamples, ns - t0);
+                    const uintptr_t a16 = a & ~uintptr_t(15);
+                    const uint32_t bytes = (uint32_t)(((e + 15) & ~uintptr_t(15)) - a16);
+                    for (uint32_t q = 0; q < bytes; q += 16) cp_async16(row_s + q, reinterpret_cast<const void *>(a16 + q));
+                }
+                cp_async_commit();
+            };
+            __syncwarp();
+            if (ntiles) issue(0, 0);
+            for (uint32_t t = 0; t < ntiles; t++) {
+                const uint32_t b = t & 1u, t0 = t * kTileSamples;
+                if (t + 1 < ntiles) { issue(t + 1, b ^ 1u); cp_async_wait<1>(); } else cp_async_wait<0>();
+                if (t0 < ns) {
+                    // the lane's samples sit in its row from the byte the source address has inside its 16-byte unit (even)
+                    const uint32_t ra = row0_s + b * (uint32_t)sizeof(W.in[0]) + (uint32_t)(reinterpret_cast<uintptr_t>(base + t0) & 15);
+                    const uint32_t wa = ra & ~3u, sh = (ra & 3u) * 8u;
+                    uint32_t *orow = W.nib + lane * kNibPitch;
+                    uint32_t lo = lds32(wa);
+#pragma unroll
+                    for (int w = 0; w < kTileBytes / 4; w++) {
+                        uint32_t packed = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t hi = lds32(wa + 4u * (w * 4 + q) + 4u);
+                            const uint32_t v = __funnelshift_r(lo, hi, sh);
+                            lo = hi;
+                            // sample pairs past the end of the chunk are not encoded (keeps the carried state exact)
+                            if (t0 + 2 * (w * 4 + q) < ns) {
+                                const int n0 = ima_compress((int)(int16_t)(v & 0xffff), prev, idx, S.step);
+                                const int n1 = ima_compress((int)(int16_t)(v >> 16), prev, idx, S.step);
+                                packed |= (uint32_t)((n0 << 4) | n1) << (8 * q);
+                            }
+                        }
+                        orow[w] = packed;
+                    }
+                }
+                __syncwarp();
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t nj = W.ns[j];
+                    if (t0 >= nj) continue;
+                    const uint32_t bytes_left = (nj - t0 + 1) / 2;
+                    if ((uint32_t)lane < bytes_left)
+                        outb[W.dst[j] + 8 + t0 / 2 + lane] = reinterpret_cast<const uint8_t *>(W.nib + j * kNibPitch)[lane];
                 }
                 __syncwarp();
             }
@@ -381,15 +661,31 @@ static int adpcm_grid(int units) {
     return ctas < 1 ? 1 : (ctas < cap ? ctas : cap);
 }
 
+cudaError_t adpcm_setup_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_adpcm_decode_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdpcmBulkSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_adpcm_decode_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdpcmBulkSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_adpcm_encode_async, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdpcmEncSmem));
+    return e;
+}
+
 void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *off, const uint32_t *size, int n,
-                         int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s) {
+                         int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, int form, cudaStream_t s) {
+    if (form) {             // asynchronous input staging: 2 = cp.async.bulk + mbarrier (UBLKCP), 1 = cp.async (LDGSTS)
+        const int warps = (n + 31) / 32, ctas = (warps + kBulkWarps - 1) / kBulkWarps, cap = kNumSMs * 4;
+        const int grid = ctas < 1 ? 1 : (ctas < cap ? ctas : cap);
+        if (form == 2) AMV_LAUNCH(k_adpcm_decode_async<true>, grid, kBulkWarps * 32, sizeof(AdpcmBulkSmem), s, chunks, chunks_bytes, off, size, n,
+                                  pcm, pcm_samples, pcm_off, status);
+        else           AMV_LAUNCH(k_adpcm_decode_async<false>, grid, kBulkWarps * 32, sizeof(AdpcmBulkSmem), s, chunks, chunks_bytes, off, size, n,
+                                  pcm, pcm_samples, pcm_off, status);
+        return;
+    }
     AMV_LAUNCH(k_adpcm_decode, adpcm_grid(n), kAdpcmThreads, 0, s, chunks, chunks_bytes, off, size, n, pcm, pcm_samples, pcm_off,
                                                            status);
 }
 
 void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
                          const uint32_t *first_chunk, int nstreams, int nchunks, const int16_t *step_in, int16_t *step_out,
-                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, cudaStream_t s) {
+                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, int form, cudaStream_t s) {
     if (trellis > 0) {
         const int grid = (nstreams + 127) / 128;
 #define AMV_TRELLIS_CASE(T)                                                                                              \
@@ -400,6 +696,12 @@ void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_
             default: break;
         }
 #undef AMV_TRELLIS_CASE
+        return;
+    }
+    if (form) {             // asynchronous input staging (cp.async)
+        const int warps = (nstreams + 31) / 32, ctas = (warps + kBulkWarps - 1) / kBulkWarps, cap = kNumSMs * 5;
+        AMV_LAUNCH(k_adpcm_encode_async, ctas < 1 ? 1 : (ctas < cap ? ctas : cap), kBulkWarps * 32, sizeof(AdpcmEncSmem), s, pcm, pcm_samples,
+                   pcm_off, nsamples, first_chunk, nstreams, nchunks, step_in, step_out, out, out_bytes, out_off, status);
         return;
     }
     AMV_LAUNCH(k_adpcm_encode, adpcm_grid(nstreams), kAdpcmThreads, 0, s, pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams,

@@ -67,6 +67,7 @@ struct amv_ctx {
     // 9.16 + 9.31 / 12.38 + 8.01 / 12.33 + 8.01 ms -- the token pass is ALU-pipe bound and the 32-bit token's offset and
     // product cost it more than they save the consumer.
     int opt_token_pass = 2;
+    int opt_adpcm_form = 1;             // ADPCM decode input staging: 1 = cp.async (LDGSTS), 2 = cp.async.bulk + mbarrier (UBLKCP), 0 = cooperative loads
     bool opt_small_calls = true;        // host calls of a few frames: one pinned block, one stream, one synchronisation
     bool opt_zero_copy_packets = true;  // decode: kernels read pinned packets in place (else: DMA into a device copy)
     // plain JPEG (amv_mjpeg_configure): the table set and the header bytes every frame must start with
@@ -796,6 +797,7 @@ AMV_API int amv_create(const amv_params *params, amv_ctx **out_ctx) {
     // "done" flag left every device after the first without the shared-memory opt-in)
     cudaError_t e = encode_setup_device();
     if (e == cudaSuccess) e = decode_setup_device();
+    if (e == cudaSuccess) e = adpcm_setup_device();
     if (e == cudaSuccess) e = upload_dec_tables(ctx->stream);
     if (e == cudaSuccess) e = upload_enc_tables(ctx->stream);
     if (e == cudaSuccess) e = upload_adpcm_tables(ctx->stream);
@@ -862,6 +864,11 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
         return AMV_OK;
     }
     if (!strcmp(key, "host_zero_copy_packets")) { ctx->opt_zero_copy_packets = value != 0; return AMV_OK; }
+    if (!strcmp(key, "adpcm_form")) {
+        if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
+        ctx->opt_adpcm_form = (int)value;
+        return AMV_OK;
+    }
     if (!strcmp(key, "host_small_calls")) { ctx->opt_small_calls = value != 0; return AMV_OK; }
     if (!strcmp(key, "decode_token_pass")) {
         if (value < 0 || value > 2) return AMV_ERR_UNSUPPORTED;
@@ -1376,7 +1383,7 @@ AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx, const uint8_t *chunks, uint64_t c
         int32_t *st = status;
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
         { ScopedTimer tm(ctx, KK_ADPCM_DEC);
-          launch_adpcm_decode(chunks, chunks_bytes, chunk_off, chunk_size, n, pcm, pcm_samples, pcm_off, st, ctx->stream); }
+          launch_adpcm_decode(chunks, chunks_bytes, chunk_off, chunk_size, n, pcm, pcm_samples, pcm_off, st, ctx->opt_adpcm_form, ctx->stream); }
         return check_launch(ctx, "adpcm decode kernel");
     }
     uint8_t *d_c; uint64_t *d_off, *d_poff; uint32_t *d_sz; int16_t *d_pcm; int32_t *d_st;
@@ -1386,7 +1393,7 @@ AMV_API int amv_adpcm_dec_chunks(amv_ctx *ctx, const uint8_t *chunks, uint64_t c
     TO_DEVICE(WS_H_D, pcm_off, sizeof(uint64_t) * n, d_poff);
     ENSURE(WS_H_E, sizeof(int16_t) * pcm_samples, d_pcm);
     ENSURE(WS_H_F, sizeof(int32_t) * n, d_st);
-    launch_adpcm_decode(d_c, chunks_bytes, d_off, d_sz, n, d_pcm, pcm_samples, d_poff, d_st, ctx->stream);
+    launch_adpcm_decode(d_c, chunks_bytes, d_off, d_sz, n, d_pcm, pcm_samples, d_poff, d_st, ctx->opt_adpcm_form, ctx->stream);
     int r = check_launch(ctx, "adpcm decode kernel");
     if (r != AMV_OK) return r;
     // Only what the kernel wrote goes home: samples no chunk covers, and the regions of rejected chunks, stay as the
@@ -1421,7 +1428,7 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
         if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * nchunks, st);
         { ScopedTimer tm(ctx, KK_ADPCM_ENC);
           launch_adpcm_encode(pcm, pcm_samples, pcm_off, nsamples, first_chunk, nstreams, nchunks, step_in, step_out, out, out_bytes,
-                              out_off, st, ctx->opt_trellis, ctx->stream); }
+                              out_off, st, ctx->opt_trellis, ctx->opt_adpcm_form, ctx->stream); }
         return check_launch(ctx, "adpcm encode kernel");
     }
     if (first_chunk) {      // the stream table is on the host here: it must be monotonic and end inside the chunk arrays
@@ -1442,7 +1449,7 @@ static int adpcm_encode_common(amv_ctx *ctx, const int16_t *pcm, uint64_t pcm_sa
     ENSURE(WS_H_I, sizeof(int32_t) * nchunks, d_st);
     CK(cudaMemsetAsync(d_st, 0, sizeof(int32_t) * nchunks, ctx->stream));
     launch_adpcm_encode(d_pcm, pcm_samples, d_poff, d_ns, d_fc, nstreams, nchunks, d_si, d_so, d_out, out_bytes, d_ooff, d_st,
-                        ctx->opt_trellis, ctx->stream);
+                        ctx->opt_trellis, ctx->opt_adpcm_form, ctx->stream);
     int r = check_launch(ctx, "adpcm encode kernel");
     if (r != AMV_OK) return r;
     // as in amv_adpcm_dec_chunks: only the chunks that were written travel back, neighbours as one copy

@@ -121,6 +121,15 @@ inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (ui
 inline void sts8(uint32_t saddr, uint32_t v) { *smem_ptr<uint8_t>(saddr) = (uint8_t)v; }
 inline void sts128(uint32_t saddr, const uint4 &v) { *smem_ptr<uint4>(saddr) = v; }
 inline void red_or_shared(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) |= v; }
+// 1-D bulk asynchronous copy + mbarrier: the emulator copies at once, so every wait is already satisfied
+inline void mbar_init(uint32_t, uint32_t) {}
+inline void mbar_arrive_expect_tx(uint32_t, uint32_t) {}
+inline void bulk_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t) { memcpy(smem_ptr<uint8_t>(dst_saddr), src, bytes); }
+inline void mbar_wait(uint32_t, uint32_t) {}
+inline void fence_proxy_async() {}
+inline void cp_async16(uint32_t dst_saddr, const void *src) { memcpy(smem_ptr<uint8_t>(dst_saddr), src, 16); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
 #elif defined(__CUDACC__)
 // Shared memory through explicit 32-bit shared-window addresses: keeps the hot loops free of
 // generic-address arithmetic (ptxas otherwise re-derives the shared window base inside them).
@@ -163,6 +172,30 @@ __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {
 __device__ __forceinline__ void sts8(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
 }
+// 1-D bulk asynchronous copy global -> shared (the TMA unit's non-tensor form: SASS UBLKCP) completing on an mbarrier.
+// dst, src and bytes are multiples of 16.
+__device__ __forceinline__ void mbar_init(uint32_t bar_saddr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_saddr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar_saddr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t bar_saddr) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(bar_saddr), "r"(parity) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before its later async-proxy (bulk copy) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// per-thread asynchronous 16-byte copies global -> shared (SASS LDGSTS), grouped and waited for by group count
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_saddr), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

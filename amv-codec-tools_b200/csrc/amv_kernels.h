@@ -107,10 +107,13 @@ void launch_slot_offsets(uint64_t *off, int n, uint64_t stride, uint64_t base, c
 
 // ---- adpcm
 cudaError_t upload_adpcm_tables(cudaStream_t s);
+cudaError_t adpcm_setup_device();
 void launch_adpcm_decode(const uint8_t *chunks, uint64_t chunks_bytes, const uint64_t *off, const uint32_t *size, int n,
-                         int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status, cudaStream_t s);
+                         int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, int32_t *status,
+                         int form /* input staging: 2 cp.async.bulk + mbarrier, 1 cp.async, 0 cooperative byte loads */, cudaStream_t s);
 void launch_adpcm_encode(const int16_t *pcm, uint64_t pcm_samples, const uint64_t *pcm_off, const uint32_t *nsamples,
                          const uint32_t *first_chunk, int nstreams, int nchunks, const int16_t *step_in, int16_t *step_out,
-                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis, cudaStream_t s);
+                         uint8_t *out, uint64_t out_bytes, const uint64_t *out_off, int32_t *status, int trellis,
+                         int form /* 1 (or 2) cp.async input staging, 0 cooperative loads */, cudaStream_t s);
 
 }  // namespace amv
