@@ -63,6 +63,22 @@ __device__ __forceinline__ int ima_compress(int sample, int &prev, int &idx, con
     return q | (delta < 0 ? 8 : 0);
 }
 
+// the same with the step table addressed through its shared-window address (no generic-pointer arithmetic in the loop)
+__device__ __forceinline__ int ima_compress_s(int sample, int &prev, int &idx, uint32_t step_s) {
+    const int step = (int)lds_u16(step_s + 2u * (uint32_t)idx);
+    const int delta = sample - prev;
+    int t = (delta < 0 ? -delta : delta) * 4;
+    int q = 0;
+    if (t >= 4 * step) { q = 4; t -= 4 * step; }
+    if (t >= 2 * step) { q |= 2; t -= 2 * step; }
+    if (t >= step) q |= 1;
+    const int mv = (step * (2 * q + 1)) >> 3;        // (step * difflookup) / 8, magnitude part
+    prev = delta < 0 ? prev - mv : prev + mv;
+    prev = min(max(prev, -32768), 32767);
+    idx = min(max(idx + ima_index_adjust(q), 0), 88);
+    return q | (delta < 0 ? 8 : 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kAdpcmThreads)
 k_adpcm_decode(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, const uint64_t *__restrict__ off,
@@ -181,6 +197,7 @@ k_adpcm_decode_async(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, 
     AMV_EXTERN_SHARED(uint8_t, adpcm_smem_raw, 16);
     AdpcmBulkSmem &S = *reinterpret_cast<AdpcmBulkSmem *>(adpcm_smem_raw);
     for (int i = threadIdx.x; i < 96; i += blockDim.x) S.step[i] = g_ima_step[i];
+    const uint32_t step_s = smem_addr(&S.step[0]);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     AdpcmBulkWarp &W = S.w[wid];
     const uint32_t bar0_s = smem_addr(&W.bar[0]);                       // stage b: + 8 b
@@ -252,17 +269,35 @@ k_adpcm_decode_async(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, 
                 uint32_t *orow = W.out + lane * kBulkOutPitch;
                 const uint32_t wa = ra & ~3u, sh = (ra & 3u) * 8u;
                 uint32_t lo = lds32(wa);
+                // one nibble (adpcm_ima_expand_nibble, adpcm.c:716-742).  A single look-up per (step index, nibble) was
+                // measured too (a 5.7 KB table of difference | next index): 2.51 ms per 1 M chunks against 1.88 ms for this
+                // arithmetic -- the table's dependent shared-memory load sits in the chain from nibble to nibble.
+                auto expand = [&](int nib) -> uint32_t {
+                    const int step = (int)lds_u16(step_s + 2u * (uint32_t)idx);
+                    const int q = nib & 7;
+                    idx = min(max(idx + ima_index_adjust(q), 0), 88);
+                    const int diff = ((2 * q + 1) * step) >> 3;
+                    pred = (nib & 8) ? pred - diff : pred + diff;
+                    pred = min(max(pred, -32768), 32767);
+                    return (uint32_t)pred;
+                };
                 for (uint32_t w = 0; w * 4 < len; w++) {
                     const uint32_t hi = lds32(wa + 4 * w + 4);
                     const uint32_t v = __funnelshift_r(lo, hi, sh);
                     lo = hi;
+                    if (w * 4 + 4 <= len) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (w * 4 + k < len) {
-                            const int byte = (v >> (8 * k)) & 0xff;
-                            const int s0 = ima_expand(byte >> 4, pred, idx, S.step);      // high nibble first (:1281-1282)
-                            const int s1 = ima_expand(byte & 15, pred, idx, S.step);
-                            orow[w * 4 + k] = (uint32_t)(s0 & 0xffff) | ((uint32_t)s1 << 16);
+                        for (int k = 0; k < 4; k++) {                          // high nibble first (:1281-1282)
+                            const uint32_t s0 = expand((int)(v >> (8 * k + 4)) & 15);
+                            const uint32_t s1 = expand((int)(v >> (8 * k)) & 15);
+                            orow[w * 4 + k] = __byte_perm(s0, s1, 0x5410);
+                        }
+                    } else {
+                        for (uint32_t k = 0; w * 4 + k < len; k++) {
+                            const uint32_t byte = (v >> (8 * k)) & 0xffu;
+                            const uint32_t s0 = expand((int)(byte >> 4));
+                            const uint32_t s1 = expand((int)(byte & 15u));
+                            orow[w * 4 + k] = __byte_perm(s0, s1, 0x5410);
                         }
                     }
                 }
@@ -429,6 +464,7 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     AdpcmEncWarp &W = S.w[wid];
     const uint32_t row0_s = smem_addr(&W.in[0][lane][0]);               // stage b: + b * sizeof(W.in[0])
+    const uint32_t step_s = smem_addr(&S.step[0]);
     const int nwarps = (nstreams + 31) >> 5;
 
     for (int wg = blockIdx.x * kBulkWarps + wid; wg < nwarps; wg += gridDim.x * kBulkWarps) {
@@ -509,8 +545,8 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
                             lo = hi;
                             // sample pairs past the end of the chunk are not encoded (keeps the carried state exact)
                             if (t0 + 2 * (w * 4 + q) < ns) {
-                                const int n0 = ima_compress((int)(int16_t)(v & 0xffff), prev, idx, S.step);
-                                const int n1 = ima_compress((int)(int16_t)(v >> 16), prev, idx, S.step);
+                                const int n0 = ima_compress_s((int)(int16_t)(v & 0xffff), prev, idx, step_s);
+                                const int n1 = ima_compress_s((int)(int16_t)(v >> 16), prev, idx, step_s);
                                 packed |= (uint32_t)((n0 << 4) | n1) << (8 * q);
                             }
                         }

@@ -360,6 +360,10 @@ class Job:
         self.rank = int(os.environ.get("RANK", "0"))
         local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.dist = None
+        try:
+            self.affinity0 = os.sched_getaffinity(0)
+        except Exception:
+            self.affinity0 = None
         if self.world > 1:
             import torch.distributed as dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -443,6 +447,11 @@ class Job:
         if self.dist is not None:
             self.dist.destroy_process_group()
             self.dist = None
+        if self.affinity0 is not None:       # the CPU reference that follows (rank 0) gets all the host cores back
+            try:
+                os.sched_setaffinity(0, self.affinity0)
+            except Exception:
+                pass
 
 
 def shard_range(n, rank, world):
