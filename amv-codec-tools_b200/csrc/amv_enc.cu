@@ -891,20 +891,21 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                 if (fits) {
                     // the luma strings have been packed: their columns now stage the output bytes
                     if ((uint32_t)lane < oc) W.s.obuf[lane] = (uint8_t)cbyte;
+                    // branch-free per word: a word with an FF byte turns up in some lane in most iterations, so a byte-serial
+                    // side path would run, one lane wide, almost every time (ncu: 74 % of the iterations in the first version)
                     uint32_t o = obuf_s + oc + w0 * 4 + ff_before;
                     for (uint32_t w = w0; w < w1; w++) {
                         const uint32_t v = W.u.seg[w];
-                        const uint32_t nvalid = min(4u, B - w * 4);
-                        if (nvalid == 4 && ff_bytes(v) == 0) {
-                            sts8(o, v >> 24); sts8(o + 1, v >> 16); sts8(o + 2, v >> 8); sts8(o + 3, v);
-                            o += 4;
-                        } else {
-                            for (uint32_t k = 0; k < nvalid; k++) {
-                                const uint32_t by = (v >> (24 - 8 * k)) & 0xffu;
-                                sts8(o++, by);
-                                if (by == 0xffu) sts8(o++, 0u);
-                            }
-                        }
+                        const uint32_t nvalid = B - w * 4;                   // >= 4 except in the segment's last word
+                        const uint32_t f = ff_bytes(v);                      // 0x80 in every byte that is FF
+                        const uint32_t f0 = f >> 31, f1 = (f >> 23) & 1u, f2 = (f >> 15) & 1u, f3 = (f >> 7) & 1u;
+                        const uint32_t p1 = 1u + f0, p2 = p1 + 1u + f1, p3 = p2 + 1u + f2;
+                        sts8(o, v >> 24);
+                        if (f0) sts8(o + 1u, 0u);
+                        if (nvalid > 1u) { sts8(o + p1, v >> 16); if (f1) sts8(o + p1 + 1u, 0u); }
+                        if (nvalid > 2u) { sts8(o + p2, v >> 8); if (f2) sts8(o + p2 + 1u, 0u); }
+                        if (nvalid > 3u) { sts8(o + p3, v); if (f3) sts8(o + p3 + 1u, 0u); }
+                        o += p3 + 1u + f3;                                   // only the last word can be short, and nothing follows it
                     }
                     uint32_t total = oc + Bo;
                     if (last_half && lane == 0) { W.s.obuf[total] = 0xff; W.s.obuf[total + 1] = 0xd9; }     // EOI (mjpegenc.c:354)
