@@ -240,7 +240,8 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
     if (log2p) {
         CK(cudaMemsetAsync(rounds, 0, sizeof(uint32_t), ctx->stream));
         { ScopedTimer tm(ctx, KK_SYNC);
-          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, tabs, qtab, g.nl, g.nc, ctx->stream); }
+          launch_vlc_sync(scratch, slot_off, scan_len, n, log2p, starts, rounds, amvlib, tabs, qtab, g.nl, g.nc,
+                          !mode.tables && ctx->opt_token_pass != 0, ctx->stream); }
         lc++;
     }
     // fixed AMV / SP5X tables: the 16-bit token pass; amvlib flavour and plain JPEG (own tables, per-frame quantisers): 32-bit tokens

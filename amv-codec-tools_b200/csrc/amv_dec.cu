@@ -476,6 +476,242 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_vlc_sync_lean: the same self-synchronising rounds with the walk of k_vlc_tokens_lean (further down: AC-only symbol
+// body; a lane that ends a block parks until the next service point, where the parked lanes count their block, rotate
+// the DC sums, switch tables and read the next block's DC together).  For the fixed AMV / SP5X tables; the flat kernel
+// above stays for custom tables and the amvlib flavour.
+// ------------------------------------------------------------------------------------------------
+struct SyncLeanSmem {
+    uint32_t ring[kTokWarps][kRingWords * 32];     // 2 KB per warp, 2 KB aligned
+    uint4    bstate[8];                            // per block-in-MCU: DC table, AC table, component change on entering it, next index
+    uint32_t lut[kFlatMaxEntries];                 // AC entries with the token flag cleared: the top 9 bits are the advance
+};
+constexpr size_t kSyncLeanSmemBytes = sizeof(SyncLeanSmem) + 2048;
+struct SyncCheckpoint {     // while a walk runs: what it had at the boundary; afterwards: what it added from there to its exit
+    uint32_t bitpos, phase, nblocks;
+    int dc[3];
+    uint32_t exit_bitpos, exit_phase;   // where that walk left the subsequence
+    bool valid, fresh;
+};
+
+__global__ void __launch_bounds__(kTokThreads)
+k_vlc_sync_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
+                const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
+                uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */,
+                const DecTableSet *__restrict__ tabs, int nl, int nc /* blocks per MCU: luma, one chroma component */) {
+    AMV_EXTERN_SHARED(uint8_t, synclean_smem_raw, 16);
+    const uint32_t raw_s = smem_addr(synclean_smem_raw);
+    SyncLeanSmem &S = *reinterpret_cast<SyncLeanSmem *>(synclean_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
+    const int nlut = tabs->flat.count, ac0 = tabs->flat.base[2];
+    for (int i = threadIdx.x; i < nlut; i += blockDim.x) {
+        const uint32_t e = tabs->flat.e[i];
+        S.lut[i] = (i >= ac0 && (e & 31u)) ? e & 0x7fffffffu : e;
+    }
+    const uint32_t lut_s = smem_addr(S.lut);
+    const uint32_t nbm = (uint32_t)(nl + 2 * nc);               // blocks per MCU (<= 8): nl luma, nc Cb, nc Cr
+    if (threadIdx.x < nbm) {
+        const uint32_t bq = threadIdx.x, tq = bq >= (uint32_t)nl ? 1 : 0;
+        const bool enters = bq == 0 || bq == (uint32_t)nl || bq == (uint32_t)(nl + nc);   // first block of a component
+        uint4 bs;
+        bs.x = lut_s + (uint32_t)tabs->flat.base[tq] * 4u;
+        bs.y = lut_s + (uint32_t)tabs->flat.base[2 + tq] * 4u;
+        bs.z = enters ? 1u : 0u;
+        bs.w = bq + 1u == nbm ? 0u : bq + 1u;
+        S.bstate[bq] = bs;
+    }
+    __syncthreads();
+    const int P = 1 << log2p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (int)(gt >> log2p);
+    const int p = (int)(gt & (P - 1));
+    const bool active = f < n;
+    const uint32_t ring_s = smem_addr(&S.ring[wid][lane]);      // word w of this lane: | (w & 15) << 7
+    const uint32_t bstate_s = smem_addr(&S.bstate[0]);
+
+    const uint32_t *words = nullptr;
+    uint32_t cap_words = 0, end_bit = 0, total_bits = 0, L = 0;
+    if (active) {
+        const uint32_t U = scan_len[f];
+        words = reinterpret_cast<const uint32_t *>(scratch + slot_off[f]);
+        cap_words = (((U + 15u) & ~15u) + kSlotPad) >> 2;       // inside the zero-padded slot (U <= packet size)
+        total_bits = U * 8u;
+        L = (((total_bits + P - 1) >> log2p) + 31u) & ~31u;
+        const uint64_t e = (uint64_t)(p + 1) * L;
+        end_bit = e < total_bits ? (uint32_t)e : total_bits;
+    }
+    uint32_t start_bit = active ? (uint32_t)min((uint64_t)p * L, (uint64_t)total_bits) : 0u, start_phase = 0;
+    LaneExit ex = { 0, 0, 0, { 0, 0, 0 } };
+    auto load_group = [&](uint32_t w) -> uint4 {        // words [w, w+4) of the scan, zeros past the slot
+        if (w + 4 <= cap_words) return __ldg(reinterpret_cast<const uint4 *>(words + w));
+        return make_uint4(0, 0, 0, 0);
+    };
+    auto ring_put = [&](uint32_t w, const uint4 &q) {   // w is a multiple of 4
+        const uint32_t a = ring_s | ((w << 7) & 0x780u);
+        sts32(a, bswap32(q.x)); sts32(a + 128, bswap32(q.y)); sts32(a + 256, bswap32(q.z)); sts32(a + 384, bswap32(q.w));
+    };
+
+    // Checkpoints: the first block boundary a walk reaches at or behind a quarter and five eighths of the subsequence is
+    // remembered as (bit, block-in-MCU) with the blocks and DC sums the walk collects from there to its exit.  A later
+    // walk that arrives at the same boundary would repeat the earlier one bit for bit from there on, so it stops and
+    // adds the remembered remainder.  The second walk of a lane differs from its first only up to the point where the
+    // guessed state had re-synchronised (a few blocks in, profiles/README.md), so it ends at the first checkpoint.
+    SyncCheckpoint cp0 = { 0, 0, 0, { 0, 0, 0 }, 0, 0, false, false }, cp1 = cp0;
+    const uint32_t cp0_pos = start_bit + (L >> 2), cp1_pos = start_bit + (L >> 1) + (L >> 3);
+    auto by_component = [&](uint32_t blk, int a, int bb, int c3, int *out) {       // the rotated sums, per component
+        const int c = blk < (uint32_t)nl ? 0 : (blk < (uint32_t)(nl + nc) ? 1 : 2);
+        out[0] = c == 0 ? a : (c == 1 ? c3 : bb);
+        out[1] = c == 0 ? bb : (c == 1 ? a : c3);
+        out[2] = c == 0 ? c3 : (c == 1 ? bb : a);
+    };
+
+    uint32_t rounds = 0;
+    bool need = active;                     // this lane walks in the coming round
+    for (int r = 0; r <= P; r++) {
+        if (r > 0) {
+            // entry state = left neighbour's exit state (lane 0 of a frame starts the scan)
+            uint32_t nbit = __shfl_up_sync(0xffffffffu, ex.bitpos, 1);
+            uint32_t nph = __shfl_up_sync(0xffffffffu, ex.phase, 1);
+            if (p == 0) { nbit = 0; nph = 0; }
+            need = active && (nbit != start_bit || nph != start_phase);
+            if (!__ballot_sync(0xffffffffu, need)) break;
+            if (need) { start_bit = nbit; start_phase = nph; }
+        }
+        rounds++;
+        // ---- walk the subsequence from (start_bit, start_phase): blocks that START before end_bit
+        uint32_t bp = start_bit;
+        uint32_t wr = (start_bit >> 5) & ~3u;           // next word the ring receives; ring = words [wr-16, wr)
+        uint4 pend = make_uint4(0, 0, 0, 0);
+        bool live = need && start_bit < end_bit;        // the lane has a block to walk
+        bool joined = false;                            // the walk met a checkpoint of an earlier one: ex is complete
+        int cpn = 0;                                    // the checkpoint this walk passes next
+        bool on = false, ended = false;                 // inside a block (its DC is read) / parked at its end
+        uint32_t kb = 0;                                // zigzag position of the last symbol + 1
+        uint32_t b = start_phase, nb = 0;
+        int dA = 0, dB = 0, dC = 0;                     // sums of DC differences; dA: the current block's component
+        uint32_t dct_s, act_s, bnext;
+        {
+            const uint4 bs = S.bstate[b];
+            dct_s = bs.x; act_s = bs.y; bnext = bs.w;
+        }
+        auto window = [&]() -> uint32_t {               // the 32 bits at bp
+            const uint32_t x = bp << 2;
+            const uint32_t wa = lds32(ring_s | (x & 0x780u)), wc = lds32(ring_s | ((x + 128u) & 0x780u));
+            return __funnelshift_l(wc, wa, bp);
+        };
+        if (live) {
+            ring_put(wr, load_group(wr));
+            ring_put(wr + 4, load_group(wr + 4));
+            wr += 8;
+            pend = load_group(wr);
+        }
+        while (__any_sync(0xffffffffu, live)) {
+            // ---- service point: block ends of the parked lanes, ring top-up, the DC of every lane that starts a block
+            if (ended) {
+                nb++;
+                b = bnext;
+                const uint4 bs = lds128(bstate_s + b * 16u);
+                if (bs.z) { const int t = dA; dA = dB; dB = dC; dC = t; }       // the coming block opens another component
+                dct_s = bs.x; act_s = bs.y; bnext = bs.w;
+                ended = false;
+                live = bp < end_bit;                    // a block that starts at or behind the boundary is the neighbour's
+                if (live && cpn < 2 && bp >= (cpn == 0 ? cp0_pos : cp1_pos)) {
+                    SyncCheckpoint &cp = cpn == 0 ? cp0 : cp1;
+                    int sums[3];
+                    by_component(b, dA, dB, dC, sums);
+                    if (cp.valid && cp.bitpos == bp && cp.phase == b) {
+                        // the earlier walk went on from this very state: its exit is this walk's exit
+                        ex.bitpos = cp.exit_bitpos; ex.phase = cp.exit_phase;
+                        ex.nblocks = nb + cp.nblocks;
+                        ex.dc[0] = sums[0] + cp.dc[0]; ex.dc[1] = sums[1] + cp.dc[1]; ex.dc[2] = sums[2] + cp.dc[2];
+                        joined = true;
+                        live = false;
+                    } else {
+                        cp.bitpos = bp; cp.phase = b; cp.nblocks = nb;
+                        cp.dc[0] = sums[0]; cp.dc[1] = sums[1]; cp.dc[2] = sums[2];
+                        cp.valid = false; cp.fresh = true;
+                    }
+                    cpn++;
+                }
+            }
+            if (live) {
+                const uint32_t rd = bp >> 5;
+                if ((int)(wr + 4 - rd) <= kRingWords) { ring_put(wr, pend); wr += 4; pend = load_group(wr); }
+                if (!on) {      // the block's DC (mjpeg_decode_dc, mjpegdec.c:358-373): only its difference counts here
+                    const uint32_t hi = window();
+                    uint32_t e = lds32(dct_s + ((hi >> (32 - kFlatDcBits)) << 2));
+                    if ((e & 31u) == 0) {
+                        if (!(e & kFlatBad)) e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << kFlatDcBits) >> (32u - (e >> 24)))) << 2));
+                        if ((e & 31u) == 0) e = 1u | (1u << 8);                 // no such code: reads as difference 0
+                    }
+                    const uint32_t top = __funnelshift_l(0u, hi, e);
+                    const int sg = (int)(~top) >> 31;
+                    dA += (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
+                    bp += (e >> 8) & 0xffu;
+                    kb = 1;
+                    on = true;
+                }
+            }
+            // ---- kTokPeriod AC symbols (decode_block, mjpegdec.c:391-428), predicated; parked lanes keep their state
+#pragma unroll
+            for (int u = 0; u < kTokPeriod; u++) {
+                const uint32_t hi = window();
+                uint32_t e = lds32(act_s + ((hi >> (32 - kFlatAcBits)) << 2));
+                if ((e & 31u) == 0) {
+                    if (!(e & kFlatBad)) e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << kFlatAcBits) >> (32u - (e >> 24)))) << 2)) & 0x7fffffffu;
+                    if ((e & 31u) == 0) e = 1u | (1u << 8) | (kFlatAdvEob << 23);        // no such code: ends the block
+                }
+                if (on) { bp += (e >> 8) & 0xffu; kb += e >> 23; }
+                // a coefficient at position 63 or behind it, or EOB (advance 128), ends the block; ZRL alone does not
+                const bool nz = ((e >> 16) & 31u) != 0;
+                const bool fin = (kb & 0xc0u) != 0 && (nz || (kb & 0x80u) != 0);
+                if (on && fin) ended = true;
+                on = on && !fin;
+            }
+        }
+        if (need) {
+            if (!joined) {      // the sums sit rotated to the component of the block that comes next
+                ex.bitpos = bp; ex.phase = b; ex.nblocks = nb;
+                by_component(b, dA, dB, dC, ex.dc);
+            }
+            // what this walk noted at its checkpoints becomes the remainder from there to the exit
+            if (cp0.fresh) {
+                cp0.nblocks = ex.nblocks - cp0.nblocks;
+                cp0.dc[0] = ex.dc[0] - cp0.dc[0]; cp0.dc[1] = ex.dc[1] - cp0.dc[1]; cp0.dc[2] = ex.dc[2] - cp0.dc[2];
+                cp0.exit_bitpos = ex.bitpos; cp0.exit_phase = ex.phase;
+                cp0.fresh = false; cp0.valid = true;
+            }
+            if (cp1.fresh) {
+                cp1.nblocks = ex.nblocks - cp1.nblocks;
+                cp1.dc[0] = ex.dc[0] - cp1.dc[0]; cp1.dc[1] = ex.dc[1] - cp1.dc[1]; cp1.dc[2] = ex.dc[2] - cp1.dc[2];
+                cp1.exit_bitpos = ex.bitpos; cp1.exit_phase = ex.phase;
+                cp1.fresh = false; cp1.valid = true;
+            }
+        }
+    }
+    // segmented (width P) exclusive scans: first block index and DC difference sums
+    uint32_t nb_inc = ex.nblocks;
+    int d0 = ex.dc[0], d1 = ex.dc[1], d2 = ex.dc[2];
+    for (int d = 1; d < P; d <<= 1) {
+        const uint32_t tn = __shfl_up_sync(0xffffffffu, nb_inc, d);
+        const int t0 = __shfl_up_sync(0xffffffffu, d0, d), t1 = __shfl_up_sync(0xffffffffu, d1, d),
+                  t2 = __shfl_up_sync(0xffffffffu, d2, d);
+        if (p >= d) { nb_inc += tn; d0 += t0; d1 += t1; d2 += t2; }
+    }
+    if (active) {
+        LaneStart s;
+        s.bitpos = start_bit;
+        s.first_block = nb_inc - ex.nblocks;
+        s.nblocks = ex.nblocks;
+        s.pred[0] = 1024 + tabs->q0[0] * (d0 - ex.dc[0]);          // last_dc starts at 1024 (mjpegdec.c:805-806)
+        s.pred[1] = 1024 + tabs->q0[1] * (d1 - ex.dc[1]);
+        s.pred[2] = 1024 + tabs->q0[1] * (d2 - ex.dc[2]);
+        starts[gt] = s;
+    }
+    if (rounds_out && lane == 0) atomicMax(rounds_out, rounds);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_vlc_tokens: Huffman -> fixed-width tokens.  Every lane re-walks its (now exactly delimited)
 // subsequence and writes, per block, a DC token (absolute dequantised DC) followed by one 32-bit
 // token per non-zero AC coefficient -- already de-zigzagged and dequantised, so the consumer only
@@ -1269,6 +1505,7 @@ bool build_dec_table_set(void *host_buf, const uint8_t counts[4][16], const uint
 // opt-in to more than 48 KB of dynamic shared memory: per device, called from amv_create
 cudaError_t decode_setup_device() {
     cudaError_t e = cudaFuncSetAttribute(k_vlc_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_sync_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncLeanSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
@@ -1331,9 +1568,13 @@ void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t
 
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
-                     int nl, int nc, cudaStream_t s) {
+                     int nl, int nc, bool lean, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
+    if (lean && !amvlib && !qtab) {         // fixed AMV / SP5X tables
+        AMV_LAUNCH(k_vlc_sync_lean, grid, kTokThreads, kSyncLeanSmemBytes, s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out, tabs, nl, nc);
+        return;
+    }
     AMV_LAUNCH(k_vlc_sync, grid, kTokThreads, kSyncSmemBytes, s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
                                             amvlib ? kFlavorAmvlib : (qtab ? kFlavorJpeg : kFlavorFfmpeg), tabs, qtab, nl, nc);
 }

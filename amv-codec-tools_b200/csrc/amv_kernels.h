@@ -40,7 +40,8 @@ void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t
 // qtab != nullptr: per-frame quantisers (plain JPEG) instead of the table set's
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
-                     int nl, int nc /* blocks per MCU: luma, one chroma component */, cudaStream_t s);
+                     int nl, int nc /* blocks per MCU: luma, one chroma component */,
+                     bool lean /* fixed tables: the lean walk (k_vlc_sync_lean) */, cudaStream_t s);
 void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                        int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
                        int32_t *status, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab, int nl, int nc,

@@ -66,7 +66,8 @@ def test_encode_qscales_and_packed_vs_slots(emu, oracle):
 @pytest.mark.parametrize("log2p", [0, 2, 5])
 @pytest.mark.parametrize("token_pass", [2, 1, 0])
 def test_decode_kernels_identical(emu, oracle, token_pass, log2p):
-    cases = [(160, 120, "sinus", 3), (72, 24, "noise", 4), (48, 40, "flat", 5)]
+    cases = [(160, 120, "sinus", 3), (72, 24, "noise", 4), (48, 40, "flat", 5), (16, 16, "noise", 3), (32, 16, "flat", 2),
+             (64, 48, "edges", 7), (208, 176, "edges", 2)]      # tiny scans on many lanes: empty subsequences, blocks longer than one
     emu.set_option("decode_token_pass", token_pass)
     emu.set_option("decode_log2_lanes", log2p)
     try:
