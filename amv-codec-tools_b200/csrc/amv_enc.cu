@@ -1,21 +1,31 @@
-// amv_enc.cu -- AMV video encode kernel (sm_100a).
+// amv_enc.cu -- AMV video encode kernels (sm_100a).
 //
 // One WARP encodes one frame at a time (persistent, warp-stride over the batch) so that the two
 // serial quantities of a frame -- the running bit position of the entropy-coded segment and the
 // count of stuffed FF bytes -- never leave the warp: no look-back, no scratch traffic, no CTA
-// barriers, the packet is written once.  A frame is cut into segments of 5 macroblocks = 30 blocks
-// = 30 lanes (20 luma, 5 Cb, 5 Cr):
+// barriers, the packet is written once.  Three kernels share that plan:
 //
-//   A  thread-per-block: 128-bit/64-bit coalesced row loads of the bottom-up picture
-//      (amv_encode_picture mjpegenc.c:454-472 + edge replication mpegvideo.c:1416-1470),
-//      fdct_islow and the truncating quantiser in registers (jfdctint.c:261, mpegvideo_enc.c:3647)
-//   B  pass 1: Huffman code LENGTHS per block (encode_block mjpegenc.c:379-435)
-//   C  prefix scan of the 96 lengths in bitstream order (warp shuffles)
-//   D  pass 2: warp-cooperative bit packer -- every thread ORs its codes into the segment's
-//      shared-memory bit buffer at its scanned bit offset
-//   E  FF00 stuffing (escape_FF mjpegenc.c:282-336) as a second scan over FF counts, bytes
-//      stored straight to the packet slot; SOI/EOI framing and 1-bit padding
-//      (ff_mjpeg_encode_stuffing :338-343, trailer :345-355) at frame start / end.
+//   k_encode16v2  the one that runs (option encode_rounds = 2).  A frame is cut into segments of 16
+//                 macroblocks coded in three homogeneous rounds (32 chroma blocks, then twice 32 luma
+//                 blocks), every lane one block per round:
+//     A  coalesced 64-bit row loads of the bottom-up picture (amv_encode_picture mjpegenc.c:454-472
+//        + edge replication mpegvideo.c:1416-1470), fdct_islow in registers (jfdctint.c:261), the
+//        zigzag mask of the coefficients that survive the quantiser (mpegvideo_enc.c:3647)
+//     B  ONE Huffman pass per block into a lane-private bit string (encode_block mjpegenc.c:379-435),
+//        quantising only the survivors, branch-free bit writer
+//     C  prefix scan of the string lengths in bitstream order (warp shuffles)
+//     D  warp-cooperative bit packer: every lane shifts its string to its scanned bit offset and ORs
+//        it into the half segment's shared-memory bit buffer
+//     E  FF00 stuffing (escape_FF mjpegenc.c:282-336) as a second scan over FF counts, bytes staged
+//        in shared memory and stored to the packet slot as aligned 128-bit units; SOI/EOI framing and
+//        1-bit padding (ff_mjpeg_encode_stuffing :338-343, trailer :345-355) at frame start / end
+//   k_encode16    round 1's version of the same rounds (encode_rounds = 1; quantises every coefficient,
+//                 stores packet bytes one per lane)
+//   k_encode      the first encoder: segments of 5 macroblocks = 30 blocks on 30 lanes (20 luma, 5 Cb,
+//                 5 Cr), a code-LENGTH pass before the scan and a second Huffman pass that packs.  It
+//                 has no limit on a block's code length, so it takes the frames the rounds kernels
+//                 hand back (a string that outgrows its staging column) and runs alone at
+//                 encode_rounds = 0.
 #include "amv_common.cuh"
 #include "amv_tables.cuh"
 #include "amv_dct.cuh"
