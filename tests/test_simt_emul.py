@@ -127,3 +127,56 @@ def test_sp5x_and_amvlib_flavours(emu, oracle):
     bgr, bst = emu.decode_frames_bgr24(pk, off, sz, w, h)
     obgr, _ = oracle.amvlib_decode_frames(pk, off, sz, w, h)
     assert (bst == 0).all() and np.array_equal(bgr, obgr)
+
+
+def test_random_geometries_round_trip_every_lane_count(emu, oracle):
+    """Seeded random pictures (size, content, qscale, lanes per frame): the emulated encoder's packets are the oracle's,
+    and the emulated decoder -- lean synchronisation pass with its checkpoints, lean token pass, k_idct16 -- returns the
+    oracle's planes from them at whatever lane count the draw picked."""
+    rng = np.random.default_rng(20261019)
+    kinds = ("sinus", "noise", "flat", "edges")
+    try:
+        for _ in range(14):
+            w, h = 16 * int(rng.integers(1, 14)), 8 * int(rng.integers(1, 16))
+            if (h // 2) % 8 not in (0, 4):          # SURVEY 9.8: the heights the reference's flip addresses correctly
+                h += 8
+            kind, q, n = kinds[int(rng.integers(0, 4))], int(rng.integers(2, 32)), int(rng.integers(1, 5))
+            log2p = int(rng.integers(0, 6))
+            y, u, v = synth_frames(n, w, h, seed=int(rng.integers(1, 1 << 30)), kind=kind)
+            wpk, woff, wsz = oracle.encode_frames(y, u, v, w, h, q)
+            pk, off, sz, st = emu.encode_frames(y, u, v, qscale=q)
+            assert (st == 0).all() and np.array_equal(sz, wsz) and np.array_equal(pk, wpk), (w, h, kind, q)
+            wy, wu, wv, wst = oracle.decode_frames(wpk, woff, wsz, w, h)
+            emu.set_option("decode_log2_lanes", log2p)
+            dy, du, dv, dst = emu.decode_frames(wpk, woff, wsz, w, h)
+            assert (dst == 0).all() and np.array_equal(dy, wy) and np.array_equal(du, wu) and np.array_equal(dv, wv), (w, h, kind, q, log2p)
+    finally:
+        emu.set_option("decode_log2_lanes", -1)
+
+
+@pytest.mark.parametrize("log2p", [0, 3, 5])
+def test_bit_flipped_packets_end_and_leave_sound_neighbours_alone(emu, oracle, log2p):
+    """Packets with random bit flips in the scan (wrong codes, wrong lengths, runs past 63): every lane count must come
+    back -- the walks are bounded by the scan, the checkpoints of the synchronisation pass only ever join what a walk
+    really did -- and the sound frames between them decode to the oracle's planes.  The emulator runs the kernels in
+    host memory, so a walk that left its buffers would fault here."""
+    w, h, n = 208, 176, 6
+    rng = np.random.default_rng(31 + log2p)
+    y, u, v = synth_frames(n, w, h, seed=32, kind="sinus")
+    pk, off, sz = oracle.encode_frames(y, u, v, w, h, 3)
+    wy, wu, wv, _ = oracle.decode_frames(pk, off, sz, w, h)
+    units = [bytearray(pk[int(off[i]): int(off[i]) + int(sz[i])].tobytes()) for i in range(n)]
+    for i in (1, 3, 4):
+        for _ in range(1 + 3 * i):
+            p = int(rng.integers(2, len(units[i]) - 2))
+            units[i][p] ^= 1 << int(rng.integers(0, 8))
+            if units[i][p] == 0xff:                 # keep the framing: a new marker would just cut the scan short
+                units[i][p] = 0xfe
+    bk, boff, bsz = pack([bytes(b) for b in units])
+    emu.set_option("decode_log2_lanes", log2p)
+    try:
+        dy, du, dv, st = emu.decode_frames(bk, boff, bsz, w, h)
+    finally:
+        emu.set_option("decode_log2_lanes", -1)
+    for i in (0, 2, 5):
+        assert st[i] == 0 and np.array_equal(dy[i], wy[i]) and np.array_equal(du[i], wu[i]) and np.array_equal(dv[i], wv[i])
