@@ -180,3 +180,21 @@ def test_bit_flipped_packets_end_and_leave_sound_neighbours_alone(emu, oracle, l
         emu.set_option("decode_log2_lanes", -1)
     for i in (0, 2, 5):
         assert st[i] == 0 and np.array_equal(dy[i], wy[i]) and np.array_equal(du[i], wu[i]) and np.array_equal(dv[i], wv[i])
+
+
+def test_emulated_kernels_under_address_sanitizer():
+    """The same kernels built with -fsanitize=address (build.sh, ASAN=1) and run in a child process with libasan
+    preloaded: every "device", pinned and shared-memory access of the encoder forms, the token passes at 1 / 4 / 32 lanes
+    per frame (sound and bit-flipped packets) and the ADPCM forms stays inside its buffer (compute-sanitizer is not
+    available on the GPU pool; this is the memcheck the kernels get)."""
+    import sys
+    built = subprocess.run([BUILD], capture_output=True, text=True, env=dict(os.environ, ASAN="1"))
+    if built.returncode == 3:
+        pytest.skip("no compiler with libasan.so")
+    assert built.returncode == 0, built.stderr[-2000:]
+    libasan, so = built.stdout.strip().splitlines()[-2:]
+    env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=0:exitcode=23")
+    out = subprocess.run([sys.executable, os.path.join(HERE, "host_emul", "simt", "asan_target.py"), so], capture_output=True,
+                         text=True, env=env, timeout=1500)
+    assert out.returncode == 0 and "asan target ok" in out.stdout and "ERROR: AddressSanitizer" not in out.stderr, \
+        out.stdout[-2000:] + out.stderr[-4000:]
