@@ -20,8 +20,9 @@ def pytest_configure(config):
 EMUL = os.environ.get("AMV_EMUL") == "1"
 if EMUL:
     import subprocess
-    _so = subprocess.check_output([os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul", "simt", "build.sh")],
-                                  text=True).strip().splitlines()[-1]
+    # AMV_EMUL_ASAN_SO: the AddressSanitizer build of the same library (test_simt_emul.py runs a child process that way)
+    _so = os.environ.get("AMV_EMUL_ASAN_SO") or subprocess.check_output(
+        [os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul", "simt", "build.sh")], text=True).strip().splitlines()[-1]
     import amv_codec_tools_b200 as _amv
     _amv.AmvCuda.__init__.__defaults__ = (-1, None, _so)
     _amv.load_library.__defaults__ = (_so,)

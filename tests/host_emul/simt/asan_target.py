@@ -55,4 +55,14 @@ for form in (0, 1, 2):
     assert (st == 0).all() and np.array_equal(out, wout) and np.array_equal(so, wso), ("adpcm encode", form)
     dec, _, dst = ctx.adpcm_decode(out, ooff, osz)
     assert (dst == 0).all() and np.array_equal(dec, o.adpcm_decode(out, ooff, osz)[0]), ("adpcm decode", form)
+# range conversion and the scaler with its range steps (their GPU tests hold torch tensors; here through host buffers)
+y, u, v = synth_frames(2, 102, 56, seed=8, kind="noise")
+for direction in (0, 1):
+    cy, cu, cv = ctx.convert_range(y, u, v, direction)
+    wy, wu, wv = o.convert_range(y, u, v, direction)
+    assert np.array_equal(cy, wy) and np.array_equal(cu, wu) and np.array_equal(cv, wv), ("range", direction)
+for flags in (0, 1, 2, 3):
+    sy, su, sv = ctx.scale_frames(y, u, v, 64, 48, flags=flags)
+    wy, wu, wv = o.sws_scale(y, u, v, 64, 48, flags & 1, flags & 2)
+    assert np.array_equal(sy, wy) and np.array_equal(su, wu) and np.array_equal(sv, wv), ("scale", flags)
 print("asan target ok")

@@ -25,7 +25,8 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not ava
 
 @pytest.fixture(scope="module")
 def emu():
-    so = subprocess.check_output([BUILD], text=True).strip().splitlines()[-1]
+    # AMV_EMUL_ASAN_SO: the sanitizer build, when this file runs as the child of the AddressSanitizer test below
+    so = os.environ.get("AMV_EMUL_ASAN_SO") or subprocess.check_output([BUILD], text=True).strip().splitlines()[-1]
     c = amv.AmvCuda(device=0, lib_path=so)
     yield c
     c.close()
@@ -198,3 +199,17 @@ def test_emulated_kernels_under_address_sanitizer():
                          text=True, env=env, timeout=1500)
     assert out.returncode == 0 and "asan target ok" in out.stdout and "ERROR: AddressSanitizer" not in out.stderr, \
         out.stdout[-2000:] + out.stderr[-4000:]
+    # and this file's other tests (flavours, scaler, resampler, container, trellis, host copy paths) against the same build
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                          "-k", "not address_sanitizer"], capture_output=True, text=True, env=dict(env, AMV_EMUL_ASAN_SO=so),
+                         timeout=2400, cwd=os.path.dirname(HERE))
+    assert out.returncode == 0 and "ERROR: AddressSanitizer" not in out.stderr + out.stdout, out.stdout[-4000:] + out.stderr[-4000:]
+    # and the GPU parity tests of the kernels this file does not reach, pointed at the sanitizer build (conftest.py, AMV_EMUL=1):
+    # plain JPEG, the scaler, the audio resampler, the trellis encoder -- their golden-vector cases (tests that hold torch
+    # tensors are left out: torch's own exceptions do not get along with a preloaded libasan)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                          "-p", "no:cacheprovider", "-k", "mjpeg_decode_golden or scaler_matches_golden or audio_resampler_matches_golden "
+                          "or adpcm_trellis_golden"],
+                         capture_output=True, text=True, env=dict(env, AMV_EMUL="1", AMV_EMUL_ASAN_SO=so), timeout=2400,
+                         cwd=os.path.dirname(HERE))
+    assert out.returncode == 0 and "ERROR: AddressSanitizer" not in out.stderr + out.stdout, out.stdout[-4000:] + out.stderr[-4000:]
