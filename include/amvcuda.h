@@ -111,7 +111,8 @@ AMV_API void        amv_host_free(void *p);
  *   "encode_rounds"                encoder kernels: 2 (default) k_encode16v2, 1 k_encode16 (each + k_encode for the frames it
  *                                  hands back), 0 the one-kernel encoder, 3 = 2 at four instead of five CTAs per SM
  *   "decode_token_pass"            AMV / SP5X token pass: 2 (default) lean pass with 16-bit tokens, 1 lean pass with 32-bit
- *                                  tokens, 0 the flat symbol loop with 32-bit tokens
+ *                                  tokens, 0 the flat symbol loop with 32-bit tokens; 1 and 2 also run the lean, checkpointed
+ *                                  synchronisation pass when frames are split into lanes, 0 the flat one
  *   "scale_form"                   scaler kernel: 1 (default) tiles, 2 tiles with staged source rows, 0 direct
  *   "resample_form"                audio resampler kernel: 2 (default) phase rows, 1 tiles, 0 direct
  * One option DOES select an algorithm, like the reference's AVCodecContext.trellis does:
