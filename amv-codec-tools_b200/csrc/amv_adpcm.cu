@@ -63,15 +63,15 @@ __device__ __forceinline__ int ima_compress(int sample, int &prev, int &idx, con
     return q | (delta < 0 ? 8 : 0);
 }
 
-// the same with the step table addressed through its shared-window address (no generic-pointer arithmetic in the loop)
-__device__ __forceinline__ int ima_compress_s(int sample, int &prev, int &idx, uint32_t step_s) {
-    const int step = (int)lds_u16(step_s + 2u * (uint32_t)idx);
+// the same for the asynchronous kernel, with the quotient by reciprocal: the table holds (step, ceil(2^34 / step)) per index
+// and q = min(7, umulhi(|delta|, reciprocal)).  Exact: the product overshoots 4*|delta|/step by less than |delta| / 2^32
+// <= 2^-16, and a quotient that is not an integer lies at least 1/step >= 2^-15 below the next one (checked for all 89 steps
+// x 65 536 differences in tests/test_host_emul.py).
+__device__ __forceinline__ int ima_compress_s(int sample, int &prev, int &idx, uint32_t tab_s) {
+    const uint2 sm = lds64(tab_s + 8u * (uint32_t)idx);
+    const int step = (int)sm.x;
     const int delta = sample - prev;
-    int t = (delta < 0 ? -delta : delta) * 4;
-    int q = 0;
-    if (t >= 4 * step) { q = 4; t -= 4 * step; }
-    if (t >= 2 * step) { q |= 2; t -= 2 * step; }
-    if (t >= step) q |= 1;
+    const int q = (int)min(__umulhi((uint32_t)(delta < 0 ? -delta : delta), sm.y), 7u);
     const int mv = (step * (2 * q + 1)) >> 3;        // (step * difflookup) / 8, magnitude part
     prev = delta < 0 ? prev - mv : prev + mv;
     prev = min(max(prev, -32768), 32767);
@@ -448,7 +448,7 @@ struct AdpcmEncWarp {
     uint32_t ns[32];
 };
 struct AdpcmEncSmem {
-    uint16_t step[96];
+    uint2 step[96];                                 // (step, ceil(2^34 / step)) per step index
     __align__(16) AdpcmEncWarp w[kBulkWarps];
 };
 
@@ -459,7 +459,10 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
                      uint64_t out_bytes, const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
     AMV_EXTERN_SHARED(uint8_t, adpcm_enc_smem_raw, 16);
     AdpcmEncSmem &S = *reinterpret_cast<AdpcmEncSmem *>(adpcm_enc_smem_raw);
-    for (int i = threadIdx.x; i < 96; i += blockDim.x) S.step[i] = g_ima_step[i];
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) {
+        const uint32_t st = g_ima_step[i];
+        S.step[i] = make_uint2(st, st ? (uint32_t)(((1ull << 34) + st - 1u) / st) : 0u);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     AdpcmEncWarp &W = S.w[wid];
@@ -535,7 +538,9 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
                     const uint32_t wa = ra & ~3u, sh = (ra & 3u) * 8u;
                     uint32_t *orow = W.nib + lane * kNibPitch;
                     uint32_t lo = lds32(wa);
-#pragma unroll
+                    // eight samples per trip, not the whole tile unrolled: 3 300 SASS instructions walked by 20 warps at
+                    // different phases miss the instruction cache (ncu: no_instruction 1.0 per issue)
+#pragma unroll 1
                     for (int w = 0; w < kTileBytes / 4; w++) {
                         uint32_t packed = 0;
 #pragma unroll

@@ -116,6 +116,7 @@ inline uint32_t lds32(uint32_t saddr) { return *smem_ptr<uint32_t>(saddr); }
 inline int lds_s16(uint32_t saddr) { return *smem_ptr<int16_t>(saddr); }
 inline uint32_t lds_u16(uint32_t saddr) { return *smem_ptr<uint16_t>(saddr); }
 inline uint4 lds128(uint32_t saddr) { return *smem_ptr<uint4>(saddr); }
+inline uint2 lds64(uint32_t saddr) { return *smem_ptr<uint2>(saddr); }
 inline void sts32(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) = v; }
 inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (uint16_t)v; }
 inline void sts8(uint32_t saddr, uint32_t v) { *smem_ptr<uint8_t>(saddr) = (uint8_t)v; }
@@ -164,6 +165,11 @@ __device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {

@@ -115,3 +115,19 @@ def test_lane_decode_matches_oracle(emul, oracle, w, h, kind, log2p):
         assert np.array_equal(ey, oy[i]) and np.array_equal(eu, ou[i]) and np.array_equal(ev, ov[i])
         if log2p:
             assert 1 <= rounds.value <= (1 << log2p) + 1
+
+
+def test_adpcm_quotient_by_reciprocal_is_exact():
+    """k_adpcm_encode_async finds min(7, |delta| * 4 / step) (adpcm_ima_compress_sample, adpcm.c:219-227) as
+    min(7, umulhi(|delta|, ceil(2^34 / step))): every step of the table (read from the product's amv_tables.cuh) x every
+    difference two int16 samples can have."""
+    import re
+    src = open(os.path.join(os.path.dirname(HERE), "amv-codec-tools_b200", "csrc", "amv_tables.cuh")).read()
+    body = re.search(r"kImaStep\[89\]\s*=\s*\{([^}]*)\}", src).group(1)
+    steps = [int(t) for t in re.findall(r"\d+", body)]
+    assert len(steps) == 89 and steps[0] == 7 and steps[-1] == 32767
+    x = np.arange(65536, dtype=np.uint64)
+    for s in steps:
+        m = ((1 << 34) + s - 1) // s
+        assert m < (1 << 32)
+        assert np.array_equal(np.minimum(7, (4 * x) // s), np.minimum(7, (x * np.uint64(m)) >> np.uint64(32))), s
