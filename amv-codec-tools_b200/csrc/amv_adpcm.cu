@@ -444,8 +444,7 @@ constexpr int kEncRow = 2 * kTileSamples + 16;       // bytes: the aligned span 
 struct AdpcmEncWarp {
     __align__(16) uint8_t in[2][32][kEncRow];
     uint32_t nib[32 * kNibPitch];
-    uint64_t dst[32];
-    uint32_t ns[32];
+    uint4 row[32];                                  // per chunk of the warp: where its nibble bytes go (pointer lo, hi), how many
 };
 struct AdpcmEncSmem {
     uint2 step[96];                                 // (step, ceil(2^34 / step)) per step index
@@ -510,8 +509,10 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
                     h[4] = (uint8_t)ns; h[5] = (uint8_t)(ns >> 8); h[6] = (uint8_t)(ns >> 16); h[7] = (uint8_t)(ns >> 24);
                 }
             }
-            W.dst[lane] = dst;
-            W.ns[lane] = ns;
+            {
+                const uint64_t p = reinterpret_cast<uint64_t>(outb + dst + 8);
+                W.row[lane] = make_uint4((uint32_t)p, (uint32_t)(p >> 32), ns / 2, 0u);
+            }
             uint32_t maxs = ns;
 #pragma unroll
             for (int d = 16; d; d >>= 1) maxs = max(maxs, __shfl_xor_sync(0xffffffffu, maxs, d));
@@ -559,12 +560,14 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
                     }
                 }
                 __syncwarp();
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t nj = W.ns[j];
-                    if (t0 >= nj) continue;
-                    const uint32_t bytes_left = (nj - t0 + 1) / 2;
-                    if ((uint32_t)lane < bytes_left)
-                        outb[W.dst[j] + 8 + t0 / 2 + lane] = reinterpret_cast<const uint8_t *>(W.nib + j * kNibPitch)[lane];
+                {   // the 32 nibble bytes of every chunk of the warp: lane i stores byte i, one chunk per trip, predicated
+                    const uint32_t boff = t0 / 2 + (uint32_t)lane;
+                    const uint8_t *nb = reinterpret_cast<const uint8_t *>(W.nib) + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const uint4 r = W.row[j];
+                        if (boff < r.z) reinterpret_cast<uint8_t *>(((uint64_t)r.y << 32) | r.x)[boff] = nb[j * kNibPitch * 4];
+                    }
                 }
                 __syncwarp();
             }
