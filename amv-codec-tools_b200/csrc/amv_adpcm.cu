@@ -180,8 +180,7 @@ constexpr int kBulkOutPitch = kBulkTile + 1;         // words: 64 sample pairs +
 struct AdpcmBulkWarp {
     __align__(16) uint8_t in[2][32][kBulkRow];
     uint32_t out[32 * kBulkOutPitch];
-    uint64_t dst[32];
-    uint32_t nb[32];
+    uint4 row[32];              // per chunk of the warp: where its samples go (pointer lo, hi), nibble bytes, 32-bit aligned?
     __align__(8) uint64_t bar[2];
 };
 struct AdpcmBulkSmem {
@@ -227,8 +226,10 @@ k_adpcm_decode_async(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, 
             }
             status[c] = st;
         }
-        W.dst[lane] = dsts;
-        W.nb[lane] = nbytes;
+        {
+            const uint64_t p = reinterpret_cast<uint64_t>(pcm + dsts);
+            W.row[lane] = make_uint4((uint32_t)p, (uint32_t)(p >> 32), nbytes, (p & 3) == 0 ? 1u : 0u);
+        }
         uint32_t maxb = nbytes;
 #pragma unroll
         for (int d = 16; d; d >>= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, d));
@@ -303,20 +304,23 @@ k_adpcm_decode_async(const uint8_t *__restrict__ chunks, uint64_t chunks_bytes, 
                 }
             }
             __syncwarp();
-            // warp-cooperative store: chunk j's sample pairs, two 32-bit words per lane
-            for (int j = 0; j < 32; j++) {
-                const uint32_t nj = W.nb[j];
-                if (t0 >= nj) continue;
-                const uint32_t lenj = min((uint32_t)kBulkTile, nj - t0);
-                int16_t *d = pcm + W.dst[j] + 2ull * t0;
-                const bool al = (reinterpret_cast<uintptr_t>(d) & 3) == 0;
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const uint32_t wi = (uint32_t)lane + 32u * hh;
-                    if (wi < lenj) {
-                        const uint32_t v = W.out[j * kBulkOutPitch + wi];
-                        if (al) *reinterpret_cast<uint32_t *>(d + 2 * wi) = v;
-                        else { d[2 * wi] = (int16_t)(v & 0xffff); d[2 * wi + 1] = (int16_t)(v >> 16); }
+            // warp-cooperative store: chunk j's sample pairs (one per nibble byte), two 32-bit words per lane, predicated
+            {
+                const uint32_t w0 = t0 + (uint32_t)lane;                       // the lane's first pair of the tile, in the chunk
+                const uint32_t *orow = W.out + lane;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) {
+                    const uint4 r = W.row[j];
+                    const uint32_t v0 = orow[j * kBulkOutPitch], v1 = orow[j * kBulkOutPitch + 32];
+                    const uint64_t p = ((uint64_t)r.y << 32) | r.x;
+                    if (r.w) {
+                        uint32_t *d = reinterpret_cast<uint32_t *>(p);
+                        if (w0 < r.z) d[w0] = v0;
+                        if (w0 + 32u < r.z) d[w0 + 32u] = v1;
+                    } else {
+                        int16_t *d = reinterpret_cast<int16_t *>(p);
+                        if (w0 < r.z) { d[2 * w0] = (int16_t)(v0 & 0xffff); d[2 * w0 + 1] = (int16_t)(v0 >> 16); }
+                        if (w0 + 32u < r.z) { d[2 * w0 + 64] = (int16_t)(v1 & 0xffff); d[2 * w0 + 65] = (int16_t)(v1 >> 16); }
                     }
                 }
             }
