@@ -545,22 +545,39 @@ k_adpcm_encode_async(const int16_t *__restrict__ pcm, uint64_t pcm_samples, cons
                     uint32_t lo = lds32(wa);
                     // eight samples per trip, not the whole tile unrolled: 3 300 SASS instructions walked by 20 warps at
                     // different phases miss the instruction cache (ncu: no_instruction 1.0 per issue)
+                    if (t0 + kTileSamples <= ns) {          // a whole tile: no end-of-chunk test per pair
 #pragma unroll 1
-                    for (int w = 0; w < kTileBytes / 4; w++) {
-                        uint32_t packed = 0;
+                        for (int w = 0; w < kTileBytes / 4; w++) {
+                            uint32_t packed = 0;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const uint32_t hi = lds32(wa + 4u * (w * 4 + q) + 4u);
-                            const uint32_t v = __funnelshift_r(lo, hi, sh);
-                            lo = hi;
-                            // sample pairs past the end of the chunk are not encoded (keeps the carried state exact)
-                            if (t0 + 2 * (w * 4 + q) < ns) {
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t hi = lds32(wa + 4u * (w * 4 + q) + 4u);
+                                const uint32_t v = __funnelshift_r(lo, hi, sh);
+                                lo = hi;
                                 const int n0 = ima_compress_s((int)(int16_t)(v & 0xffff), prev, idx, step_s);
                                 const int n1 = ima_compress_s((int)(int16_t)(v >> 16), prev, idx, step_s);
                                 packed |= (uint32_t)((n0 << 4) | n1) << (8 * q);
                             }
+                            orow[w] = packed;
                         }
-                        orow[w] = packed;
+                    } else {
+#pragma unroll 1
+                        for (int w = 0; w < kTileBytes / 4; w++) {
+                            uint32_t packed = 0;
+#pragma unroll 1
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t hi = lds32(wa + 4u * (w * 4 + q) + 4u);
+                                const uint32_t v = __funnelshift_r(lo, hi, sh);
+                                lo = hi;
+                                // sample pairs past the end of the chunk are not encoded (keeps the carried state exact)
+                                if (t0 + 2 * (w * 4 + q) < ns) {
+                                    const int n0 = ima_compress_s((int)(int16_t)(v & 0xffff), prev, idx, step_s);
+                                    const int n1 = ima_compress_s((int)(int16_t)(v >> 16), prev, idx, step_s);
+                                    packed |= (uint32_t)((n0 << 4) | n1) << (8 * q);
+                                }
+                            }
+                            orow[w] = packed;
+                        }
                     }
                 }
                 __syncwarp();
