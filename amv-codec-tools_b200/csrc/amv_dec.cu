@@ -1365,7 +1365,8 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
     if (threadIdx.x < 128) tzs[threadIdx.x >> 6][threadIdx.x & 63] = tabs->tz[threadIdx.x >> 6][threadIdx.x & 63];
     __syncthreads();
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int f = (int)(gt / g.nblk);
+    // the block index fits 32 bits for every batch the workspace can hold at once (warp-uniform choice of the divide)
+    const int f = (gt >> 32) == 0 ? (int)((uint32_t)gt / (uint32_t)g.nblk) : (int)(gt / g.nblk);
     if (f >= n) return;
     if (scan_len[f] == 0) return;
     const int i = (int)(gt - (int64_t)f * g.nblk);
@@ -1436,11 +1437,14 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
     const int ls = comp ? ls_c : ls_y;
     const int vw = comp ? g.cw : g.w, vh = comp ? g.ch : g.h, r0 = comp ? g.c0 : g.y0;
     const int x0 = bx * 8, y0 = by * 8;
+    // AMV pictures are stored bottom-up (mjpegdec.c:672-677), SP5X is not: the block's first row and the step to the next
+    const int row0 = g.flip ? r0 - y0 : y0, rstep = g.flip ? -1 : 1;
+    const int64_t dstep = g.flip ? -(int64_t)ls : (int64_t)ls;
+    uint8_t *d = pl + (int64_t)row0 * ls + x0;
 #pragma unroll
-    for (int yy = 0; yy < 8; yy++) {
-        const int row = g.flip ? r0 - (y0 + yy) : y0 + yy;     // AMV pictures are stored bottom-up (mjpegdec.c:672-677), SP5X is not
+    for (int yy = 0; yy < 8; yy++, d += dstep) {
+        const int row = row0 + rstep * yy;
         if (row < 0 || row >= vh) continue;
-        uint8_t *d = pl + (int64_t)row * ls + x0;
         if (FAST) {
             *reinterpret_cast<uint2 *>(d) = make_uint2(o[2 * yy], o[2 * yy + 1]);
         } else {
