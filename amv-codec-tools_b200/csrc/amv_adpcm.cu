@@ -66,7 +66,7 @@ __device__ __forceinline__ int ima_compress(int sample, int &prev, int &idx, con
 // the same for the asynchronous kernel, with the quotient by reciprocal: the table holds (step, ceil(2^34 / step)) per index
 // and q = min(7, umulhi(|delta|, reciprocal)).  Exact: the product overshoots 4*|delta|/step by less than |delta| / 2^32
 // <= 2^-16, and a quotient that is not an integer lies at least 1/step >= 2^-15 below the next one (checked for all 89 steps
-// x 65 536 differences in tests/test_host_emul.py).
+// x 65 536 differences by the CPU test suite).
 __device__ __forceinline__ int ima_compress_s(int sample, int &prev, int &idx, uint32_t tab_s) {
     const uint2 sm = lds64(tab_s + 8u * (uint32_t)idx);
     const int step = (int)sm.x;
