@@ -60,7 +60,7 @@ struct amv_ctx {
     int opt_host_chunk = 0;             // frames per pipeline stage, 0 = choose
     int opt_resample_form = 2;          // audio resampler: 2 = phase rows (M outputs per coefficient row), 1 = tiles, 0 = direct form
     int opt_scale_form = 1;             // scaler: 2 = staged tiles (source rows staged in shared memory), 1 = tiles, 0 = direct form
-    int opt_encode_rounds = 2;          // encoder: 2 = k_encode16v2, 1 = k_encode16 (each + k_encode for the frames it hands back), 0 = k_encode alone
+    int opt_encode_rounds = 4;          // encoder: 4 = k_encode16v2 with the regrouped transform, 2 = with the factorised one, 1 = k_encode16 (each + k_encode for the frames it hands back), 0 = k_encode alone
     int opt_trellis = 0;                // ADPCM encoder: 0 = adpcm_ima_compress_sample, 1..5 = -trellis N beam search
     // decode (AMV / SP5X, fixed tables): 2 = lean pass with 16-bit tokens + k_idct16, 1 = lean pass with 32-bit tokens + k_idct,
     // 0 = k_vlc_tokens (flat loop, 32-bit tokens) + k_idct.  Measured per 100 000 frames 320x240 (profiles/r5b_*): tokens + idct
@@ -845,7 +845,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_rounds")) {
-        if (value < 0 || value > 3) return AMV_ERR_UNSUPPORTED;
+        if (value < 0 || value > 8) return AMV_ERR_UNSUPPORTED;
         ctx->opt_encode_rounds = (int)value;
         return AMV_OK;
     }

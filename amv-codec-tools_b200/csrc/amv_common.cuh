@@ -104,6 +104,17 @@ AMV_HD int msb_index(uint32_t v) {
 #endif
 }
 
+// count of leading zeros (v != 0): one FLO.SH
+AMV_HD int clz_nz(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+#else
+    return __builtin_clz(v);
+#endif
+}
+
 #if defined(AMV_EMUL)
 // emulator: "shared-window addresses" are offsets from a fixed origin below the emulator's static storage
 inline uint32_t smem_addr(const void *p) {

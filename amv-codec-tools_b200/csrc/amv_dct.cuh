@@ -153,6 +153,155 @@ AMV_HD void fdct_block(int (&b)[64]) {
         fdct_1d<false>(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
 }
 
+// ------------------------------------------------- fdct_islow, regrouped for the two integer pipes
+// Up to its descale an 8-point pass is an exact integer linear map, so any regrouping of its sums gives the same
+// bits (mod 2^32, and every true sum fits).  LL&M's factorisation minimises multiplies, which is the wrong economy on
+// an SM whose adds / shifts / byte extractions (ALU pipe) and multiply-adds / dot products (FMA pipe) each issue every
+// second cycle per scheduler: the factorised pass is 12 multiply-adds against 32 adds and shifts, plus 8 byte
+// extractions per pixel row.  The forms below move work to the multiply-add side:
+//  * row pass on the PACKED pixel bytes as loaded: output k = sum_i C[k][i] * d[i] is four two-way dot products
+//    (IDP.2A: two signed 16-bit constants x two unsigned bytes, accumulating; the rounding constant is the initial
+//    accumulator), outputs 0 and 4 two four-way dot products with +-16 (IDP.4A).  No byte is ever extracted.
+//  * column pass with the odd half written out (four multiply-adds per output on the differences v[i] - v[7-i]).
+// fdct_lin(k, i): coefficient of input i in output k of the factorised pass before rounding and shift (outputs 0 / 4:
+// before their << 4 or >> 4), derived at compile time from the factorised form itself.
+constexpr int fdct_lin(int k, int i) {
+    int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    v[i] = 1;
+    const int p0 = v[0] + v[7], m0 = v[0] - v[7], p1 = v[1] + v[6], m1 = v[1] - v[6];
+    const int p2 = v[2] + v[5], m2 = v[2] - v[5], p3 = v[3] + v[4], m3 = v[3] - v[4];
+    const int q0 = p0 + p3, q3 = p0 - p3, q1 = p1 + p2, q2 = p1 - p2;
+    const int r = (q2 + q3) * FdctC::C0_541;
+    const int sc = m3 + m1, sd = m2 + m0;
+    const int z = (sc + sd) * FdctC::C1_175;
+    const int a = (m3 + m0) * -FdctC::C0_899, b = (m2 + m1) * -FdctC::C2_562;
+    const int c = sc * -FdctC::C1_961 + z, d = sd * -FdctC::C0_390 + z;
+    switch (k) {
+    case 0: return q0 + q1;
+    case 4: return q0 - q1;
+    case 2: return r + q3 * FdctC::C0_765;
+    case 6: return r - q2 * FdctC::C1_847;
+    case 7: return m3 * FdctC::C0_298 + a + c;
+    case 5: return m2 * FdctC::C2_053 + b + d;
+    case 3: return m1 * FdctC::C3_072 + b + c;
+    default: return m0 * FdctC::C1_501 + a + d;
+    }
+}
+constexpr uint32_t pack_s16x2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+constexpr uint32_t pack_s8x4(int b0, int b1, int b2, int b3) {
+    return ((uint32_t)b0 & 0xffu) | (((uint32_t)b1 & 0xffu) << 8) | (((uint32_t)b2 & 0xffu) << 16) | ((uint32_t)b3 << 24);
+}
+
+// acc + c.lo16 * byte0(d) + c.hi16 * byte1(d)   (HI: bytes 2 and 3); constants signed, pixel bytes unsigned
+template <bool HI>
+AMV_HD int dot2_s16_u8(uint32_t c, uint32_t d, int acc) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    if (HI) asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(d), "r"(acc));
+    else    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(d), "r"(acc));
+    return r;
+#else
+    const uint32_t dd = HI ? d >> 16 : d;
+    return (int)((uint32_t)acc + (uint32_t)((int)(int16_t)(c & 0xffffu) * (int)(dd & 0xffu)) +
+                 (uint32_t)((int)(int16_t)(c >> 16) * (int)((dd >> 8) & 0xffu)));
+#endif
+}
+// acc + sum of four signed constant bytes x unsigned pixel bytes
+AMV_HD int dot4_s8_u8(uint32_t c, uint32_t d, int acc) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(d), "r"(acc));
+    return r;
+#else
+    uint32_t s = (uint32_t)acc;
+    for (int j = 0; j < 4; j++) s += (uint32_t)((int)(int8_t)(c >> (8 * j)) * (int)((d >> (8 * j)) & 0xffu));
+    return (int)s;
+#endif
+}
+
+// row pass, output K, from the row's eight pixels as two little-endian words
+template <int K>
+AMV_HD int fdct_row_dot(uint32_t lo, uint32_t hi) {
+    if (K == 0 || K == 4) {
+        constexpr uint32_t c0 = pack_s8x4(16 * fdct_lin(K, 0), 16 * fdct_lin(K, 1), 16 * fdct_lin(K, 2), 16 * fdct_lin(K, 3));
+        constexpr uint32_t c1 = pack_s8x4(16 * fdct_lin(K, 4), 16 * fdct_lin(K, 5), 16 * fdct_lin(K, 6), 16 * fdct_lin(K, 7));
+        return dot4_s8_u8(c1, hi, dot4_s8_u8(c0, lo, 0));
+    } else {
+        constexpr uint32_t c01 = pack_s16x2(fdct_lin(K, 0), fdct_lin(K, 1)), c23 = pack_s16x2(fdct_lin(K, 2), fdct_lin(K, 3));
+        constexpr uint32_t c45 = pack_s16x2(fdct_lin(K, 4), fdct_lin(K, 5)), c67 = pack_s16x2(fdct_lin(K, 6), fdct_lin(K, 7));
+        int acc = 1 << 8;
+        acc = dot2_s16_u8<false>(c01, lo, acc);
+        acc = dot2_s16_u8<true>(c23, lo, acc);
+        acc = dot2_s16_u8<false>(c45, hi, acc);
+        acc = dot2_s16_u8<true>(c67, hi, acc);
+        return acc >> 9;
+    }
+}
+
+// column pass with the odd outputs written out; EVEN_DIRECT also writes outputs 2 and 6 as two multiply-adds each
+template <int K>
+AMV_HD int fdct_col_odd(int m0, int m1, int m2, int m3) {
+    constexpr int c0 = fdct_lin(K, 0), c1 = fdct_lin(K, 1), c2 = fdct_lin(K, 2), c3 = fdct_lin(K, 3);
+    return (m0 * c0 + m1 * c1 + m2 * c2 + m3 * c3 + (1 << 16)) >> 17;
+}
+template <bool EVEN_DIRECT>
+AMV_HD void fdct_col_direct(int &v0, int &v1, int &v2, int &v3, int &v4, int &v5, int &v6, int &v7) {
+    const int p0 = v0 + v7, m0 = v0 - v7, p1 = v1 + v6, m1 = v1 - v6;
+    const int p2 = v2 + v5, m2 = v2 - v5, p3 = v3 + v4, m3 = v3 - v4;
+    const int q0 = p0 + p3, q3 = p0 - p3, q1 = p1 + p2, q2 = p1 - p2;
+    v0 = (q0 + q1 + 8) >> 4;
+    v4 = (q0 - q1 + 8) >> 4;
+    if (EVEN_DIRECT) {
+        v2 = (q3 * (FdctC::C0_541 + FdctC::C0_765) + q2 * FdctC::C0_541 + (1 << 16)) >> 17;
+        v6 = (q3 * FdctC::C0_541 + q2 * (FdctC::C0_541 - FdctC::C1_847) + (1 << 16)) >> 17;
+    } else {
+        const int r = (q2 + q3) * FdctC::C0_541 + (1 << 16);
+        v2 = (r + q3 * FdctC::C0_765) >> 17;
+        v6 = (r - q2 * FdctC::C1_847) >> 17;
+    }
+    v1 = fdct_col_odd<1>(m0, m1, m2, m3);
+    v3 = fdct_col_odd<3>(m0, m1, m2, m3);
+    v5 = fdct_col_odd<5>(m0, m1, m2, m3);
+    v7 = fdct_col_odd<7>(m0, m1, m2, m3);
+}
+
+// px: the block's pixel rows as loaded, words 2r and 2r + 1 = row r (column 0 in the lowest byte); b: coefficients, raster order.
+// FORM bit 0: row pass by dot products on the packed bytes (else bytes extracted, factorised pass);
+// FORM bit 1: column pass with the odd half written out; bit 2: outputs 2 / 6 written out as well.
+template <int FORM>
+AMV_HD void fdct_block_px(const uint32_t (&px)[16], int (&b)[64]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t lo = px[2 * r], hi = px[2 * r + 1];
+        if (FORM & 1) {
+            b[8 * r]     = fdct_row_dot<0>(lo, hi);
+            b[8 * r + 1] = fdct_row_dot<1>(lo, hi);
+            b[8 * r + 2] = fdct_row_dot<2>(lo, hi);
+            b[8 * r + 3] = fdct_row_dot<3>(lo, hi);
+            b[8 * r + 4] = fdct_row_dot<4>(lo, hi);
+            b[8 * r + 5] = fdct_row_dot<5>(lo, hi);
+            b[8 * r + 6] = fdct_row_dot<6>(lo, hi);
+            b[8 * r + 7] = fdct_row_dot<7>(lo, hi);
+        } else {
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                b[8 * r + x]     = (int)((lo >> (8 * x)) & 0xffu);
+                b[8 * r + 4 + x] = (int)((hi >> (8 * x)) & 0xffu);
+            }
+            fdct_1d<true>(b[8 * r], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3], b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        if (FORM & 2) {
+            if (FORM & 4) fdct_col_direct<true>(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+            else          fdct_col_direct<false>(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+        } else {
+            fdct_1d<false>(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ quantiser
 // dct_quantize_c intra, bias 0 (mpegvideo_enc.c:3647-3725, :492-496):
 //   DC: (b + 32) / 64 (C division);  AC: sign(b) * ((|b| * qmat) >> 22), clipped to +-1023

@@ -411,23 +411,22 @@ k_encode16(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const
                     const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
                     const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
                     int v[64];
+                    uint32_t px[16];                                        // the pixel rows as packed bytes
 #pragma unroll
                     for (int yy = 0; yy < 8; yy++) {
                         const int Y = min(by + yy, vh - 1);                 // bottom edge replication
                         const uint8_t *row = pl + (int64_t)(r0 - Y) * ls;
                         if (FAST) {
                             const uint2 q = *reinterpret_cast<const uint2 *>(row + bx);
-#pragma unroll
-                            for (int xx = 0; xx < 4; xx++) {
-                                v[yy * 8 + xx]     = (q.x >> (8 * xx)) & 0xff;
-                                v[yy * 8 + 4 + xx] = (q.y >> (8 * xx)) & 0xff;
-                            }
+                            px[2 * yy] = q.x; px[2 * yy + 1] = q.y;
                         } else {
+                            uint32_t q[2] = { 0u, 0u };
 #pragma unroll
-                            for (int xx = 0; xx < 8; xx++) v[yy * 8 + xx] = row[min(bx + xx, vw - 1)];   // right edge replication
+                            for (int xx = 0; xx < 8; xx++) q[xx >> 2] |= (uint32_t)row[min(bx + xx, vw - 1)] << (8 * (xx & 3));   // right edge replication
+                            px[2 * yy] = q[0]; px[2 * yy + 1] = q[1];
                         }
                     }
-                    fdct_block(v);
+                    fdct_block_px<0>(px, v);
                     dc = quant_dc(v[0]);
                     // raster order so the multiplier loads vectorise; mask bit = zigzag position
 #pragma unroll
@@ -637,7 +636,7 @@ struct Enc16v2Smem {
     Enc16v2WarpSmem w[kEncWarps];
 };
 
-template <bool FAST, int MINB>
+template <bool FAST, int MINB, int FD>
 __global__ void __launch_bounds__(kEncThreads, MINB)
 k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
@@ -662,6 +661,8 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
     const uint32_t obuf_s = smem_addr(&W.s.obuf[0]);
     const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
     int cur_qs = -1;
+    // macroblock index -> row by one high multiply: ceil(2^32 / mbw) is exact for mb * mbw < 2^32 (mbw == 1: row = mb)
+    const uint32_t mbw_magic = g.mbw > 1 ? 0xffffffffu / (uint32_t)g.mbw + 1u : 0u;
 
     for (int f = gw; f < n; f += nw_total) {
         const int qs = qscale ? qscale[f] : 2;
@@ -715,37 +716,38 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                 // ---------------- A: load, FDCT, survivor mask
                 if (active) {
                     const int mb = m0 + mbi;
-                    const int mx = mb % g.mbw, my = mb / g.mbw;
+                    const int my = g.mbw > 1 ? (int)__umulhi((uint32_t)mb, mbw_magic) : mb, mx = mb - my * g.mbw;
                     const int bx = comp ? mx * 8 : mx * 16 + (b & 1) * 8;
                     const int by = comp ? my * 8 : my * 16 + (b >> 1) * 8;
                     int v[64];
+                    uint32_t px[16];                                        // the pixel rows as packed bytes
 #pragma unroll
                     for (int yy = 0; yy < 8; yy++) {
                         const int Y = min(by + yy, vh - 1);                 // bottom edge replication
                         const uint8_t *row = pl + (int64_t)(r0 - Y) * ls;
                         if (FAST) {
                             const uint2 q = *reinterpret_cast<const uint2 *>(row + bx);
-#pragma unroll
-                            for (int xx = 0; xx < 4; xx++) {
-                                v[yy * 8 + xx]     = (q.x >> (8 * xx)) & 0xff;
-                                v[yy * 8 + 4 + xx] = (q.y >> (8 * xx)) & 0xff;
-                            }
+                            px[2 * yy] = q.x; px[2 * yy + 1] = q.y;
                         } else {
+                            uint32_t q[2] = { 0u, 0u };
 #pragma unroll
-                            for (int xx = 0; xx < 8; xx++) v[yy * 8 + xx] = row[min(bx + xx, vw - 1)];   // right edge replication
+                            for (int xx = 0; xx < 8; xx++) q[xx >> 2] |= (uint32_t)row[min(bx + xx, vw - 1)] << (8 * (xx & 3));   // right edge replication
+                            px[2 * yy] = q[0]; px[2 * yy + 1] = q[1];
                         }
                     }
-                    fdct_block(v);
+                    fdct_block_px<FD>(px, v);
                     dc = quant_dc(v[0]);
                     // c * c - T * T is negative exactly for the coefficients that quantise to zero: its sign bit is shifted
                     // into the (inverted) mask, highest zigzag position first so that bit k ends up at position k
+                    // ... lowest zigzag position first, so that position k ends up at bit 31 - (k & 31): the Huffman loop finds
+                    // its next coefficient with one count of leading zeros
                     uint32_t inv_lo = 0, inv_hi = 0;
 #pragma unroll
-                    for (int k4 = 15; k4 >= 0; k4--) {
+                    for (int k4 = 0; k4 < 16; k4++) {
                         const uint4 t4 = lds128(nthr_s + 16 * k4);       // -(T*T) of positions 4*k4 .. 4*k4 + 3
                         const int nt[4] = { (int)t4.x, (int)t4.y, (int)t4.z, (int)t4.w };
 #pragma unroll
-                        for (int kk = 3; kk >= 0; kk--) {
+                        for (int kk = 0; kk < 4; kk++) {
                             const int k = 4 * k4 + kk;
                             if (k == 0) continue;                         // the DC
                             const int c = v[zigzag_at(k)];
@@ -754,7 +756,7 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                             W.u.coef[k * 32 + lane] = (uint16_t)c;
                         }
                     }
-                    mask_lo = ~(inv_lo << 1) & ~1u;             // position 0 is the DC
+                    mask_lo = ~inv_lo & 0x7fffffffu;            // 31 positions went in: bit 31 (position 0, the DC) stays clear
                     mask_hi = ~inv_hi;
                 }
                 // DC predictor: the previous block of the component is the previous lane (Y0..Y3 of a macroblock and
@@ -774,14 +776,13 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                     // branch-free: the word under construction is stored every time (a string that outgrows its column
                     // keeps rewriting the last word and is caught by its length), the pointer moves by a select.
                     // t: the code and its mantissa, left-aligned; 1 <= nbits <= 27
-                    auto put = [&](uint32_t t, uint32_t nbits) {
+                    // nm32 = nbits - 32, so that "the word is full" is a sign test and the caller's (code length - leading zeros) needs no + 32
+                    auto put = [&](uint32_t t, int nm32) {
                         acc |= t >> fill;
-                        const uint32_t nf = fill + nbits;
+                        const int nf = (int)fill + nm32;             // bits in the word after this symbol, - 32
                         sts32(min(wp, wlast), acc);
-                        const bool full = nf >= 32;                  // then fill >= 5
-                        acc = full ? __funnelshift_l(0u, t, 0u - fill) : acc;      // t << (32 - fill)
-                        wp += full ? 128u : 0u;
-                        fill = nf & 31u;
+                        if (nf >= 0) { acc = __funnelshift_l(0u, t, 0u - fill); wp += 128u; }      // full, then fill >= 5: t << (32 - fill)
+                        fill = (uint32_t)nf & 31u;
                     };
                     // table entries: code left-aligned | length.  The mantissa (low `size` bits of x) goes right under the code:
                     // x << (32 - size) drops whatever sits above it, the funnel shift by the entry's low five bits moves it down
@@ -790,29 +791,32 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                         const int nb = bit_width((uint32_t)(diff < 0 ? -diff : diff));
                         const uint32_t e = lds32(huff_dc_s + nb * 4);
                         const uint32_t y = __funnelshift_l(0u, (uint32_t)(diff + (diff >> 31)), 0u - (uint32_t)nb);    // nb == 0: diff == 0
-                        put((e & ~31u) | __funnelshift_r(y, 0u, e), (e & 31u) + (uint32_t)nb);
+                        put((e & ~31u) | __funnelshift_r(y, 0u, e), (int)(e & 31u) + nb - 32);
                     }
                     const uint32_t ezrl = lds32(huff_ac_s + 0xf0 * 4), eeob = lds32(huff_ac_s);
-                    int prevk = 0;
+                    const uint32_t huff_ac_last_s = huff_ac_s + 4u + 31u * 4u;     // size = 32 - cz: entry index + 31 - cz
+                    int nprev = -1;                                  // -(position of the last coded coefficient) - 1
                     auto ac_run = [&](uint32_t m, int base) {        // encode_block's AC loop (mjpegenc.c:403-430)
+                        int k = base - 1;
                         while (m) {
-                            const int k = base + __ffs((int)m) - 1;
-                            m &= m - 1;
-                            int run = k - prevk - 1;
-                            prevk = k;
+                            const int z = clz_nz(m);                 // masks are bit-reversed: leading zeros = zero coefficients skipped
+                            m = (m << z) << 1;
+                            k += z + 1;
+                            int run = k + nprev;
+                            nprev = ~k;
                             const int raw = lds_s16(coef_s + (uint32_t)k * 64);
                             // level = |c| * qmat >> 22 (>= 1 here), sign restored (dct_quantize_c, mpegvideo_enc.c:3686-3716)
                             const uint32_t q = __umulhi((uint32_t)(raw < 0 ? -raw : raw), lds32(qm_s + (uint32_t)k * 4));
-                            const uint32_t hb = (uint32_t)msb_index(q);                       // size - 1
-                            for (; run >= 16; run -= 16) put(ezrl & ~31u, ezrl & 31u);
-                            const uint32_t e = lds32(huff_ac_s + 4u + (((uint32_t)run << 4) + hb) * 4u);
-                            const uint32_t y = __funnelshift_l(0u, q ^ (uint32_t)(raw >> 31), ~hb);   // negative: level - 1 = ~|level|; << (32 - size)
-                            put((e & ~31u) | __funnelshift_r(y, 0u, e), (e & 31u) + hb + 1u);
+                            const int cz = clz_nz(q);                                         // 32 - size
+                            for (; run >= 16; run -= 16) put(ezrl & ~31u, (int)(ezrl & 31u) - 32);
+                            const uint32_t e = lds32(huff_ac_last_s + ((uint32_t)run << 6) - ((uint32_t)cz << 2));    // entry (run << 4) + size - 1
+                            const uint32_t y = __funnelshift_l(0u, q ^ (uint32_t)(raw >> 31), (uint32_t)cz);   // negative: level - 1 = ~|level|; << (32 - size)
+                            put((e & ~31u) | __funnelshift_r(y, 0u, e), (int)(e & 31u) - cz);
                         }
                     };
                     ac_run(mask_lo, 0);
                     ac_run(mask_hi, 32);
-                    if (prevk != 63) put(eeob & ~31u, eeob & 31u);                 // EOB only if last_index < 63 (:432-434)
+                    if (nprev != -64) put(eeob & ~31u, (int)(eeob & 31u) - 32);    // EOB only if last_index < 63 (:432-434)
                     if (fill > 0) sts32(min(wp, wlast), acc);
                     len = ((wp - stage_s) >> 7) * 32u + fill;
                 }
@@ -1020,10 +1024,12 @@ cudaError_t encode_setup_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+#define AMV_ENC16V2_ATTR(MINB, FD) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, MINB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem)); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, MINB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    AMV_ENC16V2_ATTR(5, 0) AMV_ENC16V2_ATTR(4, 0) AMV_ENC16V2_ATTR(5, 3) AMV_ENC16V2_ATTR(5, 1) AMV_ENC16V2_ATTR(5, 2) AMV_ENC16V2_ATTR(5, 7)
+    AMV_ENC16V2_ATTR(4, 3)
+#undef AMV_ENC16V2_ATTR
     return e;
 }
 
@@ -1044,16 +1050,26 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
     // k_encode for the frames it flagged because a block's string outgrew its column.
     if (!redo) form = 0;
     if (form >= 2 && ((((uintptr_t)slots | slot_stride) & 15) != 0)) form = 1;
-    if (form == 3) {            // experiment: 4 CTAs per SM (128 registers, no spills) instead of 5 (96 registers)
-        if (fast) AMV_LAUNCH((k_encode16v2<true, 4>), encode_grid(n, 4), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
-                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
-        else      AMV_LAUNCH((k_encode16v2<false, 4>), encode_grid(n, 4), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
-                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
-    } else if (form == 2) {
-        if (fast) AMV_LAUNCH((k_encode16v2<true, 5>), encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
-                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
-        else      AMV_LAUNCH((k_encode16v2<false, 5>), encode_grid(n, 5), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
-                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo);
+    if (form >= 2) {
+        // form 2: five CTAs per SM (96 registers), the transform in its factorised form; 3: the same at four CTAs per SM;
+        // 4..7: the transform regrouped for the two integer pipes (amv_dct.cuh) -- 4: dot-product rows + written-out odd
+        // columns, 5: dot-product rows only, 6: written-out odd columns only, 7: rows, odd columns and outputs 2 / 6;
+        // 8: form 4 at four CTAs per SM
+#define AMV_ENC16V2_GO(MINB, FD) do { \
+        if (fast) AMV_LAUNCH((k_encode16v2<true, MINB, FD>), encode_grid(n, MINB), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, \
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo); \
+        else      AMV_LAUNCH((k_encode16v2<false, MINB, FD>), encode_grid(n, MINB), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, \
+                             qscale, slots, slot_stride, pkt_cap, out_size, status, redo); } while (0)
+        switch (form) {
+        case 3: AMV_ENC16V2_GO(4, 0); break;
+        case 4: AMV_ENC16V2_GO(5, 3); break;
+        case 5: AMV_ENC16V2_GO(5, 1); break;
+        case 6: AMV_ENC16V2_GO(5, 2); break;
+        case 7: AMV_ENC16V2_GO(5, 7); break;
+        case 8: AMV_ENC16V2_GO(4, 3); break;
+        default: AMV_ENC16V2_GO(5, 0); break;
+        }
+#undef AMV_ENC16V2_GO
     } else if (form == 1) {
         if (fast) AMV_LAUNCH(k_encode16<true>, encode_grid(n, 5), kEncThreads, sizeof(Enc16Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g,
                              qscale, slots, slot_stride, pkt_cap, out_size, status, redo);

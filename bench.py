@@ -738,7 +738,7 @@ def bench_video(args):
     frames_per_step = n
     names = {"encode": "k_encode16v2 (+ k_encode for the frames it hands back; one pair per launch)", "tokens": "k_vlc_tokens_lean",
              "sync": "k_vlc_sync", "idct": "k_idct16"}
-    if dict(J.opts).get("encode_rounds", 2) == 1:
+    if dict(J.opts).get("encode_rounds", 4) == 1:
         names["encode"] = "k_encode16 (+ k_encode for the frames it hands back)"
     tp = dict(J.opts).get("decode_token_pass", 2)
     if tp != 2:

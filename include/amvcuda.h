@@ -108,8 +108,11 @@ AMV_API void        amv_host_free(void *p);
  *   "profile_events"               1 = bracket each hot kernel launch with CUDA events on the context's stream
  *   "host_chunk_frames"            frames per stage of the AMV_MEM_HOST copy/compute pipeline (0 = choose)
  *   "host_zero_copy_packets"       0 = DMA pinned decoder input into a device copy instead of reading it in place
- *   "encode_rounds"                encoder kernels: 2 (default) k_encode16v2, 1 k_encode16 (each + k_encode for the frames it
- *                                  hands back), 0 the one-kernel encoder, 3 = 2 at four instead of five CTAs per SM
+ *   "encode_rounds"                encoder kernels: 4 (default) k_encode16v2 with the transform regrouped for the two integer
+ *                                  pipes (dot-product rows, written-out odd columns), 2 k_encode16v2 with the factorised
+ *                                  transform, 1 k_encode16 (each + k_encode for the frames it hands back), 0 the one-kernel
+ *                                  encoder; 3 = 2 and 8 = 4 at four instead of five CTAs per SM; 5 / 6 / 7 = dot-product rows
+ *                                  only / written-out odd columns only / both plus written-out outputs 2 and 6
  *   "decode_token_pass"            AMV / SP5X token pass: 2 (default) lean pass with 16-bit tokens, 1 lean pass with 32-bit
  *                                  tokens, 0 the flat symbol loop with 32-bit tokens; 1 and 2 also run the lean, checkpointed
  *                                  synchronisation pass when frames are split into lanes, 0 the flat one

@@ -199,6 +199,34 @@ void emul_fdct_quant(const int16_t *blocks, int n, int qscale, int16_t *out, int
     }
 }
 
+// the encoder's transform in its regrouped forms (fdct_block_px: dot-product rows on packed bytes, written-out columns)
+}  // extern "C"
+template <int FORM>
+static void fdct_form_run(const int16_t *blocks, int n, int16_t *fdct_out) {
+    for (int i = 0; i < n; i++) {
+        uint32_t px[16];
+        for (int k = 0; k < 16; k++) {
+            px[k] = 0;
+            for (int j = 0; j < 4; j++) px[k] |= (uint32_t)(blocks[64 * i + 4 * k + j] & 0xff) << (8 * j);
+        }
+        int v[64];
+        fdct_block_px<FORM>(px, v);
+        for (int k = 0; k < 64; k++) fdct_out[64 * i + k] = (int16_t)v[k];
+    }
+}
+extern "C" {
+int emul_fdct_form(const int16_t *blocks, int n, int form, int16_t *fdct_out) {
+    switch (form) {
+    case 0: fdct_form_run<0>(blocks, n, fdct_out); return 0;
+    case 1: fdct_form_run<1>(blocks, n, fdct_out); return 0;
+    case 2: fdct_form_run<2>(blocks, n, fdct_out); return 0;
+    case 3: fdct_form_run<3>(blocks, n, fdct_out); return 0;
+    case 6: fdct_form_run<6>(blocks, n, fdct_out); return 0;
+    case 7: fdct_form_run<7>(blocks, n, fdct_out); return 0;
+    }
+    return -1;
+}
+
 // worst-case magnitudes inside fdct_block for a block: reports whether every intermediate the
 // 32-bit kernel shifts fits (|x| < 2^31) by redoing the pass in 64 bit
 int emul_enc_huff(int idx) { init(); return (int)g_eh.e[idx]; }

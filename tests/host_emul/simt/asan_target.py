@@ -41,7 +41,7 @@ for (w, h, n, kind, q) in ((160, 120, 3, "sinus", 2), (72, 24, 4, "noise", 2), (
             assert st[0] == 0 and np.array_equal(dy[0], wy[0])
 ctx.set_option("decode_token_pass", 2)
 ctx.set_option("decode_log2_lanes", -1)
-ctx.set_option("encode_rounds", 2)
+ctx.set_option("encode_rounds", 4)
 rng = np.random.default_rng(5)
 nsamp = (rng.integers(0, 900, 70) * 2).astype(np.uint32)
 nsamp[:3] = [0, 2, 1378]

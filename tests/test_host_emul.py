@@ -98,6 +98,27 @@ def test_fdct_quant_registers(emul, oracle, qscale):
     assert np.array_equal(q, want)
 
 
+@pytest.mark.parametrize("form", [0, 1, 2, 3, 6, 7])
+def test_fdct_regrouped_forms(emul, oracle, form):
+    """fdct_block_px: the row pass as dot products on the packed pixel bytes and the column pass with its odd half (and
+    outputs 2 / 6) written out are the same integer linear maps as the factorised pass of jfdctint.c:184-341."""
+    rng = np.random.default_rng(34)
+    n = np.arange(8)
+    basis = np.cos((2 * n[None, :] + 1) * n[:, None] * np.pi / 16)
+    ext = []
+    for u in range(8):
+        for v in range(8):
+            pat = np.outer(basis[u], basis[v])
+            ext.append((pat > 0) * 255)
+            ext.append((pat < 0) * 255)
+    blocks = np.concatenate([rng.integers(0, 256, (6000, 64)), rng.choice([0, 255], (2000, 64)), np.array(ext).reshape(-1, 64),
+                             np.full((1, 64), 255), np.zeros((1, 64), int)]).astype(np.int16)
+    blocks = np.ascontiguousarray(blocks)
+    fd = np.zeros_like(blocks)
+    assert emul.emul_fdct_form(_p(blocks), blocks.shape[0], form, _p(fd)) == 0
+    assert np.array_equal(fd, oracle.fdct(blocks))
+
+
 @pytest.mark.parametrize("w,h,kind", [(160, 120, "sinus"), (64, 48, "noise"), (48, 40, "edges"), (32, 32, "flat"),
                                       (208, 176, "sinus"), (72, 24, "sinus")])
 @pytest.mark.parametrize("log2p", [0, 1, 3, 5])
