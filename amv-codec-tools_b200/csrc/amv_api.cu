@@ -845,7 +845,7 @@ AMV_API int amv_set_option(amv_ctx *ctx, const char *key, int64_t value) {
     if (!strcmp(key, "profile_events")) { ctx->opt_profile = value != 0; return AMV_OK; }
     if (!strcmp(key, "host_chunk_frames")) { ctx->opt_host_chunk = (int)value; return AMV_OK; }
     if (!strcmp(key, "encode_rounds")) {
-        if (value < 0 || value > 10) return AMV_ERR_UNSUPPORTED;
+        if (value < 0 || value > 8 || (value >= 5 && value <= 7)) return AMV_ERR_UNSUPPORTED;
         ctx->opt_encode_rounds = (int)value;
         return AMV_OK;
     }

@@ -133,7 +133,6 @@ inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (ui
 inline void sts8(uint32_t saddr, uint32_t v) { *smem_ptr<uint8_t>(saddr) = (uint8_t)v; }
 inline void sts128(uint32_t saddr, const uint4 &v) { *smem_ptr<uint4>(saddr) = v; }
 inline void red_or_shared(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) |= v; }
-inline void prefetch_l2(const void *) {}
 // 1-D bulk asynchronous copy + mbarrier: the emulator copies at once, so every wait is already satisfied
 inline void mbar_init(uint32_t, uint32_t) {}
 inline void mbar_arrive_expect_tx(uint32_t, uint32_t) {}
@@ -171,8 +170,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
 }
-// asks the line at p into the L2 (no register, no scoreboard)
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
 }

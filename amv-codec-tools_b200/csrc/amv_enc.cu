@@ -636,7 +636,7 @@ struct Enc16v2Smem {
     Enc16v2WarpSmem w[kEncWarps];
 };
 
-template <bool FAST, int MINB, int FD, int PF>
+template <bool FAST, int MINB, int FD>
 __global__ void __launch_bounds__(kEncThreads, MINB)
 k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, const uint8_t *__restrict__ pv,
              int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c, int n, Geom g, const int32_t *__restrict__ qscale,
@@ -661,12 +661,13 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
     const uint32_t obuf_s = smem_addr(&W.s.obuf[0]);
     const int gw = blockIdx.x * kEncWarps + wid, nw_total = gridDim.x * kEncWarps;
     int cur_qs = -1;
+    uint32_t px[16];                                              // the block's pixel rows as packed bytes
     // macroblock index -> row by one high multiply: ceil(2^32 / mbw) is exact for mb * mbw < 2^32 (mbw == 1: row = mb)
     const uint32_t mbw_magic = g.mbw > 1 ? 0xffffffffu / (uint32_t)g.mbw + 1u : 0u;
     // The pixel rows of this lane's block in round rrd of the segment at macroblock mm0 of frame ff, as loaded (two words per
     // row, column 0 in the lowest byte): bottom-up addressing (amv_encode_picture mjpegenc.c:454-472) and edge replication by
     // clamped indices (mpegvideo.c:1416-1470).  Lanes without a block in that round leave q alone.
-    auto fetch = [&](int ff, int mm0, int rrd, uint32_t (&q)[16], bool hint_only = false) {
+    auto fetch = [&](int ff, int mm0, int rrd, uint32_t (&q)[16]) {
         const int nmb_ = min(16, total_mb - mm0);
         const int comp_ = rrd ? 0 : 1 + (lane >> 4);
         const int mbi_ = rrd ? 8 * (rrd - 1) + (lane >> 2) : (lane & 15);
@@ -683,7 +684,6 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
         for (int yy = 0; yy < 8; yy++) {
             const int Y = min(by + yy, vh_ - 1);                 // bottom edge replication
             const uint8_t *row = pl_ + (int64_t)(r0_ - Y) * ls_;
-            if (hint_only) { prefetch_l2(row + bx); continue; }
             if (FAST) {
                 const uint2 w2 = *reinterpret_cast<const uint2 *>(row + bx);
                 q[2 * yy] = w2.x; q[2 * yy + 1] = w2.y;
@@ -695,11 +695,6 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
             }
         }
     };
-    // PF == 1: the rows of the NEXT round's block are requested right after the transform has consumed this round's (their 16
-    // registers are free from there on) and arrive while the Huffman, packing and output stages run; the tags say which
-    // round the registers hold (a frame that is handed back leaves its look-ahead unused)
-    uint32_t px[16];
-    int pf_f = -1, pf_m0 = 0, pf_rd = 0;
 
     for (int f = gw; f < n; f += nw_total) {
         const int qs = qscale ? qscale[f] : 2;
@@ -748,20 +743,11 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                 int dc = 0;
 
                 // ---------------- A: load, FDCT, survivor mask
-                if (!(PF == 1 && pf_f == f && pf_m0 == m0 && pf_rd == rd)) fetch(f, m0, rd, px);
-                int nx_f = f, nx_m0 = m0, nx_rd = rd + 1;   // the round after this one
-                if (PF) {
-                    if (nx_rd == 3 || (nx_rd == 2 && nmb <= 8)) {
-                        nx_rd = 0; nx_m0 = m0 + 16;
-                        if (nx_m0 >= total_mb) { nx_m0 = 0; nx_f = f + nw_total; }
-                    }
-                }
+                // (the rows are fetched, and the transform is closed, outside the branch the mask is built in: in this shape ptxas
+                // keeps the stage free of spills at 96 registers -- worth 0.8 ms per 100 000 frames)
+                fetch(f, m0, rd, px);
                 int v[64];
                 if (active) fdct_block_px<FD>(px, v);
-                if (PF == 1) {
-                    if (nx_f < n) { fetch(nx_f, nx_m0, nx_rd, px); pf_f = nx_f; pf_m0 = nx_m0; pf_rd = nx_rd; }
-                    else pf_f = -1;
-                }
                 if (active) {
                     dc = quant_dc(v[0]);
                     // c * c - T * T is negative exactly for the coefficients that quantise to zero: its sign bit is shifted
@@ -791,9 +777,6 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                 const bool first_of_comp = rd ? lane == 0 : (lane & 15) == 0;
                 const int pred = first_of_comp ? W.carry_dc[comp] : dc_prev;
                 __syncwarp();
-
-                // PF == 2: no registers held -- the next round's rows are only asked into the L2, here where few registers are live
-                if (PF == 2 && nx_f < n) fetch(nx_f, nx_m0, nx_rd, px, true);
 
                 // ---------------- B: Huffman-code the block into the lane's private bit string
                 uint32_t len = 0;
@@ -1053,12 +1036,10 @@ cudaError_t encode_setup_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16Smem));
-#define AMV_ENC16V2_ATTR(MINB, FD, PF) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, MINB, FD, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem)); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, MINB, FD, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
-    AMV_ENC16V2_ATTR(5, 0, 0) AMV_ENC16V2_ATTR(4, 0, 0) AMV_ENC16V2_ATTR(5, 3, 0) AMV_ENC16V2_ATTR(5, 1, 0)
-    AMV_ENC16V2_ATTR(5, 2, 0) AMV_ENC16V2_ATTR(5, 7, 0) AMV_ENC16V2_ATTR(4, 3, 0) AMV_ENC16V2_ATTR(4, 3, 1)
-    AMV_ENC16V2_ATTR(5, 3, 2)
+#define AMV_ENC16V2_ATTR(MINB, FD) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<true, MINB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem)); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_encode16v2<false, MINB, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Enc16v2Smem));
+    AMV_ENC16V2_ATTR(5, 0) AMV_ENC16V2_ATTR(4, 0) AMV_ENC16V2_ATTR(5, 3) AMV_ENC16V2_ATTR(4, 3)
 #undef AMV_ENC16V2_ATTR
     return e;
 }
@@ -1081,27 +1062,19 @@ void launch_encode(const uint8_t *y, const uint8_t *u, const uint8_t *v, int ls_
     if (!redo) form = 0;
     if (form >= 2 && ((((uintptr_t)slots | slot_stride) & 15) != 0)) form = 1;
     if (form >= 2) {
-        // form 2: five CTAs per SM (96 registers), the transform in its factorised form; 3: the same at four CTAs per SM;
-        // 4..7: the transform regrouped for the two integer pipes (amv_dct.cuh) -- 4: dot-product rows + written-out odd
-        // columns, 5: dot-product rows only, 6: written-out odd columns only, 7: rows, odd columns and outputs 2 / 6;
-        // 8: form 4 at four CTAs per SM; 9: form 8 with the next round's pixel rows requested one round ahead (16 registers held
-        // across the Huffman stage: free at 128 registers per thread); 10: form 4 with the next round's rows asked into the L2 (no
-        // registers held)
-#define AMV_ENC16V2_GO(MINB, FD, PF) do { \
-        if (fast) AMV_LAUNCH((k_encode16v2<true, MINB, FD, PF>), encode_grid(n, MINB), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, \
+        // form 4 (default): five CTAs per SM (96 registers), the transform regrouped for the two integer pipes (amv_dct.cuh:
+        // dot-product rows on the packed pixel bytes, written-out odd columns); 2: the transform in its factorised form;
+        // 3 / 8: forms 2 / 4 at four CTAs per SM (128 registers)
+#define AMV_ENC16V2_GO(MINB, FD) do { \
+        if (fast) AMV_LAUNCH((k_encode16v2<true, MINB, FD>), encode_grid(n, MINB), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, \
                              qscale, slots, slot_stride, pkt_cap, out_size, status, redo); \
-        else      AMV_LAUNCH((k_encode16v2<false, MINB, FD, PF>), encode_grid(n, MINB), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, \
+        else      AMV_LAUNCH((k_encode16v2<false, MINB, FD>), encode_grid(n, MINB), kEncThreads, sizeof(Enc16v2Smem), s, y, u, v, ls_y, ls_c, fs_y, fs_c, n, g, \
                              qscale, slots, slot_stride, pkt_cap, out_size, status, redo); } while (0)
         switch (form) {
-        case 3: AMV_ENC16V2_GO(4, 0, 0); break;
-        case 4: AMV_ENC16V2_GO(5, 3, 0); break;
-        case 5: AMV_ENC16V2_GO(5, 1, 0); break;
-        case 6: AMV_ENC16V2_GO(5, 2, 0); break;
-        case 7: AMV_ENC16V2_GO(5, 7, 0); break;
-        case 8: AMV_ENC16V2_GO(4, 3, 0); break;
-        case 9: AMV_ENC16V2_GO(4, 3, 1); break;
-        case 10: AMV_ENC16V2_GO(5, 3, 2); break;
-        default: AMV_ENC16V2_GO(5, 0, 0); break;
+        case 2: AMV_ENC16V2_GO(5, 0); break;
+        case 3: AMV_ENC16V2_GO(4, 0); break;
+        case 8: AMV_ENC16V2_GO(4, 3); break;
+        default: AMV_ENC16V2_GO(5, 3); break;
         }
 #undef AMV_ENC16V2_GO
     } else if (form == 1) {

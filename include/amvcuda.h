@@ -111,8 +111,7 @@ AMV_API void        amv_host_free(void *p);
  *   "encode_rounds"                encoder kernels: 4 (default) k_encode16v2 with the transform regrouped for the two integer
  *                                  pipes (dot-product rows, written-out odd columns), 2 k_encode16v2 with the factorised
  *                                  transform, 1 k_encode16 (each + k_encode for the frames it hands back), 0 the one-kernel
- *                                  encoder; 3 = 2 and 8 = 4 at four instead of five CTAs per SM; 5 / 6 / 7 = dot-product rows
- *                                  only / written-out odd columns only / both plus written-out outputs 2 and 6
+ *                                  encoder; 3 = 2 and 8 = 4 at four instead of five CTAs per SM
  *   "decode_token_pass"            AMV / SP5X token pass: 2 (default) lean pass with 16-bit tokens, 1 lean pass with 32-bit
  *                                  tokens, 0 the flat symbol loop with 32-bit tokens; 1 and 2 also run the lean, checkpointed
  *                                  synchronisation pass when frames are split into lanes, 0 the flat one

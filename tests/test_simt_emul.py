@@ -42,9 +42,9 @@ def test_encode_kernels_byte_identical(emu, oracle, w, h, kind):
     n = 2 if w * h > 40000 else 5
     y, u, v = synth_frames(n, w, h, seed=11, kind=kind)
     wpk, woff, wsz = oracle.encode_frames(y, u, v, w, h, 2)
-    # k_encode16v2 with the regrouped transforms (4..8) and the factorised one (2, 3), k_encode16 (each + k_encode for
+    # k_encode16v2 with the regrouped transform (4, 8) and the factorised one (2, 3), k_encode16 (each + k_encode for
     # handed-back frames), k_encode alone
-    for form in (9, 10, 4, 5, 6, 7, 8, 3, 2, 1, 0):
+    for form in (4, 8, 3, 2, 1, 0):
         emu.set_option("encode_rounds", form)
         pk, off, sz, st = emu.encode_frames(y, u, v)
         assert (st == 0).all() and np.array_equal(sz, wsz) and np.array_equal(pk, wpk), "encode_rounds=%d" % form
