@@ -104,6 +104,22 @@ AMV_HD int msb_index(uint32_t v) {
 #endif
 }
 
+// floor(x / d) and the remainder for any 32-bit x by one high multiply and one correction step: with m = floor(2^32 / d)
+// (div_magic; 2^32 - 1 for d = 1) the estimate umulhi(x, m) is the quotient or one below it.  Replaces the ~25-instruction
+// emulated division where the divisor is a launch constant.
+inline uint32_t div_magic(uint32_t d) { return d >= 2 ? (uint32_t)((1ull << 32) / d) : 0xffffffffu; }
+AMV_HD uint32_t div_by_magic(uint32_t x, uint32_t d, uint32_t m, uint32_t &rem) {
+#if defined(__CUDA_ARCH__)
+    uint32_t q = __umulhi(x, m);
+#else
+    uint32_t q = (uint32_t)(((uint64_t)x * m) >> 32);
+#endif
+    uint32_t r = x - q * d;
+    if (r >= d) { q++; r -= d; }
+    rem = r;
+    return q;
+}
+
 // count of leading zeros (v != 0): one FLO.SH
 AMV_HD int clz_nz(uint32_t v) {
 #if defined(__CUDA_ARCH__)

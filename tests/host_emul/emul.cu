@@ -199,6 +199,19 @@ void emul_fdct_quant(const int16_t *blocks, int n, int qscale, int16_t *out, int
     }
 }
 
+// div_by_magic over a range of dividends: returns the number of mismatches against the C division
+int emul_div_magic_check(uint32_t d, uint32_t x0, uint32_t count, uint32_t step) {
+    const uint32_t m = div_magic(d);
+    int bad = 0;
+    uint32_t x = x0;
+    for (uint32_t i = 0; i < count; i++, x += step) {
+        uint32_t rem;
+        const uint32_t q = div_by_magic(x, d, m, rem);
+        if (q != x / d || rem != x % d) bad++;
+    }
+    return bad;
+}
+
 // the encoder's transform in its regrouped forms (fdct_block_px: dot-product rows on packed bytes, written-out columns)
 }  // extern "C"
 template <int FORM>

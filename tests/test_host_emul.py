@@ -98,6 +98,16 @@ def test_fdct_quant_registers(emul, oracle, qscale):
     assert np.array_equal(q, want)
 
 
+def test_division_by_multiply(emul):
+    """div_by_magic (block index -> frame / block row in k_idct16): exact for every 32-bit dividend; checked densely at both
+    ends of the range and with a coarse stride in between, for the divisors the geometries produce and the edge cases."""
+    for d in (1, 2, 3, 5, 6, 7, 10, 20, 26, 40, 45, 80, 160, 429, 1800, 3300, 21600, 65535, 65536, 65537, (1 << 31) - 1, 1 << 31,
+              (1 << 32) - 1):
+        assert emul.emul_div_magic_check(C.c_uint32(d), C.c_uint32(0), C.c_uint32(200000), C.c_uint32(1)) == 0
+        assert emul.emul_div_magic_check(C.c_uint32(d), C.c_uint32((1 << 32) - 200000), C.c_uint32(200000), C.c_uint32(1)) == 0
+        assert emul.emul_div_magic_check(C.c_uint32(d), C.c_uint32(12345), C.c_uint32(400000), C.c_uint32(10007)) == 0
+
+
 @pytest.mark.parametrize("form", [0, 1, 2, 3, 6, 7])
 def test_fdct_regrouped_forms(emul, oracle, form):
     """fdct_block_px: the row pass as dot products on the packed pixel bytes and the column pass with its odd half (and
