@@ -1274,14 +1274,16 @@ template <bool FAST>
 __global__ void __launch_bounds__(kIdctThreads)
 k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off, const uint64_t *__restrict__ slot_off,
        const uint32_t *__restrict__ scan_len, int n, Geom g, uint8_t *__restrict__ py, uint8_t *__restrict__ pu,
-       uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c) {
+       uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
+       uint32_t mg_nblk, uint32_t mg_rowl, uint32_t mg_rowc /* div_magic of nblk and of the luma / chroma blocks per row */) {
     __shared__ uint32_t tile[kIdctThreads / 32][32 * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int f = (int)(gt / g.nblk);
+    uint32_t iu;        // divisions by launch constants: one high multiply and a correction each (div_by_magic)
+    const int f = (gt >> 32) == 0 ? (int)div_by_magic((uint32_t)gt, (uint32_t)g.nblk, mg_nblk, iu) : (int)(gt / g.nblk);
     if (f >= n) return;
     if (scan_len[f] == 0) return;
-    const int i = (int)(gt - (int64_t)f * g.nblk);
+    const int i = (gt >> 32) == 0 ? (int)iu : (int)(gt - (int64_t)f * g.nblk);
     // blocks are enumerated in plane raster order (all of Y, then Cb, then Cr); blk = the block's index in
     // bitstream order: MCU by MCU, inside an MCU component by component, v x h blocks in raster order
     const int nluma = g.nl * g.mbw * g.mbh, nchroma = g.nc * g.mbw * g.mbh;
@@ -1289,14 +1291,16 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
     if (i < nluma) {
         comp = 0;
         const int rowb = g.mbw << g.llh;
-        by = i / rowb; bx = i - by * rowb;
+        uint32_t rem;
+        by = (int)div_by_magic((uint32_t)i, (uint32_t)rowb, mg_rowl, rem); bx = (int)rem;
         blk = ((by >> g.llv) * g.mbw + (bx >> g.llh)) * g.nb + ((by & ((1 << g.llv) - 1)) << g.llh) + (bx & ((1 << g.llh) - 1));
     } else {
         const int j = i - nluma;
         comp = j < nchroma ? 1 : 2;
         const int jj = comp == 1 ? j : j - nchroma;
         const int rowb = g.mbw << g.lch;
-        by = jj / rowb; bx = jj - by * rowb;
+        uint32_t rem;
+        by = (int)div_by_magic((uint32_t)jj, (uint32_t)rowb, mg_rowc, rem); bx = (int)rem;
         blk = ((by >> g.lcv) * g.mbw + (bx >> g.lch)) * g.nb + g.nl + (comp - 1) * g.nc +
               ((by & ((1 << g.lcv) - 1)) << g.lch) + (bx & ((1 << g.lch) - 1));
     }
@@ -1660,12 +1664,13 @@ void launch_idct(const uint32_t *tokens, const uint32_t *blk_off, const uint64_t
     const int64_t grid = (threads + kIdctThreads - 1) / kIdctThreads;
     const bool fast = (g.w % 16 == 0) &&
                       ((((uintptr_t)y | (uintptr_t)u | (uintptr_t)v | (uintptr_t)ls_y | (uintptr_t)ls_c | fs_y | fs_c) & 7) == 0);
+    const uint32_t mg_nblk = div_magic((uint32_t)g.nblk), mg_rowl = div_magic((uint32_t)(g.mbw << g.llh)), mg_rowc = div_magic((uint32_t)(g.mbw << g.lch));
     if (fast)
         AMV_LAUNCH(k_idct<true>, (unsigned)grid, kIdctThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
-                                                             fs_y, fs_c);
+                                                             fs_y, fs_c, mg_nblk, mg_rowl, mg_rowc);
     else
         AMV_LAUNCH(k_idct<false>, (unsigned)grid, kIdctThreads, 0, s, tokens, blk_off, slot_off, scan_len, n, g, y, u, v, ls_y, ls_c,
-                                                              fs_y, fs_c);
+                                                              fs_y, fs_c, mg_nblk, mg_rowl, mg_rowc);
 }
 
 }  // namespace amv
