@@ -660,7 +660,7 @@ k_vlc_sync_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restrict_
             for (int u = 0; u < kTokPeriod; u++) {
                 const uint32_t hi = window();
                 uint32_t e = lds32(act_s + ((hi >> (32 - kFlatAcBits)) << 2));
-                if ((e & 31u) == 0) {
+                if ((e & 31u) == 0) {           // (keeping parked lanes out of this side path, as the token pass does, measured slower here: 9.16 -> 9.62 ms)
                     if (!(e & kFlatBad)) e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << kFlatAcBits) >> (32u - (e >> 24)))) << 2)) & 0x7fffffffu;
                     if ((e & 31u) == 0) e = 1u | (1u << 8) | (kFlatAdvEob << 23);        // no such code: ends the block
                 }
@@ -1142,12 +1142,14 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
     auto stage_addr = [&](uint32_t c) -> uint32_t { return T16 ? tst_s | ((c << 6) & 0x3c0u) : tst_s | ((c << 7) & 0x380u); };
     auto flush_group = [&]() {              // staged tokens [flushed, flushed + kGroup)
         uint32_t w[4];
+        // flushed is a multiple of the group size: one address, the group's slots at fixed offsets from it
+        const uint32_t fb = stage_addr(flushed);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (T16) {
-                const uint32_t lo = lds_u16(stage_addr(flushed + 2 * j)), hi16 = lds_u16(stage_addr(flushed + 2 * j + 1));
+                const uint32_t lo = lds_u16(fb + 128u * j), hi16 = lds_u16(fb + 128u * j + 64u);
                 w[j] = lo | (hi16 << 16);
-            } else w[j] = lds32(stage_addr(flushed + j));
+            } else w[j] = lds32(fb + 128u * j);
         }
         if (T16) *reinterpret_cast<uint4 *>(tok_frame16 + (tok_first + flushed)) = make_uint4(w[0], w[1], w[2], w[3]);
         else     *reinterpret_cast<uint4 *>(tok_frame32 + (tok_first + flushed)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -1223,10 +1225,13 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
         for (int u = 0; u < kTokPeriod; u++) {
             const uint32_t hi = window();
             uint32_t e = lds32(act_s + ((hi >> (32 - kFlatAcBits)) << 2));
-            if ((e & 31u) == 0) {
+            // (a parked lane looks at the next block's DC code through the AC table and would take this side path -- the long
+            // codes -- in most iterations of the warp: ncu counted it with 2.3 threads per instruction at 5 % of the kernel's
+            // instructions.  Its entry is never used, so it stays out.)
+            if ((e & 31u) == 0 && on) {
                 if (!(e & kFlatBad)) e = lds32(lut_s + ((((e >> 8) & 0xffffu) + ((hi << kFlatAcBits) >> (32u - (e >> 24)))) << 2));
                 if ((e & 31u) == 0) {       // no such code: ends the block
-                    if (on) st |= AMV_ST_BADCODE;
+                    st |= AMV_ST_BADCODE;
                     e = 1u | (1u << 8) | ((kFlatAdvEob - 1u) << 23);
                 }
             }
