@@ -88,6 +88,15 @@ AMV_HD uint32_t bswap32(uint32_t v) {
 #endif
 }
 
+// bits [15:8] of v: one PRMT
+AMV_HD uint32_t byte1(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0, 0x4441);
+#else
+    return (v >> 8) & 0xffu;
+#endif
+}
+
 AMV_HD int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // [off, off + len) lies inside [0, total): written so that a hostile offset near 2^64 cannot wrap the sum

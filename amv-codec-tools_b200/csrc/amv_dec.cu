@@ -1043,6 +1043,7 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
         uint32_t e = tabs->flat.e[i];
         // everything from the first AC table on (the AC first levels and their second levels) feeds the symbol loop
         // (16-bit tokens carry ZRL as a token, 32-bit tokens only what has a value: bit 31 as it is)
+        // (advance - 1, not the advance: for a coefficient that is its run, which the 16-bit token takes from these bits as they are)
         if (i >= ac0 && (e & 31u)) e = T16 ? ((e - (1u << 23)) & 0x7fffffffu) | ((e & kFlatTok16) << 24) : e - (1u << 23);
         S.lut[i] = e;
     }
@@ -1242,13 +1243,13 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
             if (T16) {
                 // the symbol in fixed width: run = advance - 1 (15 for ZRL) over the level
                 sts16(stage_addr(kt >> 8), ((e >> 11) & 0xf000u) | ((uint32_t)lvl & 0xfffu));
-                if (on) { bp += (e >> 8) & 0xffu; kt += (e >> 23) + 1u; }
+                if (on) { bp += byte1(e); kt += (e >> 23) + 1u; }
             } else {
                 // level * quant_matrix[j] as int16 over the consumer's column offset (:420,428); the token goes where the count
                 // stood before the symbol, and only if the symbol has a value (a ring of eight has no dead slot to spare)
                 const uint32_t slot = stage_addr(kt >> 8);
                 const bool emit = on && (int)e < 0;
-                if (on) { bp += (e >> 8) & 0xffu; kt += (e >> 23) + 1u; }
+                if (on) { bp += byte1(e); kt += (e >> 23) + 1u; }
                 const uint32_t z = lds32(tz_s | ((kt << 2) & 0x1fcu));
                 if (emit) sts32(slot, __byte_perm((uint32_t)(lvl * (int)(z & 0xffu)), z, 0x7610));
             }
