@@ -88,6 +88,17 @@ AMV_HD uint32_t bswap32(uint32_t v) {
 #endif
 }
 
+// (a & mask) | (b & ~mask): one LOP3 (written out because the compiler narrows b's mask first when only a halfword is kept)
+AMV_HD uint32_t bitselect(uint32_t a, uint32_t b, uint32_t mask) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(mask));
+    return d;
+#else
+    return (a & mask) | (b & ~mask);
+#endif
+}
+
 // bits [15:8] of v: one PRMT
 AMV_HD uint32_t byte1(uint32_t v) {
 #if defined(__CUDA_ARCH__)

@@ -1159,7 +1159,8 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
 
     bool live = count > 0;                  // the lane has blocks left
     bool on = false;                        // ... and is inside one (its DC is read; not parked at a block end)
-    bool ended = false, endnz = false;      // parked at a block end; the block's last symbol carried a coefficient
+    bool ended = false;                     // parked at a block end
+    int endlvl = 0;                         // ... whose last symbol carried this level (non-zero: a coefficient)
     uint32_t dct_s = 0, act_s = 0, bnext = 0, tz_s = 0;
     int q0 = 0;
     uint32_t cerr = 0;                      // a coefficient index ran past 63 ("error count", mjpegdec.c:423-424)
@@ -1187,7 +1188,7 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
             boff[bi] = ((ntok - blk0 - 1u) << kTokCountShift) + (tok_first + blk0);
             bi++;
             blk0 = ntok;
-            if (endnz && (kt & 0xffu) != 64u) cerr = 1;                  // the last coefficient sat past position 63
+            if (endlvl != 0 && (kt & 0xffu) != 64u) cerr = 1;            // the last coefficient sat past position 63
             const uint4 bs = lds128(bstate_s + bnext * 16u);
             if (bs.w & 0x80u) { const int t = predA; predA = predB; predB = predC; predC = t; }    // Y -> Cb -> Cr -> Y
             dct_s = bs.x; act_s = bs.y; q0 = (int)(bs.z & 0xffu); tz_s = bs.z >> 8; bnext = bs.w & 0x7fu;
@@ -1242,7 +1243,8 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
             const int lvl = (int)((__funnelshift_l(top ^ (uint32_t)sg, 0u, e >> 16) ^ (uint32_t)sg) - (uint32_t)sg);
             if (T16) {
                 // the symbol in fixed width: run = advance - 1 (15 for ZRL) over the level
-                sts16(stage_addr(kt >> 8), ((e >> 11) & 0xf000u) | ((uint32_t)lvl & 0xfffu));
+                // (one bit-select: the halfword store drops whatever the level carries above bit 15)
+                sts16(stage_addr(kt >> 8), bitselect(e >> 11, (uint32_t)lvl, 0xf000u));
                 if (on) { bp += byte1(e); kt += (e >> 23) + 1u; }
             } else {
                 // level * quant_matrix[j] as int16 over the consumer's column offset (:420,428); the token goes where the count
@@ -1256,7 +1258,7 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
             // ---- end of block: EOB (advance 128), coefficient 63, or a coefficient index > 63
             const bool nz = lvl != 0;
             const bool fin = (kt & 0xc0u) != 0 && (nz || (kt & 0x80u) != 0);
-            if (on && fin) { ended = true; endnz = nz; }
+            if (on && fin) { ended = true; endlvl = lvl; }
             on = on && !fin;
         }
     }
