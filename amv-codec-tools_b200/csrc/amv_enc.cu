@@ -793,7 +793,7 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                         acc |= t >> fill;
                         const int nf = (int)fill + nm32;             // bits in the word after this symbol, - 32
                         sts32(min(wp, wlast), acc);
-                        if (nf >= 0) { acc = __funnelshift_l(0u, t, 0u - fill); wp += 128u; }      // full, then fill >= 5: t << (32 - fill)
+                        if (nf >= 0) { acc = __funnelshift_r(0u, t, fill); wp += 128u; }          // full, then fill >= 5: t << (32 - fill) as the low word of (t : 0) >> fill
                         fill = (uint32_t)nf & 31u;
                     };
                     // table entries: code left-aligned | length.  The mantissa (low `size` bits of x) goes right under the code:
@@ -884,7 +884,7 @@ k_encode16v2(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu, con
                             red_or_shared(dst, __funnelshift_r(v, prev, sh));      // (prev:v) >> sh
                             prev = v; src += 128; dst += 4;
                         }
-                        const uint32_t tail = sh ? prev << (32 - sh) : 0u;
+                        const uint32_t tail = __funnelshift_r(0u, prev, sh);      // prev << (32 - sh), 0 for sh == 0: the low word of (prev : 0) >> sh
                         if (tail) red_or_shared(dst, tail);
                     };
                     if (len) pack(stageL_s, len, r + luma_off);
