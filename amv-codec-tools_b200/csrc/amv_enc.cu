@@ -5,14 +5,16 @@
 // count of stuffed FF bytes -- never leave the warp: no look-back, no scratch traffic, no CTA
 // barriers, the packet is written once.  Three kernels share that plan:
 //
-//   k_encode16v2  the one that runs (option encode_rounds = 2).  A frame is cut into segments of 16
-//                 macroblocks coded in three homogeneous rounds (32 chroma blocks, then twice 32 luma
-//                 blocks), every lane one block per round:
+//   k_encode16v2  the one that runs (option encode_rounds = 4; 2 = the same with the factorised transform).  A
+//                 frame is cut into segments of 16 macroblocks coded in three homogeneous rounds (32 chroma
+//                 blocks, then twice 32 luma blocks), every lane one block per round:
 //     A  coalesced 64-bit row loads of the bottom-up picture (amv_encode_picture mjpegenc.c:454-472
-//        + edge replication mpegvideo.c:1416-1470), fdct_islow in registers (jfdctint.c:261), the
-//        zigzag mask of the coefficients that survive the quantiser (mpegvideo_enc.c:3647)
+//        + edge replication mpegvideo.c:1416-1470), fdct_islow in registers (jfdctint.c:261) regrouped for
+//        the two integer pipes -- row pass as IDP.2A / IDP.4A dot products on the packed pixel bytes, column
+//        pass with its odd half written out (amv_dct.cuh) --, the bit-reversed zigzag mask of the
+//        coefficients that survive the quantiser (mpegvideo_enc.c:3647)
 //     B  ONE Huffman pass per block into a lane-private bit string (encode_block mjpegenc.c:379-435),
-//        quantising only the survivors, branch-free bit writer
+//        quantising only the survivors, 37 instructions per coded coefficient, branch-free bit writer
 //     C  prefix scan of the string lengths in bitstream order (warp shuffles)
 //     D  warp-cooperative bit packer: every lane shifts its string to its scanned bit offset and ORs
 //        it into the half segment's shared-memory bit buffer
