@@ -1012,24 +1012,28 @@ k_vlc_tokens(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ s
 // 126 bits, and receives up to 128.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTok16Stage = 16;       // staged 16-bit tokens per lane
-
-struct Tok16Smem {
-    uint32_t ring[kTokWarps][kRingWords * 32];             // 2 KB per warp, 2 KB aligned
+// CTA size of the lean token pass, chosen per launch (tok_lean_warps): three CTAs of 8 warps fit an SM (72 KB of shared memory
+// each) or two of 11 warps (82 KB).  When a launch has between 16 and 22 warps per SM -- 100 000 frames on one lane each are
+// 3 125 warps -- the 8-warp CTAs put 24 warps on some SMs and 16 on others, the 11-warp CTAs at most 22 on any: 8.39 -> 8.13 ms.
+// Outside that window the 8-warp CTAs stay (8 192 frames of 1280x720 on 8 lanes each: 9.1 ms against 12.2 ms with 11 warps).
+template <int NW>
+struct Tok16SmemT {
+    uint32_t ring[NW][kRingWords * 32];         // 2 KB per warp, 2 KB aligned
     // 1 KB per warp, 1 KB aligned.  16-bit tokens: halfword c*32 + lane = staged token c (of 16) of the lane;
     // 32-bit tokens: word c*32 + lane = staged token c (of 8)
-    uint32_t tstage[kTokWarps][8 * 32];
+    uint32_t tstage[NW][8 * 32];
     uint32_t tz[2][128];                                   // 32-bit tokens: kb = zigzag position + 1 -> (consumer column byte offset << 16) | quantiser; 512 B aligned
     uint4    bstate[8];                                    // per block-in-MCU: DC table, AC table, DC quantiser | dequant table, component change | next index
     uint32_t lut[kFlatMaxEntries];                         // AC entries rewritten: advance - 1, bit 31 = yields a token
 };
-constexpr size_t kTok16SmemBytes = sizeof(Tok16Smem) + 2048;
+template <int NW> constexpr size_t tok16_smem_bytes() { return sizeof(Tok16SmemT<NW>) + 2048; }
 
 // T16: 16-bit (run << 12 | level) tokens for k_idct16; else 32-bit (column offset << 16 | level x quantiser) tokens, DC included
 // (offset 0, absolute DC), for k_idct.  Measured (ncu, 100 000 frames): 6.36 G warp instructions against 7.71 G -- the table
 // look-up, the product, the predicated store and twice the flushes -- on a pass that is bound by the ALU pipe (77 % / 67 %
 // active): 9.2 ms against 12.4 ms, which the 32-bit tokens' cheaper consumer (8.0 against 9.3 ms) does not win back.
-template <bool T16>
-__global__ void __launch_bounds__(kTokThreads)
+template <bool T16, int NW>
+__global__ void __launch_bounds__(NW * 32)
 k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
                   const uint32_t *__restrict__ scan_len, const uint32_t *__restrict__ pkt_size, int n, int log2p,
                   const LaneStart *__restrict__ starts, int nblk, void *__restrict__ tokens_v,
@@ -1037,7 +1041,7 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
                   int nl, int nc /* blocks per MCU: luma, one chroma component */) {
     AMV_EXTERN_SHARED(uint8_t, tok16_smem_raw, 16);
     const uint32_t raw_s = smem_addr(tok16_smem_raw);
-    Tok16Smem &S = *reinterpret_cast<Tok16Smem *>(tok16_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
+    Tok16SmemT<NW> &S = *reinterpret_cast<Tok16SmemT<NW> *>(tok16_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
     const int nlut = tabs->flat.count, ac0 = tabs->flat.base[2];
     for (int i = threadIdx.x; i < nlut; i += blockDim.x) {
         uint32_t e = tabs->flat.e[i];
@@ -1047,7 +1051,7 @@ k_vlc_tokens_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restric
         if (i >= ac0 && (e & 31u)) e = T16 ? ((e - (1u << 23)) & 0x7fffffffu) | ((e & kFlatTok16) << 24) : e - (1u << 23);
         S.lut[i] = e;
     }
-    if (!T16) {     // dequant table indexed by kb; positions past 64 (only broken streams get there) alias the last one
+    if (!T16 && threadIdx.x < 256) {     // dequant table indexed by kb; positions past 64 (only broken streams get there) alias the last one
         const int c = threadIdx.x >> 7, kb = threadIdx.x & 127, kk = kb == 0 ? 0 : (kb > 64 ? 63 : kb - 1);
         S.tz[c][kb] = tabs->tz[c][kk];
     }
@@ -1548,8 +1552,10 @@ cudaError_t decode_setup_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTok16SmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTok16SmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<8>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<11>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<8>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<11>());
     return e;
 }
 
@@ -1638,22 +1644,35 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                                                                  tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
 }
 
+// warps per CTA of the lean token pass for a launch of `lanes` lanes: 11 when the launch has between 16 and 22 warps per SM
+// (then two 11-warp CTAs per SM hold it in one wave with at most 22 warps on an SM), else 8
+static int tok_lean_warps(int64_t lanes) {
+    const int64_t warps = (lanes + 31) / 32;
+    return warps > (int64_t)kNumSMs * 16 && warps <= (int64_t)kNumSMs * 2 * 11 ? 11 : 8;
+}
+
 void launch_vlc_tokens16(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                          int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
                          int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
-    const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
-    AMV_LAUNCH(k_vlc_tokens_lean<true>, grid, kTokThreads, kTok16SmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-               tokens, blk_off, status, tabs, nl, nc);
+    if (tok_lean_warps(lanes) == 11)
+        AMV_LAUNCH((k_vlc_tokens_lean<true, 11>), (int)((lanes + 351) / 352), 352, tok16_smem_bytes<11>(), s, scratch, slot_off, scan_len, pkt_size, n,
+                   log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
+    else
+        AMV_LAUNCH((k_vlc_tokens_lean<true, 8>), (int)((lanes + 255) / 256), 256, tok16_smem_bytes<8>(), s, scratch, slot_off, scan_len, pkt_size, n,
+                   log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
 }
 
 void launch_vlc_tokens_lean(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                             int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
                             int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
-    const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
-    AMV_LAUNCH(k_vlc_tokens_lean<false>, grid, kTokThreads, kTok16SmemBytes, s, scratch, slot_off, scan_len, pkt_size, n, log2p, starts, nblk,
-               tokens, blk_off, status, tabs, nl, nc);
+    if (tok_lean_warps(lanes) == 11)
+        AMV_LAUNCH((k_vlc_tokens_lean<false, 11>), (int)((lanes + 351) / 352), 352, tok16_smem_bytes<11>(), s, scratch, slot_off, scan_len, pkt_size, n,
+                   log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
+    else
+        AMV_LAUNCH((k_vlc_tokens_lean<false, 8>), (int)((lanes + 255) / 256), 256, tok16_smem_bytes<8>(), s, scratch, slot_off, scan_len, pkt_size, n,
+                   log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
 }
 
 void launch_idct16(const uint16_t *tokens, const uint32_t *blk_off, const uint64_t *slot_off, const uint32_t *scan_len, int n,
