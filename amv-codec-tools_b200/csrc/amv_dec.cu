@@ -484,12 +484,13 @@ k_vlc_sync(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slo
 // the DC sums, switch tables and read the next block's DC together).  For the fixed AMV / SP5X tables; the flat kernel
 // above stays for custom tables and the amvlib flavour.
 // ------------------------------------------------------------------------------------------------
-struct SyncLeanSmem {
-    uint32_t ring[kTokWarps][kRingWords * 32];     // 2 KB per warp, 2 KB aligned
+template <int NW>
+struct SyncLeanSmemT {
+    uint32_t ring[NW][kRingWords * 32];            // 2 KB per warp, 2 KB aligned
     uint4    bstate[8];                            // per block-in-MCU: DC table, AC table, component change on entering it, next index
     uint32_t lut[kFlatMaxEntries];                 // AC entries with the token flag cleared: the top 9 bits are the advance
 };
-constexpr size_t kSyncLeanSmemBytes = sizeof(SyncLeanSmem) + 2048;
+template <int NW> constexpr size_t sync_lean_smem_bytes() { return sizeof(SyncLeanSmemT<NW>) + 2048; }
 struct SyncCheckpoint {     // while a walk runs: what it had at the boundary; afterwards: what it added from there to its exit
     uint32_t bitpos, phase, nblocks;
     int dc[3];
@@ -497,14 +498,15 @@ struct SyncCheckpoint {     // while a walk runs: what it had at the boundary; a
     bool valid, fresh;
 };
 
-__global__ void __launch_bounds__(kTokThreads)
+template <int NW>           // warps per CTA, chosen per launch (pick_vlc_warps)
+__global__ void __launch_bounds__(NW * 32)
 k_vlc_sync_lean(const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ slot_off,
                 const uint32_t *__restrict__ scan_len, int n, int log2p, LaneStart *__restrict__ starts,
                 uint32_t *__restrict__ rounds_out /* optional: max rounds per warp, for profiling */,
                 const DecTableSet *__restrict__ tabs, int nl, int nc /* blocks per MCU: luma, one chroma component */) {
     AMV_EXTERN_SHARED(uint8_t, synclean_smem_raw, 16);
     const uint32_t raw_s = smem_addr(synclean_smem_raw);
-    SyncLeanSmem &S = *reinterpret_cast<SyncLeanSmem *>(synclean_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
+    SyncLeanSmemT<NW> &S = *reinterpret_cast<SyncLeanSmemT<NW> *>(synclean_smem_raw + (((raw_s + 2047u) & ~2047u) - raw_s));
     const int nlut = tabs->flat.count, ac0 = tabs->flat.base[2];
     for (int i = threadIdx.x; i < nlut; i += blockDim.x) {
         const uint32_t e = tabs->flat.e[i];
@@ -1547,11 +1549,14 @@ bool build_dec_table_set(void *host_buf, const uint8_t counts[4][16], const uint
 // opt-in to more than 48 KB of dynamic shared memory: per device, called from amv_create
 cudaError_t decode_setup_device() {
     cudaError_t e = cudaFuncSetAttribute(k_vlc_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_sync_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncLeanSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_sync_lean<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_lean_smem_bytes<8>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_sync_lean<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_lean_smem_bytes<7>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorJpegDri>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorAmvlib>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens<kFlavorFfmpeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTokSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<7>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<7>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<8>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<11>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vlc_tokens_lean<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok16_smem_bytes<8>());
@@ -1611,13 +1616,35 @@ void launch_mjpeg_check(const uint8_t *pkts, uint64_t pkts_bytes, const uint64_t
                                               status);
 }
 
+// Warps per CTA of the lean VLC kernels for a launch of `lanes` lanes.  Their shared memory (45 KB of tables + 2..3 KB per
+// warp) lets three CTAs of 7 or 8 warps or two of 11 warps live on an SM; the CTA scheduler deals a one-wave grid evenly, so the
+// busiest SM carries ceil(CTAs / 148) CTAs.  Among the sizes that fit the launch into one wave the one with the fewest warps on
+// the busiest SM wins (3 125 warps: 11 -> 22 warps instead of 24 with 8; 2 048 warps: 7 -> 14 instead of 16); launches of
+// several waves keep 8.
+static int pick_vlc_warps(int64_t lanes, bool allow11) {
+    const int64_t warps = (lanes + 31) / 32;
+    const int cand[3] = { 8, 7, 11 }, resident[3] = { 3, 3, 2 };
+    int best = 8;
+    int64_t best_max = INT64_MAX;
+    for (int i = 0; i < (allow11 ? 3 : 2); i++) {
+        const int64_t ctas = (warps + cand[i] - 1) / cand[i];
+        if (ctas > (int64_t)kNumSMs * resident[i]) continue;           // more than one wave
+        const int64_t busiest = ((ctas + kNumSMs - 1) / kNumSMs) * cand[i];
+        if (busiest < best_max) { best_max = busiest; best = cand[i]; }
+    }
+    return best;
+}
+
 void launch_vlc_sync(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, int n, int log2p,
                      LaneStart *starts, uint32_t *rounds_out, bool amvlib, const DecTableSet *tabs, const uint8_t *qtab,
                      int nl, int nc, bool lean, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
     const int grid = (int)((lanes + kTokThreads - 1) / kTokThreads);
     if (lean && !amvlib && !qtab) {         // fixed AMV / SP5X tables
-        AMV_LAUNCH(k_vlc_sync_lean, grid, kTokThreads, kSyncLeanSmemBytes, s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out, tabs, nl, nc);
+        if (pick_vlc_warps(lanes, false) == 7)
+            AMV_LAUNCH(k_vlc_sync_lean<7>, (int)((lanes + 223) / 224), 224, sync_lean_smem_bytes<7>(), s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out, tabs, nl, nc);
+        else
+            AMV_LAUNCH(k_vlc_sync_lean<8>, grid, kTokThreads, sync_lean_smem_bytes<8>(), s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out, tabs, nl, nc);
         return;
     }
     AMV_LAUNCH(k_vlc_sync, grid, kTokThreads, kSyncSmemBytes, s, scratch, slot_off, scan_len, n, log2p, starts, rounds_out,
@@ -1644,19 +1671,16 @@ void launch_vlc_tokens(const uint8_t *scratch, const uint64_t *slot_off, const u
                                                                  tokens, blk_off, status, tabs, nullptr, nl, nc, 0);
 }
 
-// warps per CTA of the lean token pass for a launch of `lanes` lanes: 11 when the launch has between 16 and 22 warps per SM
-// (then two 11-warp CTAs per SM hold it in one wave with at most 22 warps on an SM), else 8
-static int tok_lean_warps(int64_t lanes) {
-    const int64_t warps = (lanes + 31) / 32;
-    return warps > (int64_t)kNumSMs * 16 && warps <= (int64_t)kNumSMs * 2 * 11 ? 11 : 8;
-}
-
 void launch_vlc_tokens16(const uint8_t *scratch, const uint64_t *slot_off, const uint32_t *scan_len, const uint32_t *pkt_size,
                          int n, int log2p, const LaneStart *starts, int nblk, uint16_t *tokens, uint32_t *blk_off,
                          int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
-    if (tok_lean_warps(lanes) == 11)
+    const int nw = pick_vlc_warps(lanes, true);
+    if (nw == 11)
         AMV_LAUNCH((k_vlc_tokens_lean<true, 11>), (int)((lanes + 351) / 352), 352, tok16_smem_bytes<11>(), s, scratch, slot_off, scan_len, pkt_size, n,
+                   log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
+    else if (nw == 7)
+        AMV_LAUNCH((k_vlc_tokens_lean<true, 7>), (int)((lanes + 223) / 224), 224, tok16_smem_bytes<7>(), s, scratch, slot_off, scan_len, pkt_size, n,
                    log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
     else
         AMV_LAUNCH((k_vlc_tokens_lean<true, 8>), (int)((lanes + 255) / 256), 256, tok16_smem_bytes<8>(), s, scratch, slot_off, scan_len, pkt_size, n,
@@ -1667,8 +1691,12 @@ void launch_vlc_tokens_lean(const uint8_t *scratch, const uint64_t *slot_off, co
                             int n, int log2p, const LaneStart *starts, int nblk, uint32_t *tokens, uint32_t *blk_off,
                             int32_t *status, const DecTableSet *tabs, int nl, int nc, cudaStream_t s) {
     const int64_t lanes = (int64_t)n << log2p;
-    if (tok_lean_warps(lanes) == 11)
+    const int nw = pick_vlc_warps(lanes, true);
+    if (nw == 11)
         AMV_LAUNCH((k_vlc_tokens_lean<false, 11>), (int)((lanes + 351) / 352), 352, tok16_smem_bytes<11>(), s, scratch, slot_off, scan_len, pkt_size, n,
+                   log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
+    else if (nw == 7)
+        AMV_LAUNCH((k_vlc_tokens_lean<false, 7>), (int)((lanes + 223) / 224), 224, tok16_smem_bytes<7>(), s, scratch, slot_off, scan_len, pkt_size, n,
                    log2p, starts, nblk, tokens, blk_off, status, tabs, nl, nc);
     else
         AMV_LAUNCH((k_vlc_tokens_lean<false, 8>), (int)((lanes + 255) / 256), 256, tok16_smem_bytes<8>(), s, scratch, slot_off, scan_len, pkt_size, n,
