@@ -173,3 +173,38 @@ def test_config4_1M_frames_208x176_decode_encode(ctx, oracle):
         assert torch.equal(out[: int(esz.sum())], torch.from_numpy(want).to(dev)), "slice %d: re-encoded packets differ from the oracle's" % s
         del pk, Y, U, V, out
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n,lanes_log2,what", [
+    (37888, 0, "1 184 warps: CTAs of 8 warps (one per SM)"),
+    (90000, 0, "2 813 warps: CTAs of 11 warps (two per SM, 22 warps on the busiest)"),
+    (8192, 3, "2 048 warps: CTAs of 7 warps, with the synchronisation pass"),
+    (200000, 0, "6 250 warps: several waves, CTAs of 8 warps"),
+])
+def test_decode_every_cta_size_of_the_lean_passes(ctx, oracle, n, lanes_log2, what):
+    """The lean token pass and the lean synchronisation pass run in CTAs of 7, 8 or 11 warps, chosen per launch from the warp
+    count (pick_vlc_warps, csrc/amv_dec.cu).  Batches of small frames sized to hit each choice: every decoded frame must
+    equal the oracle's decode of the base packet it copies."""
+    import torch
+    w, h, nbase = 64, 48, 96
+    dev = torch.device("cuda", 0)
+    by, bu, bv = _base_frames(w, h, nbase, 401)
+    bpk, boff, bsz = oracle.encode_frames(by, bu, bv, w, h, 2)
+    wy, wu, wv, wst = oracle.decode_frames(bpk, boff, bsz, w, h)
+    assert (wst == 0).all()
+    idx = np.random.default_rng(402 + n).integers(0, nbase, n)
+    tidx = torch.from_numpy(idx).to(dev)
+    want, offs, sizes = _expect_packets(bpk, boff, bsz, idx)
+    pk = torch.from_numpy(want).to(dev)
+    off = torch.from_numpy(offs).to(dev)
+    size = torch.from_numpy(sizes.astype(np.int32)).to(dev)
+    ctx.set_option("decode_log2_lanes", lanes_log2)
+    try:
+        DY, DU, DV, dst = _decode_device(ctx, torch, pk, off, size, n, w, h)
+    finally:
+        ctx.set_option("decode_log2_lanes", -1)
+    assert int(dst.abs().sum().item()) == 0, what
+    for got_t, want_np in ((DY, wy), (DU, wu), (DV, wv)):
+        assert torch.equal(got_t, torch.from_numpy(want_np).to(dev)[tidx]), what
+    del DY, DU, DV, pk
+    torch.cuda.empty_cache()
