@@ -20,6 +20,8 @@ if [ -n "$ASAN" ]; then     # ASAN=1: the same library under AddressSanitizer ("
     LDFLAGS="-fsanitize=address"
 fi
 mkdir -p "$OUT"
+# one build at a time (pytest-xdist workers start this script together)
+if command -v flock >/dev/null 2>&1; then exec 9>"$OUT/.lock"; flock 9; fi
 pids=""
 for f in amv_api amv_dec amv_enc amv_adpcm amv_amvlib amv_container amv_range amv_resample; do
     $CXX $FLAGS -x c++ -include cuda_runtime.h -c "$CSRC/$f.cu" -o "$OUT/$f.o" &
