@@ -137,6 +137,7 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
             return make_uint4(0, 0, 0, 0);
         };
         uint4 qn = load_unit(0);
+        uint32_t tail_w = 0;      // last word of the tile before (lane 31's)
 
         for (uint32_t t0 = 0; !done; t0 += kUnstuffTile) {
             // this thread's 16 bytes: virtual indices i0 .. i0+15, i = (t0 + tid*16 + b) - mis
@@ -144,13 +145,22 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
             uint32_t wv[4] = { qn.x, qn.y, qn.z, qn.w };
             qn = load_unit(t0 + kUnstuffTile);
             uint32_t keep = 0, term = 0;
+            // the byte in front of this thread's unit: the left neighbour's last one, for lane 0 the last lane's of the tile
+            // before (a unit inside the payload always has a loaded unit on its left).  One-warp CTAs only.
+            uint32_t left = 0;
+            if (kUnstuffThreads == 32) {
+                left = __shfl_up_sync(0xffffffffu, wv[3], 1);
+                if (lane == 0) left = tail_w;
+                tail_w = __shfl_sync(0xffffffffu, wv[3], 31);
+            }
             if (sp5x && i0 >= 0 && i0 + 16 <= (int64_t)npay) {
                 keep = 0xffffu;                   // literal bytes: nothing to drop, nothing terminates
             } else if (!sp5x && i0 >= 1 && i0 + 16 <= (int64_t)npay) {
                 // ---- unit inside the payload: SIMD byte flags.  after_ff = the byte before is FF;
                 // drop = after_ff and (00 or FF); terminator = after_ff and not (00, FF, RSTn)
                 const uint32_t f0 = zero_bytes(~wv[0]), f1 = zero_bytes(~wv[1]), f2 = zero_bytes(~wv[2]), f3 = zero_bytes(~wv[3]);
-                const uint32_t pf = pay[i0 - 1] == 0xff ? 0x80000000u : 0u;
+                const uint32_t pf = kUnstuffThreads == 32 ? (left >= 0xff000000u ? 0x80000000u : 0u)
+                                                          : (pay[i0 - 1] == 0xff ? 0x80000000u : 0u);
                 const uint32_t a0 = __funnelshift_l(pf, f0, 8), a1 = __funnelshift_l(f0, f1, 8),
                                a2 = __funnelshift_l(f1, f2, 8), a3 = __funnelshift_l(f2, f3, 8);
                 uint32_t dropb = 0;
@@ -158,10 +168,14 @@ k_unstuff(const uint8_t *__restrict__ pkts, uint64_t pkts_bytes, const uint64_t 
                     const uint32_t n0 = zero_bytes(wv[0]) | f0, n1 = zero_bytes(wv[1]) | f1, n2 = zero_bytes(wv[2]) | f2,
                                    n3 = zero_bytes(wv[3]) | f3;
                     dropb = flag_bits(a0 & n0) | (flag_bits(a1 & n1) << 4) | (flag_bits(a2 & n2) << 8) | (flag_bits(a3 & n3) << 12);
-                    const uint32_t r0 = zero_bytes((wv[0] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u), r1 = zero_bytes((wv[1] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u),
-                                   r2 = zero_bytes((wv[2] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u), r3 = zero_bytes((wv[3] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u);
-                    term = flag_bits(a0 & ~(n0 | r0)) | (flag_bits(a1 & ~(n1 | r1)) << 4) | (flag_bits(a2 & ~(n2 | r2)) << 8) |
-                           (flag_bits(a3 & ~(n3 | r3)) << 12);
+                    // a byte behind an FF that is neither 00 nor FF: RSTn or a marker -- none in a sound AMV scan up to its
+                    // appended EOI (which the byte-serial path below sees), so the RSTn flags are built only when there is one
+                    const uint32_t m0 = a0 & ~n0, m1 = a1 & ~n1, m2 = a2 & ~n2, m3 = a3 & ~n3;
+                    if (m0 | m1 | m2 | m3) {
+                        const uint32_t r0 = zero_bytes((wv[0] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u), r1 = zero_bytes((wv[1] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u),
+                                       r2 = zero_bytes((wv[2] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u), r3 = zero_bytes((wv[3] & 0xf8f8f8f8u) ^ 0xd0d0d0d0u);
+                        term = flag_bits(m0 & ~r0) | (flag_bits(m1 & ~r1) << 4) | (flag_bits(m2 & ~r2) << 8) | (flag_bits(m3 & ~r3) << 12);
+                    }
                 }
                 keep = ~dropb & 0xffffu;
             } else if (i0 + 16 > 0 && i0 < (int64_t)V) {
