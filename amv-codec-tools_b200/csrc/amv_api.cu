@@ -220,7 +220,9 @@ int decode_front(amv_ctx *ctx, const uint8_t *pkts, uint64_t pkts_bytes, const u
     ENSURE(WS_SCAN_LEN, sizeof(uint32_t) * n, scan_len);
     ENSURE(WS_SCRATCH, scratch_bytes, scratch);
     ENSURE(WS_ROUNDS, sizeof(uint32_t), rounds);
-    ENSURE(WS_TOKENS, scratch_bytes * 16 + 1024, tokens);         // at most one 32-bit token per 2 scan bits
+    // at most one token per 2 scan bits: 16 bytes of 32-bit tokens per scan byte, 8 of 16-bit ones (the pass chosen below)
+    const bool tok16_ws = !amvlib && !mode.tables && !mode.hdr && ctx->opt_token_pass == 2;
+    ENSURE(WS_TOKENS, scratch_bytes * (tok16_ws ? 8 : 16) + 1024, tokens);
     ENSURE(WS_BLKOFF, sizeof(uint32_t) * (size_t)n * g.nblk, blk_off);
     if (!st) ENSURE(WS_STATUS, sizeof(int32_t) * n, st);
     if (log2p) ENSURE(WS_STARTS, sizeof(LaneStart) * ((size_t)n << log2p), starts);
