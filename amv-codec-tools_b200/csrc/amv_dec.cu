@@ -1390,7 +1390,7 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 // truncated to int16 (decode_block, mjpegdec.c:420,428) -- eight tokens per 128-bit load.
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>
-__global__ void __launch_bounds__(kIdctThreads, 7)     // 7 CTAs per SM (72 registers, 28 bytes of spills): 8.49 -> 8.38 ms; 8 CTAs (64 registers) the same, 6 (80, no spills) 8.49
+__global__ void __launch_bounds__(kIdctThreads, 8)     // 8 CTAs per SM (64 registers, 92 bytes of spills) with the multiply-add chain transform: 7.94 ms; 6 / 7 CTAs 8.11, 9 (56 registers) 8.26, 10 (48) 9.47
 k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off, const uint64_t *__restrict__ slot_off,
          const uint32_t *__restrict__ scan_len, int n, Geom g, const DecTableSet *__restrict__ tabs, uint8_t *__restrict__ py,
          uint8_t *__restrict__ pu, uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
