@@ -1452,10 +1452,14 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
     for (; gi <= last; gi += 8, rel += 8) {
         const uint4 nq = __ldg(reinterpret_cast<const uint4 *>(tf + gi + 8));
         const uint32_t tw[4] = { q.x, q.y, q.z, q.w };
+        // which of the group's eight tokens are the block's: 0 <= rel + j < cnt, as one bit mask per group (a bit test per
+        // token instead of an add and a compare)
+        const int srel = (int)rel;
+        const uint32_t vm = (0xffu >> (8 - min((int)cnt - srel, 8))) & (0xffu << max(-srel, 0));
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const uint32_t w = tw[j >> 1];
-            const bool valid = rel + (uint32_t)j < cnt;                    // unsigned: also false in front of the block
+            const bool valid = (vm >> j) & 1u;
             const uint32_t run = (j & 1) ? w >> 28 : (w >> 12) & 15u;
             const int lvl = (j & 1) ? (int)(w << 4) >> 20 : (int)(w << 20) >> 20;
             k = valid ? k + run + 1u : k;
