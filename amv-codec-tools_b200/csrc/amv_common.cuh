@@ -99,6 +99,17 @@ AMV_HD uint32_t bitselect(uint32_t a, uint32_t b, uint32_t mask) {
 #endif
 }
 
+// the low 12 bits of v, sign-extended: one SGXT (the compiler's shift pair is two instructions)
+AMV_HD int sext12(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("bfe.s32 %0, %1, 0, 12;" : "=r"(d) : "r"(v));
+    return d;
+#else
+    return (int)(v << 20) >> 20;
+#endif
+}
+
 // bits [15:8] of v: one PRMT
 AMV_HD uint32_t byte1(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -163,6 +174,7 @@ inline uint32_t lds32(uint32_t saddr) { return *smem_ptr<uint32_t>(saddr); }
 inline int lds_s16(uint32_t saddr) { return *smem_ptr<int16_t>(saddr); }
 inline uint32_t lds_u16(uint32_t saddr) { return *smem_ptr<uint16_t>(saddr); }
 inline uint4 lds128(uint32_t saddr) { return *smem_ptr<uint4>(saddr); }
+template <int OFF> inline uint32_t lds32_at(uint32_t saddr) { return *smem_ptr<uint32_t>(saddr + OFF); }
 inline uint2 lds64(uint32_t saddr) { return *smem_ptr<uint2>(saddr); }
 inline void sts32(uint32_t saddr, uint32_t v) { *smem_ptr<uint32_t>(saddr) = v; }
 inline void sts16(uint32_t saddr, uint32_t v) { *smem_ptr<uint16_t>(saddr) = (uint16_t)v; }
@@ -208,6 +220,13 @@ __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
 }
 __device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+// ld.shared.u32 [saddr + OFF]: the constant rides in the instruction's immediate field
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32_at(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF));
+    return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     uint4 v;

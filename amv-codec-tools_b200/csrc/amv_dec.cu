@@ -14,6 +14,7 @@
 //   k_idct      : one thread per 8x8 block in plane raster order (coalesced 256-byte row stores):
 //                 tokens -> dequantised coefficients in a conflict-free shared-memory column ->
 //                 simple_idct in registers -> bottom-up store (mjpegdec.c:672-677,710-716).
+#include <type_traits>
 #include <stdlib.h>
 #include "amv_common.cuh"
 #include "amv_tables.cuh"
@@ -1396,9 +1397,19 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
          uint8_t *__restrict__ pu, uint8_t *__restrict__ pv, int ls_y, int ls_c, uint64_t fs_y, uint64_t fs_c,
          uint32_t mg_nblk, uint32_t mg_rowl, uint32_t mg_rowc /* div_magic of nblk and of the luma / chroma blocks per row */) {
     __shared__ uint32_t tile[kIdctThreads / 32][32 * 32];
-    __shared__ __align__(256) uint32_t tzs[2][64];      // zigzag position -> (column byte offset << 16) | quantiser
+    // zigzag position -> (column byte offset << 16) | quantiser.  The scatter loop looks a symbol up at
+    // (sum of the block's runs so far, mod 64) + (the symbol's ordinal in the block + 1): the ordinal is a constant of the
+    // unrolled slot plus a per-group base, the sum wraps by itself in the top six bits of a register.  In a sound stream that
+    // index is the position (<= 63); a block has at most 144 symbols (the producer ends it once the position passes 63 / 127),
+    // so 256 entries -- 64..255 repeat 0..63 -- keep every look-up of a flagged stream inside the table as well.
+    // (8 words in front of each table: the slots of a block's first group that lie in front of the block look up ordinals -7..0)
+    __shared__ uint32_t tzs[2][8 + 256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x < 128) tzs[threadIdx.x >> 6][threadIdx.x & 63] = tabs->tz[threadIdx.x >> 6][threadIdx.x & 63];
+    if (threadIdx.x < 128) {
+        const uint32_t z = tabs->tz[threadIdx.x >> 6][threadIdx.x & 63];
+        uint32_t *t = &tzs[threadIdx.x >> 6][8 + (threadIdx.x & 63)];
+        t[0] = z; t[64] = z; t[128] = z; t[192] = z;
+    }
     __syncthreads();
     // block-stride loop (the launcher covers every block with one pass; see launch_idct16): a thread only ever touches its own
     // column of the tile, so iterations would need no synchronisation
@@ -1436,7 +1447,7 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
     const uint32_t first = bo & ((1u << kTokCountShift) - 1u), last = first + (bo >> kTokCountShift);   // DC token .. last symbol token
     uint32_t *slot = &tile[wid][lane];
     const uint32_t slot_s = smem_addr(slot);
-    const uint32_t tz_s = smem_addr(&tzs[comp ? 1 : 0][0]);
+    const uint32_t tz_s = smem_addr(&tzs[comp ? 1 : 0][8]);
 #pragma unroll
     for (int k = 0; k < 32; k++) slot[k * 32] = 0;
     // The DC token is absolute and already dequantised.  The symbol tokens behind it are fetched as aligned groups of eight
@@ -1447,27 +1458,40 @@ k_idct16(const uint16_t *__restrict__ tokens, const uint32_t *__restrict__ blk_o
     const uint32_t cnt = bo >> kTokCountShift;                             // symbol tokens: indices first + 1 .. first + cnt
     uint32_t gi = (first + 1u) & ~7u;
     uint4 q = __ldg(reinterpret_cast<const uint4 *>(tf + gi));
-    uint32_t k = 0;                                                        // zigzag position of the last symbol
+    {   // the tokens of the first group that lie in front of the block are cleared (run 0): the sum below takes every token
+        const int lead = 16 * (int)(first + 1u - gi);                      // bits in front of the block's first symbol token
+        q.x &= __funnelshift_lc(0u, ~0u, max(lead, 0));
+        q.y &= __funnelshift_lc(0u, ~0u, max(lead - 32, 0));
+        q.z &= __funnelshift_lc(0u, ~0u, max(lead - 64, 0));
+        q.w &= __funnelshift_lc(0u, ~0u, max(lead - 96, 0));
+    }
+    uint32_t k26 = 0;                                                      // (sum of the runs of the symbols so far) << 26
     uint32_t rel = gi - first - 1u;                                        // index of the group's first token among the block's symbols (may be "negative")
-    for (; gi <= last; gi += 8, rel += 8) {
+    uint32_t tzg = tz_s + 4u * rel;                                        // table address of position = ordinal of the group's first token
+    for (; gi <= last; gi += 8, rel += 8, tzg += 32u) {
         const uint4 nq = __ldg(reinterpret_cast<const uint4 *>(tf + gi + 8));
         const uint32_t tw[4] = { q.x, q.y, q.z, q.w };
         // which of the group's eight tokens are the block's: 0 <= rel + j < cnt, as one bit mask per group (a bit test per
         // token instead of an add and a compare)
         const int srel = (int)rel;
         const uint32_t vm = (0xffu >> (8 - min((int)cnt - srel, 8))) & (0xffu << max(-srel, 0));
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
+        // one slot of the group; its index is a compile-time constant (it rides in the table load's immediate field)
+        auto slot = [&](auto J) {
+            constexpr int j = decltype(J)::value;
             const uint32_t w = tw[j >> 1];
             const bool valid = (vm >> j) & 1u;
-            const uint32_t run = (j & 1) ? w >> 28 : (w >> 12) & 15u;
-            const int lvl = (j & 1) ? (int)(w << 4) >> 20 : (int)(w << 20) >> 20;
-            k = valid ? k + run + 1u : k;
-            const uint32_t z = lds32(tz_s | ((k << 2) & 0xfcu));           // past 63 only in streams the producer has flagged
+            const int lvl = (j & 1) ? (int)(w << 4) >> 20 : sext12(w);
+            // the run nibble, moved to bit 26, joins the sum: one mask, one multiply-add that shifts and adds (tokens behind
+            // the block's last only move a sum nobody reads any more)
+            k26 = (j & 1) ? mad_hi_u32(w & 0xf0000000u, 1u << 30, k26) : (uint32_t)mad_lo((int)(w & 0xf000u), 1 << 14, (int)k26);
+            const uint32_t z = lds32_at<4 * (j + 1)>(tzg + (k26 >> 24));
             // z = column offset << 16 | quantiser: the halfword stored is the low half of level x z, which is level x quantiser
             // truncated to int16 whatever the offset adds above bit 15 -- no mask needed
             if (valid) sts16(slot_s + (z >> 16), (uint32_t)lvl * z);
-        }
+        };
+        slot(std::integral_constant<int, 0>{}); slot(std::integral_constant<int, 1>{}); slot(std::integral_constant<int, 2>{});
+        slot(std::integral_constant<int, 3>{}); slot(std::integral_constant<int, 4>{}); slot(std::integral_constant<int, 5>{});
+        slot(std::integral_constant<int, 6>{}); slot(std::integral_constant<int, 7>{});
         q = nq;
     }
 
