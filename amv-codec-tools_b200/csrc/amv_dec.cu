@@ -1387,8 +1387,8 @@ k_idct(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ blk_off
 
 // ------------------------------------------------------------------------------------------------
 // k_idct16: k_idct for the 16-bit tokens of k_vlc_tokens16.  Same thread-per-block layout in plane raster order and
-// the same transform; the scatter loop walks the block's symbols -- position += run + 1, value = level x quantiser
-// truncated to int16 (decode_block, mjpegdec.c:420,428) -- eight tokens per 128-bit load.
+// the same transform; the scatter loop walks the block's symbols -- position = runs so far + symbols so far, value =
+// level x quantiser truncated to int16 (decode_block, mjpegdec.c:420,428) -- eight tokens per 128-bit load.
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>
 __global__ void __launch_bounds__(kIdctThreads, 8)     // 8 CTAs per SM (64 registers, 92 bytes of spills) with the multiply-add chain transform: 7.94 ms; 6 / 7 CTAs 8.11, 9 (56 registers) 8.26, 10 (48) 9.47
