@@ -99,6 +99,28 @@ AMV_HD uint32_t bitselect(uint32_t a, uint32_t b, uint32_t mask) {
 #endif
 }
 
+// (a * b >> 32) + c, unsigned: with b = 2^(32 - s) this is (a >> s) + c in one multiply-add
+AMV_HD uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32) + c;
+#endif
+}
+// a * b + c mod 2^32.  On the device an opaque multiply-add, so that a chain written as a chain stays one (the compiler
+// would otherwise be free to re-associate "2a - (a + b)" back into a second chain of products).
+AMV_HD int mad_lo(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (int)((uint32_t)a * (uint32_t)b + (uint32_t)c);
+#endif
+}
+
 // the low 12 bits of v, sign-extended: one SGXT (the compiler's shift pair is two instructions)
 AMV_HD int sext12(uint32_t v) {
 #if defined(__CUDA_ARCH__)
