@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
 # k_idct16 with the multiply-add chain transform at 6 / 7 / 8 CTAs per SM (80 / 72 / 64 registers, 0 / 28 / 92 bytes of spills)
+# (variants/libamvcuda_*.so: builds of the named source states made for this A/B with "make" and copied aside; not kept in the tree)
 cp amv-codec-tools_b200/lib/libamvcuda.so /tmp/lib7.so
 for n in 6 8 7; do
   if [ $n = 7 ]; then cp /tmp/lib7.so amv-codec-tools_b200/lib/libamvcuda.so; else cp variants/libamvcuda_idct$n.so amv-codec-tools_b200/lib/libamvcuda.so; fi

@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
 # k_idct16 at 9 / 10 CTAs per SM (56 / 48 registers), then the committed state (8 CTAs per SM): whole GPU suite, smoke, default bench, reference arm, configs 3 / 4 / 5
+# (variants/libamvcuda_*.so: builds of the named source states made for this A/B with "make" and copied aside; not kept in the tree)
 cp amv-codec-tools_b200/lib/libamvcuda.so /tmp/lib8.so
 for n in 9 10; do
   cp variants/libamvcuda_idct$n.so amv-codec-tools_b200/lib/libamvcuda.so

@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
 # k_idct16 scatter: run sum in the top six bits of a register + ordinal in the table load's immediate, leading tokens cleared once per block (B) against HEAD + sext12 (A)
+# (variants/libamvcuda_*.so: builds of the named source states made for this A/B with "make" and copied aside; not kept in the tree)
 cp amv-codec-tools_b200/lib/libamvcuda.so /tmp/libB.so
 for v in A B; do
   cp variants/libamvcuda_$v.so amv-codec-tools_b200/lib/libamvcuda.so
