@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
 # k_idct16 scatter: validity of a group's eight tokens as one bit mask (B) against an add and a compare per token (A)
+# (variants/libamvcuda_*.so: builds of the named source states made for this A/B with "make" and copied aside; not kept in the tree)
 cp amv-codec-tools_b200/lib/libamvcuda.so /tmp/libB.so
 for v in A B A B; do
   cp variants/libamvcuda_$v.so amv-codec-tools_b200/lib/libamvcuda.so
